@@ -1,0 +1,315 @@
+/*
+ * pxr.h — C-ABI of the B200-native featuremetric refinement engine (libpxr.so).
+ *
+ * Drop-in boundary for the featuremetric keypoint-adjustment (KA) and
+ * bundle-adjustment (BA) hot path of cvg/pixel-perfect-sfm.  The reference has
+ * no C-ABI: its boundary is the pybind11 module `pixsfm._pixsfm`
+ * (reference pixsfm/_pixsfm/bindings.cc:34-63).  Every entry point below names
+ * the reference interface it replaces; the pybind/ctypes stub a maintainer
+ * would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, `extern "C"`, no C++/torch types; all sizes explicit.
+ *  - every function returns a pxr_status; pxr_last_error() gives the message
+ *    for the calling thread.  No exception crosses the boundary, nothing
+ *    aborts the process (the reference's glog CHECKs abort:
+ *    bundle_optimizer.h:222).
+ *  - the caller owns all host memory; the library owns all device memory.
+ *  - there is NO CPU fallback: every compute entry point fails with
+ *    PXR_ERR_NO_DEVICE when no CUDA device is usable.
+ *  - one handle is used by one host thread at a time (thread-compatible).
+ *
+ * Problem IR (SoA, independent of COLMAP objects).  The host adapter resolves
+ * the reference's BundleAdjustmentSetup + BundleOptimizerOptions into plain
+ * constancy masks exactly as BundleOptimizer::Parameterize{Points,Images,
+ * Cameras} does (reference bundle_adjustment/src/bundle_optimizer.h:335-442).
+ */
+#ifndef PXR_H_
+#define PXR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXR_VERSION_MAJOR 0
+#define PXR_VERSION_MINOR 1
+#define PXR_MAX_CAM_PARAMS 12
+
+typedef enum {
+  PXR_OK = 0,
+  PXR_ERR_INVALID_ARGUMENT = 1, /* -> Python ValueError / std::invalid_argument */
+  PXR_ERR_UNSUPPORTED = 2,      /* unsupported (channels, nodes, model) combination */
+  PXR_ERR_NO_DEVICE = 3,        /* no CUDA device: the product never falls back to CPU */
+  PXR_ERR_CUDA = 4,             /* CUDA runtime error (message has the cudaError string) */
+  PXR_ERR_NCCL = 5,
+  PXR_ERR_NUMERIC = 6,          /* solver failure (non-PD reduced system that damping could not fix) */
+  PXR_ERR_INTERRUPTED = 7,      /* interrupt callback asked to stop (PyInterrupt, util/src/py_interrupt.h) */
+  PXR_ERR_INTERNAL = 8
+} pxr_status;
+
+/* COLMAP 3.8 camera model ids (colmap/base/camera_models.h; used through
+ * CAMERA_MODEL_SWITCH_CASES in reference residuals/src/feature_reference.h:224-252). */
+typedef enum {
+  PXR_CAM_SIMPLE_PINHOLE = 0, /* f, cx, cy */
+  PXR_CAM_PINHOLE = 1,        /* fx, fy, cx, cy */
+  PXR_CAM_SIMPLE_RADIAL = 2,  /* f, cx, cy, k */
+  PXR_CAM_RADIAL = 3,         /* f, cx, cy, k1, k2 */
+  PXR_CAM_OPENCV = 4,         /* fx, fy, cx, cy, k1, k2, p1, p2 */
+  PXR_CAM_OPENCV_FISHEYE = 5, /* fx, fy, cx, cy, k1, k2, k3, k4 */
+  PXR_CAM_FULL_OPENCV = 6     /* fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, k5, k6 */
+} pxr_camera_model;
+
+typedef enum { PXR_F16 = 0, PXR_F32 = 1, PXR_F64 = 2 } pxr_dtype;
+
+/* ceres loss functions reachable from the reference's {"name","params"} dicts
+ * (bundle_adjustment/main.py:37-40). */
+typedef enum {
+  PXR_LOSS_TRIVIAL = 0,
+  PXR_LOSS_CAUCHY = 1, /* default, scale 0.25 (bundle_adjustment_options.h:49) */
+  PXR_LOSS_HUBER = 2,
+  PXR_LOSS_SOFT_L1 = 3,
+  PXR_LOSS_ARCTAN = 4
+} pxr_loss_type;
+
+typedef enum {
+  PXR_SOLVER_AUTO = 0,        /* by #images as bundle_optimizer.h:181-191 */
+  PXR_SOLVER_DENSE_SCHUR = 1, /* explicit reduced camera system + dense Cholesky */
+  PXR_SOLVER_SPARSE_SCHUR = 2,/* exact too: runs the dense-Cholesky path */
+  PXR_SOLVER_ITERATIVE_SCHUR = 3 /* block-Jacobi PCG on the reduced system */
+} pxr_linear_solver;
+
+/* InterpolationConfig subset on the named path (base/src/interpolation.h:39-51):
+ * mode BICUBIC, one node {0,0}. */
+typedef struct {
+  int32_t l2_normalize;   /* default 1 */
+  int32_t use_float_simd; /* 0: fp32 horizontal + fp64 vertical (reference default), 1: all fp32 */
+  int32_t check_bounds;   /* must be 0 on this path (reference default) */
+  int32_t reserved;
+} pxr_interp_config;
+
+/* Solver options = ceres::Solver::Options fields the reference sets
+ * (bundle_adjustment_options.h:48-64, base/main.py:9-22). */
+typedef struct {
+  int32_t loss_type;                /* pxr_loss_type */
+  double loss_scale;                /* "params"[0] */
+  int32_t linear_solver;            /* pxr_linear_solver */
+  int32_t max_num_iterations;       /* 100 */
+  int32_t max_linear_solver_iterations; /* 200 */
+  int32_t max_num_consecutive_invalid_steps; /* 10 */
+  double function_tolerance;        /* 0 */
+  double gradient_tolerance;        /* 0 */
+  double parameter_tolerance;       /* 0 (KA: 1e-5) */
+  int32_t use_inner_iterations;     /* BA python default: 1 (bundle_adjustment/main.py:41-44) */
+  double inner_iteration_tolerance; /* 1e-3 (ceres default) */
+  double initial_trust_region_radius; /* 1e4 */
+  double max_trust_region_radius;   /* 1e16 */
+  double min_trust_region_radius;   /* 1e-32 */
+  double min_relative_decrease;     /* 1e-3 */
+  double min_lm_diagonal;           /* 1e-6 */
+  double max_lm_diagonal;           /* 1e32 */
+  int32_t jacobi_scaling;           /* 1 */
+  int32_t deterministic;            /* 1: fixed-order reductions (slower), 0: fp64 atomics */
+} pxr_solver_options;
+
+/* One featuremetric BA problem (reference: what BundleOptimizer::SetUp turns a
+ * colmap::Reconstruction + FeatureView + references into,
+ * bundle_optimizer.h:139-165, feature_reference_bundle_optimizer.h:90-149).
+ * Parameter arrays are IN/OUT: pxr_ba_solve updates them in place, as the
+ * reference updates the Reconstruction through raw double*
+ * (feature_reference_bundle_optimizer.h:111-114). */
+typedef struct {
+  /* cameras (intrinsics) */
+  int32_t n_cameras;
+  const int32_t* cam_model;       /* [n_cameras] pxr_camera_model */
+  double* cam_params;             /* [n_cameras][PXR_MAX_CAM_PARAMS], unused tail ignored */
+  const uint32_t* cam_const_mask; /* [n_cameras] bit i: param i constant; 0xFFFFFFFF: block constant */
+  /* images (poses); qvec is (w,x,y,z), world->camera, as COLMAP */
+  int32_t n_images;
+  double* qvec;                   /* [n_images][4] */
+  double* tvec;                   /* [n_images][3] */
+  const int32_t* img_cam;         /* [n_images] index into cameras */
+  const uint8_t* pose_const;      /* [n_images] 1: qvec and tvec constant */
+  const uint8_t* tvec_const_mask; /* [n_images] bit i: tvec[i] constant (SubsetManifold) */
+  /* points */
+  int64_t n_points;
+  double* xyz;                    /* [n_points][3] */
+  const uint8_t* point_const;     /* [n_points] 1: constant */
+  /* observations = residual blocks, sorted by point index (ties: any fixed order) */
+  int64_t n_obs;
+  const int32_t* obs_img;         /* [n_obs] */
+  const int64_t* obs_pt;          /* [n_obs] non-decreasing */
+  const int64_t* obs_patch;       /* [n_obs] index into the patch slab, or NULL: patch i = obs i */
+  /* feature patches: slab [n_patches][ph][pw][channels], HWC interleaved like
+   * FeaturePatch (features/src/featurepatch.h:244-262, grid2d.h:29-73) */
+  int64_t n_patches;
+  const void* patches;            /* host pointer (or device pointer if patches_on_device) */
+  int32_t patches_on_device;
+  int32_t patch_dtype;            /* pxr_dtype */
+  int32_t ph, pw, channels;
+  const int32_t* corner;          /* [n_patches][2] (x0,y0) */
+  const double* scale;            /* [n_patches][2] (sx,sy) */
+  double upsampling_factor;       /* FeaturePatch::upsampling_factor_, 1.0 */
+  /* per-point reference descriptors, fp64 (Reference::descriptor, references.h:32-65);
+   * NULL => residual = interpolated feature (costmap use, feature_reference.h:128-130) */
+  const double* refs;             /* [n_points][channels] */
+} pxr_ba_desc;
+
+typedef struct {
+  int32_t iteration;
+  int32_t step_is_valid;
+  int32_t step_is_successful;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double step_norm;
+  double relative_decrease;
+  double trust_region_radius;
+  int32_t linear_solver_iterations;
+  double iteration_time_s;
+} pxr_iteration_summary;
+
+/* Mirrors the fields of ceres::Solver::Summary that the reference reads
+ * (bundle_optimizer.h:236-241, util/src/statistics.h:54-129). */
+typedef struct {
+  double initial_cost;
+  double final_cost;
+  int32_t num_residual_blocks;
+  int64_t num_residuals;          /* num_residual_blocks * channels */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t num_inner_iteration_steps;
+  int32_t termination_type;       /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE, 3 USER_FAILURE */
+  double total_time_s;            /* wall, includes uploads */
+  double solve_time_s;            /* wall, LM loop only (inputs resident) */
+  double h2d_bytes, d2h_bytes;
+  int32_t num_iterations;         /* entries valid in `iterations` */
+  int32_t iterations_capacity;    /* in: capacity of `iterations` (may be 0) */
+  pxr_iteration_summary* iterations; /* caller-allocated */
+  int64_t kernel_launches;        /* CUDA kernels of this library launched by the call */
+  char message[256];
+} pxr_summary;
+
+typedef struct pxr_ctx pxr_ctx;
+typedef struct pxr_ba pxr_ba;
+
+/* ---- context ----------------------------------------------------------- */
+const char* pxr_last_error(void);
+int pxr_version(void);
+/* device < 0 → current device. Fails with PXR_ERR_NO_DEVICE when no GPU. */
+int pxr_ctx_create(int device, pxr_ctx** out);
+int pxr_ctx_destroy(pxr_ctx* ctx);
+/* Multi-GPU: point-sharded BA, one process per GPU.  nccl_unique_id is the 128-byte
+ * ncclUniqueId made on rank 0 (pxr_nccl_unique_id) and distributed by the host's own
+ * plumbing (torch.distributed broadcast in bench.py).  No reference counterpart
+ * (the reference is single-process: base/src/parallel_optimizer.h:77-211). */
+int pxr_nccl_unique_id(void* id128);
+int pxr_ctx_init_comm(pxr_ctx* ctx, int rank, int world, const void* id128);
+int pxr_ctx_sync(pxr_ctx* ctx);
+int64_t pxr_ctx_kernel_launches(pxr_ctx* ctx);
+
+/* ---- default option blocks --------------------------------------------- */
+void pxr_default_interp_config(pxr_interp_config* c);  /* base/main.py:1-7 */
+void pxr_default_ba_options(pxr_solver_options* o);    /* bundle_adjustment/main.py:30-62 */
+void pxr_default_ka_options(pxr_solver_options* o);    /* keypoint_adjustment/main.py:60-83 */
+
+/* ---- featuremetric BA ---------------------------------------------------
+ * replaces _bundle_adjustment.FeatureReferenceBundleOptimizer.run / set_up /
+ * solve_problem / summary (bundle_adjustment/bindings.cc:36-51,137-141). */
+int pxr_ba_create(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
+                  const pxr_solver_options* opt, pxr_ba** out);   /* uploads (set_up) */
+int pxr_ba_solve(pxr_ba* ba, pxr_summary* summary);               /* solve_problem */
+int pxr_ba_read_params(pxr_ba* ba, double* cam_params, double* qvec, double* tvec, double* xyz);
+int pxr_ba_destroy(pxr_ba* ba);
+/* one-shot convenience = FeatureReferenceBundleOptimizer.run: upload, solve, write back into desc arrays */
+int pxr_ba_run(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
+               const pxr_solver_options* opt, pxr_summary* summary);
+
+/* Parity / introspection: evaluates every residual block at the current parameters.
+ * Replaces calling FeatureReferenceCostFunctor::operator() per block
+ * (residuals/src/feature_reference.h:98-137).  Any output may be NULL.
+ *  sq_norm [n_obs]      ||r||^2 (uncorrected)
+ *  gtr     [n_obs][2]   G^T r,  G = [d r/d u, d r/d v] in patch pixel units (u=col, v=row)
+ *  gtg     [n_obs][3]   G^T G (uu, uv, vv)
+ *  xy      [n_obs][2]   projected image point
+ *  residuals [n_obs][C] r as double (large! optional)
+ *  cost    scalar       sum 0.5*rho(||r||^2) */
+int pxr_ba_evaluate(pxr_ba* ba, double* sq_norm, double* gtr, double* gtg, double* xy,
+                    double* residuals, double* cost);
+/* Timing hooks for bench.py: run `iters` LM iterations' worth of the named stage on the
+ * resident problem and return the average device time per launch in ms (CUDA events on the
+ * library stream).  stage: 0 residual/Jacobian kernel, 1 cost-only kernel, 2 full LM iteration */
+int pxr_ba_time_stage(pxr_ba* ba, int stage, int iters, double* ms_per_launch);
+/* Device-side synthetic scene generator used by bench.py (data: synthetic). Fills a patch slab
+ * on the device from per-patch smooth fields; see DESIGN.md §bench. */
+int pxr_synth_patches_device(pxr_ctx* ctx, void** d_patches_out, int64_t n_patches, int ps, int channels,
+                             const double* uv0 /*[n][2] true location in patch px*/,
+                             const int64_t* field_id /*[n] which smooth field (point id)*/,
+                             uint64_t seed, double noise_sigma);
+int pxr_device_free(pxr_ctx* ctx, void* dptr);
+int pxr_memcpy_d2h(pxr_ctx* ctx, void* host, const void* dev, size_t bytes);
+
+/* ---- reference extraction ----------------------------------------------
+ * replaces _bundle_adjustment.ReferenceExtractor.run (bindings.cc:28-34,172-177;
+ * reference_extractor.h:171-318, irls_optim.h:23-71).
+ *  refs_out    [n_points][C] fp64  reference descriptor (closest_to_robust_mean)
+ *  src_obs_out [n_points]    index (into obs) of the observation picked as reference, -1 if none */
+int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
+                     int loss_type, double loss_scale, int iters,
+                     double* refs_out, int64_t* src_obs_out, pxr_summary* summary);
+
+/* ---- featuremetric KA ---------------------------------------------------
+ * replaces _keypoint_adjustment.FeatureMetricKeypointOptimizer.run
+ * (keypoint_adjustment/bindings.cc:17-34; featuremetric_keypoint_optimizer.h:50-202;
+ * keypoint_optimizer.h:110-157). Keypoints are IN/OUT. */
+typedef struct {
+  int64_t n_keypoints;
+  double* keypoints;            /* [n_keypoints][2] COLMAP image coords, in/out */
+  const uint8_t* kp_const;      /* [n_keypoints] 1: constant (root nodes) */
+  const int64_t* kp_patch;      /* [n_keypoints] patch index, or NULL: identity */
+  int64_t n_edges;
+  const int64_t* edge_src;      /* [n_edges] keypoint index */
+  const int64_t* edge_dst;      /* [n_edges] */
+  const double* edge_weight;    /* [n_edges] ScaledLoss weight (similarity) */
+  const int32_t* edge_problem;  /* [n_edges] non-decreasing problem label (RunParallel groups) */
+  int32_t n_problems;
+  int64_t n_patches;
+  const void* patches;
+  int32_t patches_on_device;
+  int32_t patch_dtype;
+  int32_t ph, pw, channels;
+  const int32_t* corner;        /* [n_patches][2] */
+  const double* scale;          /* [n_patches][2] */
+  double upsampling_factor;
+  double bound;                 /* KeypointOptimizerOptions::bound, 4.0 from python */
+  int32_t patches_are_sparse;   /* FeatureMap::IsSparse() */
+} pxr_ka_desc;
+
+int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* desc, const pxr_interp_config* interp,
+               const pxr_solver_options* opt, pxr_summary* summary);
+
+/* ---- host-side integer algorithms (bit-exact targets) -------------------
+ * replace _base.compute_track_labels / compute_score_labels / compute_root_labels
+ * (base/src/graph.cc:126-256) and keypoint_adjustment/main.py:13-57 find_problem_labels. */
+int pxr_graph_track_labels(int64_t n_nodes, const int32_t* node_image, int64_t n_edges,
+                           const int64_t* e_src, const int64_t* e_dst, const double* e_sim,
+                           int64_t* track_labels_out);
+int pxr_graph_score_labels(int64_t n_nodes, int64_t n_edges, const int64_t* e_src,
+                           const int64_t* e_dst, const double* e_sim,
+                           const int64_t* track_labels, double* scores_out);
+int pxr_graph_root_labels(int64_t n_nodes, const int64_t* track_labels, const double* scores,
+                          uint8_t* is_root_out);
+int pxr_ka_problem_labels(int64_t n_nodes, const int64_t* track_labels, int32_t max_per_problem,
+                          int32_t* problem_labels_out, int32_t* n_problems_out);
+/* BA: reference bundle_adjustment/main.py:21-27 (label = p3D_id // max_tracks_per_problem) lives in Python. */
+
+/* Multi-GPU sharding plan: contiguous point ranges balanced by observation count. */
+int pxr_shard_points(int64_t n_points, int64_t n_obs, const int64_t* obs_pt, int world,
+                     int64_t* point_begin_out /*[world+1]*/, int64_t* obs_begin_out /*[world+1]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PXR_H_ */

@@ -1,0 +1,308 @@
+"""ctypes mirror of include/pxr.h (the C-ABI of libpxr.so).
+
+This module is plumbing only: struct layouts, library loading, and helpers that turn numpy
+arrays into the SoA problem IR.  It contains NO arithmetic of the hot path and NO CPU
+fallback: if libpxr.so is missing or no CUDA device is usable every compute entry point
+raises (PxrError / RuntimeError).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+PXR_MAX_CAM_PARAMS = 12
+
+# status codes -> exception types (reference: THROW_CHECK* -> py::value_error,
+# util/src/log_exceptions.h:52-84; unsupported (C,N) -> std::invalid_argument)
+PXR_OK, PXR_ERR_INVALID_ARGUMENT, PXR_ERR_UNSUPPORTED, PXR_ERR_NO_DEVICE, PXR_ERR_CUDA, \
+    PXR_ERR_NCCL, PXR_ERR_NUMERIC, PXR_ERR_INTERRUPTED, PXR_ERR_INTERNAL = range(9)
+
+CAMERA_MODEL_IDS = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, "SIMPLE_RADIAL": 2, "RADIAL": 3,
+                    "OPENCV": 4, "OPENCV_FISHEYE": 5, "FULL_OPENCV": 6}
+CAMERA_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12}
+# (focal, principal point, extra) parameter-index bit masks per model
+CAMERA_PARAM_GROUPS = {0: (0x1, 0x6, 0x0), 1: (0x3, 0xC, 0x0), 2: (0x1, 0x6, 0x8),
+                       3: (0x1, 0x6, 0x18), 4: (0x3, 0xC, 0xF0), 5: (0x3, 0xC, 0xF0),
+                       6: (0x3, 0xC, 0xFF0)}
+LOSS_IDS = {"trivial": 0, "cauchy": 1, "huber": 2, "soft_l1": 3, "softlone": 3, "arctan": 4}
+DTYPE_IDS = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
+
+
+class PxrError(RuntimeError):
+    pass
+
+
+class InterpConfig(C.Structure):
+    _fields_ = [("l2_normalize", C.c_int32), ("use_float_simd", C.c_int32),
+                ("check_bounds", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SolverOptions(C.Structure):
+    _fields_ = [("loss_type", C.c_int32), ("loss_scale", C.c_double),
+                ("linear_solver", C.c_int32), ("max_num_iterations", C.c_int32),
+                ("max_linear_solver_iterations", C.c_int32),
+                ("max_num_consecutive_invalid_steps", C.c_int32),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("use_inner_iterations", C.c_int32),
+                ("inner_iteration_tolerance", C.c_double),
+                ("initial_trust_region_radius", C.c_double),
+                ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
+                ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int32),
+                ("deterministic", C.c_int32)]
+
+
+class BADesc(C.Structure):
+    _fields_ = [("n_cameras", C.c_int32), ("cam_model", C.c_void_p), ("cam_params", C.c_void_p),
+                ("cam_const_mask", C.c_void_p),
+                ("n_images", C.c_int32), ("qvec", C.c_void_p), ("tvec", C.c_void_p),
+                ("img_cam", C.c_void_p), ("pose_const", C.c_void_p), ("tvec_const_mask", C.c_void_p),
+                ("n_points", C.c_int64), ("xyz", C.c_void_p), ("point_const", C.c_void_p),
+                ("n_obs", C.c_int64), ("obs_img", C.c_void_p), ("obs_pt", C.c_void_p),
+                ("obs_patch", C.c_void_p),
+                ("n_patches", C.c_int64), ("patches", C.c_void_p), ("patches_on_device", C.c_int32),
+                ("patch_dtype", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
+                ("channels", C.c_int32), ("corner", C.c_void_p), ("scale", C.c_void_p),
+                ("upsampling_factor", C.c_double), ("refs", C.c_void_p)]
+
+
+class IterationSummary(C.Structure):
+    _fields_ = [("iteration", C.c_int32), ("step_is_valid", C.c_int32),
+                ("step_is_successful", C.c_int32), ("cost", C.c_double),
+                ("cost_change", C.c_double), ("gradient_max_norm", C.c_double),
+                ("step_norm", C.c_double), ("relative_decrease", C.c_double),
+                ("trust_region_radius", C.c_double), ("linear_solver_iterations", C.c_int32),
+                ("iteration_time_s", C.c_double)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("num_residual_blocks", C.c_int32), ("num_residuals", C.c_int64),
+                ("num_successful_steps", C.c_int32), ("num_unsuccessful_steps", C.c_int32),
+                ("num_inner_iteration_steps", C.c_int32), ("termination_type", C.c_int32),
+                ("total_time_s", C.c_double), ("solve_time_s", C.c_double),
+                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
+                ("num_iterations", C.c_int32), ("iterations_capacity", C.c_int32),
+                ("iterations", C.POINTER(IterationSummary)), ("kernel_launches", C.c_int64),
+                ("message", C.c_char * 256)]
+
+
+class KADesc(C.Structure):
+    _fields_ = [("n_keypoints", C.c_int64), ("keypoints", C.c_void_p), ("kp_const", C.c_void_p),
+                ("kp_patch", C.c_void_p), ("n_edges", C.c_int64), ("edge_src", C.c_void_p),
+                ("edge_dst", C.c_void_p), ("edge_weight", C.c_void_p), ("edge_problem", C.c_void_p),
+                ("n_problems", C.c_int32), ("n_patches", C.c_int64), ("patches", C.c_void_p),
+                ("patches_on_device", C.c_int32), ("patch_dtype", C.c_int32), ("ph", C.c_int32),
+                ("pw", C.c_int32), ("channels", C.c_int32), ("corner", C.c_void_p),
+                ("scale", C.c_void_p), ("upsampling_factor", C.c_double), ("bound", C.c_double),
+                ("patches_are_sparse", C.c_int32)]
+
+
+def make_summary(capacity=256):
+    s = Summary()
+    buf = (IterationSummary * max(capacity, 1))()
+    s.iterations = C.cast(buf, C.POINTER(IterationSummary))
+    s.iterations_capacity = capacity
+    s._buf = buf
+    return s
+
+
+def summary_to_dict(s):
+    n = min(s.num_iterations, s.iterations_capacity)
+    its = [{f[0]: getattr(s.iterations[i], f[0]) for f in IterationSummary._fields_} for i in range(n)]
+    d = {f[0]: getattr(s, f[0]) for f in Summary._fields_ if f[0] not in ("iterations", "message")}
+    d["message"] = s.message.decode(errors="replace")
+    d["iterations"] = its
+    return d
+
+
+def default_interp(l2_normalize=True, use_float_simd=False):
+    return InterpConfig(int(l2_normalize), int(use_float_simd), 0, 0)
+
+
+def default_ba_options(**kw):
+    """bundle_adjustment/main.py:30-62 + bundle_adjustment_options.h:48-64 defaults."""
+    o = SolverOptions(loss_type=1, loss_scale=0.25, linear_solver=0, max_num_iterations=100,
+                      max_linear_solver_iterations=200, max_num_consecutive_invalid_steps=10,
+                      function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
+                      use_inner_iterations=1, inner_iteration_tolerance=1e-3,
+                      initial_trust_region_radius=1e4, max_trust_region_radius=1e16,
+                      min_trust_region_radius=1e-32, min_relative_decrease=1e-3,
+                      min_lm_diagonal=1e-6, max_lm_diagonal=1e32, jacobi_scaling=1, deterministic=0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def default_ka_options(**kw):
+    """keypoint_adjustment/main.py:60-83 + keypoint_adjustment_options.h:47-86 defaults."""
+    o = default_ba_options(use_inner_iterations=0, parameter_tolerance=1e-5)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _as(a, dtype, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class BAProblem:
+    """Holds the numpy arrays of one BA problem IR and the ctypes view of them."""
+
+    def __init__(self, cam_model, cam_params, cam_const_mask, qvec, tvec, img_cam, pose_const,
+                 tvec_const_mask, xyz, point_const, obs_img, obs_pt, patches, corner, scale,
+                 refs=None, obs_patch=None, upsampling_factor=1.0, patches_on_device=False,
+                 patch_shape=None, patch_dtype=None):
+        self.cam_model = _as(cam_model, np.int32)
+        nc = len(self.cam_model)
+        cp = np.zeros((nc, PXR_MAX_CAM_PARAMS), np.float64)
+        cam_params = np.asarray(cam_params, np.float64)
+        if cam_params.ndim == 2 and cam_params.shape[1] == PXR_MAX_CAM_PARAMS:
+            cp[:] = cam_params
+        else:
+            for i in range(nc):
+                k = CAMERA_NUM_PARAMS[int(self.cam_model[i])]
+                cp[i, :k] = np.asarray(cam_params[i], np.float64)[:k]
+        self.cam_params = cp
+        self.cam_const_mask = _as(cam_const_mask, np.uint32)
+        self.qvec = _as(qvec, np.float64, (-1, 4)).copy()
+        self.tvec = _as(tvec, np.float64, (-1, 3)).copy()
+        self.img_cam = _as(img_cam, np.int32)
+        self.pose_const = _as(pose_const, np.uint8)
+        self.tvec_const_mask = _as(tvec_const_mask, np.uint8)
+        self.xyz = _as(xyz, np.float64, (-1, 3)).copy()
+        self.point_const = _as(point_const, np.uint8)
+        self.obs_img = _as(obs_img, np.int32)
+        self.obs_pt = _as(obs_pt, np.int64)
+        if len(self.obs_pt) > 1 and np.any(np.diff(self.obs_pt) < 0):
+            raise ValueError("observations must be sorted by point index")
+        self.obs_patch = _as(obs_patch, np.int64)
+        self.patches_on_device = bool(patches_on_device)
+        if self.patches_on_device:
+            self.patches = None
+            self._patches_ptr = int(patches)
+            self.n_patches, self.ph, self.pw, self.channels = patch_shape
+            self.patch_dtype = patch_dtype
+        else:
+            if patches.dtype not in DTYPE_IDS or not patches.flags["C_CONTIGUOUS"] or patches.ndim != 4:
+                raise ValueError("patches must be a C-contiguous [N,H,W,C] f16/f32/f64 array")
+            self.patches = patches
+            self._patches_ptr = patches.ctypes.data
+            self.n_patches, self.ph, self.pw, self.channels = patches.shape
+            self.patch_dtype = DTYPE_IDS[patches.dtype]
+        self.corner = _as(corner, np.int32, (-1, 2))
+        self.scale = _as(scale, np.float64, (-1, 2))
+        self.refs = _as(refs, np.float64)
+        self.upsampling_factor = float(upsampling_factor)
+
+    @property
+    def n_obs(self):
+        return len(self.obs_pt)
+
+    def desc(self):
+        d = BADesc()
+        d.n_cameras = len(self.cam_model)
+        d.cam_model = _ptr(self.cam_model); d.cam_params = _ptr(self.cam_params)
+        d.cam_const_mask = _ptr(self.cam_const_mask)
+        d.n_images = len(self.img_cam)
+        d.qvec = _ptr(self.qvec); d.tvec = _ptr(self.tvec); d.img_cam = _ptr(self.img_cam)
+        d.pose_const = _ptr(self.pose_const); d.tvec_const_mask = _ptr(self.tvec_const_mask)
+        d.n_points = len(self.xyz)
+        d.xyz = _ptr(self.xyz); d.point_const = _ptr(self.point_const)
+        d.n_obs = len(self.obs_pt)
+        d.obs_img = _ptr(self.obs_img); d.obs_pt = _ptr(self.obs_pt); d.obs_patch = _ptr(self.obs_patch)
+        d.n_patches = self.n_patches
+        d.patches = C.c_void_p(self._patches_ptr)
+        d.patches_on_device = int(self.patches_on_device)
+        d.patch_dtype = self.patch_dtype
+        d.ph, d.pw, d.channels = self.ph, self.pw, self.channels
+        d.corner = _ptr(self.corner); d.scale = _ptr(self.scale)
+        d.upsampling_factor = self.upsampling_factor
+        d.refs = _ptr(self.refs)
+        return d
+
+    def copy(self):
+        import copy as _copy
+        o = _copy.copy(self)
+        for k in ("cam_params", "qvec", "tvec", "xyz"):
+            setattr(o, k, getattr(self, k).copy())
+        if self.refs is not None:
+            o.refs = self.refs.copy()
+        return o
+
+
+_LIB = None
+
+
+def lib_path():
+    here = os.path.dirname(os.path.abspath(__file__))
+    return os.path.normpath(os.path.join(here, "..", "..", "csrc", "libpxr.so"))
+
+
+def load_lib():
+    """Load libpxr.so (built in-tree by __graft_entry__.build()). Fails loudly if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise PxrError("libpxr.so not built (%s): run `python __graft_entry__.py build`; "
+                       "there is no CPU fallback" % p)
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib.pxr_last_error.restype = C.c_char_p
+    lib.pxr_ctx_kernel_launches.restype = C.c_int64
+    _LIB = lib
+    return lib
+
+
+def check(status):
+    if status == PXR_OK:
+        return
+    msg = load_lib().pxr_last_error().decode(errors="replace")
+    if status in (PXR_ERR_INVALID_ARGUMENT, PXR_ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    if status == PXR_ERR_INTERRUPTED:
+        raise KeyboardInterrupt(msg)
+    raise PxrError("pxr status %d: %s" % (status, msg))
+
+
+class Context:
+    def __init__(self, device=-1):
+        self.lib = load_lib()
+        self.handle = C.c_void_p()
+        check(self.lib.pxr_ctx_create(C.c_int(device), C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.lib.pxr_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def kernel_launches(self):
+        return int(self.lib.pxr_ctx_kernel_launches(self.handle))
+
+    def sync(self):
+        check(self.lib.pxr_ctx_sync(self.handle))
+
+
+_DEFAULT_CTX = None
+
+
+def default_context():
+    global _DEFAULT_CTX
+    if _DEFAULT_CTX is None:
+        _DEFAULT_CTX = Context(-1)
+    return _DEFAULT_CTX
