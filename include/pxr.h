@@ -238,9 +238,19 @@ int pxr_ba_run(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* i
  *  cost    scalar       sum 0.5*rho(||r||^2) */
 int pxr_ba_evaluate(pxr_ba* ba, double* sq_norm, double* gtr, double* gtg, double* xy,
                     double* residuals, double* cost);
+/* Introspection for parity tests: linearise at the current parameters (camera blocks Hcc [nc*nc,
+ * lower triangle], gc, point blocks Hpp [n_points*9], gp), assemble the damped Schur system S/rhs at
+ * `radius` (Jacobi scaling taken from this linearisation, as in LM iteration 0), solve it and
+ * return the full step `delta` [n_local] and the model cost change.  Any output may be NULL. */
+int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc, double* gc, double* Hpp,
+                           double* gp, double* S, double* rhs, double* delta, double* model_cost_change);
+/* Runs the per-point inner iterations (ceres CoordinateDescentMinimizer equivalent) once on the
+ * current parameters (parity tests). */
+int pxr_ba_debug_inner_iterations(pxr_ba* ba);
 /* Timing hooks for bench.py: run `iters` LM iterations' worth of the named stage on the
  * resident problem and return the average device time per launch in ms (CUDA events on the
- * library stream).  stage: 0 residual/Jacobian kernel, 1 cost-only kernel, 2 full LM iteration */
+ * library stream).  stage: 0 residual/Jacobian kernel (K1), 1 cost-only kernel, 2 projection+K1+block build,
+ * 3 projection kernel (K0), 4 block build, 5 inner-iteration kernel */
 int pxr_ba_time_stage(pxr_ba* ba, int stage, int iters, double* ms_per_launch);
 /* Device-side synthetic scene generator used by bench.py (data: synthetic). Fills a patch slab
  * on the device from per-patch smooth fields; see DESIGN.md §bench. */

@@ -204,6 +204,17 @@ int orc_ba_solve(const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_so
   return 0;
 }
 
+// CoordinateDescentMinimizer::Minimize alone on the current parameters (updates desc->xyz)
+int orc_ba_inner_iterations(const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so) {
+  BAEvalOptions eo = MakeEO(ic, so);
+  BAEvaluator ev(*d, eo);
+  std::vector<double> x(ev.NumParameters());
+  ev.PackParameters(x.data());
+  ev.InnerIterations(x.data());
+  ev.UnpackParameters(x.data());
+  return 0;
+}
+
 // CPU-baseline timing: seconds for `reps` Jacobian evaluations (residuals + full Jacobians +
 // normal-equation blocks, all host threads), and for one damped Schur solve.
 int orc_ba_time(const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so,

@@ -1,0 +1,301 @@
+// pxr_api.cu — context, error handling, NCCL plumbing and the host-side integer algorithms of
+// the C-ABI (include/pxr.h).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <set>
+#include <tuple>
+#include <unordered_map>
+
+#include "pxr_internal.h"
+
+namespace pxr {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+int fail(int status, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return status;
+}
+
+// ---- NCCL through dlopen (libnccl.so.2: torch's bundled copy if already loaded, else the system one)
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  void* InitRank = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+struct Uid128 { char b[128]; };
+static int load_nccl() {
+  if (g_nccl.h) return PXR_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(PXR_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.h = h;
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.InitRank = dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.InitRank || !g_nccl.AllReduce)
+    return fail(PXR_ERR_NCCL, "libnccl.so.2 lacks the expected symbols");
+  return PXR_OK;
+}
+
+int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count) {
+  if (!ctx->nccl_comm || ctx->world <= 1 || count == 0) return PXR_OK;
+  // ncclFloat64 = 8, ncclSum = 0
+  const int rc = g_nccl.AllReduce(dptr, dptr, count, 8, 0, ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return fail(PXR_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return PXR_OK;
+}
+
+}  // namespace pxr
+
+using namespace pxr;
+
+extern "C" {
+
+const char* pxr_last_error(void) { return g_error.c_str(); }
+int pxr_version(void) { return PXR_VERSION_MAJOR * 100 + PXR_VERSION_MINOR; }
+
+int pxr_ctx_create(int device, pxr_ctx** out) {
+  if (!out) return fail(PXR_ERR_INVALID_ARGUMENT, "out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(PXR_ERR_NO_DEVICE, "no CUDA device available (%s); libpxr has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= count) return fail(PXR_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, count);
+  PXR_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PXR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 9)
+    return fail(PXR_ERR_NO_DEVICE, "device %d is sm_%d%d; libpxr is built for sm_100a only", device, prop.major, prop.minor);
+  pxr_ctx* c = new pxr_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  PXR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return PXR_OK;
+}
+
+int pxr_ctx_destroy(pxr_ctx* ctx) {
+  if (!ctx) return PXR_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return PXR_OK;
+}
+
+int pxr_nccl_unique_id(void* id128) {
+  PXR_TRY(load_nccl());
+  const int rc = g_nccl.GetUniqueId(id128);
+  if (rc != 0) return fail(PXR_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  return PXR_OK;
+}
+
+int pxr_ctx_init_comm(pxr_ctx* ctx, int rank, int world, const void* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(PXR_ERR_INVALID_ARGUMENT, "bad comm arguments");
+  ctx->rank = rank; ctx->world = world;
+  if (world == 1) return PXR_OK;
+  PXR_TRY(load_nccl());
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  Uid128 uid;
+  std::memcpy(uid.b, id128, 128);
+  typedef int (*init_t)(void**, int, Uid128, int);
+  const int rc = ((init_t)g_nccl.InitRank)(&ctx->nccl_comm, world, uid, rank);
+  if (rc != 0) return fail(PXR_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return PXR_OK;
+}
+
+int pxr_ctx_sync(pxr_ctx* ctx) {
+  if (!ctx) return fail(PXR_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PXR_OK;
+}
+int64_t pxr_ctx_kernel_launches(pxr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void pxr_default_interp_config(pxr_interp_config* c) {
+  c->l2_normalize = 1; c->use_float_simd = 0; c->check_bounds = 0; c->reserved = 0;
+}
+void pxr_default_ba_options(pxr_solver_options* o) {
+  o->loss_type = PXR_LOSS_CAUCHY; o->loss_scale = 0.25; o->linear_solver = PXR_SOLVER_AUTO;
+  o->max_num_iterations = 100; o->max_linear_solver_iterations = 200;
+  o->max_num_consecutive_invalid_steps = 10;
+  o->function_tolerance = 0.0; o->gradient_tolerance = 0.0; o->parameter_tolerance = 0.0;
+  o->use_inner_iterations = 1; o->inner_iteration_tolerance = 1e-3;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->jacobi_scaling = 1; o->deterministic = 0;
+}
+void pxr_default_ka_options(pxr_solver_options* o) {
+  pxr_default_ba_options(o);
+  o->use_inner_iterations = 0;
+  o->parameter_tolerance = 1e-5;
+}
+
+int pxr_device_free(pxr_ctx* ctx, void* dptr) {
+  if (ctx) cudaSetDevice(ctx->device);
+  if (dptr) PXR_CUDA(cudaFree(dptr));
+  return PXR_OK;
+}
+int pxr_memcpy_d2h(pxr_ctx* ctx, void* host, const void* dev, size_t bytes) {
+  if (!ctx) return fail(PXR_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  PXR_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PXR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side integer algorithms (bit-exact targets).  Product code: written against the
+// reference's behaviour (base/src/graph.cc:126-256), independent of oracle/.
+static int64_t uf_root(int64_t i, std::vector<int64_t>& parent) {
+  int64_t r = i;
+  while (parent[r] != -1) r = parent[r];
+  while (parent[i] != -1) { const int64_t nx = parent[i]; parent[i] = r; i = nx; }  // path compression
+  return r;
+}
+
+int pxr_graph_track_labels(int64_t n_nodes, const int32_t* node_image, int64_t n_edges, const int64_t* e_src,
+                           const int64_t* e_dst, const double* e_sim, int64_t* out) {
+  if (n_nodes < 0 || n_edges < 0 || (n_nodes && (!node_image || !out)) || (n_edges && (!e_src || !e_dst)))
+    return fail(PXR_ERR_INVALID_ARGUMENT, "bad graph arguments");
+  // edges in DESCENDING lexicographic (sim, node1, node2) order == sort ascending + reverse
+  std::vector<int64_t> order(n_edges);
+  for (int64_t e = 0; e < n_edges; ++e) order[e] = e;
+  auto sim_of = [&](int64_t e) { return e_sim ? e_sim[e] : 1.0; };
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    return std::make_tuple(sim_of(a), (uint64_t)e_src[a], (uint64_t)e_dst[a]) >
+           std::make_tuple(sim_of(b), (uint64_t)e_src[b], (uint64_t)e_dst[b]);
+  });
+  std::vector<int64_t> parent(n_nodes, -1);
+  // image sets as sorted vectors (merged on union)
+  std::vector<std::vector<int32_t>> images(n_nodes);
+  for (int64_t i = 0; i < n_nodes; ++i) images[i].push_back(node_image[i]);
+  std::vector<int32_t> merged;
+  for (int64_t e : order) {
+    const int64_t a = e_src[e], b = e_dst[e];
+    if (a < 0 || b < 0 || a >= n_nodes || b >= n_nodes) return fail(PXR_ERR_INVALID_ARGUMENT, "edge endpoint out of range");
+    const int64_t r1 = uf_root(a, parent), r2 = uf_root(b, parent);
+    if (r1 == r2) continue;
+    const std::vector<int32_t>& s1 = images[r1];
+    const std::vector<int32_t>& s2 = images[r2];
+    bool intersects = false;
+    for (size_t i = 0, j = 0; i < s1.size() && j < s2.size();) {
+      if (s1[i] < s2[j]) ++i; else if (s2[j] < s1[i]) ++j; else { intersects = true; break; }
+    }
+    if (intersects) continue;
+    merged.resize(s1.size() + s2.size());
+    std::merge(s1.begin(), s1.end(), s2.begin(), s2.end(), merged.begin());
+    if (s1.size() < s2.size()) { parent[r1] = r2; images[r2] = merged; images[r1].clear(); images[r1].shrink_to_fit(); }
+    else { parent[r2] = r1; images[r1] = merged; images[r2].clear(); images[r2].shrink_to_fit(); }
+  }
+  int64_t n_tracks = 0;
+  for (int64_t i = 0; i < n_nodes; ++i) out[i] = parent[i] == -1 ? n_tracks++ : -1;
+  for (int64_t i = 0; i < n_nodes; ++i) if (out[i] == -1) out[i] = out[uf_root(i, parent)];
+  return PXR_OK;
+}
+
+int pxr_graph_score_labels(int64_t n_nodes, int64_t n_edges, const int64_t* e_src, const int64_t* e_dst,
+                           const double* e_sim, const int64_t* labels, double* scores) {
+  for (int64_t i = 0; i < n_nodes; ++i) scores[i] = 0.0;
+  for (int64_t e = 0; e < n_edges; ++e) {
+    const double s = e_sim ? e_sim[e] : 1.0;
+    if (labels[e_src[e]] == labels[e_dst[e]]) { scores[e_src[e]] += s; scores[e_dst[e]] += s; }
+  }
+  return PXR_OK;
+}
+
+int pxr_graph_root_labels(int64_t n_nodes, const int64_t* labels, const double* scores, uint8_t* is_root) {
+  int64_t n_tracks = 0;
+  for (int64_t i = 0; i < n_nodes; ++i) n_tracks = std::max(n_tracks, labels[i] + 1);
+  std::vector<int64_t> order(n_nodes);
+  for (int64_t i = 0; i < n_nodes; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    return std::make_pair(scores[a], (uint64_t)a) > std::make_pair(scores[b], (uint64_t)b);
+  });
+  std::vector<char> has_root(n_tracks, 0);
+  for (int64_t i = 0; i < n_nodes; ++i) is_root[i] = 0;
+  for (int64_t n : order) {
+    if (has_root[labels[n]]) continue;
+    is_root[n] = 1; has_root[labels[n]] = 1;
+  }
+  return PXR_OK;
+}
+
+// keypoint_adjustment/main.py:13-57 (first-fit-decreasing; Counter.most_common order = count
+// descending, ties by first appearance)
+int pxr_ka_problem_labels(int64_t n_nodes, const int64_t* labels, int32_t max_per_problem, int32_t* out,
+                          int32_t* n_problems_out) {
+  std::vector<int64_t> order;
+  std::unordered_map<int64_t, int64_t> count;
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    auto it = count.find(labels[i]);
+    if (it == count.end()) { count.emplace(labels[i], 1); order.push_back(labels[i]); } else ++it->second;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return count[a] > count[b]; });
+  int64_t maxpp = max_per_problem;
+  if (maxpp == -1) for (auto& kv : count) maxpp = std::max(maxpp, kv.second);
+  std::vector<int64_t> bins;
+  std::unordered_map<int64_t, int32_t> t2p;
+  size_t start = 0;
+  int64_t last_v = std::numeric_limits<int64_t>::max();
+  for (int64_t k : order) {
+    const int64_t v = count[k];
+    if (v < last_v) { start = 0; last_v = v; }
+    bool found = false;
+    if (v < maxpp) {
+      for (size_t i = start; i < bins.size(); ++i)
+        if (bins[i] + v <= maxpp) { bins[i] += v; t2p[k] = (int32_t)i; found = true; start = i; break; }
+    }
+    if (!found) { t2p[k] = (int32_t)bins.size(); start = bins.size(); bins.push_back(v); }
+  }
+  for (int64_t i = 0; i < n_nodes; ++i) out[i] = t2p[labels[i]];
+  if (n_problems_out) *n_problems_out = (int32_t)bins.size();
+  return PXR_OK;
+}
+
+// Contiguous point ranges balanced by observation count.
+int pxr_shard_points(int64_t n_points, int64_t n_obs, const int64_t* obs_pt, int world, int64_t* point_begin,
+                     int64_t* obs_begin) {
+  if (world < 1 || n_points < 0 || n_obs < 0) return fail(PXR_ERR_INVALID_ARGUMENT, "bad shard arguments");
+  std::vector<int64_t> pt_begin(n_points + 1, 0);
+  for (int64_t o = 0; o < n_obs; ++o) {
+    if (obs_pt[o] < 0 || obs_pt[o] >= n_points) return fail(PXR_ERR_INVALID_ARGUMENT, "obs_pt out of range");
+    if (o && obs_pt[o] < obs_pt[o - 1]) return fail(PXR_ERR_INVALID_ARGUMENT, "observations must be sorted by point");
+    pt_begin[obs_pt[o] + 1]++;
+  }
+  for (int64_t p = 0; p < n_points; ++p) pt_begin[p + 1] += pt_begin[p];
+  point_begin[0] = 0; obs_begin[0] = 0;
+  int64_t p = 0;
+  for (int r = 1; r < world; ++r) {
+    const int64_t target = (n_obs * r) / world;
+    while (p < n_points && pt_begin[p] < target) ++p;
+    point_begin[r] = p; obs_begin[r] = pt_begin[p];
+  }
+  point_begin[world] = n_points; obs_begin[world] = n_obs;
+  return PXR_OK;
+}
+
+}  // extern "C"

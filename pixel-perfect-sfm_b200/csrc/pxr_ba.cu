@@ -1,0 +1,671 @@
+// pxr_ba.cu — featuremetric bundle adjustment on the device: problem upload, the fused
+// residual/Jacobian evaluation (K0+K1), and the Levenberg-Marquardt driver that replaces
+// ceres::Solve for FeatureReferenceBundleOptimizer (reference
+// pixsfm/bundle_adjustment/src/bundle_optimizer.h:114-245,
+// feature_reference_bundle_optimizer.h:90-149).  The host only orchestrates launches and reads
+// back a handful of scalars per LM iteration; all arithmetic runs in the CUDA kernels of
+// pxr_fm_eval.cuh / pxr_ba_kernels.cuh / pxr_inner.cuh.
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "pxr_ba_host.h"
+
+namespace pxr {
+
+// -------------------------------------------------------------------------------- fm_eval dispatch
+template <typename T, int C, int MODE, bool FS>
+static int launch_fm(pxr_ctx* ctx, const FmEvalArgs& a, int* n_partials) {
+  typedef FmCfg<T, C> Cfg;
+  auto kern = fm_eval_kernel<T, C, MODE, FS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PXR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_set = true;
+  }
+  const int64_t n_batches = cdiv(a.end - a.begin, 32);
+  int64_t grid = cdiv(n_batches, Cfg::kWarps);
+  const int64_t resident = (int64_t)ctx->sm_count * std::max(1, (int)(200 * 1024 / Cfg::kSmem));
+  if (grid > resident) grid = resident;
+  if (grid < 1) grid = 1;
+  *n_partials = (int)(grid * Cfg::kWarps);
+  PXR_LAUNCH(ctx, kern, (unsigned)grid, Cfg::kWarps * 32, Cfg::kSmem, a);
+  PXR_CUDA(cudaGetLastError());
+  return PXR_OK;
+}
+
+template <typename T, int C>
+static int launch_fm_tc(pxr_ctx* ctx, const FmEvalArgs& a, int mode, bool fs, int* np) {
+  if (mode == 1) return fs ? launch_fm<T, C, 1, true>(ctx, a, np) : launch_fm<T, C, 1, false>(ctx, a, np);
+  return fs ? launch_fm<T, C, 0, true>(ctx, a, np) : launch_fm<T, C, 0, false>(ctx, a, np);
+}
+
+int fm_supported(int dtype, int C) {
+  if (dtype == PXR_F16) return C == 8 || C == 16 || C == 32 || C == 64 || C == 128 || C == 256;
+  if (dtype == PXR_F32) return C == 16 || C == 64 || C == 128;
+  if (dtype == PXR_F64) return C == 16 || C == 128;
+  return 0;
+}
+
+int fm_max_partials(pxr_ctx* ctx) { return ctx->sm_count * 16 * 64; }
+
+int launch_fm_eval(pxr_ctx* ctx, int dtype, int C, int mode, bool float_simd, const FmEvalArgs& a, int* np) {
+#define PXR_CASE(T, CC) \
+  if (C == CC) return launch_fm_tc<T, CC>(ctx, a, mode, float_simd, np);
+  if (dtype == PXR_F16) {
+    PXR_CASE(__half, 128) PXR_CASE(__half, 64) PXR_CASE(__half, 32) PXR_CASE(__half, 16) PXR_CASE(__half, 8)
+    PXR_CASE(__half, 256)
+  } else if (dtype == PXR_F32) {
+    PXR_CASE(float, 128) PXR_CASE(float, 64) PXR_CASE(float, 16)
+  } else if (dtype == PXR_F64) {
+    PXR_CASE(double, 128) PXR_CASE(double, 16)
+  }
+#undef PXR_CASE
+  return fail(PXR_ERR_UNSUPPORTED, "Unsupported dimensions (CHANNELS=%d, dtype=%d, N_NODES=1).", C, dtype);
+}
+
+// -------------------------------------------------------------------------------- problem upload
+static int check_desc(const pxr_ba_desc* d) {
+  if (!d) return fail(PXR_ERR_INVALID_ARGUMENT, "desc is NULL");
+  if (d->n_cameras <= 0 || d->n_images <= 0 || d->n_points < 0 || d->n_obs < 0)
+    return fail(PXR_ERR_INVALID_ARGUMENT, "empty problem");
+  if (!d->cam_model || !d->cam_params || !d->cam_const_mask || !d->qvec || !d->tvec || !d->img_cam ||
+      !d->pose_const || !d->tvec_const_mask || (d->n_points && (!d->xyz || !d->point_const)) ||
+      (d->n_obs && (!d->obs_img || !d->obs_pt)) || !d->patches || !d->corner || !d->scale)
+    return fail(PXR_ERR_INVALID_ARGUMENT, "a required array is NULL");
+  if (!fm_supported(d->patch_dtype, d->channels))
+    return fail(PXR_ERR_UNSUPPORTED, "Unsupported dimensions (CHANNELS=%d, dtype=%d, N_NODES=1).", d->channels, d->patch_dtype);
+  if (d->ph < 1 || d->pw < 1) return fail(PXR_ERR_INVALID_ARGUMENT, "bad patch size");
+  for (int c = 0; c < d->n_cameras; ++c)
+    if (cam_num_params(d->cam_model[c]) == 0) return fail(PXR_ERR_UNSUPPORTED, "unsupported camera model id %d", d->cam_model[c]);
+  for (int i = 0; i < d->n_images; ++i)
+    if (d->img_cam[i] < 0 || d->img_cam[i] >= d->n_cameras) return fail(PXR_ERR_INVALID_ARGUMENT, "img_cam out of range");
+  const int64_t np = d->obs_patch ? d->n_patches : d->n_obs;
+  for (int64_t o = 0; o < d->n_obs; ++o) {
+    if (d->obs_img[o] < 0 || d->obs_img[o] >= d->n_images) return fail(PXR_ERR_INVALID_ARGUMENT, "obs_img out of range");
+    if (d->obs_pt[o] < 0 || d->obs_pt[o] >= d->n_points) return fail(PXR_ERR_INVALID_ARGUMENT, "obs_pt out of range");
+    if (o && d->obs_pt[o] < d->obs_pt[o - 1]) return fail(PXR_ERR_INVALID_ARGUMENT, "observations must be sorted by point index");
+    if (d->obs_patch && (d->obs_patch[o] < 0 || d->obs_patch[o] >= np)) return fail(PXR_ERR_INVALID_ARGUMENT, "obs_patch out of range");
+  }
+  if (!d->obs_patch && d->n_patches < d->n_obs) return fail(PXR_ERR_INVALID_ARGUMENT, "n_patches < n_obs with identity patch map");
+  return PXR_OK;
+}
+
+int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so) {
+  ctx = c;
+  PXR_TRY(check_desc(d));
+  if (ic) interp = *ic; else pxr_default_interp_config(&interp);
+  if (so) opt = *so; else pxr_default_ba_options(&opt);
+  if (interp.check_bounds) return fail(PXR_ERR_UNSUPPORTED, "check_bounds=true is not supported on this path");
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  n_cameras = d->n_cameras; n_images = d->n_images; n_points = d->n_points; n_obs = d->n_obs;
+  C = d->channels; ph = d->ph; pw = d->pw; dtype = d->patch_dtype; ups = d->upsampling_factor;
+  n_patches = d->obs_patch ? d->n_patches : std::max(d->n_patches, d->n_obs);
+  has_refs = d->refs != nullptr;
+  // ---- layout (same rules as BundleOptimizer::Parameterize*, resolved into masks by the caller)
+  K = 0;
+  for (int i = 0; i < n_cameras; ++i) K = std::max(K, cam_num_params(d->cam_model[i]));
+  dcmax = 6 + K;
+  juv_stride = 2 * (9 + K);
+  h_pose_off.assign(n_images, -1); h_intr_off.assign(n_cameras, -1); h_point_off.assign(n_points, -1);
+  int off = 0;
+  for (int i = 0; i < n_images; ++i) {
+    if (d->pose_const[i]) continue;
+    h_pose_off[i] = off;
+    off += 3 + (3 - __builtin_popcount(d->tvec_const_mask[i] & 7u));
+  }
+  std::vector<uint32_t> cmask(n_cameras);
+  for (int i = 0; i < n_cameras; ++i) {
+    const int k = cam_num_params(d->cam_model[i]);
+    const uint32_t full = (1u << k) - 1u;
+    cmask[i] = d->cam_const_mask[i] & full;
+    if (cmask[i] == full) continue;
+    h_intr_off[i] = off;
+    off += k - __builtin_popcount(cmask[i]);
+  }
+  nc = off;
+  int64_t po = off;
+  for (int64_t p = 0; p < n_points; ++p) if (!d->point_const[p]) { h_point_off[p] = po; po += 3; }
+  nl = (int64_t)po;
+  h_pt_begin.assign(n_points + 1, 0);
+  for (int64_t o = 0; o < n_obs; ++o) h_pt_begin[d->obs_pt[o] + 1]++;
+  for (int64_t p = 0; p < n_points; ++p) h_pt_begin[p + 1] += h_pt_begin[p];
+  if ((int64_t)nc * nc * 8 > (int64_t)40e9) return fail(PXR_ERR_UNSUPPORTED, "reduced camera system too large for the dense path (nc=%d)", nc);
+
+  double h2d = 0;
+  auto up = [&](auto& buf, const auto* host, size_t n) -> int { h2d += n * sizeof(*host); return buf.upload(host, n, s); };
+  PXR_TRY(up(obs_img, d->obs_img, n_obs));
+  PXR_TRY(up(obs_pt, d->obs_pt, n_obs));
+  if (d->obs_patch) PXR_TRY(up(obs_patch, d->obs_patch, n_obs));
+  PXR_TRY(up(img_cam, d->img_cam, n_images));
+  PXR_TRY(up(cam_model, d->cam_model, n_cameras));
+  PXR_TRY(up(cam_mask, cmask.data(), n_cameras));
+  PXR_TRY(up(tmask, d->tvec_const_mask, n_images));
+  PXR_TRY(up(pose_off, h_pose_off.data(), n_images));
+  PXR_TRY(up(intr_off, h_intr_off.data(), n_cameras));
+  PXR_TRY(up(point_off, h_point_off.data(), n_points));
+  PXR_TRY(up(pt_begin, h_pt_begin.data(), n_points + 1));
+  PXR_TRY(up(corner, d->corner, (size_t)n_patches * 2));
+  PXR_TRY(up(scale, d->scale, (size_t)n_patches * 2));
+  if (has_refs) PXR_TRY(up(refs, d->refs, (size_t)n_points * C));
+  const size_t esz = dtype == PXR_F16 ? 2 : (dtype == PXR_F32 ? 4 : 8);
+  const size_t pbytes = (size_t)n_patches * ph * pw * C * esz;
+  if (d->patches_on_device) {
+    d_patches = (const uint8_t*)d->patches;
+  } else {
+    PXR_TRY(patches_owned.alloc(pbytes));
+    PXR_CUDA(cudaMemcpyAsync(patches_owned.p, d->patches, pbytes, cudaMemcpyHostToDevice, s));
+    h2d += pbytes;
+    d_patches = patches_owned.p;
+  }
+  for (int k = 0; k < 2; ++k) {
+    PXR_TRY(cam[k].upload(d->cam_params, (size_t)n_cameras * kMaxK, s));
+    PXR_TRY(q[k].upload(d->qvec, (size_t)n_images * 4, s));
+    PXR_TRY(t[k].upload(d->tvec, (size_t)n_images * 3, s));
+    PXR_TRY(X[k].upload(d->xyz, (size_t)n_points * 3, s));
+  }
+  h2d += ((size_t)n_cameras * kMaxK + n_images * 7 + n_points * 3) * 8.0;
+  cur = 0;
+  // per-observation and linearisation buffers
+  PXR_TRY(uv.alloc((size_t)n_obs * 2));
+  PXR_TRY(obs_out.alloc((size_t)n_obs * 8));
+  PXR_TRY(juv.alloc((size_t)n_obs * juv_stride));
+  PXR_TRY(Hcc.alloc((size_t)nc * nc)); PXR_TRY(gc.alloc(nc));
+  PXR_TRY(Hpp.alloc((size_t)n_points * 9)); PXR_TRY(gp.alloc((size_t)n_points * 3));
+  PXR_TRY(W.alloc((size_t)n_obs * dcmax * 3)); PXR_TRY(Wcols.alloc((size_t)n_obs * dcmax)); PXR_TRY(Wdc.alloc(n_obs));
+  PXR_TRY(S.alloc((size_t)nc * nc)); PXR_TRY(rhs.alloc(nc));
+  PXR_TRY(diag.alloc(nl)); PXR_TRY(jscale.alloc(nl)); PXR_TRY(D2.alloc(nl)); PXR_TRY(delta.alloc(nl));
+  PXR_TRY(partials.alloc(fm_max_partials(ctx)));
+  PXR_TRY(scalars.alloc(16));
+  PXR_TRY(flags.alloc(4));
+  PXR_TRY(Hpp.zero(s)); PXR_TRY(gp.zero(s)); PXR_TRY(obs_out.zero(s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  h2d_bytes = h2d;
+  return PXR_OK;
+}
+
+// -------------------------------------------------------------------------------- evaluation
+int BA::project(int set, bool jac, double* xy_out) {
+  ProjectArgs a;
+  a.obs_img = obs_img.p; a.obs_pt = obs_pt.p; a.obs_patch = obs_patch.p;
+  a.img_cam = img_cam.p; a.cam_model = cam_model.p;
+  a.cam_params = cam[set].p; a.qvec = q[set].p; a.tvec = t[set].p; a.xyz = X[set].p;
+  a.corner = corner.p; a.scale = scale.p; a.ups = ups;
+  a.obs_begin = 0; a.obs_end = n_obs;
+  a.uv = uv.p; a.xy = xy_out; a.juv = jac ? juv.p : nullptr; a.juv_stride = juv_stride; a.juv_k = K;
+  if (n_obs == 0) return PXR_OK;
+  if (jac) PXR_LAUNCH(ctx, ba_project_kernel<true>, (unsigned)cdiv(n_obs, 128), 128, 0, a);
+  else PXR_LAUNCH(ctx, ba_project_kernel<false>, (unsigned)cdiv(n_obs, 128), 128, 0, a);
+  PXR_CUDA(cudaGetLastError());
+  return PXR_OK;
+}
+
+int BA::fm(int mode, double* residuals_out, double* cost_dev /* device scalar */) {
+  FmEvalArgs a;
+  a.uv = uv.p; a.item_patch = obs_patch.p; a.item_ref = obs_pt.p;
+  a.patches = d_patches; a.ph = ph; a.pw = pw;
+  a.refs = has_refs ? refs.p : nullptr;
+  a.begin = 0; a.end = n_obs;
+  a.out = obs_out.p; a.residuals = residuals_out; a.desc = nullptr;
+  a.cost_partials = partials.p;
+  a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
+  a.l2_normalize = interp.l2_normalize;
+  int np = 0;
+  if (n_obs > 0) {
+    PXR_TRY(launch_fm_eval(ctx, dtype, C, mode, interp.use_float_simd != 0, a, &np));
+    PXR_LAUNCH(ctx, reduce_partials_kernel, 1, 1024, 0, partials.p, (int64_t)np, cost_dev);
+  } else {
+    PXR_CUDA(cudaMemsetAsync(cost_dev, 0, 8, ctx->stream));
+  }
+  return PXR_OK;
+}
+
+// cost (and with jac the full linearisation) at parameter set `set`; returns the global cost
+int BA::evaluate(int set, bool jac, double* cost_out) {
+  PXR_TRY(project(set, jac, nullptr));
+  PXR_TRY(fm(jac ? 1 : 0, nullptr, scalars.p + 0));
+  if (jac) PXR_TRY(build());
+  PXR_TRY(allreduce_f64(ctx, scalars.p + 0, 1));
+  double c = 0;
+  PXR_CUDA(cudaMemcpyAsync(&c, scalars.p + 0, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  *cost_out = c;
+  return PXR_OK;
+}
+
+BADev BA::dev() {
+  BADev d;
+  d.n_cameras = n_cameras; d.n_images = n_images; d.K = K; d.n_points = n_points; d.n_obs = n_obs;
+  d.nc = nc; d.nl = (int)nl; d.dcmax = dcmax; d.juv_stride = juv_stride;
+  d.obs_img = obs_img.p; d.obs_pt = obs_pt.p; d.img_cam = img_cam.p; d.cam_model = cam_model.p;
+  d.cam_mask = cam_mask.p; d.tmask = tmask.p; d.pose_off = pose_off.p; d.intr_off = intr_off.p;
+  d.point_off = point_off.p; d.pt_begin = pt_begin.p; d.obs_out = obs_out.p; d.juv = juv.p;
+  d.Hcc = Hcc.p; d.gc = gc.p; d.Hpp = Hpp.p; d.gp = gp.p; d.W = W.p; d.Wcols = Wcols.p; d.Wdc = Wdc.p;
+  d.loss.type = opt.loss_type; d.loss.a = opt.loss_scale;
+  return d;
+}
+
+int BA::build() {
+  PXR_TRY(Hcc.zero(ctx->stream));
+  PXR_TRY(gc.zero(ctx->stream));
+  if (n_points > 0) PXR_LAUNCH(ctx, ba_build_kernel, (unsigned)cdiv(n_points, 128), 128, 0, dev());
+  // multi-GPU: camera blocks and gradient are sums over all ranks' observations
+  PXR_TRY(allreduce_f64(ctx, Hcc.p, (size_t)nc * nc));
+  PXR_TRY(allreduce_f64(ctx, gc.p, nc));
+  const int64_t n = std::max<int64_t>(nc, n_points);
+  if (n > 0) PXR_LAUNCH(ctx, ba_diag_kernel, (unsigned)cdiv(n, 256), 256, 0, dev(), diag.p);
+  PXR_CUDA(cudaGetLastError());
+  return PXR_OK;
+}
+
+// One LM step attempt at the current linearisation: fills delta, returns validity and model cost change
+int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
+  cudaStream_t s = ctx->stream;
+  BADev d = dev();
+  if (nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, D2.p, nl, radius,
+                         opt.min_lm_diagonal, opt.max_lm_diagonal);
+  PXR_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), s));
+  if (ctx->world <= 1) {
+    if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p, gc.p, D2.p, S.p, rhs.p, nc);
+  } else {
+    // Schur contributions are per-rank partial sums: accumulate them in a zeroed buffer, allreduce,
+    // then add the (already global) damped Hcc.  One NCCL allreduce of [S | rhs] per LM attempt.
+    PXR_CUDA(cudaMemsetAsync(S.p, 0, (size_t)nc * nc * 8, s));
+    PXR_CUDA(cudaMemsetAsync(rhs.p, 0, (size_t)nc * 8, s));
+  }
+  if (n_points > 0) PXR_LAUNCH(ctx, ba_schur_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, S.p, rhs.p, flags.p);
+  if (ctx->world > 1) {
+    PXR_TRY(allreduce_f64(ctx, S.p, (size_t)nc * nc));
+    PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
+    PXR_LAUNCH(ctx, ba_add_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p, gc.p, D2.p, S.p, rhs.p, nc);
+  }
+  const int nb = (int)cdiv(nc, kNB);
+  for (int k = 0; k < nb; ++k) {
+    PXR_LAUNCH(ctx, chol_panel_kernel, nb - k, kNB * kNB, 0, S.p, nc, k, flags.p + 1);
+    const int rem = nb - (k + 1);
+    if (rem > 0) PXR_LAUNCH(ctx, chol_update_kernel, rem * (rem + 1) / 2, kNB * kNB, 0, S.p, nc, k);
+  }
+  if (nc > 0) {
+    PXR_LAUNCH(ctx, chol_solve_kernel, 1, 1024, 0, S.p, rhs.p, nc);
+    PXR_CUDA(cudaMemcpyAsync(delta.p, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
+  if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points, 128), 128, 0, d, D2.p, delta.p, scalars.p + 4);
+  PXR_TRY(allreduce_f64(ctx, scalars.p + 4, 1));
+  if (nc > 0) PXR_LAUNCH(ctx, ba_cam_model_kernel, (unsigned)cdiv(nc, 256), 256, 0, Hcc.p, gc.p, delta.p, nc, scalars.p + 4);
+  PXR_CUDA(cudaGetLastError());
+  double acc = 0;
+  int fl[4];
+  PXR_CUDA(cudaMemcpyAsync(&acc, scalars.p + 4, 8, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaMemcpyAsync(fl, flags.p, sizeof(fl), cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  const bool solved = fl[0] == 0 && fl[1] == 0 && std::isfinite(acc);
+  *model_cost_change = -acc;
+  *valid = solved && (*model_cost_change > 0.0);
+  return PXR_OK;
+}
+
+// candidate (other set) = Plus(current, delta); returns ||step|| and ||x|| (ambient)
+int BA::apply_step(double* step_norm, double* x_norm) {
+  PlusArgs a;
+  a.n_cameras = n_cameras; a.n_images = n_images; a.n_points = n_points;
+  a.cam_model = cam_model.p; a.cam_mask = cam_mask.p; a.tmask = tmask.p;
+  a.pose_off = pose_off.p; a.intr_off = intr_off.p; a.point_off = point_off.p;
+  a.cam = cam[cur].p; a.q = q[cur].p; a.t = t[cur].p; a.X = X[cur].p;
+  a.cam_o = cam[1 - cur].p; a.q_o = q[1 - cur].p; a.t_o = t[1 - cur].p; a.X_o = X[1 - cur].p;
+  a.delta = delta.p; a.acc = scalars.p + 4;
+  PXR_CUDA(cudaMemsetAsync(scalars.p + 5, 0, 2 * 8, ctx->stream));
+  const int64_t n = std::max<int64_t>(std::max<int64_t>(n_points, n_images), n_cameras);
+  PXR_LAUNCH(ctx, ba_plus_kernel, (unsigned)cdiv(n, 128), 128, 0, a);
+  PXR_CUDA(cudaGetLastError());
+  if (step_norm || x_norm) {
+    if (ctx->world > 1) {
+      // points are sharded, cameras replicated: only the point part must be summed. The norms are
+      // used for parameter_tolerance only; with world>1 they are reported per rank.
+    }
+    double v[2];
+    PXR_CUDA(cudaMemcpyAsync(v, scalars.p + 5, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (step_norm) *step_norm = std::sqrt(v[0]);
+    if (x_norm) *x_norm = std::sqrt(v[1]);
+  }
+  return PXR_OK;
+}
+
+int BA::inner_iterations(int set) {
+  InnerArgs a;
+  a.n_points = n_points; a.point_off = point_off.p; a.pt_begin = pt_begin.p;
+  a.obs_img = obs_img.p; a.obs_patch = obs_patch.p; a.img_cam = img_cam.p; a.cam_model = cam_model.p;
+  a.cam_params = cam[set].p; a.qvec = q[set].p; a.tvec = t[set].p; a.xyz = X[set].p;
+  a.corner = corner.p; a.scale = scale.p; a.ups = ups;
+  a.patches = d_patches; a.ph = ph; a.pw = pw;
+  a.refs = has_refs ? refs.p : nullptr;
+  a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
+  a.l2_normalize = interp.l2_normalize;
+  if (n_points == 0) return PXR_OK;
+  return launch_inner(ctx, dtype, C, interp.use_float_simd != 0, a);
+}
+
+int BA::step_norm_between_sets(double* out) {
+  cudaStream_t s = ctx->stream;
+  PXR_CUDA(cudaMemsetAsync(scalars.p + 9, 0, 8, s));
+  auto run = [&](const double* a, const double* b, int64_t n) {
+    if (n > 0) PXR_LAUNCH(ctx, diff_norm_kernel, (unsigned)cdiv(n, 256), 256, 0, a, b, n, scalars.p + 9);
+  };
+  run(cam[0].p, cam[1].p, (int64_t)n_cameras * kMaxK);
+  run(q[0].p, q[1].p, (int64_t)n_images * 4);
+  run(t[0].p, t[1].p, (int64_t)n_images * 3);
+  run(X[0].p, X[1].p, n_points * 3);
+  double v = 0;
+  PXR_CUDA(cudaMemcpyAsync(&v, scalars.p + 9, 8, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  *out = std::sqrt(v);
+  return PXR_OK;
+}
+
+int BA::gradient_max_norm(double* out) {
+  PXR_CUDA(cudaMemsetAsync(scalars.p + 8, 0, 8, ctx->stream));
+  const int64_t n = std::max<int64_t>(nc, n_points);
+  if (n > 0) PXR_LAUNCH(ctx, ba_gradmax_kernel, (unsigned)cdiv(n, 256), 256, 0, dev(), scalars.p + 8);
+  PXR_CUDA(cudaMemcpyAsync(out, scalars.p + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PXR_OK;
+}
+
+// -------------------------------------------------------------------------------- LM driver
+// Mirrors ceres::internal::TrustRegionMinimizer::Minimize (Ceres 2.1) with
+// LevenbergMarquardtStrategy, monotonic steps, Jacobi scaling, inner iterations.
+int BA::solve(pxr_summary* sum) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  const int64_t launches0 = ctx->launches;
+  std::vector<pxr_iteration_summary> its;
+  int term = 1;
+  std::string message = "Maximum number of iterations reached.";
+  int n_succ = 0, n_unsucc = 0, n_inner = 0;
+
+  double x_cost = 0, candidate_cost = 0, model_cost_change = 0;
+  double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
+  bool inner_enabled = opt.use_inner_iterations != 0;
+  int num_invalid = 0;
+
+  // ---- IterationZero
+  PXR_TRY(evaluate(cur, true, &x_cost));
+  if (!std::isfinite(x_cost)) return fail(PXR_ERR_NUMERIC, "initial cost is not finite");
+  if (nl > 0) PXR_LAUNCH(ctx, ba_scale_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, nl, opt.jacobi_scaling);
+  pxr_iteration_summary it;
+  std::memset(&it, 0, sizeof(it));
+  it.cost = x_cost;
+  PXR_TRY(gradient_max_norm(&it.gradient_max_norm));
+  const double initial_cost = x_cost;
+  double minimum_cost = x_cost;
+  double current_cost = x_cost;
+  double x_norm = 0;
+  bool done = false;
+  auto it_start = clk::now();
+
+  auto finalize = [&]() -> bool {
+    if (it.step_is_successful) { ++n_succ; if (x_cost < minimum_cost) minimum_cost = x_cost; }
+    else if (it.iteration > 0) ++n_unsucc;
+    it.trust_region_radius = radius;
+    it.iteration_time_s = std::chrono::duration<double>(clk::now() - it_start).count();
+    its.push_back(it);
+    if (it.iteration >= opt.max_num_iterations) { term = 1; message = "Maximum number of iterations reached."; return false; }
+    if (it.gradient_max_norm <= opt.gradient_tolerance) { term = 0; message = "Gradient tolerance reached."; return false; }
+    if (radius < opt.min_trust_region_radius) { term = 0; message = "Minimum trust region radius reached."; return false; }
+    return true;
+  };
+
+  while (!done && finalize()) {
+    it_start = clk::now();
+    const double prev_gmax = it.gradient_max_norm;
+    const int iteration = it.iteration + 1;
+    std::memset(&it, 0, sizeof(it));
+    it.iteration = iteration;
+
+    bool valid = false;
+    PXR_TRY(compute_step(radius, &valid, &model_cost_change));
+    it.linear_solver_iterations = 1;
+    it.step_is_valid = valid;
+    if (!valid) {
+      if (++num_invalid >= opt.max_num_consecutive_invalid_steps) {
+        term = 2; message = "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps";
+        break;
+      }
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      it.cost = x_cost; it.gradient_max_norm = prev_gmax;
+      continue;
+    }
+    num_invalid = 0;
+
+    double step_norm = 0;
+    PXR_TRY(apply_step(&step_norm, &x_norm));
+    PXR_TRY(evaluate(1 - cur, false, &candidate_cost));
+    if (!std::isfinite(candidate_cost)) candidate_cost = std::numeric_limits<double>::max();
+
+    bool inner_useful = false;
+    if (inner_enabled && candidate_cost < std::numeric_limits<double>::max()) {
+      ++n_inner;
+      PXR_TRY(inner_iterations(1 - cur));
+      double inner_cost = 0;
+      PXR_TRY(evaluate(1 - cur, false, &inner_cost));
+      if (std::isfinite(inner_cost)) {
+        model_cost_change += candidate_cost - inner_cost;
+        inner_useful = inner_cost < x_cost;
+        const double rel = 1.0 - inner_cost / candidate_cost;
+        inner_enabled = rel > opt.inner_iteration_tolerance;
+        candidate_cost = inner_cost;
+        PXR_TRY(step_norm_between_sets(&step_norm));
+      }
+    }
+    it.step_norm = step_norm;
+    if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+      term = 0; message = "Parameter tolerance reached."; break;
+    }
+    it.cost_change = x_cost - candidate_cost;
+    if (std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) {
+      term = 0; message = "Function tolerance reached."; break;
+    }
+    it.relative_decrease = (current_cost - candidate_cost) / model_cost_change;
+    const bool ok = inner_useful || it.relative_decrease > opt.min_relative_decrease;
+    if (ok) {
+      cur = 1 - cur;
+      PXR_TRY(evaluate(cur, true, &x_cost));
+      it.cost = x_cost;
+      PXR_TRY(gradient_max_norm(&it.gradient_max_norm));
+      it.step_is_successful = 1;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+      radius = std::min(opt.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      current_cost = candidate_cost;
+    } else {
+      it.step_is_successful = 0;
+      it.cost = candidate_cost;
+      it.gradient_max_norm = prev_gmax;
+      radius /= decrease_factor; decrease_factor *= 2.0;
+    }
+  }
+  if (x_cost < minimum_cost) minimum_cost = x_cost;
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (sum) {
+    sum->initial_cost = initial_cost; sum->final_cost = minimum_cost;
+    sum->num_residual_blocks = (int32_t)n_obs; sum->num_residuals = n_obs * C;
+    sum->num_successful_steps = n_succ; sum->num_unsuccessful_steps = n_unsucc;
+    sum->num_inner_iteration_steps = n_inner; sum->termination_type = term;
+    sum->solve_time_s = std::chrono::duration<double>(clk::now() - t0).count();
+    sum->total_time_s = sum->solve_time_s;
+    sum->h2d_bytes = h2d_bytes; sum->d2h_bytes = 0;
+    sum->num_iterations = (int32_t)its.size();
+    const int m = std::min<int>((int)its.size(), sum->iterations ? sum->iterations_capacity : 0);
+    for (int i = 0; i < m; ++i) sum->iterations[i] = its[i];
+    sum->kernel_launches = ctx->launches - launches0;
+    std::snprintf(sum->message, sizeof(sum->message), "%s", message.c_str());
+  }
+  return PXR_OK;
+}
+
+int BA::read_params(double* cam_o, double* q_o, double* t_o, double* X_o) {
+  cudaStream_t s = ctx->stream;
+  if (cam_o) PXR_CUDA(cudaMemcpyAsync(cam_o, cam[cur].p, (size_t)n_cameras * kMaxK * 8, cudaMemcpyDeviceToHost, s));
+  if (q_o) PXR_CUDA(cudaMemcpyAsync(q_o, q[cur].p, (size_t)n_images * 4 * 8, cudaMemcpyDeviceToHost, s));
+  if (t_o) PXR_CUDA(cudaMemcpyAsync(t_o, t[cur].p, (size_t)n_images * 3 * 8, cudaMemcpyDeviceToHost, s));
+  if (X_o) PXR_CUDA(cudaMemcpyAsync(X_o, X[cur].p, (size_t)n_points * 3 * 8, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  return PXR_OK;
+}
+
+}  // namespace pxr
+
+using namespace pxr;
+
+extern "C" {
+
+int pxr_ba_create(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
+                  const pxr_solver_options* opt, pxr_ba** out) {
+  if (!ctx || !out) return fail(PXR_ERR_INVALID_ARGUMENT, "ctx/out is NULL");
+  BA* b = new BA();
+  const int rc = b->create(ctx, desc, interp, opt);
+  if (rc != PXR_OK) { delete b; return rc; }
+  *out = reinterpret_cast<pxr_ba*>(b);
+  return PXR_OK;
+}
+int pxr_ba_destroy(pxr_ba* ba) {
+  if (ba) { BA* b = reinterpret_cast<BA*>(ba); cudaSetDevice(b->ctx->device); delete b; }
+  return PXR_OK;
+}
+int pxr_ba_solve(pxr_ba* ba, pxr_summary* summary) {
+  if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
+  return reinterpret_cast<BA*>(ba)->solve(summary);
+}
+int pxr_ba_read_params(pxr_ba* ba, double* cam_params, double* qvec, double* tvec, double* xyz) {
+  if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
+  return reinterpret_cast<BA*>(ba)->read_params(cam_params, qvec, tvec, xyz);
+}
+int pxr_ba_run(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
+               const pxr_solver_options* opt, pxr_summary* summary) {
+  const auto t0 = std::chrono::steady_clock::now();
+  pxr_ba* h = nullptr;
+  PXR_TRY(pxr_ba_create(ctx, desc, interp, opt, &h));
+  BA* b = reinterpret_cast<BA*>(h);
+  int rc = b->solve(summary);
+  if (rc == PXR_OK) rc = b->read_params(desc->cam_params, desc->qvec, desc->tvec, desc->xyz);
+  if (summary) {
+    summary->d2h_bytes = ((double)desc->n_cameras * kMaxK + desc->n_images * 7.0 + desc->n_points * 3.0) * 8.0;
+    summary->total_time_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  pxr_ba_destroy(h);
+  return rc;
+}
+
+int pxr_ba_evaluate(pxr_ba* ba, double* sq_norm, double* gtr, double* gtg, double* xy, double* residuals,
+                    double* cost) {
+  if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
+  BA* b = reinterpret_cast<BA*>(ba);
+  pxr_ctx* ctx = b->ctx;
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double> dxy, dres;
+  if (xy) PXR_TRY(dxy.alloc((size_t)b->n_obs * 2));
+  if (residuals) PXR_TRY(dres.alloc((size_t)b->n_obs * b->C));
+  PXR_TRY(b->project(b->cur, true, dxy.p));
+  PXR_TRY(b->fm(1, dres.p, b->scalars.p + 0));
+  std::vector<double> out((size_t)b->n_obs * 8);
+  double c = 0;
+  PXR_CUDA(cudaMemcpyAsync(out.data(), b->obs_out.p, out.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PXR_CUDA(cudaMemcpyAsync(&c, b->scalars.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (xy) PXR_CUDA(cudaMemcpyAsync(xy, dxy.p, (size_t)b->n_obs * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (residuals) PXR_CUDA(cudaMemcpyAsync(residuals, dres.p, (size_t)b->n_obs * b->C * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int64_t o = 0; o < b->n_obs; ++o) {
+    const double* r = &out[(size_t)o * 8];
+    if (sq_norm) sq_norm[o] = r[0];
+    if (gtr) { gtr[2 * o] = r[1]; gtr[2 * o + 1] = r[2]; }
+    if (gtg) { gtg[3 * o] = r[3]; gtg[3 * o + 1] = r[4]; gtg[3 * o + 2] = r[5]; }
+  }
+  if (cost) *cost = c;
+  return PXR_OK;
+}
+
+
+// Introspection for parity tests: linearise at the current parameters and compute one LM step at
+// `radius` (Jacobi scaling from this linearisation, as in iteration 0).  Any output may be NULL.
+int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc, double* gc, double* Hpp,
+                           double* gp, double* S, double* rhs, double* delta, double* model_cost_change) {
+  if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
+  BA* b = reinterpret_cast<BA*>(ba);
+  pxr_ctx* ctx = b->ctx;
+  cudaStream_t s = ctx->stream;
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  double c = 0;
+  PXR_TRY(b->evaluate(b->cur, true, &c));
+  if (cost) *cost = c;
+  if (b->nl > 0) PXR_LAUNCH(ctx, ba_scale_kernel, (unsigned)cdiv(b->nl, 256), 256, 0, b->diag.p, b->jscale.p, b->nl, b->opt.jacobi_scaling);
+  const size_t nc = b->nc;
+  if (Hcc) PXR_CUDA(cudaMemcpyAsync(Hcc, b->Hcc.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));
+  if (gc) PXR_CUDA(cudaMemcpyAsync(gc, b->gc.p, nc * 8, cudaMemcpyDeviceToHost, s));
+  if (Hpp) PXR_CUDA(cudaMemcpyAsync(Hpp, b->Hpp.p, (size_t)b->n_points * 72, cudaMemcpyDeviceToHost, s));
+  if (gp) PXR_CUDA(cudaMemcpyAsync(gp, b->gp.p, (size_t)b->n_points * 24, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  if (S || rhs) {
+    // the damped Schur system before factorisation: rerun the assembly part only
+    BADev d = b->dev();
+    if (b->nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(b->nl, 256), 256, 0, b->diag.p, b->jscale.p, b->D2.p, b->nl, radius,
+                              b->opt.min_lm_diagonal, b->opt.max_lm_diagonal);
+    if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, b->Hcc.p, b->gc.p, b->D2.p, b->S.p, b->rhs.p, (int)nc);
+    PXR_CUDA(cudaMemsetAsync(b->flags.p, 0, 4 * sizeof(int), s));
+    if (b->n_points > 0) PXR_LAUNCH(ctx, ba_schur_kernel, (unsigned)cdiv(b->n_points * 32, 256), 256, 0, d, b->D2.p, b->S.p, b->rhs.p, b->flags.p);
+    if (S) PXR_CUDA(cudaMemcpyAsync(S, b->S.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));
+    if (rhs) PXR_CUDA(cudaMemcpyAsync(rhs, b->rhs.p, nc * 8, cudaMemcpyDeviceToHost, s));
+    PXR_CUDA(cudaStreamSynchronize(s));
+  }
+  bool valid = false;
+  double mcc = 0;
+  PXR_TRY(b->compute_step(radius, &valid, &mcc));
+  if (delta) PXR_CUDA(cudaMemcpyAsync(delta, b->delta.p, (size_t)b->nl * 8, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  if (model_cost_change) *model_cost_change = mcc;
+  return PXR_OK;
+}
+
+// Runs inner iterations on the current parameter set (parity tests).
+int pxr_ba_debug_inner_iterations(pxr_ba* ba) {
+  if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
+  BA* b = reinterpret_cast<BA*>(ba);
+  PXR_CUDA(cudaSetDevice(b->ctx->device));
+  PXR_TRY(b->inner_iterations(b->cur));
+  PXR_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  return PXR_OK;
+}
+
+int pxr_ba_time_stage(pxr_ba* ba, int stage, int iters, double* ms_per_launch) {
+  if (!ba || iters < 1 || !ms_per_launch) return fail(PXR_ERR_INVALID_ARGUMENT, "bad arguments");
+  BA* b = reinterpret_cast<BA*>(ba);
+  pxr_ctx* ctx = b->ctx;
+  cudaStream_t s = ctx->stream;
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  cudaEvent_t e0, e1;
+  PXR_CUDA(cudaEventCreate(&e0)); PXR_CUDA(cudaEventCreate(&e1));
+  double c;
+  PXR_TRY(b->project(b->cur, true, nullptr));  // uv for the current parameters
+  PXR_CUDA(cudaStreamSynchronize(s));
+  PXR_CUDA(cudaEventRecord(e0, s));
+  for (int i = 0; i < iters; ++i) {
+    if (stage == 0) PXR_TRY(b->fm(1, nullptr, b->scalars.p));
+    else if (stage == 1) PXR_TRY(b->fm(0, nullptr, b->scalars.p));
+    else if (stage == 3) PXR_TRY(b->project(b->cur, true, nullptr));
+    else if (stage == 4) PXR_TRY(b->build());
+    else if (stage == 5) PXR_TRY(b->inner_iterations(1 - b->cur));
+    else PXR_TRY(b->evaluate(b->cur, true, &c));
+  }
+  PXR_CUDA(cudaEventRecord(e1, s));
+  PXR_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  PXR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = (double)ms / iters;
+  return PXR_OK;
+}
+
+}  // extern "C"

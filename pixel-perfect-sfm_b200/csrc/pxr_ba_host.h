@@ -1,0 +1,61 @@
+// pxr_ba_host.h — host-side state of one featuremetric BA problem resident on the device.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "pxr_ba_kernels.cuh"
+#include "pxr_fm_eval.cuh"
+#include "pxr_inner.cuh"
+#include "pxr_internal.h"
+
+namespace pxr {
+
+int fm_supported(int dtype, int C);
+int fm_max_partials(pxr_ctx* ctx);
+int launch_fm_eval(pxr_ctx* ctx, int dtype, int C, int mode, bool float_simd, const FmEvalArgs& a, int* n_partials);
+int launch_inner(pxr_ctx* ctx, int dtype, int C, bool float_simd, const InnerArgs& a);
+
+struct BA {
+  pxr_ctx* ctx = nullptr;
+  pxr_interp_config interp;
+  pxr_solver_options opt;
+  // sizes
+  int n_cameras = 0, n_images = 0, K = 0, C = 0, ph = 0, pw = 0, dtype = 0;
+  int64_t n_points = 0, n_obs = 0, n_patches = 0, nl = 0;
+  int nc = 0, dcmax = 0, juv_stride = 0;
+  double ups = 1.0;
+  bool has_refs = false;
+  double h2d_bytes = 0;
+  // host layout
+  std::vector<int32_t> h_pose_off, h_intr_off;
+  std::vector<int64_t> h_point_off, h_pt_begin;
+  // device: topology
+  DevBuf<int32_t> obs_img, img_cam, cam_model, pose_off, intr_off, corner, Wcols, Wdc;
+  DevBuf<int64_t> obs_pt, obs_patch, point_off, pt_begin;
+  DevBuf<uint32_t> cam_mask;
+  DevBuf<uint8_t> tmask, patches_owned;
+  DevBuf<double> scale, refs;
+  const uint8_t* d_patches = nullptr;
+  // device: parameters (two sets: current / candidate)
+  DevBuf<double> cam[2], q[2], t[2], X[2];
+  int cur = 0;
+  // device: per-observation and linearisation
+  DevBuf<double> uv, obs_out, juv, Hcc, gc, Hpp, gp, W, S, rhs, diag, jscale, D2, delta, partials, scalars;
+  DevBuf<int> flags;
+
+  int create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so);
+  BADev dev();
+  int project(int set, bool jac, double* xy_out);
+  int fm(int mode, double* residuals_out, double* cost_dev);
+  int build();
+  int evaluate(int set, bool jac, double* cost_out);
+  int compute_step(double radius, bool* valid, double* model_cost_change);
+  int apply_step(double* step_norm, double* x_norm);
+  int gradient_max_norm(double* out);
+  int inner_iterations(int set);
+  int step_norm_between_sets(double* out);
+  int solve(pxr_summary* sum);
+  int read_params(double* cam_o, double* q_o, double* t_o, double* X_o);
+};
+
+}  // namespace pxr

@@ -1,0 +1,504 @@
+// pxr_ba_kernels.cuh — "geometric BA with a 2x2 weight per observation".
+//
+// After K1 has collapsed every residual block to (||r||^2, G^T r, G^T G), the normal equations of
+// the featuremetric BA are  J^T J = P^T (rho' G^T G) P,  J^T r = P^T (rho' G^T r)  with
+// P = d(uv)/d(theta) from K0.  These kernels replace what Ceres does inside ceres::Solve for
+// the reference (bundle_optimizer.h:224): block assembly, per-point Schur elimination
+// (SchurEliminator), the reduced camera system solve (DENSE_SCHUR / SPARSE_SCHUR are exact
+// factorizations -> dense Cholesky here), back-substitution, and the manifold Plus
+// (QuaternionManifold, SubsetManifold — bundle_optimizer.h:384-389,436-438).
+#pragma once
+#include "pxr_device.cuh"
+
+namespace pxr {
+
+constexpr int kMaxDc = 6 + kMaxK;
+
+struct BADev {
+  // sizes
+  int n_cameras, n_images, K;  // K = max #intrinsics in the problem (juv columns)
+  int64_t n_points, n_obs;
+  int nc, nl;                  // reduced camera system size, total tangent size
+  int dcmax;                   // 6 + K
+  int juv_stride;
+  // topology / masks
+  const int32_t* obs_img; const int64_t* obs_pt; const int32_t* img_cam; const int32_t* cam_model;
+  const uint32_t* cam_mask; const uint8_t* tmask;
+  const int32_t* pose_off; const int32_t* intr_off; const int64_t* point_off; const int64_t* pt_begin;
+  // per-observation data
+  const double* obs_out; const double* juv;
+  // linearisation
+  double* Hcc; double* gc; double* Hpp; double* gp; double* W; int32_t* Wcols; int32_t* Wdc;
+  LossParams loss;
+};
+
+__device__ __forceinline__ void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
+
+// K2: one thread per point. Builds Hpp, gp (no atomics), W per observation, and adds the camera
+// blocks J_c^T A' J_c / J_c^T b' into the dense Hcc (lower triangle) / gc with fp64 atomics.
+static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.n_points) return;
+  const bool pvar = d.point_off[p] >= 0;
+  double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+  const int Wd = 9 + d.K;
+  for (int64_t o = d.pt_begin[p]; o < d.pt_begin[p + 1]; ++o) {
+    const double* oo = d.obs_out + o * 8;
+    const double s = oo[0];
+    double rho[3];
+    loss_eval(d.loss, 1.0, s, rho);
+    const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
+    const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
+    const double* J = d.juv + o * (int64_t)d.juv_stride;  // rows: J[0..Wd), J[Wd..2Wd)
+    const int img = d.obs_img[o];
+    const int cam = d.img_cam[img];
+    // local camera-side columns
+    int cols[kMaxDc];
+    double Ju[kMaxDc], Jv[kMaxDc];
+    int dc = 0;
+    const int po = d.pose_off[img];
+    if (po >= 0) {
+      const uint32_t tm = d.tmask[img];
+      for (int k = 0; k < 3; ++k) { cols[dc] = po + k; Ju[dc] = J[k]; Jv[dc] = J[Wd + k]; ++dc; }
+      int la = 3;
+      for (int k = 0; k < 3; ++k) {
+        if (tm & (1u << k)) continue;
+        cols[dc] = po + la++; Ju[dc] = J[3 + k]; Jv[dc] = J[Wd + 3 + k]; ++dc;
+      }
+    }
+    const int io = d.intr_off[cam];
+    if (io >= 0) {
+      const uint32_t cm = d.cam_mask[cam];
+      const int Kc = cam_num_params(d.cam_model[cam]);
+      int la = 0;
+      for (int k = 0; k < Kc; ++k) {
+        if (cm & (1u << k)) continue;
+        cols[dc] = io + la++; Ju[dc] = J[9 + k]; Jv[dc] = J[Wd + 9 + k]; ++dc;
+      }
+    }
+    d.Wdc[o] = dc;
+    // A' J rows:  (AJu, AJv)[k] = A' * (Ju[k], Jv[k])
+    const double pu0 = J[6], pu1 = J[7], pu2 = J[8], pv0 = J[Wd + 6], pv1 = J[Wd + 7], pv2 = J[Wd + 8];
+    const double apu[3] = {auu * pu0 + auv * pv0, auu * pu1 + auv * pv1, auu * pu2 + auv * pv2};
+    const double apv[3] = {auv * pu0 + avv * pv0, auv * pu1 + avv * pv1, auv * pu2 + avv * pv2};
+    if (pvar) {
+      const double pu[3] = {pu0, pu1, pu2}, pv[3] = {pv0, pv1, pv2};
+      H[0] += pu[0] * apu[0] + pv[0] * apv[0];
+      H[1] += pu[0] * apu[1] + pv[0] * apv[1];
+      H[2] += pu[0] * apu[2] + pv[0] * apv[2];
+      H[3] += pu[1] * apu[1] + pv[1] * apv[1];
+      H[4] += pu[1] * apu[2] + pv[1] * apv[2];
+      H[5] += pu[2] * apu[2] + pv[2] * apv[2];
+      for (int k = 0; k < 3; ++k) g[k] += pu[k] * bu + pv[k] * bv;
+    }
+    double* Wo = d.W + o * (int64_t)d.dcmax * 3;
+    int32_t* Wc = d.Wcols + o * (int64_t)d.dcmax;
+    for (int a = 0; a < dc; ++a) {
+      Wc[a] = cols[a];
+      if (pvar) {
+        Wo[a * 3 + 0] = Ju[a] * apu[0] + Jv[a] * apv[0];
+        Wo[a * 3 + 1] = Ju[a] * apu[1] + Jv[a] * apv[1];
+        Wo[a * 3 + 2] = Ju[a] * apu[2] + Jv[a] * apv[2];
+      }
+      const double aju = auu * Ju[a] + auv * Jv[a], ajv = auv * Ju[a] + avv * Jv[a];
+      atomic_add_f64(&d.gc[cols[a]], Ju[a] * bu + Jv[a] * bv);
+      for (int b = 0; b <= a; ++b) {
+        const double v = Ju[b] * aju + Jv[b] * ajv;
+        const int ca = cols[a], cb = cols[b];  // cols ascending within an observation
+        atomic_add_f64(&d.Hcc[(int64_t)ca * d.nc + cb], v);
+      }
+    }
+  }
+  if (pvar) {
+    double* Hp = d.Hpp + p * 9;
+    Hp[0] = H[0]; Hp[1] = H[1]; Hp[2] = H[2]; Hp[3] = H[1]; Hp[4] = H[3]; Hp[5] = H[4];
+    Hp[6] = H[2]; Hp[7] = H[4]; Hp[8] = H[5];
+    d.gp[p * 3] = g[0]; d.gp[p * 3 + 1] = g[1]; d.gp[p * 3 + 2] = g[2];
+  }
+}
+
+// diag(J^T J) in local order: cameras from Hcc's diagonal, points from Hpp
+static __global__ void ba_diag_kernel(BADev d, double* diag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < d.nc) diag[i] = d.Hcc[i * d.nc + i];
+  const int64_t p = i;
+  if (p < d.n_points) {
+    const int64_t po = d.point_off[p];
+    if (po >= 0) { diag[po] = d.Hpp[p * 9]; diag[po + 1] = d.Hpp[p * 9 + 4]; diag[po + 2] = d.Hpp[p * 9 + 8]; }
+  }
+}
+
+// jacobi scaling (iteration 0): scale = 1/(1+sqrt(diag)) (ceres trust_region_minimizer.cc)
+static __global__ void ba_scale_kernel(const double* diag, double* scale, int64_t n, int enabled) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scale[i] = enabled ? 1.0 / (1.0 + sqrt(diag[i])) : 1.0;
+}
+// LM diagonal in unscaled variables: D2 = clamp(diag*scale^2, lo, hi) / (radius*scale^2)
+static __global__ void ba_d2_kernel(const double* diag, const double* scale, double* D2, int64_t n, double radius,
+                             double lo, double hi) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s2 = scale[i] * scale[i];
+  D2[i] = fmin(fmax(diag[i] * s2, lo), hi) / (radius * s2);
+}
+
+// S = Hcc + diag(D2c) (lower), rhs = -gc
+static __global__ void ba_init_reduced_kernel(const double* Hcc, const double* gc, const double* D2, double* S,
+                                       double* rhs, int nc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n2 = (int64_t)nc * nc;
+  if (i < n2) {
+    const int r = (int)(i / nc), c = (int)(i % nc);
+    double v = c <= r ? Hcc[i] : 0.0;
+    if (r == c) v += D2[r];
+    S[i] = v;
+  }
+  if (i < nc) rhs[i] = -gc[i];
+}
+
+__device__ __forceinline__ bool inv3_sym(const double* H, const double* D2, double inv[9]) {
+  const double a = H[0] + D2[0], b = H[1], c = H[2], dd = H[4] + D2[1], e = H[5], f = H[8] + D2[2];
+  if (!(a > 0.0)) return false;
+  const double l00 = sqrt(a), l10 = b / l00, l20 = c / l00;
+  const double t11 = dd - l10 * l10;
+  if (!(t11 > 0.0)) return false;
+  const double l11 = sqrt(t11), l21 = (e - l20 * l10) / l11;
+  const double t22 = f - l20 * l20 - l21 * l21;
+  if (!(t22 > 0.0)) return false;
+  const double l22 = sqrt(t22);
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  inv[0] = i00 * i00 + i10 * i10 + i20 * i20;
+  inv[1] = inv[3] = i10 * i11 + i20 * i21;
+  inv[2] = inv[6] = i20 * i22;
+  inv[4] = i11 * i11 + i21 * i21;
+  inv[5] = inv[7] = i21 * i22;
+  inv[8] = i22 * i22;
+  return true;
+}
+
+// K3: per-point Schur elimination, one warp per point.
+//   S[cols_i, cols_j] -= W_i (Hpp + D)^-1 W_j^T   (lower triangle only, fp64 atomics)
+//   rhs[cols_i]       += W_i (Hpp + D)^-1 gp
+static __global__ void __launch_bounds__(256) ba_schur_kernel(BADev d, const double* D2, double* S, double* rhs,
+                                                       int* fail_flag) {
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= d.n_points) return;
+  const int64_t po = d.point_off[p];
+  if (po < 0) return;
+  double inv[9];
+  if (!inv3_sym(d.Hpp + p * 9, D2 + po, inv)) { if (lane == 0) *fail_flag = 1; return; }
+  const double g0 = d.gp[p * 3], g1 = d.gp[p * 3 + 1], g2 = d.gp[p * 3 + 2];
+  const double ig[3] = {inv[0] * g0 + inv[1] * g1 + inv[2] * g2, inv[3] * g0 + inv[4] * g1 + inv[5] * g2,
+                        inv[6] * g0 + inv[7] * g1 + inv[8] * g2};
+  const int64_t ob = d.pt_begin[p], oe = d.pt_begin[p + 1];
+  const int L = (int)(oe - ob);
+  const int dcm = d.dcmax;
+  // rhs: entries (i, a)
+  for (int e = lane; e < L * dcm; e += 32) {
+    const int i = e / dcm, a = e % dcm;
+    const int64_t o = ob + i;
+    if (a >= d.Wdc[o]) continue;
+    const double* w = d.W + (o * dcm + a) * 3;
+    atomic_add_f64(&rhs[d.Wcols[o * dcm + a]], w[0] * ig[0] + w[1] * ig[1] + w[2] * ig[2]);
+  }
+  // S: entries (i, a, j, b) with col_i[a] >= col_j[b]
+  const int64_t total = (int64_t)L * dcm * L * dcm;
+  for (int64_t e = lane; e < total; e += 32) {
+    const int b = (int)(e % dcm);
+    int64_t r = e / dcm;
+    const int j = (int)(r % L); r /= L;
+    const int a = (int)(r % dcm);
+    const int i = (int)(r / dcm);
+    const int64_t oi = ob + i, oj = ob + j;
+    if (a >= d.Wdc[oi] || b >= d.Wdc[oj]) continue;
+    const int ca = d.Wcols[oi * dcm + a], cb = d.Wcols[oj * dcm + b];
+    if (ca < cb) continue;
+    const double* wi = d.W + (oi * dcm + a) * 3;
+    const double* wj = d.W + (oj * dcm + b) * 3;
+    const double t0 = wi[0] * inv[0] + wi[1] * inv[3] + wi[2] * inv[6];
+    const double t1 = wi[0] * inv[1] + wi[1] * inv[4] + wi[2] * inv[7];
+    const double t2 = wi[0] * inv[2] + wi[1] * inv[5] + wi[2] * inv[8];
+    atomic_add_f64(&S[(int64_t)ca * d.nc + cb], -(t0 * wj[0] + t1 * wj[1] + t2 * wj[2]));
+  }
+}
+
+// ---------------------------------------------------------------- dense Cholesky (lower, in place)
+constexpr int kNB = 32;
+// Panel step k: every CTA factors the diagonal block A_kk redundantly in shared memory; CTA 0
+// writes L_kk, CTA b>0 solves its 32-row block  L_bk = A_bk L_kk^-T.
+static __global__ void __launch_bounds__(kNB* kNB) chol_panel_kernel(double* A, int n, int k, int* fail_flag) {
+  __shared__ double Lkk[kNB][kNB + 1];
+  __shared__ double Ab[kNB][kNB + 1];
+  __shared__ int bad;
+  const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;
+  const int k0 = k * kNB;
+  const int kb = min(kNB, n - k0);
+  if (threadIdx.x == 0) bad = 0;
+  Lkk[ty][tx] = (ty < kb && tx < kb && tx <= ty) ? A[(int64_t)(k0 + ty) * n + k0 + tx] : (ty == tx ? 1.0 : 0.0);
+  __syncthreads();
+  // unblocked right-looking Cholesky on the 32x32 block
+  for (int j = 0; j < kb; ++j) {
+    if (threadIdx.x == 0) {
+      const double dj = Lkk[j][j];
+      if (!(dj > 0.0) || !isfinite(dj)) { bad = 1; Lkk[j][j] = 1.0; } else Lkk[j][j] = sqrt(dj);
+    }
+    __syncthreads();
+    if (ty == 0 && tx > j && tx < kb) Lkk[tx][j] /= Lkk[j][j];
+    __syncthreads();
+    if (tx > j && ty > j && tx <= ty && ty < kb) Lkk[ty][tx] -= Lkk[ty][j] * Lkk[tx][j];
+    __syncthreads();
+  }
+  if (bad) { if (threadIdx.x == 0 && blockIdx.x == 0) *fail_flag = 1; return; }
+  const int b = blockIdx.x;
+  if (b == 0) {
+    if (ty < kb && tx < kb && tx <= ty) A[(int64_t)(k0 + ty) * n + k0 + tx] = Lkk[ty][tx];
+    return;
+  }
+  const int r0 = k0 + b * kNB;
+  const int rb = min(kNB, n - r0);
+  Ab[ty][tx] = (ty < rb && tx < kb) ? A[(int64_t)(r0 + ty) * n + k0 + tx] : 0.0;
+  __syncthreads();
+  // row ty: x L_kk^T = a  -> forward substitution along tx (done by the tx==0 thread of each row...)
+  // parallel variant: all 32 threads of a row cooperate column by column
+  for (int j = 0; j < kb; ++j) {
+    if (tx == j) Ab[ty][j] /= Lkk[j][j];
+    __syncthreads();
+    if (tx > j && tx < kb) Ab[ty][tx] -= Ab[ty][j] * Lkk[tx][j];
+    __syncthreads();
+  }
+  if (ty < rb && tx < kb) A[(int64_t)(r0 + ty) * n + k0 + tx] = Ab[ty][tx];
+}
+
+// Trailing update after panel k: A_ij -= L_ik L_jk^T for i >= j > k (32x32 tiles)
+static __global__ void __launch_bounds__(kNB* kNB) chol_update_kernel(double* A, int n, int k) {
+  const int nb = (n + kNB - 1) / kNB;
+  const int rem = nb - (k + 1);
+  // linear tile index over the lower triangle of a rem x rem tile grid
+  int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  const int bj = t - bi * (bi + 1) / 2;
+  if (bi >= rem) return;
+  const int i0 = (k + 1 + bi) * kNB, j0 = (k + 1 + bj) * kNB, k0 = k * kNB;
+  const int kb = min(kNB, n - k0);
+  __shared__ double Li[kNB][kNB + 1];
+  __shared__ double Lj[kNB][kNB + 1];
+  const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;
+  Li[ty][tx] = (i0 + ty < n && tx < kb) ? A[(int64_t)(i0 + ty) * n + k0 + tx] : 0.0;
+  Lj[ty][tx] = (j0 + ty < n && tx < kb) ? A[(int64_t)(j0 + ty) * n + k0 + tx] : 0.0;
+  __syncthreads();
+  const int r = i0 + ty, c = j0 + tx;
+  if (r < n && c < n && c <= r) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kNB; ++q) s += Li[ty][q] * Lj[tx][q];
+    A[(int64_t)r * n + c] -= s;
+  }
+}
+
+// Solve L L^T x = b in place (b -> x). Single CTA, blocked by 32.
+static __global__ void __launch_bounds__(1024) chol_solve_kernel(const double* L, double* b, int n) {
+  __shared__ double xb[kNB];
+  const int nb = (n + kNB - 1) / kNB;
+  // forward: L y = b
+  for (int k = 0; k < nb; ++k) {
+    const int k0 = k * kNB, kb = min(kNB, n - k0);
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      double v = lane < kb ? b[k0 + lane] : 0.0;
+      for (int j = 0; j < kb; ++j) {
+        const double ljj = L[(int64_t)(k0 + j) * n + k0 + j];
+        const double yj = __shfl_sync(0xffffffffu, v, j) / ljj;
+        if (lane == j) v = yj;
+        else if (lane > j && lane < kb) v -= L[(int64_t)(k0 + lane) * n + k0 + j] * yj;
+      }
+      if (lane < kb) { b[k0 + lane] = v; xb[lane] = v; }
+    }
+    __syncthreads();
+    for (int r = k0 + kb + threadIdx.x; r < n; r += blockDim.x) {
+      double s = 0.0;
+      for (int j = 0; j < kb; ++j) s += L[(int64_t)r * n + k0 + j] * xb[j];
+      b[r] -= s;
+    }
+    __syncthreads();
+  }
+  // backward: L^T x = y
+  for (int k = nb - 1; k >= 0; --k) {
+    const int k0 = k * kNB, kb = min(kNB, n - k0);
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      double v = lane < kb ? b[k0 + lane] : 0.0;
+      for (int j = kb - 1; j >= 0; --j) {
+        const double ljj = L[(int64_t)(k0 + j) * n + k0 + j];
+        const double xj = __shfl_sync(0xffffffffu, v, j) / ljj;
+        if (lane == j) v = xj;
+        else if (lane < j) v -= L[(int64_t)(k0 + j) * n + k0 + lane] * xj;
+      }
+      if (lane < kb) { b[k0 + lane] = v; xb[lane] = v; }
+    }
+    __syncthreads();
+    // b[r] -= sum_j L[k0+j][r] * x[j] for r < k0
+    for (int r = threadIdx.x; r < k0; r += blockDim.x) {
+      double s = 0.0;
+      for (int j = 0; j < kb; ++j) s += L[(int64_t)(k0 + j) * n + r] * xb[j];
+      b[r] -= s;
+    }
+    __syncthreads();
+  }
+}
+
+// K5: back-substitution (one thread per point) + pieces of the model cost change.
+//   delta_p = (Hpp+D)^-1 (-gp - sum_i W_i^T delta_c[cols_i])
+//   acc[0] += gp.dp + 0.5 dp^T Hpp dp + sum_i dc_i^T W_i dp      (point part of g.d + d^T H d / 2)
+static __global__ void __launch_bounds__(128) ba_backsub_kernel(BADev d, const double* D2, double* delta, double* acc) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double part = 0.0;
+  if (p < d.n_points && d.point_off[p] >= 0) {
+    const int64_t po = d.point_off[p];
+    double inv[9];
+    inv3_sym(d.Hpp + p * 9, D2 + po, inv);
+    double v[3] = {-d.gp[p * 3], -d.gp[p * 3 + 1], -d.gp[p * 3 + 2]};
+    double wd[3] = {0, 0, 0};
+    for (int64_t o = d.pt_begin[p]; o < d.pt_begin[p + 1]; ++o) {
+      const int dc = d.Wdc[o];
+      for (int a = 0; a < dc; ++a) {
+        const double dca = delta[d.Wcols[o * d.dcmax + a]];
+        const double* w = d.W + (o * d.dcmax + a) * 3;
+        wd[0] += w[0] * dca; wd[1] += w[1] * dca; wd[2] += w[2] * dca;
+      }
+    }
+    v[0] -= wd[0]; v[1] -= wd[1]; v[2] -= wd[2];
+    double dp[3];
+    for (int a = 0; a < 3; ++a) dp[a] = inv[a * 3] * v[0] + inv[a * 3 + 1] * v[1] + inv[a * 3 + 2] * v[2];
+    delta[po] = dp[0]; delta[po + 1] = dp[1]; delta[po + 2] = dp[2];
+    const double* H = d.Hpp + p * 9;
+    double hd = 0.0;
+    for (int a = 0; a < 3; ++a) hd += dp[a] * (H[a * 3] * dp[0] + H[a * 3 + 1] * dp[1] + H[a * 3 + 2] * dp[2]);
+    part = d.gp[p * 3] * dp[0] + d.gp[p * 3 + 1] * dp[1] + d.gp[p * 3 + 2] * dp[2] + 0.5 * hd +
+           (wd[0] * dp[0] + wd[1] * dp[1] + wd[2] * dp[2]);
+  }
+  // block reduce
+  __shared__ double sh[4];
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) atomic_add_f64(&acc[0], sh[0] + sh[1] + sh[2] + sh[3]);
+}
+
+// camera part of g.d + d^T H d / 2 with the symmetric Hcc stored as lower triangle
+static __global__ void __launch_bounds__(256) ba_cam_model_kernel(const double* Hcc, const double* gc, const double* delta,
+                                                          int nc, double* acc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  double part = 0.0;
+  if (r < nc) {
+    double row = 0.0;
+    for (int c = 0; c < r; ++c) row += Hcc[(int64_t)r * nc + c] * delta[c];  // strictly lower, counted twice
+    part = gc[r] * delta[r] + delta[r] * row + 0.5 * delta[r] * Hcc[(int64_t)r * nc + r] * delta[r];
+  }
+  __shared__ double sh[8];
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0; for (int i = 0; i < 8; ++i) s += sh[i]; atomic_add_f64(&acc[0], s); }
+}
+
+// K6: x_plus = Plus(x, delta) for every block; also accumulates ||x||^2, ||x_plus - x||^2 (ambient)
+struct PlusArgs {
+  int n_cameras, n_images; int64_t n_points;
+  const int32_t* cam_model; const uint32_t* cam_mask; const uint8_t* tmask;
+  const int32_t* pose_off; const int32_t* intr_off; const int64_t* point_off;
+  const double* cam; const double* q; const double* t; const double* X;
+  double* cam_o; double* q_o; double* t_o; double* X_o;
+  const double* delta;
+  double* acc;  // [1] += ||x_plus - x||^2 ; [2] += ||x||^2
+};
+static __global__ void __launch_bounds__(128) ba_plus_kernel(PlusArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double dn = 0.0, xn = 0.0;
+  if (i < a.n_points) {
+    const int64_t po = a.point_off[i];
+    for (int k = 0; k < 3; ++k) {
+      const double x = a.X[3 * i + k];
+      const double xp = po >= 0 ? x + a.delta[po + k] : x;
+      a.X_o[3 * i + k] = xp;
+      dn += (xp - x) * (xp - x); xn += x * x;
+    }
+  }
+  if (i < a.n_images) {
+    const int po = a.pose_off[i];
+    double qn[4];
+    const double* q = a.q + 4 * i;
+    const double* t = a.t + 3 * i;
+    if (po >= 0) {
+      quaternion_plus(q, a.delta + po, qn);
+      int la = 3;
+      for (int k = 0; k < 3; ++k) {
+        double tp = t[k];
+        if (!(a.tmask[i] & (1u << k))) tp += a.delta[po + la++];
+        a.t_o[3 * i + k] = tp;
+        dn += (tp - t[k]) * (tp - t[k]);
+      }
+    } else {
+      for (int k = 0; k < 4; ++k) qn[k] = q[k];
+      for (int k = 0; k < 3; ++k) a.t_o[3 * i + k] = t[k];
+    }
+    for (int k = 0; k < 4; ++k) { a.q_o[4 * i + k] = qn[k]; dn += (qn[k] - q[k]) * (qn[k] - q[k]); xn += q[k] * q[k]; }
+    for (int k = 0; k < 3; ++k) xn += t[k] * t[k];
+  }
+  if (i < a.n_cameras) {
+    const int io = a.intr_off[i];
+    const int Kc = cam_num_params(a.cam_model[i]);
+    int la = 0;
+    for (int k = 0; k < kMaxK; ++k) {
+      const double c = a.cam[i * kMaxK + k];
+      double cpv = c;
+      if (io >= 0 && k < Kc && !(a.cam_mask[i] & (1u << k))) cpv += a.delta[io + la++];
+      a.cam_o[i * kMaxK + k] = cpv;
+      dn += (cpv - c) * (cpv - c);
+      if (k < Kc) xn += c * c;
+    }
+  }
+  __shared__ double sh[2][4];
+  dn = warp_sum(dn); xn = warp_sum(xn);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = dn; sh[1][threadIdx.x >> 5] = xn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomic_add_f64(&a.acc[1], sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]);
+    atomic_add_f64(&a.acc[2], sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3]);
+  }
+}
+
+// deterministic final reduction of per-warp cost partials: out[0] = sum
+static __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* partials, int64_t n, double* out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = sh[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+// max |g| over the local gradient (cameras from gc, points from gp)
+static __global__ void __launch_bounds__(256) ba_gradmax_kernel(BADev d, double* out /* as ordered-uint max */) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if (i < d.nc) m = fabs(d.gc[i]);
+  if (i < d.n_points && d.point_off[i] >= 0)
+    m = fmax(m, fmax(fabs(d.gp[i * 3]), fmax(fabs(d.gp[i * 3 + 1]), fabs(d.gp[i * 3 + 2]))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0)
+    atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+}  // namespace pxr

@@ -1,0 +1,79 @@
+// pxr_internal.h — host-side plumbing shared by the translation units of libpxr.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pxr.h"
+
+struct pxr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  int sm_count = 148;
+  // multi-GPU (NCCL resolved with dlopen at pxr_ctx_init_comm)
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+namespace pxr {
+
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);
+
+#define PXR_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return pxr::fail(PXR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define PXR_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != PXR_OK) return _s; \
+  } while (0)
+
+#define PXR_LAUNCH(ctx, kernel, grid, block, smem, ...)          \
+  do {                                                           \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+    (ctx)->launches++;                                           \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return PXR_OK;
+    PXR_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    return PXR_OK;
+  }
+  int upload(const T* host, size_t count, cudaStream_t s) {
+    PXR_TRY(alloc(count));
+    if (count) PXR_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return PXR_OK;
+  }
+  int zero(cudaStream_t s) {
+    if (n) PXR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    return PXR_OK;
+  }
+};
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// allreduce (sum, fp64) on ctx->stream when a communicator is attached; no-op otherwise
+int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count);
+
+}  // namespace pxr

@@ -1,0 +1,88 @@
+"""Thin object wrappers over the C-ABI handles (plumbing only; no arithmetic)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class BAHandle:
+    """pxr_ba: a BA problem resident on the device (== FeatureReferenceBundleOptimizer.set_up)."""
+
+    def __init__(self, problem, interp=None, options=None, ctx=None):
+        self.ctx = ctx or _capi.default_context()
+        self.lib = self.ctx.lib
+        self.problem = problem
+        self.interp = interp or _capi.default_interp()
+        self.options = options or _capi.default_ba_options()
+        self._desc = problem.desc()
+        self.handle = C.c_void_p()
+        _capi.check(self.lib.pxr_ba_create(self.ctx.handle, C.byref(self._desc), C.byref(self.interp),
+                                           C.byref(self.options), C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.lib.pxr_ba_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def evaluate(self, residuals=False):
+        n = self.problem.n_obs
+        out = dict(sq_norm=np.zeros(n), gtr=np.zeros((n, 2)), gtg=np.zeros((n, 3)), xy=np.zeros((n, 2)))
+        res = np.zeros((n, self.problem.channels)) if residuals else None
+        cost = C.c_double()
+        _capi.check(self.lib.pxr_ba_evaluate(self.handle, _p(out["sq_norm"]), _p(out["gtr"]), _p(out["gtg"]),
+                                             _p(out["xy"]), _p(res), C.byref(cost)))
+        out["cost"] = cost.value
+        if residuals:
+            out["residuals"] = res
+        return out
+
+    def debug_linearize(self, nc, nl, radius=1e4):
+        npts = len(self.problem.xyz)
+        out = dict(Hcc=np.zeros((nc, nc)), gc=np.zeros(nc), Hpp=np.zeros((npts, 3, 3)), gp=np.zeros((npts, 3)),
+                   S=np.zeros((nc, nc)), rhs=np.zeros(nc), delta=np.zeros(nl))
+        cost = C.c_double(); mcc = C.c_double()
+        _capi.check(self.lib.pxr_ba_debug_linearize(self.handle, C.c_double(radius), C.byref(cost), _p(out["Hcc"]),
+                                                    _p(out["gc"]), _p(out["Hpp"]), _p(out["gp"]), _p(out["S"]),
+                                                    _p(out["rhs"]), _p(out["delta"]), C.byref(mcc)))
+        out["cost"] = cost.value; out["model_cost_change"] = mcc.value
+        return out
+
+    def debug_inner_iterations(self):
+        _capi.check(self.lib.pxr_ba_debug_inner_iterations(self.handle))
+
+    def solve(self, capacity=512):
+        s = _capi.make_summary(capacity)
+        _capi.check(self.lib.pxr_ba_solve(self.handle, C.byref(s)))
+        return _capi.summary_to_dict(s)
+
+    def read_params(self):
+        """Copies the current device parameters back into the BAProblem arrays."""
+        p = self.problem
+        _capi.check(self.lib.pxr_ba_read_params(self.handle, _p(p.cam_params), _p(p.qvec), _p(p.tvec), _p(p.xyz)))
+
+    def time_stage(self, stage, iters):
+        ms = C.c_double()
+        _capi.check(self.lib.pxr_ba_time_stage(self.handle, int(stage), int(iters), C.byref(ms)))
+        return ms.value
+
+
+def ba_run(problem, interp=None, options=None, ctx=None, capacity=512):
+    """pxr_ba_run: upload, solve, write the refined parameters back into `problem` (in place)."""
+    ctx = ctx or _capi.default_context()
+    interp = interp or _capi.default_interp()
+    options = options or _capi.default_ba_options()
+    d = problem.desc()
+    s = _capi.make_summary(capacity)
+    _capi.check(ctx.lib.pxr_ba_run(ctx.handle, C.byref(d), C.byref(interp), C.byref(options), C.byref(s)))
+    return _capi.summary_to_dict(s)

@@ -1,0 +1,148 @@
+"""GPU parity: the CUDA path (through the C-ABI of libpxr.so) against the CPU oracle on the same
+seeded inputs.  Tolerances: the reference's own SIMD-vs-Ceres tolerance is 1e-5 on f/df
+(interpolation_test.cc:352-354); because the kernels reproduce the reference's per-channel
+operation order, much tighter bounds hold and are asserted here."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pixsfm._pixsfm import _capi, _engine
+from pixsfm.util import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(**kw):
+    args = dict(n_cams=6, n_points=60, track_len=4, channels=128, seed=0)
+    args.update(kw)
+    prob, gt = synthetic.make_ba_scene(**args)
+    ic = _capi.default_interp()
+    refs, _ = O.refs_compute(prob, ic)
+    prob.refs = refs
+    return prob, gt, ic
+
+
+@pytest.mark.parametrize("channels,dtype", [(128, np.float16), (64, np.float16), (16, np.float16),
+                                            (128, np.float32), (16, np.float64), (128, np.float64)])
+def test_residual_blocks_match_oracle(channels, dtype):
+    prob, gt, ic = _scene(channels=channels, dtype=dtype, n_points=40)
+    so = _capi.default_ba_options(use_inner_iterations=0)
+    ref = O.ba_evaluate(prob, ic, so, residuals=True)
+    h = _engine.BAHandle(prob, ic, so)
+    got = h.evaluate(residuals=True)
+    assert np.allclose(got["xy"], ref["xy"], rtol=0, atol=1e-9)
+    assert np.abs(got["residuals"] - ref["residuals"]).max() < 1e-12
+    assert np.allclose(got["sq_norm"], ref["sq_norm"], rtol=1e-10, atol=1e-15)
+    assert np.allclose(got["gtr"], ref["gtr"], rtol=1e-9, atol=1e-13)
+    assert np.allclose(got["gtg"], ref["gtg"], rtol=1e-10, atol=1e-14)
+    assert abs(got["cost"] - ref["cost"]) <= 1e-11 * abs(ref["cost"])
+
+
+def test_float_simd_mode_and_no_l2():
+    prob, gt, _ = _scene(n_points=30)
+    for l2, fs in ((True, True), (False, False), (False, True)):
+        ic = _capi.default_interp(l2_normalize=l2, use_float_simd=fs)
+        so = _capi.default_ba_options(use_inner_iterations=0)
+        ref = O.ba_evaluate(prob, ic, so, residuals=True)
+        got = _engine.BAHandle(prob, ic, so).evaluate(residuals=True)
+        assert np.abs(got["residuals"] - ref["residuals"]).max() < 1e-12
+        assert np.allclose(got["gtg"], ref["gtg"], rtol=1e-9, atol=1e-13)
+
+
+def test_border_clamp_matches_oracle():
+    # push projections to and beyond the patch border: per-tap clamp path (grid2d.h:29-35)
+    prob, gt, ic = _scene(n_points=40)
+    rng = np.random.default_rng(1)
+    prob.corner[:] += rng.integers(-9, 10, prob.corner.shape).astype(np.int32)
+    so = _capi.default_ba_options(use_inner_iterations=0)
+    ref = O.ba_evaluate(prob, ic, so, residuals=True)
+    got = _engine.BAHandle(prob, ic, so).evaluate(residuals=True)
+    assert np.abs(got["residuals"] - ref["residuals"]).max() < 1e-12
+    assert np.allclose(got["gtr"], ref["gtr"], rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("shared_camera", [False, True])
+def test_normal_equations_schur_and_step_match_oracle(shared_camera):
+    prob, gt, ic = _scene(shared_camera=shared_camera)
+    so = _capi.default_ba_options(use_inner_iterations=0)
+    ref = O.ba_linearize(prob, ic, so, radius=1e4)
+    h = _engine.BAHandle(prob, ic, so)
+    got = h.debug_linearize(ref["nc"], ref["nl"], radius=1e4)
+    tril = lambda M: np.tril(M)
+    assert abs(got["cost"] - ref["cost"]) <= 1e-11 * ref["cost"]
+    scale = np.abs(ref["Hcc"]).max()
+    assert np.abs(tril(got["Hcc"]) - tril(ref["Hcc"])).max() <= 1e-10 * scale
+    assert np.allclose(got["gc"], ref["gc"], rtol=1e-8, atol=1e-10 * np.abs(ref["gc"]).max())
+    assert np.allclose(got["Hpp"], ref["Hpp"], rtol=1e-9, atol=1e-10 * np.abs(ref["Hpp"]).max())
+    assert np.allclose(got["gp"], ref["gp"], rtol=1e-8, atol=1e-10 * np.abs(ref["gp"]).max())
+    assert np.abs(tril(got["S"]) - tril(ref["S"])).max() <= 1e-9 * np.abs(ref["S"]).max()
+    assert np.allclose(got["rhs"], ref["rhs"], rtol=1e-7, atol=1e-9 * np.abs(ref["rhs"]).max())
+    assert np.allclose(got["delta"], ref["delta"], rtol=1e-5, atol=1e-8 * np.abs(ref["delta"]).max())
+    assert abs(got["model_cost_change"] - ref["model_cost_change"]) <= 1e-7 * abs(ref["model_cost_change"])
+
+
+def test_constant_blocks_and_partial_masks():
+    prob, gt, ic = _scene(n_cams=7, n_points=50, refine_pp=True)
+    prob.point_const[::7] = 1
+    prob.pose_const[3] = 1
+    prob.tvec_const_mask[4] = 0b101
+    prob.cam_const_mask[2] = 0xFFFFFFFF
+    so = _capi.default_ba_options(use_inner_iterations=0)
+    ref = O.ba_linearize(prob, ic, so, radius=3e3)
+    got = _engine.BAHandle(prob, ic, so).debug_linearize(ref["nc"], ref["nl"], radius=3e3)
+    assert np.allclose(got["delta"], ref["delta"], rtol=1e-5, atol=1e-8 * np.abs(ref["delta"]).max())
+    assert abs(got["model_cost_change"] - ref["model_cost_change"]) <= 1e-7 * abs(ref["model_cost_change"])
+
+
+def _compare_solutions(a, b, tol):
+    assert np.abs(a.qvec - b.qvec).max() < tol
+    assert np.abs(a.tvec - b.tvec).max() < tol
+    assert np.abs(a.xyz - b.xyz).max() < tol
+    assert np.abs(a.cam_params[:, 1:] - b.cam_params[:, 1:]).max() < tol
+    assert np.abs(a.cam_params[:, 0] / b.cam_params[:, 0] - 1).max() < tol
+
+
+@pytest.mark.parametrize("inner", [0, 1])
+def test_full_solve_matches_oracle(inner):
+    prob, gt, ic = _scene()
+    so = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=15)
+    p_ref = prob.copy(); p_gpu = prob.copy()
+    s_ref = O.ba_solve(p_ref, ic, so)
+    s_gpu = _engine.ba_run(p_gpu, ic, so)
+    assert s_gpu["num_iterations"] == s_ref["num_iterations"]
+    assert abs(s_gpu["initial_cost"] - s_ref["initial_cost"]) <= 1e-10 * s_ref["initial_cost"]
+    assert abs(s_gpu["final_cost"] - s_ref["final_cost"]) <= 1e-6 * s_ref["final_cost"]
+    for ig, ir in zip(s_gpu["iterations"], s_ref["iterations"]):
+        assert ig["step_is_successful"] == ir["step_is_successful"]
+        assert abs(ig["cost"] - ir["cost"]) <= 1e-6 * abs(ir["cost"])
+    # the reference's own parameter tolerance for BA-vs-BA comparisons is 1e-4 (bundle_optimizer_test.cc:52)
+    _compare_solutions(p_gpu, p_ref, 1e-6)
+    assert s_gpu["kernel_launches"] > 0
+
+
+def test_inner_iterations_kernel_matches_oracle_points():
+    prob, gt, ic = _scene(n_points=30)
+    prob.xyz += np.random.default_rng(5).normal(0, 0.004, prob.xyz.shape)
+    so = _capi.default_ba_options(use_inner_iterations=1)
+    h = _engine.BAHandle(prob.copy(), ic, so)
+    h.debug_inner_iterations()
+    h.read_params()
+    # oracle: run ONLY the point coordinate descent = BA with everything but points constant, via
+    # the public solve with max_num_iterations=0 is not possible; use the dedicated hook
+    import ctypes as C
+    p_ref = prob.copy()
+    d = p_ref.desc()
+    O.lib().orc_ba_inner_iterations(C.byref(d), C.byref(ic), C.byref(so))
+    assert np.abs(h.problem.xyz - p_ref.xyz).max() < 1e-7
+    assert np.abs(p_ref.xyz - prob.xyz).max() > 1e-5  # the points did move
+
+
+def test_unsupported_channels_raise_value_error():
+    prob, gt, ic = _scene(channels=16, n_points=10)
+    bad = prob.copy()
+    bad.patches = np.ascontiguousarray(prob.patches[..., :3])
+    bad._patches_ptr = bad.patches.ctypes.data
+    bad.channels = 3
+    bad.refs = np.ascontiguousarray(prob.refs[:, :3])
+    with pytest.raises(ValueError):
+        _engine.BAHandle(bad, ic, _capi.default_ba_options())
