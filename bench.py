@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — featuremetric BA observations/sec and LM-iteration ms on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference path
+
+Workload (config.workload): BASELINE.json configs[2] — synthetic 200 cams / 50 000 points /
+500 000 observations, 128-channel fp16 16x16 patches (32.8 GB), bicubic + L2 normalisation,
+Cauchy(0.25), reference default options (inner iterations on).  north_star quotes its target on
+this config; configs[1] (8k observations, 33 MB of taps) fits in L2 and cannot exercise the HBM
+roofline.  A "step" is ONE Levenberg-Marquardt iteration of one continuing trajectory.
+With N>1 every rank holds its own 50k points / 500k observations over the SAME 200 cameras (weak
+scaling); the reduced camera system is all-reduced with NCCL every LM iteration.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "pixel-perfect-sfm_b200"))
+
+ALGO_BYTES_PER_OBS = 4736  # 16 taps x 128 ch x 2 B + fp32-equivalent ref 512 B + 128 B metadata
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cams", type=int, default=200)
+    ap.add_argument("--points", type=int, default=50000)
+    ap.add_argument("--track", type=int, default=10)
+    ap.add_argument("--channels", type=int, default=128)
+    ap.add_argument("--ps", type=int, default=16)
+    ap.add_argument("--no-inner", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-points", type=int, default=1500)
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def geometry(args, rank):
+    """cameras identical on every rank, points per rank"""
+    from pixsfm.util import synthetic
+    geo_c = synthetic.make_geometry(args.cams, 1, 1, seed=args.seed)  # cameras only
+    rng = np.random.default_rng(args.seed * 1000 + 17 + rank)
+    n_pts, L = args.points, min(args.track, args.cams)
+    xyz = rng.uniform(-1, 1, (n_pts, 3))
+    # every point is seen by L distinct cameras
+    keys = rng.random((n_pts, args.cams))
+    obs_img = np.sort(np.argpartition(keys, L - 1, axis=1)[:, :L], axis=1).astype(np.int32).reshape(-1)
+    obs_pt = np.repeat(np.arange(n_pts, dtype=np.int64), L)
+    qvec, tvec, cam_params, img_cam = geo_c["qvec"], geo_c["tvec"], geo_c["cam_params"], geo_c["img_cam"]
+    xy = np.empty((len(obs_pt), 2))
+    for i in range(args.cams):
+        m = obs_img == i
+        if m.any():
+            xy[m] = synthetic.project_simple_radial(cam_params[img_cam[i]], qvec[i], tvec[i], xyz[obs_pt[m]])
+    ps = args.ps
+    scale = np.ones((len(obs_pt), 2))
+    corners = np.clip((xy * scale - ps / 2.0).astype(np.int32), [0, 0], np.array([1000, 1000]) - ps - 1).astype(np.int32)
+    uv0 = xy * scale - 0.5 - corners
+    # perturbed start (cameras: same on every rank)
+    rc = np.random.default_rng(args.seed + 991)
+    q0, t0 = qvec.copy(), tvec.copy()
+    for i in range(args.cams):
+        w = rc.normal(0, np.deg2rad(0.02), 3)
+        ang = np.linalg.norm(w)
+        dq = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * w / ang])
+        q0[i] = synthetic.quat_mul(dq, q0[i]); q0[i] /= np.linalg.norm(q0[i])
+        t0[i] += rc.normal(0, 0.002, 3)
+    X0 = xyz + rng.normal(0, 0.005, xyz.shape)
+    return dict(xyz=X0, qvec=q0, tvec=t0, cam_params=cam_params, img_cam=img_cam, obs_img=obs_img, obs_pt=obs_pt,
+                corners=corners, scale=scale, uv0=uv0)
+
+
+def make_problem(args, g, patches, on_device, sel=None):
+    from pixsfm._pixsfm import _capi
+    n_cams = args.cams
+    n_models = len(g["cam_params"])
+    pose_const = np.zeros(n_cams, np.uint8); pose_const[0] = 1
+    tmask = np.zeros(n_cams, np.uint8); tmask[1] = 1
+    focal, pp, extra = _capi.CAMERA_PARAM_GROUPS[2]
+    kw = dict(cam_model=np.full(n_models, 2, np.int32), cam_params=g["cam_params"],
+              cam_const_mask=np.full(n_models, pp, np.uint32), qvec=g["qvec"], tvec=g["tvec"], img_cam=g["img_cam"],
+              pose_const=pose_const, tvec_const_mask=tmask)
+    if sel is None:
+        n_pts = len(g["xyz"])
+        return _capi.BAProblem(xyz=g["xyz"], point_const=np.zeros(n_pts, np.uint8), obs_img=g["obs_img"],
+                               obs_pt=g["obs_pt"], patches=patches, corner=g["corners"], scale=g["scale"],
+                               patches_on_device=on_device,
+                               patch_shape=(len(g["obs_pt"]), args.ps, args.ps, args.channels) if on_device else None,
+                               patch_dtype=0 if on_device else None, **kw)
+    n_pts, n_obs = sel
+    return _capi.BAProblem(xyz=g["xyz"][:n_pts], point_const=np.zeros(n_pts, np.uint8), obs_img=g["obs_img"][:n_obs],
+                           obs_pt=g["obs_pt"][:n_obs], patches=patches, corner=g["corners"][:n_obs],
+                           scale=g["scale"][:n_obs], **kw)
+
+
+def cpu_arm(args, g, d_patches, refs, ctx, steps, label):
+    """Times the CPU restatement of the reference path (oracle/) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from pixsfm._pixsfm import _capi, _engine
+    L = min(args.track, args.cams)
+    n_pts = min(args.cpu_sample_points, len(g["xyz"]))
+    n_obs = n_pts * L
+    pbytes = n_obs * args.ps * args.ps * args.channels * 2
+    host = np.empty((n_obs, args.ps, args.ps, args.channels), np.float16)
+    _engine.memcpy_d2h(host, d_patches, pbytes, ctx)
+    prob = make_problem(args, g, host, False, sel=(n_pts, n_obs))
+    prob.refs = np.ascontiguousarray(refs[:n_pts])
+    ic = _capi.default_interp()
+    so = _capi.default_ba_options(use_inner_iterations=0 if args.no_inner else 1, max_num_iterations=steps)
+    cores = O.lib().orc_num_threads()
+    t0 = time.time()
+    s = O.ba_solve(prob, ic, so)
+    dt = time.time() - t0
+    iters = max(1, s["num_iterations"] - 1)
+    # subtract nothing: the iteration-zero evaluation is part of a Ceres solve as well
+    return {"value": n_obs * iters / dt, "unit": "observations/s", "cores": int(cores), "kind": "port",
+            "sample": "%s: first %d points / %d observations of the workload, %d LM iterations, all host threads "
+                      "(CPU restatement of the reference Ceres/AVX2 path; Ceres itself is not installable offline)"
+                      % (label, n_pts, n_obs, iters),
+            "ms_per_lm_iteration_sample": 1e3 * dt / iters, "seconds": dt}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    from pixsfm._pixsfm import _capi, _engine
+
+    dist = None
+    if world > 1 and args.impl != "reference":
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _capi.Context(local_rank)
+    if dist is not None:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(_capi.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        ctx.init_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+
+    t_setup = time.time()
+    g = geometry(args, rank)
+    n_obs = len(g["obs_pt"])
+    d_patches = _engine.synth_patches_device(n_obs, args.ps, args.channels, g["uv0"], g["obs_pt"],
+                                             seed=args.seed * 7919 + rank, noise=0.01, ctx=ctx)
+    prob = make_problem(args, g, d_patches, True)
+    ic = _capi.default_interp()
+    refs, _ = _engine.refs_compute(prob, ic, ctx=ctx)
+    prob.refs = refs
+    setup_s = time.time() - t_setup
+
+    inner = 0 if args.no_inner else 1
+    workload = ("synthetic %d cams / %d pts / %d obs per GPU, %d-ch fp16 %dx%d patches, bicubic+L2, Cauchy(0.25)"
+                % (args.cams, args.points, n_obs, args.channels, args.ps, args.ps))
+    config = {"workload": workload, "baseline_config": "configs[2]", "use_inner_iterations": bool(inner),
+              "parallelism": "point-sharded x%d, cameras replicated, NCCL allreduce of the reduced camera system" % world,
+              "l2_flush": "inputs (%.1f GB of taps per pass) larger than L2" % (n_obs * 4096 / 1e9),
+              "step": "one LM iteration (step solve + trial cost%s + Jacobian on acceptance)" % (" + inner iterations" if inner else "")}
+
+    if args.impl == "reference":
+        cb = cpu_arm(args, g, d_patches, refs, ctx, max(1, args.steps), "reference arm")
+        line = {"impl": "reference", "metric": "featuremetric BA observations/sec", "value": cb["value"],
+                "unit": "observations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * n_obs / cb["value"],  # full-workload LM iteration extrapolated from the sample rate
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    so = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.warmup + args.steps)
+    h = _engine.BAHandle(prob, ic, so, ctx=ctx)
+    # ---- warm-up: W iterations of the trajectory (plus iteration zero)
+    h.iterate(max(args.warmup, 0))
+    ctx.sync()
+    if dist is not None:
+        dist.barrier()
+    h.kernel_timing(enable=1, read=False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.kernel_launches()
+    ctx.timer_start()
+    t0 = time.time()
+    s = h.iterate(args.steps)
+    ms = ctx.timer_stop()
+    wall = time.time() - t0
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop()
+    k1_ms, k1_n = h.kernel_timing(enable=0, which=1)
+    if dist is not None:
+        import torch
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        dist.barrier()
+    its = s["iterations"][-args.steps:] if args.steps > 0 else []
+    steps_done = len(its)
+    total_obs = n_obs * world
+    value = total_obs * steps_done / (ms / 1e3) if ms > 0 else 0.0
+
+    # ---- roofline of the dominant kernel (K1, Jacobian mode), CUDA events inside the timed region
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k1_avg_ms = k1_ms / k1_n if k1_n else float("nan")
+    achieved = ALGO_BYTES_PER_OBS * n_obs / (k1_avg_ms * 1e-3) / 1e9 if k1_n else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "fm_eval_kernel<half,128,JAC> (K1 residual/Jacobian)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "avg_launch_ms": k1_avg_ms, "launches_timed": k1_n,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_OBS * n_obs,
+                "share_of_step": (k1_ms / ms) if ms else None}
+
+    # ---- e2e: the public one-shot call on HOST buffers (upload + K iterations + read-back)
+    e2e = None
+    if not args.no_e2e:
+        try:
+            pbytes = n_obs * args.ps * args.ps * args.channels * 2
+            hp = C.c_void_p()
+            pinned = ctx.lib.pxr_host_alloc_pinned(C.byref(hp), C.c_size_t(pbytes)) == 0
+            if pinned:
+                host = np.ctypeslib.as_array((C.c_uint16 * (pbytes // 2)).from_address(hp.value)).view(np.float16)
+                host = host.reshape(n_obs, args.ps, args.ps, args.channels)
+            else:
+                host = np.empty((n_obs, args.ps, args.ps, args.channels), np.float16)
+            _engine.memcpy_d2h(host, d_patches, pbytes, ctx)
+            g2 = geometry(args, rank)
+            prob_h = make_problem(args, g2, host, False)
+            prob_h.refs = refs
+            so2 = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.steps)
+            if dist is not None:
+                dist.barrier()
+            t0 = time.time()
+            s2 = _engine.ba_run(prob_h, ic, so2, ctx=ctx)
+            dt = time.time() - t0
+            if dist is not None:
+                import torch
+                tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            it2 = max(1, s2["num_iterations"] - 1)
+            e2e = {"value": total_obs * it2 / dt, "unit": "observations/s",
+                   "h2d_bytes_per_step": s2["h2d_bytes"] / it2, "d2h_bytes_per_step": s2["d2h_bytes"] / it2,
+                   "seconds": dt, "lm_iterations": it2, "pinned_host": bool(pinned),
+                   "call": "pxr_ba_run (upload %.1f GB of patches + solve + read back)" % (pbytes / 1e9),
+                   "final_cost": s2["final_cost"]}
+            if pinned:
+                del host
+                ctx.lib.pxr_host_free_pinned(hp)
+        except Exception as ex:  # report, never fake
+            e2e = {"value": None, "unit": "observations/s", "error": repr(ex)}
+
+    cb = None
+    if rank == 0 and world == 1:
+        try:
+            cb = cpu_arm(args, g, d_patches, refs, ctx, 2, "cpu_baseline")
+        except Exception as ex:
+            cb = {"value": None, "error": repr(ex)}
+
+    if rank == 0:
+        line = {"metric": "featuremetric BA observations/sec", "value": value, "unit": "observations/s",
+                "n_gpus": world, "steps": steps_done, "warmup": args.warmup, "ms_per_step": ms / max(1, steps_done),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp16 taps, fp32 horizontal, fp64 vertical/solve)",
+                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cb,
+                "lm": {"successful_steps": int(sum(i["step_is_successful"] for i in its)), "steps": steps_done,
+                       "cost_first": its[0]["cost"] if its else None, "cost_last": its[-1]["cost"] if its else None,
+                       "wall_ms_per_step": 1e3 * wall / max(1, steps_done)},
+                "setup_seconds": setup_s}
+        print(json.dumps(line))
+    _engine.device_free(d_patches, ctx)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -208,6 +208,9 @@ int pxr_ctx_destroy(pxr_ctx* ctx);
 int pxr_nccl_unique_id(void* id128);
 int pxr_ctx_init_comm(pxr_ctx* ctx, int rank, int world, const void* id128);
 int pxr_ctx_sync(pxr_ctx* ctx);
+/* CUDA-event stopwatch on the library stream (bench.py times K LM iterations with it) */
+int pxr_ctx_timer_start(pxr_ctx* ctx);
+int pxr_ctx_timer_stop(pxr_ctx* ctx, double* elapsed_ms);
 int64_t pxr_ctx_kernel_launches(pxr_ctx* ctx);
 
 /* ---- default option blocks --------------------------------------------- */
@@ -221,6 +224,12 @@ void pxr_default_ka_options(pxr_solver_options* o);    /* keypoint_adjustment/ma
 int pxr_ba_create(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
                   const pxr_solver_options* opt, pxr_ba** out);   /* uploads (set_up) */
 int pxr_ba_solve(pxr_ba* ba, pxr_summary* summary);               /* solve_problem */
+/* Continues (or starts) the LM trajectory of `ba` for n more iterations (bench.py: W warm-up, then K timed). */
+int pxr_ba_iterate(pxr_ba* ba, int n_iterations, pxr_summary* summary);
+/* CUDA-event timing of the residual/Jacobian kernel launches inside solve/iterate.
+ * enable: 1/0 switches recording and clears the log, -1 leaves it; which: 1 Jacobian-mode K1, 0 cost-only K1.
+ * total_ms/count (optional) receive the summed device time and number of recorded launches. */
+int pxr_ba_kernel_timing(pxr_ba* ba, int enable, int which, double* total_ms, int* count);
 int pxr_ba_read_params(pxr_ba* ba, double* cam_params, double* qvec, double* tvec, double* xyz);
 int pxr_ba_destroy(pxr_ba* ba);
 /* one-shot convenience = FeatureReferenceBundleOptimizer.run: upload, solve, write back into desc arrays */
@@ -259,6 +268,9 @@ int pxr_synth_patches_device(pxr_ctx* ctx, void** d_patches_out, int64_t n_patch
                              const int64_t* field_id /*[n] which smooth field (point id)*/,
                              uint64_t seed, double noise_sigma);
 int pxr_device_free(pxr_ctx* ctx, void* dptr);
+/* pinned host staging buffers for callers that want full PCIe bandwidth on the patch upload */
+int pxr_host_alloc_pinned(void** out, size_t bytes);
+int pxr_host_free_pinned(void* p);
 int pxr_memcpy_d2h(pxr_ctx* ctx, void* host, const void* dev, size_t bytes);
 
 /* ---- reference extraction ----------------------------------------------

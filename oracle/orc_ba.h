@@ -328,13 +328,16 @@ class BAEvaluator : public TREvaluator {
       std::fill(Hpp.begin(), Hpp.end(), 0.0);
       std::fill(gp.begin(), gp.end(), 0.0);
     }
+    // small systems: per-thread accumulators (deterministic given the schedule); large systems:
+    // atomic adds into the shared blocks (what ceres' SchurEliminator does with block locks)
+    const bool shared_acc = (size_t)nc * nc > (size_t)256 * 256;
     std::vector<std::vector<double>> tH(with_jac ? nthreads : 0), tg(with_jac ? nthreads : 0);
 #pragma omp parallel reduction(+ : total)
     {
       const int tid = omp_get_thread_num();
       std::vector<double> r, Jc, Jp, Jamb, scratch;
       int cols[kMaxDc];
-      if (with_jac) { tH[tid].assign((size_t)nc * nc, 0.0); tg[tid].assign(nc, 0.0); }
+      if (with_jac && !shared_acc) { tH[tid].assign((size_t)nc * nc, 0.0); tg[tid].assign(nc, 0.0); }
 #pragma omp for schedule(dynamic, 16)
       for (int64_t p = 0; p < d.n_points; ++p) {
         for (int64_t o = L.pt_begin[p]; o < L.pt_begin[p + 1]; ++o) {
@@ -345,15 +348,22 @@ class BAEvaluator : public TREvaluator {
           if (!with_jac) continue;
           const int C = d.channels;
           const bool pvar = L.point_off[p] >= 0;
-          double* Hc = tH[tid].data(); double* g = tg[tid].data();
+          double* Hc = shared_acc ? Hcc.data() : tH[tid].data();
+          double* g = shared_acc ? gc.data() : tg[tid].data();
           for (int a = 0; a < dc; ++a) {
             double ga = 0;
             for (int i = 0; i < C; ++i) ga += Jc[(size_t)i * kMaxDc + a] * r[i];
-            g[cols[a]] += ga;
+            if (shared_acc) {
+#pragma omp atomic
+              g[cols[a]] += ga;
+            } else g[cols[a]] += ga;
             for (int b = 0; b < dc; ++b) {
               double v = 0;
               for (int i = 0; i < C; ++i) v += Jc[(size_t)i * kMaxDc + a] * Jc[(size_t)i * kMaxDc + b];
-              Hc[(size_t)cols[a] * nc + cols[b]] += v;
+              if (shared_acc) {
+#pragma omp atomic
+                Hc[(size_t)cols[a] * nc + cols[b]] += v;
+              } else Hc[(size_t)cols[a] * nc + cols[b]] += v;
             }
           }
           Wdc[o] = dc;

@@ -134,6 +134,23 @@ int pxr_ctx_sync(pxr_ctx* ctx) {
   PXR_CUDA(cudaStreamSynchronize(ctx->stream));
   return PXR_OK;
 }
+int pxr_ctx_timer_start(pxr_ctx* ctx) {
+  if (!ctx) return fail(PXR_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->ev0) { PXR_CUDA(cudaEventCreate(&ctx->ev0)); PXR_CUDA(cudaEventCreate(&ctx->ev1)); }
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  PXR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  return PXR_OK;
+}
+int pxr_ctx_timer_stop(pxr_ctx* ctx, double* elapsed_ms) {
+  if (!ctx || !ctx->ev0 || !elapsed_ms) return fail(PXR_ERR_INVALID_ARGUMENT, "timer not started");
+  PXR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  PXR_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0;
+  PXR_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *elapsed_ms = ms;
+  return PXR_OK;
+}
 int64_t pxr_ctx_kernel_launches(pxr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 void pxr_default_interp_config(pxr_interp_config* c) {
@@ -158,6 +175,15 @@ void pxr_default_ka_options(pxr_solver_options* o) {
 int pxr_device_free(pxr_ctx* ctx, void* dptr) {
   if (ctx) cudaSetDevice(ctx->device);
   if (dptr) PXR_CUDA(cudaFree(dptr));
+  return PXR_OK;
+}
+int pxr_host_alloc_pinned(void** out, size_t bytes) {
+  if (!out) return fail(PXR_ERR_INVALID_ARGUMENT, "out is NULL");
+  PXR_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return PXR_OK;
+}
+int pxr_host_free_pinned(void* p) {
+  if (p) PXR_CUDA(cudaFreeHost(p));
   return PXR_OK;
 }
 int pxr_memcpy_d2h(pxr_ctx* ctx, void* host, const void* dev, size_t bytes) {

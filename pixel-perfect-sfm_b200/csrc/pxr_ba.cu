@@ -214,7 +214,13 @@ int BA::fm(int mode, double* residuals_out, double* cost_dev /* device scalar */
   a.l2_normalize = interp.l2_normalize;
   int np = 0;
   if (n_obs > 0) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (time_kernels) {
+      PXR_CUDA(cudaEventCreate(&e0)); PXR_CUDA(cudaEventCreate(&e1));
+      PXR_CUDA(cudaEventRecord(e0, ctx->stream));
+    }
     PXR_TRY(launch_fm_eval(ctx, dtype, C, mode, interp.use_float_simd != 0, a, &np));
+    if (time_kernels) { PXR_CUDA(cudaEventRecord(e1, ctx->stream)); timed[mode ? 1 : 0].push_back({e0, e1}); }
     PXR_LAUNCH(ctx, reduce_partials_kernel, 1, 1024, 0, partials.p, (int64_t)np, cost_dev);
   } else {
     PXR_CUDA(cudaMemsetAsync(cost_dev, 0, 8, ctx->stream));
@@ -376,134 +382,150 @@ int BA::gradient_max_norm(double* out) {
 
 // -------------------------------------------------------------------------------- LM driver
 // Mirrors ceres::internal::TrustRegionMinimizer::Minimize (Ceres 2.1) with
-// LevenbergMarquardtStrategy, monotonic steps, Jacobi scaling, inner iterations.
-int BA::solve(pxr_summary* sum) {
-  using clk = std::chrono::steady_clock;
-  const auto t0 = clk::now();
+// LevenbergMarquardtStrategy, monotonic steps, Jacobi scaling, inner iterations.  The loop state
+// lives in the BA object so that a solve can be continued (pxr_ba_iterate) — bench.py times K
+// consecutive iterations of one trajectory after W warm-up iterations.
+int BA::lm_begin() {
   PXR_CUDA(cudaSetDevice(ctx->device));
-  const int64_t launches0 = ctx->launches;
-  std::vector<pxr_iteration_summary> its;
-  int term = 1;
-  std::string message = "Maximum number of iterations reached.";
-  int n_succ = 0, n_unsucc = 0, n_inner = 0;
-
-  double x_cost = 0, candidate_cost = 0, model_cost_change = 0;
-  double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
-  bool inner_enabled = opt.use_inner_iterations != 0;
-  int num_invalid = 0;
-
+  lm = LMState();
+  lm.radius = opt.initial_trust_region_radius;
+  lm.inner_enabled = opt.use_inner_iterations != 0;
   // ---- IterationZero
-  PXR_TRY(evaluate(cur, true, &x_cost));
-  if (!std::isfinite(x_cost)) return fail(PXR_ERR_NUMERIC, "initial cost is not finite");
+  PXR_TRY(evaluate(cur, true, &lm.x_cost));
+  if (!std::isfinite(lm.x_cost)) return fail(PXR_ERR_NUMERIC, "initial cost is not finite");
   if (nl > 0) PXR_LAUNCH(ctx, ba_scale_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, nl, opt.jacobi_scaling);
-  pxr_iteration_summary it;
-  std::memset(&it, 0, sizeof(it));
-  it.cost = x_cost;
-  PXR_TRY(gradient_max_norm(&it.gradient_max_norm));
-  const double initial_cost = x_cost;
-  double minimum_cost = x_cost;
-  double current_cost = x_cost;
-  double x_norm = 0;
-  bool done = false;
-  auto it_start = clk::now();
+  std::memset(&lm.it, 0, sizeof(lm.it));
+  lm.it.cost = lm.x_cost;
+  PXR_TRY(gradient_max_norm(&lm.it.gradient_max_norm));
+  lm.initial_cost = lm.minimum_cost = lm.current_cost = lm.x_cost;
+  lm.started = true;
+  lm.pending_finalize = true;
+  lm.term = 1;
+  lm.message = "Maximum number of iterations reached.";
+  return PXR_OK;
+}
 
-  auto finalize = [&]() -> bool {
-    if (it.step_is_successful) { ++n_succ; if (x_cost < minimum_cost) minimum_cost = x_cost; }
-    else if (it.iteration > 0) ++n_unsucc;
-    it.trust_region_radius = radius;
-    it.iteration_time_s = std::chrono::duration<double>(clk::now() - it_start).count();
-    its.push_back(it);
-    if (it.iteration >= opt.max_num_iterations) { term = 1; message = "Maximum number of iterations reached."; return false; }
-    if (it.gradient_max_norm <= opt.gradient_tolerance) { term = 0; message = "Gradient tolerance reached."; return false; }
-    if (radius < opt.min_trust_region_radius) { term = 0; message = "Minimum trust region radius reached."; return false; }
-    return true;
-  };
+// FinalizeIterationAndCheckIfMinimizerCanContinue
+bool BA::lm_finalize(int max_iteration) {
+  pxr_iteration_summary& it = lm.it;
+  if (lm.pending_finalize) {
+    if (it.step_is_successful) { ++lm.n_succ; if (lm.x_cost < lm.minimum_cost) lm.minimum_cost = lm.x_cost; }
+    else if (it.iteration > 0) ++lm.n_unsucc;
+    it.trust_region_radius = lm.radius;
+    it.iteration_time_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - lm.it_start).count();
+    lm.its.push_back(it);
+    lm.pending_finalize = false;
+  }
+  if (it.iteration >= max_iteration) { lm.term = 1; lm.message = "Maximum number of iterations reached."; return false; }
+  if (it.gradient_max_norm <= opt.gradient_tolerance) { lm.term = 0; lm.message = "Gradient tolerance reached."; lm.finished = true; return false; }
+  if (lm.radius < opt.min_trust_region_radius) { lm.term = 0; lm.message = "Minimum trust region radius reached."; lm.finished = true; return false; }
+  return true;
+}
 
-  while (!done && finalize()) {
-    it_start = clk::now();
+// Runs LM iterations until iteration index `max_iteration` (absolute) or termination.
+int BA::lm_iterate(int max_iteration) {
+  using clk = std::chrono::steady_clock;
+  if (!lm.started) PXR_TRY(lm_begin());
+  lm.it_start = clk::now();
+  while (!lm.finished && lm_finalize(max_iteration)) {
+    lm.it_start = clk::now();
+    pxr_iteration_summary& it = lm.it;
     const double prev_gmax = it.gradient_max_norm;
     const int iteration = it.iteration + 1;
     std::memset(&it, 0, sizeof(it));
     it.iteration = iteration;
+    lm.pending_finalize = true;
 
     bool valid = false;
-    PXR_TRY(compute_step(radius, &valid, &model_cost_change));
+    double model_cost_change = 0;
+    PXR_TRY(compute_step(lm.radius, &valid, &model_cost_change));
     it.linear_solver_iterations = 1;
     it.step_is_valid = valid;
     if (!valid) {
-      if (++num_invalid >= opt.max_num_consecutive_invalid_steps) {
-        term = 2; message = "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps";
+      if (++lm.num_invalid >= opt.max_num_consecutive_invalid_steps) {
+        lm.term = 2; lm.finished = true;
+        lm.message = "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps";
         break;
       }
-      radius /= decrease_factor; decrease_factor *= 2.0;
-      it.cost = x_cost; it.gradient_max_norm = prev_gmax;
+      lm.radius /= lm.decrease_factor; lm.decrease_factor *= 2.0;
+      it.cost = lm.x_cost; it.gradient_max_norm = prev_gmax;
       continue;
     }
-    num_invalid = 0;
+    lm.num_invalid = 0;
 
-    double step_norm = 0;
+    double step_norm = 0, x_norm = 0, candidate_cost = 0;
     PXR_TRY(apply_step(&step_norm, &x_norm));
     PXR_TRY(evaluate(1 - cur, false, &candidate_cost));
     if (!std::isfinite(candidate_cost)) candidate_cost = std::numeric_limits<double>::max();
 
     bool inner_useful = false;
-    if (inner_enabled && candidate_cost < std::numeric_limits<double>::max()) {
-      ++n_inner;
+    if (lm.inner_enabled && candidate_cost < std::numeric_limits<double>::max()) {
+      ++lm.n_inner;
       PXR_TRY(inner_iterations(1 - cur));
       double inner_cost = 0;
       PXR_TRY(evaluate(1 - cur, false, &inner_cost));
       if (std::isfinite(inner_cost)) {
         model_cost_change += candidate_cost - inner_cost;
-        inner_useful = inner_cost < x_cost;
+        inner_useful = inner_cost < lm.x_cost;
         const double rel = 1.0 - inner_cost / candidate_cost;
-        inner_enabled = rel > opt.inner_iteration_tolerance;
+        lm.inner_enabled = rel > opt.inner_iteration_tolerance;
         candidate_cost = inner_cost;
         PXR_TRY(step_norm_between_sets(&step_norm));
       }
     }
     it.step_norm = step_norm;
     if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
-      term = 0; message = "Parameter tolerance reached."; break;
+      lm.term = 0; lm.message = "Parameter tolerance reached."; lm.finished = true; break;
     }
-    it.cost_change = x_cost - candidate_cost;
-    if (std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) {
-      term = 0; message = "Function tolerance reached."; break;
+    it.cost_change = lm.x_cost - candidate_cost;
+    if (std::fabs(it.cost_change) <= opt.function_tolerance * lm.x_cost) {
+      lm.term = 0; lm.message = "Function tolerance reached."; lm.finished = true; break;
     }
-    it.relative_decrease = (current_cost - candidate_cost) / model_cost_change;
+    it.relative_decrease = (lm.current_cost - candidate_cost) / model_cost_change;
     const bool ok = inner_useful || it.relative_decrease > opt.min_relative_decrease;
     if (ok) {
       cur = 1 - cur;
-      PXR_TRY(evaluate(cur, true, &x_cost));
-      it.cost = x_cost;
+      PXR_TRY(evaluate(cur, true, &lm.x_cost));
+      it.cost = lm.x_cost;
       PXR_TRY(gradient_max_norm(&it.gradient_max_norm));
       it.step_is_successful = 1;
-      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
-      radius = std::min(opt.max_trust_region_radius, radius);
-      decrease_factor = 2.0;
-      current_cost = candidate_cost;
+      lm.radius = lm.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+      lm.radius = std::min(opt.max_trust_region_radius, lm.radius);
+      lm.decrease_factor = 2.0;
+      lm.current_cost = candidate_cost;
     } else {
       it.step_is_successful = 0;
       it.cost = candidate_cost;
       it.gradient_max_norm = prev_gmax;
-      radius /= decrease_factor; decrease_factor *= 2.0;
+      lm.radius /= lm.decrease_factor; lm.decrease_factor *= 2.0;
     }
   }
-  if (x_cost < minimum_cost) minimum_cost = x_cost;
+  if (lm.x_cost < lm.minimum_cost) lm.minimum_cost = lm.x_cost;
   PXR_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (sum) {
-    sum->initial_cost = initial_cost; sum->final_cost = minimum_cost;
-    sum->num_residual_blocks = (int32_t)n_obs; sum->num_residuals = n_obs * C;
-    sum->num_successful_steps = n_succ; sum->num_unsuccessful_steps = n_unsucc;
-    sum->num_inner_iteration_steps = n_inner; sum->termination_type = term;
-    sum->solve_time_s = std::chrono::duration<double>(clk::now() - t0).count();
-    sum->total_time_s = sum->solve_time_s;
-    sum->h2d_bytes = h2d_bytes; sum->d2h_bytes = 0;
-    sum->num_iterations = (int32_t)its.size();
-    const int m = std::min<int>((int)its.size(), sum->iterations ? sum->iterations_capacity : 0);
-    for (int i = 0; i < m; ++i) sum->iterations[i] = its[i];
-    sum->kernel_launches = ctx->launches - launches0;
-    std::snprintf(sum->message, sizeof(sum->message), "%s", message.c_str());
-  }
+  return PXR_OK;
+}
+
+void BA::fill_summary(pxr_summary* sum, double seconds, int64_t launches) {
+  if (!sum) return;
+  sum->initial_cost = lm.initial_cost; sum->final_cost = lm.minimum_cost;
+  sum->num_residual_blocks = (int32_t)n_obs; sum->num_residuals = n_obs * C;
+  sum->num_successful_steps = lm.n_succ; sum->num_unsuccessful_steps = lm.n_unsucc;
+  sum->num_inner_iteration_steps = lm.n_inner; sum->termination_type = lm.term;
+  sum->solve_time_s = seconds; sum->total_time_s = seconds;
+  sum->h2d_bytes = h2d_bytes; sum->d2h_bytes = 0;
+  sum->num_iterations = (int32_t)lm.its.size();
+  const int m = std::min<int>((int)lm.its.size(), sum->iterations ? sum->iterations_capacity : 0);
+  for (int i = 0; i < m; ++i) sum->iterations[i] = lm.its[i];
+  sum->kernel_launches = launches;
+  std::snprintf(sum->message, sizeof(sum->message), "%s", lm.message.c_str());
+}
+
+int BA::solve(pxr_summary* sum) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const int64_t l0 = ctx->launches;
+  PXR_TRY(lm_begin());
+  PXR_TRY(lm_iterate(opt.max_num_iterations));
+  fill_summary(sum, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), ctx->launches - l0);
   return PXR_OK;
 }
 
@@ -539,6 +561,36 @@ int pxr_ba_destroy(pxr_ba* ba) {
 int pxr_ba_solve(pxr_ba* ba, pxr_summary* summary) {
   if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
   return reinterpret_cast<BA*>(ba)->solve(summary);
+}
+int pxr_ba_iterate(pxr_ba* ba, int n_iterations, pxr_summary* summary) {
+  if (!ba || n_iterations < 0) return fail(PXR_ERR_INVALID_ARGUMENT, "bad arguments");
+  BA* b = reinterpret_cast<BA*>(ba);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int64_t l0 = b->ctx->launches;
+  if (!b->lm.started) PXR_TRY(b->lm_begin());
+  PXR_TRY(b->lm_iterate(b->lm.it.iteration + n_iterations));
+  b->fill_summary(summary, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), b->ctx->launches - l0);
+  return PXR_OK;
+}
+int pxr_ba_kernel_timing(pxr_ba* ba, int enable, int which, double* total_ms, int* count) {
+  if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
+  BA* b = reinterpret_cast<BA*>(ba);
+  PXR_CUDA(cudaSetDevice(b->ctx->device));
+  if (total_ms || count) {
+    PXR_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    double tot = 0; int n = 0;
+    for (auto& pr : b->timed[which ? 1 : 0]) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { tot += ms; ++n; }
+    }
+    if (total_ms) *total_ms = tot;
+    if (count) *count = n;
+  }
+  if (enable >= 0) {
+    for (int k = 0; k < 2; ++k) { for (auto& pr : b->timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } b->timed[k].clear(); }
+    b->time_kernels = enable != 0;
+  }
+  return PXR_OK;
 }
 int pxr_ba_read_params(pxr_ba* ba, double* cam_params, double* qvec, double* tvec, double* xyz) {
   if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");

@@ -1,6 +1,8 @@
 // pxr_ba_host.h — host-side state of one featuremetric BA problem resident on the device.
 #pragma once
+#include <chrono>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "pxr_ba_kernels.cuh"
@@ -15,8 +17,21 @@ int fm_max_partials(pxr_ctx* ctx);
 int launch_fm_eval(pxr_ctx* ctx, int dtype, int C, int mode, bool float_simd, const FmEvalArgs& a, int* n_partials);
 int launch_inner(pxr_ctx* ctx, int dtype, int C, bool float_simd, const InnerArgs& a);
 
+struct LMState {
+  bool started = false, finished = false, pending_finalize = false, inner_enabled = false;
+  double x_cost = 0, radius = 1e4, decrease_factor = 2.0, initial_cost = 0, minimum_cost = 0, current_cost = 0;
+  int num_invalid = 0, n_succ = 0, n_unsucc = 0, n_inner = 0, term = 1;
+  pxr_iteration_summary it;
+  std::vector<pxr_iteration_summary> its;
+  std::string message;
+  std::chrono::steady_clock::time_point it_start;
+};
+
 struct BA {
   pxr_ctx* ctx = nullptr;
+  LMState lm;
+  bool time_kernels = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];  // [0] cost-only K1 launches, [1] Jacobian K1 launches
   pxr_interp_config interp;
   pxr_solver_options opt;
   // sizes
@@ -54,6 +69,10 @@ struct BA {
   int gradient_max_norm(double* out);
   int inner_iterations(int set);
   int step_norm_between_sets(double* out);
+  int lm_begin();
+  bool lm_finalize(int max_iteration);
+  int lm_iterate(int max_iteration);
+  void fill_summary(pxr_summary* sum, double seconds, int64_t launches);
   int solve(pxr_summary* sum);
   int read_params(double* cam_o, double* q_o, double* t_o, double* X_o);
 };

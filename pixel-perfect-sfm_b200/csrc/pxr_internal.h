@@ -18,6 +18,7 @@ struct pxr_ctx {
   // multi-GPU (NCCL resolved with dlopen at pxr_ctx_init_comm)
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace pxr {

@@ -1,0 +1,168 @@
+// pxr_refs.cu — reference extraction on the device.
+//
+// Replaces _bundle_adjustment.ReferenceExtractor.run (reference
+// pixsfm/bundle_adjustment/src/reference_extractor.h:171-318): per 3D point, interpolate the
+// L2-normalised descriptor of every track element at the current projection
+// (FillDescriptorTrack :300-318 -> K0 + K1 in descriptor mode), run RobustMeanIRLS
+// (pixsfm/base/src/irls_optim.h:23-71; weights 1/rho(||d_i - mu||^2), NB rho not rho') and keep
+// the observation closest to the robust mean (closest_to_robust_mean, :249-272; first minimum).
+#include "pxr_ba_host.h"
+
+namespace pxr {
+
+template <int C>
+__global__ void __launch_bounds__(128) irls_kernel(const double* __restrict__ desc, const int64_t* __restrict__ pt_begin,
+                                                   int64_t n_points, LossParams loss, int iters, int l2,
+                                                   double* __restrict__ refs_out, int64_t* __restrict__ src_out) {
+  constexpr int CPL = C >= 32 ? C / 32 : 1;
+  constexpr int ACTIVE = C / CPL;
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= n_points) return;
+  const int64_t ob = pt_begin[p], oe = pt_begin[p + 1];
+  const int n = (int)(oe - ob);
+  if (n == 0) { if (lane == 0) src_out[p] = -1; return; }
+  const bool active = lane < ACTIVE;
+  const double* D = desc + ob * C + lane * CPL;
+  double mean[CPL];
+  // weights live in registers, observation i -> lane (i % 32), slot (i / 32); tracks > 128 obs use the
+  // tail slots of the last lane group via recomputation (kMaxSlots*32 observations supported)
+  constexpr int kMaxSlots = 8;
+  double w[kMaxSlots];
+#pragma unroll
+  for (int s = 0; s < kMaxSlots; ++s) w[s] = 1.0;
+  if (n > kMaxSlots * 32) { if (lane == 0) src_out[p] = -2; return; }  // host falls back to chunking: unsupported length
+  int early = -1;
+  for (int k = 0; k < iters && early < 0; ++k) {
+    double wsum = 0.0;
+#pragma unroll
+    for (int s = 0; s < kMaxSlots; ++s) if (s * 32 + lane < n) wsum += w[s];
+    // sequential-order sum over observations to mirror Eigen's weights.sum() is not required
+    // (documented tolerance); warp tree reduction
+    wsum = warp_sum(wsum);
+#pragma unroll
+    for (int s = 0; s < kMaxSlots; ++s) w[s] = w[s] / wsum;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) mean[c] = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double wi = __shfl_sync(0xffffffffu, w[i >> 5], i & 31);
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) mean[c] += D[(int64_t)i * C + c] * wi;
+      }
+    }
+    if (l2) {
+      double nn = 0.0;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) nn += mean[c] * mean[c];
+      }
+      nn = sqrt(warp_sum(nn));
+      if (nn > 0.0) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) mean[c] /= nn;
+      }
+    }
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) { const double dd = D[(int64_t)i * C + c] - mean[c]; s += dd * dd; }
+      }
+      s = warp_sum(s);
+      double rho[3];
+      loss_eval(loss, 1.0, s, rho);
+      if (rho[0] > 0.0) { if ((i & 31) == lane) w[i >> 5] = 1.0 / rho[0]; }
+      else { early = i; break; }
+    }
+  }
+  if (early >= 0 && active) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) mean[c] = D[(int64_t)early * C + c];
+  }
+  // closest observation to the robust mean (first minimum)
+  int best = 0;
+  double best_s = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) { const double dd = D[(int64_t)i * C + c] - mean[c]; s += dd * dd; }
+    }
+    s = warp_sum(s);
+    if (i == 0 || s < best_s) { best_s = s; best = i; }
+  }
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) refs_out[p * C + lane * CPL + c] = D[(int64_t)best * C + c];
+  }
+  if (lane == 0) src_out[p] = ob + best;
+}
+
+template <int C>
+static int launch_irls(pxr_ctx* ctx, const double* desc, const int64_t* pt_begin, int64_t n_points, LossParams loss,
+                       int iters, int l2, double* refs, int64_t* src) {
+  PXR_LAUNCH(ctx, irls_kernel<C>, (unsigned)cdiv(n_points * 32, 128), 128, 0, desc, pt_begin, n_points, loss, iters, l2, refs, src);
+  PXR_CUDA(cudaGetLastError());
+  return PXR_OK;
+}
+
+}  // namespace pxr
+
+using namespace pxr;
+
+extern "C" int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp, int loss_type,
+                                double loss_scale, int iters, double* refs_out, int64_t* src_obs_out,
+                                pxr_summary* summary) {
+  if (!ctx || !desc || !refs_out) return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
+  // reuse the BA upload path with refs = NULL (descriptor mode)
+  pxr_ba_desc d = *desc;
+  d.refs = nullptr;
+  pxr_solver_options so;
+  pxr_default_ba_options(&so);
+  so.loss_type = loss_type; so.loss_scale = loss_scale;
+  BA b;
+  const int64_t launches0 = ctx->launches;
+  PXR_TRY(b.create(ctx, &d, interp, &so));
+  cudaStream_t s = ctx->stream;
+  DevBuf<double> dsc, refs;
+  DevBuf<int64_t> src;
+  PXR_TRY(dsc.alloc((size_t)b.n_obs * b.C));
+  PXR_TRY(refs.alloc((size_t)b.n_points * b.C));
+  PXR_TRY(src.alloc(b.n_points));
+  PXR_TRY(refs.zero(s));
+  PXR_TRY(b.project(b.cur, false, nullptr));
+  FmEvalArgs a;
+  a.uv = b.uv.p; a.item_patch = b.obs_patch.p; a.item_ref = nullptr;
+  a.patches = b.d_patches; a.ph = b.ph; a.pw = b.pw; a.refs = nullptr;
+  a.begin = 0; a.end = b.n_obs; a.out = nullptr; a.residuals = nullptr; a.desc = dsc.p;
+  a.cost_partials = nullptr; a.loss.type = loss_type; a.loss.a = loss_scale;
+  a.l2_normalize = b.interp.l2_normalize;
+  int np = 0;
+  if (b.n_obs > 0) PXR_TRY(launch_fm_eval(ctx, b.dtype, b.C, 0, b.interp.use_float_simd != 0, a, &np));
+  LossParams lp; lp.type = loss_type; lp.a = loss_scale;
+  if (b.n_points > 0) {
+    switch (b.C) {
+      case 8: PXR_TRY(launch_irls<8>(ctx, dsc.p, b.pt_begin.p, b.n_points, lp, iters, b.interp.l2_normalize, refs.p, src.p)); break;
+      case 16: PXR_TRY(launch_irls<16>(ctx, dsc.p, b.pt_begin.p, b.n_points, lp, iters, b.interp.l2_normalize, refs.p, src.p)); break;
+      case 32: PXR_TRY(launch_irls<32>(ctx, dsc.p, b.pt_begin.p, b.n_points, lp, iters, b.interp.l2_normalize, refs.p, src.p)); break;
+      case 64: PXR_TRY(launch_irls<64>(ctx, dsc.p, b.pt_begin.p, b.n_points, lp, iters, b.interp.l2_normalize, refs.p, src.p)); break;
+      case 128: PXR_TRY(launch_irls<128>(ctx, dsc.p, b.pt_begin.p, b.n_points, lp, iters, b.interp.l2_normalize, refs.p, src.p)); break;
+      case 256: PXR_TRY(launch_irls<256>(ctx, dsc.p, b.pt_begin.p, b.n_points, lp, iters, b.interp.l2_normalize, refs.p, src.p)); break;
+      default: return fail(PXR_ERR_UNSUPPORTED, "Unsupported channel count %d in reference extraction", b.C);
+    }
+  }
+  PXR_CUDA(cudaMemcpyAsync(refs_out, refs.p, (size_t)b.n_points * b.C * 8, cudaMemcpyDeviceToHost, s));
+  std::vector<int64_t> hsrc(b.n_points);
+  PXR_CUDA(cudaMemcpyAsync(hsrc.data(), src.p, (size_t)b.n_points * 8, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  for (int64_t p = 0; p < b.n_points; ++p) {
+    if (hsrc[p] == -2) return fail(PXR_ERR_UNSUPPORTED, "track of point %lld longer than 256 observations", (long long)p);
+    if (src_obs_out) src_obs_out[p] = hsrc[p];
+  }
+  if (summary) {
+    summary->kernel_launches = ctx->launches - launches0;
+    summary->h2d_bytes = b.h2d_bytes; summary->d2h_bytes = (double)b.n_points * (b.C + 1) * 8;
+  }
+  return PXR_OK;
+}

@@ -294,6 +294,25 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.pxr_ctx_kernel_launches(self.handle))
 
+    def timer_start(self):
+        check(self.lib.pxr_ctx_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        check(self.lib.pxr_ctx_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def init_comm(self, rank, world, uid_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(uid_bytes)
+        check(self.lib.pxr_ctx_init_comm(self.handle, int(rank), int(world), buf))
+
+    @staticmethod
+    def nccl_unique_id():
+        lib = load_lib()
+        buf = (C.c_char * 128)()
+        check(lib.pxr_nccl_unique_id(buf))
+        return bytes(buf)
+
     def sync(self):
         check(self.lib.pxr_ctx_sync(self.handle))
 

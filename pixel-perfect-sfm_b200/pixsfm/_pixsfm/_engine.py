@@ -66,6 +66,17 @@ class BAHandle:
         _capi.check(self.lib.pxr_ba_solve(self.handle, C.byref(s)))
         return _capi.summary_to_dict(s)
 
+    def iterate(self, n, capacity=512):
+        s = _capi.make_summary(capacity)
+        _capi.check(self.lib.pxr_ba_iterate(self.handle, int(n), C.byref(s)))
+        return _capi.summary_to_dict(s)
+
+    def kernel_timing(self, enable=-1, which=1, read=True):
+        ms = C.c_double(); cnt = C.c_int()
+        _capi.check(self.lib.pxr_ba_kernel_timing(self.handle, int(enable), int(which),
+                                                  C.byref(ms) if read else None, C.byref(cnt) if read else None))
+        return ms.value, cnt.value
+
     def read_params(self):
         """Copies the current device parameters back into the BAProblem arrays."""
         p = self.problem
@@ -86,3 +97,36 @@ def ba_run(problem, interp=None, options=None, ctx=None, capacity=512):
     s = _capi.make_summary(capacity)
     _capi.check(ctx.lib.pxr_ba_run(ctx.handle, C.byref(d), C.byref(interp), C.byref(options), C.byref(s)))
     return _capi.summary_to_dict(s)
+
+
+def refs_compute(problem, interp=None, loss_type=1, loss_scale=0.25, iters=100, ctx=None):
+    """pxr_refs_compute == ReferenceExtractor.run: -> (refs [n_points,C] f64, src_obs [n_points])"""
+    ctx = ctx or _capi.default_context()
+    interp = interp or _capi.default_interp()
+    d = problem.desc()
+    refs = np.zeros((len(problem.xyz), problem.channels))
+    src = np.zeros(len(problem.xyz), np.int64)
+    s = _capi.make_summary(0)
+    _capi.check(ctx.lib.pxr_refs_compute(ctx.handle, C.byref(d), C.byref(interp), int(loss_type), C.c_double(loss_scale),
+                                         int(iters), _p(refs), _p(src), C.byref(s)))
+    return refs, src
+
+
+def synth_patches_device(n_patches, ps, channels, uv0, field_id, seed=0, noise=0.01, ctx=None):
+    """Device-side synthetic patch slab (fp16). Returns the device pointer (int)."""
+    ctx = ctx or _capi.default_context()
+    uv0 = np.ascontiguousarray(uv0, np.float64); field_id = np.ascontiguousarray(field_id, np.int64)
+    out = C.c_void_p()
+    _capi.check(ctx.lib.pxr_synth_patches_device(ctx.handle, C.byref(out), C.c_int64(n_patches), int(ps), int(channels),
+                                                 _p(uv0), _p(field_id), C.c_uint64(seed), C.c_double(noise)))
+    return out.value
+
+
+def device_free(ptr, ctx=None):
+    ctx = ctx or _capi.default_context()
+    _capi.check(ctx.lib.pxr_device_free(ctx.handle, C.c_void_p(ptr)))
+
+
+def memcpy_d2h(host_array, dev_ptr, nbytes, ctx=None):
+    ctx = ctx or _capi.default_context()
+    _capi.check(ctx.lib.pxr_memcpy_d2h(ctx.handle, _p(host_array), C.c_void_p(dev_ptr), C.c_size_t(nbytes)))
