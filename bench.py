@@ -26,6 +26,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "pixel-perfect-sfm_b200"))
 
+
+def usable_cpus():
+    """host threads this process may really use: affinity mask capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
+# the CPU baseline uses OpenMP: no busy-waiting worker threads, bind nothing
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
+
 ALGO_BYTES_PER_OBS = 4736  # SURVEY.md §8d: 16 taps x 128 ch x 2 B + fp32-equivalent ref 512 B + 128 B metadata
 
 
@@ -170,6 +187,7 @@ def cpu_arm(args, g, d_patches, refs, ctx, steps, label):
     prob.refs = np.ascontiguousarray(refs[:n_pts])
     ic = _capi.default_interp()
     so = _capi.default_ba_options(use_inner_iterations=0 if args.no_inner else 1, max_num_iterations=steps)
+    O.lib().orc_set_num_threads(usable_cpus())
     cores = O.lib().orc_num_threads()
     t0 = time.time()
     s = O.ba_solve(prob, ic, so)
@@ -254,6 +272,14 @@ def main():
     wall = time.time() - t0
     launches = ctx.kernel_launches() - launches0
     clocks = sampler.stop()
+    stage_names = ["K1 cost-only", "K1 residual/Jacobian", "K0 projection", "block build", "damping+Schur assembly",
+                   "Cholesky factor", "Cholesky solve", "back-substitution+model cost", "manifold plus",
+                   "inner iterations", "cost reduction", "misc"]
+    stage_ms = {}
+    for sid, nm in enumerate(stage_names):
+        tms, tn = h.kernel_timing(enable=-1, which=sid)
+        if tn:
+            stage_ms[nm] = {"ms_per_step": tms / max(1, args.steps), "launch_groups": tn}
     k1_ms, k1_n = h.kernel_timing(enable=0, which=1)
     if dist is not None:
         import torch
@@ -338,7 +364,7 @@ def main():
                 "n_gpus": world, "steps": steps_done, "warmup": args.warmup, "ms_per_step": ms / max(1, steps_done),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp16 taps, fp32 horizontal, fp64 vertical/solve)",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cb,
+                "roofline": roofline, "cpu_baseline": cb, "stage_ms": stage_ms,
                 "lm": {"successful_steps": int(sum(i["step_is_successful"] for i in its)), "steps": steps_done,
                        "cost_first": its[0]["cost"] if its else None, "cost_last": its[-1]["cost"] if its else None,
                        "wall_ms_per_step": 1e3 * wall / max(1, steps_done)},

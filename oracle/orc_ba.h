@@ -49,22 +49,51 @@ inline void QuaternionPlusJacobian(const double* x, double* J /*4x3 row-major*/)
 }
 
 inline bool CholeskySolveInPlace(int n, std::vector<double>& A, std::vector<double>& b) {
-  // A row-major symmetric (lower used); overwritten by L.
-  for (int j = 0; j < n; ++j) {
-    double d = A[(size_t)j * n + j];
-    for (int k = 0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
-    if (!(d > 0.0) || !std::isfinite(d)) return false;
-    d = std::sqrt(d);
-    A[(size_t)j * n + j] = d;
-#pragma omp parallel for schedule(static) if (n - j > 256)
-    for (int i = j + 1; i < n; ++i) {
-      double s = A[(size_t)i * n + j];
-      const double* ai = &A[(size_t)i * n];
-      const double* aj = &A[(size_t)j * n];
-      for (int k = 0; k < j; ++k) s -= ai[k] * aj[k];
-      A[(size_t)i * n + j] = s / d;
+  // A row-major symmetric (lower used); overwritten by L.  Blocked right-looking factorization:
+  // three parallel regions per 64-wide panel (what a threaded LAPACK dpotrf does).
+  const int NB = 64;
+  bool ok = true;
+  for (int k0 = 0; k0 < n && ok; k0 += NB) {
+    const int kb = std::min(NB, n - k0);
+    // diagonal block (serial)
+    for (int j = k0; j < k0 + kb; ++j) {
+      double d = A[(size_t)j * n + j];
+      for (int k = k0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+      if (!(d > 0.0) || !std::isfinite(d)) { ok = false; break; }
+      d = std::sqrt(d);
+      A[(size_t)j * n + j] = d;
+      for (int i = j + 1; i < k0 + kb; ++i) {
+        double s = A[(size_t)i * n + j];
+        for (int k = k0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+        A[(size_t)i * n + j] = s / d;
+      }
+    }
+    if (!ok) break;
+    const int r0 = k0 + kb;
+    // panel: rows below, X L_kk^T = A_ik
+#pragma omp parallel for schedule(static) if (n - r0 > 128)
+    for (int i = r0; i < n; ++i) {
+      double* ai = &A[(size_t)i * n];
+      for (int j = k0; j < k0 + kb; ++j) {
+        double s = ai[j];
+        const double* aj = &A[(size_t)j * n];
+        for (int k = k0; k < j; ++k) s -= ai[k] * aj[k];
+        ai[j] = s / aj[j];
+      }
+    }
+    // trailing update: A_ij -= L_ik L_jk^T, i >= j >= r0
+#pragma omp parallel for schedule(dynamic, 8) if (n - r0 > 128)
+    for (int i = r0; i < n; ++i) {
+      double* ai = &A[(size_t)i * n];
+      for (int j = r0; j <= i; ++j) {
+        const double* aj = &A[(size_t)j * n];
+        double s = 0;
+        for (int k = k0; k < k0 + kb; ++k) s += ai[k] * aj[k];
+        ai[j] -= s;
+      }
     }
   }
+  if (!ok) return false;
   for (int i = 0; i < n; ++i) {
     double s = b[i];
     for (int k = 0; k < i; ++k) s -= A[(size_t)i * n + k] * b[k];

@@ -196,6 +196,7 @@ int BA::project(int set, bool jac, double* xy_out) {
   a.obs_begin = 0; a.obs_end = n_obs;
   a.uv = uv.p; a.xy = xy_out; a.juv = jac ? juv.p : nullptr; a.juv_stride = juv_stride; a.juv_k = K;
   if (n_obs == 0) return PXR_OK;
+  StageScope st(this, 2);
   if (jac) PXR_LAUNCH(ctx, ba_project_kernel<true>, (unsigned)cdiv(n_obs, 128), 128, 0, a);
   else PXR_LAUNCH(ctx, ba_project_kernel<false>, (unsigned)cdiv(n_obs, 128), 128, 0, a);
   PXR_CUDA(cudaGetLastError());
@@ -209,19 +210,16 @@ int BA::fm(int mode, double* residuals_out, double* cost_dev /* device scalar */
   a.refs = has_refs ? refs.p : nullptr;
   a.begin = 0; a.end = n_obs;
   a.out = obs_out.p; a.residuals = residuals_out; a.desc = nullptr;
-  a.cost_partials = partials.p;
   a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
   a.l2_normalize = interp.l2_normalize;
   int np = 0;
   if (n_obs > 0) {
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (time_kernels) {
-      PXR_CUDA(cudaEventCreate(&e0)); PXR_CUDA(cudaEventCreate(&e1));
-      PXR_CUDA(cudaEventRecord(e0, ctx->stream));
-    }
-    PXR_TRY(launch_fm_eval(ctx, dtype, C, mode, interp.use_float_simd != 0, a, &np));
-    if (time_kernels) { PXR_CUDA(cudaEventRecord(e1, ctx->stream)); timed[mode ? 1 : 0].push_back({e0, e1}); }
-    PXR_LAUNCH(ctx, reduce_partials_kernel, 1, 1024, 0, partials.p, (int64_t)np, cost_dev);
+    { StageScope st(this, mode ? 1 : 0);
+      PXR_TRY(launch_fm_eval(ctx, dtype, C, mode, interp.use_float_simd != 0, a, &np)); }
+    StageScope st2(this, 10);
+    const int cb = std::min<int>(fm_max_partials(ctx), ctx->sm_count * 8);
+    PXR_LAUNCH(ctx, cost_from_sq_norm_kernel, cb, 256, 0, obs_out.p, (int64_t)0, n_obs, a.loss, partials.p);
+    PXR_LAUNCH(ctx, reduce_partials_kernel, 1, 1024, 0, partials.p, (int64_t)cb, cost_dev);
   } else {
     PXR_CUDA(cudaMemsetAsync(cost_dev, 0, 8, ctx->stream));
   }
@@ -254,6 +252,7 @@ BADev BA::dev() {
 }
 
 int BA::build() {
+  StageScope st(this, 3);
   PXR_TRY(Hcc.zero(ctx->stream));
   PXR_TRY(gc.zero(ctx->stream));
   if (n_points > 0) PXR_LAUNCH(ctx, ba_build_kernel, (unsigned)cdiv(n_points, 128), 128, 0, dev());
@@ -270,6 +269,7 @@ int BA::build() {
 int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   cudaStream_t s = ctx->stream;
   BADev d = dev();
+  StageScope* st = new StageScope(this, 4);
   if (nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, D2.p, nl, radius,
                          opt.min_lm_diagonal, opt.max_lm_diagonal);
   PXR_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), s));
@@ -287,21 +287,25 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
     PXR_LAUNCH(ctx, ba_add_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p, gc.p, D2.p, S.p, rhs.p, nc);
   }
+  delete st; st = new StageScope(this, 5);
   const int nb = (int)cdiv(nc, kNB);
   for (int k = 0; k < nb; ++k) {
     PXR_LAUNCH(ctx, chol_panel_kernel, nb - k, kNB * kNB, 0, S.p, nc, k, flags.p + 1);
     const int rem = nb - (k + 1);
     if (rem > 0) PXR_LAUNCH(ctx, chol_update_kernel, rem * (rem + 1) / 2, kNB * kNB, 0, S.p, nc, k);
   }
+  delete st; st = new StageScope(this, 6);
   if (nc > 0) {
     PXR_LAUNCH(ctx, chol_solve_kernel, 1, 1024, 0, S.p, rhs.p, nc);
     PXR_CUDA(cudaMemcpyAsync(delta.p, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
   }
+  delete st; st = new StageScope(this, 7);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
   if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points, 128), 128, 0, d, D2.p, delta.p, scalars.p + 4);
   PXR_TRY(allreduce_f64(ctx, scalars.p + 4, 1));
   if (nc > 0) PXR_LAUNCH(ctx, ba_cam_model_kernel, (unsigned)cdiv(nc, 256), 256, 0, Hcc.p, gc.p, delta.p, nc, scalars.p + 4);
   PXR_CUDA(cudaGetLastError());
+  delete st;
   double acc = 0;
   int fl[4];
   PXR_CUDA(cudaMemcpyAsync(&acc, scalars.p + 4, 8, cudaMemcpyDeviceToHost, s));
@@ -322,6 +326,7 @@ int BA::apply_step(double* step_norm, double* x_norm) {
   a.cam = cam[cur].p; a.q = q[cur].p; a.t = t[cur].p; a.X = X[cur].p;
   a.cam_o = cam[1 - cur].p; a.q_o = q[1 - cur].p; a.t_o = t[1 - cur].p; a.X_o = X[1 - cur].p;
   a.delta = delta.p; a.acc = scalars.p + 4;
+  StageScope st(this, 8);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 5, 0, 2 * 8, ctx->stream));
   const int64_t n = std::max<int64_t>(std::max<int64_t>(n_points, n_images), n_cameras);
   PXR_LAUNCH(ctx, ba_plus_kernel, (unsigned)cdiv(n, 128), 128, 0, a);
@@ -351,6 +356,7 @@ int BA::inner_iterations(int set) {
   a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
   a.l2_normalize = interp.l2_normalize;
   if (n_points == 0) return PXR_OK;
+  StageScope st(this, 9);
   return launch_inner(ctx, dtype, C, interp.use_float_simd != 0, a);
 }
 
@@ -579,7 +585,8 @@ int pxr_ba_kernel_timing(pxr_ba* ba, int enable, int which, double* total_ms, in
   if (total_ms || count) {
     PXR_CUDA(cudaStreamSynchronize(b->ctx->stream));
     double tot = 0; int n = 0;
-    for (auto& pr : b->timed[which ? 1 : 0]) {
+    if (which < 0 || which >= BA::kNumStages) return fail(PXR_ERR_INVALID_ARGUMENT, "bad stage id");
+    for (auto& pr : b->timed[which]) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { tot += ms; ++n; }
     }
@@ -587,7 +594,7 @@ int pxr_ba_kernel_timing(pxr_ba* ba, int enable, int which, double* total_ms, in
     if (count) *count = n;
   }
   if (enable >= 0) {
-    for (int k = 0; k < 2; ++k) { for (auto& pr : b->timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } b->timed[k].clear(); }
+    for (int k = 0; k < BA::kNumStages; ++k) { for (auto& pr : b->timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } b->timed[k].clear(); }
     b->time_kernels = enable != 0;
   }
   return PXR_OK;

@@ -30,8 +30,19 @@ struct LMState {
 struct BA {
   pxr_ctx* ctx = nullptr;
   LMState lm;
+  // optional CUDA-event timing of the LM stages (pxr_ba_kernel_timing): 0 K1 cost-only, 1 K1 Jacobian,
+  // 2 projection K0, 3 block build, 4 damping+Schur assembly, 5 Cholesky factor, 6 Cholesky solve,
+  // 7 back-substitution+model cost, 8 manifold plus, 9 inner iterations, 10 cost reduction, 11 misc
+  static constexpr int kNumStages = 12;
   bool time_kernels = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];  // [0] cost-only K1 launches, [1] Jacobian K1 launches
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[kNumStages];
+  struct StageScope {
+    BA* b; int id; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    StageScope(BA* b_, int id_) : b(b_), id(id_) {
+      if (b->time_kernels && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, b->ctx->stream);
+    }
+    ~StageScope() { if (e0 && e1) { cudaEventRecord(e1, b->ctx->stream); b->timed[id].push_back({e0, e1}); } }
+  };
   pxr_interp_config interp;
   pxr_solver_options opt;
   // sizes

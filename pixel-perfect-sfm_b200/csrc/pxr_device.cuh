@@ -45,6 +45,33 @@ __device__ __forceinline__ void spline_f32(float p0, float p1, float p2, float p
   }
 }
 
+// Packed fp32x2 variant (Blackwell FFMA2, sm_100a): two channels per instruction, bit-identical
+// lanes.  Signs are folded into the constants so that no explicit negation is needed:
+// fma(3,p1,-p0) == -fma(-3,p1,p0) exactly, etc.
+template <bool DERIV>
+__device__ __forceinline__ void spline_f32x2(float2 p0, float2 p1, float2 p2, float2 p3,
+                                             const SplineCoefF32& c, float2& f, float2& d) {
+  const float2 m3 = make_float2(-3.0f, -3.0f), m4 = make_float2(-4.0f, -4.0f), m25 = make_float2(-2.5f, -2.5f);
+  const float2 m1 = make_float2(-1.0f, -1.0f), mh = make_float2(-0.5f, -0.5f), ph = make_float2(0.5f, 0.5f);
+  const float2 nt1 = __ffma2_rn(m3, p1, p0);    // -t1
+  const float2 nt2 = __ffma2_rn(m3, p2, p3);    // -t2
+  const float2 nt4 = __ffma2_rn(m4, p2, p3);    // -t4
+  const float2 nt5 = __ffma2_rn(m25, p1, p0);   // -t5
+  const float2 t6 = __ffma2_rn(m1, p0, p2);
+  const float2 t3 = __ffma2_rn(m1, nt1, nt2);   // t1 - t2 (single rounding, == fsub)
+  const float2 b = __ffma2_rn(mh, nt4, nt5);    // 0.5*t4 - t5
+  const float2 xh = make_float2(c.xhalf, c.xhalf), x2 = make_float2(c.x2s, c.x2s);
+  const float2 t7 = __ffma2_rn(xh, t6, p1);
+  const float2 t8 = __ffma2_rn(xh, t3, b);
+  f = __ffma2_rn(x2, t8, t7);
+  if (DERIV) {
+    const float2 fx = make_float2(c.fourx, c.fourx), o5 = make_float2(c.onefivex2, c.onefivex2);
+    const float2 t9 = __ffma2_rn(fx, b, t6);
+    const float2 t10 = __fmul2_rn(o5, t3);
+    d = __ffma2_rn(ph, t9, t10);
+  }
+}
+
 // f64-in overload (:56-121)
 struct SplineCoefF64 {
   double x2s, fourx, xhalf, onefivex2;
@@ -356,6 +383,32 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+
+// Transposed reduction of 8 per-lane doubles over the warp: 9 double shuffles instead of 40.
+// On return lane L holds the total of value index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1).
+__device__ __forceinline__ double warp_reduce8_transposed(const double v[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  double a[4], b[2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double keep = b4 ? v[4 + j] : v[j];
+    const double send = b4 ? v[j] : v[4 + j];
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double keep = b3 ? a[2 + j] : a[j];
+    const double send = b3 ? a[j] : a[2 + j];
+    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const double keep = b2 ? b[1] : b[0];
+  const double send = b2 ? b[0] : b[1];
+  double c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
 }
 
 }  // namespace pxr

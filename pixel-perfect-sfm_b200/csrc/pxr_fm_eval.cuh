@@ -83,17 +83,22 @@ struct FmEvalArgs {
   double* out;                 // [n][8]: s, b_u, b_v, a_uu, a_uv, a_vv, 0, 0  (JAC) / only s (COST)
   double* residuals;           // optional [n][C]
   double* desc;                // optional [n][C]: interpolated (normalised) descriptor f (reference extraction)
-  double* cost_partials;       // [gridDim.x * warps] 0.5*rho(s) partial sums, or null
   LossParams loss;
   int l2_normalize;
 };
 
 constexpr int kFmStages = 2;   // TMA ring slots per warp
+struct FmAux {                 // per-item window geometry, one entry per lane of a batch
+  double xc, xr;
+  const uint8_t* src;
+  const double* ref;
+  int col, row;
+};
 // warps per CTA so that the ring fits in ~128 KiB of shared memory
 template <typename T, int C> struct FmCfg {
   static constexpr int kSlot = 16 * C * (int)sizeof(T);
   static constexpr int kWarps = kSlot <= 4096 ? 16 : (kSlot <= 8192 ? 8 : (kSlot <= 16384 ? 4 : 2));
-  static constexpr int kSmem = kWarps * kFmStages * kSlot + kWarps * kFmStages * 8;
+  static constexpr int kSmem = kWarps * kFmStages * kSlot + kWarps * kFmStages * 8 + kWarps * 32 * (int)sizeof(FmAux);
 };
 
 template <typename T> struct HorizT { typedef float type; };
@@ -173,11 +178,22 @@ __device__ __forceinline__ void bicubic_window(const Addr& addr, int lane, doubl
       load_tap<T, CPL>(addr(i, 3) + loff, p3);
       if (sizeof(H) == 4) {
         const SplineCoefF32 cc(xc);
+        if (CPL % 2 == 0) {
+          // Blackwell packed fp32x2 FMA: two channels per instruction, bit-identical results
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          float ff, dd = 0.f;
-          spline_f32<DERIV>((float)p0[k], (float)p1[k], (float)p2[k], (float)p3[k], cc, ff, dd);
-          hf[i][k] = (H)ff; hd[i][k] = (H)dd;
+          for (int k = 0; k < CPL; k += 2) {
+            float2 ff, dd = make_float2(0.f, 0.f);
+            spline_f32x2<DERIV>(make_float2((float)p0[k], (float)p0[k + 1]), make_float2((float)p1[k], (float)p1[k + 1]),
+                                make_float2((float)p2[k], (float)p2[k + 1]), make_float2((float)p3[k], (float)p3[k + 1]), cc, ff, dd);
+            hf[i][k] = (H)ff.x; hf[i][k + 1] = (H)ff.y; hd[i][k] = (H)dd.x; hd[i][k + 1] = (H)dd.y;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            float ff, dd = 0.f;
+            spline_f32<DERIV>((float)p0[k], (float)p1[k], (float)p2[k], (float)p3[k], cc, ff, dd);
+            hf[i][k] = (H)ff; hd[i][k] = (H)dd;
+          }
         }
       } else {
         const SplineCoefF64 cc(xc);
@@ -242,11 +258,13 @@ __device__ __forceinline__ void bicubic_window(const Addr& addr, int lane, doubl
 }
 
 // PixelInterpolator L2 normalisation + residual + rank-2 reduction for one item, whole warp.
-// Returns (lane-uniform after the shuffles) s and, with DERIV, b_u,b_v,a_uu,a_uv,a_vv.
-template <int CPL, bool DERIV>
-__device__ __forceinline__ void normalize_and_reduce(bool active, bool l2, const double* refp /*lane's CPL refs or null*/,
-                                                     double f[CPL], double fr[CPL], double fc[CPL],
-                                                     double r[CPL], double red[6]) {
+// ALLRED=true : red[0..5] valid in every lane (butterfly all-reduce).
+// ALLRED=false: transposed reduction — returns in lane L the total of value ((L>>4)&1)*4+((L>>3)&1)*2+((L>>2)&1)
+//               (0:s 1:b_u 2:b_v 3:a_uu 4:a_uv 5:a_vv), 9 double shuffles instead of 30.
+template <int CPL, bool DERIV, bool ALLRED>
+__device__ __forceinline__ double normalize_and_reduce(bool active, bool l2, const double* refp /*lane's CPL refs or null*/,
+                                                       double f[CPL], double fr[CPL], double fc[CPL],
+                                                       double r[CPL], double red[6], int lane) {
   if (l2) {
     double n2 = 0.0;
     if (active) {
@@ -267,23 +285,25 @@ __device__ __forceinline__ void normalize_and_reduce(bool active, bool l2, const
       for (int k = 0; k < CPL; ++k) { fc[k] -= dc * f[k]; fr[k] -= dr * f[k]; }
     }
   }
-  double s = 0, bu = 0, bv = 0, auu = 0, auv = 0, avv = 0;
+  double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (active) {
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       r[k] = refp ? f[k] - refp[k] : f[k];
-      s += r[k] * r[k];
+      v[0] += r[k] * r[k];
       if (DERIV) {
-        bu += fc[k] * r[k]; bv += fr[k] * r[k];
-        auu += fc[k] * fc[k]; auv += fc[k] * fr[k]; avv += fr[k] * fr[k];
+        v[1] += fc[k] * r[k]; v[2] += fr[k] * r[k];
+        v[3] += fc[k] * fc[k]; v[4] += fc[k] * fr[k]; v[5] += fr[k] * fr[k];
       }
     }
   }
-  red[0] = warp_sum(s);
-  if (DERIV) {
-    red[1] = warp_sum(bu); red[2] = warp_sum(bv);
-    red[3] = warp_sum(auu); red[4] = warp_sum(auv); red[5] = warp_sum(avv);
+  if (!DERIV) { red[0] = warp_sum(v[0]); return red[0]; }
+  if (ALLRED) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) red[k] = warp_sum(v[k]);
+    return red[0];
   }
+  return warp_reduce8_transposed(v, lane);
 }
 
 // MODE 0: cost only (f), MODE 1: value + derivatives
@@ -300,6 +320,7 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wbase = smem + (size_t)warp * kFmStages * SLOT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kFmWarps * kFmStages * SLOT_BYTES) + warp * kFmStages;
+  FmAux* aux = reinterpret_cast<FmAux*>(smem + (size_t)kFmWarps * kFmStages * SLOT_BYTES + kFmWarps * kFmStages * 8) + warp * 32;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kFmStages; ++s) mbar_init(&bars[s], 1);
@@ -312,32 +333,37 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
   const int64_t warp_global = (int64_t)blockIdx.x * kFmWarps + warp;
   const int64_t warps_total = (int64_t)gridDim.x * kFmWarps;
   uint32_t phase_bits = 0;
-  double cost_acc = 0.0;
   const int64_t patch_bytes = (int64_t)a.ph * a.pw * TAP_BYTES;
+  const bool has_ref = a.refs != nullptr;
 
   for (int64_t batch = warp_global; batch < n_batches; batch += warps_total) {
     const int64_t o = a.begin + batch * 32 + lane;
     const int nvalid = (int)min((int64_t)32, a.end - (a.begin + batch * 32));
-    // ---- phase 1: per-lane window geometry
-    double u = 0.0, v = 0.0;
-    int64_t pidx = 0, ridx = 0;
-    if (lane < nvalid) {
-      u = a.uv[2 * o]; v = a.uv[2 * o + 1];
-      pidx = a.item_patch ? a.item_patch[o] : o;
-      ridx = a.item_ref ? a.item_ref[o] : o;
+    // ---- phase 1: per-lane window geometry, published to the warp through shared memory
+    __syncwarp();
+    {
+      double u = 0.0, v = 0.0;
+      int64_t pidx = 0, ridx = 0;
+      if (lane < nvalid) {
+        u = a.uv[2 * o]; v = a.uv[2 * o + 1];
+        pidx = a.item_patch ? a.item_patch[o] : o;
+        ridx = a.item_ref ? a.item_ref[o] : o;
+      }
+      const double fu = floor(u), fv = floor(v);
+      // guard the int conversion (NaN/huge projections clamp to the border like any far-away tap)
+      FmAux x;
+      x.col = (int)fmin(fmax(fu, -4.0), (double)a.pw + 4.0);
+      x.row = (int)fmin(fmax(fv, -4.0), (double)a.ph + 4.0);
+      x.xc = u - fu; x.xr = v - fv;
+      x.src = a.patches + pidx * patch_bytes;
+      x.ref = has_ref ? a.refs + ridx * C : nullptr;
+      aux[lane] = x;
     }
-    const double fu = floor(u), fv = floor(v);
-    // guard the int conversion (NaN/huge projections clamp to the border like any far-away tap)
-    const int col = (int)fmin(fmax(fu, -4.0), (double)a.pw + 4.0);
-    const int row = (int)fmin(fmax(fv, -4.0), (double)a.ph + 4.0);
-    const double xc = u - fu, xr = v - fv;
-    const uint8_t* pbase = a.patches + pidx * patch_bytes;
+    __syncwarp();
 
     auto issue = [&](int j, int slot) {
-      const int jc = __shfl_sync(0xffffffffu, col, j);
-      const int jr = __shfl_sync(0xffffffffu, row, j);
-      const uint64_t jb = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)pbase, j);
-      const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)jb);
+      const int jc = aux[j].col, jr = aux[j].row;
+      const uint8_t* src = aux[j].src;
       uint8_t* dst = wbase + (size_t)slot * SLOT_BYTES;
       if (lane == 0) mbar_expect_tx(&bars[slot], SLOT_BYTES);
       __syncwarp();
@@ -360,13 +386,10 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       if (s < nvalid) issue(s, s);
     for (int j = 0; j < nvalid; ++j) {
       const int slot = j % kFmStages;
-      const double jxc = __shfl_sync(0xffffffffu, xc, j);
-      const double jxr = __shfl_sync(0xffffffffu, xr, j);
-      const int64_t jref = __shfl_sync(0xffffffffu, (long long)ridx, j);
+      const double jxc = aux[j].xc, jxr = aux[j].xr;
       double refv[CPL];
-      const bool has_ref = a.refs != nullptr;
       if (has_ref && active) {
-        const double* rp = a.refs + jref * C + lane * CPL;
+        const double* rp = aux[j].ref + lane * CPL;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) refv[k] = __ldg(rp + k);
       }
@@ -381,7 +404,7 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       }
       __syncwarp();
       if (j + kFmStages < nvalid) issue(j + kFmStages, slot);  // refill the slot just consumed
-      normalize_and_reduce<CPL, DERIV>(active, a.l2_normalize != 0, has_ref ? refv : nullptr, f, fr, fc, r, red);
+      const double tot = normalize_and_reduce<CPL, DERIV, false>(active, a.l2_normalize != 0, has_ref ? refv : nullptr, f, fr, fc, r, red, lane);
       const int64_t oj = a.begin + batch * 32 + j;
       if (a.residuals && active) {
 #pragma unroll
@@ -391,24 +414,33 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
 #pragma unroll
         for (int k = 0; k < CPL; ++k) a.desc[oj * C + lane * CPL + k] = f[k];
       }
-      if (lane == 0) {
-        if (a.out) {
-          double* op = a.out + oj * 8;
-          if (DERIV) {
-            reinterpret_cast<double2*>(op)[0] = make_double2(red[0], red[1]);
-            reinterpret_cast<double2*>(op)[1] = make_double2(red[2], red[3]);
-            reinterpret_cast<double2*>(op)[2] = make_double2(red[4], red[5]);
-          } else {
-            op[0] = red[0];
-          }
+      if (a.out) {
+        if (DERIV) {
+          // lanes 0,4,..,28 hold s, a_vv?...: value index = bit4*4 + bit3*2 + bit2
+          const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+          if ((lane & 3) == 0 && idx < 6) a.out[oj * 8 + idx] = tot;
+        } else if (lane == 0) {
+          a.out[oj * 8] = tot;
         }
-        double rho[3];
-        loss_eval(a.loss, 1.0, red[0], rho);
-        cost_acc += 0.5 * rho[0];
       }
     }
   }
-  if (a.cost_partials && lane == 0) a.cost_partials[warp_global] = cost_acc;
+}
+
+// cost = sum_i 0.5 * rho(s_i) over items (s at out[i*8]); per-block partials, fixed order
+static __global__ void __launch_bounds__(256) cost_from_sq_norm_kernel(const double* __restrict__ out, int64_t begin, int64_t end,
+                                                                       LossParams loss, double* __restrict__ partials) {
+  double acc = 0.0;
+  for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (int64_t)gridDim.x * blockDim.x) {
+    double rho[3];
+    loss_eval(loss, 1.0, out[i * 8], rho);
+    acc += 0.5 * rho[0];
+  }
+  __shared__ double sh[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; ++k) t += sh[k]; partials[blockIdx.x] = t; }
 }
 
 }  // namespace pxr

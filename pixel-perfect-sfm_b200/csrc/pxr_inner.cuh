@@ -92,7 +92,7 @@ __device__ __forceinline__ void inner_eval(const InnerArgs& a, int64_t p, int la
 #pragma unroll
       for (int k = 0; k < CPL; ++k) { f[k] = 0; fr[k] = 0; fc[k] = 0; r[k] = 0; }
       if (active) bicubic_window<T, C, CPL, true, FS>(win, lane, jxc, jxr, f, fr, fc);
-      normalize_and_reduce<CPL, true>(active, a.l2_normalize != 0, a.refs ? refv : nullptr, f, fr, fc, r, red);
+      normalize_and_reduce<CPL, true, true>(active, a.l2_normalize != 0, a.refs ? refv : nullptr, f, fr, fc, r, red, lane);
       if (lane == j) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) my_red[k] = red[k];

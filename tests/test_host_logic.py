@@ -1,0 +1,119 @@
+"""CPU-side checks of the product library (no compute kernels are launched): the C-ABI loads and
+exports every symbol include/pxr.h declares, the host-side integer algorithms are bit-exact
+against fixtures generated from the reference's own graph.cc, and compute entry points refuse to
+run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import HAS_GPU, ROOT
+from pixsfm._pixsfm import _capi
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _capi.load_lib()
+    hdr = open(os.path.join(ROOT, "include", "pxr.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(pxr_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) > 25
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+@pytest.mark.skipif(HAS_GPU, reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_device():
+    lib = _capi.load_lib()
+    h = C.c_void_p()
+    rc = lib.pxr_ctx_create(-1, C.byref(h))
+    assert rc == _capi.PXR_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.pxr_last_error()
+    with pytest.raises(_capi.PxrError):
+        _capi.Context(-1)
+
+
+def test_graph_labels_bit_exact_vs_reference_fixture():
+    lib = _capi.load_lib()
+    z = np.load(os.path.join(GOLD, "graph_ref.npz"))
+    for g in range(int(z["n_graphs"])):
+        ni = z["g%d_node_image" % g]; es = z["g%d_es" % g]; ed = z["g%d_ed" % g]; sim = z["g%d_sim" % g]
+        n = len(ni)
+        tl = np.zeros(n, np.int64); sc = np.zeros(n); rt = np.zeros(n, np.uint8)
+        assert lib.pxr_graph_track_labels(C.c_int64(n), _p(ni), C.c_int64(len(es)), _p(es), _p(ed), _p(sim), _p(tl)) == 0
+        assert lib.pxr_graph_score_labels(C.c_int64(n), C.c_int64(len(es)), _p(es), _p(ed), _p(sim), _p(tl), _p(sc)) == 0
+        assert lib.pxr_graph_root_labels(C.c_int64(n), _p(tl), _p(sc), _p(rt)) == 0
+        assert np.array_equal(tl, z["g%d_track_labels" % g])
+        assert np.array_equal(sc, z["g%d_scores" % g])
+        assert np.array_equal(rt, z["g%d_is_root" % g])
+
+
+def test_ka_problem_labels_match_python_reference():
+    from collections import Counter
+    import sys
+    lib = _capi.load_lib()
+
+    def ref_labels(track_labels, max_per_problem):  # keypoint_adjustment/main.py:13-57
+        track_count = Counter(track_labels)
+        bins = []; t2p = [-1] * len(track_count); start = 0; last_v = sys.maxsize
+        for k, v in track_count.most_common():
+            if v < last_v:
+                start = 0; last_v = v
+            found = False
+            if v < max_per_problem:
+                for i in range(start, len(bins)):
+                    if bins[i] + v <= max_per_problem:
+                        bins[i] += v; t2p[k] = i; found = True; start = i
+                        break
+            if not found:
+                t2p[k] = len(bins); start = len(bins); bins.append(v)
+        return [t2p[v] for v in track_labels], bins
+
+    rng = np.random.default_rng(2)
+    for trial in range(6):
+        n_tracks = int(rng.integers(3, 300))
+        labels = np.repeat(np.arange(n_tracks), rng.integers(1, 14, n_tracks))
+        rng.shuffle(labels)
+        mp = [50, 10, 13, 50, 7, 50][trial]
+        exp, bins = ref_labels(labels.tolist(), mp)
+        out = np.zeros(len(labels), np.int32); nb = C.c_int32()
+        assert lib.pxr_ka_problem_labels(C.c_int64(len(labels)), _p(labels.astype(np.int64)), mp, _p(out), C.byref(nb)) == 0
+        assert nb.value == len(bins) and out.tolist() == exp
+
+
+def test_shard_points_plan():
+    lib = _capi.load_lib()
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 20, 1000)
+    obs_pt = np.repeat(np.arange(1000, dtype=np.int64), lens)
+    for world in (1, 2, 3, 8):
+        pb = np.zeros(world + 1, np.int64); ob = np.zeros(world + 1, np.int64)
+        assert lib.pxr_shard_points(C.c_int64(1000), C.c_int64(len(obs_pt)), _p(obs_pt), world, _p(pb), _p(ob)) == 0
+        assert pb[0] == 0 and pb[-1] == 1000 and ob[0] == 0 and ob[-1] == len(obs_pt)
+        assert np.all(np.diff(pb) >= 0) and np.all(np.diff(ob) >= 0)
+        for r in range(world):  # a rank owns whole points: its obs range is exactly its points' observations
+            sel = (obs_pt >= pb[r]) & (obs_pt < pb[r + 1])
+            assert sel.sum() == ob[r + 1] - ob[r]
+        assert np.diff(ob).max() - np.diff(ob).min() <= 2 * lens.max() + 1
+    bad = obs_pt[::-1].copy()
+    pb = np.zeros(3, np.int64); ob = np.zeros(3, np.int64)
+    assert lib.pxr_shard_points(C.c_int64(1000), C.c_int64(len(bad)), _p(bad), 2, _p(pb), _p(ob)) == _capi.PXR_ERR_INVALID_ARGUMENT
+
+
+def test_default_option_blocks_match_reference_python_defaults():
+    lib = _capi.load_lib()
+    o = _capi.SolverOptions()
+    lib.pxr_default_ba_options(C.byref(o))
+    ref = _capi.default_ba_options()
+    for f, _t in _capi.SolverOptions._fields_:
+        assert getattr(o, f) == getattr(ref, f), f
+    assert o.loss_type == 1 and o.loss_scale == 0.25 and o.max_num_iterations == 100 and o.use_inner_iterations == 1
+    lib.pxr_default_ka_options(C.byref(o))
+    assert o.parameter_tolerance == 1e-5 and o.use_inner_iterations == 0
