@@ -174,8 +174,9 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   PXR_TRY(juv.alloc((size_t)n_obs * juv_stride));
   PXR_TRY(Hcc.alloc((size_t)nc * nc)); PXR_TRY(gc.alloc(nc));
   PXR_TRY(Hpp.alloc((size_t)n_points * 9)); PXR_TRY(gp.alloc((size_t)n_points * 3));
+  h_obs_img.assign(d->obs_img, d->obs_img + n_obs);
   PXR_TRY(W.alloc((size_t)n_obs * dcmax * 3)); PXR_TRY(Wcols.alloc((size_t)n_obs * dcmax)); PXR_TRY(Wdc.alloc(n_obs));
-  PXR_TRY(S.alloc((size_t)nc * nc)); PXR_TRY(rhs.alloc(nc));
+  PXR_TRY(S.alloc((size_t)(nc + 1) * nc)); PXR_TRY(rhs.alloc(nc));
   PXR_TRY(diag.alloc(nl)); PXR_TRY(jscale.alloc(nl)); PXR_TRY(D2.alloc(nl)); PXR_TRY(delta.alloc(nl));
   PXR_TRY(partials.alloc(fm_max_partials(ctx)));
   PXR_TRY(scalars.alloc(16));
@@ -184,6 +185,70 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   PXR_CUDA(cudaStreamSynchronize(s));
   h2d_bytes = h2d;
   return PXR_OK;
+}
+
+// Static structure of the Schur complement: every pair of observations (i >= j) of a variable point,
+// grouped by the (image_i, image_j) pair they address in the reduced camera system; long groups are
+// split into chunks of at most kChunk entries (one warp each).
+int BA::build_schur_pairs() {
+  if (sp_built) return PXR_OK;
+  PXR_TRY(Tbuf.alloc((size_t)n_obs * dcmax * 3));
+  const int64_t kChunk = 128;
+  const int64_t ni = n_images;
+  auto key_of = [&](int ia, int ib, bool self) -> int64_t {  // ia >= ib
+    return ((int64_t)ia * (ia + 1) / 2 + ib) * 2 + (self ? 1 : 0);
+  };
+  const int64_t n_keys = (ni * (ni + 1) / 2) * 2;
+  std::vector<int64_t> count(n_keys + 1, 0);
+  int64_t total = 0;
+  for (int64_t p = 0; p < n_points; ++p) {
+    if (h_point_off[p] < 0) continue;
+    for (int64_t i = h_pt_begin[p]; i < h_pt_begin[p + 1]; ++i)
+      for (int64_t j = h_pt_begin[p]; j <= i; ++j) {
+        const int a = h_obs_img[i], b = h_obs_img[j];
+        count[key_of(std::max(a, b), std::min(a, b), i == j) + 1]++;
+        ++total;
+      }
+  }
+  if (total >= ((int64_t)1 << 31) || n_obs >= ((int64_t)1 << 31))
+    return fail(PXR_ERR_UNSUPPORTED, "too many observation pairs for 32-bit pair indices");
+  for (int64_t k = 0; k < n_keys; ++k) count[k + 1] += count[k];
+  std::vector<int32_t> px(total), py(total);
+  {
+    std::vector<int64_t> cursor(count.begin(), count.end() - 1);
+    for (int64_t p = 0; p < n_points; ++p) {
+      if (h_point_off[p] < 0) continue;
+      for (int64_t i = h_pt_begin[p]; i < h_pt_begin[p + 1]; ++i)
+        for (int64_t j = h_pt_begin[p]; j <= i; ++j) {
+          const int a = h_obs_img[i], b = h_obs_img[j];
+          const int64_t k = cursor[key_of(std::max(a, b), std::min(a, b), i == j)]++;
+          // x = the observation in the image with the larger index
+          if (a >= b) { px[k] = (int32_t)i; py[k] = (int32_t)j; } else { px[k] = (int32_t)j; py[k] = (int32_t)i; }
+        }
+    }
+  }
+  std::vector<int64_t> cb;
+  std::vector<uint8_t> cself;
+  for (int64_t k = 0; k < n_keys; ++k) {
+    for (int64_t s = count[k]; s < count[k + 1]; s += kChunk) { cb.push_back(s); cself.push_back((uint8_t)(k & 1)); }
+  }
+  cb.push_back(total);
+  sp_n_chunks = (int64_t)cself.size();
+  cudaStream_t s = ctx->stream;
+  PXR_TRY(sp_px.upload(px.data(), px.size(), s));
+  PXR_TRY(sp_py.upload(py.data(), py.size(), s));
+  PXR_TRY(sp_chunk_begin.upload(cb.data(), cb.size(), s));
+  PXR_TRY(sp_chunk_self.upload(cself.data(), cself.size(), s));
+  PXR_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
+  sp_built = true;
+  return PXR_OK;
+}
+
+SchurPairs BA::schur_pairs() {
+  SchurPairs sp;
+  sp.px = sp_px.p; sp.py = sp_py.p; sp.chunk_begin = sp_chunk_begin.p; sp.chunk_self = sp_chunk_self.p;
+  sp.n_chunks = sp_n_chunks;
+  return sp;
 }
 
 // -------------------------------------------------------------------------------- evaluation
@@ -268,6 +333,7 @@ int BA::build() {
 // One LM step attempt at the current linearisation: fills delta, returns validity and model cost change
 int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   cudaStream_t s = ctx->stream;
+  PXR_TRY(build_schur_pairs());
   BADev d = dev();
   StageScope* st = new StageScope(this, 4);
   if (nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, D2.p, nl, radius,
@@ -281,24 +347,27 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     PXR_CUDA(cudaMemsetAsync(S.p, 0, (size_t)nc * nc * 8, s));
     PXR_CUDA(cudaMemsetAsync(rhs.p, 0, (size_t)nc * 8, s));
   }
-  if (n_points > 0) PXR_LAUNCH(ctx, ba_schur_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, S.p, rhs.p, flags.p);
+  if (n_points > 0) {
+    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_points, 128), 128, 0, d, D2.p, Tbuf.p, rhs.p, flags.p);
+    if (sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, 256), 256, 0, d, schur_pairs(), Tbuf.p, S.p);
+  }
   if (ctx->world > 1) {
     PXR_TRY(allreduce_f64(ctx, S.p, (size_t)nc * nc));
     PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
     PXR_LAUNCH(ctx, ba_add_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p, gc.p, D2.p, S.p, rhs.p, nc);
   }
   delete st; st = new StageScope(this, 5);
+  // rhs rides along as row nc of S: the factorisation performs the forward substitution
+  if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
   const int nb = (int)cdiv(nc, kNB);
+  const int nrb = (int)cdiv(nc + 1, kNB);  // row blocks including the rhs row
   for (int k = 0; k < nb; ++k) {
-    PXR_LAUNCH(ctx, chol_panel_kernel, nb - k, kNB * kNB, 0, S.p, nc, k, flags.p + 1);
-    const int rem = nb - (k + 1);
-    if (rem > 0) PXR_LAUNCH(ctx, chol_update_kernel, rem * (rem + 1) / 2, kNB * kNB, 0, S.p, nc, k);
+    PXR_LAUNCH(ctx, chol_panel_kernel, nrb - k, kNB * kNB, 0, S.p, nc, nc + 1, k, flags.p + 1);
+    const int rem = nrb - (k + 1);
+    if (rem > 0) PXR_LAUNCH(ctx, chol_update_kernel, rem * (rem + 1) / 2, kNB * kNB, 0, S.p, nc, nc + 1, k);
   }
   delete st; st = new StageScope(this, 6);
-  if (nc > 0) {
-    PXR_LAUNCH(ctx, chol_solve_kernel, 1, 1024, 0, S.p, rhs.p, nc);
-    PXR_CUDA(cudaMemcpyAsync(delta.p, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
-  }
+  if (nc > 0) PXR_LAUNCH(ctx, chol_backsolve_kernel, 1, 1024, 0, S.p, S.p + (size_t)nc * nc, delta.p, nc);
   delete st; st = new StageScope(this, 7);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
   if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points, 128), 128, 0, d, D2.p, delta.p, scalars.p + 4);
@@ -669,12 +738,16 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
   PXR_CUDA(cudaStreamSynchronize(s));
   if (S || rhs) {
     // the damped Schur system before factorisation: rerun the assembly part only
+    PXR_TRY(b->build_schur_pairs());
     BADev d = b->dev();
     if (b->nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(b->nl, 256), 256, 0, b->diag.p, b->jscale.p, b->D2.p, b->nl, radius,
                               b->opt.min_lm_diagonal, b->opt.max_lm_diagonal);
     if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, b->Hcc.p, b->gc.p, b->D2.p, b->S.p, b->rhs.p, (int)nc);
     PXR_CUDA(cudaMemsetAsync(b->flags.p, 0, 4 * sizeof(int), s));
-    if (b->n_points > 0) PXR_LAUNCH(ctx, ba_schur_kernel, (unsigned)cdiv(b->n_points * 32, 256), 256, 0, d, b->D2.p, b->S.p, b->rhs.p, b->flags.p);
+    if (b->n_points > 0) {
+      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_points, 128), 128, 0, d, b->D2.p, b->Tbuf.p, b->rhs.p, b->flags.p);
+      if (b->sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(b->sp_n_chunks * 32, 256), 256, 0, d, b->schur_pairs(), b->Tbuf.p, b->S.p);
+    }
     if (S) PXR_CUDA(cudaMemcpyAsync(S, b->S.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));
     if (rhs) PXR_CUDA(cudaMemcpyAsync(rhs, b->rhs.p, nc * 8, cudaMemcpyDeviceToHost, s));
     PXR_CUDA(cudaStreamSynchronize(s));

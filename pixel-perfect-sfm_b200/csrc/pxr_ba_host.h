@@ -68,6 +68,16 @@ struct BA {
   // device: per-observation and linearisation
   DevBuf<double> uv, obs_out, juv, Hcc, gc, Hpp, gp, W, S, rhs, diag, jscale, D2, delta, partials, scalars;
   DevBuf<int> flags;
+  // static co-visibility structure for the Schur complement (see ba_schur_pairs_kernel)
+  DevBuf<int32_t> sp_px, sp_py;
+  DevBuf<int64_t> sp_chunk_begin;
+  DevBuf<uint8_t> sp_chunk_self;
+  DevBuf<double> Tbuf;
+  int64_t sp_n_chunks = 0;
+  bool sp_built = false;
+  std::vector<int32_t> h_obs_img;
+  int build_schur_pairs();
+  SchurPairs schur_pairs();
 
   int create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so);
   BADev dev();

@@ -179,121 +179,158 @@ __device__ __forceinline__ bool inv3_sym(const double* H, const double* D2, doub
   return true;
 }
 
-// K3: per-point Schur elimination, one warp per point.
-//   S[cols_i, cols_j] -= W_i (Hpp + D)^-1 W_j^T   (lower triangle only, fp64 atomics)
-//   rhs[cols_i]       += W_i (Hpp + D)^-1 gp
-static __global__ void __launch_bounds__(256) ba_schur_kernel(BADev d, const double* D2, double* S, double* rhs,
-                                                       int* fail_flag) {
-  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// K3: per-point Schur elimination without per-entry atomics.
+//   S[cols_i, cols_j] -= W_i (Hpp + D)^-1 W_j^T ,   rhs[cols_i] += W_i (Hpp + D)^-1 gp
+// K3a (one thread per point): T_i = W_i (Hpp+D)^-1 for every observation of the point, rhs terms.
+// K3b (one warp per co-visibility chunk): all observation pairs (i,j) of all points that fall on
+//      the same (image_i, image_j) pair address the same block of S; the pair list is sorted by that
+//      key once on the host (static sparsity), a warp accumulates the dc_i x dc_j block of a chunk in
+//      registers and touches S once per element.
+static __global__ void __launch_bounds__(128) ba_schur_prep_kernel(BADev d, const double* D2, double* T, double* rhs,
+                                                                   int* fail_flag) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= d.n_points) return;
   const int64_t po = d.point_off[p];
   if (po < 0) return;
   double inv[9];
-  if (!inv3_sym(d.Hpp + p * 9, D2 + po, inv)) { if (lane == 0) *fail_flag = 1; return; }
+  if (!inv3_sym(d.Hpp + p * 9, D2 + po, inv)) { *fail_flag = 1; return; }
   const double g0 = d.gp[p * 3], g1 = d.gp[p * 3 + 1], g2 = d.gp[p * 3 + 2];
-  const double ig[3] = {inv[0] * g0 + inv[1] * g1 + inv[2] * g2, inv[3] * g0 + inv[4] * g1 + inv[5] * g2,
-                        inv[6] * g0 + inv[7] * g1 + inv[8] * g2};
-  const int64_t ob = d.pt_begin[p], oe = d.pt_begin[p + 1];
-  const int L = (int)(oe - ob);
   const int dcm = d.dcmax;
-  // rhs: entries (i, a)
-  for (int e = lane; e < L * dcm; e += 32) {
-    const int i = e / dcm, a = e % dcm;
-    const int64_t o = ob + i;
-    if (a >= d.Wdc[o]) continue;
-    const double* w = d.W + (o * dcm + a) * 3;
-    atomic_add_f64(&rhs[d.Wcols[o * dcm + a]], w[0] * ig[0] + w[1] * ig[1] + w[2] * ig[2]);
+  for (int64_t o = d.pt_begin[p]; o < d.pt_begin[p + 1]; ++o) {
+    const int dc = d.Wdc[o];
+    for (int a = 0; a < dc; ++a) {
+      const double* w = d.W + (o * dcm + a) * 3;
+      const double t0 = w[0] * inv[0] + w[1] * inv[3] + w[2] * inv[6];
+      const double t1 = w[0] * inv[1] + w[1] * inv[4] + w[2] * inv[7];
+      const double t2 = w[0] * inv[2] + w[1] * inv[5] + w[2] * inv[8];
+      double* tp = T + (o * dcm + a) * 3;
+      tp[0] = t0; tp[1] = t1; tp[2] = t2;
+      atomic_add_f64(&rhs[d.Wcols[o * dcm + a]], t0 * g0 + t1 * g1 + t2 * g2);
+    }
   }
-  // S: entries (i, a, j, b) with col_i[a] >= col_j[b]
-  const int64_t total = (int64_t)L * dcm * L * dcm;
-  for (int64_t e = lane; e < total; e += 32) {
-    const int b = (int)(e % dcm);
-    int64_t r = e / dcm;
-    const int j = (int)(r % L); r /= L;
-    const int a = (int)(r % dcm);
-    const int i = (int)(r / dcm);
-    const int64_t oi = ob + i, oj = ob + j;
-    if (a >= d.Wdc[oi] || b >= d.Wdc[oj]) continue;
-    const int ca = d.Wcols[oi * dcm + a], cb = d.Wcols[oj * dcm + b];
-    if (ca < cb) continue;
-    const double* wi = d.W + (oi * dcm + a) * 3;
-    const double* wj = d.W + (oj * dcm + b) * 3;
-    const double t0 = wi[0] * inv[0] + wi[1] * inv[3] + wi[2] * inv[6];
-    const double t1 = wi[0] * inv[1] + wi[1] * inv[4] + wi[2] * inv[7];
-    const double t2 = wi[0] * inv[2] + wi[1] * inv[5] + wi[2] * inv[8];
-    atomic_add_f64(&S[(int64_t)ca * d.nc + cb], -(t0 * wj[0] + t1 * wj[1] + t2 * wj[2]));
+}
+
+struct SchurPairs {
+  const int32_t* px; const int32_t* py;   // observation pair entries, sorted by chunk
+  const int64_t* chunk_begin;             // [n_chunks + 1]
+  const uint8_t* chunk_self;              // [n_chunks] 1: entries are (o,o) self pairs
+  int64_t n_chunks;
+};
+
+static __global__ void __launch_bounds__(256) ba_schur_pairs_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
+                                                                    double* S) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= sp.n_chunks) return;
+  const int64_t kb = sp.chunk_begin[c], ke = sp.chunk_begin[c + 1];
+  if (ke <= kb) return;
+  const int dcm = d.dcmax;
+  const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
+  const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
+  const int nel = dcx * dcy;
+  constexpr int kMaxT = (kMaxDc * kMaxDc + 31) / 32;
+  double acc[kMaxT];
+#pragma unroll
+  for (int t = 0; t < kMaxT; ++t) acc[t] = 0.0;
+  for (int64_t k = kb; k < ke; ++k) {
+    const double* Tx = T + (int64_t)sp.px[k] * dcm * 3;
+    const double* Wy = d.W + (int64_t)sp.py[k] * dcm * 3;
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) {
+      const int e = lane + 32 * t;
+      if (e < nel) {
+        const int a = e / dcy, b = e - a * dcy;
+        acc[t] += Tx[a * 3] * Wy[b * 3] + Tx[a * 3 + 1] * Wy[b * 3 + 1] + Tx[a * 3 + 2] * Wy[b * 3 + 2];
+      }
+    }
+  }
+  const bool self = sp.chunk_self[c] != 0;
+#pragma unroll
+  for (int t = 0; t < kMaxT; ++t) {
+    const int e = lane + 32 * t;
+    if (e >= nel) continue;
+    const int a = e / dcy, b = e - a * dcy;
+    const int ca = d.Wcols[ox0 * dcm + a], cb = d.Wcols[oy0 * dcm + b];
+    const double v = -acc[t];
+    if (self) { if (a >= b) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v); }
+    else if (ca > cb) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v);
+    else if (ca < cb) atomic_add_f64(&S[(int64_t)cb * d.nc + ca], v);
+    else atomic_add_f64(&S[(int64_t)ca * d.nc + ca], 2.0 * v);
   }
 }
 
 // ---------------------------------------------------------------- dense Cholesky (lower, in place)
+// The reduced system is stored as an (n+1) x n row-major array: rows 0..n-1 hold the lower
+// triangle of S, row n holds the right-hand side.  Factorising with the extra row performs the
+// forward substitution for free: after the last panel row n holds y = L^-1 rhs.
 constexpr int kNB = 32;
-// Panel step k: every CTA factors the diagonal block A_kk redundantly in shared memory; CTA 0
-// writes L_kk, CTA b>0 solves its 32-row block  L_bk = A_bk L_kk^-T.
-static __global__ void __launch_bounds__(kNB* kNB) chol_panel_kernel(double* A, int n, int k, int* fail_flag) {
+// Panel step k: every CTA factors the diagonal block A_kk redundantly in shared memory (one warp,
+// warp-synchronous); CTA 0 writes L_kk back, CTA b>0 solves its 32-row block L_bk = A_bk L_kk^-T
+// with one warp per row.
+static __global__ void __launch_bounds__(kNB* kNB) chol_panel_kernel(double* A, int n, int n_rows, int k, int* fail_flag) {
   __shared__ double Lkk[kNB][kNB + 1];
-  __shared__ double Ab[kNB][kNB + 1];
   __shared__ int bad;
-  const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;
+  const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;  // ty = warp id, tx = lane
   const int k0 = k * kNB;
   const int kb = min(kNB, n - k0);
   if (threadIdx.x == 0) bad = 0;
   Lkk[ty][tx] = (ty < kb && tx < kb && tx <= ty) ? A[(int64_t)(k0 + ty) * n + k0 + tx] : (ty == tx ? 1.0 : 0.0);
   __syncthreads();
-  // unblocked right-looking Cholesky on the 32x32 block
-  for (int j = 0; j < kb; ++j) {
-    if (threadIdx.x == 0) {
+  if (ty == 0) {
+    // lane i owns row i of the block
+    for (int j = 0; j < kb; ++j) {
       const double dj = Lkk[j][j];
-      if (!(dj > 0.0) || !isfinite(dj)) { bad = 1; Lkk[j][j] = 1.0; } else Lkk[j][j] = sqrt(dj);
+      if (!(dj > 0.0) || !isfinite(dj)) { if (tx == 0) bad = 1; break; }
+      const double sj = sqrt(dj);
+      double lij = 0.0;
+      if (tx == j) Lkk[j][j] = sj;
+      else if (tx > j && tx < kb) { lij = Lkk[tx][j] / sj; Lkk[tx][j] = lij; }
+      __syncwarp();
+      if (tx > j && tx < kb) {
+#pragma unroll 4
+        for (int c = j + 1; c <= tx; ++c) Lkk[tx][c] -= lij * Lkk[c][j];
+      }
+      __syncwarp();
     }
-    __syncthreads();
-    if (ty == 0 && tx > j && tx < kb) Lkk[tx][j] /= Lkk[j][j];
-    __syncthreads();
-    if (tx > j && ty > j && tx <= ty && ty < kb) Lkk[ty][tx] -= Lkk[ty][j] * Lkk[tx][j];
-    __syncthreads();
   }
+  __syncthreads();
   if (bad) { if (threadIdx.x == 0 && blockIdx.x == 0) *fail_flag = 1; return; }
   const int b = blockIdx.x;
-  if (b == 0) {
-    if (ty < kb && tx < kb && tx <= ty) A[(int64_t)(k0 + ty) * n + k0 + tx] = Lkk[ty][tx];
+  const int r = k0 + b * kNB + ty;
+  if (r < k0 + kb) {  // a row of the diagonal block itself (CTA 0): write the factor back
+    if (tx < kb && tx <= ty) A[(int64_t)r * n + k0 + tx] = Lkk[ty][tx];
     return;
   }
-  const int r0 = k0 + b * kNB;
-  const int rb = min(kNB, n - r0);
-  Ab[ty][tx] = (ty < rb && tx < kb) ? A[(int64_t)(r0 + ty) * n + k0 + tx] : 0.0;
-  __syncthreads();
-  // row ty: x L_kk^T = a  -> forward substitution along tx (done by the tx==0 thread of each row...)
-  // parallel variant: all 32 threads of a row cooperate column by column
+  // rows below the diagonal block (including the appended rhs row): one warp per row
+  if (r >= n_rows) return;
+  double v = tx < kb ? A[(int64_t)r * n + k0 + tx] : 0.0;
   for (int j = 0; j < kb; ++j) {
-    if (tx == j) Ab[ty][j] /= Lkk[j][j];
-    __syncthreads();
-    if (tx > j && tx < kb) Ab[ty][tx] -= Ab[ty][j] * Lkk[tx][j];
-    __syncthreads();
+    const double xj = __shfl_sync(0xffffffffu, v, j) / Lkk[j][j];
+    if (tx == j) v = xj;
+    else if (tx > j && tx < kb) v -= xj * Lkk[tx][j];
   }
-  if (ty < rb && tx < kb) A[(int64_t)(r0 + ty) * n + k0 + tx] = Ab[ty][tx];
+  if (tx < kb) A[(int64_t)r * n + k0 + tx] = v;
 }
 
-// Trailing update after panel k: A_ij -= L_ik L_jk^T for i >= j > k (32x32 tiles)
-static __global__ void __launch_bounds__(kNB* kNB) chol_update_kernel(double* A, int n, int k) {
-  const int nb = (n + kNB - 1) / kNB;
-  const int rem = nb - (k + 1);
-  // linear tile index over the lower triangle of a rem x rem tile grid
+// Trailing update after panel k: A_ij -= L_ik L_jk^T for row tiles i >= column tiles j > k, rows
+// up to n_rows (the rhs row rides along), columns < n.
+static __global__ void __launch_bounds__(kNB* kNB) chol_update_kernel(double* A, int n, int n_rows, int k) {
   int t = blockIdx.x;
   int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
   while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
   while (bi * (bi + 1) / 2 > t) --bi;
   const int bj = t - bi * (bi + 1) / 2;
-  if (bi >= rem) return;
   const int i0 = (k + 1 + bi) * kNB, j0 = (k + 1 + bj) * kNB, k0 = k * kNB;
+  if (i0 >= n_rows || j0 >= n) return;
   const int kb = min(kNB, n - k0);
   __shared__ double Li[kNB][kNB + 1];
   __shared__ double Lj[kNB][kNB + 1];
   const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;
-  Li[ty][tx] = (i0 + ty < n && tx < kb) ? A[(int64_t)(i0 + ty) * n + k0 + tx] : 0.0;
+  Li[ty][tx] = (i0 + ty < n_rows && tx < kb) ? A[(int64_t)(i0 + ty) * n + k0 + tx] : 0.0;
   Lj[ty][tx] = (j0 + ty < n && tx < kb) ? A[(int64_t)(j0 + ty) * n + k0 + tx] : 0.0;
   __syncthreads();
   const int r = i0 + ty, c = j0 + tx;
-  if (r < n && c < n && c <= r) {
+  if (r < n_rows && c < n && (c <= r)) {
     double s = 0.0;
 #pragma unroll
     for (int q = 0; q < kNB; ++q) s += Li[ty][q] * Lj[tx][q];
@@ -301,52 +338,34 @@ static __global__ void __launch_bounds__(kNB* kNB) chol_update_kernel(double* A,
   }
 }
 
-// Solve L L^T x = b in place (b -> x). Single CTA, blocked by 32.
-static __global__ void __launch_bounds__(1024) chol_solve_kernel(const double* L, double* b, int n) {
+// Backward substitution L^T x = y (y = row n of the factorised array, see above), single CTA.
+// Each 32-block: stage L_kk in shared memory, one warp solves it with shuffles, then all threads
+// apply the block's contribution to the remaining entries with coalesced row reads.
+static __global__ void __launch_bounds__(1024) chol_backsolve_kernel(const double* L, const double* y_in, double* x, int n) {
+  __shared__ double Lkk[kNB][kNB + 1];
   __shared__ double xb[kNB];
   const int nb = (n + kNB - 1) / kNB;
-  // forward: L y = b
-  for (int k = 0; k < nb; ++k) {
-    const int k0 = k * kNB, kb = min(kNB, n - k0);
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      double v = lane < kb ? b[k0 + lane] : 0.0;
-      for (int j = 0; j < kb; ++j) {
-        const double ljj = L[(int64_t)(k0 + j) * n + k0 + j];
-        const double yj = __shfl_sync(0xffffffffu, v, j) / ljj;
-        if (lane == j) v = yj;
-        else if (lane > j && lane < kb) v -= L[(int64_t)(k0 + lane) * n + k0 + j] * yj;
-      }
-      if (lane < kb) { b[k0 + lane] = v; xb[lane] = v; }
-    }
-    __syncthreads();
-    for (int r = k0 + kb + threadIdx.x; r < n; r += blockDim.x) {
-      double s = 0.0;
-      for (int j = 0; j < kb; ++j) s += L[(int64_t)r * n + k0 + j] * xb[j];
-      b[r] -= s;
-    }
-    __syncthreads();
-  }
-  // backward: L^T x = y
+  const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = y_in[i];
+  __syncthreads();
   for (int k = nb - 1; k >= 0; --k) {
     const int k0 = k * kNB, kb = min(kNB, n - k0);
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      double v = lane < kb ? b[k0 + lane] : 0.0;
+    Lkk[ty][tx] = (ty < kb && tx < kb && tx <= ty) ? L[(int64_t)(k0 + ty) * n + k0 + tx] : (ty == tx ? 1.0 : 0.0);
+    __syncthreads();
+    if (ty == 0) {
+      double v = tx < kb ? x[k0 + tx] : 0.0;
       for (int j = kb - 1; j >= 0; --j) {
-        const double ljj = L[(int64_t)(k0 + j) * n + k0 + j];
-        const double xj = __shfl_sync(0xffffffffu, v, j) / ljj;
-        if (lane == j) v = xj;
-        else if (lane < j) v -= L[(int64_t)(k0 + j) * n + k0 + lane] * xj;
+        const double xj = __shfl_sync(0xffffffffu, v, j) / Lkk[j][j];
+        if (tx == j) v = xj;
+        else if (tx < j) v -= Lkk[j][tx] * xj;
       }
-      if (lane < kb) { b[k0 + lane] = v; xb[lane] = v; }
+      if (tx < kb) { x[k0 + tx] = v; xb[tx] = v; }
     }
     __syncthreads();
-    // b[r] -= sum_j L[k0+j][r] * x[j] for r < k0
-    for (int r = threadIdx.x; r < k0; r += blockDim.x) {
+    for (int c = threadIdx.x; c < k0; c += blockDim.x) {
       double s = 0.0;
-      for (int j = 0; j < kb; ++j) s += L[(int64_t)(k0 + j) * n + r] * xb[j];
-      b[r] -= s;
+      for (int j = 0; j < kb; ++j) s += L[(int64_t)(k0 + j) * n + c] * xb[j];
+      x[c] -= s;
     }
     __syncthreads();
   }
