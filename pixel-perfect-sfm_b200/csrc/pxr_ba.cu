@@ -7,6 +7,7 @@
 // pxr_fm_eval.cuh / pxr_ba_kernels.cuh / pxr_inner.cuh.
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -175,6 +176,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   PXR_TRY(Hcc.alloc((size_t)nc * nc)); PXR_TRY(gc.alloc(nc));
   PXR_TRY(Hpp.alloc((size_t)n_points * 9)); PXR_TRY(gp.alloc((size_t)n_points * 3));
   h_obs_img.assign(d->obs_img, d->obs_img + n_obs);
+  use_monolithic_inner = std::getenv("PXR_INNER_MONOLITHIC") != nullptr;
   PXR_TRY(W.alloc((size_t)n_obs * dcmax * 3)); PXR_TRY(Wcols.alloc((size_t)n_obs * dcmax)); PXR_TRY(Wdc.alloc(n_obs));
   PXR_TRY(S.alloc((size_t)(nc + 1) * nc)); PXR_TRY(rhs.alloc(nc));
   PXR_TRY(diag.alloc(nl)); PXR_TRY(jscale.alloc(nl)); PXR_TRY(D2.alloc(nl)); PXR_TRY(delta.alloc(nl));
@@ -258,7 +260,7 @@ int BA::project(int set, bool jac, double* xy_out) {
   a.img_cam = img_cam.p; a.cam_model = cam_model.p;
   a.cam_params = cam[set].p; a.qvec = q[set].p; a.tvec = t[set].p; a.xyz = X[set].p;
   a.corner = corner.p; a.scale = scale.p; a.ups = ups;
-  a.obs_begin = 0; a.obs_end = n_obs;
+  a.obs_begin = 0; a.obs_end = n_obs; a.item_index = nullptr;
   a.uv = uv.p; a.xy = xy_out; a.juv = jac ? juv.p : nullptr; a.juv_stride = juv_stride; a.juv_k = K;
   if (n_obs == 0) return PXR_OK;
   StageScope st(this, 2);
@@ -273,7 +275,7 @@ int BA::fm(int mode, double* residuals_out, double* cost_dev /* device scalar */
   a.uv = uv.p; a.item_patch = obs_patch.p; a.item_ref = obs_pt.p;
   a.patches = d_patches; a.ph = ph; a.pw = pw;
   a.refs = has_refs ? refs.p : nullptr;
-  a.begin = 0; a.end = n_obs;
+  a.begin = 0; a.end = n_obs; a.item_index = nullptr;
   a.out = obs_out.p; a.residuals = residuals_out; a.desc = nullptr;
   a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
   a.l2_normalize = interp.l2_normalize;
@@ -320,7 +322,9 @@ int BA::build() {
   StageScope st(this, 3);
   PXR_TRY(Hcc.zero(ctx->stream));
   PXR_TRY(gc.zero(ctx->stream));
-  if (n_points > 0) PXR_LAUNCH(ctx, ba_build_kernel, (unsigned)cdiv(n_points, 128), 128, 0, dev());
+  PXR_TRY(Hpp.zero(ctx->stream));
+  PXR_TRY(gp.zero(ctx->stream));
+  if (n_obs > 0) PXR_LAUNCH(ctx, ba_build_kernel, (unsigned)cdiv(n_obs, 128), 128, 0, dev());
   // multi-GPU: camera blocks and gradient are sums over all ranks' observations
   PXR_TRY(allreduce_f64(ctx, Hcc.p, (size_t)nc * nc));
   PXR_TRY(allreduce_f64(ctx, gc.p, nc));
@@ -348,7 +352,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     PXR_CUDA(cudaMemsetAsync(rhs.p, 0, (size_t)nc * 8, s));
   }
   if (n_points > 0) {
-    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_points, 128), 128, 0, d, D2.p, Tbuf.p, rhs.p, flags.p);
+    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, D2.p, Tbuf.p, rhs.p, flags.p);
     if (sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, 256), 256, 0, d, schur_pairs(), Tbuf.p, S.p);
   }
   if (ctx->world > 1) {
@@ -370,7 +374,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   if (nc > 0) PXR_LAUNCH(ctx, chol_backsolve_kernel, 1, 1024, 0, S.p, S.p + (size_t)nc * nc, delta.p, nc);
   delete st; st = new StageScope(this, 7);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
-  if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points, 128), 128, 0, d, D2.p, delta.p, scalars.p + 4);
+  if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p, scalars.p + 4);
   PXR_TRY(allreduce_f64(ctx, scalars.p + 4, 1));
   if (nc > 0) PXR_LAUNCH(ctx, ba_cam_model_kernel, (unsigned)cdiv(nc, 256), 256, 0, Hcc.p, gc.p, delta.p, nc, scalars.p + 4);
   PXR_CUDA(cudaGetLastError());
@@ -414,7 +418,63 @@ int BA::apply_step(double* step_norm, double* x_norm) {
   return PXR_OK;
 }
 
+// K0 (with Jacobians) + K1 (Jacobian mode) over an explicit list of observations
+int BA::eval_list(int set, const int64_t* list, int64_t n) {
+  if (n <= 0) return PXR_OK;
+  ProjectArgs pa;
+  pa.obs_img = obs_img.p; pa.obs_pt = obs_pt.p; pa.obs_patch = obs_patch.p;
+  pa.img_cam = img_cam.p; pa.cam_model = cam_model.p;
+  pa.cam_params = cam[set].p; pa.qvec = q[set].p; pa.tvec = t[set].p; pa.xyz = X[set].p;
+  pa.corner = corner.p; pa.scale = scale.p; pa.ups = ups;
+  pa.obs_begin = 0; pa.obs_end = n; pa.item_index = list;
+  pa.uv = uv.p; pa.xy = nullptr; pa.juv = juv.p; pa.juv_stride = juv_stride; pa.juv_k = K;
+  PXR_LAUNCH(ctx, ba_project_kernel<true>, (unsigned)cdiv(n, 128), 128, 0, pa);
+  FmEvalArgs a;
+  a.uv = uv.p; a.item_patch = obs_patch.p; a.item_ref = obs_pt.p;
+  a.patches = d_patches; a.ph = ph; a.pw = pw;
+  a.refs = has_refs ? refs.p : nullptr;
+  a.begin = 0; a.end = n; a.item_index = list;
+  a.out = obs_out.p; a.residuals = nullptr; a.desc = nullptr;
+  a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
+  a.l2_normalize = interp.l2_normalize;
+  int np = 0;
+  PXR_TRY(launch_fm_eval(ctx, dtype, C, 1, interp.use_float_simd != 0, a, &np));
+  return PXR_OK;
+}
+
+// Inner iterations, batched: see pxr_inner.cuh.  Same state machine as ba_inner_kernel.
+int BA::inner_iterations_batched(int set) {
+  if (n_points == 0 || n_obs == 0) return PXR_OK;
+  StageScope stg(this, 9);
+  cudaStream_t s = ctx->stream;
+  if (!inner_state.p) {
+    PXR_TRY(inner_state.alloc(n_points));
+    PXR_TRY(inner_list.alloc(n_obs));
+    PXR_TRY(inner_counters.alloc(2));
+  }
+  InnerStepArgs a;
+  a.n_points = n_points; a.point_off = point_off.p; a.pt_begin = pt_begin.p;
+  a.obs_out = obs_out.p; a.juv = juv.p; a.juv_stride = juv_stride; a.juv_w = 9 + K;
+  a.xyz = X[set].p; a.st = inner_state.p;
+  a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
+  a.list = inner_list.p; a.counters = inner_counters.p;
+  const unsigned pgrid = (unsigned)cdiv(n_points, 128);
+  unsigned long long cnt[2] = {0, 0};
+  for (int round = 0; round <= 52; ++round) {
+    PXR_CUDA(cudaMemsetAsync(inner_counters.p, 0, 2 * sizeof(unsigned long long), s));
+    PXR_LAUNCH(ctx, inner_list_kernel, pgrid, 128, 0, a, round == 0 ? 1 : 0);
+    PXR_CUDA(cudaMemcpyAsync(cnt, inner_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    PXR_CUDA(cudaStreamSynchronize(s));
+    if (cnt[0] == 0) break;
+    PXR_TRY(eval_list(set, inner_list.p, (int64_t)cnt[0]));
+    PXR_LAUNCH(ctx, inner_step_kernel, pgrid, 128, 0, a, round == 0 ? 0 : 1);
+  }
+  PXR_CUDA(cudaGetLastError());
+  return PXR_OK;
+}
+
 int BA::inner_iterations(int set) {
+  if (!use_monolithic_inner) return inner_iterations_batched(set);
   InnerArgs a;
   a.n_points = n_points; a.point_off = point_off.p; a.pt_begin = pt_begin.p;
   a.obs_img = obs_img.p; a.obs_patch = obs_patch.p; a.img_cam = img_cam.p; a.cam_model = cam_model.p;
@@ -745,7 +805,7 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
     if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, b->Hcc.p, b->gc.p, b->D2.p, b->S.p, b->rhs.p, (int)nc);
     PXR_CUDA(cudaMemsetAsync(b->flags.p, 0, 4 * sizeof(int), s));
     if (b->n_points > 0) {
-      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_points, 128), 128, 0, d, b->D2.p, b->Tbuf.p, b->rhs.p, b->flags.p);
+      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_obs * b->dcmax, 256), 256, 0, d, b->D2.p, b->Tbuf.p, b->rhs.p, b->flags.p);
       if (b->sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(b->sp_n_chunks * 32, 256), 256, 0, d, b->schur_pairs(), b->Tbuf.p, b->S.p);
     }
     if (S) PXR_CUDA(cudaMemcpyAsync(S, b->S.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));

@@ -89,6 +89,12 @@ struct BA {
   int apply_step(double* step_norm, double* x_norm);
   int gradient_max_norm(double* out);
   int inner_iterations(int set);
+  int inner_iterations_batched(int set);
+  int eval_list(int set, const int64_t* list, int64_t n);
+  DevBuf<InnerState> inner_state;
+  DevBuf<int64_t> inner_list;
+  DevBuf<unsigned long long> inner_counters;
+  bool use_monolithic_inner = false;
   int step_norm_between_sets(double* out);
   int lm_begin();
   bool lm_finalize(int max_iteration);

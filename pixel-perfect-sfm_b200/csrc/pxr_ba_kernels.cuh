@@ -34,86 +34,79 @@ struct BADev {
 
 __device__ __forceinline__ void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
 
-// K2: one thread per point. Builds Hpp, gp (no atomics), W per observation, and adds the camera
-// blocks J_c^T A' J_c / J_c^T b' into the dense Hcc (lower triangle) / gc with fp64 atomics.
-static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= d.n_points) return;
-  const bool pvar = d.point_off[p] >= 0;
-  double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-  const int Wd = 9 + d.K;
-  for (int64_t o = d.pt_begin[p]; o < d.pt_begin[p + 1]; ++o) {
-    const double* oo = d.obs_out + o * 8;
-    const double s = oo[0];
-    double rho[3];
-    loss_eval(d.loss, 1.0, s, rho);
-    const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
-    const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
-    const double* J = d.juv + o * (int64_t)d.juv_stride;  // rows: J[0..Wd), J[Wd..2Wd)
-    const int img = d.obs_img[o];
-    const int cam = d.img_cam[img];
-    // local camera-side columns
-    int cols[kMaxDc];
-    double Ju[kMaxDc], Jv[kMaxDc];
-    int dc = 0;
-    const int po = d.pose_off[img];
-    if (po >= 0) {
-      const uint32_t tm = d.tmask[img];
-      for (int k = 0; k < 3; ++k) { cols[dc] = po + k; Ju[dc] = J[k]; Jv[dc] = J[Wd + k]; ++dc; }
-      int la = 3;
-      for (int k = 0; k < 3; ++k) {
-        if (tm & (1u << k)) continue;
-        cols[dc] = po + la++; Ju[dc] = J[3 + k]; Jv[dc] = J[Wd + 3 + k]; ++dc;
-      }
-    }
-    const int io = d.intr_off[cam];
-    if (io >= 0) {
-      const uint32_t cm = d.cam_mask[cam];
-      const int Kc = cam_num_params(d.cam_model[cam]);
-      int la = 0;
-      for (int k = 0; k < Kc; ++k) {
-        if (cm & (1u << k)) continue;
-        cols[dc] = io + la++; Ju[dc] = J[9 + k]; Jv[dc] = J[Wd + 9 + k]; ++dc;
-      }
-    }
-    d.Wdc[o] = dc;
-    // A' J rows:  (AJu, AJv)[k] = A' * (Ju[k], Jv[k])
-    const double pu0 = J[6], pu1 = J[7], pu2 = J[8], pv0 = J[Wd + 6], pv1 = J[Wd + 7], pv2 = J[Wd + 8];
-    const double apu[3] = {auu * pu0 + auv * pv0, auu * pu1 + auv * pv1, auu * pu2 + auv * pv2};
-    const double apv[3] = {auv * pu0 + avv * pv0, auv * pu1 + avv * pv1, auv * pu2 + avv * pv2};
-    if (pvar) {
-      const double pu[3] = {pu0, pu1, pu2}, pv[3] = {pv0, pv1, pv2};
-      H[0] += pu[0] * apu[0] + pv[0] * apv[0];
-      H[1] += pu[0] * apu[1] + pv[0] * apv[1];
-      H[2] += pu[0] * apu[2] + pv[0] * apv[2];
-      H[3] += pu[1] * apu[1] + pv[1] * apv[1];
-      H[4] += pu[1] * apu[2] + pv[1] * apv[2];
-      H[5] += pu[2] * apu[2] + pv[2] * apv[2];
-      for (int k = 0; k < 3; ++k) g[k] += pu[k] * bu + pv[k] * bv;
-    }
-    double* Wo = d.W + o * (int64_t)d.dcmax * 3;
-    int32_t* Wc = d.Wcols + o * (int64_t)d.dcmax;
-    for (int a = 0; a < dc; ++a) {
-      Wc[a] = cols[a];
-      if (pvar) {
-        Wo[a * 3 + 0] = Ju[a] * apu[0] + Jv[a] * apv[0];
-        Wo[a * 3 + 1] = Ju[a] * apu[1] + Jv[a] * apv[1];
-        Wo[a * 3 + 2] = Ju[a] * apu[2] + Jv[a] * apv[2];
-      }
-      const double aju = auu * Ju[a] + auv * Jv[a], ajv = auv * Ju[a] + avv * Jv[a];
-      atomic_add_f64(&d.gc[cols[a]], Ju[a] * bu + Jv[a] * bv);
-      for (int b = 0; b <= a; ++b) {
-        const double v = Ju[b] * aju + Jv[b] * ajv;
-        const int ca = cols[a], cb = cols[b];  // cols ascending within an observation
-        atomic_add_f64(&d.Hcc[(int64_t)ca * d.nc + cb], v);
-      }
+// local camera-side columns of one observation: pose (3 rot + non-constant t) then intrinsics
+__device__ __forceinline__ int obs_local_columns(const BADev& d, int64_t o, const double* J, int Wd, int* cols, double* Ju, double* Jv) {
+  const int img = d.obs_img[o];
+  const int cam = d.img_cam[img];
+  int dc = 0;
+  const int po = d.pose_off[img];
+  if (po >= 0) {
+    const uint32_t tm = d.tmask[img];
+    for (int k = 0; k < 3; ++k) { cols[dc] = po + k; Ju[dc] = J[k]; Jv[dc] = J[Wd + k]; ++dc; }
+    int la = 3;
+    for (int k = 0; k < 3; ++k) {
+      if (tm & (1u << k)) continue;
+      cols[dc] = po + la++; Ju[dc] = J[3 + k]; Jv[dc] = J[Wd + 3 + k]; ++dc;
     }
   }
+  const int io = d.intr_off[cam];
+  if (io >= 0) {
+    const uint32_t cm = d.cam_mask[cam];
+    const int Kc = cam_num_params(d.cam_model[cam]);
+    int la = 0;
+    for (int k = 0; k < Kc; ++k) {
+      if (cm & (1u << k)) continue;
+      cols[dc] = io + la++; Ju[dc] = J[9 + k]; Jv[dc] = J[Wd + 9 + k]; ++dc;
+    }
+  }
+  return dc;
+}
+
+// K2: one thread per observation.  W_o = J_c^T A' J_p, camera blocks J_c^T A' J_c / J_c^T b' into
+// the dense Hcc (lower triangle) / gc and the point blocks Hpp / gp, all with fp64 atomics
+// (Hpp/gp/Hcc/gc are zeroed by the caller).
+static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= d.n_obs) return;
+  const int64_t p = d.obs_pt[o];
+  const bool pvar = d.point_off[p] >= 0;
+  const int Wd = 9 + d.K;
+  const double* oo = d.obs_out + o * 8;
+  double rho[3];
+  loss_eval(d.loss, 1.0, oo[0], rho);
+  const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
+  const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
+  const double* J = d.juv + o * (int64_t)d.juv_stride;  // rows: J[0..Wd), J[Wd..2Wd)
+  int cols[kMaxDc];
+  double Ju[kMaxDc], Jv[kMaxDc];
+  const int dc = obs_local_columns(d, o, J, Wd, cols, Ju, Jv);
+  d.Wdc[o] = dc;
+  const double pu[3] = {J[6], J[7], J[8]}, pv[3] = {J[Wd + 6], J[Wd + 7], J[Wd + 8]};
+  double apu[3], apv[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { apu[k] = auu * pu[k] + auv * pv[k]; apv[k] = auv * pu[k] + avv * pv[k]; }
   if (pvar) {
     double* Hp = d.Hpp + p * 9;
-    Hp[0] = H[0]; Hp[1] = H[1]; Hp[2] = H[2]; Hp[3] = H[1]; Hp[4] = H[3]; Hp[5] = H[4];
-    Hp[6] = H[2]; Hp[7] = H[4]; Hp[8] = H[5];
-    d.gp[p * 3] = g[0]; d.gp[p * 3 + 1] = g[1]; d.gp[p * 3 + 2] = g[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomic_add_f64(&d.gp[p * 3 + a], pu[a] * bu + pv[a] * bv);
+#pragma unroll
+      for (int b = 0; b < 3; ++b) atomic_add_f64(&Hp[a * 3 + b], pu[a] * apu[b] + pv[a] * apv[b]);
+    }
+  }
+  double* Wo = d.W + o * (int64_t)d.dcmax * 3;
+  int32_t* Wc = d.Wcols + o * (int64_t)d.dcmax;
+  for (int a = 0; a < dc; ++a) {
+    Wc[a] = cols[a];
+    if (pvar) {
+      Wo[a * 3 + 0] = Ju[a] * apu[0] + Jv[a] * apv[0];
+      Wo[a * 3 + 1] = Ju[a] * apu[1] + Jv[a] * apv[1];
+      Wo[a * 3 + 2] = Ju[a] * apu[2] + Jv[a] * apv[2];
+    }
+    const double aju = auu * Ju[a] + auv * Jv[a], ajv = auv * Ju[a] + avv * Jv[a];
+    atomic_add_f64(&d.gc[cols[a]], Ju[a] * bu + Jv[a] * bv);
+    for (int b = 0; b <= a; ++b)  // cols ascending within an observation -> lower triangle
+      atomic_add_f64(&d.Hcc[(int64_t)cols[a] * d.nc + cols[b]], Ju[b] * aju + Jv[b] * ajv);
   }
 }
 
@@ -186,28 +179,26 @@ __device__ __forceinline__ bool inv3_sym(const double* H, const double* D2, doub
 //      the same (image_i, image_j) pair address the same block of S; the pair list is sorted by that
 //      key once on the host (static sparsity), a warp accumulates the dc_i x dc_j block of a chunk in
 //      registers and touches S once per element.
-static __global__ void __launch_bounds__(128) ba_schur_prep_kernel(BADev d, const double* D2, double* T, double* rhs,
+static __global__ void __launch_bounds__(256) ba_schur_prep_kernel(BADev d, const double* D2, double* T, double* rhs,
                                                                    int* fail_flag) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= d.n_points) return;
+  // one thread per (observation, local camera row)
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int dcm = d.dcmax;
+  const int64_t o = idx / dcm;
+  const int a = (int)(idx - o * dcm);
+  if (o >= d.n_obs || a >= d.Wdc[o]) return;
+  const int64_t p = d.obs_pt[o];
   const int64_t po = d.point_off[p];
   if (po < 0) return;
   double inv[9];
   if (!inv3_sym(d.Hpp + p * 9, D2 + po, inv)) { *fail_flag = 1; return; }
-  const double g0 = d.gp[p * 3], g1 = d.gp[p * 3 + 1], g2 = d.gp[p * 3 + 2];
-  const int dcm = d.dcmax;
-  for (int64_t o = d.pt_begin[p]; o < d.pt_begin[p + 1]; ++o) {
-    const int dc = d.Wdc[o];
-    for (int a = 0; a < dc; ++a) {
-      const double* w = d.W + (o * dcm + a) * 3;
-      const double t0 = w[0] * inv[0] + w[1] * inv[3] + w[2] * inv[6];
-      const double t1 = w[0] * inv[1] + w[1] * inv[4] + w[2] * inv[7];
-      const double t2 = w[0] * inv[2] + w[1] * inv[5] + w[2] * inv[8];
-      double* tp = T + (o * dcm + a) * 3;
-      tp[0] = t0; tp[1] = t1; tp[2] = t2;
-      atomic_add_f64(&rhs[d.Wcols[o * dcm + a]], t0 * g0 + t1 * g1 + t2 * g2);
-    }
-  }
+  const double* w = d.W + (o * dcm + a) * 3;
+  const double t0 = w[0] * inv[0] + w[1] * inv[3] + w[2] * inv[6];
+  const double t1 = w[0] * inv[1] + w[1] * inv[4] + w[2] * inv[7];
+  const double t2 = w[0] * inv[2] + w[1] * inv[5] + w[2] * inv[8];
+  double* tp = T + (o * dcm + a) * 3;
+  tp[0] = t0; tp[1] = t1; tp[2] = t2;
+  atomic_add_f64(&rhs[d.Wcols[o * dcm + a]], t0 * d.gp[p * 3] + t1 * d.gp[p * 3 + 1] + t2 * d.gp[p * 3 + 2]);
 }
 
 struct SchurPairs {
@@ -269,6 +260,7 @@ constexpr int kNB = 32;
 // with one warp per row.
 static __global__ void __launch_bounds__(kNB* kNB) chol_panel_kernel(double* A, int n, int n_rows, int k, int* fail_flag) {
   __shared__ double Lkk[kNB][kNB + 1];
+  __shared__ double rdiag[kNB];  // 1 / L_jj
   __shared__ int bad;
   const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;  // ty = warp id, tx = lane
   const int k0 = k * kNB;
@@ -281,10 +273,11 @@ static __global__ void __launch_bounds__(kNB* kNB) chol_panel_kernel(double* A, 
     for (int j = 0; j < kb; ++j) {
       const double dj = Lkk[j][j];
       if (!(dj > 0.0) || !isfinite(dj)) { if (tx == 0) bad = 1; break; }
-      const double sj = sqrt(dj);
+      const double rj = rsqrt(dj);
+      const double sj = dj * rj;
       double lij = 0.0;
-      if (tx == j) Lkk[j][j] = sj;
-      else if (tx > j && tx < kb) { lij = Lkk[tx][j] / sj; Lkk[tx][j] = lij; }
+      if (tx == j) { Lkk[j][j] = sj; rdiag[j] = rj; }
+      else if (tx > j && tx < kb) { lij = Lkk[tx][j] * rj; Lkk[tx][j] = lij; }
       __syncwarp();
       if (tx > j && tx < kb) {
 #pragma unroll 4
@@ -305,7 +298,7 @@ static __global__ void __launch_bounds__(kNB* kNB) chol_panel_kernel(double* A, 
   if (r >= n_rows) return;
   double v = tx < kb ? A[(int64_t)r * n + k0 + tx] : 0.0;
   for (int j = 0; j < kb; ++j) {
-    const double xj = __shfl_sync(0xffffffffu, v, j) / Lkk[j][j];
+    const double xj = __shfl_sync(0xffffffffu, v, j) * rdiag[j];
     if (tx == j) v = xj;
     else if (tx > j && tx < kb) v -= xj * Lkk[tx][j];
   }
@@ -371,42 +364,47 @@ static __global__ void __launch_bounds__(1024) chol_backsolve_kernel(const doubl
   }
 }
 
-// K5: back-substitution (one thread per point) + pieces of the model cost change.
+// K5: back-substitution (one warp per point) + pieces of the model cost change.
 //   delta_p = (Hpp+D)^-1 (-gp - sum_i W_i^T delta_c[cols_i])
 //   acc[0] += gp.dp + 0.5 dp^T Hpp dp + sum_i dc_i^T W_i dp      (point part of g.d + d^T H d / 2)
-static __global__ void __launch_bounds__(128) ba_backsub_kernel(BADev d, const double* D2, double* delta, double* acc) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+static __global__ void __launch_bounds__(256) ba_backsub_kernel(BADev d, const double* D2, double* delta, double* acc) {
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   double part = 0.0;
   if (p < d.n_points && d.point_off[p] >= 0) {
     const int64_t po = d.point_off[p];
-    double inv[9];
-    inv3_sym(d.Hpp + p * 9, D2 + po, inv);
-    double v[3] = {-d.gp[p * 3], -d.gp[p * 3 + 1], -d.gp[p * 3 + 2]};
-    double wd[3] = {0, 0, 0};
-    for (int64_t o = d.pt_begin[p]; o < d.pt_begin[p + 1]; ++o) {
-      const int dc = d.Wdc[o];
-      for (int a = 0; a < dc; ++a) {
+    const int64_t ob = d.pt_begin[p];
+    const int n = (int)(d.pt_begin[p + 1] - ob) * d.dcmax;
+    double w0 = 0, w1 = 0, w2 = 0;
+    for (int e = lane; e < n; e += 32) {
+      const int64_t o = ob + e / d.dcmax;
+      const int a = e % d.dcmax;
+      if (a < d.Wdc[o]) {
         const double dca = delta[d.Wcols[o * d.dcmax + a]];
         const double* w = d.W + (o * d.dcmax + a) * 3;
-        wd[0] += w[0] * dca; wd[1] += w[1] * dca; wd[2] += w[2] * dca;
+        w0 += w[0] * dca; w1 += w[1] * dca; w2 += w[2] * dca;
       }
     }
-    v[0] -= wd[0]; v[1] -= wd[1]; v[2] -= wd[2];
-    double dp[3];
-    for (int a = 0; a < 3; ++a) dp[a] = inv[a * 3] * v[0] + inv[a * 3 + 1] * v[1] + inv[a * 3 + 2] * v[2];
-    delta[po] = dp[0]; delta[po + 1] = dp[1]; delta[po + 2] = dp[2];
-    const double* H = d.Hpp + p * 9;
-    double hd = 0.0;
-    for (int a = 0; a < 3; ++a) hd += dp[a] * (H[a * 3] * dp[0] + H[a * 3 + 1] * dp[1] + H[a * 3 + 2] * dp[2]);
-    part = d.gp[p * 3] * dp[0] + d.gp[p * 3 + 1] * dp[1] + d.gp[p * 3 + 2] * dp[2] + 0.5 * hd +
-           (wd[0] * dp[0] + wd[1] * dp[1] + wd[2] * dp[2]);
+    w0 = warp_sum(w0); w1 = warp_sum(w1); w2 = warp_sum(w2);
+    if (lane == 0) {
+      double inv[9];
+      inv3_sym(d.Hpp + p * 9, D2 + po, inv);
+      const double v[3] = {-d.gp[p * 3] - w0, -d.gp[p * 3 + 1] - w1, -d.gp[p * 3 + 2] - w2};
+      double dp[3];
+      for (int a = 0; a < 3; ++a) dp[a] = inv[a * 3] * v[0] + inv[a * 3 + 1] * v[1] + inv[a * 3 + 2] * v[2];
+      delta[po] = dp[0]; delta[po + 1] = dp[1]; delta[po + 2] = dp[2];
+      const double* H = d.Hpp + p * 9;
+      double hd = 0.0;
+      for (int a = 0; a < 3; ++a) hd += dp[a] * (H[a * 3] * dp[0] + H[a * 3 + 1] * dp[1] + H[a * 3 + 2] * dp[2]);
+      part = d.gp[p * 3] * dp[0] + d.gp[p * 3 + 1] * dp[1] + d.gp[p * 3 + 2] * dp[2] + 0.5 * hd +
+             (w0 * dp[0] + w1 * dp[1] + w2 * dp[2]);
+    }
   }
-  // block reduce
-  __shared__ double sh[4];
+  __shared__ double sh[8];
   part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  if (lane == 0) sh[threadIdx.x >> 5] = part;
   __syncthreads();
-  if (threadIdx.x == 0) atomic_add_f64(&acc[0], sh[0] + sh[1] + sh[2] + sh[3]);
+  if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; ++k) t += sh[k]; atomic_add_f64(&acc[0], t); }
 }
 
 // camera part of g.d + d^T H d / 2 with the symmetric Hcc stored as lower triangle

@@ -27,6 +27,7 @@ struct ProjectArgs {
   const double* cam_params; const double* qvec; const double* tvec; const double* xyz;
   const int32_t* corner; const double* scale; double ups;
   int64_t obs_begin, obs_end;
+  const int64_t* item_index;  // optional: process observations item_index[obs_begin..obs_end) (inner iterations)
   double* uv;    // [n_obs][2] (u = col, v = row), patch pixel units
   double* xy;    // optional [n_obs][2]
   double* juv;   // optional [n_obs][juv_stride]: 2 x (6 pose | 3 point | K intr), row-major
@@ -36,8 +37,9 @@ struct ProjectArgs {
 
 template <bool JAC>
 __global__ void __launch_bounds__(128) ba_project_kernel(ProjectArgs a) {
-  const int64_t o = a.obs_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= a.obs_end) return;
+  const int64_t k = a.obs_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.obs_end) return;
+  const int64_t o = a.item_index ? a.item_index[k] : k;
   const int img = a.obs_img[o];
   const int64_t pt = a.obs_pt[o];
   const int64_t pi = a.obs_patch ? a.obs_patch[o] : o;
@@ -80,6 +82,7 @@ struct FmEvalArgs {
   const uint8_t* patches; int ph, pw;
   const double* refs;          // [n_refs][C] or null -> residual = f
   int64_t begin, end;          // item range
+  const int64_t* item_index;   // optional indirection: item k is observation item_index[k] (all per-item arrays use that id)
   double* out;                 // [n][8]: s, b_u, b_v, a_uu, a_uv, a_vv, 0, 0  (JAC) / only s (COST)
   double* residuals;           // optional [n][C]
   double* desc;                // optional [n][C]: interpolated (normalised) descriptor f (reference extraction)
@@ -90,6 +93,7 @@ struct FmEvalArgs {
 constexpr int kFmStages = 2;   // TMA ring slots per warp
 struct FmAux {                 // per-item window geometry, one entry per lane of a batch
   double xc, xr;
+  int64_t item;
   const uint8_t* src;
   const double* ref;
   int col, row;
@@ -337,8 +341,9 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
   const bool has_ref = a.refs != nullptr;
 
   for (int64_t batch = warp_global; batch < n_batches; batch += warps_total) {
-    const int64_t o = a.begin + batch * 32 + lane;
     const int nvalid = (int)min((int64_t)32, a.end - (a.begin + batch * 32));
+    int64_t o = a.begin + batch * 32 + lane;
+    if (a.item_index && lane < nvalid) o = a.item_index[o];
     // ---- phase 1: per-lane window geometry, published to the warp through shared memory
     __syncwarp();
     {
@@ -352,6 +357,7 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       const double fu = floor(u), fv = floor(v);
       // guard the int conversion (NaN/huge projections clamp to the border like any far-away tap)
       FmAux x;
+      x.item = o;
       x.col = (int)fmin(fmax(fu, -4.0), (double)a.pw + 4.0);
       x.row = (int)fmin(fmax(fv, -4.0), (double)a.ph + 4.0);
       x.xc = u - fu; x.xr = v - fv;
@@ -405,7 +411,7 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       __syncwarp();
       if (j + kFmStages < nvalid) issue(j + kFmStages, slot);  // refill the slot just consumed
       const double tot = normalize_and_reduce<CPL, DERIV, false>(active, a.l2_normalize != 0, has_ref ? refv : nullptr, f, fr, fc, r, red, lane);
-      const int64_t oj = a.begin + batch * 32 + j;
+      const int64_t oj = aux[j].item;
       if (a.residuals && active) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) a.residuals[oj * C + lane * CPL + k] = r[k];

@@ -204,6 +204,170 @@ __global__ void __launch_bounds__(128) ba_inner_kernel(InnerArgs a) {
   if (lane == 0) { a.xyz[3 * p] = x[0]; a.xyz[3 * p + 1] = x[1]; a.xyz[3 * p + 2] = x[2]; }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched inner iterations: the same per-point Levenberg-Marquardt state machine, but every
+// evaluation of ALL still-active points goes through the hot kernels K0 + K1 (TMA-staged, the
+// windows are L2 resident), and a thread-per-point kernel applies the LM logic between passes.
+struct InnerState {
+  double x[3];        // last accepted point
+  double cand[3];     // candidate being evaluated (also written to the parameter set)
+  double cost, current_cost, H[6], g[3], sc[3];
+  double radius, decf, xnorm, gmax, mcc;
+  int iter, invalid, active;
+};
+
+struct InnerStepArgs {
+  int64_t n_points;
+  const int64_t* point_off; const int64_t* pt_begin;
+  const double* obs_out; const double* juv; int juv_stride; int juv_w;  // juv_w = 9 + K
+  double* xyz;          // candidate parameter set
+  InnerState* st;
+  LossParams loss;
+  int64_t* list;        // active observation list (output of the list kernel)
+  unsigned long long* counters;  // [0] #active observations, [1] #active points
+};
+
+__device__ __forceinline__ bool inner_propose(InnerState& s) {
+  // ceres Solver::Options defaults (CoordinateDescentMinimizer::Solve)
+  const int max_iter = 50, max_invalid = 5;
+  const double gtol = 1e-10, min_radius = 1e-32, min_diag = 1e-6, max_diag = 1e32;
+  for (;;) {
+    s.iter += 1;
+    if (s.iter - 1 >= max_iter) return false;
+    if (s.gmax <= gtol) return false;
+    if (s.radius < min_radius) return false;
+    const double diag[3] = {s.H[0], s.H[3], s.H[5]};
+    double D2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double s2 = s.sc[k] * s.sc[k];
+      D2[k] = fmin(fmax(diag[k] * s2, min_diag), max_diag) / (s.radius * s2);
+    }
+    const double Hf[9] = {s.H[0], s.H[1], s.H[2], s.H[1], s.H[3], s.H[4], s.H[2], s.H[4], s.H[5]};
+    double inv[9];
+    bool valid = inv3_sym(Hf, D2, inv);
+    double d[3] = {0, 0, 0}, mcc = 0;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d[k] = -(inv[k * 3] * s.g[0] + inv[k * 3 + 1] * s.g[1] + inv[k * 3 + 2] * s.g[2]);
+      double gd = 0, dHd = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        gd += s.g[k] * d[k];
+        dHd += d[k] * (Hf[k * 3] * d[0] + Hf[k * 3 + 1] * d[1] + Hf[k * 3 + 2] * d[2]);
+      }
+      mcc = -gd - 0.5 * dHd;
+      valid = isfinite(d[0]) && isfinite(d[1]) && isfinite(d[2]) && mcc > 0.0;
+    }
+    if (!valid) {
+      if (++s.invalid >= max_invalid) return false;
+      s.radius /= s.decf; s.decf *= 2.0;
+      continue;
+    }
+    s.invalid = 0;
+    s.mcc = mcc;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s.cand[k] = s.x[k] + d[k];
+    return true;
+  }
+}
+
+// phase 0: state from the evaluation at the start point; phase 1: judge the evaluated candidate
+static __global__ void __launch_bounds__(128) inner_step_kernel(InnerStepArgs a, int phase) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n_points) return;
+  InnerState s = a.st[p];
+  if (phase == 0) {
+    s.active = (a.point_off[p] >= 0 && a.pt_begin[p + 1] > a.pt_begin[p]) ? 1 : 0;
+    s.iter = 0; s.invalid = 0;
+    if (!s.active) { a.st[p] = s; return; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s.x[k] = a.xyz[3 * p + k];
+  } else if (!s.active) return;
+  // cost / J^T J / J^T r of this point at the evaluated location
+  double cost = 0, H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+  for (int64_t o = a.pt_begin[p]; o < a.pt_begin[p + 1]; ++o) {
+    const double* oo = a.obs_out + o * 8;
+    double rho[3];
+    loss_eval(a.loss, 1.0, oo[0], rho);
+    cost += 0.5 * rho[0];
+    const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
+    const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
+    const double* J = a.juv + o * (int64_t)a.juv_stride;
+    const double pu[3] = {J[6], J[7], J[8]}, pv[3] = {J[a.juv_w + 6], J[a.juv_w + 7], J[a.juv_w + 8]};
+    double apu[3], apv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { apu[k] = auu * pu[k] + auv * pv[k]; apv[k] = auv * pu[k] + avv * pv[k]; }
+    H[0] += pu[0] * apu[0] + pv[0] * apv[0];
+    H[1] += pu[0] * apu[1] + pv[0] * apv[1];
+    H[2] += pu[0] * apu[2] + pv[0] * apv[2];
+    H[3] += pu[1] * apu[1] + pv[1] * apv[1];
+    H[4] += pu[1] * apu[2] + pv[1] * apv[2];
+    H[5] += pu[2] * apu[2] + pv[2] * apv[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g[k] += pu[k] * bu + pv[k] * bv;
+  }
+  const double ftol = 1e-6, ptol = 1e-8, min_rel_dec = 1e-3, max_radius = 1e16;
+  bool go = true;
+  if (phase == 0) {
+    if (!isfinite(cost)) go = false;
+    s.cost = s.current_cost = cost;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s.H[k] = H[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s.g[k] = g[k];
+    s.sc[0] = 1.0 / (1.0 + sqrt(H[0])); s.sc[1] = 1.0 / (1.0 + sqrt(H[3])); s.sc[2] = 1.0 / (1.0 + sqrt(H[5]));
+    s.radius = 1e4; s.decf = 2.0;
+    s.xnorm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2]);
+    s.gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+  } else {
+    const double candidate_cost = isfinite(cost) ? cost : 1.7976931348623157e308;
+    const double dx = s.cand[0] - s.x[0], dy = s.cand[1] - s.x[1], dz = s.cand[2] - s.x[2];
+    const double step_norm = sqrt(dx * dx + dy * dy + dz * dz);
+    if (step_norm <= ptol * (s.xnorm + ptol)) go = false;                      // parameter tolerance
+    else if (fabs(s.cost - candidate_cost) <= ftol * s.cost) go = false;       // function tolerance
+    else {
+      const double rel = (s.current_cost - candidate_cost) / s.mcc;
+      if (rel > min_rel_dec) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s.x[k] = s.cand[k]; s.g[k] = g[k]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s.H[k] = H[k];
+        s.xnorm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2]);
+        s.cost = cost; s.current_cost = candidate_cost;
+        s.gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+        s.radius = s.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+        s.radius = fmin(max_radius, s.radius);
+        s.decf = 2.0;
+      } else {
+        s.radius /= s.decf; s.decf *= 2.0;
+      }
+    }
+  }
+  if (go) go = inner_propose(s);
+  if (go) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.xyz[3 * p + k] = s.cand[k];
+  } else {
+    s.active = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.xyz[3 * p + k] = s.x[k];
+  }
+  a.st[p] = s;
+}
+
+// compacts the observations of the active points into `list`
+static __global__ void __launch_bounds__(128) inner_list_kernel(InnerStepArgs a, int all_variable) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n_points) return;
+  const bool act = all_variable ? (a.point_off[p] >= 0 && a.pt_begin[p + 1] > a.pt_begin[p]) : (a.st[p].active != 0);
+  if (!act) return;
+  const int64_t ob = a.pt_begin[p], n = a.pt_begin[p + 1] - ob;
+  const unsigned long long base = atomicAdd(&a.counters[0], (unsigned long long)n);
+  atomicAdd(&a.counters[1], 1ull);
+  for (int64_t i = 0; i < n; ++i) a.list[base + i] = ob + i;
+}
+
 // ||a - b|| over two parameter sets (ambient), for step_norm after inner iterations
 static __global__ void __launch_bounds__(256) diff_norm_kernel(const double* a, const double* b, int64_t n, double* acc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

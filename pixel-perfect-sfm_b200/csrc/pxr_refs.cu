@@ -135,7 +135,7 @@ extern "C" int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr
   FmEvalArgs a;
   a.uv = b.uv.p; a.item_patch = b.obs_patch.p; a.item_ref = nullptr;
   a.patches = b.d_patches; a.ph = b.ph; a.pw = b.pw; a.refs = nullptr;
-  a.begin = 0; a.end = b.n_obs; a.out = nullptr; a.residuals = nullptr; a.desc = dsc.p;
+  a.begin = 0; a.end = b.n_obs; a.item_index = nullptr; a.out = nullptr; a.residuals = nullptr; a.desc = dsc.p;
   a.loss.type = loss_type; a.loss.a = loss_scale;
   a.l2_normalize = b.interp.l2_normalize;
   int np = 0;
