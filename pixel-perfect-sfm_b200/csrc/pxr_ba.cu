@@ -93,7 +93,7 @@ static int check_desc(const pxr_ba_desc* d) {
   return PXR_OK;
 }
 
-int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so) {
+int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so, bool for_solve) {
   ctx = c;
   PXR_TRY(check_desc(d));
   if (ic) interp = *ic; else pxr_default_interp_config(&interp);
@@ -105,6 +105,18 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   C = d->channels; ph = d->ph; pw = d->pw; dtype = d->patch_dtype; ups = d->upsampling_factor;
   n_patches = d->obs_patch ? d->n_patches : std::max(d->n_patches, d->n_obs);
   has_refs = d->refs != nullptr;
+  // the big patch upload goes first: the host-side layout / co-visibility work below overlaps with the DMA
+  double h2d_patch = 0;
+  const size_t esz = dtype == PXR_F16 ? 2 : (dtype == PXR_F32 ? 4 : 8);
+  const size_t pbytes = (size_t)n_patches * ph * pw * C * esz;
+  if (d->patches_on_device) {
+    d_patches = (const uint8_t*)d->patches;
+  } else {
+    PXR_TRY(patches_owned.alloc(pbytes));
+    PXR_CUDA(cudaMemcpyAsync(patches_owned.p, d->patches, pbytes, cudaMemcpyHostToDevice, s));
+    h2d_patch = (double)pbytes;
+    d_patches = patches_owned.p;
+  }
   // ---- layout (same rules as BundleOptimizer::Parameterize*, resolved into masks by the caller)
   K = 0;
   for (int i = 0; i < n_cameras; ++i) K = std::max(K, cam_num_params(d->cam_model[i]));
@@ -135,7 +147,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   for (int64_t p = 0; p < n_points; ++p) h_pt_begin[p + 1] += h_pt_begin[p];
   if ((int64_t)nc * nc * 8 > (int64_t)40e9) return fail(PXR_ERR_UNSUPPORTED, "reduced camera system too large for the dense path (nc=%d)", nc);
 
-  double h2d = 0;
+  double h2d = h2d_patch;
   auto up = [&](auto& buf, const auto* host, size_t n) -> int { h2d += n * sizeof(*host); return buf.upload(host, n, s); };
   PXR_TRY(up(obs_img, d->obs_img, n_obs));
   PXR_TRY(up(obs_pt, d->obs_pt, n_obs));
@@ -151,16 +163,6 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   PXR_TRY(up(corner, d->corner, (size_t)n_patches * 2));
   PXR_TRY(up(scale, d->scale, (size_t)n_patches * 2));
   if (has_refs) PXR_TRY(up(refs, d->refs, (size_t)n_points * C));
-  const size_t esz = dtype == PXR_F16 ? 2 : (dtype == PXR_F32 ? 4 : 8);
-  const size_t pbytes = (size_t)n_patches * ph * pw * C * esz;
-  if (d->patches_on_device) {
-    d_patches = (const uint8_t*)d->patches;
-  } else {
-    PXR_TRY(patches_owned.alloc(pbytes));
-    PXR_CUDA(cudaMemcpyAsync(patches_owned.p, d->patches, pbytes, cudaMemcpyHostToDevice, s));
-    h2d += pbytes;
-    d_patches = patches_owned.p;
-  }
   for (int k = 0; k < 2; ++k) {
     PXR_TRY(cam[k].upload(d->cam_params, (size_t)n_cameras * kMaxK, s));
     PXR_TRY(q[k].upload(d->qvec, (size_t)n_images * 4, s));
@@ -177,6 +179,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   PXR_TRY(Hpp.alloc((size_t)n_points * 9)); PXR_TRY(gp.alloc((size_t)n_points * 3));
   h_obs_img.assign(d->obs_img, d->obs_img + n_obs);
   use_monolithic_inner = std::getenv("PXR_INNER_MONOLITHIC") != nullptr;
+  if (for_solve) PXR_TRY(build_schur_pairs());
   PXR_TRY(W.alloc((size_t)n_obs * dcmax * 3)); PXR_TRY(Wcols.alloc((size_t)n_obs * dcmax)); PXR_TRY(Wdc.alloc(n_obs));
   PXR_TRY(S.alloc((size_t)(nc + 1) * nc)); PXR_TRY(rhs.alloc(nc));
   PXR_TRY(diag.alloc(nl)); PXR_TRY(jscale.alloc(nl)); PXR_TRY(D2.alloc(nl)); PXR_TRY(delta.alloc(nl));
@@ -366,7 +369,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   const int nb = (int)cdiv(nc, kNB);
   const int nrb = (int)cdiv(nc + 1, kNB);  // row blocks including the rhs row
   for (int k = 0; k < nb; ++k) {
-    PXR_LAUNCH(ctx, chol_panel_kernel, nrb - k, kNB * kNB, 0, S.p, nc, nc + 1, k, flags.p + 1);
+    PXR_LAUNCH(ctx, chol_panel_kernel, nrb - k, kPanelThreads, 0, S.p, nc, nc + 1, k, flags.p + 1);
     const int rem = nrb - (k + 1);
     if (rem > 0) PXR_LAUNCH(ctx, chol_update_kernel, rem * (rem + 1) / 2, kNB * kNB, 0, S.p, nc, nc + 1, k);
   }
@@ -374,9 +377,9 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   if (nc > 0) PXR_LAUNCH(ctx, chol_backsolve_kernel, 1, 1024, 0, S.p, S.p + (size_t)nc * nc, delta.p, nc);
   delete st; st = new StageScope(this, 7);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
-  if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p, scalars.p + 4);
+  if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p);
+  if (n_obs > 0) PXR_LAUNCH(ctx, ba_model_cost_kernel, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
   PXR_TRY(allreduce_f64(ctx, scalars.p + 4, 1));
-  if (nc > 0) PXR_LAUNCH(ctx, ba_cam_model_kernel, (unsigned)cdiv(nc, 256), 256, 0, Hcc.p, gc.p, delta.p, nc, scalars.p + 4);
   PXR_CUDA(cudaGetLastError());
   delete st;
   double acc = 0;
@@ -684,7 +687,7 @@ int pxr_ba_create(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config
                   const pxr_solver_options* opt, pxr_ba** out) {
   if (!ctx || !out) return fail(PXR_ERR_INVALID_ARGUMENT, "ctx/out is NULL");
   BA* b = new BA();
-  const int rc = b->create(ctx, desc, interp, opt);
+  const int rc = b->create(ctx, desc, interp, opt, true);
   if (rc != PXR_OK) { delete b; return rc; }
   *out = reinterpret_cast<pxr_ba*>(b);
   return PXR_OK;

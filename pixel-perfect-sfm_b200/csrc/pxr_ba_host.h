@@ -79,7 +79,7 @@ struct BA {
   int build_schur_pairs();
   SchurPairs schur_pairs();
 
-  int create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so);
+  int create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so, bool for_solve);
   BADev dev();
   int project(int set, bool jac, double* xy_out);
   int fm(int mode, double* residuals_out, double* cost_dev);

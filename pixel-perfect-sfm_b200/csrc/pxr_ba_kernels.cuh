@@ -218,6 +218,43 @@ static __global__ void __launch_bounds__(256) ba_schur_pairs_kernel(BADev d, Sch
   const int dcm = d.dcmax;
   const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
+  const bool self = sp.chunk_self[c] != 0;
+  if (dcx <= 8 && dcy <= 8) {
+    // fast path: 4 groups of 8 lanes work on 4 entries at a time; lane (g, a) owns row a of the block
+    const int g = lane >> 3, a = lane & 7;
+    double acc[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b] = 0.0;
+    for (int64_t k = kb + g; k < ke; k += 4) {
+      const double* Tx = T + ((int64_t)sp.px[k] * dcm + a) * 3;
+      const double* Wy = d.W + (int64_t)sp.py[k] * dcm * 3;
+      if (a < dcx) {
+        const double t0 = Tx[0], t1 = Tx[1], t2 = Tx[2];
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          if (b < dcy) acc[b] += t0 * Wy[b * 3] + t1 * Wy[b * 3 + 1] + t2 * Wy[b * 3 + 2];
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 8);
+      acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
+    }
+    if (g == 0 && a < dcx) {
+      const int ca = d.Wcols[ox0 * dcm + a];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b >= dcy) continue;
+        const int cb = d.Wcols[oy0 * dcm + b];
+        const double v = -acc[b];
+        if (self) { if (a >= b) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v); }
+        else if (ca > cb) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v);
+        else if (ca < cb) atomic_add_f64(&S[(int64_t)cb * d.nc + ca], v);
+        else atomic_add_f64(&S[(int64_t)ca * d.nc + ca], 2.0 * v);
+      }
+    }
+    return;
+  }
   const int nel = dcx * dcy;
   constexpr int kMaxT = (kMaxDc * kMaxDc + 31) / 32;
   double acc[kMaxT];
@@ -235,7 +272,6 @@ static __global__ void __launch_bounds__(256) ba_schur_pairs_kernel(BADev d, Sch
       }
     }
   }
-  const bool self = sp.chunk_self[c] != 0;
 #pragma unroll
   for (int t = 0; t < kMaxT; ++t) {
     const int e = lane + 32 * t;
@@ -258,7 +294,8 @@ constexpr int kNB = 32;
 // Panel step k: every CTA factors the diagonal block A_kk redundantly in shared memory (one warp,
 // warp-synchronous); CTA 0 writes L_kk back, CTA b>0 solves its 32-row block L_bk = A_bk L_kk^-T
 // with one warp per row.
-static __global__ void __launch_bounds__(kNB* kNB) chol_panel_kernel(double* A, int n, int n_rows, int k, int* fail_flag) {
+constexpr int kPanelThreads = 512;  // 16 warps: 128 registers/thread so that a 32-double row fits
+static __global__ void __launch_bounds__(kPanelThreads) chol_panel_kernel(double* A, int n, int n_rows, int k, int* fail_flag) {
   __shared__ double Lkk[kNB][kNB + 1];
   __shared__ double rdiag[kNB];  // 1 / L_jj
   __shared__ int bad;
@@ -266,43 +303,52 @@ static __global__ void __launch_bounds__(kNB* kNB) chol_panel_kernel(double* A, 
   const int k0 = k * kNB;
   const int kb = min(kNB, n - k0);
   if (threadIdx.x == 0) bad = 0;
-  Lkk[ty][tx] = (ty < kb && tx < kb && tx <= ty) ? A[(int64_t)(k0 + ty) * n + k0 + tx] : (ty == tx ? 1.0 : 0.0);
+  for (int rr = ty; rr < kNB; rr += kPanelThreads / 32)
+    Lkk[rr][tx] = (rr < kb && tx < kb && tx <= rr) ? A[(int64_t)(k0 + rr) * n + k0 + tx] : (rr == tx ? 1.0 : 0.0);
   __syncthreads();
   if (ty == 0) {
-    // lane i owns row i of the block
-    for (int j = 0; j < kb; ++j) {
-      const double dj = Lkk[j][j];
-      if (!(dj > 0.0) || !isfinite(dj)) { if (tx == 0) bad = 1; break; }
+    // lane i keeps row i of the 32x32 block in registers; column values travel by shuffle
+    double r[kNB];
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) r[c] = Lkk[tx][c];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) {
+      const double dj = __shfl_sync(0xffffffffu, r[j], j);
+      if (!(dj > 0.0) || !isfinite(dj)) ok = false;
       const double rj = rsqrt(dj);
-      const double sj = dj * rj;
-      double lij = 0.0;
-      if (tx == j) { Lkk[j][j] = sj; rdiag[j] = rj; }
-      else if (tx > j && tx < kb) { lij = Lkk[tx][j] * rj; Lkk[tx][j] = lij; }
-      __syncwarp();
-      if (tx > j && tx < kb) {
-#pragma unroll 4
-        for (int c = j + 1; c <= tx; ++c) Lkk[tx][c] -= lij * Lkk[c][j];
+      if (tx == j) { r[j] = dj * rj; rdiag[j] = rj; }
+      else if (tx > j) r[j] *= rj;
+      const double lij = r[j];
+#pragma unroll
+      for (int c = j + 1; c < kNB; ++c) {
+        const double lcj = __shfl_sync(0xffffffffu, lij, c);
+        if (tx >= c) r[c] -= lij * lcj;
       }
-      __syncwarp();
     }
+    if (!ok && tx == 0) bad = 1;
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) Lkk[tx][c] = r[c];
   }
   __syncthreads();
   if (bad) { if (threadIdx.x == 0 && blockIdx.x == 0) *fail_flag = 1; return; }
   const int b = blockIdx.x;
-  const int r = k0 + b * kNB + ty;
-  if (r < k0 + kb) {  // a row of the diagonal block itself (CTA 0): write the factor back
-    if (tx < kb && tx <= ty) A[(int64_t)r * n + k0 + tx] = Lkk[ty][tx];
-    return;
+  for (int rr = ty; rr < kNB; rr += kPanelThreads / 32) {
+    const int r = k0 + b * kNB + rr;
+    if (r < k0 + kb) {  // a row of the diagonal block itself (CTA 0): write the factor back
+      if (tx < kb && tx <= rr) A[(int64_t)r * n + k0 + tx] = Lkk[rr][tx];
+      continue;
+    }
+    // rows below the diagonal block (including the appended rhs row): one warp per row
+    if (r >= n_rows) continue;
+    double v = tx < kb ? A[(int64_t)r * n + k0 + tx] : 0.0;
+    for (int j = 0; j < kb; ++j) {
+      const double xj = __shfl_sync(0xffffffffu, v, j) * rdiag[j];
+      if (tx == j) v = xj;
+      else if (tx > j && tx < kb) v -= xj * Lkk[tx][j];
+    }
+    if (tx < kb) A[(int64_t)r * n + k0 + tx] = v;
   }
-  // rows below the diagonal block (including the appended rhs row): one warp per row
-  if (r >= n_rows) return;
-  double v = tx < kb ? A[(int64_t)r * n + k0 + tx] : 0.0;
-  for (int j = 0; j < kb; ++j) {
-    const double xj = __shfl_sync(0xffffffffu, v, j) * rdiag[j];
-    if (tx == j) v = xj;
-    else if (tx > j && tx < kb) v -= xj * Lkk[tx][j];
-  }
-  if (tx < kb) A[(int64_t)r * n + k0 + tx] = v;
 }
 
 // Trailing update after panel k: A_ij -= L_ik L_jk^T for row tiles i >= column tiles j > k, rows
@@ -347,8 +393,9 @@ static __global__ void __launch_bounds__(1024) chol_backsolve_kernel(const doubl
     __syncthreads();
     if (ty == 0) {
       double v = tx < kb ? x[k0 + tx] : 0.0;
+      const double rd = 1.0 / Lkk[tx][tx];
       for (int j = kb - 1; j >= 0; --j) {
-        const double xj = __shfl_sync(0xffffffffu, v, j) / Lkk[j][j];
+        const double xj = __shfl_sync(0xffffffffu, v, j) * __shfl_sync(0xffffffffu, rd, j);
         if (tx == j) v = xj;
         else if (tx < j) v -= Lkk[j][tx] * xj;
       }
@@ -364,64 +411,61 @@ static __global__ void __launch_bounds__(1024) chol_backsolve_kernel(const doubl
   }
 }
 
-// K5: back-substitution (one warp per point) + pieces of the model cost change.
-//   delta_p = (Hpp+D)^-1 (-gp - sum_i W_i^T delta_c[cols_i])
-//   acc[0] += gp.dp + 0.5 dp^T Hpp dp + sum_i dc_i^T W_i dp      (point part of g.d + d^T H d / 2)
-static __global__ void __launch_bounds__(256) ba_backsub_kernel(BADev d, const double* D2, double* delta, double* acc) {
+// K5a: back-substitution, one warp per point:  delta_p = (Hpp+D)^-1 (-gp - sum_i W_i^T delta_c[cols_i])
+static __global__ void __launch_bounds__(256) ba_backsub_kernel(BADev d, const double* D2, double* delta) {
   const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  double part = 0.0;
-  if (p < d.n_points && d.point_off[p] >= 0) {
-    const int64_t po = d.point_off[p];
-    const int64_t ob = d.pt_begin[p];
-    const int n = (int)(d.pt_begin[p + 1] - ob) * d.dcmax;
-    double w0 = 0, w1 = 0, w2 = 0;
-    for (int e = lane; e < n; e += 32) {
-      const int64_t o = ob + e / d.dcmax;
-      const int a = e % d.dcmax;
-      if (a < d.Wdc[o]) {
-        const double dca = delta[d.Wcols[o * d.dcmax + a]];
-        const double* w = d.W + (o * d.dcmax + a) * 3;
-        w0 += w[0] * dca; w1 += w[1] * dca; w2 += w[2] * dca;
-      }
-    }
-    w0 = warp_sum(w0); w1 = warp_sum(w1); w2 = warp_sum(w2);
-    if (lane == 0) {
-      double inv[9];
-      inv3_sym(d.Hpp + p * 9, D2 + po, inv);
-      const double v[3] = {-d.gp[p * 3] - w0, -d.gp[p * 3 + 1] - w1, -d.gp[p * 3 + 2] - w2};
-      double dp[3];
-      for (int a = 0; a < 3; ++a) dp[a] = inv[a * 3] * v[0] + inv[a * 3 + 1] * v[1] + inv[a * 3 + 2] * v[2];
-      delta[po] = dp[0]; delta[po + 1] = dp[1]; delta[po + 2] = dp[2];
-      const double* H = d.Hpp + p * 9;
-      double hd = 0.0;
-      for (int a = 0; a < 3; ++a) hd += dp[a] * (H[a * 3] * dp[0] + H[a * 3 + 1] * dp[1] + H[a * 3 + 2] * dp[2]);
-      part = d.gp[p * 3] * dp[0] + d.gp[p * 3 + 1] * dp[1] + d.gp[p * 3 + 2] * dp[2] + 0.5 * hd +
-             (w0 * dp[0] + w1 * dp[1] + w2 * dp[2]);
+  if (p >= d.n_points || d.point_off[p] < 0) return;
+  const int64_t po = d.point_off[p];
+  const int64_t ob = d.pt_begin[p];
+  const int n = (int)(d.pt_begin[p + 1] - ob) * d.dcmax;
+  double w0 = 0, w1 = 0, w2 = 0;
+  for (int e = lane; e < n; e += 32) {
+    const int64_t o = ob + e / d.dcmax;
+    const int a = e % d.dcmax;
+    if (a < d.Wdc[o]) {
+      const double dca = delta[d.Wcols[o * d.dcmax + a]];
+      const double* w = d.W + (o * d.dcmax + a) * 3;
+      w0 += w[0] * dca; w1 += w[1] * dca; w2 += w[2] * dca;
     }
   }
-  __shared__ double sh[8];
-  part = warp_sum(part);
-  if (lane == 0) sh[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; ++k) t += sh[k]; atomic_add_f64(&acc[0], t); }
+  w0 = warp_sum(w0); w1 = warp_sum(w1); w2 = warp_sum(w2);
+  if (lane == 0) {
+    double inv[9];
+    inv3_sym(d.Hpp + p * 9, D2 + po, inv);
+    const double v[3] = {-d.gp[p * 3] - w0, -d.gp[p * 3 + 1] - w1, -d.gp[p * 3 + 2] - w2};
+    for (int a = 0; a < 3; ++a) delta[po + a] = inv[a * 3] * v[0] + inv[a * 3 + 1] * v[1] + inv[a * 3 + 2] * v[2];
+  }
 }
 
-// camera part of g.d + d^T H d / 2 with the symmetric Hcc stored as lower triangle
-static __global__ void __launch_bounds__(256) ba_cam_model_kernel(const double* Hcc, const double* gc, const double* delta,
-                                                          int nc, double* acc) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// K5b: model cost change, the literal ceres formula  -(J d)^T (r + J d / 2)  per residual block in
+// the reduced 2-D space:  u = d(uv)/d(theta) * delta ;  acc += u^T b' + u^T A' u / 2   (one thread per obs)
+static __global__ void __launch_bounds__(256) ba_model_cost_kernel(BADev d, const double* delta, double* acc) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double part = 0.0;
-  if (r < nc) {
-    double row = 0.0;
-    for (int c = 0; c < r; ++c) row += Hcc[(int64_t)r * nc + c] * delta[c];  // strictly lower, counted twice
-    part = gc[r] * delta[r] + delta[r] * row + 0.5 * delta[r] * Hcc[(int64_t)r * nc + r] * delta[r];
+  if (o < d.n_obs) {
+    const int Wd = 9 + d.K;
+    const double* oo = d.obs_out + o * 8;
+    double rho[3];
+    loss_eval(d.loss, 1.0, oo[0], rho);
+    const double* J = d.juv + o * (int64_t)d.juv_stride;
+    int cols[kMaxDc];
+    double Ju[kMaxDc], Jv[kMaxDc];
+    const int dc = obs_local_columns(d, o, J, Wd, cols, Ju, Jv);
+    double uu = 0.0, uv = 0.0;
+    for (int a = 0; a < dc; ++a) { const double dl = delta[cols[a]]; uu += Ju[a] * dl; uv += Jv[a] * dl; }
+    const int64_t po = d.point_off[d.obs_pt[o]];
+    if (po >= 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const double dl = delta[po + k]; uu += J[6 + k] * dl; uv += J[Wd + 6 + k] * dl; }
+    }
+    part = rho[1] * (uu * oo[1] + uv * oo[2] + 0.5 * (uu * (oo[3] * uu + oo[4] * uv) + uv * (oo[4] * uu + oo[5] * uv)));
   }
   __shared__ double sh[8];
   part = warp_sum(part);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
   __syncthreads();
-  if (threadIdx.x == 0) { double s = 0; for (int i = 0; i < 8; ++i) s += sh[i]; atomic_add_f64(&acc[0], s); }
+  if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; ++k) t += sh[k]; atomic_add_f64(&acc[0], t); }
 }
 
 // K6: x_plus = Plus(x, delta) for every block; also accumulates ||x||^2, ||x_plus - x||^2 (ambient)

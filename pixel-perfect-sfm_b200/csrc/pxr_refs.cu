@@ -123,7 +123,7 @@ extern "C" int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr
   so.loss_type = loss_type; so.loss_scale = loss_scale;
   BA b;
   const int64_t launches0 = ctx->launches;
-  PXR_TRY(b.create(ctx, &d, interp, &so));
+  PXR_TRY(b.create(ctx, &d, interp, &so, false));
   cudaStream_t s = ctx->stream;
   DevBuf<double> dsc, refs;
   DevBuf<int64_t> src;
