@@ -186,6 +186,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   PXR_TRY(partials.alloc(fm_max_partials(ctx)));
   PXR_TRY(scalars.alloc(16));
   PXR_TRY(flags.alloc(4));
+  PXR_TRY(rdiag.alloc(kNB));
   PXR_TRY(Hpp.zero(s)); PXR_TRY(gp.zero(s)); PXR_TRY(obs_out.zero(s));
   PXR_CUDA(cudaStreamSynchronize(s));
   h2d_bytes = h2d;
@@ -367,11 +368,14 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   // rhs rides along as row nc of S: the factorisation performs the forward substitution
   if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
   const int nb = (int)cdiv(nc, kNB);
-  const int nrb = (int)cdiv(nc + 1, kNB);  // row blocks including the rhs row
   for (int k = 0; k < nb; ++k) {
-    PXR_LAUNCH(ctx, chol_panel_kernel, nrb - k, kPanelThreads, 0, S.p, nc, nc + 1, k, flags.p + 1);
+    const int k0 = k * kNB, kb = std::min(kNB, nc - k0);
+    const int rows_below = nc + 1 - (k0 + kb);               // includes the rhs row
+    PXR_LAUNCH(ctx, chol_diag_kernel, 1, 32, 0, S.p, nc, k, rdiag.p, flags.p + 1);
+    if (rows_below > 0) PXR_LAUNCH(ctx, chol_panel_kernel, (unsigned)cdiv(rows_below, kNB), kPanelThreads, 0, S.p, nc, nc + 1, k, rdiag.p);
+    const int nrb = (int)cdiv(nc + 1, kNB);
     const int rem = nrb - (k + 1);
-    if (rem > 0) PXR_LAUNCH(ctx, chol_update_kernel, rem * (rem + 1) / 2, kNB * kNB, 0, S.p, nc, nc + 1, k);
+    if (rem > 0 && kb == kNB) PXR_LAUNCH(ctx, chol_update_kernel, rem * (rem + 1) / 2, kNB * kNB, 0, S.p, nc, nc + 1, k);
   }
   delete st; st = new StageScope(this, 6);
   if (nc > 0) PXR_LAUNCH(ctx, chol_backsolve_kernel, 1, 1024, 0, S.p, S.p + (size_t)nc * nc, delta.p, nc);

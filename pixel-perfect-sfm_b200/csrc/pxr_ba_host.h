@@ -68,6 +68,7 @@ struct BA {
   // device: per-observation and linearisation
   DevBuf<double> uv, obs_out, juv, Hcc, gc, Hpp, gp, W, S, rhs, diag, jscale, D2, delta, partials, scalars;
   DevBuf<int> flags;
+  DevBuf<double> rdiag;
   // static co-visibility structure for the Schur complement (see ba_schur_pairs_kernel)
   DevBuf<int32_t> sp_px, sp_py;
   DevBuf<int64_t> sp_chunk_begin;

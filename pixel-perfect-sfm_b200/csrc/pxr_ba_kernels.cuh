@@ -294,61 +294,57 @@ constexpr int kNB = 32;
 // Panel step k: every CTA factors the diagonal block A_kk redundantly in shared memory (one warp,
 // warp-synchronous); CTA 0 writes L_kk back, CTA b>0 solves its 32-row block L_bk = A_bk L_kk^-T
 // with one warp per row.
-constexpr int kPanelThreads = 512;  // 16 warps: 128 registers/thread so that a 32-double row fits
-static __global__ void __launch_bounds__(kPanelThreads) chol_panel_kernel(double* A, int n, int n_rows, int k, int* fail_flag) {
-  __shared__ double Lkk[kNB][kNB + 1];
-  __shared__ double rdiag[kNB];  // 1 / L_jj
-  __shared__ int bad;
-  const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;  // ty = warp id, tx = lane
+// Panel step k, part 1: one warp factors the 32x32 diagonal block A_kk entirely in registers (lane i
+// keeps row i, column values travel by shuffle) and writes L_kk back plus the reciprocal diagonal.
+static __global__ void __launch_bounds__(32) chol_diag_kernel(double* A, int n, int k, double* rdiag_out, int* fail_flag) {
+  const int tx = threadIdx.x;
   const int k0 = k * kNB;
   const int kb = min(kNB, n - k0);
-  if (threadIdx.x == 0) bad = 0;
-  for (int rr = ty; rr < kNB; rr += kPanelThreads / 32)
-    Lkk[rr][tx] = (rr < kb && tx < kb && tx <= rr) ? A[(int64_t)(k0 + rr) * n + k0 + tx] : (rr == tx ? 1.0 : 0.0);
-  __syncthreads();
-  if (ty == 0) {
-    // lane i keeps row i of the 32x32 block in registers; column values travel by shuffle
-    double r[kNB];
+  double r[kNB];
 #pragma unroll
-    for (int c = 0; c < kNB; ++c) r[c] = Lkk[tx][c];
-    bool ok = true;
+  for (int c = 0; c < kNB; ++c) r[c] = (tx < kb && c < kb && c <= tx) ? A[(int64_t)(k0 + tx) * n + k0 + c] : (c == tx ? 1.0 : 0.0);
+  bool ok = true;
 #pragma unroll
-    for (int j = 0; j < kNB; ++j) {
-      const double dj = __shfl_sync(0xffffffffu, r[j], j);
-      if (!(dj > 0.0) || !isfinite(dj)) ok = false;
-      const double rj = rsqrt(dj);
-      if (tx == j) { r[j] = dj * rj; rdiag[j] = rj; }
-      else if (tx > j) r[j] *= rj;
-      const double lij = r[j];
+  for (int j = 0; j < kNB; ++j) {
+    const double dj = __shfl_sync(0xffffffffu, r[j], j);
+    if (!(dj > 0.0) || !isfinite(dj)) ok = false;
+    const double rj = rsqrt(dj);
+    if (tx == j) { r[j] = dj * rj; rdiag_out[j] = rj; }
+    else if (tx > j) r[j] *= rj;
+    const double lij = r[j];
 #pragma unroll
-      for (int c = j + 1; c < kNB; ++c) {
-        const double lcj = __shfl_sync(0xffffffffu, lij, c);
-        if (tx >= c) r[c] -= lij * lcj;
-      }
+    for (int c = j + 1; c < kNB; ++c) {
+      const double lcj = __shfl_sync(0xffffffffu, lij, c);
+      if (tx >= c) r[c] -= lij * lcj;
     }
-    if (!ok && tx == 0) bad = 1;
-#pragma unroll
-    for (int c = 0; c < kNB; ++c) Lkk[tx][c] = r[c];
   }
+  if (!ok && tx == 0) *fail_flag = 1;
+#pragma unroll
+  for (int c = 0; c < kNB; ++c)
+    if (tx < kb && c < kb && c <= tx) A[(int64_t)(k0 + tx) * n + k0 + c] = r[c];
+}
+
+// Panel step k, part 2: rows below the diagonal block (including the appended rhs row):
+// L_bk = A_bk L_kk^-T, one warp per row, CTA b handles the 32 rows starting at k0 + kb + b*32.
+constexpr int kPanelThreads = 1024;
+static __global__ void __launch_bounds__(kPanelThreads) chol_panel_kernel(double* A, int n, int n_rows, int k, const double* rdiag_in) {
+  __shared__ double Lkk[kNB][kNB + 1];
+  __shared__ double rdiag[kNB];
+  const int tx = threadIdx.x % kNB, ty = threadIdx.x / kNB;
+  const int k0 = k * kNB;
+  const int kb = min(kNB, n - k0);
+  Lkk[ty][tx] = (ty < kb && tx < kb && tx <= ty) ? A[(int64_t)(k0 + ty) * n + k0 + tx] : 0.0;
+  if (ty == 0) rdiag[tx] = rdiag_in[tx];
   __syncthreads();
-  if (bad) { if (threadIdx.x == 0 && blockIdx.x == 0) *fail_flag = 1; return; }
-  const int b = blockIdx.x;
-  for (int rr = ty; rr < kNB; rr += kPanelThreads / 32) {
-    const int r = k0 + b * kNB + rr;
-    if (r < k0 + kb) {  // a row of the diagonal block itself (CTA 0): write the factor back
-      if (tx < kb && tx <= rr) A[(int64_t)r * n + k0 + tx] = Lkk[rr][tx];
-      continue;
-    }
-    // rows below the diagonal block (including the appended rhs row): one warp per row
-    if (r >= n_rows) continue;
-    double v = tx < kb ? A[(int64_t)r * n + k0 + tx] : 0.0;
-    for (int j = 0; j < kb; ++j) {
-      const double xj = __shfl_sync(0xffffffffu, v, j) * rdiag[j];
-      if (tx == j) v = xj;
-      else if (tx > j && tx < kb) v -= xj * Lkk[tx][j];
-    }
-    if (tx < kb) A[(int64_t)r * n + k0 + tx] = v;
+  const int r = k0 + kb + blockIdx.x * kNB + ty;
+  if (r >= n_rows) return;
+  double v = tx < kb ? A[(int64_t)r * n + k0 + tx] : 0.0;
+  for (int j = 0; j < kb; ++j) {
+    const double xj = __shfl_sync(0xffffffffu, v, j) * rdiag[j];
+    if (tx == j) v = xj;
+    else if (tx > j && tx < kb) v -= xj * Lkk[tx][j];
   }
+  if (tx < kb) A[(int64_t)r * n + k0 + tx] = v;
 }
 
 // Trailing update after panel k: A_ij -= L_ik L_jk^T for row tiles i >= column tiles j > k, rows

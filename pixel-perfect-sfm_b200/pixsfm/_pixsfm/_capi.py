@@ -325,3 +325,56 @@ def default_context():
     if _DEFAULT_CTX is None:
         _DEFAULT_CTX = Context(-1)
     return _DEFAULT_CTX
+
+
+class KAProblem:
+    """numpy arrays of one keypoint-adjustment problem set + the ctypes view (pxr_ka_desc)."""
+
+    def __init__(self, keypoints, kp_const, edge_src, edge_dst, edge_weight, edge_problem, n_problems, patches,
+                 corner, scale, kp_patch=None, bound=4.0, patches_are_sparse=True, upsampling_factor=1.0):
+        self.keypoints = _as(keypoints, np.float64, (-1, 2)).copy()
+        self.kp_const = _as(kp_const, np.uint8)
+        self.edge_src = _as(edge_src, np.int64)
+        self.edge_dst = _as(edge_dst, np.int64)
+        self.edge_weight = _as(edge_weight, np.float64)
+        self.edge_problem = _as(edge_problem, np.int32)
+        if len(self.edge_problem) > 1 and np.any(np.diff(self.edge_problem) < 0):
+            raise ValueError("edges must be sorted by problem label")
+        self.n_problems = int(n_problems)
+        if patches.dtype not in DTYPE_IDS or not patches.flags["C_CONTIGUOUS"] or patches.ndim != 4:
+            raise ValueError("patches must be a C-contiguous [N,H,W,C] f16/f32/f64 array")
+        self.patches = patches
+        self.corner = _as(corner, np.int32, (-1, 2))
+        self.scale = _as(scale, np.float64, (-1, 2))
+        self.kp_patch = _as(kp_patch, np.int64)
+        self.bound = float(bound)
+        self.patches_are_sparse = bool(patches_are_sparse)
+        self.upsampling_factor = float(upsampling_factor)
+
+    @property
+    def channels(self):
+        return self.patches.shape[3]
+
+    def desc(self):
+        d = KADesc()
+        d.n_keypoints = len(self.keypoints)
+        d.keypoints = _ptr(self.keypoints); d.kp_const = _ptr(self.kp_const); d.kp_patch = _ptr(self.kp_patch)
+        d.n_edges = len(self.edge_src)
+        d.edge_src = _ptr(self.edge_src); d.edge_dst = _ptr(self.edge_dst)
+        d.edge_weight = _ptr(self.edge_weight); d.edge_problem = _ptr(self.edge_problem)
+        d.n_problems = self.n_problems
+        d.n_patches = self.patches.shape[0]
+        d.patches = _ptr(self.patches); d.patches_on_device = 0
+        d.patch_dtype = DTYPE_IDS[self.patches.dtype]
+        d.ph, d.pw, d.channels = self.patches.shape[1:]
+        d.corner = _ptr(self.corner); d.scale = _ptr(self.scale)
+        d.upsampling_factor = self.upsampling_factor
+        d.bound = self.bound
+        d.patches_are_sparse = int(self.patches_are_sparse)
+        return d
+
+    def copy(self):
+        import copy as _copy
+        o = _copy.copy(self)
+        o.keypoints = self.keypoints.copy()
+        return o

@@ -130,3 +130,36 @@ def device_free(ptr, ctx=None):
 def memcpy_d2h(host_array, dev_ptr, nbytes, ctx=None):
     ctx = ctx or _capi.default_context()
     _capi.check(ctx.lib.pxr_memcpy_d2h(ctx.handle, _p(host_array), C.c_void_p(dev_ptr), C.c_size_t(nbytes)))
+
+
+def ka_run(problem, interp=None, options=None, ctx=None):
+    """pxr_ka_run == FeatureMetricKeypointOptimizer.run: refines problem.keypoints IN PLACE."""
+    ctx = ctx or _capi.default_context()
+    interp = interp or _capi.default_interp()
+    options = options or _capi.default_ka_options()
+    d = problem.desc()
+    s = _capi.make_summary(0)
+    _capi.check(ctx.lib.pxr_ka_run(ctx.handle, C.byref(d), C.byref(interp), C.byref(options), C.byref(s)))
+    return _capi.summary_to_dict(s)
+
+
+def graph_labels(node_image, edge_src, edge_dst, edge_sim):
+    """compute_track_labels / compute_score_labels / compute_root_labels on flat arrays (host, bit-exact)."""
+    lib = _capi.load_lib()
+    node_image = np.ascontiguousarray(node_image, np.int32)
+    es = np.ascontiguousarray(edge_src, np.int64); ed = np.ascontiguousarray(edge_dst, np.int64)
+    sim = np.ascontiguousarray(edge_sim, np.float64)
+    n = len(node_image)
+    tl = np.zeros(n, np.int64); sc = np.zeros(n); rt = np.zeros(n, np.uint8)
+    _capi.check(lib.pxr_graph_track_labels(C.c_int64(n), _p(node_image), C.c_int64(len(es)), _p(es), _p(ed), _p(sim), _p(tl)))
+    _capi.check(lib.pxr_graph_score_labels(C.c_int64(n), C.c_int64(len(es)), _p(es), _p(ed), _p(sim), _p(tl), _p(sc)))
+    _capi.check(lib.pxr_graph_root_labels(C.c_int64(n), _p(tl), _p(sc), _p(rt)))
+    return tl, sc, rt
+
+
+def ka_problem_labels(track_labels, max_per_problem=50):
+    lib = _capi.load_lib()
+    tl = np.ascontiguousarray(track_labels, np.int64)
+    out = np.zeros(len(tl), np.int32); nb = C.c_int32()
+    _capi.check(lib.pxr_ka_problem_labels(C.c_int64(len(tl)), _p(tl), int(max_per_problem), _p(out), C.byref(nb)))
+    return out, nb.value

@@ -119,3 +119,19 @@ def refs_compute(prob, interp, loss_type=1, loss_scale=0.25, iters=100):
     refs = np.zeros((d.n_points, prob.channels)); src = np.zeros(d.n_points, np.int64)
     lib().orc_refs_compute(C.byref(d), C.byref(interp), loss_type, C.c_double(loss_scale), iters, p(refs), p(src))
     return refs, src
+
+
+def ka_solve(kaprob, interp, opts):
+    """Oracle KA on kaprob IN PLACE (keypoints updated). Returns (initial_cost, final_cost)."""
+    from pixsfm._pixsfm import _capi
+    d = kaprob.desc()
+    s = _capi.make_summary(0)
+    lib().orc_ka_solve(C.byref(d), C.byref(interp), C.byref(opts), C.byref(s))
+    return s.initial_cost, s.final_cost
+
+
+def ka_evaluate(kaprob, interp, opts):
+    d = kaprob.desc()
+    sq = np.zeros(len(kaprob.edge_src)); cost = C.c_double()
+    lib().orc_ka_evaluate(C.byref(d), C.byref(interp), C.byref(opts), p(sq), C.byref(cost))
+    return sq, cost.value
