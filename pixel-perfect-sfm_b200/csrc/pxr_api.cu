@@ -60,10 +60,10 @@ static int load_nccl() {
   return PXR_OK;
 }
 
-int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count) {
+int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count, bool max_op) {
   if (!ctx->nccl_comm || ctx->world <= 1 || count == 0) return PXR_OK;
-  // ncclFloat64 = 8, ncclSum = 0
-  const int rc = g_nccl.AllReduce(dptr, dptr, count, 8, 0, ctx->nccl_comm, ctx->stream);
+  // ncclFloat64 = 8, ncclSum = 0, ncclMax = 2
+  const int rc = g_nccl.AllReduce(dptr, dptr, count, 8, max_op ? 2 : 0, ctx->nccl_comm, ctx->stream);
   if (rc != 0) return fail(PXR_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
   return PXR_OK;
 }

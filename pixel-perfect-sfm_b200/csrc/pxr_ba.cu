@@ -367,18 +367,32 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   delete st; st = new StageScope(this, 5);
   // rhs rides along as row nc of S: the factorisation performs the forward substitution
   if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
-  const int nb = (int)cdiv(nc, kNB);
-  for (int k = 0; k < nb; ++k) {
-    const int k0 = k * kNB, kb = std::min(kNB, nc - k0);
-    const int rows_below = nc + 1 - (k0 + kb);               // includes the rhs row
-    PXR_LAUNCH(ctx, chol_diag_kernel, 1, 32, 0, S.p, nc, k, rdiag.p, flags.p + 1);
-    if (rows_below > 0) PXR_LAUNCH(ctx, chol_panel_kernel, (unsigned)cdiv(rows_below, kNB), kPanelThreads, 0, S.p, nc, nc + 1, k, rdiag.p);
-    const int nrb = (int)cdiv(nc + 1, kNB);
-    const int rem = nrb - (k + 1);
-    if (rem > 0 && kb == kNB) PXR_LAUNCH(ctx, chol_update_kernel, rem * (rem + 1) / 2, kNB * kNB, 0, S.p, nc, nc + 1, k);
+  // The factorisation + back-substitution is a fixed sequence of ~3*nc/32 dependent launches: it is
+  // captured once into a CUDA graph and replayed, which removes the per-launch gaps.
+  if (nc > 0) {
+    if (!chol_graph_exec) {
+      cudaGraph_t graph = nullptr;
+      PXR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int nb = (int)cdiv(nc, kNB);
+      int64_t captured = 0;
+      for (int k = 0; k < nb; ++k) {
+        const int k0 = k * kNB, kb = std::min(kNB, nc - k0);
+        const int rows_below = nc + 1 - (k0 + kb);               // includes the rhs row
+        chol_diag_kernel<<<1, 32, 0, s>>>(S.p, nc, k, rdiag.p, flags.p + 1); ++captured;
+        if (rows_below > 0) { chol_panel_kernel<<<(unsigned)cdiv(rows_below, kNB), kPanelThreads, 0, s>>>(S.p, nc, nc + 1, k, rdiag.p); ++captured; }
+        const int nrb = (int)cdiv(nc + 1, kNB);
+        const int rem = nrb - (k + 1);
+        if (rem > 0 && kb == kNB) { chol_update_kernel<<<rem * (rem + 1) / 2, kNB * kNB, 0, s>>>(S.p, nc, nc + 1, k); ++captured; }
+      }
+      chol_backsolve_kernel<<<1, 1024, 0, s>>>(S.p, S.p + (size_t)nc * nc, delta.p, nc); ++captured;
+      PXR_CUDA(cudaStreamEndCapture(s, &graph));
+      PXR_CUDA(cudaGraphInstantiate(&chol_graph_exec, graph, 0));
+      cudaGraphDestroy(graph);
+      chol_graph_kernels = captured;
+    }
+    PXR_CUDA(cudaGraphLaunch(chol_graph_exec, s));
+    ctx->launches += chol_graph_kernels;
   }
-  delete st; st = new StageScope(this, 6);
-  if (nc > 0) PXR_LAUNCH(ctx, chol_backsolve_kernel, 1, 1024, 0, S.p, S.p + (size_t)nc * nc, delta.p, nc);
   delete st; st = new StageScope(this, 7);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
   if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p);
@@ -386,12 +400,13 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   PXR_TRY(allreduce_f64(ctx, scalars.p + 4, 1));
   PXR_CUDA(cudaGetLastError());
   delete st;
-  double acc = 0;
-  int fl[4];
+  double acc = 0, fld = 0;
+  PXR_LAUNCH(ctx, flags_to_double_kernel, 1, 1, 0, flags.p, scalars.p + 13);
+  PXR_TRY(allreduce_f64(ctx, scalars.p + 13, 1));  // every rank must take the same branch
   PXR_CUDA(cudaMemcpyAsync(&acc, scalars.p + 4, 8, cudaMemcpyDeviceToHost, s));
-  PXR_CUDA(cudaMemcpyAsync(fl, flags.p, sizeof(fl), cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaMemcpyAsync(&fld, scalars.p + 13, 8, cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaStreamSynchronize(s));
-  const bool solved = fl[0] == 0 && fl[1] == 0 && std::isfinite(acc);
+  const bool solved = fld == 0.0 && std::isfinite(acc);
   *model_cost_change = -acc;
   *valid = solved && (*model_cost_change > 0.0);
   return PXR_OK;
@@ -407,20 +422,17 @@ int BA::apply_step(double* step_norm, double* x_norm) {
   a.cam_o = cam[1 - cur].p; a.q_o = q[1 - cur].p; a.t_o = t[1 - cur].p; a.X_o = X[1 - cur].p;
   a.delta = delta.p; a.acc = scalars.p + 4;
   StageScope st(this, 8);
-  PXR_CUDA(cudaMemsetAsync(scalars.p + 5, 0, 2 * 8, ctx->stream));
+  PXR_CUDA(cudaMemsetAsync(scalars.p + 5, 0, 4 * 8, ctx->stream));
   const int64_t n = std::max<int64_t>(std::max<int64_t>(n_points, n_images), n_cameras);
   PXR_LAUNCH(ctx, ba_plus_kernel, (unsigned)cdiv(n, 128), 128, 0, a);
   PXR_CUDA(cudaGetLastError());
   if (step_norm || x_norm) {
-    if (ctx->world > 1) {
-      // points are sharded, cameras replicated: only the point part must be summed. The norms are
-      // used for parameter_tolerance only; with world>1 they are reported per rank.
-    }
-    double v[2];
-    PXR_CUDA(cudaMemcpyAsync(v, scalars.p + 5, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PXR_TRY(allreduce_f64(ctx, scalars.p + 5, 2));  // point parts are sharded, camera parts replicated
+    double v[4];
+    PXR_CUDA(cudaMemcpyAsync(v, scalars.p + 5, 32, cudaMemcpyDeviceToHost, ctx->stream));
     PXR_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (step_norm) *step_norm = std::sqrt(v[0]);
-    if (x_norm) *x_norm = std::sqrt(v[1]);
+    if (step_norm) *step_norm = std::sqrt(v[0] + v[2]);
+    if (x_norm) *x_norm = std::sqrt(v[1] + v[3]);
   }
   return PXR_OK;
 }
@@ -498,26 +510,28 @@ int BA::inner_iterations(int set) {
 
 int BA::step_norm_between_sets(double* out) {
   cudaStream_t s = ctx->stream;
-  PXR_CUDA(cudaMemsetAsync(scalars.p + 9, 0, 8, s));
-  auto run = [&](const double* a, const double* b, int64_t n) {
-    if (n > 0) PXR_LAUNCH(ctx, diff_norm_kernel, (unsigned)cdiv(n, 256), 256, 0, a, b, n, scalars.p + 9);
+  PXR_CUDA(cudaMemsetAsync(scalars.p + 11, 0, 16, s));
+  auto run = [&](const double* a, const double* b, int64_t n, double* acc) {
+    if (n > 0) PXR_LAUNCH(ctx, diff_norm_kernel, (unsigned)cdiv(n, 256), 256, 0, a, b, n, acc);
   };
-  run(cam[0].p, cam[1].p, (int64_t)n_cameras * kMaxK);
-  run(q[0].p, q[1].p, (int64_t)n_images * 4);
-  run(t[0].p, t[1].p, (int64_t)n_images * 3);
-  run(X[0].p, X[1].p, n_points * 3);
-  double v = 0;
-  PXR_CUDA(cudaMemcpyAsync(&v, scalars.p + 9, 8, cudaMemcpyDeviceToHost, s));
+  run(cam[0].p, cam[1].p, (int64_t)n_cameras * kMaxK, scalars.p + 12);
+  run(q[0].p, q[1].p, (int64_t)n_images * 4, scalars.p + 12);
+  run(t[0].p, t[1].p, (int64_t)n_images * 3, scalars.p + 12);
+  run(X[0].p, X[1].p, n_points * 3, scalars.p + 11);
+  PXR_TRY(allreduce_f64(ctx, scalars.p + 11, 1));
+  double v[2] = {0, 0};
+  PXR_CUDA(cudaMemcpyAsync(v, scalars.p + 11, 16, cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaStreamSynchronize(s));
-  *out = std::sqrt(v);
+  *out = std::sqrt(v[0] + v[1]);
   return PXR_OK;
 }
 
 int BA::gradient_max_norm(double* out) {
-  PXR_CUDA(cudaMemsetAsync(scalars.p + 8, 0, 8, ctx->stream));
+  PXR_CUDA(cudaMemsetAsync(scalars.p + 10, 0, 8, ctx->stream));
   const int64_t n = std::max<int64_t>(nc, n_points);
-  if (n > 0) PXR_LAUNCH(ctx, ba_gradmax_kernel, (unsigned)cdiv(n, 256), 256, 0, dev(), scalars.p + 8);
-  PXR_CUDA(cudaMemcpyAsync(out, scalars.p + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n > 0) PXR_LAUNCH(ctx, ba_gradmax_kernel, (unsigned)cdiv(n, 256), 256, 0, dev(), scalars.p + 10);
+  PXR_TRY(allreduce_f64(ctx, scalars.p + 10, 1, true));
+  PXR_CUDA(cudaMemcpyAsync(out, scalars.p + 10, 8, cudaMemcpyDeviceToHost, ctx->stream));
   PXR_CUDA(cudaStreamSynchronize(ctx->stream));
   return PXR_OK;
 }

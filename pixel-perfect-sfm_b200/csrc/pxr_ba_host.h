@@ -69,6 +69,9 @@ struct BA {
   DevBuf<double> uv, obs_out, juv, Hcc, gc, Hpp, gp, W, S, rhs, diag, jscale, D2, delta, partials, scalars;
   DevBuf<int> flags;
   DevBuf<double> rdiag;
+  cudaGraphExec_t chol_graph_exec = nullptr;
+  int64_t chol_graph_kernels = 0;
+  ~BA() { if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
   // static co-visibility structure for the Schur complement (see ba_schur_pairs_kernel)
   DevBuf<int32_t> sp_px, sp_py;
   DevBuf<int64_t> sp_chunk_begin;

@@ -472,11 +472,11 @@ struct PlusArgs {
   const double* cam; const double* q; const double* t; const double* X;
   double* cam_o; double* q_o; double* t_o; double* X_o;
   const double* delta;
-  double* acc;  // [1] += ||x_plus - x||^2 ; [2] += ||x||^2
+  double* acc;  // points: [1] += ||x_plus - x||^2, [2] += ||x||^2 ; cameras/poses: [3], [4] (replicated across ranks)
 };
 static __global__ void __launch_bounds__(128) ba_plus_kernel(PlusArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double dn = 0.0, xn = 0.0;
+  double dn = 0.0, xn = 0.0, dnc = 0.0, xnc = 0.0;
   if (i < a.n_points) {
     const int64_t po = a.point_off[i];
     for (int k = 0; k < 3; ++k) {
@@ -498,14 +498,14 @@ static __global__ void __launch_bounds__(128) ba_plus_kernel(PlusArgs a) {
         double tp = t[k];
         if (!(a.tmask[i] & (1u << k))) tp += a.delta[po + la++];
         a.t_o[3 * i + k] = tp;
-        dn += (tp - t[k]) * (tp - t[k]);
+        dnc += (tp - t[k]) * (tp - t[k]);
       }
     } else {
       for (int k = 0; k < 4; ++k) qn[k] = q[k];
       for (int k = 0; k < 3; ++k) a.t_o[3 * i + k] = t[k];
     }
-    for (int k = 0; k < 4; ++k) { a.q_o[4 * i + k] = qn[k]; dn += (qn[k] - q[k]) * (qn[k] - q[k]); xn += q[k] * q[k]; }
-    for (int k = 0; k < 3; ++k) xn += t[k] * t[k];
+    for (int k = 0; k < 4; ++k) { a.q_o[4 * i + k] = qn[k]; dnc += (qn[k] - q[k]) * (qn[k] - q[k]); xnc += q[k] * q[k]; }
+    for (int k = 0; k < 3; ++k) xnc += t[k] * t[k];
   }
   if (i < a.n_cameras) {
     const int io = a.intr_off[i];
@@ -516,19 +516,21 @@ static __global__ void __launch_bounds__(128) ba_plus_kernel(PlusArgs a) {
       double cpv = c;
       if (io >= 0 && k < Kc && !(a.cam_mask[i] & (1u << k))) cpv += a.delta[io + la++];
       a.cam_o[i * kMaxK + k] = cpv;
-      dn += (cpv - c) * (cpv - c);
-      if (k < Kc) xn += c * c;
+      dnc += (cpv - c) * (cpv - c);
+      if (k < Kc) xnc += c * c;
     }
   }
-  __shared__ double sh[2][4];
-  dn = warp_sum(dn); xn = warp_sum(xn);
-  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = dn; sh[1][threadIdx.x >> 5] = xn; }
+  __shared__ double sh[4][4];
+  dn = warp_sum(dn); xn = warp_sum(xn); dnc = warp_sum(dnc); xnc = warp_sum(xnc);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = dn; sh[1][threadIdx.x >> 5] = xn; sh[2][threadIdx.x >> 5] = dnc; sh[3][threadIdx.x >> 5] = xnc; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    atomic_add_f64(&a.acc[1], sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]);
-    atomic_add_f64(&a.acc[2], sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3]);
+  if (threadIdx.x < 4) {
+    const double v = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
+    if (v != 0.0) atomic_add_f64(&a.acc[1 + threadIdx.x], v);
   }
 }
+
+static __global__ void flags_to_double_kernel(const int* flags, double* out) { out[0] = (double)(flags[0] + flags[1]); }
 
 // deterministic final reduction of per-warp cost partials: out[0] = sum
 static __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* partials, int64_t n, double* out) {

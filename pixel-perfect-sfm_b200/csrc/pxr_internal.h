@@ -75,6 +75,6 @@ struct DevBuf {
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // allreduce (sum, fp64) on ctx->stream when a communicator is attached; no-op otherwise
-int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count);
+int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count, bool max_op = false);
 
 }  // namespace pxr
