@@ -40,6 +40,7 @@ def usable_cpus():
 
 
 # the CPU baseline uses OpenMP: no busy-waiting worker threads, bind nothing
+os.environ["NCCL_DEBUG"] = os.environ.get("PXR_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
 

@@ -155,6 +155,12 @@ typedef struct {
   /* per-point reference descriptors, fp64 (Reference::descriptor, references.h:32-65);
    * NULL => residual = interpolated feature (costmap use, feature_reference.h:128-130) */
   const double* refs;             /* [n_points][channels] */
+  /* Optional: the patch slab given as several host blocks (one per FeatureMap numpy array, no host-side
+   * concatenation: featuremap.cc:38-44 keeps references to the arrays).  When n_patch_blocks > 0,
+   * `patches` is ignored and patch index i lives in the block b with offsets[b] <= i < offsets[b+1]. */
+  int32_t n_patch_blocks;
+  const void* const* patch_block_ptrs;   /* [n_patch_blocks] */
+  const int64_t* patch_block_counts;     /* [n_patch_blocks] patches per block */
 } pxr_ba_desc;
 
 typedef struct {

@@ -73,7 +73,7 @@ static int check_desc(const pxr_ba_desc* d) {
     return fail(PXR_ERR_INVALID_ARGUMENT, "empty problem");
   if (!d->cam_model || !d->cam_params || !d->cam_const_mask || !d->qvec || !d->tvec || !d->img_cam ||
       !d->pose_const || !d->tvec_const_mask || (d->n_points && (!d->xyz || !d->point_const)) ||
-      (d->n_obs && (!d->obs_img || !d->obs_pt)) || !d->patches || !d->corner || !d->scale)
+      (d->n_obs && (!d->obs_img || !d->obs_pt)) || (!d->patches && d->n_patch_blocks <= 0) || !d->corner || !d->scale)
     return fail(PXR_ERR_INVALID_ARGUMENT, "a required array is NULL");
   if (!fm_supported(d->patch_dtype, d->channels))
     return fail(PXR_ERR_UNSUPPORTED, "Unsupported dimensions (CHANNELS=%d, dtype=%d, N_NODES=1).", d->channels, d->patch_dtype);
@@ -109,7 +109,21 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   double h2d_patch = 0;
   const size_t esz = dtype == PXR_F16 ? 2 : (dtype == PXR_F32 ? 4 : 8);
   const size_t pbytes = (size_t)n_patches * ph * pw * C * esz;
-  if (d->patches_on_device) {
+  if (d->n_patch_blocks > 0) {
+    if (!d->patch_block_ptrs || !d->patch_block_counts) return fail(PXR_ERR_INVALID_ARGUMENT, "patch block arrays are NULL");
+    int64_t tot = 0;
+    for (int b = 0; b < d->n_patch_blocks; ++b) tot += d->patch_block_counts[b];
+    if (tot < n_patches) return fail(PXR_ERR_INVALID_ARGUMENT, "patch blocks hold %lld patches, %lld needed", (long long)tot, (long long)n_patches);
+    PXR_TRY(patches_owned.alloc((size_t)tot * ph * pw * C * esz));
+    size_t off = 0;
+    for (int b = 0; b < d->n_patch_blocks; ++b) {
+      const size_t bytes = (size_t)d->patch_block_counts[b] * ph * pw * C * esz;
+      if (bytes) PXR_CUDA(cudaMemcpyAsync(patches_owned.p + off, d->patch_block_ptrs[b], bytes, cudaMemcpyHostToDevice, s));
+      off += bytes;
+    }
+    h2d_patch = (double)off;
+    d_patches = patches_owned.p;
+  } else if (d->patches_on_device) {
     d_patches = (const uint8_t*)d->patches;
   } else {
     PXR_TRY(patches_owned.alloc(pbytes));

@@ -1,0 +1,372 @@
+"""Mirror of `pixsfm._pixsfm._bundle_adjustment` (pixsfm/bundle_adjustment/bindings.cc:28-177) backed by the
+C-ABI: BundleAdjustmentSetup, BundleOptimizerOptions, ReferenceConfig, ReferenceExtractor and
+FeatureReferenceBundleOptimizer.  This layer restates the reference's problem construction
+(bundle_optimizer.h:139-165,247-331) and parameterisation rules (:335-442) as integer logic that
+resolves to the SoA problem IR of include/pxr.h; all arithmetic runs in libpxr.so on the GPU."""
+import numpy as np
+
+from . import _capi, _engine
+from ._base import InterpolationConfig
+from ._features import FeatureView, PatchSlab, Reference
+from .. import logger
+
+
+class BundleAdjustmentSetup:
+    """colmap::BundleAdjustmentConfig with pixsfm's throwing overrides (bundle_adjustment_options.cc:7-31)."""
+
+    def __init__(self):
+        self._images, self._const_poses, self._const_tvecs = set(), set(), {}
+        self._const_cameras, self._var_points, self._const_points = set(), set(), set()
+
+    # images
+    def add_image(self, image_id): self._images.add(int(image_id))
+    def add_images(self, image_ids):
+        for i in image_ids: self.add_image(i)
+    def has_image(self, image_id): return int(image_id) in self._images
+    def remove_image(self, image_id): self._images.discard(int(image_id))
+    @property
+    def image_ids(self): return set(self._images)
+    def num_images(self): return len(self._images)
+    # cameras
+    def set_constant_camera(self, camera_id): self._const_cameras.add(int(camera_id))
+    def set_variable_camera(self, camera_id): self._const_cameras.discard(int(camera_id))
+    def is_constant_camera(self, camera_id): return int(camera_id) in self._const_cameras
+    # poses
+    def set_constant_pose(self, image_id):
+        if not self.has_image(image_id) or self.has_constant_tvec(image_id):
+            raise ValueError("set_constant_pose: image must be in the setup and must not have a constant tvec")
+        self._const_poses.add(int(image_id))
+    def set_variable_pose(self, image_id): self._const_poses.discard(int(image_id))
+    def has_constant_pose(self, image_id): return int(image_id) in self._const_poses
+    def set_constant_tvec(self, image_id, idxs):
+        idxs = [int(i) for i in idxs]
+        if not (0 < len(idxs) <= 3) or not self.has_image(image_id) or self.has_constant_pose(image_id) or len(set(idxs)) != len(idxs):
+            raise ValueError("set_constant_tvec: invalid arguments")
+        self._const_tvecs[int(image_id)] = idxs
+    def remove_constant_tvec(self, image_id): self._const_tvecs.pop(int(image_id), None)
+    def has_constant_tvec(self, image_id): return int(image_id) in self._const_tvecs
+    def constant_tvec(self, image_id): return self._const_tvecs[int(image_id)]
+    # points
+    def add_variable_point(self, point3D_id):
+        if self.has_constant_point(point3D_id): raise ValueError("point is already constant")
+        self._var_points.add(int(point3D_id))
+    def add_constant_point(self, point3D_id):
+        if self.has_variable_point(point3D_id): raise ValueError("point is already variable")
+        self._const_points.add(int(point3D_id))
+    def has_point(self, p): return self.has_variable_point(p) or self.has_constant_point(p)
+    def has_variable_point(self, p): return int(p) in self._var_points
+    def has_constant_point(self, p): return int(p) in self._const_points
+    def remove_variable_point(self, p): self._var_points.discard(int(p))
+    def remove_constant_point(self, p): self._const_points.discard(int(p))
+    @property
+    def variable_point3D_ids(self): return set(self._var_points)
+    @property
+    def constant_point3D_ids(self): return set(self._const_points)
+
+
+class _DictOptions:
+    """make_dataclass semantics (_pixsfm/src/helpers.h:149-303): dict/kwargs construction, strict keys."""
+    _defaults = {}
+
+    def __init__(self, conf=None, **kw):
+        for k, v in self._defaults.items():
+            setattr(self, k, v() if callable(v) else v)
+        self.mergedict(dict(conf or {}, **kw))
+
+    def mergedict(self, d):
+        for k, v in d.items():
+            if k not in self._defaults:
+                raise ValueError("%s: unknown option '%s'" % (type(self).__name__, k))
+            cur = getattr(self, k)
+            if isinstance(cur, dict) and isinstance(v, dict):
+                merged = dict(cur); merged.update(v); v = merged
+            setattr(self, k, v)
+
+    def todict(self):
+        return {k: getattr(self, k) for k in self._defaults}
+
+
+_SOLVER_KEYS = {"function_tolerance", "gradient_tolerance", "parameter_tolerance", "minimizer_progress_to_stdout",
+                "max_num_iterations", "max_linear_solver_iterations", "max_num_consecutive_invalid_steps",
+                "max_consecutive_nonmonotonic_steps", "use_inner_iterations", "use_nonmonotonic_steps",
+                "update_state_every_iteration", "num_threads", "callbacks", "inner_iteration_tolerance",
+                "initial_trust_region_radius", "max_trust_region_radius", "min_trust_region_radius",
+                "min_relative_decrease", "min_lm_diagonal", "max_lm_diagonal", "jacobi_scaling", "logging_type"}
+
+
+def solver_options_from(loss, solver, base):
+    """{"name","params"} + pyceres-SolverOptions-like dict -> pxr_solver_options"""
+    o = base
+    name = str(loss.get("name", "cauchy")).lower()
+    if name not in _capi.LOSS_IDS:
+        raise ValueError("unsupported loss '%s'" % name)
+    o.loss_type = _capi.LOSS_IDS[name]
+    params = loss.get("params", [])
+    o.loss_scale = float(params[0]) if len(params) else 1.0
+    for k, v in solver.items():
+        if k not in _SOLVER_KEYS:
+            raise ValueError("solver: unknown option '%s'" % k)
+        if k == "use_nonmonotonic_steps" and v:
+            raise ValueError("use_nonmonotonic_steps=True is not supported on the B200 path")
+        if hasattr(o, k) and k != "callbacks":
+            setattr(o, k, type(getattr(o, k))(v))
+    return o
+
+
+class BundleOptimizerOptions(_DictOptions):
+    """bundle_adjustment_options.h:44-98 (C++ defaults; the Python BundleAdjuster overrides `solver`)"""
+    _defaults = dict(refine_focal_length=True, refine_principal_point=False, refine_extra_params=True,
+                     refine_extrinsics=True, print_summary=True, min_track_length=-1,
+                     loss=lambda: {"name": "cauchy", "params": [0.25]},
+                     solver=lambda: {"function_tolerance": 0.0, "gradient_tolerance": 0.0, "parameter_tolerance": 0.0,
+                                     "max_num_iterations": 100, "max_linear_solver_iterations": 200,
+                                     "max_num_consecutive_invalid_steps": 10, "use_inner_iterations": False})
+
+
+class ReferenceConfig(_DictOptions):
+    """reference_extractor.h:57-67 (C++ default iters=10; the Python layer passes 100)"""
+    _defaults = dict(keep_observations=False, iters=10, compute_offsets3D=False, num_threads=-1,
+                     loss=lambda: {"name": "cauchy", "params": [0.25]})
+
+
+def _cam_const_mask(camera, options, setup, camera_id):
+    constant_camera = not (options.refine_focal_length or options.refine_principal_point or options.refine_extra_params)
+    if constant_camera or setup.is_constant_camera(camera_id):
+        return 0xFFFFFFFF
+    focal, pp, extra = _capi.CAMERA_PARAM_GROUPS[int(camera.model_id)]
+    mask = 0
+    if not options.refine_focal_length: mask |= focal
+    if not options.refine_principal_point: mask |= pp
+    if not options.refine_extra_params: mask |= extra
+    return mask
+
+
+class ProblemIR:
+    """Index maps between the reconstruction and the flat problem IR."""
+
+    def __init__(self):
+        self.image_ids, self.camera_ids, self.point_ids = [], [], []
+        self.obs = []  # (image_id, point2D_idx, point3D_id)
+
+
+def build_problem(reconstruction, feature_view, setup, options, references=None, for_references=None):
+    """Restates BundleOptimizer::SetUp + Parameterize for the featuremetric optimizer and returns
+    (_capi.BAProblem, ProblemIR).  With `for_references` (a set of point3D ids) the observation list is the
+    one of ReferenceExtractor::GetVisibleObservations instead (reference_extractor.h:171-205)."""
+    rec = reconstruction
+    ir = ProblemIR()
+    obs = []                      # (point3D_id, image_id, point2D_idx)
+    reg_track = {}                # point3D_id -> set(track idx)   (point3D_reg_track_idx_)
+    image_num_residuals, camera_num_residuals = {}, {}
+    setup_images = sorted(setup.image_ids) if setup is not None else []
+    extra_const_cameras = set()
+
+    def add_residual(image_id, point2D_idx):
+        image = rec.images[image_id]
+        p2D = image.points2D[point2D_idx]
+        if not p2D.has_point3D():
+            return
+        pid = p2D.point3D_id
+        obs.append((pid, image_id, point2D_idx))
+        constant_pose = (not options.refine_extrinsics) or setup.has_constant_pose(image_id)
+        if not constant_pose:
+            image_num_residuals[image_id] = image_num_residuals.get(image_id, 0) + 1
+        track = rec.points3D[pid].track.elements
+        for k, el in enumerate(track):   # RegisterPoint3DObservation (linear search, :321-327)
+            if el.image_id == image_id and el.point2D_idx == point2D_idx:
+                reg_track.setdefault(pid, set()).add(k)
+                break
+        else:
+            raise RuntimeError("Failed to register track element.")
+        camera_num_residuals[image.camera_id] = camera_num_residuals.get(image.camera_id, 0) + 1
+
+    if for_references is None:
+        for image_id in setup_images:                      # AddImageToProblem (:247-275)
+            image = rec.images[image_id]
+            image.qvec /= np.linalg.norm(image.qvec)       # image.NormalizeQvec()
+            for p2D_idx in range(len(image.points2D)):
+                p2D = image.points2D[p2D_idx]
+                if not p2D.has_point3D():
+                    continue
+                if rec.points3D[p2D.point3D_id].track.length() < options.min_track_length:
+                    continue
+                add_residual(image_id, p2D_idx)
+        for pid in list(sorted(setup.variable_point3D_ids)) + list(sorted(setup.constant_point3D_ids)):   # AddPointToProblem (:277-313)
+            track = rec.points3D[pid].track.elements
+            if len(reg_track.get(pid, ())) == len(track):
+                continue
+            for el in track:
+                if setup.has_image(el.image_id):
+                    continue
+                cam_id = rec.images[el.image_id].camera_id
+                if camera_num_residuals.get(cam_id, 0) == 0:
+                    extra_const_cameras.add(cam_id)
+                add_residual(el.image_id, el.point2D_idx)
+    else:
+        for pid in sorted(for_references):
+            for el in rec.points3D[pid].track.elements:
+                if not feature_view.has_feature_patch(el.image_id, el.point2D_idx):
+                    logger.warning("Warning: Patch at (%d, %d) does not exist.", el.image_id, el.point2D_idx)
+                    continue
+                obs.append((pid, el.image_id, el.point2D_idx))
+
+    # canonical order of the IR: observations sorted by point id (stable: image enumeration order kept)
+    order = sorted(range(len(obs)), key=lambda k: obs[k][0])
+    obs = [obs[k] for k in order]
+    ir.point_ids = sorted({o[0] for o in obs})
+    ir.image_ids = sorted({o[1] for o in obs})
+    ir.camera_ids = sorted({rec.images[i].camera_id for i in ir.image_ids})
+    pidx = {p: k for k, p in enumerate(ir.point_ids)}
+    iidx = {i: k for k, i in enumerate(ir.image_ids)}
+    cidx = {c: k for k, c in enumerate(ir.camera_ids)}
+    ir.obs = [(o[1], o[2], o[0]) for o in obs]
+
+    n_img, n_cam, n_pts = len(ir.image_ids), len(ir.camera_ids), len(ir.point_ids)
+    cam_model = np.array([int(rec.cameras[c].model_id) for c in ir.camera_ids], np.int32)
+    cam_params = [np.asarray(rec.cameras[c].params, np.float64) for c in ir.camera_ids]
+    qvec = np.array([rec.images[i].qvec for i in ir.image_ids], np.float64).reshape(-1, 4)
+    tvec = np.array([rec.images[i].tvec for i in ir.image_ids], np.float64).reshape(-1, 3)
+    img_cam = np.array([cidx[rec.images[i].camera_id] for i in ir.image_ids], np.int32)
+    xyz = np.array([rec.points3D[p].xyz for p in ir.point_ids], np.float64).reshape(-1, 3)
+    pose_const = np.ones(n_img, np.uint8)
+    tmask = np.zeros(n_img, np.uint8)
+    point_const = np.zeros(n_pts, np.uint8)
+    cam_mask = np.full(n_cam, 0xFFFFFFFF, np.uint32)
+    if for_references is None:
+        # ParameterizeImages (:360-398)
+        for image_id, nres in image_num_residuals.items():
+            if nres <= 0:
+                continue
+            constant_pose = (not options.refine_extrinsics) or setup.has_constant_pose(image_id) or not setup.has_image(image_id)
+            if not constant_pose:
+                pose_const[iidx[image_id]] = 0
+                if setup.has_constant_tvec(image_id):
+                    for k in setup.constant_tvec(image_id):
+                        tmask[iidx[image_id]] |= (1 << k)
+        # ParameterizeCameras (:400-442)
+        for cam_id, nres in camera_num_residuals.items():
+            if nres <= 0:
+                continue
+            if cam_id in extra_const_cameras:
+                cam_mask[cidx[cam_id]] = 0xFFFFFFFF
+            else:
+                cam_mask[cidx[cam_id]] = _cam_const_mask(rec.cameras[cam_id], options, setup, cam_id)
+        # ParameterizePoints (:335-358)
+        for pid, reg in reg_track.items():
+            tl = rec.points3D[pid].track.length()
+            mtl = min(options.min_track_length, tl) if options.min_track_length > 0 else tl
+            if mtl > len(reg):
+                point_const[pidx[pid]] = 1
+        for pid in setup.constant_point3D_ids:
+            if pid in pidx:
+                point_const[pidx[pid]] = 1
+
+    if not obs:
+        import types
+        return types.SimpleNamespace(n_obs=0), ir
+    slab = PatchSlab()
+    obs_patch = np.zeros(len(obs), np.int64)
+    for k, (pid, image_id, p2D_idx) in enumerate(obs):
+        name = feature_view.image_name(image_id)
+        obs_patch[k] = slab.index(name, feature_view.get_feature_map(image_id), p2D_idx)
+    blocks, corners, scales = slab.arrays()
+    refs = None
+    if references is not None:
+        C_ = feature_view.channels
+        refs = np.zeros((n_pts, C_))
+        for pid in ir.point_ids:
+            refs[pidx[pid]] = np.asarray(references[pid].descriptor, np.float64).reshape(-1)[:C_]
+    prob = _capi.BAProblem(cam_model=cam_model, cam_params=cam_params, cam_const_mask=cam_mask, qvec=qvec, tvec=tvec,
+                           img_cam=img_cam, pose_const=pose_const, tvec_const_mask=tmask, xyz=xyz,
+                           point_const=point_const, obs_img=np.array([iidx[o[1]] for o in obs], np.int32),
+                           obs_pt=np.array([pidx[o[0]] for o in obs], np.int64), patches=None, corner=corners,
+                           scale=scales, refs=refs, obs_patch=obs_patch, patch_blocks=blocks)
+    return prob, ir
+
+
+def write_back(reconstruction, prob, ir):
+    """the reference updates the Reconstruction in place through raw double* (feature_reference_bundle_optimizer.h:111-114)"""
+    for k, i in enumerate(ir.image_ids):
+        reconstruction.images[i].qvec[:] = prob.qvec[k]
+        reconstruction.images[i].tvec[:] = prob.tvec[k]
+    for k, c in enumerate(ir.camera_ids):
+        n = len(reconstruction.cameras[c].params)
+        reconstruction.cameras[c].params[:] = prob.cam_params[k, :n]
+    for k, p in enumerate(ir.point_ids):
+        reconstruction.points3D[p].xyz[:] = prob.xyz[k]
+
+
+class ReferenceExtractor:
+    """_bundle_adjustment.ReferenceExtractor(ReferenceConfig|dict, InterpolationConfig|dict).run(problem_labels,
+    reconstruction, feature_set) -> {point3D_id: Reference}"""
+
+    def __init__(self, config, interpolation_config):
+        self.config = config if isinstance(config, ReferenceConfig) else ReferenceConfig(config)
+        self.interp = interpolation_config if isinstance(interpolation_config, InterpolationConfig) else InterpolationConfig(interpolation_config)
+        self.interp.validate_for_device()
+
+    def run(self, problem_labels, reconstruction, feature_set):
+        ids = {p for p in reconstruction.points3D.keys() if p < len(problem_labels) and problem_labels[p] >= 0}
+        fview = FeatureView(feature_set, reconstruction)
+        prob, ir = build_problem(reconstruction, fview, None, None, None, for_references=ids)
+        refs = {p: Reference() for p in ids}   # InitReferences
+        if prob.n_obs == 0:
+            return refs
+        loss = self.config.loss
+        if str(loss.get("name", "cauchy")).lower() not in _capi.LOSS_IDS:
+            raise ValueError("unsupported loss")
+        ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
+        desc, src = _engine.refs_compute(prob, ic, _capi.LOSS_IDS[str(loss.get("name", "cauchy")).lower()],
+                                         float(loss.get("params", [1.0])[0]), int(self.config.iters))
+        for k, pid in enumerate(ir.point_ids):
+            if src[k] < 0:
+                continue
+            image_id, p2D_idx, _ = ir.obs[int(src[k])]
+            refs[pid] = Reference((image_id, p2D_idx), desc[k].reshape(1, -1).copy())
+        return refs
+
+
+class _Summary(dict):
+    __getattr__ = dict.get
+
+
+class FeatureReferenceBundleOptimizer:
+    """_bundle_adjustment.FeatureReferenceBundleOptimizer(options, setup, interpolation)
+    .run(reconstruction, feature_view, references) -> bool   (mutates `reconstruction` in place)"""
+
+    def __init__(self, options, setup, interpolation_config):
+        self.options = options if isinstance(options, BundleOptimizerOptions) else BundleOptimizerOptions(options)
+        self.setup = setup
+        self.interp = interpolation_config if isinstance(interpolation_config, InterpolationConfig) else InterpolationConfig(interpolation_config)
+        self._summary, self._used = None, False
+        logger.info("Start feature-reference bundle adjustment.")
+
+    def run(self, reconstruction, feature_view, references):
+        if reconstruction is None:
+            raise ValueError("reconstruction cannot be NULL.")
+        if self._used:
+            raise ValueError("Cannot use the same BundleOptimizer multiple times")
+        self._used = True
+        self.interp.validate_for_device()
+        n_nodes = len(self.interp.nodes)
+        if (feature_view.channels, n_nodes) not in {(c, 1) for c in (8, 16, 32, 64, 128, 256)}:
+            raise ValueError("Unsupported dimensions (CHANNELS,N_NODES).")
+        prob, ir = build_problem(reconstruction, feature_view, self.setup, self.options, references)
+        if prob.n_obs == 0:
+            return False   # problem_->NumResiduals() == 0 (bundle_optimizer.h:175-177)
+        so = solver_options_from(self.options.loss, self.options.solver, _capi.default_ba_options(use_inner_iterations=0))
+        ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
+        callbacks = self.options.solver.get("callbacks") or []
+        s = _engine.ba_run(prob, ic, so)
+        for cb in callbacks:   # ceres IterationCallback-like objects are invoked once per recorded iteration
+            for it in s["iterations"]:
+                cb(it)
+        write_back(reconstruction, prob, ir)
+        self._summary = _Summary(s, num_residuals_reduced=s["num_residuals"], total_time_in_seconds=s["total_time_s"])
+        nres = max(1, s["num_residuals"])
+        logger.info("BA Time: %.4gs, cost change: %.6g --> %.6g", s["total_time_s"],
+                    np.sqrt(s["initial_cost"] / nres), np.sqrt(s["final_cost"] / nres))
+        return True
+
+    def summary(self):
+        return self._summary

@@ -62,7 +62,8 @@ class BADesc(C.Structure):
                 ("n_patches", C.c_int64), ("patches", C.c_void_p), ("patches_on_device", C.c_int32),
                 ("patch_dtype", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
                 ("channels", C.c_int32), ("corner", C.c_void_p), ("scale", C.c_void_p),
-                ("upsampling_factor", C.c_double), ("refs", C.c_void_p)]
+                ("upsampling_factor", C.c_double), ("refs", C.c_void_p),
+                ("n_patch_blocks", C.c_int32), ("patch_block_ptrs", C.c_void_p), ("patch_block_counts", C.c_void_p)]
 
 
 class IterationSummary(C.Structure):
@@ -160,7 +161,7 @@ class BAProblem:
     def __init__(self, cam_model, cam_params, cam_const_mask, qvec, tvec, img_cam, pose_const,
                  tvec_const_mask, xyz, point_const, obs_img, obs_pt, patches, corner, scale,
                  refs=None, obs_patch=None, upsampling_factor=1.0, patches_on_device=False,
-                 patch_shape=None, patch_dtype=None):
+                 patch_shape=None, patch_dtype=None, patch_blocks=None):
         self.cam_model = _as(cam_model, np.int32)
         nc = len(self.cam_model)
         cp = np.zeros((nc, PXR_MAX_CAM_PARAMS), np.float64)
@@ -186,7 +187,22 @@ class BAProblem:
             raise ValueError("observations must be sorted by point index")
         self.obs_patch = _as(obs_patch, np.int64)
         self.patches_on_device = bool(patches_on_device)
-        if self.patches_on_device:
+        self.patch_blocks = None
+        if patch_blocks is not None:
+            # list of C-contiguous [n_i, H, W, C] arrays (one per FeatureMap), uploaded without concatenation
+            blocks = [b for b in patch_blocks]
+            for b in blocks:
+                if b.dtype not in DTYPE_IDS or not b.flags["C_CONTIGUOUS"] or b.ndim != 4 or b.shape[1:] != blocks[0].shape[1:]:
+                    raise ValueError("patch blocks must be C-contiguous [N,H,W,C] arrays of one dtype/shape")
+            self.patch_blocks = blocks
+            self._block_ptrs = (C.c_void_p * len(blocks))(*[b.ctypes.data for b in blocks])
+            self._block_counts = np.array([b.shape[0] for b in blocks], np.int64)
+            self.patches = None
+            self._patches_ptr = blocks[0].ctypes.data
+            self.n_patches = int(self._block_counts.sum())
+            _, self.ph, self.pw, self.channels = blocks[0].shape
+            self.patch_dtype = DTYPE_IDS[blocks[0].dtype]
+        elif self.patches_on_device:
             self.patches = None
             self._patches_ptr = int(patches)
             self.n_patches, self.ph, self.pw, self.channels = patch_shape
@@ -227,6 +243,10 @@ class BAProblem:
         d.corner = _ptr(self.corner); d.scale = _ptr(self.scale)
         d.upsampling_factor = self.upsampling_factor
         d.refs = _ptr(self.refs)
+        if self.patch_blocks is not None:
+            d.n_patch_blocks = len(self.patch_blocks)
+            d.patch_block_ptrs = C.cast(self._block_ptrs, C.c_void_p)
+            d.patch_block_counts = _ptr(self._block_counts)
         return d
 
     def copy(self):

@@ -1,0 +1,197 @@
+"""Mirror of `pixsfm._pixsfm._features` (pixsfm/features/bindings.cc:38-300): FeaturePatch / FeatureMap /
+FeatureSet / FeatureView / FeatureManager and Reference.  Patches stay numpy references (no copy), as
+featuremap.cc:9-45 does; the device upload happens when an optimizer runs.  HDF5 loading
+(featuremap.cc:138-267) is out of scope this round (no HDF5 offline)."""
+import numpy as np
+
+kDenseId = 1000000  # util/src/types.h:33
+
+
+class FeaturePatch:
+    def __init__(self, data, corner, scale, upsampling_factor=1.0):
+        self.data = data  # [H,W,C] view
+        self.corner = np.asarray(corner, np.int32)
+        self.scale = np.asarray(scale, np.float64)
+        self.upsampling_factor = float(upsampling_factor)
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def height(self):
+        return self.data.shape[0]
+
+    @property
+    def width(self):
+        return self.data.shape[1]
+
+    @property
+    def channels(self):
+        return self.data.shape[2]
+
+    def to_pixel_coordinates(self, xy):  # featurepatch.h:250-255
+        return (np.asarray(xy) * self.scale - 0.5 - self.corner) * self.upsampling_factor
+
+
+class FeatureMap:
+    """FeatureMap(patches[N,H,W,C] C-contiguous, point2D_ids, corners[N,2] (x,y) int32, metadata{"scale","is_sparse"})"""
+
+    def __init__(self, patches, point2D_ids, corners, metadata):
+        patches = np.asarray(patches)
+        if patches.ndim != 4 or not patches.flags["C_CONTIGUOUS"]:
+            raise ValueError("patches must be a C-contiguous [N,H,W,C] array")
+        if patches.dtype not in (np.float16, np.float32, np.float64):
+            raise ValueError("patches must be float16/float32/float64")
+        self.patches = patches
+        self.point2D_ids = [int(i) for i in point2D_ids]
+        if len(self.point2D_ids) != patches.shape[0]:
+            raise ValueError("number of point2D_ids and patches differ")
+        self.corners = np.ascontiguousarray(corners, np.int32).reshape(-1, 2)
+        self.scale = np.asarray(metadata["scale"], np.float64).reshape(2)
+        self.is_sparse = bool(metadata.get("is_sparse", True))
+        self._index = {pid: k for k, pid in enumerate(self.point2D_ids)}
+
+    @property
+    def shape(self):
+        return self.patches.shape[1:]
+
+    @property
+    def channels(self):
+        return self.patches.shape[3]
+
+    @property
+    def dtype(self):
+        return self.patches.dtype
+
+    def size(self):
+        return self.patches.shape[0]
+
+    def has_point2D(self, point2D_idx):
+        return int(point2D_idx) in self._index
+
+    def local_index(self, point2D_idx):
+        if not self.is_sparse and kDenseId in self._index:
+            raise ValueError("dense feature maps are not supported on the B200 path yet")
+        return self._index[int(point2D_idx)]
+
+    def fpatch(self, point2D_idx):
+        k = self.local_index(point2D_idx)
+        return FeaturePatch(self.patches[k], self.corners[k], self.scale)
+
+
+class FeatureSet:
+    def __init__(self, channels=None, dtype=None):
+        self._channels, self._dtype, self._maps = channels, dtype, {}
+
+    @property
+    def channels(self):
+        return self._channels
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    def emplace(self, image_name, fmap):
+        if self._channels is None:
+            self._channels = fmap.channels
+        if fmap.channels != self._channels:
+            raise ValueError("FeatureMap has %d channels, FeatureSet expects %d" % (fmap.channels, self._channels))
+        if self._dtype is None:
+            self._dtype = fmap.dtype
+        self._maps[image_name] = fmap
+
+    __setitem__ = emplace
+
+    def has_fmap(self, image_name):
+        return image_name in self._maps
+
+    def fmap(self, image_name):
+        return self._maps[image_name]
+
+    __getitem__ = fmap
+
+    def keys(self):
+        return self._maps.keys()
+
+
+class FeatureManager:
+    def __init__(self, channels_per_level, dtype=np.float16):
+        self.fsets = [FeatureSet(c, np.dtype(dtype)) for c in channels_per_level]
+
+    @property
+    def num_levels(self):
+        return len(self.fsets)
+
+    def fset(self, level_index):
+        return self.fsets[level_index]
+
+
+class FeatureView:
+    """FeatureView(feature_set, reconstruction | graph): resolves image ids to names (featureview.cc:70-126)."""
+
+    def __init__(self, feature_set, source, *_):
+        self.fset = feature_set
+        if hasattr(source, "image_id_to_name"):
+            self._id_to_name = dict(source.image_id_to_name)
+        else:
+            self._id_to_name = {iid: im.name for iid, im in source.images.items()}
+
+    @property
+    def channels(self):
+        return self.fset.channels
+
+    def image_name(self, image_id):
+        return self._id_to_name[image_id]
+
+    def has_feature_patch(self, image_id, point2D_idx):
+        name = self._id_to_name.get(image_id)
+        return name is not None and self.fset.has_fmap(name) and self.fset.fmap(name).has_point2D(point2D_idx)
+
+    def get_feature_map(self, image_id):
+        return self.fset.fmap(self._id_to_name[image_id])
+
+    def get_feature_patch(self, image_id, point2D_idx):
+        return self.get_feature_map(image_id).fpatch(point2D_idx)
+
+
+class Reference:
+    """features/src/references.h:32-65 (fields used on the named path)"""
+
+    def __init__(self, source=(0, 0), descriptor=None):
+        self.source = source  # (image_id, point2D_idx)
+        self.descriptor = descriptor  # [n_nodes, C] float64
+        self.track, self.observations, self.costs = None, [], []
+
+    @property
+    def source_image_id(self):
+        return self.source[0]
+
+    @property
+    def source_point2D_idx(self):
+        return self.source[1]
+
+    def channels(self):
+        return self.descriptor.shape[1]
+
+    def num_nodes(self):
+        return self.descriptor.shape[0]
+
+
+class PatchSlab:
+    """Device-upload plan for a set of FeatureMaps: blocks in first-use order + global patch indices."""
+
+    def __init__(self):
+        self.blocks, self.corners, self.scales, self._offset, self._n = [], [], [], {}, 0
+
+    def index(self, image_name, fmap, point2D_idx):
+        if image_name not in self._offset:
+            self._offset[image_name] = self._n
+            self.blocks.append(fmap.patches)
+            self.corners.append(fmap.corners)
+            self.scales.append(np.tile(fmap.scale, (fmap.size(), 1)))
+            self._n += fmap.size()
+        return self._offset[image_name] + fmap.local_index(point2D_idx)
+
+    def arrays(self):
+        return self.blocks, np.concatenate(self.corners), np.concatenate(self.scales)

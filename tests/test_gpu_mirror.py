@@ -1,0 +1,87 @@
+"""End-to-end through the reference-facing Python surface (BundleAdjuster / KeypointAdjuster, the names and call
+shapes of the reference's pixsfm package) on the GPU, checked against the oracle run on the same problem IR."""
+import copy
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pixsfm import base, bundle_adjustment as ba_pkg, features, keypoint_adjustment as ka_pkg
+from pixsfm._pixsfm import _bundle_adjustment as ba
+from pixsfm._pixsfm import _capi
+from pixsfm.util import synthetic
+from recon_util import make_reconstruction
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bundle_adjuster_refine_multilevel_matches_oracle():
+    rec, fm, _, gt = make_reconstruction(n_cams=6, n_points=60, track_len=4, channels=128, seed=21)
+    rec_ref = copy.deepcopy(rec)
+    conf = {"optimizer": {"solver": {"max_num_iterations": 12}}}
+    out = ba_pkg.BundleAdjuster.create(conf).refine_multilevel(rec, fm)
+    assert len(out["summary"]) == 1 and len(out["references"]) == 1
+    summary, references = out["summary"][0], out["references"][0]
+    assert summary.final_cost < summary.initial_cost
+    # oracle on the IR the mirror builds from the untouched copy
+    setup = ba_pkg.default_problem_setup(rec_ref)
+    options = ba.BundleOptimizerOptions()
+    fview = features.FeatureView(fm.fset(0), rec_ref)
+    ic = _capi.default_interp()
+    prob_r, ir_r = ba.build_problem(rec_ref, fview, None, None, None, for_references=set(rec_ref.points3D.keys()))
+    refs_o, src_o = O.refs_compute(prob_r, ic, iters=100)
+    for k, pid in enumerate(ir_r.point_ids):   # reference source + descriptor: index bit-exact, values tight
+        assert references[pid].source == ir_r.obs[int(src_o[k])][:2]
+        assert np.abs(references[pid].descriptor.reshape(-1) - refs_o[k]).max() < 1e-12
+    oracle_refs = {pid: features.Reference(ir_r.obs[int(src_o[k])][:2], refs_o[k].reshape(1, -1)) for k, pid in enumerate(ir_r.point_ids)}
+    prob, ir = ba.build_problem(rec_ref, fview, setup, options, oracle_refs)
+    so = _capi.default_ba_options(use_inner_iterations=1, max_num_iterations=12)
+    s = O.ba_solve(prob, ic, so)
+    assert abs(summary.final_cost - s["final_cost"]) <= 1e-6 * s["final_cost"]
+    ba.write_back(rec_ref, prob, ir)
+    for i in rec.images:
+        assert np.abs(rec.images[i].qvec - rec_ref.images[i].qvec).max() < 1e-6
+        assert np.abs(rec.images[i].tvec - rec_ref.images[i].tvec).max() < 1e-6
+    for c in rec.cameras:
+        assert np.abs(rec.cameras[c].params[1:] - rec_ref.cameras[c].params[1:]).max() < 1e-6
+        assert abs(rec.cameras[c].params[0] / rec_ref.cameras[c].params[0] - 1) < 1e-6
+    for p in rec.points3D:
+        assert np.abs(rec.points3D[p].xyz - rec_ref.points3D[p].xyz).max() < 1e-6
+    # gauge: first image untouched, x translation of the second fixed (default_problem_setup)
+    assert np.array_equal(rec.images[1].qvec / np.linalg.norm(rec.images[1].qvec), rec.images[1].qvec)
+
+
+def test_keypoint_adjuster_refine_multilevel_moves_keypoints_towards_truth():
+    sc = synthetic.make_ka_scene(n_images=6, n_tracks=50, track_len=4, channels=128, seed=9, kp_sigma=1.0)
+    g = base.Graph()
+    names = ["im%d" % i for i in range(6)]
+    keypoints = {}
+    for i in range(6):
+        m = sc["node_image"] == i
+        keypoints[names[i]] = np.ascontiguousarray(sc["keypoints"][m])
+    for n in range(len(sc["node_image"])):   # node n = (image, feature); same insertion order as the flat arrays
+        g.add_node(names[sc["node_image"][n]], int(sc["node_feature"][n]))
+    for e in range(len(sc["edge_src"])):
+        g.add_edge(g.nodes[sc["edge_src"][e]], g.nodes[sc["edge_dst"][e]], sc["edge_sim"][e])
+    fm = features.FeatureManager([128], np.float16)
+    for i in range(6):
+        m = np.where(sc["node_image"] == i)[0]
+        fm.fset(0).emplace(names[i], features.FeatureMap(np.ascontiguousarray(sc["patches"][m]),
+                                                          sc["node_feature"][m].tolist(), sc["corner"][m],
+                                                          {"scale": sc["scale"][m[0]], "is_sparse": True}))
+    before = {k: v.copy() for k, v in keypoints.items()}
+    out = ka_pkg.KeypointAdjuster.create({"max_kps_per_problem": 20}).refine_multilevel(keypoints, fm, g)
+    s = out["summary"][0]
+    assert s.final_cost < 0.5 * s.initial_cost
+    moved = sum(np.abs(keypoints[k] - before[k]).max() > 1e-3 for k in keypoints)
+    assert moved == 6
+    # cross-check with the flat-IR path that tests/test_gpu_ka.py pins against the oracle
+    from ka_util import make_ka_problem
+    from pixsfm._pixsfm import _engine
+    prob, _, lab = make_ka_problem(n_images=6, n_tracks=50, track_len=4, channels=128, seed=9, kp_sigma=1.0,
+                                   max_per_problem=20, bound=4.0)
+    _engine.ka_run(prob, _capi.default_interp(), _capi.default_ka_options())
+    flat = np.zeros_like(prob.keypoints)
+    for n in range(len(sc["node_image"])):
+        flat[n] = keypoints[names[sc["node_image"][n]]][sc["node_feature"][n]]
+    assert np.abs(flat - prob.keypoints).max() < 1e-9

@@ -1,0 +1,129 @@
+"""CPU tests of the reference-facing Python mirror: the problem construction / parameterisation semantics of
+BundleOptimizer<D> (the cases of the reference's bundle_optimizer_test.cc:163-353, which pins them with the
+geometric residual) resolved into the constancy masks of the problem IR; configuration plumbing and error
+behaviour.  No GPU needed: nothing is solved here."""
+import numpy as np
+import pytest
+
+from pixsfm import base, bundle_adjustment as ba_pkg, keypoint_adjustment as ka_pkg
+from pixsfm._pixsfm import _bundle_adjustment as ba
+from pixsfm._pixsfm._features import FeatureView
+from recon_util import make_reconstruction
+
+
+def _build(rec, fm, setup, **opt):
+    options = ba.BundleOptimizerOptions(opt)
+    fview = FeatureView(fm.fset(0), rec)
+    return ba.build_problem(rec, fview, setup, options, references=None)
+
+
+def test_default_setup_two_view_gauge():
+    rec, fm, prob0, _ = make_reconstruction(n_cams=2, n_points=30, track_len=2, channels=16)
+    setup = ba_pkg.default_problem_setup(rec)            # TestTwoView: pose(0) constant, tvec(1).x constant
+    prob, ir = _build(rec, fm, setup)
+    assert ir.image_ids == [1, 2] and len(ir.obs) == 60
+    assert prob.pose_const.tolist() == [1, 0] and prob.tvec_const_mask.tolist() == [0, 1]
+    assert prob.point_const.sum() == 0
+    assert prob.cam_const_mask.tolist() == [0x6, 0x6]   # SIMPLE_RADIAL: principal point (cx,cy) constant by default
+    assert np.all(np.diff(prob.obs_pt) >= 0)
+    # observations of one point keep the image enumeration order (ascending image id)
+    assert prob.obs_img[:2].tolist() == [0, 1]
+
+
+def test_two_view_constant_camera_and_refine_flags():
+    rec, fm, _, _ = make_reconstruction(n_cams=2, n_points=20, track_len=2, channels=16)
+    setup = ba_pkg.default_problem_setup(rec)
+    setup.set_constant_camera(1)                         # TestTwoViewConstantCamera
+    prob, _ = _build(rec, fm, setup)
+    assert prob.cam_const_mask.tolist() == [0xFFFFFFFF, 0x6]
+    prob, _ = _build(rec, fm, setup, refine_focal_length=False, refine_extra_params=False)
+    assert prob.cam_const_mask.tolist() == [0xFFFFFFFF, 0xFFFFFFFF]
+    prob, _ = _build(rec, fm, ba_pkg.default_problem_setup(rec), refine_principal_point=True, refine_extra_params=False)
+    assert prob.cam_const_mask.tolist() == [0x8, 0x8]
+    prob, _ = _build(rec, fm, ba_pkg.default_problem_setup(rec), refine_extrinsics=False)
+    assert prob.pose_const.tolist() == [1, 1]
+
+
+def test_partially_contained_tracks_become_constant_points():
+    rec, fm, _, _ = make_reconstruction(n_cams=3, n_points=25, track_len=3, channels=16)
+    setup = ba.BundleAdjustmentSetup()                   # TestPartiallyContainedTracks: only images 1 and 2 in the problem
+    setup.add_images({1, 2})
+    setup.set_constant_pose(1)
+    setup.set_constant_tvec(2, [0])
+    prob, ir = _build(rec, fm, setup)
+    assert ir.image_ids == [1, 2] and len(ir.obs) == 50
+    assert prob.point_const.all()                        # every track has a third element outside the problem
+    setup.add_variable_point(5)                          # TestPartiallyContainedTracksForceToOptimizePoint
+    prob, ir = _build(rec, fm, setup)
+    assert ir.image_ids == [1, 2, 3] and len(ir.obs) == 51
+    k = ir.point_ids.index(5)
+    assert prob.point_const[k] == 0 and prob.point_const.sum() == 24
+    assert prob.pose_const.tolist() == [1, 0, 1]         # image 3 is not in the setup: pose constant
+    assert prob.cam_const_mask[ir.camera_ids.index(rec.images[3].camera_id)] == 0xFFFFFFFF
+    setup2 = ba.BundleAdjustmentSetup(); setup2.add_images({1, 2, 3}); setup2.add_constant_point(7)   # TestConstantPoints
+    prob, ir = _build(rec, fm, setup2)
+    assert prob.point_const.sum() == 1 and prob.point_const[ir.point_ids.index(7)] == 1
+
+
+def test_min_track_length_and_empty_problem():
+    rec, fm, _, _ = make_reconstruction(n_cams=3, n_points=10, track_len=2, channels=16)
+    setup = ba.BundleAdjustmentSetup(); setup.add_images({1, 2, 3})
+    prob, ir = _build(rec, fm, setup, min_track_length=3)
+    assert prob.n_obs == 0                               # all tracks have length 2 -> skipped (bundle_optimizer.h:262-265)
+    opt = ba.FeatureReferenceBundleOptimizer({"min_track_length": 3}, setup, base.interpolation_default_conf)
+    assert opt.run(rec, FeatureView(fm.fset(0), rec), {}) is False   # returns False when there are no residuals
+
+
+def test_setup_error_behaviour_matches_reference():
+    s = ba.BundleAdjustmentSetup(); s.add_image(1)
+    with pytest.raises(ValueError):
+        s.set_constant_pose(2)                           # image not in setup
+    s.set_constant_pose(1)
+    with pytest.raises(ValueError):
+        s.set_constant_tvec(1, [0])                      # already constant pose
+    s.add_image(2)
+    with pytest.raises(ValueError):
+        s.set_constant_tvec(2, [0, 0])                   # duplicate indices
+    s.add_variable_point(3)
+    with pytest.raises(ValueError):
+        s.add_constant_point(3)
+    with pytest.raises(ValueError):
+        ba.BundleOptimizerOptions({"no_such_option": 1})    # strict keys (helpers.h:149-232)
+    with pytest.raises(ValueError):
+        base.InterpolationConfig({"nodes": [[0, 0], [1, 1]]}).validate_for_device()
+    with pytest.raises(ValueError):
+        ba_pkg.BundleAdjuster.create({"strategy": "patch_warp"})
+    opt = ba.FeatureReferenceBundleOptimizer({}, s, base.interpolation_default_conf)
+    with pytest.raises(ValueError):
+        opt.run(None, None, {})
+
+
+def test_python_defaults_are_the_reference_defaults():
+    conf = ba_pkg.BundleAdjuster.create({}).conf
+    assert conf.optimizer.solver.use_inner_iterations is True and conf.references.iters == 100
+    assert conf.max_tracks_per_problem == 10 and conf.optimizer.loss.params == [0.25]
+    assert conf.optimizer.refine_principal_point is False and conf.interpolation.l2_normalize is True
+    conf = ka_pkg.KeypointAdjuster.create({"optimizer": {"bound": 2.0}}).conf
+    assert conf.optimizer.bound == 2.0 and conf.optimizer.solver.parameter_tolerance == 1.0e-5
+    assert conf.max_kps_per_problem == 50 and conf.optimizer.weight_by_sim is True
+    rec, fm, _, _ = make_reconstruction(n_cams=2, n_points=25, track_len=2, channels=16)
+    labels = ba_pkg.find_problem_labels(rec, 10)
+    assert labels[0] == -1 and labels[1] == 0 and labels[10] == 1 and labels[25] == 2
+
+
+def test_graph_mirror_and_labels():
+    g = base.Graph()
+    g.register_matches("a", "b", np.array([[0, 0], [1, 1], [2, 2]]), np.array([0.9, 0.8, 0.7]))
+    g.register_matches("b", "c", np.array([[0, 0], [1, 2]]), np.array([0.6, 0.95]))
+    g.register_matches("a", "c", np.array([[0, 1]]), np.array([0.5]))   # would put two features of c into one track
+    assert g.image_name_to_id == {"a": 0, "b": 1, "c": 2} and len(g.nodes) == 9
+    tl = base.compute_track_labels(g)
+    sc = base.compute_score_labels(g, tl)
+    rt = base.compute_root_labels(g, tl, sc)
+    node = {(n.image_id, n.feature_idx): n.node_idx for n in g.nodes}
+    assert tl[node[(0, 0)]] == tl[node[(1, 0)]] == tl[node[(2, 0)]]
+    assert tl[node[(2, 1)]] != tl[node[(0, 0)]]          # refused: track already has a feature in image c
+    assert tl[node[(0, 1)]] == tl[node[(1, 1)]] == tl[node[(2, 2)]]
+    assert sum(rt) == len(set(tl))
+    labels, bins = ka_pkg.find_problem_labels(tl, 50)
+    assert len(bins) == 1 and set(labels) == {0}
