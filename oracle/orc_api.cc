@@ -71,6 +71,8 @@ static BAEvalOptions MakeEO(const pxr_interp_config* ic, const pxr_solver_option
   BAEvalOptions eo;
   eo.interp = ToInterp(ic);
   eo.loss.type = so->loss_type; eo.loss.a = so->loss_scale; eo.loss.weight = 1.0;
+  eo.iterative_schur = so->linear_solver == PXR_SOLVER_ITERATIVE_SCHUR;
+  eo.max_linear_solver_iterations = so->max_linear_solver_iterations;
   return eo;
 }
 

@@ -245,8 +245,78 @@ inline EvalBlockFn SelectEval(int model) {
 struct BAEvalOptions {
   InterpConfig interp;
   Loss loss;
+  bool iterative_schur = false;     // ITERATIVE_SCHUR + SCHUR_JACOBI (bundle_optimizer.h:188-190)
+  int max_linear_solver_iterations = 200;
+  double eta = 0.1;                 // ceres Solver::Options::eta -> CG q_tolerance
   TROptions inner;  // defaults = ceres Solver::Options defaults (CoordinateDescentMinimizer::Solve)
 };
+
+// (ceres) ConjugateGradientsSolver::Solve (internal/ceres/conjugate_gradients_solver.cc @2.1) on the explicit
+// damped Schur complement S (symmetric, full storage) with the SCHUR_JACOBI preconditioner = inverse of the
+// diagonal blocks of S (one block per camera-side parameter block).  x starts at 0.
+inline bool SchurJacobiPCG(int n, const std::vector<double>& S, const std::vector<double>& b,
+                           const std::vector<std::pair<int, int>>& blocks, int max_iter, double q_tolerance,
+                           std::vector<double>* xout, int* iters_out) {
+  std::vector<double> Minv((size_t)n * 12, 0.0);  // row-wise storage of the block inverses (block dim <= 12)
+  for (auto& bk : blocks) {
+    const int o = bk.first, d = bk.second;
+    // invert the SPD block by Gauss-Jordan on [B | I]
+    std::vector<double> A((size_t)d * 2 * d, 0.0);
+    for (int i = 0; i < d; ++i) { for (int j = 0; j < d; ++j) A[(size_t)i * 2 * d + j] = S[(size_t)(o + i) * n + o + j]; A[(size_t)i * 2 * d + d + i] = 1.0; }
+    for (int k = 0; k < d; ++k) {
+      const double pv = A[(size_t)k * 2 * d + k];
+      if (!(pv > 0.0)) return false;
+      for (int j = 0; j < 2 * d; ++j) A[(size_t)k * 2 * d + j] /= pv;
+      for (int i = 0; i < d; ++i) {
+        if (i == k) continue;
+        const double f = A[(size_t)i * 2 * d + k];
+        for (int j = 0; j < 2 * d; ++j) A[(size_t)i * 2 * d + j] -= f * A[(size_t)k * 2 * d + j];
+      }
+    }
+    for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) Minv[(size_t)(o + i) * 12 + j] = A[(size_t)i * 2 * d + d + j];
+  }
+  std::vector<int> blk_of(n, 0), blk_off(n, 0), blk_dim(n, 0);
+  for (auto& bk : blocks) for (int i = 0; i < bk.second; ++i) { blk_off[bk.first + i] = bk.first; blk_dim[bk.first + i] = bk.second; }
+  auto apply_M = [&](const std::vector<double>& r, std::vector<double>& z) {
+    for (int i = 0; i < n; ++i) { double s = 0; for (int j = 0; j < blk_dim[i]; ++j) s += Minv[(size_t)i * 12 + j] * r[blk_off[i] + j]; z[i] = s; }
+  };
+  auto mul = [&](const std::vector<double>& v, std::vector<double>& out) {
+#pragma omp parallel for schedule(static) if (n > 512)
+    for (int i = 0; i < n; ++i) { double s = 0; const double* row = &S[(size_t)i * n]; for (int j = 0; j < n; ++j) s += row[j] * v[j]; out[i] = s; }
+  };
+  auto dot = [&](const std::vector<double>& a, const std::vector<double>& c) { double s = 0; for (int i = 0; i < n; ++i) s += a[i] * c[i]; return s; };
+  std::vector<double>& x = *xout;
+  x.assign(n, 0.0);
+  *iters_out = 0;
+  const double norm_b = std::sqrt(dot(b, b));
+  if (norm_b == 0.0) return true;
+  std::vector<double> r(b), z(n), p(n), q(n), tmp(n);
+  double rho = 1.0, Q0 = 0.0;  // -0.5 * x.(b + r) with x = 0
+  for (int it = 1;; ++it) {
+    apply_M(r, z);
+    const double last_rho = rho;
+    rho = dot(r, z);
+    if (rho == 0.0 || !std::isfinite(rho)) return false;
+    if (it == 1) p = z;
+    else { const double beta = rho / last_rho; if (beta == 0.0 || !std::isfinite(beta)) return false; for (int i = 0; i < n; ++i) p[i] = z[i] + beta * p[i]; }
+    mul(p, q);
+    const double pq = dot(p, q);
+    if (pq <= 0.0 || !std::isfinite(pq)) { *iters_out = it; break; }
+    const double alpha = rho / pq;
+    if (!std::isfinite(alpha)) return false;
+    for (int i = 0; i < n; ++i) x[i] += alpha * p[i];
+    if (it % 10 == 0) { mul(x, tmp); for (int i = 0; i < n; ++i) r[i] = b[i] - tmp[i]; }   // residual_reset_period
+    else for (int i = 0; i < n; ++i) r[i] -= alpha * q[i];
+    double xbr = 0; for (int i = 0; i < n; ++i) xbr += x[i] * (b[i] + r[i]);
+    const double Q1 = -0.5 * xbr;
+    const double zeta = it * (Q1 - Q0) / Q1;
+    *iters_out = it;
+    if (zeta < q_tolerance) break;
+    Q0 = Q1;
+    if (it >= max_iter) break;
+  }
+  return true;
+}
 
 class BAEvaluator : public TREvaluator {
  public:
@@ -494,7 +564,15 @@ class BAEvaluator : public TREvaluator {
     }
     if (!ok) return false;
     S_last = S; rhs_last = rhs;
-    if (nc > 0 && !CholeskySolveInPlace(nc, S, rhs)) return false;
+    int lin_iters = 1;
+    if (eo.iterative_schur && nc > 0) {
+      std::vector<std::pair<int, int>> blocks;
+      for (int i = 0; i < d.n_images; ++i) if (L.pose_off[i] >= 0) blocks.push_back({L.pose_off[i], L.pose_dim[i]});
+      for (int c = 0; c < d.n_cameras; ++c) if (L.intr_off[c] >= 0) blocks.push_back({L.intr_off[c], L.intr_dim[c]});
+      std::vector<double> xs;
+      if (!SchurJacobiPCG(nc, S, rhs, blocks, eo.max_linear_solver_iterations, eo.eta, &xs, &lin_iters)) return false;
+      rhs = xs;
+    } else if (nc > 0 && !CholeskySolveInPlace(nc, S, rhs)) return false;
     for (int i = 0; i < nc; ++i) delta[i] = rhs[i];
     for (int64_t p = 0; p < d.n_points; ++p) {
       if (L.point_off[p] < 0) continue;
@@ -508,7 +586,7 @@ class BAEvaluator : public TREvaluator {
       for (int a = 0; a < 3; ++a)
         delta[L.point_off[p] + a] = iv[a * 3] * v[0] + iv[a * 3 + 1] * v[1] + iv[a * 3 + 2] * v[2];
     }
-    *iters = 1;
+    *iters = lin_iters;
     return true;
   }
 

@@ -11,6 +11,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr",
          "-Xptxas", "-v"]
+if os.environ.get("PXR_FM_WARPS"):
+    FLAGS.append("-DPXR_FM_WARPS=" + os.environ["PXR_FM_WARPS"])
 
 
 def _newer(src, obj):

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <limits>
 
@@ -193,6 +194,9 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   PXR_TRY(Hpp.alloc((size_t)n_points * 9)); PXR_TRY(gp.alloc((size_t)n_points * 3));
   h_obs_img.assign(d->obs_img, d->obs_img + n_obs);
   use_monolithic_inner = std::getenv("PXR_INNER_MONOLITHIC") != nullptr;
+  // linear solver as BundleOptimizer::SolveProblem picks it (bundle_optimizer.h:181-191): exact factorisation up to
+  // 1000 images, ITERATIVE_SCHUR + SCHUR_JACOBI above (or when asked for)
+  use_pcg = opt.linear_solver == PXR_SOLVER_ITERATIVE_SCHUR || (opt.linear_solver == PXR_SOLVER_AUTO && n_images > 1000);
   if (for_solve) PXR_TRY(build_schur_pairs());
   PXR_TRY(W.alloc((size_t)n_obs * dcmax * 3)); PXR_TRY(Wcols.alloc((size_t)n_obs * dcmax)); PXR_TRY(Wdc.alloc(n_obs));
   PXR_TRY(S.alloc((size_t)(nc + 1) * nc)); PXR_TRY(rhs.alloc(nc));
@@ -381,9 +385,12 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   delete st; st = new StageScope(this, 5);
   // rhs rides along as row nc of S: the factorisation performs the forward substitution
   if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
-  // The factorisation + back-substitution is a fixed sequence of ~3*nc/32 dependent launches: it is
-  // captured once into a CUDA graph and replayed, which removes the per-launch gaps.
-  if (nc > 0) {
+  last_linear_iterations = 1;
+  if (nc > 0 && use_pcg) {
+    PXR_TRY(pcg_solve());
+  } else if (nc > 0) {
+    // The factorisation + back-substitution is a fixed sequence of ~3*nc/32 dependent launches: it is
+    // captured once into a CUDA graph and replayed, which removes the per-launch gaps.
     if (!chol_graph_exec) {
       cudaGraph_t graph = nullptr;
       PXR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -540,6 +547,56 @@ int BA::step_norm_between_sets(double* out) {
   return PXR_OK;
 }
 
+// S delta_c = rhs by Schur-Jacobi preconditioned CG (pxr_pcg.cuh); result in delta[0..nc)
+int BA::pcg_solve() {
+  cudaStream_t s = ctx->stream;
+  if (!cg_state.p) {
+    std::vector<int32_t> off, dim;
+    for (int i = 0; i < n_images; ++i) if (h_pose_off[i] >= 0) { off.push_back(h_pose_off[i]); dim.push_back(0); }
+    for (int c = 0; c < n_cameras; ++c) if (h_intr_off[c] >= 0) { off.push_back(h_intr_off[c]); dim.push_back(0); }
+    std::vector<int32_t> order(off.size());
+    for (size_t k = 0; k < off.size(); ++k) order[k] = (int32_t)k;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return off[a] < off[b]; });
+    std::vector<int32_t> so(off.size()), sd(off.size());
+    for (size_t k = 0; k < off.size(); ++k) so[k] = off[order[k]];
+    for (size_t k = 0; k < off.size(); ++k) sd[k] = (k + 1 < off.size() ? so[k + 1] : nc) - so[k];
+    cg_nblk = (int)so.size();
+    PXR_TRY(cg_blk_off.upload(so.data(), so.size(), s)); PXR_TRY(cg_blk_dim.upload(sd.data(), sd.size(), s));
+    PXR_TRY(cg_Minv.alloc((size_t)nc * 12)); PXR_TRY(cg_row_off.alloc(nc)); PXR_TRY(cg_row_dim.alloc(nc));
+    PXR_TRY(cg_z.alloc(nc)); PXR_TRY(cg_p.alloc(nc)); PXR_TRY(cg_q.alloc(nc)); PXR_TRY(cg_r.alloc(nc)); PXR_TRY(cg_x.alloc(nc)); PXR_TRY(cg_tmp.alloc(nc));
+    PXR_TRY(cg_state.alloc(1));
+    PXR_CUDA(cudaStreamSynchronize(s));
+  }
+  const int n = nc;
+  const unsigned gv = (unsigned)cdiv((int64_t)n * 32, 256);
+  PXR_LAUNCH(ctx, cg_mirror_kernel, (unsigned)cdiv((int64_t)n * n, 256), 256, 0, S.p, n);
+  PXR_LAUNCH(ctx, cg_block_inverse_kernel, (unsigned)cdiv(cg_nblk, 64), 64, 0, S.p, n, cg_blk_off.p, cg_blk_dim.p, cg_nblk, cg_Minv.p,
+             cg_row_off.p, cg_row_dim.p, flags.p + 1);
+  PXR_LAUNCH(ctx, cg_init_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p, opt.max_linear_solver_iterations, 0.1);
+  CGState hs;
+  for (int it = 0; it < opt.max_linear_solver_iterations; ++it) {
+    PXR_LAUNCH(ctx, cg_precond_kernel, 1, 1024, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, cg_p.p, n, cg_state.p);
+    PXR_LAUNCH(ctx, cg_gemv_kernel, gv, 256, 0, S.p, cg_p.p, cg_q.p, n, cg_state.p);
+    PXR_LAUNCH(ctx, cg_update_kernel, 1, 1024, 0, rhs.p, cg_p.p, cg_q.p, cg_x.p, cg_r.p, n, cg_state.p);
+    if ((it + 1) % 10 == 0) {   // residual_reset_period
+      PXR_LAUNCH(ctx, cg_gemv_kernel, gv, 256, 0, S.p, cg_x.p, cg_tmp.p, n, cg_state.p);
+      PXR_LAUNCH(ctx, cg_refresh_kernel, 1, 1024, 0, rhs.p, cg_tmp.p, cg_r.p, n, cg_state.p);
+    }
+    PXR_LAUNCH(ctx, cg_check_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p);
+    if ((it + 1) % 8 == 0 || it + 1 == opt.max_linear_solver_iterations) {
+      PXR_CUDA(cudaMemcpyAsync(&hs, cg_state.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+      PXR_CUDA(cudaStreamSynchronize(s));
+      if (hs.done) break;
+    }
+  }
+  PXR_CUDA(cudaMemcpyAsync(&hs, cg_state.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaMemcpyAsync(delta.p, cg_x.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  last_linear_iterations = hs.it;
+  if (hs.failed) { int one = 1; PXR_CUDA(cudaMemcpyAsync(flags.p + 1, &one, sizeof(int), cudaMemcpyHostToDevice, s)); }
+  return PXR_OK;
+}
+
 int BA::gradient_max_norm(double* out) {
   PXR_CUDA(cudaMemsetAsync(scalars.p + 10, 0, 8, ctx->stream));
   const int64_t n = std::max<int64_t>(nc, n_points);
@@ -609,7 +666,7 @@ int BA::lm_iterate(int max_iteration) {
     bool valid = false;
     double model_cost_change = 0;
     PXR_TRY(compute_step(lm.radius, &valid, &model_cost_change));
-    it.linear_solver_iterations = 1;
+    it.linear_solver_iterations = last_linear_iterations;
     it.step_is_valid = valid;
     if (!valid) {
       if (++lm.num_invalid >= opt.max_num_consecutive_invalid_steps) {

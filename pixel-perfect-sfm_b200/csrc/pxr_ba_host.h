@@ -9,6 +9,7 @@
 #include "pxr_fm_eval.cuh"
 #include "pxr_inner.cuh"
 #include "pxr_internal.h"
+#include "pxr_pcg.cuh"
 
 namespace pxr {
 
@@ -69,6 +70,13 @@ struct BA {
   DevBuf<double> uv, obs_out, juv, Hcc, gc, Hpp, gp, W, S, rhs, diag, jscale, D2, delta, partials, scalars;
   DevBuf<int> flags;
   DevBuf<double> rdiag;
+  // ITERATIVE_SCHUR (PCG) workspace
+  bool use_pcg = false;
+  DevBuf<double> cg_Minv, cg_z, cg_p, cg_q, cg_r, cg_x, cg_tmp;
+  DevBuf<int32_t> cg_blk_off, cg_blk_dim, cg_row_off, cg_row_dim;
+  DevBuf<CGState> cg_state;
+  int cg_nblk = 0, last_linear_iterations = 1;
+  int pcg_solve();
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
   ~BA() { if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }

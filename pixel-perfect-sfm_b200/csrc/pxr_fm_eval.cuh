@@ -90,18 +90,20 @@ struct FmEvalArgs {
   int l2_normalize;
 };
 
+#ifndef PXR_FM_WARPS
+#define PXR_FM_WARPS 16
+#endif
 constexpr int kFmStages = 2;   // TMA ring slots per warp
-struct FmAux {                 // per-item window geometry, one entry per lane of a batch
+struct FmAux {                 // per-item window geometry, one entry per lane of a batch (40 B)
   double xc, xr;
   int64_t item;
   const uint8_t* src;
-  const double* ref;
   int col, row;
 };
 // warps per CTA so that the ring fits in ~128 KiB of shared memory
 template <typename T, int C> struct FmCfg {
   static constexpr int kSlot = 16 * C * (int)sizeof(T);
-  static constexpr int kWarps = kSlot <= 4096 ? 16 : (kSlot <= 8192 ? 8 : (kSlot <= 16384 ? 4 : 2));
+  static constexpr int kWarps = kSlot <= 4096 ? PXR_FM_WARPS : (kSlot <= 8192 ? 8 : (kSlot <= 16384 ? 4 : 2));
   static constexpr int kSmem = kWarps * kFmStages * kSlot + kWarps * kFmStages * 8 + kWarps * 32 * (int)sizeof(FmAux);
 };
 
@@ -346,6 +348,7 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
     if (a.item_index && lane < nvalid) o = a.item_index[o];
     // ---- phase 1: per-lane window geometry, published to the warp through shared memory
     __syncwarp();
+    int64_t ref_idx = 0;
     {
       double u = 0.0, v = 0.0;
       int64_t pidx = 0, ridx = 0;
@@ -362,8 +365,8 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       x.row = (int)fmin(fmax(fv, -4.0), (double)a.ph + 4.0);
       x.xc = u - fu; x.xr = v - fv;
       x.src = a.patches + pidx * patch_bytes;
-      x.ref = has_ref ? a.refs + ridx * C : nullptr;
       aux[lane] = x;
+      ref_idx = ridx;
     }
     __syncwarp();
 
@@ -394,8 +397,9 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       const int slot = j % kFmStages;
       const double jxc = aux[j].xc, jxr = aux[j].xr;
       double refv[CPL];
-      if (has_ref && active) {
-        const double* rp = aux[j].ref + lane * CPL;
+      if (has_ref) {
+        const int64_t jref = __shfl_sync(0xffffffffu, (long long)ref_idx, j);
+        const double* rp = a.refs + jref * C + (active ? lane * CPL : 0);
 #pragma unroll
         for (int k = 0; k < CPL; ++k) refv[k] = __ldg(rp + k);
       }
