@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--ps", type=int, default=16)
     ap.add_argument("--no-inner", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-points", type=int, default=1500)
+    ap.add_argument("--cpu-sample-points", type=int, default=20000)
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 

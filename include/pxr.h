@@ -288,6 +288,36 @@ int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_con
                      int loss_type, double loss_scale, int iters,
                      double* refs_out, int64_t* src_obs_out, pxr_summary* summary);
 
+/* ---- cost maps ---------------------------------------
+ * replaces _bundle_adjustment.CostMapExtractor.run (bundle_adjustment/bindings.cc:20-26,179-184;
+ * costmap_extractor.h:93-228 Run/RunSubset, :230-358 FillPointCostmap) followed, on the caller's side,
+ * by CostMapBundleOptimizer (costmap_bundle_optimizer.h:76-132) = pxr_ba_* on the returned
+ * 3-channel patches with refs == NULL and l2_normalize == 0 (bundle_adjustment/main.py:262-281).
+ * Config mirrors CostMapConfig (costmap_extractor.h:18-40) + the ReferenceConfig used by the
+ * extractor's embedded ReferenceExtractor (reference_extractor.h:30-50). */
+typedef struct pxr_costmap_config {
+  int32_t loss_type;                /* pxr_loss_type, default TRIVIAL */
+  double loss_scale;
+  int32_t as_gradientfield;         /* 1: (cost, dcost/dr, dcost/dc), 0: cost only */
+  int32_t compute_cross_derivative; /* must be 0 (4-channel variant not built) */
+  int32_t apply_sqrt;
+  double upsampling_factor;         /* must be 1.0 */
+  int32_t compute_refs;             /* 1: run the reference extraction first, on the same upload */
+  int32_t ref_loss_type;            /* CAUCHY 0.25, 100 IRLS iterations (bundle_adjustment/main.py:46-57) */
+  double ref_loss_scale;
+  int32_t ref_iters;
+} pxr_costmap_config;
+int pxr_default_costmap_config(pxr_costmap_config* cfg);
+/*  desc        the feature problem (C-channel patches, geometry); desc->refs used when !compute_refs
+ *  refs_io     [n_points][C] fp64: written when compute_refs, else read if desc->refs is NULL; may be NULL
+ *  src_obs_out [n_points] or NULL (see pxr_refs_compute)
+ *  out_host    [n_patches][ph][pw][OC] in desc->patch_dtype (the reference instantiates Run<dtype,dtype>), or NULL
+ *  out_device  if not NULL receives a device pointer to the same array (release with pxr_device_free):
+ *              feed it to pxr_ba_create with patches_on_device = 1 to skip the host round trip */
+int pxr_costmaps_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
+                         const pxr_costmap_config* cfg, double* refs_io, int64_t* src_obs_out,
+                         void* out_host, void** out_device, pxr_summary* summary);
+
 /* ---- featuremetric KA ---------------------------------------------------
  * replaces _keypoint_adjustment.FeatureMetricKeypointOptimizer.run
  * (keypoint_adjustment/bindings.cc:17-34; featuremetric_keypoint_optimizer.h:50-202;

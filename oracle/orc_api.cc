@@ -7,6 +7,7 @@
 #include "orc_ba.h"
 #include "orc_refs_graph.h"
 #include "orc_ka.h"
+#include "orc_costmap.h"
 
 using namespace orc;
 
@@ -261,6 +262,13 @@ void orc_robust_mean_irls(const double* desc, int n, int C, int loss_type, doubl
   std::vector<double> dv(desc, desc + (size_t)n * C), m;
   RobustMeanIRLS(dv, n, C, l, iters, l2_normalize != 0, &m);
   std::memcpy(mean, m.data(), sizeof(double) * C);
+}
+
+// f1 — cost maps (costmap_extractor.h:230-358); `out` in the patches' dtype, [n_patches][ph][pw][3 or 1]
+int orc_costmaps_compute(const pxr_ba_desc* d, int loss_type, double loss_scale, int as_gradientfield,
+                         int apply_sqrt, void* out) {
+  Loss l; l.type = loss_type; l.a = loss_scale; l.weight = 1.0;
+  return ComputeCostmaps(*d, l, as_gradientfield != 0, apply_sqrt != 0, out);
 }
 
 // a13/a14

@@ -43,7 +43,20 @@ static int launch_fm_tc(pxr_ctx* ctx, const FmEvalArgs& a, int mode, bool fs, in
   return fs ? launch_fm<T, C, 0, true>(ctx, a, np) : launch_fm<T, C, 0, false>(ctx, a, np);
 }
 
+template <typename T, int C>
+static int launch_fm_small(pxr_ctx* ctx, const FmEvalArgs& a, int mode, int* np) {
+  const int64_t n = a.end - a.begin;
+  *np = 0;
+  if (n <= 0) return PXR_OK;
+  if (mode == 1) PXR_LAUNCH(ctx, (fm_eval_small_kernel<T, C, 1>), (unsigned)cdiv(n, 128), 128, 0, a);
+  else PXR_LAUNCH(ctx, (fm_eval_small_kernel<T, C, 0>), (unsigned)cdiv(n, 128), 128, 0, a);
+  PXR_CUDA(cudaGetLastError());
+  return PXR_OK;
+}
+
 int fm_supported(int dtype, int C) {
+  // C < 8: the reference's all-double bicubic branch (interpolation.h:224); 3/4 = cost maps, 1 = scalar maps
+  if ((C == 1 || C == 3 || C == 4) && (dtype == PXR_F16 || dtype == PXR_F32 || dtype == PXR_F64)) return 1;
   if (dtype == PXR_F16) return C == 8 || C == 16 || C == 32 || C == 64 || C == 128 || C == 256;
   if (dtype == PXR_F32) return C == 16 || C == 64 || C == 128;
   if (dtype == PXR_F64) return C == 16 || C == 128;
@@ -53,6 +66,14 @@ int fm_supported(int dtype, int C) {
 int fm_max_partials(pxr_ctx* ctx) { return ctx->sm_count * 16 * 64; }
 
 int launch_fm_eval(pxr_ctx* ctx, int dtype, int C, int mode, bool float_simd, const FmEvalArgs& a, int* np) {
+#define PXR_SMALL(T) \
+  { if (C == 3) return launch_fm_small<T, 3>(ctx, a, mode, np); if (C == 4) return launch_fm_small<T, 4>(ctx, a, mode, np); \
+    if (C == 1) return launch_fm_small<T, 1>(ctx, a, mode, np); }
+  if (C < 8) {
+    if (dtype == PXR_F16) PXR_SMALL(__half) else if (dtype == PXR_F32) PXR_SMALL(float) else if (dtype == PXR_F64) PXR_SMALL(double)
+    return fail(PXR_ERR_UNSUPPORTED, "Unsupported dimensions (CHANNELS=%d, dtype=%d, N_NODES=1).", C, dtype);
+  }
+#undef PXR_SMALL
 #define PXR_CASE(T, CC) \
   if (C == CC) return launch_fm_tc<T, CC>(ctx, a, mode, float_simd, np);
   if (dtype == PXR_F16) {
@@ -392,10 +413,33 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     // The factorisation + back-substitution is a fixed sequence of ~3*nc/32 dependent launches: it is
     // captured once into a CUDA graph and replayed, which removes the per-launch gaps.
     if (!chol_graph_exec) {
+      chol_multikernel = getenv("PXR_CHOL_MULTIKERNEL") != nullptr;
+      if (!chol_multikernel) {
+        // every CTA of the persistent kernel must be resident at once: grid = occupancy x SMs
+        int per_sm = 0, sms = 0, dev = 0;
+        PXR_CUDA(cudaGetDevice(&dev));
+        PXR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PXR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pxr_chol::chol_persistent_kernel, pxr_chol::kThreads, 0));
+        if (per_sm < 1) return pxr::fail(PXR_ERR_CUDA, "persistent Cholesky kernel does not fit on an SM");
+        const int nbt = (int)cdiv(nc, kNB);
+        const int64_t tiles = (int64_t)(nbt + 1) * nbt / 2 + nbt;
+        chol_grid = (int)std::min<int64_t>((int64_t)per_sm * sms, std::max<int64_t>(2, tiles + 1));
+        PXR_TRY(chol_sync.alloc(pxr_chol::sync_ints(nbt)));
+        if (getenv("PXR_CHOL_TRACE")) { PXR_TRY(chol_trace.alloc((size_t)(nbt + 2) * 8 + nbt)); PXR_TRY(chol_trace.zero(s)); }
+      }
       cudaGraph_t graph = nullptr;
       PXR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       const int nb = (int)cdiv(nc, kNB);
       int64_t captured = 0;
+      if (!chol_multikernel) {
+        // one persistent kernel: tile DAG with flags (pxr_chol.cuh); the memset of the flags is part of the graph
+        PXR_CUDA(cudaMemsetAsync(chol_sync.p, 0, chol_sync.n * sizeof(int), s));
+        pxr_chol::Args ca;
+        ca.A = S.p; ca.x = delta.p; ca.n = nc; ca.nb = nb;
+        ca.diag_ready = chol_sync.p; ca.ready = ca.diag_ready + nb; ca.upd = ca.ready + (size_t)(nb + 1) * nb;
+        ca.xready = ca.upd + (size_t)(nb + 1) * nb; ca.abort = ca.xready + nb; ca.fail_flag = flags.p + 1; ca.trace = chol_trace.p;
+        pxr_chol::chol_persistent_kernel<<<chol_grid, pxr_chol::kThreads, 0, s>>>(ca); ++captured;
+      } else {
       for (int k = 0; k < nb; ++k) {
         const int k0 = k * kNB, kb = std::min(kNB, nc - k0);
         const int rows_below = nc + 1 - (k0 + kb);               // includes the rhs row
@@ -406,6 +450,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
         if (rem > 0 && kb == kNB) { chol_update_kernel<<<rem * (rem + 1) / 2, kNB * kNB, 0, s>>>(S.p, nc, nc + 1, k); ++captured; }
       }
       chol_backsolve_kernel<<<1, 1024, 0, s>>>(S.p, S.p + (size_t)nc * nc, delta.p, nc); ++captured;
+      }
       PXR_CUDA(cudaStreamEndCapture(s, &graph));
       PXR_CUDA(cudaGraphInstantiate(&chol_graph_exec, graph, 0));
       cudaGraphDestroy(graph);
@@ -413,6 +458,18 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     }
     PXR_CUDA(cudaGraphLaunch(chol_graph_exec, s));
     ctx->launches += chol_graph_kernels;
+    if (chol_trace.p) {   // debugging aid: dump the panel CTA's time line of this factorisation
+      std::vector<long long> h(chol_trace.n);
+      PXR_CUDA(cudaMemcpyAsync(h.data(), chol_trace.p, h.size() * 8, cudaMemcpyDeviceToHost, s));
+      PXR_CUDA(cudaStreamSynchronize(s));
+      if (FILE* f = fopen(getenv("PXR_CHOL_TRACE"), "w")) {
+        const int nbt = (int)cdiv(nc, kNB);
+        for (int k = 0; k < nbt; ++k) { for (int q = 0; q < 6; ++q) fprintf(f, "%lld ", h[(size_t)k * 8 + q] - h[0]); fprintf(f, "\n"); }
+        fprintf(f, "backsolve_start %lld\n", h[(size_t)nbt * 8] - h[0]);
+        for (int c = nbt - 1; c >= 0; --c) fprintf(f, "x %d %lld\n", c, h[(size_t)nbt * 8 + 8 + c] - h[0]);
+        fclose(f);
+      }
+    }
   }
   delete st; st = new StageScope(this, 7);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]

@@ -6,7 +6,9 @@
 #include <vector>
 
 #include "pxr_ba_kernels.cuh"
+#include "pxr_chol.cuh"
 #include "pxr_fm_eval.cuh"
+#include "pxr_fm_small.cuh"
 #include "pxr_inner.cuh"
 #include "pxr_internal.h"
 #include "pxr_pcg.cuh"
@@ -79,6 +81,9 @@ struct BA {
   int pcg_solve();
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
+  bool chol_multikernel = false; int chol_grid = 0;
+  DevBuf<long long> chol_trace;     // PXR_CHOL_TRACE=<file>: panel-CTA time stamps
+  DevBuf<int> chol_sync;            // flags of the persistent tile-DAG Cholesky (pxr_chol.cuh)
   ~BA() { if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
   // static co-visibility structure for the Schur complement (see ba_schur_pairs_kernel)
   DevBuf<int32_t> sp_px, sp_py;

@@ -1,0 +1,353 @@
+// Dense Cholesky of the reduced camera system as ONE persistent kernel (tile DAG with flags).
+//
+// Replaces, for the exact DENSE_SCHUR / SPARSE_SCHUR step of ceres::Solve (reference call site
+// bundle_adjustment/src/bundle_optimizer.h:181-191,224), the chain of ~3*n/32 dependent launches
+// (pxr_ba_kernels.cuh: chol_diag/panel/update + single-CTA back-substitution) whose cost was launch
+// and DRAM-round-trip latency, not arithmetic.
+//
+// Storage is the same (n+1) x n row-major array: rows 0..n-1 = lower triangle of S, row n = rhs.
+// Tiles are 32x32; column tiles j in [0,nb), row tiles i in [0,nb] where row tile nb is the rhs row.
+//
+//   CTA 0 ("panel CTA") walks the critical path alone and entirely out of shared memory:
+//        factor L_kk (one warp, registers) -> publish -> solve L_{k+1,k} -> publish ->
+//        A_{k+1,k+1} -= L_{k+1,k} L_{k+1,k}^T -> next k.  Its idle warps prefetch the two tiles
+//        it needs next while warp 0 factors.
+//   CTAs 1.. ("workers") own the remaining tiles round-robin in column-major tile order, and for
+//        every panel k, in that order: solve their tiles of column k (i >= k+2), then apply panel k
+//        to their tiles of columns > k.  Every tile is only ever written by its owner (the panel CTA
+//        takes over the diagonal / sub-diagonal tile after the owner has published `upd`), so there
+//        are no atomics on matrix data.
+//   Dependencies travel through three flag arrays in global memory (release/acquire at gpu scope):
+//        diag_ready[k], ready[i,k] (L_ik final), upd[i,j] (panels applied by the owner; only read for
+//        diagonal and sub-diagonal tiles).  Every CTA executes its tasks in an order compatible with
+//        the DAG ((k, tile) lexicographic), all CTAs are co-resident (grid <= occupancy x SMs), so
+//        the waits cannot deadlock; a cycle-count bail-out sets `abort`+fail instead of hanging.
+//   The same kernel then runs the back-substitution L^T x = y column block by column block, one CTA
+//   per block, chained through xready[c].
+//
+// Matrix data written by another SM is always read with ld.global.cg (L1 is not coherent).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pxr_chol {
+
+constexpr int TB = 32;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct Args {
+  double* A;        // (n+1) x n
+  double* x;        // n, solution
+  int n, nb;
+  int* diag_ready;  // [nb]
+  int* ready;       // [(nb+1)*nb]
+  int* upd;         // [(nb+1)*nb]
+  int* xready;      // [nb]
+  int* abort;       // [1]
+  int* fail_flag;   // set when a pivot is not positive / on bail-out
+  long long* trace; // optional [nb+2][8] globaltimer stamps of the panel CTA (PXR_CHOL_TRACE), else null
+};
+
+static inline size_t sync_ints(int nb) { return (size_t)2 * (nb + 1) * nb + 2 * (size_t)nb + 1; }
+
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PXR_CHOL_STAMP(slot) do { if (a.trace && tid == 0) a.trace[(int64_t)k * 8 + (slot)] = gtime(); } while (0)
+
+struct Geo {
+  int n, nb;
+  __device__ __forceinline__ int row0(int i) const { return i < nb ? i * TB : n; }
+  __device__ __forceinline__ int rows(int i) const { return i < nb ? min(TB, n - i * TB) : 1; }
+  __device__ __forceinline__ int cols(int j) const { return min(TB, n - j * TB); }
+  // column-major enumeration of the tiles i >= j, i in [j, nb]
+  __device__ __forceinline__ int64_t off(int j) const { return (int64_t)j * (nb + 1) - (int64_t)j * (j - 1) / 2; }
+};
+
+// Spin (thread `who` only) until *p >= target or the abort flag is up; all threads then pass a barrier.
+template <int BAR, int NTHREADS>
+__device__ __forceinline__ void wait_flags(const int* p0, int t0, const int* p1, int t1, int* abort_flag, int* fail_flag,
+                                           bool leader) {
+  if (leader) {
+    long long start = 0;
+    unsigned spins = 0;
+    while (true) {
+      const bool ok0 = ld_acquire(p0) >= t0;
+      const bool ok1 = (p1 == nullptr) || ld_acquire(p1) >= t1;
+      if (ok0 && ok1) break;
+      if ((++spins & 1023u) == 0) {
+        if (ld_acquire(abort_flag)) break;
+        const long long now = clock64();
+        if (start == 0) start = now;
+        else if (now - start > 4000000000LL) { st_release(abort_flag, 1); *fail_flag = 1; break; }
+      }
+    }
+  }
+  if (BAR == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(BAR), "r"(NTHREADS) : "memory");
+}
+
+// Tile (i, j) -> shared [32][33], zero-filled outside the valid rows/cols; `lower_only` zeroes c > r.
+template <int NT>
+__device__ __forceinline__ void load_tile(double (*dst)[TB + 1], const double* A, const Geo& g, int i, int j, int tid,
+                                          bool lower_only = false) {
+  const int r0 = g.row0(i), nr = g.rows(i), c0 = j * TB, ncl = g.cols(j);
+  for (int e = tid; e < TB * TB; e += NT) {
+    const int r = e >> 5, c = e & 31;
+    double v = 0.0;
+    if (r < nr && c < ncl && !(lower_only && c > r)) v = __ldcg(A + (int64_t)(r0 + r) * g.n + c0 + c);
+    dst[r][c] = v;
+  }
+}
+template <int NT>
+__device__ __forceinline__ void store_tile(double (*src)[TB + 1], double* A, const Geo& g, int i, int j, int tid,
+                                           bool lower_only = false) {
+  const int r0 = g.row0(i), nr = g.rows(i), c0 = j * TB, ncl = g.cols(j);
+  for (int e = tid; e < TB * TB; e += NT) {
+    const int r = e >> 5, c = e & 31;
+    if (r < nr && c < ncl && !(lower_only && c > r)) __stcg(A + (int64_t)(r0 + r) * g.n + c0 + c, src[r][c]);
+  }
+}
+
+// One warp factors the 32x32 block in `a` (lower triangle valid, identity-padded) in registers.
+// Leaves L (zeros above the diagonal) in `a`, reciprocal pivots in rd. Returns false on a bad pivot.
+static __device__ __noinline__ bool factor_diag_warp(double (*a)[TB + 1], double* rd, int kb, int lane) {
+  double r[TB];
+#pragma unroll
+  for (int c = 0; c < TB; ++c) r[c] = (lane < kb && c < kb && c <= lane) ? a[lane][c] : (c == lane ? 1.0 : 0.0);
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < TB; ++j) {
+    const double dj = __shfl_sync(0xffffffffu, r[j], j);
+    if (!(dj > 0.0) || !isfinite(dj)) ok = false;
+    const double rj = rsqrt(dj);
+    if (lane == j) { r[j] = dj * rj; rd[j] = rj; }
+    else if (lane > j) r[j] *= rj;
+    const double lij = r[j];
+    a[lane][j] = (lane >= j) ? lij : 0.0;            // column j is final: r[j] dies here
+#pragma unroll
+    for (int c = j + 1; c < TB; ++c) {
+      const double lcj = __shfl_sync(0xffffffffu, lij, c);
+      if (lane >= c) r[c] -= lij * lcj;
+    }
+  }
+  return ok;
+}
+
+// Rows of `t` (32 rows, lane = column) <- t L^-T, L in `l` with reciprocal pivots rd. Each warp takes
+// TB/NW rows and runs them interleaved for ILP.
+template <int NW>
+__device__ __forceinline__ void solve_rows(double (*t)[TB + 1], double (*l)[TB + 1], const double* rd, int kb, int warp, int lane) {
+  constexpr int R = TB / NW;
+  double v[R];
+#pragma unroll
+  for (int m = 0; m < R; ++m) v[m] = t[warp * R + m][lane];
+  for (int j = 0; j < kb; ++j) {
+    const double rj = rd[j];
+    const double lj = l[lane][j];
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const double xj = __shfl_sync(0xffffffffu, v[m], j) * rj;
+      if (lane == j) v[m] = xj;
+      else if (lane > j) v[m] -= xj * lj;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < R; ++m) t[warp * R + m][lane] = v[m];
+}
+
+// out[r][c] -= sum_q li[r][q] lj[c][q] for a 2x2 micro-tile per thread (256 threads), out in shared.
+__device__ __forceinline__ void syrk_tile_smem(double (*out)[TB + 1], double (*li)[TB + 1], double (*lj)[TB + 1], int tid) {
+  const int ty = tid >> 4, tx = tid & 15;
+  double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll 8
+  for (int q = 0; q < TB; ++q) {
+    const double a0 = li[ty][q], a1 = li[ty + 16][q], b0 = lj[tx][q], b1 = lj[tx + 16][q];
+    s00 += a0 * b0; s01 += a0 * b1; s10 += a1 * b0; s11 += a1 * b1;
+  }
+  out[ty][tx] -= s00; out[ty][tx + 16] -= s01; out[ty + 16][tx] -= s10; out[ty + 16][tx + 16] -= s11;
+}
+
+static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Args a) {
+  __shared__ double sbuf[3][TB][TB + 1];
+  __shared__ double srd[TB];
+  __shared__ double sx[TB];
+  __shared__ double sred[kWarps][TB];
+  __shared__ int s_ok;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Geo g{a.n, a.nb};
+  const int nb = a.nb;
+  const int W = (int)gridDim.x - 1;                 // workers
+  double* A = a.A;
+  auto RD = [&](int i, int j) { return a.ready + (int64_t)i * nb + j; };
+  auto UP = [&](int i, int j) { return a.upd + (int64_t)i * nb + j; };
+
+  if (blockIdx.x == 0) {
+    // ------------------------------------------------------------------ panel CTA
+    int ia = 0, ib = 1, ic = 2;                      // sbuf roles: A_kk / L_{k+1,k} / next diagonal tile
+    load_tile<kThreads>(sbuf[ia], A, g, 0, 0, tid, true);
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+      const int kb = g.cols(k);
+      PXR_CHOL_STAMP(0);
+      if (warp == 0) {
+        const bool ok = factor_diag_warp(sbuf[ia], srd, kb, lane);
+        if (a.trace && lane == 0) a.trace[(int64_t)k * 8 + 1] = gtime();
+        if (!ok && lane == 0) *a.fail_flag = 1;
+      } else {
+        constexpr int NT = kThreads - 32;
+        const int t2 = tid - 32;
+        // tile (k+1, k): owner has applied panels 0..k-1
+        wait_flags<1, NT>(UP(k + 1, k), k, (k + 1 < nb) ? UP(k + 1, k + 1) : nullptr, k, a.abort, a.fail_flag, t2 == 0);
+        load_tile<NT>(sbuf[ib], A, g, k + 1, k, t2);
+        if (k + 1 < nb) load_tile<NT>(sbuf[ic], A, g, k + 1, k + 1, t2, true);
+      }
+      __syncthreads();
+      PXR_CHOL_STAMP(2);                              // factor done AND both prefetches landed
+      store_tile<kThreads>(sbuf[ia], A, g, k, k, tid, true);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release(a.diag_ready + k, 1);
+      PXR_CHOL_STAMP(3);
+      solve_rows<kWarps>(sbuf[ib], sbuf[ia], srd, kb, warp, lane);
+      __syncthreads();
+      PXR_CHOL_STAMP(4);
+      store_tile<kThreads>(sbuf[ib], A, g, k + 1, k, tid);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release(RD(k + 1, k), 1);
+      PXR_CHOL_STAMP(5);
+      if (k + 1 < nb) {
+        syrk_tile_smem(sbuf[ic], sbuf[ib], sbuf[ib], tid);
+        __syncthreads();
+        const int t = ia; ia = ic; ic = t;
+      }
+    }
+  } else if (W > 0) {
+    // ------------------------------------------------------------------ workers
+    const int w = (int)blockIdx.x - 1;
+    const int64_t total = g.off(nb);                 // number of tiles
+    double (*sK)[TB + 1] = sbuf[0];
+    double (*sI)[TB + 1] = sbuf[1];
+    double (*sJ)[TB + 1] = sbuf[2];
+    const int ty = tid >> 4, tx = tid & 15;
+    for (int k = 0; k < nb; ++k) {
+      const int kb = g.cols(k);
+      const int64_t o = g.off(k);
+      int64_t t = o + ((w - o) % W + W) % W;         // smallest owned tile index >= off(k)
+      int j = k;
+      bool have_lkk = false;
+      for (; t < total; t += W) {
+        while (t >= g.off(j + 1)) ++j;
+        const int i = j + (int)(t - g.off(j));
+        if (j == k) {
+          if (i < k + 2) continue;
+          if (!have_lkk) {
+            wait_flags<0, kThreads>(a.diag_ready + k, 1, nullptr, 0, a.abort, a.fail_flag, tid == 0);
+            load_tile<kThreads>(sK, A, g, k, k, tid, true);
+            __syncthreads();
+            if (tid < TB) srd[tid] = 1.0 / (tid < kb ? sK[tid][tid] : 1.0);
+            have_lkk = true;
+          }
+          load_tile<kThreads>(sI, A, g, i, k, tid);
+          __syncthreads();
+          solve_rows<kWarps>(sI, sK, srd, kb, warp, lane);
+          __syncthreads();
+          store_tile<kThreads>(sI, A, g, i, k, tid);
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) st_release(RD(i, k), 1);
+        } else {
+          if (i == j && k == j - 1) continue;        // the panel CTA applies this one itself
+          wait_flags<0, kThreads>(RD(i, k), 1, (i != j) ? RD(j, k) : nullptr, 1, a.abort, a.fail_flag, tid == 0);
+          load_tile<kThreads>(sI, A, g, i, k, tid);
+          if (i != j) load_tile<kThreads>(sJ, A, g, j, k, tid);
+          // the tile itself, read-modify-write straight from global (2x2 per thread)
+          const int r0 = g.row0(i), nr = g.rows(i), c0 = j * TB, ncl = g.cols(j);
+          double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+          const bool v0 = ty < nr, v1 = ty + 16 < nr, u0 = tx < ncl, u1 = tx + 16 < ncl;
+          double* p0 = A + (int64_t)(r0 + ty) * g.n + c0 + tx;
+          double* p1 = p0 + (int64_t)16 * g.n;
+          if (v0 && u0) c00 = __ldcg(p0);
+          if (v0 && u1) c01 = __ldcg(p0 + 16);
+          if (v1 && u0) c10 = __ldcg(p1);
+          if (v1 && u1) c11 = __ldcg(p1 + 16);
+          __syncthreads();
+          double (*lj)[TB + 1] = (i != j) ? sJ : sI;
+#pragma unroll 8
+          for (int q = 0; q < TB; ++q) {
+            const double a0 = sI[ty][q], a1 = sI[ty + 16][q], b0 = lj[tx][q], b1 = lj[tx + 16][q];
+            c00 -= a0 * b0; c01 -= a0 * b1; c10 -= a1 * b0; c11 -= a1 * b1;
+          }
+          if (v0 && u0) __stcg(p0, c00);
+          if (v0 && u1) __stcg(p0 + 16, c01);
+          if (v1 && u0) __stcg(p1, c10);
+          if (v1 && u1) __stcg(p1 + 16, c11);
+          const bool watched = (i == j) || (i == j + 1);
+          if (watched) __threadfence();
+          __syncthreads();                            // sI/sJ free again; stores of a watched tile fenced
+          if (watched && tid == 0) st_release(UP(i, j), k + 1);
+        }
+      }
+    }
+  }
+
+  // -------------------------------------------------------------------- back-substitution L^T x = y
+  // y_c = row n, columns of block c  (tile (nb, c));  x_c = L_cc^-T (y_c - sum_{j>c} L_jc^T x_j)
+  const int G = (int)gridDim.x;
+  if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[(int64_t)nb * 8] = gtime();
+  for (int c = nb - 1 - (int)blockIdx.x; c >= 0; c -= G) {
+    const int kb = g.cols(c), c0 = c * TB;
+    const int wr = tid >> 5;                         // row group: rows wr, wr+8, wr+16, wr+24 of a tile
+    double acc = 0.0;
+    for (int j = nb - 1; j > c; --j) {
+      // L_jc is final once ready[j,c]; prefetch it before waiting for x_j
+      wait_flags<0, kThreads>(RD(j, c), 1, nullptr, 0, a.abort, a.fail_flag, tid == 0);
+      const int r0 = j * TB, nr = g.rows(j);
+      double l[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int r = wr + 8 * m;
+        l[m] = (r < nr && lane < kb) ? __ldcg(A + (int64_t)(r0 + r) * g.n + c0 + lane) : 0.0;
+      }
+      wait_flags<0, kThreads>(a.xready + j, 1, nullptr, 0, a.abort, a.fail_flag, tid == 0);
+      if (tid < TB) sx[tid] = tid < nr ? __ldcg(a.x + r0 + tid) : 0.0;
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < 4; ++m) acc += l[m] * sx[wr + 8 * m];
+      __syncthreads();
+    }
+    sred[wr][lane] = acc;
+    wait_flags<0, kThreads>(a.diag_ready + c, 1, RD(nb, c), 1, a.abort, a.fail_flag, tid == 0);   // also the barrier for sred
+    load_tile<kThreads>(sbuf[0], A, g, c, c, tid, true);
+    __syncthreads();
+    if (warp == 0) {
+      double v = lane < kb ? __ldcg(A + (int64_t)g.n * g.n + c0 + lane) : 0.0;
+#pragma unroll
+      for (int m = 0; m < kWarps; ++m) v -= sred[m][lane];
+      const double rdv = 1.0 / (lane < kb ? sbuf[0][lane][lane] : 1.0);
+      for (int jj = kb - 1; jj >= 0; --jj) {
+        const double xj = __shfl_sync(0xffffffffu, v, jj) * __shfl_sync(0xffffffffu, rdv, jj);
+        if (lane == jj) v = xj;
+        else if (lane < jj) v -= sbuf[0][jj][lane] * xj;
+      }
+      if (lane < kb) __stcg(a.x + c0 + lane, v);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release(a.xready + c, 1);
+      if (a.trace && lane == 0) a.trace[(int64_t)nb * 8 + 8 + c] = gtime();   // x_c published
+    }
+    __syncthreads();
+  }
+  (void)s_ok;
+}
+
+}  // namespace pxr_chol

@@ -107,26 +107,12 @@ static int launch_irls(pxr_ctx* ctx, const double* desc, const int64_t* pt_begin
   return PXR_OK;
 }
 
-}  // namespace pxr
-
-using namespace pxr;
-
-extern "C" int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp, int loss_type,
-                                double loss_scale, int iters, double* refs_out, int64_t* src_obs_out,
-                                pxr_summary* summary) {
-  if (!ctx || !desc || !refs_out) return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
-  // reuse the BA upload path with refs = NULL (descriptor mode)
-  pxr_ba_desc d = *desc;
-  d.refs = nullptr;
-  pxr_solver_options so;
-  pxr_default_ba_options(&so);
-  so.loss_type = loss_type; so.loss_scale = loss_scale;
-  BA b;
-  const int64_t launches0 = ctx->launches;
-  PXR_TRY(b.create(ctx, &d, interp, &so, false));
+// Reference extraction on an uploaded problem: descriptors at the current projections (K0 + K1 in
+// descriptor mode), then one warp per point of IRLS + argmin. refs [n_points][C], src [n_points].
+static int refs_on_device(pxr_ctx* ctx, BA& b, int loss_type, double loss_scale, int iters, DevBuf<double>& refs,
+                          DevBuf<int64_t>& src) {
   cudaStream_t s = ctx->stream;
-  DevBuf<double> dsc, refs;
-  DevBuf<int64_t> src;
+  DevBuf<double> dsc;
   PXR_TRY(dsc.alloc((size_t)b.n_obs * b.C));
   PXR_TRY(refs.alloc((size_t)b.n_points * b.C));
   PXR_TRY(src.alloc(b.n_points));
@@ -152,17 +138,120 @@ extern "C" int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr
       default: return fail(PXR_ERR_UNSUPPORTED, "Unsupported channel count %d in reference extraction", b.C);
     }
   }
-  PXR_CUDA(cudaMemcpyAsync(refs_out, refs.p, (size_t)b.n_points * b.C * 8, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));   // dsc is released on return
+  return PXR_OK;
+}
+
+static int read_src(pxr_ctx* ctx, const BA& b, const DevBuf<int64_t>& src, int64_t* src_obs_out) {
   std::vector<int64_t> hsrc(b.n_points);
-  PXR_CUDA(cudaMemcpyAsync(hsrc.data(), src.p, (size_t)b.n_points * 8, cudaMemcpyDeviceToHost, s));
-  PXR_CUDA(cudaStreamSynchronize(s));
+  PXR_CUDA(cudaMemcpyAsync(hsrc.data(), src.p, (size_t)b.n_points * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int64_t p = 0; p < b.n_points; ++p) {
     if (hsrc[p] == -2) return fail(PXR_ERR_UNSUPPORTED, "track of point %lld longer than 256 observations", (long long)p);
     if (src_obs_out) src_obs_out[p] = hsrc[p];
   }
+  return PXR_OK;
+}
+
+template <typename T>
+static int launch_costmaps(pxr_ctx* ctx, const CostmapArgs& a) {
+  const int64_t warps = a.n_items * a.ph * a.pw;
+  if (warps > 0) PXR_LAUNCH(ctx, (costmap_extract_kernel<T, T>), (unsigned)cdiv(warps * 32, 256), 256, 0, a);
+  PXR_CUDA(cudaGetLastError());
+  return PXR_OK;
+}
+
+}  // namespace pxr
+
+using namespace pxr;
+
+extern "C" int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp, int loss_type,
+                                double loss_scale, int iters, double* refs_out, int64_t* src_obs_out,
+                                pxr_summary* summary) {
+  if (!ctx || !desc || !refs_out) return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
+  // reuse the BA upload path with refs = NULL (descriptor mode)
+  pxr_ba_desc d = *desc;
+  d.refs = nullptr;
+  pxr_solver_options so;
+  pxr_default_ba_options(&so);
+  so.loss_type = loss_type; so.loss_scale = loss_scale;
+  BA b;
+  const int64_t launches0 = ctx->launches;
+  PXR_TRY(b.create(ctx, &d, interp, &so, false));
+  DevBuf<double> refs;
+  DevBuf<int64_t> src;
+  PXR_TRY(refs_on_device(ctx, b, loss_type, loss_scale, iters, refs, src));
+  PXR_CUDA(cudaMemcpyAsync(refs_out, refs.p, (size_t)b.n_points * b.C * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PXR_TRY(read_src(ctx, b, src, src_obs_out));
   if (summary) {
     summary->kernel_launches = ctx->launches - launches0;
     summary->h2d_bytes = b.h2d_bytes; summary->d2h_bytes = (double)b.n_points * (b.C + 1) * 8;
   }
   return PXR_OK;
+}
+
+extern "C" int pxr_default_costmap_config(pxr_costmap_config* c) {
+  if (!c) return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
+  c->loss_type = PXR_LOSS_TRIVIAL; c->loss_scale = 1.0;      // CostMapConfig(): TrivialLoss, costmap_extractor.h:19
+  c->as_gradientfield = 1; c->compute_cross_derivative = 0; c->apply_sqrt = 0; c->upsampling_factor = 1.0;
+  c->compute_refs = 1; c->ref_loss_type = PXR_LOSS_CAUCHY; c->ref_loss_scale = 0.25; c->ref_iters = 100;
+  return PXR_OK;
+}
+
+extern "C" int pxr_costmaps_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
+                                    const pxr_costmap_config* cfg, double* refs_io, int64_t* src_obs_out,
+                                    void* out_host, void** out_device, pxr_summary* summary) {
+  if (!ctx || !desc || !cfg || (!out_host && !out_device)) return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (cfg->upsampling_factor != 1.0 || cfg->compute_cross_derivative)
+    return fail(PXR_ERR_UNSUPPORTED, "cost maps: only upsampling_factor == 1 without the cross derivative (the reference's default branch)");
+  if (!cfg->compute_refs && !desc->refs && !refs_io) return fail(PXR_ERR_INVALID_ARGUMENT, "references are required when compute_refs == 0");
+  pxr_ba_desc d = *desc;
+  d.refs = nullptr;
+  pxr_solver_options so;
+  pxr_default_ba_options(&so);
+  BA b;
+  const int64_t launches0 = ctx->launches;
+  PXR_TRY(b.create(ctx, &d, interp, &so, false));
+  cudaStream_t s = ctx->stream;
+  DevBuf<double> refs;
+  DevBuf<int64_t> src;
+  double d2h = 0;
+  if (cfg->compute_refs) {
+    PXR_TRY(refs_on_device(ctx, b, cfg->ref_loss_type, cfg->ref_loss_scale, cfg->ref_iters, refs, src));
+    if (refs_io) { PXR_CUDA(cudaMemcpyAsync(refs_io, refs.p, (size_t)b.n_points * b.C * 8, cudaMemcpyDeviceToHost, s)); d2h += (double)b.n_points * b.C * 8; }
+    PXR_TRY(read_src(ctx, b, src, src_obs_out));
+  } else {
+    const double* hr = desc->refs ? desc->refs : refs_io;
+    PXR_TRY(refs.upload(hr, (size_t)b.n_points * b.C, s));
+  }
+  const int OC = cfg->as_gradientfield ? 3 : 1;
+  const size_t esz = b.dtype == PXR_F16 ? 2 : (b.dtype == PXR_F32 ? 4 : 8);
+  const size_t out_bytes = (size_t)b.n_patches * b.ph * b.pw * OC * esz;
+  uint8_t* dout = nullptr;
+  PXR_CUDA(cudaMalloc((void**)&dout, std::max<size_t>(out_bytes, 16)));
+  cudaError_t e = cudaMemsetAsync(dout, 0, out_bytes, s);
+  CostmapArgs a;
+  a.patches = b.d_patches; a.ph = b.ph; a.pw = b.pw; a.C = b.C;
+  a.refs = refs.p; a.item_patch = b.obs_patch.p; a.item_ref = b.obs_pt.p; a.n_items = b.n_obs;
+  a.out = dout; a.OC = OC; a.loss.type = cfg->loss_type; a.loss.a = cfg->loss_scale;
+  a.as_gradientfield = cfg->as_gradientfield; a.apply_sqrt = cfg->apply_sqrt;
+  int rc = e == cudaSuccess ? PXR_OK : fail(PXR_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+  if (rc == PXR_OK) {
+    if (b.dtype == PXR_F16) rc = launch_costmaps<__half>(ctx, a);
+    else if (b.dtype == PXR_F32) rc = launch_costmaps<float>(ctx, a);
+    else rc = launch_costmaps<double>(ctx, a);
+  }
+  if (rc == PXR_OK && out_host) {
+    e = cudaMemcpyAsync(out_host, dout, out_bytes, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) rc = fail(PXR_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    d2h += (double)out_bytes;
+  }
+  e = cudaStreamSynchronize(s);
+  if (rc == PXR_OK && e != cudaSuccess) rc = fail(PXR_ERR_CUDA, "cost-map extraction failed: %s", cudaGetErrorString(e));
+  if (rc != PXR_OK || !out_device) cudaFree(dout); else *out_device = dout;
+  if (rc == PXR_OK && summary) {
+    summary->kernel_launches = ctx->launches - launches0;
+    summary->h2d_bytes = b.h2d_bytes; summary->d2h_bytes = d2h;
+  }
+  return rc;
 }

@@ -129,6 +129,17 @@ class ReferenceConfig(_DictOptions):
                      loss=lambda: {"name": "cauchy", "params": [0.25]})
 
 
+class CostMapConfig(_DictOptions):
+    """costmap_extractor.h:18-40 (bindings.cc:55-65); loss defaults to TrivialLoss."""
+    _defaults = dict(upsampling_factor=1.0, as_gradientfield=True, compute_cross_derivative=False, apply_sqrt=False,
+                     num_threads=-1, dense_cut_size=12, loss=lambda: {"name": "trivial", "params": []})
+
+    def get_effective_channels(self):
+        if self.as_gradientfield:
+            return 4 if self.compute_cross_derivative else 3
+        return 1
+
+
 def _cam_const_mask(camera, options, setup, camera_id):
     constant_camera = not (options.refine_focal_length or options.refine_principal_point or options.refine_extra_params)
     if constant_camera or setup.is_constant_camera(camera_id):
@@ -270,6 +281,7 @@ def build_problem(reconstruction, feature_view, setup, options, references=None,
         name = feature_view.image_name(image_id)
         obs_patch[k] = slab.index(name, feature_view.get_feature_map(image_id), p2D_idx)
     blocks, corners, scales = slab.arrays()
+    ir.slab_offsets = dict(slab._offset)     # image name -> first global patch index, in block order
     refs = None
     if references is not None:
         C_ = feature_view.channels
@@ -370,3 +382,86 @@ class FeatureReferenceBundleOptimizer:
 
     def summary(self):
         return self._summary
+
+
+def _loss_id_scale(loss):
+    name = str(loss.get("name", "trivial")).lower()
+    if name not in _capi.LOSS_IDS:
+        raise ValueError("unsupported loss %r" % name)
+    params = list(loss.get("params", []) or [])
+    return _capi.LOSS_IDS[name], float(params[0]) if params else 1.0
+
+
+class CostMapExtractor:
+    """_bundle_adjustment.CostMapExtractor(CostMapConfig|dict, InterpolationConfig|dict)
+    .run(problem_labels, reconstruction, feature_set, ref_extractor) -> (costmap FeatureSet, {point3D_id: Reference})
+    (bindings.cc:20-26,179-184; costmap_extractor.h:93-228).  References and cost maps come out of ONE upload of the
+    feature patches (pxr_costmaps_compute); the cost patches keep the source patches' corner / scale."""
+
+    def __init__(self, config, interpolation_config):
+        self.config = config if isinstance(config, CostMapConfig) else CostMapConfig(config)
+        self.interp = interpolation_config if isinstance(interpolation_config, InterpolationConfig) else InterpolationConfig(interpolation_config)
+        self.interp.validate_for_device()
+
+    def run(self, problem_labels, reconstruction, feature_set, ref_extractor):
+        if len(self.interp.nodes) != 1:
+            raise ValueError("CostMap extract: n_nodes must be 1")       # THROW_CHECK_EQ(n_nodes, 1), :107
+        if ref_extractor is None:
+            raise ValueError("a ReferenceExtractor is required (the references are computed in the same pass)")
+        from ._features import FeatureMap, FeatureSet
+        ids = {p for p in reconstruction.points3D.keys() if p < len(problem_labels) and problem_labels[p] >= 0}
+        fview = FeatureView(feature_set, reconstruction)
+        prob, ir = build_problem(reconstruction, fview, None, None, None, for_references=ids)
+        refs = {p: Reference() for p in ids}
+        out_channels = self.config.get_effective_channels()
+        cost_fset = FeatureSet(out_channels, feature_set.dtype if hasattr(feature_set, "dtype") else None)
+        if prob.n_obs == 0:
+            return cost_fset, refs
+        lt, ls = _loss_id_scale(self.config.loss)
+        rlt, rls = _loss_id_scale(ref_extractor.config.loss)
+        cfg = _capi.default_costmap_config(loss_type=lt, loss_scale=ls, as_gradientfield=int(bool(self.config.as_gradientfield)),
+                                           compute_cross_derivative=int(bool(self.config.compute_cross_derivative)),
+                                           apply_sqrt=int(bool(self.config.apply_sqrt)),
+                                           upsampling_factor=float(self.config.upsampling_factor), compute_refs=1,
+                                           ref_loss_type=rlt, ref_loss_scale=rls, ref_iters=int(ref_extractor.config.iters))
+        ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
+        out = _engine.costmaps_compute(prob, ic, cfg)
+        for k, pid in enumerate(ir.point_ids):
+            if out["src_obs"][k] < 0:
+                continue
+            image_id, p2D_idx, _ = ir.obs[int(out["src_obs"][k])]
+            refs[pid] = Reference((image_id, p2D_idx), out["refs"][k].reshape(1, -1).copy())
+        cm = out["costmaps"]
+        for name, off in ir.slab_offsets.items():
+            fmap = feature_set.fmap(name) if hasattr(feature_set, "fmap") else feature_set[name]
+            cost_fset.emplace(name, FeatureMap(cm[off:off + fmap.size()], fmap.point2D_ids, fmap.corners,
+                                               {"scale": fmap.scale, "is_sparse": True}))
+        return cost_fset, refs
+
+
+class CostMapBundleOptimizer(FeatureReferenceBundleOptimizer):
+    """_bundle_adjustment.CostMapBundleOptimizer(options, setup, interpolation).run(reconstruction, costmap_view)
+    (bindings.cc:143-160; costmap_bundle_optimizer.h:60-132): the residual of an observation is the interpolated
+    cost-map vector itself (no reference descriptor, no L2 normalisation)."""
+
+    def run(self, reconstruction, feature_view):   # noqa: D102
+        if reconstruction is None:
+            raise ValueError("reconstruction cannot be NULL.")
+        if self._used:
+            raise ValueError("Cannot use the same BundleOptimizer multiple times")
+        self._used = True
+        self.interp.validate_for_device()
+        if len(self.interp.nodes) != 1 or feature_view.channels not in (1, 3, 4):
+            raise ValueError("Unsupported dimensions (CHANNELS,N_NODES).")
+        prob, ir = build_problem(reconstruction, feature_view, self.setup, self.options, None)
+        if prob.n_obs == 0:
+            return False
+        so = solver_options_from(self.options.loss, self.options.solver, _capi.default_ba_options(use_inner_iterations=0))
+        ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
+        s = _engine.ba_run(prob, ic, so)
+        for cb in (self.options.solver.get("callbacks") or []):
+            for it in s["iterations"]:
+                cb(it)
+        write_back(reconstruction, prob, ir)
+        self._summary = _Summary(s, num_residuals_reduced=s["num_residuals"], total_time_in_seconds=s["total_time_s"])
+        return True

@@ -51,6 +51,14 @@ class SolverOptions(C.Structure):
                 ("deterministic", C.c_int32)]
 
 
+class CostmapConfig(C.Structure):
+    """pxr_costmap_config == CostMapConfig (costmap_extractor.h:18-40) + the embedded ReferenceConfig."""
+    _fields_ = [("loss_type", C.c_int32), ("loss_scale", C.c_double), ("as_gradientfield", C.c_int32),
+                ("compute_cross_derivative", C.c_int32), ("apply_sqrt", C.c_int32),
+                ("upsampling_factor", C.c_double), ("compute_refs", C.c_int32),
+                ("ref_loss_type", C.c_int32), ("ref_loss_scale", C.c_double), ("ref_iters", C.c_int32)]
+
+
 class BADesc(C.Structure):
     _fields_ = [("n_cameras", C.c_int32), ("cam_model", C.c_void_p), ("cam_params", C.c_void_p),
                 ("cam_const_mask", C.c_void_p),
@@ -118,6 +126,16 @@ def summary_to_dict(s):
 
 def default_interp(l2_normalize=True, use_float_simd=False):
     return InterpConfig(int(l2_normalize), int(use_float_simd), 0, 0)
+
+
+def default_costmap_config(**kw):
+    c = CostmapConfig(loss_type=0, loss_scale=1.0, as_gradientfield=1, compute_cross_derivative=0, apply_sqrt=0,
+                      upsampling_factor=1.0, compute_refs=1, ref_loss_type=1, ref_loss_scale=0.25, ref_iters=100)
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise ValueError("unknown cost-map option %r" % k)
+        setattr(c, k, v)
+    return c
 
 
 def default_ba_options(**kw):
@@ -222,6 +240,18 @@ class BAProblem:
     @property
     def n_obs(self):
         return len(self.obs_pt)
+
+    @property
+    def patch_np_dtype(self):
+        return {v: k for k, v in DTYPE_IDS.items()}[self.patch_dtype]
+
+    def with_patches(self, patches, refs=None, on_device=False, patch_shape=None, patch_dtype=None):
+        """Same geometry / observation lists, other patches (e.g. the 3-channel cost maps of these features)."""
+        return BAProblem(self.cam_model, self.cam_params, self.cam_const_mask, self.qvec, self.tvec, self.img_cam,
+                         self.pose_const, self.tvec_const_mask, self.xyz, self.point_const, self.obs_img, self.obs_pt,
+                         patches, self.corner, self.scale, refs=refs, obs_patch=self.obs_patch,
+                         upsampling_factor=self.upsampling_factor, patches_on_device=on_device,
+                         patch_shape=patch_shape, patch_dtype=patch_dtype)
 
     def desc(self):
         d = BADesc()

@@ -112,6 +112,32 @@ def refs_compute(problem, interp=None, loss_type=1, loss_scale=0.25, iters=100, 
     return refs, src
 
 
+def costmaps_compute(problem, interp=None, cfg=None, refs=None, to_host=True, to_device=False, ctx=None):
+    """pxr_costmaps_compute == CostMapExtractor.run: reference extraction (unless cfg.compute_refs == 0) and one
+    cost patch per observation patch.  -> dict(costmaps [n_patches,ph,pw,OC] in the patch dtype or None,
+    device_ptr or None, refs [n_points,C], src_obs [n_points])"""
+    ctx = ctx or _capi.default_context()
+    interp = interp or _capi.default_interp()
+    cfg = cfg or _capi.default_costmap_config()
+    d = problem.desc()
+    n_points = len(problem.xyz)
+    if refs is None:
+        refs = np.zeros((n_points, problem.channels))
+    else:
+        refs = np.ascontiguousarray(refs, np.float64)
+    src = np.full(n_points, -1, np.int64)
+    oc = 3 if cfg.as_gradientfield else 1
+    n_patches = d.n_patches if d.n_patches else d.n_obs
+    out = np.zeros((n_patches, problem.ph, problem.pw, oc), problem.patch_np_dtype) if to_host else None
+    dptr = C.c_void_p()
+    s = _capi.make_summary(0)
+    _capi.check(ctx.lib.pxr_costmaps_compute(ctx.handle, C.byref(d), C.byref(interp), C.byref(cfg), _p(refs), _p(src),
+                                             _p(out) if to_host else None, C.byref(dptr) if to_device else None,
+                                             C.byref(s)))
+    return {"costmaps": out, "device_ptr": dptr.value if to_device else None, "refs": refs, "src_obs": src,
+            "summary": _capi.summary_to_dict(s)}
+
+
 def synth_patches_device(n_patches, ps, channels, uv0, field_id, seed=0, noise=0.01, ctx=None):
     """Device-side synthetic patch slab (fp16). Returns the device pointer (int)."""
     ctx = ctx or _capi.default_context()

@@ -121,6 +121,18 @@ def refs_compute(prob, interp, loss_type=1, loss_scale=0.25, iters=100):
     return refs, src
 
 
+def costmaps_compute(prob, loss_type=0, loss_scale=1.0, as_gradientfield=True, apply_sqrt=False):
+    """orc_costmaps_compute (costmap_extractor.h:230-358); prob.refs must be set."""
+    d = prob.desc()
+    oc = 3 if as_gradientfield else 1
+    n_patches = d.n_patches if d.n_patches else d.n_obs
+    out = np.zeros((n_patches, prob.ph, prob.pw, oc), prob.patch_np_dtype)
+    rc = lib().orc_costmaps_compute(C.byref(d), int(loss_type), C.c_double(loss_scale), int(as_gradientfield),
+                                    int(apply_sqrt), p(out))
+    assert rc == 0
+    return out
+
+
 def ka_solve(kaprob, interp, opts):
     """Oracle KA on kaprob IN PLACE (keypoints updated). Returns (initial_cost, final_cost)."""
     from pixsfm._pixsfm import _capi

@@ -151,3 +151,42 @@ def test_unsupported_channels_raise_value_error():
     bad.refs = np.ascontiguousarray(prob.refs[:, :3])
     with pytest.raises(ValueError):
         _engine.BAHandle(bad, ic, _capi.default_ba_options())
+
+
+def test_iterative_schur_pcg_matches_oracle():
+    """ITERATIVE_SCHUR (bundle_optimizer.h:181-191 picks it above 1000 images): block-Jacobi PCG on the reduced
+    camera system, Ceres' Q-based termination. Inexact steps -> compare at the reference's own 1e-4 BA tolerance."""
+    prob, gt, ic = _scene()
+    so = _capi.default_ba_options(use_inner_iterations=0, max_num_iterations=12, linear_solver=3)
+    p_ref = prob.copy(); p_gpu = prob.copy()
+    s_ref = O.ba_solve(p_ref, ic, so)
+    s_gpu = _engine.ba_run(p_gpu, ic, so)
+    assert abs(s_gpu["initial_cost"] - s_ref["initial_cost"]) <= 1e-10 * s_ref["initial_cost"]
+    assert abs(s_gpu["final_cost"] - s_ref["final_cost"]) <= 1e-5 * s_ref["final_cost"]
+    it_g = [i["linear_solver_iterations"] for i in s_gpu["iterations"][1:]]
+    it_r = [i["linear_solver_iterations"] for i in s_ref["iterations"][1:]]
+    assert min(it_g) >= 1 and len(it_g) == len(it_r)
+    assert max(abs(a - b) for a, b in zip(it_g, it_r)) <= 2, (it_g, it_r)
+    _compare_solutions(p_gpu, p_ref, 1e-4)
+    # and the inexact path lands where the exact one does
+    p_ex = prob.copy()
+    s_ex = _engine.ba_run(p_ex, ic, _capi.default_ba_options(use_inner_iterations=0, max_num_iterations=12))
+    assert abs(s_gpu["final_cost"] - s_ex["final_cost"]) <= 1e-3 * s_ex["final_cost"]
+
+
+@pytest.mark.parametrize("n_cams,multikernel", [(45, False), (45, True), (150, False), (33, False)])
+def test_reduced_system_cholesky_tile_dag(n_cams, multikernel, monkeypatch):
+    """The exact reduced-camera-system solve (DENSE/SPARSE_SCHUR, bundle_optimizer.h:181-191) at sizes that span
+    many 32x32 tiles with a ragged last tile: the persistent tile-DAG kernel (pxr_chol.cuh) and the older
+    launch-per-panel path must both reproduce the oracle's step."""
+    if multikernel:
+        monkeypatch.setenv("PXR_CHOL_MULTIKERNEL", "1")
+    prob, gt, ic = _scene(n_cams=n_cams, n_points=12 * n_cams, track_len=6, channels=16, seed=n_cams)
+    so = _capi.default_ba_options(use_inner_iterations=0)
+    ref = O.ba_linearize(prob, ic, so, radius=1e4)
+    assert ref["nc"] > 32 * 6
+    h = _engine.BAHandle(prob, ic, so)
+    for _ in range(2):       # twice: the second call replays the captured graph with re-zeroed flags
+        got = h.debug_linearize(ref["nc"], ref["nl"], radius=1e4)
+        assert np.allclose(got["delta"], ref["delta"], rtol=1e-5, atol=1e-8 * np.abs(ref["delta"]).max())
+    assert abs(got["model_cost_change"] - ref["model_cost_change"]) <= 1e-7 * abs(ref["model_cost_change"])

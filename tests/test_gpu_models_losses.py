@@ -90,7 +90,16 @@ def test_large_track_and_ragged_inputs():
     ic = _capi.default_interp()
     r_cpu, s_cpu = O.refs_compute(sub, ic)
     r_gpu, s_gpu = _engine.refs_compute(sub, ic)
-    assert np.array_equal(s_cpu, s_gpu) and (s_gpu == -1).sum() >= 10
+    # A 2-observation track is an exact mathematical tie (both descriptors are equidistant from their
+    # normalised mean), so its argmin is decided by summation-order rounding in the reference as well
+    # (Eigen's squaredNorm, reference_extractor.h:249-255): compare the index only for the other tracks.
+    tl = np.bincount(sub.obs_pt, minlength=50)
+    pinned = tl != 2
+    assert np.array_equal(s_cpu[pinned], s_gpu[pinned]) and (s_gpu == -1).sum() >= 10
+    assert ((s_cpu >= 0) == (s_gpu >= 0)).all()
+    first = np.concatenate([[0], np.cumsum(tl)])[:-1]
+    two = np.where(tl == 2)[0]
+    assert all(first[p] <= s_gpu[p] < first[p] + 2 for p in two)
     sub.refs = r_cpu
     so = _capi.default_ba_options(use_inner_iterations=1, max_num_iterations=6)
     a, b = sub.copy(), sub.copy()

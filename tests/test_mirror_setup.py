@@ -7,6 +7,7 @@ import pytest
 
 from pixsfm import base, bundle_adjustment as ba_pkg, keypoint_adjustment as ka_pkg
 from pixsfm._pixsfm import _bundle_adjustment as ba
+from pixsfm._pixsfm import _capi
 from pixsfm._pixsfm._features import FeatureView
 from recon_util import make_reconstruction
 
@@ -127,3 +128,26 @@ def test_graph_mirror_and_labels():
     assert sum(rt) == len(set(tl))
     labels, bins = ka_pkg.find_problem_labels(tl, 50)
     assert len(bins) == 1 and set(labels) == {0}
+
+
+def test_costmap_strategy_surface_and_defaults():
+    """bundle_adjustment/main.py:218-238 + costmap_extractor.h:18-40: same class names, keys and defaults."""
+    from pixsfm import bundle_adjustment as ba_pkg
+    from pixsfm._pixsfm import _bundle_adjustment as ba
+    adj = ba_pkg.BundleAdjuster.create({"strategy": "costmaps"})
+    assert isinstance(adj, ba_pkg.CostMapBundleAdjuster)
+    assert adj.conf.costmaps.loss.name == "trivial" and adj.conf.costmaps.as_gradientfield is True
+    assert adj.conf.costmaps.compute_cross_derivative is False
+    cfg = ba.CostMapConfig()
+    assert (cfg.upsampling_factor, cfg.as_gradientfield, cfg.compute_cross_derivative, cfg.apply_sqrt, cfg.dense_cut_size) == \
+        (1.0, True, False, False, 12)
+    assert cfg.get_effective_channels() == 3
+    assert ba.CostMapConfig({"as_gradientfield": False}).get_effective_channels() == 1
+    assert ba.CostMapConfig({"compute_cross_derivative": True}).get_effective_channels() == 4
+    with pytest.raises(ValueError):
+        ba.CostMapConfig({"no_such_key": 1})
+    with pytest.raises(ValueError):
+        ba_pkg.BundleAdjuster.create({"strategy": "patch_warp"})
+    c = _capi.default_costmap_config()
+    assert (c.loss_type, c.as_gradientfield, c.apply_sqrt, c.upsampling_factor, c.ref_loss_type, c.ref_loss_scale, c.ref_iters) == \
+        (0, 1, 0, 1.0, 1, 0.25, 100)

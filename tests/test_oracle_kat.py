@@ -145,6 +145,21 @@ def test_model_cost_change_and_schur_consistency():
     assert np.allclose(S @ lin["delta"][:nc], lin["rhs"], rtol=1e-8, atol=1e-10)
 
 
+def test_iterative_schur_pcg_restatement():
+    """Ceres ITERATIVE_SCHUR + SCHUR_JACOBI as restated in oracle/orc_ba.h (SchurJacobiPCG): the inexact steps
+    must converge to the exact solver's optimum, with CG iteration counts reported and bounded."""
+    prob, ic, so = _small_scene()
+    pe = prob.copy(); pi = prob.copy()
+    so_e = _capi.default_ba_options(use_inner_iterations=0, max_num_iterations=15)
+    so_i = _capi.default_ba_options(use_inner_iterations=0, max_num_iterations=15, linear_solver=3)
+    se = O.ba_solve(pe, ic, so_e); si = O.ba_solve(pi, ic, so_i)
+    assert abs(si["final_cost"] - se["final_cost"]) <= 1e-3 * se["final_cost"]
+    its = [i["linear_solver_iterations"] for i in si["iterations"][1:]]
+    assert its and min(its) >= 1 and max(its) <= so_i.max_linear_solver_iterations
+    assert all(i["linear_solver_iterations"] == 0 for i in se["iterations"][:1])
+    # (parameters are not compared: this scene has scale-gauge freedom, inexact steps drift along it)
+
+
 # --- (v) IRLS, reference pixsfm/base/src/irls_optim.h:23-71 vs a numpy restatement -------------------
 @pytest.mark.parametrize("C_,n", [(128, 10), (128, 100), (3, 10), (3, 1000)])
 def test_irls_matches_numpy(C_, n):
@@ -196,3 +211,36 @@ def test_loss_functions_derivatives():
                 assert abs((rp[0] - rm[0]) / (2 * h) - rho[1]) < 1e-4
     O.lib().orc_loss(1, C.c_double(0.25), C.c_double(1.0), C.c_double(0.0625), p(rho))
     assert np.allclose(rho, [0.0625 * np.log(2), 0.5, -4.0])
+
+
+# --- (viii) cost maps, reference costmap_extractor.h:230-358 vs an independent numpy restatement ------
+@pytest.mark.parametrize("dtype", [np.float16, np.float64])
+def test_costmap_extraction_matches_numpy(dtype):
+    from pixsfm.util import synthetic
+    prob, gt = synthetic.make_ba_scene(n_cams=4, n_points=12, track_len=3, channels=16, seed=2, dtype=dtype)
+    ic = _capi.default_interp()
+    prob.refs = O.refs_compute(prob, ic)[0]
+    got = O.costmaps_compute(prob, loss_type=1, loss_scale=0.25, as_gradientfield=True, apply_sqrt=False)
+    P = prob.patches
+    H, W = P.shape[1:3]
+    up = np.minimum(np.arange(H) + 1, H - 1); dn = np.maximum(np.arange(H) - 1, 0)
+    rt = np.minimum(np.arange(W) + 1, W - 1); lf = np.maximum(np.arange(W) - 1, 0)
+    for o in (0, 5, prob.n_obs - 1):
+        f = P[o].astype(np.float64)
+        # the difference is formed in the patch dtype (Eigen evaluates Map<dtype> - Map<dtype> first)
+        dfdr = 0.5 * (P[o][up] - P[o][dn]).astype(dtype).astype(np.float64)
+        dfdc = 0.5 * (P[o][:, rt] - P[o][:, lf]).astype(dtype).astype(np.float64)
+        r = f - prob.refs[prob.obs_pt[o]]
+        s = (r * r).sum(-1)
+        b = 0.25 ** 2
+        rho0 = b * np.log1p(s / b); rho1 = 1.0 / (1.0 + s / b)
+        cost = 0.5 * rho0
+        live = cost > 1e-8
+        want = np.stack([cost, np.where(live, rho1 * (r * dfdr).sum(-1), 0.0), np.where(live, rho1 * (r * dfdc).sum(-1), 0.0)], -1)
+        tol = 2e-3 if dtype == np.float16 else 1e-12
+        assert np.allclose(got[o].astype(np.float64), want, rtol=tol, atol=tol * 1e-2 + 1e-15)
+    # a patch identical to its reference everywhere has zero cost and (cost <= 1e-8 branch) zero gradient
+    prob2 = prob.with_patches(np.ascontiguousarray(np.broadcast_to(prob.refs[prob.obs_pt][:, None, None, :], P.shape).astype(dtype)),
+                              refs=prob.refs[:].astype(dtype).astype(np.float64))
+    z = O.costmaps_compute(prob2)
+    assert np.abs(z.astype(np.float64)).max() == 0.0
