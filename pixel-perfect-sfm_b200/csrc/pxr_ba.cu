@@ -434,6 +434,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
       if (!chol_multikernel) {
         // one persistent kernel: tile DAG with flags (pxr_chol.cuh); the memset of the flags is part of the graph
         PXR_CUDA(cudaMemsetAsync(chol_sync.p, 0, chol_sync.n * sizeof(int), s));
+        PXR_CUDA(cudaMemsetAsync(delta.p, 0xFF, (size_t)nc * 8, s));   // x doubles as its own ready flag (pxr_chol.cuh)
         pxr_chol::Args ca;
         ca.A = S.p; ca.x = delta.p; ca.n = nc; ca.nb = nb;
         ca.diag_ready = chol_sync.p; ca.ready = ca.diag_ready + nb; ca.upd = ca.ready + (size_t)(nb + 1) * nb;
@@ -464,7 +465,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
       PXR_CUDA(cudaStreamSynchronize(s));
       if (FILE* f = fopen(getenv("PXR_CHOL_TRACE"), "w")) {
         const int nbt = (int)cdiv(nc, kNB);
-        for (int k = 0; k < nbt; ++k) { for (int q = 0; q < 6; ++q) fprintf(f, "%lld ", h[(size_t)k * 8 + q] - h[0]); fprintf(f, "\n"); }
+        for (int k = 0; k < nbt; ++k) { for (int q = 0; q < 7; ++q) fprintf(f, "%lld ", h[(size_t)k * 8 + q] - h[0]); fprintf(f, "\n"); }
         fprintf(f, "backsolve_start %lld\n", h[(size_t)nbt * 8] - h[0]);
         for (int c = nbt - 1; c >= 0; --c) fprintf(f, "x %d %lld\n", c, h[(size_t)nbt * 8 + 8 + c] - h[0]);
         fclose(f);

@@ -45,6 +45,11 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+constexpr unsigned long long kXSentinel = 0xFFFFFFFFFFFFFFFFull;   // memset(0xFF): a NaN no computation produces
+
 struct Args {
   double* A;        // (n+1) x n
   double* x;        // n, solution
@@ -71,6 +76,37 @@ struct Geo {
   // column-major enumeration of the tiles i >= j, i in [j, nb]
   __device__ __forceinline__ int64_t off(int j) const { return (int64_t)j * (nb + 1) - (int64_t)j * (j - 1) / 2; }
 };
+
+// One thread spins until *p >= target (or the abort flag is up / the cycle budget is gone).
+__device__ __forceinline__ void spin_until(const int* p, int target, int* abort_flag, int* fail_flag) {
+  long long start = 0;
+  unsigned spins = 0;
+  while (ld_acquire(p) < target) {
+    if ((++spins & 1023u) == 0) {
+      if (ld_acquire(abort_flag)) break;
+      const long long now = clock64();
+      if (start == 0) start = now;
+      else if (now - start > 4000000000LL) { st_release(abort_flag, 1); *fail_flag = 1; break; }
+    }
+  }
+}
+// Poll a double that the host pre-set to kXSentinel until its producer has stored the value.
+__device__ __forceinline__ double poll_value(const double* p, int* abort_flag, int* fail_flag) {
+  long long start = 0;
+  unsigned spins = 0;
+  unsigned long long bits;
+  while (true) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory");
+    if (bits != kXSentinel) break;
+    if ((++spins & 1023u) == 0) {
+      if (ld_acquire(abort_flag)) break;
+      const long long now = clock64();
+      if (start == 0) start = now;
+      else if (now - start > 4000000000LL) { st_release(abort_flag, 1); *fail_flag = 1; break; }
+    }
+  }
+  return __longlong_as_double((long long)bits);
+}
 
 // Spin (thread `who` only) until *p >= target or the abort flag is up; all threads then pass a barrier.
 template <int BAR, int NTHREADS>
@@ -117,27 +153,63 @@ __device__ __forceinline__ void store_tile(double (*src)[TB + 1], double* A, con
   }
 }
 
-// One warp factors the 32x32 block in `a` (lower triangle valid, identity-padded) in registers.
-// Leaves L (zeros above the diagonal) in `a`, reciprocal pivots in rd. Returns false on a bad pivot.
-static __device__ __noinline__ bool factor_diag_warp(double (*a)[TB + 1], double* rd, int kb, int lane) {
-  double r[TB];
-#pragma unroll
-  for (int c = 0; c < TB; ++c) r[c] = (lane < kb && c < kb && c <= lane) ? a[lane][c] : (c == lane ? 1.0 : 0.0);
+// The whole CTA factors the 32x32 block in `a` (lower triangle valid, identity-padded), two-level:
+// four 8-column panels; warp 0 factors a panel with lane = row and the 8 entries of the row in
+// registers (8 dependent steps of shuffle + rsqrt + <= 7 rank-1 column updates: ~70 instructions per
+// step), then all warps apply the rank-8 update to the trailing block out of shared memory.
+// Leaves L (zeros above the diagonal) in `a`, reciprocal pivots in rd; returns false on a bad pivot
+// (meaningful in warp 0).  While warp 0 works on the first panel the other warps run `prefetch`.
+//
+// Why not one warp with the full row in registers: the measured cost of that was the warp's own
+// instruction stream (400 instructions per column with a rotating window, or 10k straight-line
+// instructions = 160 KB of i-cache when fully unrolled): ~20 us per tile against a ~2.5 us dependency
+// chain (32 x [shuffle, rsqrt, multiply, shuffle, fma]).
+template <class PrefetchFn>
+__device__ __forceinline__ bool factor_diag_cta(double (*a)[TB + 1], double* rd, int kb, int tid, PrefetchFn prefetch) {
+  const int warp = tid >> 5, lane = tid & 31;
   bool ok = true;
+  if (tid >= kb && tid < TB) a[tid][tid] = 1.0;      // identity padding of a ragged last tile (loads zero-fill it)
+  __syncthreads();
+#pragma unroll 1
+  for (int jb = 0; jb < 4; ++jb) {
+    const int j0 = jb * 8;
+    if (warp == 0) {
+      double r[8];
 #pragma unroll
-  for (int j = 0; j < TB; ++j) {
-    const double dj = __shfl_sync(0xffffffffu, r[j], j);
-    if (!(dj > 0.0) || !isfinite(dj)) ok = false;
-    const double rj = rsqrt(dj);
-    if (lane == j) { r[j] = dj * rj; rd[j] = rj; }
-    else if (lane > j) r[j] *= rj;
-    const double lij = r[j];
-    a[lane][j] = (lane >= j) ? lij : 0.0;            // column j is final: r[j] dies here
+      for (int c = 0; c < 8; ++c) r[c] = a[lane][j0 + c];
 #pragma unroll
-    for (int c = j + 1; c < TB; ++c) {
-      const double lcj = __shfl_sync(0xffffffffu, lij, c);
-      if (lane >= c) r[c] -= lij * lcj;
+      for (int c = 0; c < 8; ++c) {
+        const int j = j0 + c;
+        const double dj = __shfl_sync(0xffffffffu, r[c], j);
+        if (!(dj > 0.0) || !isfinite(dj)) ok = false;
+        const double rj = rsqrt(dj);
+        double lij = r[c];
+        if (lane == j) { lij = dj * rj; rd[j] = rj; }
+        else if (lane > j) lij *= rj;
+        r[c] = lij;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2) {
+          const double lcj = __shfl_sync(0xffffffffu, lij, j0 + c2);
+          if (lane >= j0 + c2) r[c2] -= lij * lcj;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[lane][j0 + c] = (lane >= j0 + c) ? r[c] : 0.0;
+    } else if (jb == 0) {
+      prefetch();
     }
+    __syncthreads();
+    const int n0 = j0 + 8, m = TB - n0;              // trailing m x m block (lower part)
+    for (int e = tid; e < m * m; e += kThreads) {
+      const int rr = n0 + e / m, cc = n0 + e % m;
+      if (rr >= cc) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sacc += a[rr][j0 + q] * a[cc][j0 + q];
+        a[rr][cc] -= sacc;
+      }
+    }
+    __syncthreads();
   }
   return ok;
 }
@@ -176,7 +248,7 @@ __device__ __forceinline__ void syrk_tile_smem(double (*out)[TB + 1], double (*l
   out[ty][tx] -= s00; out[ty][tx + 16] -= s01; out[ty + 16][tx] -= s10; out[ty + 16][tx + 16] -= s11;
 }
 
-static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Args a) {
+static __global__ void __launch_bounds__(kThreads, 2) chol_persistent_kernel(Args a) {
   __shared__ double sbuf[3][TB][TB + 1];
   __shared__ double srd[TB];
   __shared__ double sx[TB];
@@ -198,30 +270,30 @@ static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Arg
     for (int k = 0; k < nb; ++k) {
       const int kb = g.cols(k);
       PXR_CHOL_STAMP(0);
-      if (warp == 0) {
-        const bool ok = factor_diag_warp(sbuf[ia], srd, kb, lane);
-        if (a.trace && lane == 0) a.trace[(int64_t)k * 8 + 1] = gtime();
-        if (!ok && lane == 0) *a.fail_flag = 1;
-      } else {
-        constexpr int NT = kThreads - 32;
-        const int t2 = tid - 32;
-        // tile (k+1, k): owner has applied panels 0..k-1
-        wait_flags<1, NT>(UP(k + 1, k), k, (k + 1 < nb) ? UP(k + 1, k + 1) : nullptr, k, a.abort, a.fail_flag, t2 == 0);
-        load_tile<NT>(sbuf[ib], A, g, k + 1, k, t2);
-        if (k + 1 < nb) load_tile<NT>(sbuf[ic], A, g, k + 1, k + 1, t2, true);
+      {
+        // tiles (k+1,k) and (k+1,k+1) — the owners have applied panels 0..k-1 — land while warp 0 factors
+        auto prefetch = [&]() {
+          constexpr int NT = kThreads - 32;
+          const int t2 = tid - 32;
+          wait_flags<1, NT>(UP(k + 1, k), k, (k + 1 < nb) ? UP(k + 1, k + 1) : nullptr, k, a.abort, a.fail_flag, t2 == 0);
+          if (a.trace && t2 == 0) a.trace[(int64_t)k * 8 + 6] = gtime();
+          load_tile<NT>(sbuf[ib], A, g, k + 1, k, t2);
+          if (k + 1 < nb) load_tile<NT>(sbuf[ic], A, g, k + 1, k + 1, t2, true);
+        };
+        const bool ok = factor_diag_cta(sbuf[ia], srd, kb, tid, prefetch);
+        if (!ok && tid == 0) *a.fail_flag = 1;
+        PXR_CHOL_STAMP(1);
       }
       __syncthreads();
       PXR_CHOL_STAMP(2);                              // factor done AND both prefetches landed
       store_tile<kThreads>(sbuf[ia], A, g, k, k, tid, true);
-      __threadfence();
-      __syncthreads();
+      __syncthreads();                                // barrier + release store by one thread is cumulative
       if (tid == 0) st_release(a.diag_ready + k, 1);
       PXR_CHOL_STAMP(3);
       solve_rows<kWarps>(sbuf[ib], sbuf[ia], srd, kb, warp, lane);
       __syncthreads();
       PXR_CHOL_STAMP(4);
       store_tile<kThreads>(sbuf[ib], A, g, k + 1, k, tid);
-      __threadfence();
       __syncthreads();
       if (tid == 0) st_release(RD(k + 1, k), 1);
       PXR_CHOL_STAMP(5);
@@ -250,6 +322,7 @@ static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Arg
         const int i = j + (int)(t - g.off(j));
         if (j == k) {
           if (i < k + 2) continue;
+          load_tile<kThreads>(sI, A, g, i, k, tid);  // own tile (all its updates are this CTA's): no flag needed
           if (!have_lkk) {
             wait_flags<0, kThreads>(a.diag_ready + k, 1, nullptr, 0, a.abort, a.fail_flag, tid == 0);
             load_tile<kThreads>(sK, A, g, k, k, tid, true);
@@ -257,20 +330,15 @@ static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Arg
             if (tid < TB) srd[tid] = 1.0 / (tid < kb ? sK[tid][tid] : 1.0);
             have_lkk = true;
           }
-          load_tile<kThreads>(sI, A, g, i, k, tid);
           __syncthreads();
           solve_rows<kWarps>(sI, sK, srd, kb, warp, lane);
           __syncthreads();
           store_tile<kThreads>(sI, A, g, i, k, tid);
-          __threadfence();
           __syncthreads();
           if (tid == 0) st_release(RD(i, k), 1);
         } else {
           if (i == j && k == j - 1) continue;        // the panel CTA applies this one itself
-          wait_flags<0, kThreads>(RD(i, k), 1, (i != j) ? RD(j, k) : nullptr, 1, a.abort, a.fail_flag, tid == 0);
-          load_tile<kThreads>(sI, A, g, i, k, tid);
-          if (i != j) load_tile<kThreads>(sJ, A, g, j, k, tid);
-          // the tile itself, read-modify-write straight from global (2x2 per thread)
+          // the tile itself (owned: no flag), read-modify-write straight from global, 2x2 per thread
           const int r0 = g.row0(i), nr = g.rows(i), c0 = j * TB, ncl = g.cols(j);
           double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
           const bool v0 = ty < nr, v1 = ty + 16 < nr, u0 = tx < ncl, u1 = tx + 16 < ncl;
@@ -280,6 +348,9 @@ static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Arg
           if (v0 && u1) c01 = __ldcg(p0 + 16);
           if (v1 && u0) c10 = __ldcg(p1);
           if (v1 && u1) c11 = __ldcg(p1 + 16);
+          wait_flags<0, kThreads>(RD(i, k), 1, (i != j) ? RD(j, k) : nullptr, 1, a.abort, a.fail_flag, tid == 0);
+          load_tile<kThreads>(sI, A, g, i, k, tid);
+          if (i != j) load_tile<kThreads>(sJ, A, g, j, k, tid);
           __syncthreads();
           double (*lj)[TB + 1] = (i != j) ? sJ : sI;
 #pragma unroll 8
@@ -292,8 +363,7 @@ static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Arg
           if (v1 && u0) __stcg(p1, c10);
           if (v1 && u1) __stcg(p1 + 16, c11);
           const bool watched = (i == j) || (i == j + 1);
-          if (watched) __threadfence();
-          __syncthreads();                            // sI/sJ free again; stores of a watched tile fenced
+          __syncthreads();                            // sI/sJ free again; orders the tile stores before the release below
           if (watched && tid == 0) st_release(UP(i, j), k + 1);
         }
       }
@@ -302,15 +372,29 @@ static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Arg
 
   // -------------------------------------------------------------------- back-substitution L^T x = y
   // y_c = row n, columns of block c  (tile (nb, c));  x_c = L_cc^-T (y_c - sum_{j>c} L_jc^T x_j)
+  // One CTA per column block.  Everything that does not depend on x is done up front (flags of column c,
+  // L_cc^-T formed explicitly so the last step is a mat-vec, not a 32-step substitution).  x itself is
+  // the message: the host pre-fills x with an all-ones NaN pattern, the producer stores plain doubles,
+  // every consumer warp polls the 32 values it needs — one L2 round trip per block, no flag, no fence.
   const int G = (int)gridDim.x;
   if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[(int64_t)nb * 8] = gtime();
   for (int c = nb - 1 - (int)blockIdx.x; c >= 0; c -= G) {
     const int kb = g.cols(c), c0 = c * TB;
     const int wr = tid >> 5;                         // row group: rows wr, wr+8, wr+16, wr+24 of a tile
+    // ---- phase A: column c is final once diag_ready[c] and ready[j,c] for j in (c, nb]
+    for (int t = tid; t <= nb - c; t += kThreads)
+      spin_until(t == 0 ? a.diag_ready + c : RD(c + t, c), 1, a.abort, a.fail_flag);
+    __syncthreads();
+    load_tile<kThreads>(sbuf[0], A, g, c, c, tid, true);
+    for (int e = tid; e < TB * TB; e += kThreads) sbuf[1][e >> 5][e & 31] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+    __syncthreads();
+    if (tid < TB) srd[tid] = 1.0 / (tid < kb ? sbuf[0][tid][tid] : 1.0);
+    __syncthreads();
+    solve_rows<kWarps>(sbuf[1], sbuf[0], srd, kb, warp, lane);      // I L^-T : sbuf[1] = L_cc^-T (upper triangular)
+    const double yv = (warp == 0 && lane < kb) ? __ldcg(A + (int64_t)g.n * g.n + c0 + lane) : 0.0;
+    // ---- phase B: accumulate L_jc^T x_j as the x_j arrive (j descending)
     double acc = 0.0;
     for (int j = nb - 1; j > c; --j) {
-      // L_jc is final once ready[j,c]; prefetch it before waiting for x_j
-      wait_flags<0, kThreads>(RD(j, c), 1, nullptr, 0, a.abort, a.fail_flag, tid == 0);
       const int r0 = j * TB, nr = g.rows(j);
       double l[4];
 #pragma unroll
@@ -318,31 +402,26 @@ static __global__ void __launch_bounds__(kThreads, 1) chol_persistent_kernel(Arg
         const int r = wr + 8 * m;
         l[m] = (r < nr && lane < kb) ? __ldcg(A + (int64_t)(r0 + r) * g.n + c0 + lane) : 0.0;
       }
-      wait_flags<0, kThreads>(a.xready + j, 1, nullptr, 0, a.abort, a.fail_flag, tid == 0);
-      if (tid < TB) sx[tid] = tid < nr ? __ldcg(a.x + r0 + tid) : 0.0;
-      __syncthreads();
+      const double xv = lane < nr ? poll_value(a.x + r0 + lane, a.abort, a.fail_flag) : 0.0;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) acc += l[m] * sx[wr + 8 * m];
-      __syncthreads();
+      for (int m = 0; m < 4; ++m) acc += l[m] * __shfl_sync(0xffffffffu, xv, wr + 8 * m);
     }
     sred[wr][lane] = acc;
-    wait_flags<0, kThreads>(a.diag_ready + c, 1, RD(nb, c), 1, a.abort, a.fail_flag, tid == 0);   // also the barrier for sred
-    load_tile<kThreads>(sbuf[0], A, g, c, c, tid, true);
     __syncthreads();
+    // ---- phase C: x_c = L_cc^-T (y_c - s)
     if (warp == 0) {
-      double v = lane < kb ? __ldcg(A + (int64_t)g.n * g.n + c0 + lane) : 0.0;
+      double v = yv;
 #pragma unroll
       for (int m = 0; m < kWarps; ++m) v -= sred[m][lane];
-      const double rdv = 1.0 / (lane < kb ? sbuf[0][lane][lane] : 1.0);
-      for (int jj = kb - 1; jj >= 0; --jj) {
-        const double xj = __shfl_sync(0xffffffffu, v, jj) * __shfl_sync(0xffffffffu, rdv, jj);
-        if (lane == jj) v = xj;
-        else if (lane < jj) v -= sbuf[0][jj][lane] * xj;
+      double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+      for (int q = 0; q < TB; q += 4) {
+        x0 += sbuf[1][lane][q] * __shfl_sync(0xffffffffu, v, q);
+        x1 += sbuf[1][lane][q + 1] * __shfl_sync(0xffffffffu, v, q + 1);
+        x2 += sbuf[1][lane][q + 2] * __shfl_sync(0xffffffffu, v, q + 2);
+        x3 += sbuf[1][lane][q + 3] * __shfl_sync(0xffffffffu, v, q + 3);
       }
-      if (lane < kb) __stcg(a.x + c0 + lane, v);
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) st_release(a.xready + c, 1);
+      if (lane < kb) st_relaxed_f64(a.x + c0 + lane, (x0 + x1) + (x2 + x3));
       if (a.trace && lane == 0) a.trace[(int64_t)nb * 8 + 8 + c] = gtime();   // x_c published
     }
     __syncthreads();

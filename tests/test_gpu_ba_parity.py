@@ -145,10 +145,11 @@ def test_inner_iterations_kernel_matches_oracle_points(monolithic, monkeypatch):
 def test_unsupported_channels_raise_value_error():
     prob, gt, ic = _scene(channels=16, n_points=10)
     bad = prob.copy()
-    bad.patches = np.ascontiguousarray(prob.patches[..., :3])
+    # 1/3/4 (cost maps) and 8..256 are built; anything else is refused like feature_reference_bundle_optimizer.h:12-18
+    bad.patches = np.ascontiguousarray(prob.patches[..., :5])
     bad._patches_ptr = bad.patches.ctypes.data
-    bad.channels = 3
-    bad.refs = np.ascontiguousarray(prob.refs[:, :3])
+    bad.channels = 5
+    bad.refs = np.ascontiguousarray(prob.refs[:, :5])
     with pytest.raises(ValueError):
         _engine.BAHandle(bad, ic, _capi.default_ba_options())
 
