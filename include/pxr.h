@@ -159,7 +159,7 @@ typedef struct {
    * concatenation: featuremap.cc:38-44 keeps references to the arrays).  When n_patch_blocks > 0,
    * `patches` is ignored and patch index i lives in the block b with offsets[b] <= i < offsets[b+1]. */
   int32_t n_patch_blocks;
-  const void* const* patch_block_ptrs;   /* [n_patch_blocks] */
+  const void* const* patch_block_ptrs;   /* [n_patch_blocks]; each block may be host OR device memory */
   const int64_t* patch_block_counts;     /* [n_patch_blocks] patches per block */
 } pxr_ba_desc;
 

@@ -69,6 +69,11 @@ struct BA {
   DevBuf<double> cam[2], q[2], t[2], X[2];
   int cur = 0;
   // device: per-observation and linearisation
+  // uv/obs_out/juv hold the linearisation at the CURRENT point; every trial-point evaluation (cost-only,
+  // speculative Jacobian, inner iterations) runs on the *_alt set (swap_sets()) so a rejected step never
+  // clobbers what the next compute_step reads.
+  DevBuf<double> uv_alt, obs_out_alt, juv_alt;
+  void swap_sets() { std::swap(uv.p, uv_alt.p); std::swap(uv.n, uv_alt.n); std::swap(obs_out.p, obs_out_alt.p); std::swap(obs_out.n, obs_out_alt.n); std::swap(juv.p, juv_alt.p); std::swap(juv.n, juv_alt.n); }
   DevBuf<double> uv, obs_out, juv, Hcc, gc, Hpp, gp, W, S, rhs, diag, jscale, D2, delta, partials, scalars;
   DevBuf<int> flags;
   DevBuf<double> rdiag;
@@ -82,6 +87,8 @@ struct BA {
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
   bool chol_multikernel = false; int chol_grid = 0;
+  DevBuf<int32_t> io_obs;           // observations grouped by image, chunks of <= 128 (camera-block build)
+  DevBuf<int64_t> io_chunk_begin; int64_t io_n_chunks = 0;
   DevBuf<long long> chol_trace;     // PXR_CHOL_TRACE=<file>: panel-CTA time stamps
   DevBuf<int> chol_sync;            // flags of the persistent tile-DAG Cholesky (pxr_chol.cuh)
   ~BA() { if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }

@@ -65,7 +65,7 @@ __device__ __forceinline__ int obs_local_columns(const BADev& d, int64_t o, cons
 // K2: one thread per observation.  W_o = J_c^T A' J_p, camera blocks J_c^T A' J_c / J_c^T b' into
 // the dense Hcc (lower triangle) / gc and the point blocks Hpp / gp, all with fp64 atomics
 // (Hpp/gp/Hcc/gc are zeroed by the caller).
-static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d) {
+static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d, int cam_blocks) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= d.n_obs) return;
   const int64_t p = d.obs_pt[o];
@@ -103,10 +103,71 @@ static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d) {
       Wo[a * 3 + 1] = Ju[a] * apu[1] + Jv[a] * apv[1];
       Wo[a * 3 + 2] = Ju[a] * apu[2] + Jv[a] * apv[2];
     }
+    if (!cam_blocks) continue;   // the per-image chunk kernel below accumulates Hcc / gc
     const double aju = auu * Ju[a] + auv * Jv[a], ajv = auv * Ju[a] + avv * Jv[a];
     atomic_add_f64(&d.gc[cols[a]], Ju[a] * bu + Jv[a] * bv);
     for (int b = 0; b <= a; ++b)  // cols ascending within an observation -> lower triangle
       atomic_add_f64(&d.Hcc[(int64_t)cols[a] * d.nc + cols[b]], Ju[b] * aju + Jv[b] * ajv);
+  }
+}
+
+// K2c: camera blocks without per-observation atomics.  Observations are listed per image in chunks of
+// <= 128 (all observations of an image share their parameter columns); one warp per chunk accumulates
+// J_c^T A' J_c (lower triangle, 36 values for dc <= 8) and J_c^T b' (8) in registers, reduces them across
+// the warp with the transposed butterfly (9 double shuffles per 8 values) and issues ONE atomic per
+// element per chunk: 128x fewer L2 atomics than ba_build_kernel's camera part.  Used when dcmax <= 8.
+static __global__ void __launch_bounds__(256) ba_build_cam_kernel(BADev d, const int32_t* __restrict__ io_obs,
+                                                                  const int64_t* __restrict__ chunk_begin, int64_t n_chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (chunk >= n_chunks) return;
+  const int64_t beg = chunk_begin[chunk], end = chunk_begin[chunk + 1];
+  const int Wd = 9 + d.K;
+  double acc[48];
+#pragma unroll
+  for (int k = 0; k < 48; ++k) acc[k] = 0.0;
+  int cols[kMaxDc];
+  int dc = 0;
+  for (int64_t e = beg + lane; e < end; e += 32) {
+    const int64_t o = io_obs[e];
+    const double* oo = d.obs_out + o * 8;
+    double rho[3];
+    loss_eval(d.loss, 1.0, oo[0], rho);
+    const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
+    const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
+    const double* J = d.juv + o * (int64_t)d.juv_stride;
+    double Ju[kMaxDc], Jv[kMaxDc];
+    dc = obs_local_columns(d, o, J, Wd, cols, Ju, Jv);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      if (a < dc) {
+        const double aju = auu * Ju[a] + auv * Jv[a], ajv = auv * Ju[a] + avv * Jv[a];
+        acc[36 + a] += Ju[a] * bu + Jv[a] * bv;
+#pragma unroll
+        for (int b = 0; b <= a; ++b)
+          if (b < dc) acc[a * (a + 1) / 2 + b] += Ju[b] * aju + Jv[b] * ajv;
+      }
+    }
+  }
+  // the chunk's columns: every observation of the image has the same ones; lane 0 always has an observation
+  dc = __shfl_sync(0xffffffffu, dc, 0);
+#pragma unroll
+  for (int a = 0; a < 8; ++a) cols[a] = __shfl_sync(0xffffffffu, cols[a], 0);
+  const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+  for (int gsel = 0; gsel < 6; ++gsel) {
+    const double tot = warp_reduce8_transposed(acc + gsel * 8, lane);
+    if ((lane & 3) != 0) continue;
+    const int vi = gsel * 8 + idx;
+    if (vi < 36) {
+      int a = 0;
+      while ((a + 1) * (a + 2) / 2 <= vi) ++a;
+      const int b = vi - a * (a + 1) / 2;
+      if (a < dc) atomic_add_f64(&d.Hcc[(int64_t)cols[a] * d.nc + cols[b]], tot);
+    } else if (vi < 44) {
+      const int a = vi - 36;
+      if (a < dc) atomic_add_f64(&d.gc[cols[a]], tot);
+    }
   }
 }
 

@@ -213,7 +213,9 @@ class BAProblem:
                 if b.dtype not in DTYPE_IDS or not b.flags["C_CONTIGUOUS"] or b.ndim != 4 or b.shape[1:] != blocks[0].shape[1:]:
                     raise ValueError("patch blocks must be C-contiguous [N,H,W,C] arrays of one dtype/shape")
             self.patch_blocks = blocks
-            self._block_ptrs = (C.c_void_p * len(blocks))(*[b.ctypes.data for b in blocks])
+            # host numpy blocks and device-resident blocks (anything with .ptr, e.g. _features.DevicePatches) can be
+            # mixed: the library copies with cudaMemcpyDefault
+            self._block_ptrs = (C.c_void_p * len(blocks))(*[getattr(b, "ptr", None) or b.ctypes.data for b in blocks])
             self._block_counts = np.array([b.shape[0] for b in blocks], np.int64)
             self.patches = None
             self._patches_ptr = blocks[0].ctypes.data

@@ -7,6 +7,35 @@ import numpy as np
 kDenseId = 1000000  # util/src/types.h:33
 
 
+class DevicePatches:
+    """A [N,H,W,C] patch array that already lives in device memory (the features come out of
+    the CNN on the GPU; the reference moves them GPU -> numpy -> FeatureMap and flags that round trip as its
+    bottleneck, features/extractor.py:152-236, extract_patches.py:41).  Wraps anything with the CUDA array
+    interface (a contiguous torch.cuda tensor, a cupy array): the optimizers copy it device-to-device into their
+    slab, nothing crosses PCIe.  Keeps the owner alive."""
+
+    _TYPESTR = {"<f2": np.float16, "<f4": np.float32, "<f8": np.float64}
+
+    def __init__(self, owner):
+        cai = getattr(owner, "__cuda_array_interface__", None)
+        if cai is None:
+            raise ValueError("object does not expose __cuda_array_interface__")
+        if cai.get("strides") is not None:
+            raise ValueError("device patches must be C-contiguous")
+        if cai["typestr"] not in self._TYPESTR:
+            raise ValueError("device patches must be float16/float32/float64")
+        self.owner = owner
+        self.shape = tuple(int(v) for v in cai["shape"])
+        self.ndim = len(self.shape)
+        self.dtype = np.dtype(self._TYPESTR[cai["typestr"]])
+        self.ptr = int(cai["data"][0])
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.flags = {"C_CONTIGUOUS": True}
+
+    def __len__(self):
+        return self.shape[0]
+
+
 class FeaturePatch:
     def __init__(self, data, corner, scale, upsampling_factor=1.0):
         self.data = data  # [H,W,C] view
@@ -38,7 +67,10 @@ class FeatureMap:
     """FeatureMap(patches[N,H,W,C] C-contiguous, point2D_ids, corners[N,2] (x,y) int32, metadata{"scale","is_sparse"})"""
 
     def __init__(self, patches, point2D_ids, corners, metadata):
-        patches = np.asarray(patches)
+        if hasattr(patches, "__cuda_array_interface__"):
+            patches = DevicePatches(patches)        # stays on the device
+        elif not isinstance(patches, DevicePatches):
+            patches = np.asarray(patches)
         if patches.ndim != 4 or not patches.flags["C_CONTIGUOUS"]:
             raise ValueError("patches must be a C-contiguous [N,H,W,C] array")
         if patches.dtype not in (np.float16, np.float32, np.float64):
@@ -77,6 +109,8 @@ class FeatureMap:
 
     def fpatch(self, point2D_idx):
         k = self.local_index(point2D_idx)
+        if isinstance(self.patches, DevicePatches):
+            raise ValueError("patch data is device-resident; host views are not available")
         return FeaturePatch(self.patches[k], self.corners[k], self.scale)
 
 
