@@ -343,6 +343,11 @@ typedef struct {
   double upsampling_factor;
   double bound;                 /* KeypointOptimizerOptions::bound, 4.0 from python */
   int32_t patches_are_sparse;   /* FeatureMap::IsSparse() */
+  /* optional: patches given as blocks (one per FeatureMap numpy array, featuremap.cc:38-44) that are laid out
+   * back to back on the device, as in pxr_ba_desc; each block may be host OR device memory */
+  int32_t n_patch_blocks;
+  const void* const* patch_block_ptrs;
+  const int64_t* patch_block_counts;
 } pxr_ka_desc;
 
 int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* desc, const pxr_interp_config* interp,

@@ -22,7 +22,14 @@ inline Patch MakeKAPatch(const pxr_ka_desc& d, int64_t kp) {
   const int64_t pi = d.kp_patch ? d.kp_patch[kp] : kp;
   Patch p;
   const size_t esz = d.patch_dtype == PXR_F16 ? 2 : (d.patch_dtype == PXR_F32 ? 4 : 8);
-  p.data = (const char*)d.patches + (size_t)pi * d.ph * d.pw * d.channels * esz;
+  if (d.n_patch_blocks > 0) {   // host blocks laid out back to back (device blocks are not readable here)
+    int64_t local = pi;
+    int b = 0;
+    while (b < d.n_patch_blocks - 1 && local >= d.patch_block_counts[b]) { local -= d.patch_block_counts[b]; ++b; }
+    p.data = (const char*)d.patch_block_ptrs[b] + (size_t)local * d.ph * d.pw * d.channels * esz;
+  } else {
+    p.data = (const char*)d.patches + (size_t)pi * d.ph * d.pw * d.channels * esz;
+  }
   p.dtype = d.patch_dtype; p.h = d.ph; p.w = d.pw; p.c = d.channels;
   p.corner[0] = d.corner[2 * pi]; p.corner[1] = d.corner[2 * pi + 1];
   p.scale[0] = d.scale[2 * pi]; p.scale[1] = d.scale[2 * pi + 1];

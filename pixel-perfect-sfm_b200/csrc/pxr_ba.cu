@@ -413,11 +413,16 @@ int BA::build() {
   if (n_obs > 0) PXR_LAUNCH(ctx, ba_build_kernel, (unsigned)cdiv(n_obs, 128), 128, 0, dev(), chunked ? 0 : 1);
   if (n_obs > 0 && chunked)
     PXR_LAUNCH(ctx, ba_build_cam_kernel, (unsigned)cdiv(io_n_chunks * 32, 256), 256, 0, dev(), io_obs.p, io_chunk_begin.p, io_n_chunks);
-  // multi-GPU: camera blocks and gradient are sums over all ranks' observations
-  PXR_TRY(allreduce_f64(ctx, Hcc.p, (size_t)nc * nc));
-  PXR_TRY(allreduce_f64(ctx, gc.p, nc));
   const int64_t n = std::max<int64_t>(nc, n_points);
   if (n > 0) PXR_LAUNCH(ctx, ba_diag_kernel, (unsigned)cdiv(n, 256), 256, 0, dev(), diag.p);
+  if (ctx->world > 1 && nc > 0) {
+    // multi-GPU: Hcc stays a per-rank partial sum (it only ever enters the reduced system, which is all-reduced
+    // anyway); globally needed are its diagonal (Jacobi scaling / LM damping) and the gradient
+    if (!gc_local.p) PXR_TRY(gc_local.alloc(nc));
+    PXR_CUDA(cudaMemcpyAsync(gc_local.p, gc.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    PXR_TRY(allreduce_f64(ctx, diag.p, nc));
+    PXR_TRY(allreduce_f64(ctx, gc.p, nc));
+  }
   PXR_CUDA(cudaGetLastError());
   return PXR_OK;
 }
@@ -431,26 +436,21 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   if (nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, D2.p, nl, radius,
                          opt.min_lm_diagonal, opt.max_lm_diagonal);
   PXR_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), s));
-  if (ctx->world <= 1) {
-    if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p, gc.p, D2.p, S.p, rhs.p, nc);
-  } else {
-    // Schur contributions are per-rank partial sums: accumulate them in a zeroed buffer, allreduce,
-    // then add the (already global) damped Hcc.  One NCCL allreduce of [S | rhs] per LM attempt.
-    PXR_CUDA(cudaMemsetAsync(S.p, 0, (size_t)nc * nc * 8, s));
-    PXR_CUDA(cudaMemsetAsync(rhs.p, 0, (size_t)nc * 8, s));
-  }
+  // multi-GPU: every rank starts from ITS partial Hcc / gc (rank 0 adds the damping), subtracts its points' Schur
+  // contributions, and ONE all-reduce of [S | rhs] (rhs is row nc of the same array) yields the reduced system
+  if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p,
+                         ctx->world > 1 ? gc_local.p : gc.p, D2.p, S.p, rhs.p, nc, (ctx->world <= 1 || ctx->rank == 0) ? 1 : 0);
   if (n_points > 0) {
     PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, D2.p, Tbuf.p, rhs.p, flags.p);
     if (sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, 256), 256, 0, d, schur_pairs(), Tbuf.p, S.p);
   }
-  if (ctx->world > 1) {
-    PXR_TRY(allreduce_f64(ctx, S.p, (size_t)nc * nc));
-    PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
-    PXR_LAUNCH(ctx, ba_add_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p, gc.p, D2.p, S.p, rhs.p, nc);
-  }
-  delete st; st = new StageScope(this, 5);
   // rhs rides along as row nc of S: the factorisation performs the forward substitution
   if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
+  if (ctx->world > 1 && nc > 0) {
+    PXR_TRY(allreduce_f64(ctx, S.p, (size_t)(nc + 1) * nc));
+    PXR_CUDA(cudaMemcpyAsync(rhs.p, S.p + (size_t)nc * nc, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));   // PCG / debug read rhs
+  }
+  delete st; st = new StageScope(this, 5);
   last_linear_iterations = 1;
   if (nc > 0 && use_pcg) {
     PXR_TRY(pcg_solve());
@@ -521,15 +521,15 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
   if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p);
   if (n_obs > 0) PXR_LAUNCH(ctx, ba_model_cost_kernel, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
-  PXR_TRY(allreduce_f64(ctx, scalars.p + 4, 1));
   PXR_CUDA(cudaGetLastError());
   delete st;
   double acc = 0, fld = 0;
-  PXR_LAUNCH(ctx, flags_to_double_kernel, 1, 1, 0, flags.p, scalars.p + 13);
-  PXR_TRY(allreduce_f64(ctx, scalars.p + 13, 1));  // every rank must take the same branch
-  PXR_CUDA(cudaMemcpyAsync(&acc, scalars.p + 4, 8, cudaMemcpyDeviceToHost, s));
-  PXR_CUDA(cudaMemcpyAsync(&fld, scalars.p + 13, 8, cudaMemcpyDeviceToHost, s));
+  PXR_LAUNCH(ctx, flags_to_double_kernel, 1, 1, 0, flags.p, scalars.p + 5);
+  PXR_TRY(allreduce_f64(ctx, scalars.p + 4, 2));   // model cost change + failure flag: every rank takes the same branch
+  double two[2] = {0, 0};
+  PXR_CUDA(cudaMemcpyAsync(two, scalars.p + 4, 16, cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaStreamSynchronize(s));
+  acc = two[0]; fld = two[1];
   const bool solved = fld == 0.0 && std::isfinite(acc);
   *model_cost_change = -acc;
   *valid = solved && (*model_cost_change > 0.0);
@@ -1025,7 +1025,7 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
     BADev d = b->dev();
     if (b->nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(b->nl, 256), 256, 0, b->diag.p, b->jscale.p, b->D2.p, b->nl, radius,
                               b->opt.min_lm_diagonal, b->opt.max_lm_diagonal);
-    if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, b->Hcc.p, b->gc.p, b->D2.p, b->S.p, b->rhs.p, (int)nc);
+    if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, b->Hcc.p, b->gc.p, b->D2.p, b->S.p, b->rhs.p, (int)nc, 1);
     PXR_CUDA(cudaMemsetAsync(b->flags.p, 0, 4 * sizeof(int), s));
     if (b->n_points > 0) {
       PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_obs * b->dcmax, 256), 256, 0, d, b->D2.p, b->Tbuf.p, b->rhs.p, b->flags.p);

@@ -197,14 +197,15 @@ static __global__ void ba_d2_kernel(const double* diag, const double* scale, dou
 }
 
 // S = Hcc + diag(D2c) (lower), rhs = -gc
+// (multi-GPU: Hcc / gc are this rank's partial sums and only rank 0 adds the damping, add_d2)
 static __global__ void ba_init_reduced_kernel(const double* Hcc, const double* gc, const double* D2, double* S,
-                                       double* rhs, int nc) {
+                                       double* rhs, int nc, int add_d2) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n2 = (int64_t)nc * nc;
   if (i < n2) {
     const int r = (int)(i / nc), c = (int)(i % nc);
     double v = c <= r ? Hcc[i] : 0.0;
-    if (r == c) v += D2[r];
+    if (r == c && add_d2) v += D2[r];
     S[i] = v;
   }
   if (i < nc) rhs[i] = -gc[i];

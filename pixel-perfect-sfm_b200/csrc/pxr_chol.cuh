@@ -164,10 +164,14 @@ __device__ __forceinline__ void store_tile(double (*src)[TB + 1], double* A, con
 // instruction stream (400 instructions per column with a rotating window, or 10k straight-line
 // instructions = 160 KB of i-cache when fully unrolled): ~20 us per tile against a ~2.5 us dependency
 // chain (32 x [shuffle, rsqrt, multiply, shuffle, fma]).
-template <class PrefetchFn>
-__device__ __forceinline__ bool factor_diag_cta(double (*a)[TB + 1], double* rd, int kb, int tid, PrefetchFn prefetch) {
+template <class TryPrefetchFn>
+__device__ __forceinline__ bool factor_diag_cta(double (*a)[TB + 1], double* rd, int kb, int tid, TryPrefetchFn try_prefetch) {
+  // While warp 0 factors an 8-column panel, warps 1..7 call try_prefetch(blocking=false): one non-blocking look
+  // at the flags per panel, the tile loads (224 threads) as soon as they are up.  A late flag therefore overlaps
+  // the whole factorisation; only what is still missing at the end is waited for (blocking=true).
   const int warp = tid >> 5, lane = tid & 31;
   bool ok = true;
+  bool loaded = false;                               // uniform over warps 1..7
   if (tid >= kb && tid < TB) a[tid][tid] = 1.0;      // identity padding of a ragged last tile (loads zero-fill it)
   __syncthreads();
 #pragma unroll 1
@@ -195,8 +199,8 @@ __device__ __forceinline__ bool factor_diag_cta(double (*a)[TB + 1], double* rd,
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c) a[lane][j0 + c] = (lane >= j0 + c) ? r[c] : 0.0;
-    } else if (jb == 0) {
-      prefetch();
+    } else if (!loaded) {
+      loaded = try_prefetch(false);
     }
     __syncthreads();
     const int n0 = j0 + 8, m = TB - n0;              // trailing m x m block (lower part)
@@ -211,6 +215,8 @@ __device__ __forceinline__ bool factor_diag_cta(double (*a)[TB + 1], double* rd,
     }
     __syncthreads();
   }
+  if (warp != 0 && !loaded) try_prefetch(true);
+  __syncthreads();
   return ok;
 }
 
@@ -254,6 +260,7 @@ static __global__ void __launch_bounds__(kThreads, 2) chol_persistent_kernel(Arg
   __shared__ double sx[TB];
   __shared__ double sred[kWarps][TB];
   __shared__ int s_ok;
+  __shared__ int s_pf;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo g{a.n, a.nb};
   const int nb = a.nb;
@@ -272,15 +279,31 @@ static __global__ void __launch_bounds__(kThreads, 2) chol_persistent_kernel(Arg
       PXR_CHOL_STAMP(0);
       {
         // tiles (k+1,k) and (k+1,k+1) — the owners have applied panels 0..k-1 — land while warp 0 factors
-        auto prefetch = [&]() {
+        auto try_prefetch = [&](bool blocking) -> bool {   // warps 1..7 (224 threads, named barrier 1)
           constexpr int NT = kThreads - 32;
           const int t2 = tid - 32;
-          wait_flags<1, NT>(UP(k + 1, k), k, (k + 1 < nb) ? UP(k + 1, k + 1) : nullptr, k, a.abort, a.fail_flag, t2 == 0);
-          if (a.trace && t2 == 0) a.trace[(int64_t)k * 8 + 6] = gtime();
-          load_tile<NT>(sbuf[ib], A, g, k + 1, k, t2);
-          if (k + 1 < nb) load_tile<NT>(sbuf[ic], A, g, k + 1, k + 1, t2, true);
+          if (t2 == 0) {
+            if (blocking) {
+              spin_until(UP(k + 1, k), k, a.abort, a.fail_flag);
+              if (k + 1 < nb) spin_until(UP(k + 1, k + 1), k, a.abort, a.fail_flag);
+              s_pf = 1;
+            } else {
+              const int f0 = ld_acquire(UP(k + 1, k));
+              const int f1 = (k + 1 < nb) ? ld_acquire(UP(k + 1, k + 1)) : k;
+              s_pf = (f0 >= k && f1 >= k) ? 1 : 0;
+            }
+            if (s_pf && a.trace) a.trace[(int64_t)k * 8 + 6] = gtime();
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+          const bool up = s_pf != 0;
+          if (up) {
+            load_tile<NT>(sbuf[ib], A, g, k + 1, k, t2);
+            if (k + 1 < nb) load_tile<NT>(sbuf[ic], A, g, k + 1, k + 1, t2, true);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");   // s_pf may be rewritten by the next attempt
+          return up;
         };
-        const bool ok = factor_diag_cta(sbuf[ia], srd, kb, tid, prefetch);
+        const bool ok = factor_diag_cta(sbuf[ia], srd, kb, tid, try_prefetch);
         if (!ok && tid == 0) *a.fail_flag = 1;
         PXR_CHOL_STAMP(1);
       }
@@ -305,69 +328,114 @@ static __global__ void __launch_bounds__(kThreads, 2) chol_persistent_kernel(Arg
     }
   } else if (W > 0) {
     // ------------------------------------------------------------------ workers
+    // Per stage k a worker runs, for the tiles it owns:
+    //   F   finish the deferred ("bulk") updates that column k+1 still waits for
+    //   A   panel k-1 -> columns k and k+1      (what the panel CTA and the solves of stage k need next)
+    //   B   bulk updates (panel p -> columns >= p+3, oldest first), one tile at a time, until diag_ready[k]
+    //   C   solve its tiles of column k against L_kk, publish them
+    // so the latency-critical work never queues behind the O(n^2) trailing updates, which are pre-emptible
+    // at tile granularity and may lag by one panel.  Per tile the panels still arrive in increasing order
+    // (bulk p <= j-3 is forced before A applies p = j-2), which keeps `upd` a prefix count.
     const int w = (int)blockIdx.x - 1;
     const int64_t total = g.off(nb);                 // number of tiles
     double (*sK)[TB + 1] = sbuf[0];
     double (*sI)[TB + 1] = sbuf[1];
     double (*sJ)[TB + 1] = sbuf[2];
+    __shared__ int s_poll[2];
     const int ty = tid >> 4, tx = tid & 15;
+    auto first_tile = [&](int j) -> int64_t { const int64_t o = g.off(j); return o + ((w - o) % W + W) % W; };
+
+    // tile (i, j) -= L_ip L_jp^T
+    auto do_update = [&](int i, int j, int p) {
+      const int r0 = g.row0(i), nr = g.rows(i), c0 = j * TB, ncl = g.cols(j);
+      double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+      const bool v0 = ty < nr, v1 = ty + 16 < nr, u0 = tx < ncl, u1 = tx + 16 < ncl;
+      double* p0 = A + (int64_t)(r0 + ty) * g.n + c0 + tx;
+      double* p1 = p0 + (int64_t)16 * g.n;
+      // the tile itself is owned (no flag): read-modify-write straight from global, 2x2 per thread
+      if (v0 && u0) c00 = __ldcg(p0);
+      if (v0 && u1) c01 = __ldcg(p0 + 16);
+      if (v1 && u0) c10 = __ldcg(p1);
+      if (v1 && u1) c11 = __ldcg(p1 + 16);
+      wait_flags<0, kThreads>(RD(i, p), 1, (i != j) ? RD(j, p) : nullptr, 1, a.abort, a.fail_flag, tid == 0);
+      load_tile<kThreads>(sI, A, g, i, p, tid);
+      if (i != j) load_tile<kThreads>(sJ, A, g, j, p, tid);
+      __syncthreads();
+      double (*lj)[TB + 1] = (i != j) ? sJ : sI;
+#pragma unroll 8
+      for (int q = 0; q < TB; ++q) {
+        const double a0 = sI[ty][q], a1 = sI[ty + 16][q], b0 = lj[tx][q], b1 = lj[tx + 16][q];
+        c00 -= a0 * b0; c01 -= a0 * b1; c10 -= a1 * b0; c11 -= a1 * b1;
+      }
+      if (v0 && u0) __stcg(p0, c00);
+      if (v0 && u1) __stcg(p0 + 16, c01);
+      if (v1 && u0) __stcg(p1, c10);
+      if (v1 && u1) __stcg(p1 + 16, c11);
+      const bool watched = (i == j) || (i == j + 1);
+      __syncthreads();                                // sI/sJ free again; orders the tile stores before the release
+      if (watched && tid == 0) st_release(UP(i, j), p + 1);
+    };
+
+    // bulk cursor: panel bp, my next tile bt (column bj), columns >= bp + 3
+    int bp = 0, bj = 3;
+    int64_t bt = (3 < nb) ? first_tile(3) : total;
+    auto bulk_has = [&](int limit_p) -> bool {        // a deferred tile of a panel <= limit_p is left
+      while (bp <= limit_p && bt >= total) { ++bp; bj = bp + 3; bt = (bj < nb) ? first_tile(bj) : total; }
+      return bp <= limit_p;
+    };
+    auto bulk_col = [&]() -> int { while (bt >= g.off(bj + 1)) ++bj; return bj; };
+    auto bulk_step = [&]() {
+      const int j = bulk_col();
+      do_update(j + (int)(bt - g.off(j)), j, bp);
+      bt += W;
+    };
+
     for (int k = 0; k < nb; ++k) {
       const int kb = g.cols(k);
-      const int64_t o = g.off(k);
-      int64_t t = o + ((w - o) % W + W) % W;         // smallest owned tile index >= off(k)
-      int j = k;
+      // F: everything deferred that column k+1 (and older) still needs: bulk through (panel k-2, column k+1)
+      while (bulk_has(k - 2)) {
+        if (bp == k - 2 && bulk_col() > k + 1) break;
+        bulk_step();
+      }
+      // A: panel k-1 -> columns k, k+1
+      if (k >= 1) {
+        for (int j = k; j <= k + 1 && j < nb; ++j)
+          for (int64_t t = first_tile(j); t < g.off(j + 1); t += W) {
+            const int i = j + (int)(t - g.off(j));
+            if (i == j && j == k) continue;           // (k,k) -= L_{k,k-1} L_{k,k-1}^T is the panel CTA's
+            do_update(i, j, k - 1);
+          }
+      }
+      // B: deferred updates until L_kk is there; one look at the flag per tile, so the solves below start at
+      // most one tile (~2.5 us) after diag_ready[k]
+      while (bulk_has(k - 1)) {
+        if (tid == 0) s_poll[0] = ld_acquire(a.diag_ready + k);
+        __syncthreads();
+        if (s_poll[0] != 0) break;
+        bulk_step();                                  // its barriers separate this read of s_poll from the next write
+      }
+      // C: solves of column k
       bool have_lkk = false;
-      for (; t < total; t += W) {
-        while (t >= g.off(j + 1)) ++j;
-        const int i = j + (int)(t - g.off(j));
-        if (j == k) {
-          if (i < k + 2) continue;
-          load_tile<kThreads>(sI, A, g, i, k, tid);  // own tile (all its updates are this CTA's): no flag needed
-          if (!have_lkk) {
-            wait_flags<0, kThreads>(a.diag_ready + k, 1, nullptr, 0, a.abort, a.fail_flag, tid == 0);
-            load_tile<kThreads>(sK, A, g, k, k, tid, true);
-            __syncthreads();
-            if (tid < TB) srd[tid] = 1.0 / (tid < kb ? sK[tid][tid] : 1.0);
-            have_lkk = true;
-          }
+      for (int64_t t = first_tile(k); t < g.off(k + 1); t += W) {
+        const int i = k + (int)(t - g.off(k));
+        if (i < k + 2) continue;                      // diagonal and sub-diagonal tile: panel CTA
+        load_tile<kThreads>(sI, A, g, i, k, tid);    // own tile (all its updates are this CTA's): no flag needed
+        if (!have_lkk) {
+          wait_flags<0, kThreads>(a.diag_ready + k, 1, nullptr, 0, a.abort, a.fail_flag, tid == 0);
+          load_tile<kThreads>(sK, A, g, k, k, tid, true);
           __syncthreads();
-          solve_rows<kWarps>(sI, sK, srd, kb, warp, lane);
-          __syncthreads();
-          store_tile<kThreads>(sI, A, g, i, k, tid);
-          __syncthreads();
-          if (tid == 0) st_release(RD(i, k), 1);
-        } else {
-          if (i == j && k == j - 1) continue;        // the panel CTA applies this one itself
-          // the tile itself (owned: no flag), read-modify-write straight from global, 2x2 per thread
-          const int r0 = g.row0(i), nr = g.rows(i), c0 = j * TB, ncl = g.cols(j);
-          double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-          const bool v0 = ty < nr, v1 = ty + 16 < nr, u0 = tx < ncl, u1 = tx + 16 < ncl;
-          double* p0 = A + (int64_t)(r0 + ty) * g.n + c0 + tx;
-          double* p1 = p0 + (int64_t)16 * g.n;
-          if (v0 && u0) c00 = __ldcg(p0);
-          if (v0 && u1) c01 = __ldcg(p0 + 16);
-          if (v1 && u0) c10 = __ldcg(p1);
-          if (v1 && u1) c11 = __ldcg(p1 + 16);
-          wait_flags<0, kThreads>(RD(i, k), 1, (i != j) ? RD(j, k) : nullptr, 1, a.abort, a.fail_flag, tid == 0);
-          load_tile<kThreads>(sI, A, g, i, k, tid);
-          if (i != j) load_tile<kThreads>(sJ, A, g, j, k, tid);
-          __syncthreads();
-          double (*lj)[TB + 1] = (i != j) ? sJ : sI;
-#pragma unroll 8
-          for (int q = 0; q < TB; ++q) {
-            const double a0 = sI[ty][q], a1 = sI[ty + 16][q], b0 = lj[tx][q], b1 = lj[tx + 16][q];
-            c00 -= a0 * b0; c01 -= a0 * b1; c10 -= a1 * b0; c11 -= a1 * b1;
-          }
-          if (v0 && u0) __stcg(p0, c00);
-          if (v0 && u1) __stcg(p0 + 16, c01);
-          if (v1 && u0) __stcg(p1, c10);
-          if (v1 && u1) __stcg(p1 + 16, c11);
-          const bool watched = (i == j) || (i == j + 1);
-          __syncthreads();                            // sI/sJ free again; orders the tile stores before the release below
-          if (watched && tid == 0) st_release(UP(i, j), k + 1);
+          if (tid < TB) srd[tid] = 1.0 / (tid < kb ? sK[tid][tid] : 1.0);
+          have_lkk = true;
         }
+        __syncthreads();
+        solve_rows<kWarps>(sI, sK, srd, kb, warp, lane);
+        __syncthreads();
+        store_tile<kThreads>(sI, A, g, i, k, tid);
+        __syncthreads();
+        if (tid == 0) st_release(RD(i, k), 1);
       }
     }
+    while (bulk_has(nb - 1)) bulk_step();            // nothing is left in a complete run; keeps the invariant explicit
   }
 
   // -------------------------------------------------------------------- back-substitution L^T x = y

@@ -535,7 +535,7 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
   const auto t0 = std::chrono::steady_clock::now();
   if (!ctx || !d) return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
   if (d->n_keypoints < 0 || d->n_edges < 0 || !d->keypoints || !d->kp_const || (d->n_edges && (!d->edge_src || !d->edge_dst)) ||
-      !d->patches || !d->corner || !d->scale || d->n_problems < 0)
+      (!d->patches && d->n_patch_blocks <= 0) || !d->corner || !d->scale || d->n_problems < 0)
     return fail(PXR_ERR_INVALID_ARGUMENT, "a required array is NULL");
   pxr_interp_config ic; if (interp_in) ic = *interp_in; else pxr_default_interp_config(&ic);
   pxr_solver_options so; if (opt_in) so = *opt_in; else pxr_default_ka_options(&so);
@@ -618,7 +618,25 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
   const size_t esz = d->patch_dtype == PXR_F16 ? 2 : (d->patch_dtype == PXR_F32 ? 4 : 8);
   const size_t pbytes = (size_t)n_patches * d->ph * d->pw * C * esz;
   const uint8_t* dp = nullptr;
-  if (d->patches_on_device) dp = (const uint8_t*)d->patches;
+  if (d->n_patch_blocks > 0) {
+    if (!d->patch_block_ptrs || !d->patch_block_counts) return fail(PXR_ERR_INVALID_ARGUMENT, "patch block arrays are NULL");
+    int64_t tot = 0;
+    for (int b = 0; b < d->n_patch_blocks; ++b) tot += d->patch_block_counts[b];
+    if (tot < n_patches) return fail(PXR_ERR_INVALID_ARGUMENT, "patch blocks hold %lld patches, %lld needed", (long long)tot, (long long)n_patches);
+    const size_t per = (size_t)d->ph * d->pw * C * esz;
+    PXR_TRY(d_patches.alloc((size_t)tot * per));
+    size_t off = 0;
+    for (int b = 0; b < d->n_patch_blocks; ++b) {
+      const size_t bytes = (size_t)d->patch_block_counts[b] * per;
+      if (bytes) PXR_CUDA(cudaMemcpyAsync(d_patches.p + off, d->patch_block_ptrs[b], bytes, cudaMemcpyDefault, s));
+      cudaPointerAttributes pa;
+      const bool on_dev = bytes && cudaPointerGetAttributes(&pa, d->patch_block_ptrs[b]) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+      cudaGetLastError();
+      if (!on_dev) h2d += (double)bytes;
+      off += bytes;
+    }
+    dp = d_patches.p;
+  } else if (d->patches_on_device) dp = (const uint8_t*)d->patches;
   else { PXR_TRY(d_patches.alloc(pbytes)); PXR_CUDA(cudaMemcpyAsync(d_patches.p, d->patches, pbytes, cudaMemcpyHostToDevice, s)); dp = d_patches.p; h2d += pbytes; }
   h2d += d->n_edges * 40.0 + d->n_keypoints * 24.0;
   KAArgs a;

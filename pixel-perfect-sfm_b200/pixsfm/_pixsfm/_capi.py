@@ -103,7 +103,8 @@ class KADesc(C.Structure):
                 ("patches_on_device", C.c_int32), ("patch_dtype", C.c_int32), ("ph", C.c_int32),
                 ("pw", C.c_int32), ("channels", C.c_int32), ("corner", C.c_void_p),
                 ("scale", C.c_void_p), ("upsampling_factor", C.c_double), ("bound", C.c_double),
-                ("patches_are_sparse", C.c_int32)]
+                ("patches_are_sparse", C.c_int32), ("n_patch_blocks", C.c_int32),
+                ("patch_block_ptrs", C.c_void_p), ("patch_block_counts", C.c_void_p)]
 
 
 def make_summary(capacity=256):
@@ -218,7 +219,7 @@ class BAProblem:
             self._block_ptrs = (C.c_void_p * len(blocks))(*[getattr(b, "ptr", None) or b.ctypes.data for b in blocks])
             self._block_counts = np.array([b.shape[0] for b in blocks], np.int64)
             self.patches = None
-            self._patches_ptr = blocks[0].ctypes.data
+            self._patches_ptr = getattr(blocks[0], "ptr", None) or blocks[0].ctypes.data
             self.n_patches = int(self._block_counts.sum())
             _, self.ph, self.pw, self.channels = blocks[0].shape
             self.patch_dtype = DTYPE_IDS[blocks[0].dtype]
@@ -383,7 +384,8 @@ class KAProblem:
     """numpy arrays of one keypoint-adjustment problem set + the ctypes view (pxr_ka_desc)."""
 
     def __init__(self, keypoints, kp_const, edge_src, edge_dst, edge_weight, edge_problem, n_problems, patches,
-                 corner, scale, kp_patch=None, bound=4.0, patches_are_sparse=True, upsampling_factor=1.0):
+                 corner, scale, kp_patch=None, bound=4.0, patches_are_sparse=True, upsampling_factor=1.0,
+                 patch_blocks=None):
         self.keypoints = _as(keypoints, np.float64, (-1, 2)).copy()
         self.kp_const = _as(kp_const, np.uint8)
         self.edge_src = _as(edge_src, np.int64)
@@ -393,8 +395,23 @@ class KAProblem:
         if len(self.edge_problem) > 1 and np.any(np.diff(self.edge_problem) < 0):
             raise ValueError("edges must be sorted by problem label")
         self.n_problems = int(n_problems)
-        if patches.dtype not in DTYPE_IDS or not patches.flags["C_CONTIGUOUS"] or patches.ndim != 4:
-            raise ValueError("patches must be a C-contiguous [N,H,W,C] f16/f32/f64 array")
+        self.patch_blocks = None
+        if patch_blocks is not None:
+            # one block per FeatureMap (host numpy or device-resident), uploaded without host concatenation
+            blocks = list(patch_blocks)
+            for b in blocks:
+                if b.dtype not in DTYPE_IDS or not b.flags["C_CONTIGUOUS"] or b.ndim != 4 or b.shape[1:] != blocks[0].shape[1:]:
+                    raise ValueError("patch blocks must be C-contiguous [N,H,W,C] arrays of one dtype/shape")
+            self.patch_blocks = blocks
+            self._block_ptrs = (C.c_void_p * len(blocks))(*[getattr(b, "ptr", None) or b.ctypes.data for b in blocks])
+            self._block_counts = np.array([b.shape[0] for b in blocks], np.int64)
+            patches = blocks[0]
+            self._shape = (int(self._block_counts.sum()),) + tuple(blocks[0].shape[1:])
+            self._dtype = np.dtype(blocks[0].dtype)
+        else:
+            if patches.dtype not in DTYPE_IDS or not patches.flags["C_CONTIGUOUS"] or patches.ndim != 4:
+                raise ValueError("patches must be a C-contiguous [N,H,W,C] f16/f32/f64 array")
+            self._shape, self._dtype = tuple(patches.shape), np.dtype(patches.dtype)
         self.patches = patches
         self.corner = _as(corner, np.int32, (-1, 2))
         self.scale = _as(scale, np.float64, (-1, 2))
@@ -405,7 +422,7 @@ class KAProblem:
 
     @property
     def channels(self):
-        return self.patches.shape[3]
+        return self._shape[3]
 
     def desc(self):
         d = KADesc()
@@ -415,10 +432,17 @@ class KAProblem:
         d.edge_src = _ptr(self.edge_src); d.edge_dst = _ptr(self.edge_dst)
         d.edge_weight = _ptr(self.edge_weight); d.edge_problem = _ptr(self.edge_problem)
         d.n_problems = self.n_problems
-        d.n_patches = self.patches.shape[0]
-        d.patches = _ptr(self.patches); d.patches_on_device = 0
-        d.patch_dtype = DTYPE_IDS[self.patches.dtype]
-        d.ph, d.pw, d.channels = self.patches.shape[1:]
+        d.n_patches = self._shape[0]
+        d.patches_on_device = 0
+        if self.patch_blocks is not None:
+            d.patches = None
+            d.n_patch_blocks = len(self.patch_blocks)
+            d.patch_block_ptrs = C.cast(self._block_ptrs, C.c_void_p)
+            d.patch_block_counts = _ptr(self._block_counts)
+        else:
+            d.patches = _ptr(self.patches)
+        d.patch_dtype = DTYPE_IDS[self._dtype]
+        d.ph, d.pw, d.channels = self._shape[1:]
         d.corner = _ptr(self.corner); d.scale = _ptr(self.scale)
         d.upsampling_factor = self.upsampling_factor
         d.bound = self.bound

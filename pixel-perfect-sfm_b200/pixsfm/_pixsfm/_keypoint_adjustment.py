@@ -108,14 +108,13 @@ class FeatureMetricKeypointOptimizer:
             kconst[kidx[n]] = 1 if self.setup.is_node_constant(graph.nodes[n]) else 0
             kpatch[kidx[n]] = slab.index(name, fmap, fidx)
         blocks, corners, scales = slab.arrays()
-        patches = blocks[0] if len(blocks) == 1 else np.concatenate(blocks)
         labels = sorted({problem_labels[e[0]] for e in flat})
         lmap = {l: k for k, l in enumerate(labels)}
         prob = _capi.KAProblem(keypoints=kps, kp_const=kconst, edge_src=[kidx[e[0]] for e in flat],
                                edge_dst=[kidx[e[1]] for e in flat], edge_weight=[e[2] for e in flat],
                                edge_problem=[lmap[problem_labels[e[0]]] for e in flat], n_problems=len(labels),
-                               patches=patches, corner=corners, scale=scales, kp_patch=kpatch, bound=opt.bound,
-                               patches_are_sparse=sparse)
+                               patches=None, corner=corners, scale=scales, kp_patch=kpatch, bound=opt.bound,
+                               patches_are_sparse=sparse, patch_blocks=blocks)
         if feature_set.channels not in (8, 16, 32, 64, 128):
             raise ValueError("Unsupported dimensions (CHANNELS,N_NODES).")
         so = solver_options_from(opt.loss, opt.solver, _capi.default_ka_options(parameter_tolerance=1e-4))

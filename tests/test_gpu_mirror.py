@@ -85,3 +85,30 @@ def test_keypoint_adjuster_refine_multilevel_moves_keypoints_towards_truth():
     for n in range(len(sc["node_image"])):
         flat[n] = keypoints[names[sc["node_image"][n]]][sc["node_feature"][n]]
     assert np.abs(flat - prob.keypoints).max() < 1e-9
+
+
+def test_device_resident_feature_maps_give_identical_results():
+    """FeatureMaps whose patches already live on the GPU (anything with
+    __cuda_array_interface__, e.g. the torch tensors the CNN produces) are consumed without a host round trip and
+    give the same results as the numpy path (up to the run-to-run order of the fp64 atomics in the block build)."""
+    torch = pytest.importorskip("torch")
+    rec, fm, _, gt = make_reconstruction(n_cams=6, n_points=50, track_len=4, channels=128, seed=31)
+    rec_dev = copy.deepcopy(rec)
+    keep = []   # the device tensors must outlive the FeatureMaps (they hold only the pointer's owner)
+    fm_dev = features.FeatureManager([128], np.float16)
+    for name in fm.fset(0).keys():
+        m = fm.fset(0).fmap(name)
+        t = torch.from_numpy(m.patches).cuda().contiguous()
+        keep.append(t)
+        fm_dev.fset(0).emplace(name, features.FeatureMap(t, m.point2D_ids, m.corners, {"scale": m.scale, "is_sparse": True}))
+        assert fm_dev.fset(0).fmap(name).patches.ptr == t.data_ptr()
+    conf = {"optimizer": {"solver": {"max_num_iterations": 8}}}
+    out_h = ba_pkg.BundleAdjuster.create(conf).refine_multilevel(rec, fm)
+    out_d = ba_pkg.BundleAdjuster.create(conf).refine_multilevel(rec_dev, fm_dev)
+    assert abs(out_d["summary"][0].final_cost - out_h["summary"][0].final_cost) <= 1e-12 * out_h["summary"][0].final_cost
+    assert out_d["summary"][0].h2d_bytes < 0.01 * out_h["summary"][0].h2d_bytes
+    for p in rec.points3D:
+        assert np.abs(rec.points3D[p].xyz - rec_dev.points3D[p].xyz).max() < 1e-10
+    # cost-map strategy on the device-resident maps too
+    out_c = ba_pkg.BundleAdjuster.create({"strategy": "costmaps", **conf}).refine_multilevel(copy.deepcopy(rec_dev), fm_dev)
+    assert out_c["summary"][0].final_cost < out_c["summary"][0].initial_cost
