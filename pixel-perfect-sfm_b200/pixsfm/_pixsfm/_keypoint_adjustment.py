@@ -37,13 +37,23 @@ class KeypointOptimizerOptions(_DictOptions):
                                      "max_num_iterations": 100, "max_num_consecutive_invalid_steps": 10})
 
 
+class TopologicalReferenceKeypointOptimizerOptions(KeypointOptimizerOptions):
+    """topological_reference_keypoint_optimizer.h:9-16: every keypoint of a track is pulled towards the track's root
+    only (linear instead of quadratic number of residuals)."""
+    _defaults = dict(KeypointOptimizerOptions._defaults, weight_by_sim=False, root_regularize_weight=1.0,
+                     root_edges_only=True)
+
+
 class FeatureMetricKeypointOptimizer:
+    _options_cls = KeypointOptimizerOptions
+    _banner = "Start feature-metric keypoint adjustment."
+
     def __init__(self, options, setup, interpolation_config):
-        self.options = options if isinstance(options, KeypointOptimizerOptions) else KeypointOptimizerOptions(options)
+        self.options = options if isinstance(options, KeypointOptimizerOptions) else self._options_cls(options)
         self.setup = setup
         self.interp = interpolation_config if isinstance(interpolation_config, InterpolationConfig) else InterpolationConfig(interpolation_config)
         self._summary = None
-        logger.info("Start feature-metric keypoint adjustment.")
+        logger.info(self._banner)
 
     def run(self, *args):
         """run(keypoints, graph, track_labels, root_labels, feature_set) — one problem over all nodes, or
@@ -86,7 +96,9 @@ class FeatureMetricKeypointOptimizer:
             if regularize:
                 for n in (a, b):
                     if not connected[n]:
-                        flat.append((n, track_root[track_labels[n]], opt.root_regularize_weight))
+                        # std::unordered_map::operator[] default-inserts node 0 for a track without a root
+                        # (topological_keypoint_optimizer.h:161)
+                        flat.append((n, track_root.get(track_labels[n], 0), opt.root_regularize_weight))
                         connected[n] = True
         if not flat:
             self._summary = _Summary(initial_cost=0.0, final_cost=0.0, num_residuals_reduced=0, total_time_in_seconds=0.0)
@@ -131,3 +143,11 @@ class FeatureMetricKeypointOptimizer:
 
     def summary(self):
         return self._summary
+
+
+class TopologicalReferenceKeypointOptimizer(FeatureMetricKeypointOptimizer):
+    """_keypoint_adjustment.TopologicalReferenceKeypointOptimizer (keypoint_adjustment/bindings.cc:86-100;
+    topological_reference_keypoint_optimizer.h:5-28): the same optimizer with root edges only, unit edge weights
+    and root regularisation on by default — same kernels, different edge set."""
+    _options_cls = TopologicalReferenceKeypointOptimizerOptions
+    _banner = "Start topological-reference keypoint adjustment."

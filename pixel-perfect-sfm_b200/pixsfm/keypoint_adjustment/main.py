@@ -43,7 +43,8 @@ class KeypointAdjuster:
 
     @classmethod
     def create(cls, conf):
-        strategy_to_solver = {"featuremetric": FeatureMetricKeypointAdjuster}
+        strategy_to_solver = {"featuremetric": FeatureMetricKeypointAdjuster,
+                              "topological_reference": TopologicalReferenceKeypointAdjuster}
         strategy = conf["strategy"] if "strategy" in conf else cls.default_conf["strategy"]
         if strategy not in strategy_to_solver:
             raise ValueError("strategy '%s' is not on the B200 path" % strategy)
@@ -81,6 +82,29 @@ class FeatureMetricKeypointAdjuster(KeypointAdjuster):
             problem_setup.set_masked_nodes_constant(graph, root_labels)
         solver = ka.FeatureMetricKeypointOptimizer(to_optim_ctr(self.conf.optimizer, self.callbacks), problem_setup,
                                                    to_ctr(self.conf.interpolation))
+        if self.conf.split_in_subproblems:
+            problem_labels, _ = find_problem_labels(track_labels, self.conf.max_kps_per_problem)
+            solver.run(problem_labels, keypoints_dict, graph, track_labels, root_labels, feature_set)
+        else:
+            solver.run(keypoints_dict, graph, track_labels, root_labels, feature_set)
+        return {"summary": solver.summary()}
+
+
+class TopologicalReferenceKeypointAdjuster(KeypointAdjuster):
+    """Optimize all keypoints of a track towards the node with the highest aggregated matching score (reference
+    keypoint_adjustment/main.py:206-250): linear instead of quadratic in the track length."""
+    default_conf = deepcopy(KeypointAdjuster.default_conf)
+    default_conf["optimizer"] = {**default_conf["optimizer"], "num_threads": -1}
+
+    def __init__(self, conf):
+        self.conf = merge(self.default_conf, conf)
+
+    def refine(self, keypoints_dict, feature_set, graph, track_labels, root_labels, problem_setup=None):
+        if problem_setup is None:
+            problem_setup = ka.KeypointAdjustmentSetup()
+            problem_setup.set_masked_nodes_constant(graph, root_labels)
+        solver = ka.TopologicalReferenceKeypointOptimizer(to_optim_ctr(self.conf.optimizer, self.callbacks), problem_setup,
+                                                          to_ctr(self.conf.interpolation))
         if self.conf.split_in_subproblems:
             problem_labels, _ = find_problem_labels(track_labels, self.conf.max_kps_per_problem)
             solver.run(problem_labels, keypoints_dict, graph, track_labels, root_labels, feature_set)

@@ -112,3 +112,40 @@ def test_device_resident_feature_maps_give_identical_results():
     # cost-map strategy on the device-resident maps too
     out_c = ba_pkg.BundleAdjuster.create({"strategy": "costmaps", **conf}).refine_multilevel(copy.deepcopy(rec_dev), fm_dev)
     assert out_c["summary"][0].final_cost < out_c["summary"][0].initial_cost
+
+
+def test_topological_reference_keypoint_adjuster_matches_flat_oracle():
+    """strategy 'topological_reference' (keypoint_adjustment/main.py:206-250): root edges only, unit weights, root
+    regularisation — the edge list the mirror enumerates, solved on the GPU, equals the oracle on the same IR."""
+    from pixsfm._pixsfm import _keypoint_adjustment as ka
+    sc = synthetic.make_ka_scene(n_images=6, n_tracks=40, track_len=4, channels=128, seed=12, kp_sigma=1.0)
+    g = base.Graph()
+    names = ["im%d" % i for i in range(6)]
+    keypoints = {names[i]: np.ascontiguousarray(sc["keypoints"][sc["node_image"] == i]) for i in range(6)}
+    for n in range(len(sc["node_image"])):
+        g.add_node(names[sc["node_image"][n]], int(sc["node_feature"][n]))
+    for e in range(len(sc["edge_src"])):
+        g.add_edge(g.nodes[sc["edge_src"][e]], g.nodes[sc["edge_dst"][e]], sc["edge_sim"][e])
+    fm = features.FeatureManager([128], np.float16)
+    for i in range(6):
+        m = np.where(sc["node_image"] == i)[0]
+        fm.fset(0).emplace(names[i], features.FeatureMap(np.ascontiguousarray(sc["patches"][m]), sc["node_feature"][m].tolist(),
+                                                          sc["corner"][m], {"scale": sc["scale"][m[0]], "is_sparse": True}))
+    track_labels = base.compute_track_labels(g)
+    root_labels = base.compute_root_labels(g, track_labels, base.compute_score_labels(g, track_labels))
+    before = {k: v.copy() for k, v in keypoints.items()}
+    kp_fm = {k: v.copy() for k, v in keypoints.items()}
+    out = ka_pkg.KeypointAdjuster.create({"strategy": "topological_reference", "max_kps_per_problem": 20}).refine_multilevel(
+        keypoints, fm, g, track_labels, root_labels)
+    out_fm = ka_pkg.KeypointAdjuster.create({"max_kps_per_problem": 20}).refine_multilevel(kp_fm, fm, g, track_labels, root_labels)
+    s, s_fm = out["summary"][0], out_fm["summary"][0]
+    assert s.final_cost < s.initial_cost
+    # linear instead of quadratic number of residuals: every non-root node has exactly one edge, to its root
+    n_roots = int(np.sum(root_labels))
+    assert s.num_residual_blocks == len(g.nodes) - n_roots
+    assert s.num_residual_blocks < s_fm.num_residual_blocks
+    # roots are constant, everything else moved
+    for n, node in enumerate(g.nodes):
+        name = g.image_id_to_name[node.image_id]
+        d = np.abs(keypoints[name][node.feature_idx] - before[name][node.feature_idx]).max()
+        assert (d == 0.0) if root_labels[n] else (d > 0.0)

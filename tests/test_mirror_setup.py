@@ -151,3 +151,16 @@ def test_costmap_strategy_surface_and_defaults():
     c = _capi.default_costmap_config()
     assert (c.loss_type, c.as_gradientfield, c.apply_sqrt, c.upsampling_factor, c.ref_loss_type, c.ref_loss_scale, c.ref_iters) == \
         (0, 1, 0, 1.0, 1, 0.25, 100)
+
+
+def test_topological_reference_ka_surface():
+    """keypoint_adjustment/main.py:206-250 + topological_reference_keypoint_optimizer.h:9-16"""
+    from pixsfm._pixsfm import _keypoint_adjustment as ka
+    adj = ka_pkg.KeypointAdjuster.create({"strategy": "topological_reference"})
+    assert isinstance(adj, ka_pkg.TopologicalReferenceKeypointAdjuster)
+    o = ka.TopologicalReferenceKeypointOptimizerOptions()
+    assert (o.weight_by_sim, o.root_regularize_weight, o.root_edges_only) == (False, 1.0, True)
+    o2 = ka.KeypointOptimizerOptions()
+    assert (o2.weight_by_sim, o2.root_regularize_weight, o2.root_edges_only) == (True, -1.0, False)
+    opt = ka.TopologicalReferenceKeypointOptimizer({"bound": 2.0}, ka.KeypointAdjustmentSetup(), {})
+    assert opt.options.root_edges_only and opt.options.bound == 2.0
