@@ -185,7 +185,6 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   h_pt_begin.assign(n_points + 1, 0);
   for (int64_t o = 0; o < n_obs; ++o) h_pt_begin[d->obs_pt[o] + 1]++;
   for (int64_t p = 0; p < n_points; ++p) h_pt_begin[p + 1] += h_pt_begin[p];
-  if ((int64_t)nc * nc * 8 > (int64_t)40e9) return fail(PXR_ERR_UNSUPPORTED, "reduced camera system too large for the dense path (nc=%d)", nc);
 
   double h2d = h2d_patch;
   auto up = [&](auto& buf, const auto* host, size_t n) -> int { h2d += n * sizeof(*host); return buf.upload(host, n, s); };
@@ -219,13 +218,44 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     PXR_TRY(uv_alt.alloc((size_t)n_obs * 2)); PXR_TRY(obs_out_alt.alloc((size_t)n_obs * 8)); PXR_TRY(juv_alt.alloc((size_t)n_obs * juv_stride));
     PXR_TRY(obs_out_alt.zero(s));
   }
-  PXR_TRY(Hcc.alloc((size_t)nc * nc)); PXR_TRY(gc.alloc(nc));
-  PXR_TRY(Hpp.alloc((size_t)n_points * 9)); PXR_TRY(gp.alloc((size_t)n_points * 3));
-  h_obs_img.assign(d->obs_img, d->obs_img + n_obs);
-  use_monolithic_inner = std::getenv("PXR_INNER_MONOLITHIC") != nullptr;
   // linear solver as BundleOptimizer::SolveProblem picks it (bundle_optimizer.h:181-191): exact factorisation up to
   // 1000 images, ITERATIVE_SCHUR + SCHUR_JACOBI above (or when asked for)
   use_pcg = opt.linear_solver == PXR_SOLVER_ITERATIVE_SCHUR || (opt.linear_solver == PXR_SOLVER_AUTO && n_images > 1000);
+  {
+    // per-image column tables: an observation's camera columns are [pose columns | intrinsics columns] of its image
+    int dc_needed = 0;
+    h_img_cols.assign((size_t)n_images * 8, -1); h_img_pd.assign(n_images, 0);
+    for (int i = 0; i < n_images; ++i) {
+      std::vector<int> cols;
+      if (h_pose_off[i] >= 0) {
+        for (int k = 0; k < 3; ++k) cols.push_back(h_pose_off[i] + k);
+        int la = 3;
+        for (int k = 0; k < 3; ++k) if (!(d->tvec_const_mask[i] & (1u << k))) cols.push_back(h_pose_off[i] + la++);
+      }
+      const int pd = (int)cols.size();
+      const int cam_i = d->img_cam[i];
+      if (h_intr_off[cam_i] >= 0) {
+        const int kc = cam_num_params(d->cam_model[cam_i]);
+        int la = 0;
+        for (int k = 0; k < kc; ++k) if (!(cmask[cam_i] & (1u << k))) cols.push_back(h_intr_off[cam_i] + la++);
+      }
+      dc_needed = std::max(dc_needed, (int)cols.size());
+      h_img_pd[i] = pd;
+      for (size_t k = 0; k < cols.size() && k < 8; ++k) h_img_cols[(size_t)i * 8 + k] = cols[k];
+    }
+    img_dc_max = dc_needed;
+    h_img_cam.assign(d->img_cam, d->img_cam + n_images);
+    // implicit block-sparse reduced system: on request, or when the dense one would not fit comfortably
+    sparse_schur = for_solve && use_pcg && dc_needed <= 8 && n_obs > 0 &&
+                   (getenv("PXR_PCG_SPARSE") != nullptr || (int64_t)nc * nc * 8 > (int64_t)4e9);
+    if (!sparse_schur && (int64_t)nc * nc * 8 > (int64_t)40e9)
+      return fail(PXR_ERR_UNSUPPORTED, "reduced camera system too large for the dense path (nc=%d) and the block-sparse path needs ITERATIVE_SCHUR with <= 8 camera columns per image", nc);
+  }
+  if (!sparse_schur) PXR_TRY(Hcc.alloc((size_t)nc * nc));
+  PXR_TRY(gc.alloc(nc));
+  PXR_TRY(Hpp.alloc((size_t)n_points * 9)); PXR_TRY(gp.alloc((size_t)n_points * 3));
+  h_obs_img.assign(d->obs_img, d->obs_img + n_obs);
+  use_monolithic_inner = std::getenv("PXR_INNER_MONOLITHIC") != nullptr;
   if (for_solve) PXR_TRY(build_schur_pairs());
   if (for_solve && n_obs > 0 && n_obs < ((int64_t)1 << 31)) {
     // per-image observation chunks for the camera-block build (ba_build_cam_kernel): images whose pose and
@@ -262,7 +292,8 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     }
   }
   PXR_TRY(W.alloc((size_t)n_obs * dcmax * 3)); PXR_TRY(Wcols.alloc((size_t)n_obs * dcmax)); PXR_TRY(Wdc.alloc(n_obs));
-  PXR_TRY(S.alloc((size_t)(nc + 1) * nc)); PXR_TRY(rhs.alloc(nc));
+  if (!sparse_schur) PXR_TRY(S.alloc((size_t)(nc + 1) * nc));
+  PXR_TRY(rhs.alloc(nc));
   PXR_TRY(diag.alloc(nl)); PXR_TRY(jscale.alloc(nl)); PXR_TRY(D2.alloc(nl)); PXR_TRY(delta.alloc(nl));
   PXR_TRY(partials.alloc(fm_max_partials(ctx)));
   PXR_TRY(scalars.alloc(16));
@@ -316,10 +347,33 @@ int BA::build_schur_pairs() {
   }
   std::vector<int64_t> cb;
   std::vector<uint8_t> cself;
-  for (int64_t k = 0; k < n_keys; ++k) {
-    for (int64_t s = count[k]; s < count[k + 1]; s += kChunk) { cb.push_back(s); cself.push_back((uint8_t)(k & 1)); }
+  std::vector<int32_t> ckey, ka, kbv;      // sparse path: compact id of every non-empty (image pair, self) key
+  std::vector<uint8_t> kself;
+  {
+    int64_t k = 0;
+    for (int64_t ia = 0; ia < ni; ++ia)
+      for (int64_t ib = 0; ib <= ia; ++ib)
+        for (int self = 0; self < 2; ++self, ++k) {
+          if (count[k + 1] == count[k]) continue;
+          if (sparse_schur) { ka.push_back((int32_t)ia); kbv.push_back((int32_t)ib); kself.push_back((uint8_t)self); }
+          for (int64_t s = count[k]; s < count[k + 1]; s += kChunk) {
+            cb.push_back(s); cself.push_back((uint8_t)self);
+            if (sparse_schur) ckey.push_back((int32_t)ka.size() - 1);
+          }
+        }
   }
   cb.push_back(total);
+  if (sparse_schur) {
+    ss_n_keys = (int)ka.size();
+    PXR_TRY(ss_key_a.upload(ka.data(), ka.size(), ctx->stream)); PXR_TRY(ss_key_b.upload(kbv.data(), kbv.size(), ctx->stream));
+    PXR_TRY(ss_key_self.upload(kself.data(), kself.size(), ctx->stream));
+    PXR_TRY(ss_chunk_key.upload(ckey.data(), ckey.size(), ctx->stream));
+    PXR_TRY(ss_Bk.alloc((size_t)std::max(ss_n_keys, 1) * 64));
+    PXR_TRY(ss_Himg.alloc((size_t)n_images * 64));
+    PXR_TRY(ss_img_cols.upload(h_img_cols.data(), h_img_cols.size(), ctx->stream));
+    PXR_TRY(ss_img_pd.upload(h_img_pd.data(), h_img_pd.size(), ctx->stream));
+    PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   sp_n_chunks = (int64_t)cself.size();
   cudaStream_t s = ctx->stream;
   PXR_TRY(sp_px.upload(px.data(), px.size(), s));
@@ -405,16 +459,21 @@ BADev BA::dev() {
 
 int BA::build() {
   StageScope st(this, 3);
-  PXR_TRY(Hcc.zero(ctx->stream));
+  if (!sparse_schur) PXR_TRY(Hcc.zero(ctx->stream));
   PXR_TRY(gc.zero(ctx->stream));
   PXR_TRY(Hpp.zero(ctx->stream));
   PXR_TRY(gp.zero(ctx->stream));
-  const bool chunked = io_n_chunks > 0 && getenv("PXR_BUILD_ATOMIC") == nullptr;
+  const bool chunked = io_n_chunks > 0 && (sparse_schur || getenv("PXR_BUILD_ATOMIC") == nullptr);
+  if (sparse_schur && !chunked && n_obs > 0) return fail(PXR_ERR_INTERNAL, "block-sparse path without per-image chunks");
+  if (sparse_schur) PXR_TRY(ss_Himg.zero(ctx->stream));
   if (n_obs > 0) PXR_LAUNCH(ctx, ba_build_kernel, (unsigned)cdiv(n_obs, 128), 128, 0, dev(), chunked ? 0 : 1);
   if (n_obs > 0 && chunked)
-    PXR_LAUNCH(ctx, ba_build_cam_kernel, (unsigned)cdiv(io_n_chunks * 32, 256), 256, 0, dev(), io_obs.p, io_chunk_begin.p, io_n_chunks);
+    PXR_LAUNCH(ctx, ba_build_cam_kernel, (unsigned)cdiv(io_n_chunks * 32, 256), 256, 0, dev(), io_obs.p, io_chunk_begin.p, io_n_chunks,
+               sparse_schur ? ss_Himg.p : nullptr);
   const int64_t n = std::max<int64_t>(nc, n_points);
+  if (sparse_schur && nc > 0) PXR_CUDA(cudaMemsetAsync(diag.p, 0, (size_t)nc * 8, ctx->stream));
   if (n > 0) PXR_LAUNCH(ctx, ba_diag_kernel, (unsigned)cdiv(n, 256), 256, 0, dev(), diag.p);
+  if (sparse_schur && nc > 0) PXR_LAUNCH(ctx, sp_diag_kernel, (unsigned)cdiv((int64_t)n_images * 8, 256), 256, 0, sparse(), diag.p);
   if (ctx->world > 1 && nc > 0) {
     // multi-GPU: Hcc stays a per-rank partial sum (it only ever enters the reduced system, which is all-reduced
     // anyway); globally needed are its diagonal (Jacobi scaling / LM damping) and the gradient
@@ -427,6 +486,15 @@ int BA::build() {
   return PXR_OK;
 }
 
+SparseSchur BA::sparse() {
+  SparseSchur q;
+  q.n_images = n_images; q.n_keys = ss_n_keys; q.nc = nc;
+  q.img_cols = ss_img_cols.p; q.img_pd = ss_img_pd.p; q.img_pose_blk = ss_img_pose_blk.p; q.img_cam_blk = ss_img_cam_blk.p;
+  q.key_a = ss_key_a.p; q.key_b = ss_key_b.p; q.key_self = ss_key_self.p;
+  q.Himg = ss_Himg.p; q.Bk = ss_Bk.p;
+  return q;
+}
+
 // One LM step attempt at the current linearisation: fills delta, returns validity and model cost change
 int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   cudaStream_t s = ctx->stream;
@@ -436,6 +504,16 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   if (nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, D2.p, nl, radius,
                          opt.min_lm_diagonal, opt.max_lm_diagonal);
   PXR_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), s));
+  if (sparse_schur) {
+    // image-block form (pxr_sparse_schur.cuh): rhs = -gc + sum T gp, B_ab = sum T_x W_y^T; nothing of size nc^2
+    if (nc > 0) PXR_LAUNCH(ctx, sp_init_rhs_kernel, (unsigned)cdiv(nc, 256), 256, 0, ctx->world > 1 ? gc_local.p : gc.p, rhs.p, nc);
+    PXR_TRY(ss_Bk.zero(s));
+    if (n_points > 0) {
+      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, D2.p, Tbuf.p, rhs.p, flags.p);
+      if (sp_n_chunks > 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, 256), 256, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, ss_Bk.p);
+    }
+    if (ctx->world > 1 && nc > 0) PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
+  } else {
   // multi-GPU: every rank starts from ITS partial Hcc / gc (rank 0 adds the damping), subtracts its points' Schur
   // contributions, and ONE all-reduce of [S | rhs] (rhs is row nc of the same array) yields the reduced system
   if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p,
@@ -450,9 +528,12 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     PXR_TRY(allreduce_f64(ctx, S.p, (size_t)(nc + 1) * nc));
     PXR_CUDA(cudaMemcpyAsync(rhs.p, S.p + (size_t)nc * nc, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));   // PCG / debug read rhs
   }
+  }
   delete st; st = new StageScope(this, 5);
   last_linear_iterations = 1;
-  if (nc > 0 && use_pcg) {
+  if (nc > 0 && sparse_schur) {
+    PXR_TRY(pcg_solve_sparse());
+  } else if (nc > 0 && use_pcg) {
     PXR_TRY(pcg_solve());
   } else if (nc > 0) {
     // The factorisation + back-substitution is a fixed sequence of ~3*nc/32 dependent launches: it is
@@ -651,25 +732,87 @@ int BA::step_norm_between_sets(double* out) {
 }
 
 // S delta_c = rhs by Schur-Jacobi preconditioned CG (pxr_pcg.cuh); result in delta[0..nc)
+int BA::pcg_setup_blocks() {
+  if (cg_state.p) return PXR_OK;
+  cudaStream_t s = ctx->stream;
+  // SCHUR_JACOBI blocks = the camera-side parameter blocks (one per variable pose, one per variable intrinsics)
+  std::vector<int32_t> off;
+  for (int i = 0; i < n_images; ++i) if (h_pose_off[i] >= 0) off.push_back(h_pose_off[i]);
+  for (int c = 0; c < n_cameras; ++c) if (h_intr_off[c] >= 0) off.push_back(h_intr_off[c]);
+  std::sort(off.begin(), off.end());
+  std::vector<int32_t> sd(off.size());
+  for (size_t k = 0; k < off.size(); ++k) sd[k] = (k + 1 < off.size() ? off[k + 1] : nc) - off[k];
+  cg_nblk = (int)off.size();
+  PXR_TRY(cg_blk_off.upload(off.data(), off.size(), s)); PXR_TRY(cg_blk_dim.upload(sd.data(), sd.size(), s));
+  PXR_TRY(cg_Minv.alloc((size_t)nc * 12)); PXR_TRY(cg_row_off.alloc(nc)); PXR_TRY(cg_row_dim.alloc(nc));
+  PXR_TRY(cg_z.alloc(nc)); PXR_TRY(cg_p.alloc(nc)); PXR_TRY(cg_q.alloc(nc)); PXR_TRY(cg_r.alloc(nc)); PXR_TRY(cg_x.alloc(nc)); PXR_TRY(cg_tmp.alloc(nc));
+  PXR_TRY(cg_state.alloc(1));
+  if (sparse_schur) {
+    auto blk_of = [&](int offset) -> int32_t { return (int32_t)(std::lower_bound(off.begin(), off.end(), offset) - off.begin()); };
+    h_img_pose_blk.assign(n_images, -1); h_img_cam_blk.assign(n_images, -1);
+    for (int i = 0; i < n_images; ++i) {
+      if (h_pose_off[i] >= 0) h_img_pose_blk[i] = blk_of(h_pose_off[i]);
+      const int io = h_intr_off[h_img_cam[i]];
+      if (io >= 0) h_img_cam_blk[i] = blk_of(io);
+    }
+    PXR_TRY(ss_img_pose_blk.upload(h_img_pose_blk.data(), h_img_pose_blk.size(), s));
+    PXR_TRY(ss_img_cam_blk.upload(h_img_cam_blk.data(), h_img_cam_blk.size(), s));
+    PXR_TRY(ss_Dblk.alloc((size_t)std::max(cg_nblk, 1) * 144));
+  }
+  PXR_CUDA(cudaStreamSynchronize(s));
+  return PXR_OK;
+}
+
+// ITERATIVE_SCHUR on the implicit block-sparse reduced system (pxr_sparse_schur.cuh).  Same CG recurrences and
+// termination as pcg_solve(); the mat-vec gathers/scatters through the image blocks, and in the multi-GPU path the
+// product (nc doubles) is all-reduced per iteration instead of the matrix once.
+int BA::pcg_solve_sparse() {
+  cudaStream_t s = ctx->stream;
+  PXR_TRY(pcg_setup_blocks());
+  const int n = nc;
+  const SparseSchur sp = sparse();
+  const int64_t nthreads = std::max<int64_t>(((int64_t)n_images + ss_n_keys) * 8, n);
+  const unsigned gs = (unsigned)cdiv(nthreads, 256);
+  const int add_d2 = (ctx->world <= 1 || ctx->rank == 0) ? 1 : 0;
+  auto spmv = [&](const double* x, double* y) -> int {
+    PXR_CUDA(cudaMemsetAsync(y, 0, (size_t)n * 8, s));
+    PXR_LAUNCH(ctx, sp_spmv_kernel, gs, 256, 0, sp, D2.p, x, y, add_d2, cg_state.p);
+    if (ctx->world > 1) PXR_TRY(allreduce_f64(ctx, y, n));
+    return PXR_OK;
+  };
+  PXR_TRY(ss_Dblk.zero(s));
+  PXR_LAUNCH(ctx, sp_blockdiag_kernel, (unsigned)cdiv(((int64_t)n_images + ss_n_keys) * 8, 256), 256, 0, sp, ss_Dblk.p);
+  if (ctx->world > 1) PXR_TRY(allreduce_f64(ctx, ss_Dblk.p, (size_t)cg_nblk * 144));
+  PXR_LAUNCH(ctx, sp_block_inverse_kernel, (unsigned)cdiv(cg_nblk, 64), 64, 0, ss_Dblk.p, D2.p, 1, cg_blk_off.p, cg_blk_dim.p, cg_nblk,
+             cg_Minv.p, cg_row_off.p, cg_row_dim.p, flags.p + 1);
+  PXR_LAUNCH(ctx, cg_init_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p, opt.max_linear_solver_iterations, 0.1);
+  CGState hs;
+  for (int it = 0; it < opt.max_linear_solver_iterations; ++it) {
+    PXR_LAUNCH(ctx, cg_precond_kernel, 1, 1024, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, cg_p.p, n, cg_state.p);
+    PXR_TRY(spmv(cg_p.p, cg_q.p));
+    PXR_LAUNCH(ctx, cg_update_kernel, 1, 1024, 0, rhs.p, cg_p.p, cg_q.p, cg_x.p, cg_r.p, n, cg_state.p);
+    if ((it + 1) % 10 == 0) {   // residual_reset_period
+      PXR_TRY(spmv(cg_x.p, cg_tmp.p));
+      PXR_LAUNCH(ctx, cg_refresh_kernel, 1, 1024, 0, rhs.p, cg_tmp.p, cg_r.p, n, cg_state.p);
+    }
+    PXR_LAUNCH(ctx, cg_check_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p);
+    if ((it + 1) % 8 == 0 || it + 1 == opt.max_linear_solver_iterations) {
+      PXR_CUDA(cudaMemcpyAsync(&hs, cg_state.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+      PXR_CUDA(cudaStreamSynchronize(s));
+      if (hs.done) break;
+    }
+  }
+  PXR_CUDA(cudaMemcpyAsync(&hs, cg_state.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaMemcpyAsync(delta.p, cg_x.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  last_linear_iterations = hs.it;
+  if (hs.failed) { int one = 1; PXR_CUDA(cudaMemcpyAsync(flags.p + 1, &one, sizeof(int), cudaMemcpyHostToDevice, s)); }
+  return PXR_OK;
+}
+
 int BA::pcg_solve() {
   cudaStream_t s = ctx->stream;
-  if (!cg_state.p) {
-    std::vector<int32_t> off, dim;
-    for (int i = 0; i < n_images; ++i) if (h_pose_off[i] >= 0) { off.push_back(h_pose_off[i]); dim.push_back(0); }
-    for (int c = 0; c < n_cameras; ++c) if (h_intr_off[c] >= 0) { off.push_back(h_intr_off[c]); dim.push_back(0); }
-    std::vector<int32_t> order(off.size());
-    for (size_t k = 0; k < off.size(); ++k) order[k] = (int32_t)k;
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return off[a] < off[b]; });
-    std::vector<int32_t> so(off.size()), sd(off.size());
-    for (size_t k = 0; k < off.size(); ++k) so[k] = off[order[k]];
-    for (size_t k = 0; k < off.size(); ++k) sd[k] = (k + 1 < off.size() ? so[k + 1] : nc) - so[k];
-    cg_nblk = (int)so.size();
-    PXR_TRY(cg_blk_off.upload(so.data(), so.size(), s)); PXR_TRY(cg_blk_dim.upload(sd.data(), sd.size(), s));
-    PXR_TRY(cg_Minv.alloc((size_t)nc * 12)); PXR_TRY(cg_row_off.alloc(nc)); PXR_TRY(cg_row_dim.alloc(nc));
-    PXR_TRY(cg_z.alloc(nc)); PXR_TRY(cg_p.alloc(nc)); PXR_TRY(cg_q.alloc(nc)); PXR_TRY(cg_r.alloc(nc)); PXR_TRY(cg_x.alloc(nc)); PXR_TRY(cg_tmp.alloc(nc));
-    PXR_TRY(cg_state.alloc(1));
-    PXR_CUDA(cudaStreamSynchronize(s));
-  }
+  PXR_TRY(pcg_setup_blocks());
   const int n = nc;
   const unsigned gv = (unsigned)cdiv((int64_t)n * 32, 256);
   PXR_LAUNCH(ctx, cg_mirror_kernel, (unsigned)cdiv((int64_t)n * n, 256), 256, 0, S.p, n);
@@ -1009,6 +1152,7 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
   pxr_ctx* ctx = b->ctx;
   cudaStream_t s = ctx->stream;
   PXR_CUDA(cudaSetDevice(ctx->device));
+  if (b->sparse_schur && (Hcc || S)) return fail(PXR_ERR_UNSUPPORTED, "the block-sparse path has no dense Hcc / S to return");
   double c = 0;
   PXR_TRY(b->evaluate(b->cur, true, &c));
   if (cost) *cost = c;

@@ -12,6 +12,7 @@
 #include "pxr_inner.cuh"
 #include "pxr_internal.h"
 #include "pxr_pcg.cuh"
+#include "pxr_sparse_schur.cuh"
 
 namespace pxr {
 
@@ -51,7 +52,7 @@ struct BA {
   // sizes
   int n_cameras = 0, n_images = 0, K = 0, C = 0, ph = 0, pw = 0, dtype = 0;
   int64_t n_points = 0, n_obs = 0, n_patches = 0, nl = 0;
-  int nc = 0, dcmax = 0, juv_stride = 0;
+  int nc = 0, dcmax = 0, juv_stride = 0, img_dc_max = 0;
   double ups = 1.0;
   bool has_refs = false;
   double h2d_bytes = 0;
@@ -85,6 +86,16 @@ struct BA {
   DevBuf<CGState> cg_state;
   int cg_nblk = 0, last_linear_iterations = 1;
   int pcg_solve();
+  // implicit block-sparse reduced system (pxr_sparse_schur.cuh): no nc x nc array is ever allocated
+  bool sparse_schur = false;
+  int ss_n_keys = 0;
+  std::vector<int32_t> h_img_cols, h_img_pd, h_img_pose_blk, h_img_cam_blk, h_img_cam;
+  DevBuf<int32_t> ss_img_cols, ss_img_pd, ss_img_pose_blk, ss_img_cam_blk, ss_key_a, ss_key_b, ss_chunk_key;
+  DevBuf<uint8_t> ss_key_self;
+  DevBuf<double> ss_Himg, ss_Bk, ss_Dblk;
+  SparseSchur sparse();
+  int pcg_solve_sparse();
+  int pcg_setup_blocks();
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
   bool chol_multikernel = false; int chol_grid = 0;

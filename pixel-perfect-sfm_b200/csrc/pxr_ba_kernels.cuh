@@ -117,7 +117,8 @@ static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d, int cam_b
 // the warp with the transposed butterfly (9 double shuffles per 8 values) and issues ONE atomic per
 // element per chunk: 128x fewer L2 atomics than ba_build_kernel's camera part.  Used when dcmax <= 8.
 static __global__ void __launch_bounds__(256) ba_build_cam_kernel(BADev d, const int32_t* __restrict__ io_obs,
-                                                                  const int64_t* __restrict__ chunk_begin, int64_t n_chunks) {
+                                                                  const int64_t* __restrict__ chunk_begin, int64_t n_chunks,
+                                                                  double* __restrict__ Himg /* [n_images][64] or null: dense Hcc */) {
   const int lane = threadIdx.x & 31;
   const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (chunk >= n_chunks) return;
@@ -163,7 +164,10 @@ static __global__ void __launch_bounds__(256) ba_build_cam_kernel(BADev d, const
       int a = 0;
       while ((a + 1) * (a + 2) / 2 <= vi) ++a;
       const int b = vi - a * (a + 1) / 2;
-      if (a < dc) atomic_add_f64(&d.Hcc[(int64_t)cols[a] * d.nc + cols[b]], tot);
+      if (a < dc) {
+        if (Himg) atomic_add_f64(&Himg[(int64_t)d.obs_img[io_obs[beg]] * 64 + a * 8 + b], tot);
+        else atomic_add_f64(&d.Hcc[(int64_t)cols[a] * d.nc + cols[b]], tot);
+      }
     } else if (vi < 44) {
       const int a = vi - 36;
       if (a < dc) atomic_add_f64(&d.gc[cols[a]], tot);
@@ -174,7 +178,7 @@ static __global__ void __launch_bounds__(256) ba_build_cam_kernel(BADev d, const
 // diag(J^T J) in local order: cameras from Hcc's diagonal, points from Hpp
 static __global__ void ba_diag_kernel(BADev d, double* diag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < d.nc) diag[i] = d.Hcc[i * d.nc + i];
+  if (i < d.nc && d.Hcc) diag[i] = d.Hcc[i * d.nc + i];     // sparse mode (Hcc == null): sp_diag_kernel fills the camera part
   const int64_t p = i;
   if (p < d.n_points) {
     const int64_t po = d.point_off[p];

@@ -191,3 +191,32 @@ def test_reduced_system_cholesky_tile_dag(n_cams, multikernel, monkeypatch):
         got = h.debug_linearize(ref["nc"], ref["nl"], radius=1e4)
         assert np.allclose(got["delta"], ref["delta"], rtol=1e-5, atol=1e-8 * np.abs(ref["delta"]).max())
     assert abs(got["model_cost_change"] - ref["model_cost_change"]) <= 1e-7 * abs(ref["model_cost_change"])
+
+
+@pytest.mark.parametrize("variant", ["per_image_cameras", "shared_camera", "constant_blocks"])
+def test_iterative_schur_block_sparse_matches_dense_and_oracle(variant, monkeypatch):
+    """The implicit block-sparse reduced system (pxr_sparse_schur.cuh; what config 5's 5 000 cameras need) against
+    the dense PCG path and the oracle's PCG on the same problems: identical CG recurrences, different storage."""
+    kw = dict(n_cams=12, n_points=150, track_len=5, channels=16, seed=5)
+    if variant == "shared_camera":
+        kw["shared_camera"] = True
+    prob, gt, ic = _scene(**kw)
+    if variant == "constant_blocks":
+        prob.point_const[::9] = 1
+        prob.pose_const[3] = 1
+        prob.tvec_const_mask[4] = 0b101
+        prob.cam_const_mask[2] = 0xFFFFFFFF
+    so = _capi.default_ba_options(use_inner_iterations=0, max_num_iterations=10, linear_solver=3)
+    p_ref, p_dense, p_sparse = prob.copy(), prob.copy(), prob.copy()
+    s_ref = O.ba_solve(p_ref, ic, so)
+    s_dense = _engine.ba_run(p_dense, ic, so)
+    monkeypatch.setenv("PXR_PCG_SPARSE", "1")
+    s_sparse = _engine.ba_run(p_sparse, ic, so)
+    monkeypatch.delenv("PXR_PCG_SPARSE")
+    it_s = [i["linear_solver_iterations"] for i in s_sparse["iterations"][1:]]
+    it_d = [i["linear_solver_iterations"] for i in s_dense["iterations"][1:]]
+    assert len(it_s) == len(it_d) and max(abs(a - b) for a, b in zip(it_s, it_d)) <= 2, (it_s, it_d)
+    assert abs(s_sparse["final_cost"] - s_dense["final_cost"]) <= 1e-6 * s_dense["final_cost"]
+    assert abs(s_sparse["final_cost"] - s_ref["final_cost"]) <= 1e-5 * s_ref["final_cost"]
+    _compare_solutions(p_sparse, p_dense, 1e-5)
+    _compare_solutions(p_sparse, p_ref, 1e-4)
