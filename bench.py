@@ -62,6 +62,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-points", type=int, default=20000)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--covis-window", type=int, default=0,
+                    help="0: every point is seen by `track` cameras drawn uniformly (BASELINE configs[2]); W>0: drawn from a "
+                         "window of W consecutive cameras (local co-visibility, what large scenes look like: configs[4])")
+    ap.add_argument("--linear-solver", type=int, default=0, help="pxr_linear_solver (0 AUTO as bundle_optimizer.h:181-191)")
     return ap.parse_args()
 
 
@@ -123,15 +127,28 @@ def geometry(args, rank):
     n_pts, L = args.points, min(args.track, args.cams)
     xyz = rng.uniform(-1, 1, (n_pts, 3))
     # every point is seen by L distinct cameras
-    keys = rng.random((n_pts, args.cams))
-    obs_img = np.sort(np.argpartition(keys, L - 1, axis=1)[:, :L], axis=1).astype(np.int32).reshape(-1)
+    if args.covis_window > 0:
+        W = max(L, min(args.covis_window, args.cams))
+        center = rng.integers(0, args.cams, n_pts)
+        offs = np.argpartition(rng.random((n_pts, W)), L - 1, axis=1)[:, :L]
+        obs_img = np.sort((center[:, None] + offs) % args.cams, axis=1).astype(np.int32).reshape(-1)
+    else:
+        keys = rng.random((n_pts, args.cams))
+        obs_img = np.sort(np.argpartition(keys, L - 1, axis=1)[:, :L], axis=1).astype(np.int32).reshape(-1)
     obs_pt = np.repeat(np.arange(n_pts, dtype=np.int64), L)
     qvec, tvec, cam_params, img_cam = geo_c["qvec"], geo_c["tvec"], geo_c["cam_params"], geo_c["img_cam"]
-    xy = np.empty((len(obs_pt), 2))
-    for i in range(args.cams):
-        m = obs_img == i
-        if m.any():
-            xy[m] = synthetic.project_simple_radial(cam_params[img_cam[i]], qvec[i], tvec[i], xyz[obs_pt[m]])
+    # all observations at once: rotate by the observation's quaternion (same arithmetic as project_simple_radial)
+    qo = qvec[obs_img] / np.linalg.norm(qvec[obs_img], axis=1, keepdims=True)
+    w_, x_, y_, z_ = qo[:, 0], qo[:, 1], qo[:, 2], qo[:, 3]
+    Xo = xyz[obs_pt]
+    R = np.stack([1 - 2 * (y_ * y_ + z_ * z_), 2 * (x_ * y_ - w_ * z_), 2 * (x_ * z_ + w_ * y_),
+                  2 * (x_ * y_ + w_ * z_), 1 - 2 * (x_ * x_ + z_ * z_), 2 * (y_ * z_ - w_ * x_),
+                  2 * (x_ * z_ - w_ * y_), 2 * (y_ * z_ + w_ * x_), 1 - 2 * (x_ * x_ + y_ * y_)], 1).reshape(-1, 3, 3)
+    pc = np.einsum("nij,nj->ni", R, Xo) + tvec[obs_img]
+    un, vn = pc[:, 0] / pc[:, 2], pc[:, 1] / pc[:, 2]
+    cp = cam_params[img_cam[obs_img]]
+    rad = cp[:, 3] * (un * un + vn * vn)
+    xy = np.stack([cp[:, 0] * (un + un * rad) + cp[:, 1], cp[:, 0] * (vn + vn * rad) + cp[:, 2]], 1)
     ps = args.ps
     scale = np.ones((len(obs_pt), 2))
     corners = np.clip((xy * scale - ps / 2.0).astype(np.int32), [0, 0], np.array([1000, 1000]) - ps - 1).astype(np.int32)
@@ -187,7 +204,8 @@ def cpu_arm(args, g, d_patches, refs, ctx, steps, label):
     prob = make_problem(args, g, host, False, sel=(n_pts, n_obs))
     prob.refs = np.ascontiguousarray(refs[:n_pts])
     ic = _capi.default_interp()
-    so = _capi.default_ba_options(use_inner_iterations=0 if args.no_inner else 1, max_num_iterations=steps)
+    so = _capi.default_ba_options(use_inner_iterations=0 if args.no_inner else 1, max_num_iterations=steps,
+                                  linear_solver=args.linear_solver)
     O.lib().orc_set_num_threads(usable_cpus())
     cores = O.lib().orc_num_threads()
     t0 = time.time()
@@ -242,7 +260,7 @@ def main():
     config = {"workload": workload, "baseline_config": "configs[2]", "use_inner_iterations": bool(inner),
               "parallelism": "point-sharded x%d, cameras replicated, NCCL allreduce of the reduced camera system" % world,
               "l2_flush": "inputs (%.1f GB of taps per pass) larger than L2" % (n_obs * 4096 / 1e9),
-              "step": "one LM iteration (step solve + trial cost%s + Jacobian on acceptance)" % (" + inner iterations" if inner else "")}
+              "step": "one LM iteration (step solve + trial-point evaluation%s; the trial evaluation runs in Jacobian mode and is reused as the next linearisation on acceptance)" % (" + inner iterations while active" if inner else "")}
 
     if args.impl == "reference":
         cb = cpu_arm(args, g, d_patches, refs, ctx, max(1, args.steps), "reference arm")
@@ -255,7 +273,8 @@ def main():
         print(json.dumps(line))
         return 0
 
-    so = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.warmup + args.steps)
+    so = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.warmup + args.steps,
+                                  linear_solver=args.linear_solver)
     h = _engine.BAHandle(prob, ic, so, ctx=ctx)
     # ---- warm-up: W iterations of the trajectory (plus iteration zero)
     h.iterate(max(args.warmup, 0))
@@ -330,7 +349,8 @@ def main():
             g2 = geometry(args, rank)
             prob_h = make_problem(args, g2, host, False)
             prob_h.refs = refs
-            so2 = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.steps)
+            so2 = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.steps,
+                                           linear_solver=args.linear_solver)
             if dist is not None:
                 dist.barrier()
             t0 = time.time()
@@ -354,7 +374,7 @@ def main():
             e2e = {"value": None, "unit": "observations/s", "error": repr(ex)}
 
     cb = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.cpu_sample_points > 0:
         try:
             cb = cpu_arm(args, g, d_patches, refs, ctx, 2, "cpu_baseline")
         except Exception as ex:
