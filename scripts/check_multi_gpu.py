@@ -30,7 +30,11 @@ def main():
     ctx.init_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
 
     ok_all = True
-    for inner, solver in ((0, 0), (1, 0), (0, 3)):
+    for inner, solver, sparse in ((0, 0, 0), (1, 0, 0), (0, 3, 0), (0, 3, 1)):
+        if sparse:
+            os.environ["PXR_PCG_SPARSE"] = "1"     # implicit block-sparse reduced system, q all-reduced per CG iteration
+        else:
+            os.environ.pop("PXR_PCG_SPARSE", None)
         prob, _ = synthetic.make_ba_scene(n_cams=40, n_points=480, track_len=5, channels=16, seed=77)
         ic = _capi.default_interp()
         so = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=10, linear_solver=solver)
@@ -60,8 +64,8 @@ def main():
             dx = np.abs(shard.xyz - full.xyz[p0:p1]).max()
             dc = abs(s["final_cost"] - sr["final_cost"]) / sr["final_cost"]
             ok = same and dq < tol and dt < tol and dx < tol and dc < 1e-5 and s["num_iterations"] == sr["num_iterations"]
-            print("inner=%d solver=%d world=%d: ranks identical=%s  |dq|=%.2e |dt|=%.2e |dX|=%.2e  dcost=%.2e  iters %d/%d  -> %s"
-                  % (inner, solver, world, same, dq, dt, dx, dc, s["num_iterations"], sr["num_iterations"], "OK" if ok else "MISMATCH"), flush=True)
+            print("inner=%d solver=%d sparse=%d world=%d: ranks identical=%s  |dq|=%.2e |dt|=%.2e |dX|=%.2e  dcost=%.2e  iters %d/%d  -> %s"
+                  % (inner, solver, sparse, world, same, dq, dt, dx, dc, s["num_iterations"], sr["num_iterations"], "OK" if ok else "MISMATCH"), flush=True)
             ok_all = ok_all and ok
     dist.barrier()
     dist.destroy_process_group()
