@@ -425,6 +425,9 @@ class CostMapExtractor:
                                            upsampling_factor=float(self.config.upsampling_factor), compute_refs=1,
                                            ref_loss_type=rlt, ref_loss_scale=rls, ref_iters=int(ref_extractor.config.iters))
         ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
+        if any(not (feature_set.fmap(name) if hasattr(feature_set, "fmap") else feature_set[name]).is_sparse
+               for name in ir.slab_offsets):
+            raise ValueError("cost maps from dense feature maps (dense_cut_size slicing, costmap_extractor.h:186-200) are not built")
         out = _engine.costmaps_compute(prob, ic, cfg)
         for k, pid in enumerate(ir.point_ids):
             if out["src_obs"][k] < 0:

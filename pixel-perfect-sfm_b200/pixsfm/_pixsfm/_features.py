@@ -100,11 +100,14 @@ class FeatureMap:
         return self.patches.shape[0]
 
     def has_point2D(self, point2D_idx):
+        # featuremap.h:113-119: a dense map answers for every keypoint with its single kDensePatchId patch
+        if not self.is_sparse:
+            return len(self._index) == 1 and kDenseId in self._index
         return int(point2D_idx) in self._index
 
     def local_index(self, point2D_idx):
-        if not self.is_sparse and kDenseId in self._index:
-            raise ValueError("dense feature maps are not supported on the B200 path yet")
+        if not self.is_sparse:
+            return self._index[kDenseId]            # GetFeaturePatch (featuremap.h:104-111)
         return self._index[int(point2D_idx)]
 
     def fpatch(self, point2D_idx):

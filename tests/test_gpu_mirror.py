@@ -149,3 +149,42 @@ def test_topological_reference_keypoint_adjuster_matches_flat_oracle():
         name = g.image_id_to_name[node.image_id]
         d = np.abs(keypoints[name][node.feature_idx] - before[name][node.feature_idx]).max()
         assert (d == 0.0) if root_labels[n] else (d > 0.0)
+
+
+def test_dense_feature_maps_match_oracle():
+    """Dense FeatureMaps (one kDenseId patch per image answering for every keypoint, featuremap.h:104-119) run through
+    the same kernels: many observations share one large patch.  GPU vs oracle on the IR the mirror builds."""
+    rec, fm_sparse, prob0, gt = make_reconstruction(n_cams=5, n_points=40, track_len=3, channels=16, seed=41)
+    rng = np.random.default_rng(7)
+    H = W = 72
+    fm = features.FeatureManager([16], np.float16)
+    for name in fm_sparse.fset(0).keys():
+        # a smooth random field so that the bicubic gradients are informative
+        base_f = rng.normal(size=(H // 8 + 2, W // 8 + 2, 16))
+        yy, xx = np.meshgrid(np.linspace(1, H // 8, H), np.linspace(1, W // 8, W), indexing="ij")
+        y0, x0 = yy.astype(int), xx.astype(int)
+        fy, fx = (yy - y0)[..., None], (xx - x0)[..., None]
+        dense = ((1 - fy) * (1 - fx) * base_f[y0, x0] + (1 - fy) * fx * base_f[y0, x0 + 1]
+                 + fy * (1 - fx) * base_f[y0 + 1, x0] + fy * fx * base_f[y0 + 1, x0 + 1]).astype(np.float16)
+        fm.fset(0).emplace(name, features.FeatureMap(np.ascontiguousarray(dense[None]), [features.kDenseId], np.zeros((1, 2), np.int32),
+                                                     {"scale": (W / 1000.0, H / 1000.0), "is_sparse": False}))
+    rec_ref = copy.deepcopy(rec)
+    conf = {"optimizer": {"solver": {"max_num_iterations": 8}}}
+    out = ba_pkg.BundleAdjuster.create(conf).refine_multilevel(rec, fm)
+    s = out["summary"][0]
+    fview = features.FeatureView(fm.fset(0), rec_ref)
+    ic = _capi.default_interp()
+    prob_r, ir_r = ba.build_problem(rec_ref, fview, None, None, None, for_references=set(rec_ref.points3D.keys()))
+    assert prob_r.n_patches == 5 and prob_r.n_obs == 120 and (prob_r.ph, prob_r.pw) == (H, W)
+    refs_o, src_o = O.refs_compute(prob_r, ic, iters=100)
+    oracle_refs = {pid: features.Reference(ir_r.obs[int(src_o[k])][:2], refs_o[k].reshape(1, -1)) for k, pid in enumerate(ir_r.point_ids)}
+    prob, ir = ba.build_problem(rec_ref, fview, ba_pkg.default_problem_setup(rec_ref), ba.BundleOptimizerOptions(), oracle_refs)
+    so = _capi.default_ba_options(use_inner_iterations=1, max_num_iterations=8)
+    s_o = O.ba_solve(prob, ic, so)
+    assert s.num_iterations == s_o["num_iterations"]
+    assert abs(s.final_cost - s_o["final_cost"]) <= 1e-6 * s_o["final_cost"]
+    ba.write_back(rec_ref, prob, ir)
+    for p in rec.points3D:
+        assert np.abs(rec.points3D[p].xyz - rec_ref.points3D[p].xyz).max() < 1e-6
+    with pytest.raises(ValueError):
+        ba_pkg.BundleAdjuster.create({"strategy": "costmaps"}).refine_multilevel(copy.deepcopy(rec), fm)
