@@ -288,6 +288,11 @@ int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_con
                      int loss_type, double loss_scale, int iters,
                      double* refs_out, int64_t* src_obs_out, pxr_summary* summary);
 
+/* descriptors of every observation at its current projection = ReferenceExtractor::FillDescriptorTrack
+ * (reference_extractor.h:207-237), what Reference.observations holds with keep_observations=True (needed by
+ * FindNearestReferences).  out_desc [n_obs][channels] fp64, in observation order. */
+int pxr_obs_descriptors(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp, double* out_desc);
+
 /* ---- cost maps ---------------------------------------
  * replaces _bundle_adjustment.CostMapExtractor.run (bundle_adjustment/bindings.cc:20-26,179-184;
  * costmap_extractor.h:93-228 Run/RunSubset, :230-358 FillPointCostmap) followed, on the caller's side,
@@ -317,6 +322,17 @@ int pxr_default_costmap_config(pxr_costmap_config* cfg);
 int pxr_costmaps_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
                          const pxr_costmap_config* cfg, double* refs_io, int64_t* src_obs_out,
                          void* out_host, void** out_device, pxr_summary* summary);
+
+/* ---- descriptor interpolation ------------------------------------------------
+ * replaces _features.PatchInterpolator(cfg).interpolate / interpolate_nodes for one node
+ * (features/bindings.cc, features/src/patch_interpolator.h:125-135, dynamic_patch_interpolator.h): the bicubic
+ * (+ L2-normalised) descriptor of patch item_patch[i] at image coordinates xy[i], the quantity
+ * FindNearestReferences (localization/src/nearest_references.h:20-53) and find_feature_inliers compare.
+ *  patches [n_patches][ph][pw][channels] host memory; corner/scale per patch; out_desc [n_items][channels] fp64 */
+int pxr_interpolate_descriptors(pxr_ctx* ctx, const void* patches, int64_t n_patches, int32_t patch_dtype,
+                                int32_t ph, int32_t pw, int32_t channels, const int32_t* corner, const double* scale,
+                                double upsampling_factor, int64_t n_items, const int64_t* item_patch, const double* xy,
+                                const pxr_interp_config* interp, double* out_desc);
 
 /* ---- featuremetric KA ---------------------------------------------------
  * replaces _keypoint_adjustment.FeatureMetricKeypointOptimizer.run
@@ -348,6 +364,13 @@ typedef struct {
   int32_t n_patch_blocks;
   const void* const* patch_block_ptrs;
   const int64_t* patch_block_counts;
+  /* optional "query" mode (localization/src/single_query_keypoint_optimizer.h:84-203, residual
+   * FeatureReference2DCostFunctor, residuals/src/feature_reference.h:14-62): when ref_desc != NULL EVERY edge is
+   * (keypoint edge_src[e]) against the FIXED descriptor ref_desc[edge_dst[e]]; edge_dst then indexes ref_desc, not
+   * keypoints.  The normal equations are block diagonal (2x2 per keypoint), so a problem may hold any number of
+   * keypoints; all keypoints of one problem still share one trust region, as in the reference's single ceres::Problem. */
+  const double* ref_desc;       /* [n_ref_desc][channels] fp64 or NULL */
+  int64_t n_ref_desc;
 } pxr_ka_desc;
 
 int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* desc, const pxr_interp_config* interp,

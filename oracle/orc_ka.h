@@ -72,7 +72,8 @@ class KAProblemEvaluator : public TREvaluator {
   void Finalize() {
     // will_be_optimized_: keypoints touched by at least one residual block
     for (int64_t e : edges) {
-      for (int64_t kp : {d.edge_src[e], d.edge_dst[e]}) {
+      for (int q = 0; q < (d.ref_desc ? 1 : 2); ++q) {    // query mode: edge_dst indexes ref_desc
+        const int64_t kp = q == 0 ? d.edge_src[e] : d.edge_dst[e];
         if (d.kp_const[kp]) continue;
         if (var_idx.find(kp) == var_idx.end()) { var_idx[kp] = (int)var_kps.size(); var_kps.push_back(kp); }
       }
@@ -124,12 +125,17 @@ class KAProblemEvaluator : public TREvaluator {
     double total = 0;
     for (int64_t e : edges) {
       const int64_t k1 = d.edge_src[e], k2 = d.edge_dst[e];
-      if (k1 == k2) continue;  // "Avoid optimizing a keypoint to itself" (topological_keypoint_optimizer.h:139-143)
-      int v1, v2;
+      if (!d.ref_desc && k1 == k2) continue;  // "Avoid optimizing a keypoint to itself" (topological_keypoint_optimizer.h:139-143)
+      int v1, v2 = -1;
       const double* x1 = KP(x, k1, &v1);
-      const double* x2 = KP(x, k2, &v2);
       KAInterp(MakeKAPatch(d, k1), ic, x1, f1.data(), with_jac ? a1.data() : nullptr, b1.data(), tmp);
-      KAInterp(MakeKAPatch(d, k2), ic, x2, f2.data(), with_jac ? a2.data() : nullptr, b2.data(), tmp);
+      if (d.ref_desc) {
+        // FeatureReference2DCostFunctor (residuals/src/feature_reference.h:44-59): target - fixed reference
+        for (int i = 0; i < C; ++i) { f2[i] = d.ref_desc[(size_t)k2 * C + i]; a2[i] = 0; b2[i] = 0; }
+      } else {
+        const double* x2 = KP(x, k2, &v2);
+        KAInterp(MakeKAPatch(d, k2), ic, x2, f2.data(), with_jac ? a2.data() : nullptr, b2.data(), tmp);
+      }
       double s = 0;
       for (int i = 0; i < C; ++i) { r[i] = f1[i] - f2[i]; s += r[i] * r[i]; }
       Loss l = base_loss; l.weight = d.edge_weight ? d.edge_weight[e] : 1.0;
@@ -196,9 +202,10 @@ inline int KAEvaluateAll(const pxr_ka_desc& d, const InterpConfig& ic, const pxr
   for (int64_t e = 0; e < d.n_edges; ++e) {
     std::vector<double> f1(C), f2(C), tmp;
     const int64_t k1 = d.edge_src[e], k2 = d.edge_dst[e];
-    if (k1 == k2) { if (sq_norm) sq_norm[e] = 0; continue; }
+    if (!d.ref_desc && k1 == k2) { if (sq_norm) sq_norm[e] = 0; continue; }
     KAInterp(MakeKAPatch(d, k1), ic, d.keypoints + 2 * k1, f1.data(), nullptr, nullptr, tmp);
-    KAInterp(MakeKAPatch(d, k2), ic, d.keypoints + 2 * k2, f2.data(), nullptr, nullptr, tmp);
+    if (d.ref_desc) for (int i = 0; i < C; ++i) f2[i] = d.ref_desc[(size_t)k2 * C + i];
+    else KAInterp(MakeKAPatch(d, k2), ic, d.keypoints + 2 * k2, f2.data(), nullptr, nullptr, tmp);
     double s = 0;
     for (int i = 0; i < C; ++i) { const double r = f1[i] - f2[i]; s += r * r; }
     if (sq_norm) sq_norm[e] = s;

@@ -48,6 +48,10 @@ struct KAArgs {
   int jacobi_scaling;
   // outputs per problem: initial cost, final cost, iterations, successful, unsuccessful, termination
   double* prob_out;                 // [P][6]
+  // query mode (REF): every edge is (keypoint e_k1, fixed descriptor ref_desc[e_k2]); block-diagonal normal equations,
+  // workspace in global memory so that a problem may hold any number of keypoints
+  const double* ref_desc;           // [n_ref][C]
+  double* workspace; const int64_t* ws_off;   // per problem: 26 * nv doubles at workspace + ws_off[p]
   int n_max;                        // max 2*nv over problems (shared memory sizing)
 };
 
@@ -114,7 +118,8 @@ struct KAWork {
 };
 
 // mode 0: cost, 1: cost + gradient (into gout), 2: cost + gradient + J^T J (into H, gout)
-template <typename T, int C, bool FS>
+// REF: block-diagonal mode, H holds (h00, h10, h11) per keypoint
+template <typename T, int C, bool FS, bool REF>
 __device__ double ka_evaluate(const KAArgs& a, const KAWork& w, int64_t eb, int64_t ee, int n, const double* xv, int mode,
                               double* gout) {
   constexpr int CPL = C >= 32 ? C / 32 : 1;
@@ -123,27 +128,32 @@ __device__ double ka_evaluate(const KAArgs& a, const KAWork& w, int64_t eb, int6
   const bool active = lane < ACTIVE;
   __syncthreads();
   if (mode >= 1) for (int i = threadIdx.x; i < n; i += kKAThreads) gout[i] = 0.0;
-  if (mode == 2) for (int i = threadIdx.x; i < n * (n + 1) / 2; i += kKAThreads) w.H[i] = 0.0;
+  if (mode == 2) for (int i = threadIdx.x; i < (REF ? 3 * (n / 2) : n * (n + 1) / 2); i += kKAThreads) w.H[i] = 0.0;
   __syncthreads();
   double cost = 0.0;
   for (int64_t e = eb + warp; e < ee; e += kKAWarps) {
     const int64_t k1 = a.e_k1[e], k2 = a.e_k2[e];
-    if (k1 == k2) continue;  // "Avoid optimizing a keypoint to itself" (topological_keypoint_optimizer.h:139-143)
-    const int v1 = a.e_v1[e], v2 = a.e_v2[e];
-    double p1[2], p2[2];
+    if (!REF && k1 == k2) continue;  // "Avoid optimizing a keypoint to itself" (topological_keypoint_optimizer.h:139-143)
+    const int v1 = a.e_v1[e], v2 = REF ? -1 : a.e_v2[e];
+    double p1[2], p2[2] = {0.0, 0.0};
     if (v1 >= 0) { p1[0] = xv[2 * v1]; p1[1] = xv[2 * v1 + 1]; } else { p1[0] = a.keypoints[2 * k1]; p1[1] = a.keypoints[2 * k1 + 1]; }
-    if (v2 >= 0) { p2[0] = xv[2 * v2]; p2[1] = xv[2 * v2 + 1]; } else { p2[0] = a.keypoints[2 * k2]; p2[1] = a.keypoints[2 * k2 + 1]; }
-    double xc1, xr1, xc2, xr2, sx1, sy1, sx2, sy2;
+    if (!REF) { if (v2 >= 0) { p2[0] = xv[2 * v2]; p2[1] = xv[2 * v2 + 1]; } else { p2[0] = a.keypoints[2 * k2]; p2[1] = a.keypoints[2 * k2 + 1]; } }
+    double xc1, xr1, xc2 = 0, xr2 = 0, sx1, sy1, sx2 = 0, sy2 = 0;
     const GlobalWindow w1 = make_window<T, C>(a, k1, p1, xc1, xr1, sx1, sy1);
-    const GlobalWindow w2 = make_window<T, C>(a, k2, p2, xc2, xr2, sx2, sy2);
+    GlobalWindow w2 = w1;
+    if (!REF) w2 = make_window<T, C>(a, k2, p2, xc2, xr2, sx2, sy2);
     double f1[CPL], r1[CPL], c1[CPL], f2[CPL], r2[CPL], c2[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) { f1[k] = r1[k] = c1[k] = f2[k] = r2[k] = c2[k] = 0.0; }
     double s;
     double red[14];
     if (mode == 0) {
-      if (active) { bicubic_window<T, C, CPL, false, FS>(w1, lane, xc1, xr1, f1, r1, c1); bicubic_window<T, C, CPL, false, FS>(w2, lane, xc2, xr2, f2, r2, c2); }
-      if (a.l2_normalize) { l2_normalize_desc<CPL, false>(active, f1, r1, c1); l2_normalize_desc<CPL, false>(active, f2, r2, c2); }
+      if (active) { bicubic_window<T, C, CPL, false, FS>(w1, lane, xc1, xr1, f1, r1, c1); if (!REF) bicubic_window<T, C, CPL, false, FS>(w2, lane, xc2, xr2, f2, r2, c2); }
+      if (a.l2_normalize) { l2_normalize_desc<CPL, false>(active, f1, r1, c1); if (!REF) l2_normalize_desc<CPL, false>(active, f2, r2, c2); }
+      if (REF && active) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) f2[k] = a.ref_desc[k2 * C + lane * CPL + k];   // the fixed reference descriptor
+      }
       double ss = 0.0;
       if (active) {
 #pragma unroll
@@ -151,8 +161,12 @@ __device__ double ka_evaluate(const KAArgs& a, const KAWork& w, int64_t eb, int6
       }
       s = warp_sum(ss);
     } else {
-      if (active) { bicubic_window<T, C, CPL, true, FS>(w1, lane, xc1, xr1, f1, r1, c1); bicubic_window<T, C, CPL, true, FS>(w2, lane, xc2, xr2, f2, r2, c2); }
-      if (a.l2_normalize) { l2_normalize_desc<CPL, true>(active, f1, r1, c1); l2_normalize_desc<CPL, true>(active, f2, r2, c2); }
+      if (active) { bicubic_window<T, C, CPL, true, FS>(w1, lane, xc1, xr1, f1, r1, c1); if (!REF) bicubic_window<T, C, CPL, true, FS>(w2, lane, xc2, xr2, f2, r2, c2); }
+      if (a.l2_normalize) { l2_normalize_desc<CPL, true>(active, f1, r1, c1); if (!REF) l2_normalize_desc<CPL, true>(active, f2, r2, c2); }
+      if (REF && active) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) f2[k] = a.ref_desc[k2 * C + lane * CPL + k];   // r2 = c2 = 0: no derivative
+      }
       double v[15];
 #pragma unroll
       for (int k = 0; k < 15; ++k) v[k] = 0.0;
@@ -188,12 +202,20 @@ __device__ double ka_evaluate(const KAArgs& a, const KAWork& w, int64_t eb, int6
           // dot(Ga, Gb) for the 4 columns
           const double dd[4][4] = {{red[4], red[5], red[10], red[11]}, {red[5], red[6], red[12], red[13]},
                                    {red[10], red[12], red[7], red[8]}, {red[11], red[13], red[8], red[9]}};
+          if (REF) {
+            if (v1 >= 0) {
+              atomicAdd(&w.H[3 * v1 + 0], rho[1] * cf[0] * cf[0] * dd[0][0]);
+              atomicAdd(&w.H[3 * v1 + 1], rho[1] * cf[1] * cf[0] * dd[1][0]);
+              atomicAdd(&w.H[3 * v1 + 2], rho[1] * cf[1] * cf[1] * dd[1][1]);
+            }
+          } else {
           for (int q = 0; q < 4; ++q)
             for (int t = 0; t < 4; ++t) {
               if (col[q] < 0 || col[t] < 0 || col[q] < col[t]) continue;
               if (col[q] == col[t] && q != t) continue;
               atomicAdd(&w.H[tri(col[q], col[t])], rho[1] * cf[q] * cf[t] * dd[q][t]);
             }
+          }
         }
       }
     }
@@ -317,9 +339,10 @@ __device__ double ka_min_interp_poly(const KASample* smp, int ns, double xmin, d
 
 enum { C_STOP = 0, C_RADIUS, C_DECF, C_XCOST, C_CURCOST, C_XNORM, C_GMAX, C_MCC, C_CAND, C_TMP, C_TMP2, C_FLAG, C_N };
 
-template <typename T, int C, bool FS>
+template <typename T, int C, bool FS, bool REF>
 __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
   extern __shared__ __align__(16) double sm[];
+  auto hdiag = [](int i) { return REF ? 3 * (i >> 1) + ((i & 1) ? 2 : 0) : tri(i, i); };
   const int p = blockIdx.x;
   if (p >= a.n_problems) return;
   const int64_t eb = a.prob_edge_begin[p], ee = a.prob_edge_begin[p + 1];
@@ -328,7 +351,13 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
   const int n = 2 * nv;
   const int nmax = a.n_max;
   KAWork w;
-  {
+  if (REF) {
+    double* q = a.workspace + a.ws_off[p];           // global memory: n is not bounded in query mode
+    w.H = q; q += 3 * nv; w.L = q; q += 3 * nv;
+    w.g = q; q += n; w.gq = q; q += n; w.x = q; q += n; w.cand = q; q += n; w.delta = q; q += n;
+    w.scale = q; q += n; w.D2 = q; q += n; w.lo = q; q += n; w.hi = q; q += n; w.tmp = q; q += n;
+    w.wcost = sm; w.ctrl = sm + kKAWarps;
+  } else {
     double* q = sm;
     const int tsz = nmax * (nmax + 1) / 2;
     w.H = q; q += tsz; w.L = q; q += tsz;
@@ -339,7 +368,7 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
   const int tid = threadIdx.x;
   double* out = a.prob_out + (int64_t)p * 6;
   if (n == 0) {
-    const double c = ka_evaluate<T, C, FS>(a, w, eb, ee, 0, w.x, 0, w.g);
+    const double c = ka_evaluate<T, C, FS, REF>(a, w, eb, ee, 0, w.x, 0, w.g);
     if (tid == 0) { out[0] = c; out[1] = c; out[2] = 0; out[3] = 0; out[4] = 0; out[5] = 0; }
     return;
   }
@@ -352,7 +381,7 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
     if (constrained) v = fmin(fmax(v, w.lo[i]), w.hi[i]);  // IterationZero: x = Plus(x, 0)
     w.x[i] = v;
   }
-  double x_cost = ka_evaluate<T, C, FS>(a, w, eb, ee, n, w.x, 2, w.g);
+  double x_cost = ka_evaluate<T, C, FS, REF>(a, w, eb, ee, n, w.x, 2, w.g);
   auto reduce_max_proj_grad = [&]() {  // ||x - Plus(x, -g)||_inf, result in ctrl[C_TMP]
     __syncthreads();
     double m = 0.0;
@@ -373,7 +402,7 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
     __syncthreads();
     return t;
   };
-  for (int i = tid; i < n; i += kKAThreads) w.scale[i] = a.jacobi_scaling ? 1.0 / (1.0 + sqrt(w.H[tri(i, i)])) : 1.0;
+  for (int i = tid; i < n; i += kKAThreads) w.scale[i] = a.jacobi_scaling ? 1.0 / (1.0 + sqrt(w.H[hdiag(i)])) : 1.0;
   { double v = 0; for (int i = tid; i < n; i += kKAThreads) v += w.x[i] * w.x[i]; const double t = block_sum(v); if (tid == 0) w.ctrl[C_XNORM] = sqrt(t); }
   reduce_max_proj_grad();
   if (tid == 0) {
@@ -394,16 +423,41 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
     // ---- LM step: (H + D) delta = -g
     for (int i = tid; i < n; i += kKAThreads) {
       const double s2 = w.scale[i] * w.scale[i];
-      w.D2[i] = fmin(fmax(w.H[tri(i, i)] * s2, a.min_diag), a.max_diag) / (radius * s2);
+      w.D2[i] = fmin(fmax(w.H[hdiag(i)] * s2, a.min_diag), a.max_diag) / (radius * s2);
       w.delta[i] = -w.g[i];
     }
     __syncthreads();
+    bool valid;
+    double mcc = 0.0;
+    if (REF) {
+      // block-diagonal system: one 2x2 Cholesky + solve per keypoint
+      if (tid == 0) w.ctrl[C_FLAG] = 0.0;
+      __syncthreads();
+      double part = 0.0;
+      for (int v = tid; v < nv; v += kKAThreads) {
+        const double h00 = w.H[3 * v], h10 = w.H[3 * v + 1], h11 = w.H[3 * v + 2];
+        const double a00 = h00 + w.D2[2 * v], a11 = h11 + w.D2[2 * v + 1];
+        bool ok = a00 > 0.0 && isfinite(a00);
+        const double l00 = sqrt(ok ? a00 : 1.0), l10 = h10 / l00;
+        const double s11 = a11 - l10 * l10;
+        ok = ok && s11 > 0.0 && isfinite(s11);
+        const double l11 = sqrt(ok ? s11 : 1.0);
+        if (!ok) w.ctrl[C_FLAG] = 1.0;
+        const double y0 = w.delta[2 * v] / l00, y1 = (w.delta[2 * v + 1] - l10 * y0) / l11;
+        const double d1 = y1 / l11, d0 = (y0 - l10 * d1) / l00;
+        w.delta[2 * v] = d0; w.delta[2 * v + 1] = d1;
+        const double hd0 = h00 * d0 + h10 * d1, hd1 = h10 * d0 + h11 * d1;
+        part += w.g[2 * v] * d0 + 0.5 * d0 * hd0 + w.g[2 * v + 1] * d1 + 0.5 * d1 * hd1;
+        if (!isfinite(d0) || !isfinite(d1)) part = nan("");
+      }
+      mcc = -block_sum(part);
+      valid = w.ctrl[C_FLAG] == 0.0 && isfinite(mcc) && mcc > 0.0;
+    } else {
     for (int i = tid; i < n * (n + 1) / 2; i += kKAThreads) w.L[i] = w.H[i];
     __syncthreads();
     for (int i = tid; i < n; i += kKAThreads) w.L[tri(i, i)] += w.D2[i];
     __syncthreads();
-    bool valid = ka_cholesky(w.L, n, &w.ctrl[C_FLAG]);
-    double mcc = 0.0;
+    valid = ka_cholesky(w.L, n, &w.ctrl[C_FLAG]);
     if (valid) {
       ka_chol_solve(w.L, n, w.delta);
       // model cost change = -g.d - d^T H d / 2
@@ -416,6 +470,7 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
       }
       mcc = -block_sum(part);
       valid = isfinite(mcc) && mcc > 0.0;
+    }
     }
     if (!valid) {
       if (++invalid >= a.max_invalid) { term = 2; break; }
@@ -438,7 +493,7 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
       KASample initial = {0.0, x_cost, ig, 1, 1}, previous = {0, 0, 0, 0, 0}, current = {0, 0, 0, 0, 0};
       auto ls_eval = [&](double alpha, KASample& s) {
         for (int i = tid; i < n; i += kKAThreads) w.cand[i] = fmin(fmax(w.x[i] + alpha * w.delta[i], w.lo[i]), w.hi[i]);
-        const double c = ka_evaluate<T, C, FS>(a, w, eb, ee, n, w.cand, 1, w.gq);
+        const double c = ka_evaluate<T, C, FS, REF>(a, w, eb, ee, n, w.cand, 1, w.gq);
         double v = 0; for (int i = tid; i < n; i += kKAThreads) v += w.gq[i] * w.delta[i];
         const double gd = block_sum(v);
         s.x = alpha; s.value = c; s.value_valid = isfinite(c) ? 1 : 0; s.gradient = gd; s.gradient_valid = (s.value_valid && isfinite(gd)) ? 1 : 0;
@@ -480,7 +535,7 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
       __syncthreads();
     } else {
       for (int i = tid; i < n; i += kKAThreads) w.cand[i] = w.x[i] + w.delta[i];
-      candidate_cost = ka_evaluate<T, C, FS>(a, w, eb, ee, n, w.cand, 0, w.gq);
+      candidate_cost = ka_evaluate<T, C, FS, REF>(a, w, eb, ee, n, w.cand, 0, w.gq);
       if (!isfinite(candidate_cost)) candidate_cost = 1.7976931348623157e308;
     }
     // ---- tolerances and step acceptance
@@ -491,7 +546,7 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
     if (rel > a.min_rel_dec) {
       __syncthreads();
       for (int i = tid; i < n; i += kKAThreads) w.x[i] = w.cand[i];
-      x_cost = ka_evaluate<T, C, FS>(a, w, eb, ee, n, w.x, 2, w.g);
+      x_cost = ka_evaluate<T, C, FS, REF>(a, w, eb, ee, n, w.x, 2, w.g);
       { double v = 0; for (int i = tid; i < n; i += kKAThreads) v += w.x[i] * w.x[i]; const double t = block_sum(v); if (tid == 0) w.ctrl[C_XNORM] = sqrt(t); }
       reduce_max_proj_grad();
       if (tid == 0) {
@@ -514,13 +569,16 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
 }
 
 template <typename T, int C>
-static int launch_ka(pxr_ctx* ctx, bool fs, const KAArgs& a, size_t smem) {
-  if (fs) {
-    PXR_CUDA(cudaFuncSetAttribute(ka_solve_kernel<T, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PXR_LAUNCH(ctx, (ka_solve_kernel<T, C, true>), a.n_problems, kKAThreads, smem, a);
+static int launch_ka(pxr_ctx* ctx, bool fs, bool ref, const KAArgs& a, size_t smem) {
+  if (ref) {
+    if (fs) return fail(PXR_ERR_UNSUPPORTED, "use_float_simd is not built for the query (reference-descriptor) mode");
+    PXR_LAUNCH(ctx, (ka_solve_kernel<T, C, false, true>), a.n_problems, kKAThreads, smem, a);
+  } else if (fs) {
+    PXR_CUDA(cudaFuncSetAttribute(ka_solve_kernel<T, C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PXR_LAUNCH(ctx, (ka_solve_kernel<T, C, true, false>), a.n_problems, kKAThreads, smem, a);
   } else {
-    PXR_CUDA(cudaFuncSetAttribute(ka_solve_kernel<T, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PXR_LAUNCH(ctx, (ka_solve_kernel<T, C, false>), a.n_problems, kKAThreads, smem, a);
+    PXR_CUDA(cudaFuncSetAttribute(ka_solve_kernel<T, C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PXR_LAUNCH(ctx, (ka_solve_kernel<T, C, false, false>), a.n_problems, kKAThreads, smem, a);
   }
   PXR_CUDA(cudaGetLastError());
   return PXR_OK;
@@ -539,6 +597,8 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
     return fail(PXR_ERR_INVALID_ARGUMENT, "a required array is NULL");
   pxr_interp_config ic; if (interp_in) ic = *interp_in; else pxr_default_interp_config(&ic);
   pxr_solver_options so; if (opt_in) so = *opt_in; else pxr_default_ka_options(&so);
+  const bool refmode = d->ref_desc != nullptr;
+  if (refmode && d->n_ref_desc <= 0) return fail(PXR_ERR_INVALID_ARGUMENT, "ref_desc without n_ref_desc");
   const int C = d->channels;
   const bool c_ok = (d->patch_dtype == PXR_F16 && (C == 128 || C == 64 || C == 32 || C == 16 || C == 8)) ||
                     (d->patch_dtype == PXR_F32 && (C == 128 || C == 16)) || (d->patch_dtype == PXR_F64 && (C == 128 || C == 16));
@@ -553,7 +613,8 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
     const int pl = d->edge_problem ? d->edge_problem[e] : 0;
     if (pl < 0 || pl >= P) return fail(PXR_ERR_INVALID_ARGUMENT, "edge_problem out of range");
     if (e && d->edge_problem && d->edge_problem[e] < d->edge_problem[e - 1]) return fail(PXR_ERR_INVALID_ARGUMENT, "edges must be sorted by problem label");
-    if (d->edge_src[e] < 0 || d->edge_src[e] >= d->n_keypoints || d->edge_dst[e] < 0 || d->edge_dst[e] >= d->n_keypoints)
+    if (d->edge_src[e] < 0 || d->edge_src[e] >= d->n_keypoints || d->edge_dst[e] < 0 ||
+        d->edge_dst[e] >= (refmode ? d->n_ref_desc : d->n_keypoints))
       return fail(PXR_ERR_INVALID_ARGUMENT, "edge endpoint out of range");
     peb[pl + 1]++;
   }
@@ -568,10 +629,10 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
     std::unordered_map<int64_t, int> idx;
     pvb[p] = (int32_t)var_kp.size();
     for (int64_t e = peb[p]; e < peb[p + 1]; ++e) {
-      const int64_t ks[2] = {d->edge_src[e], d->edge_dst[e]};
+      const int64_t ks[2] = {d->edge_src[e], refmode ? -1 : d->edge_dst[e]};
       int v[2] = {-1, -1};
       if (ks[0] != ks[1]) {
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < (refmode ? 1 : 2); ++q) {
           if (d->kp_const[ks[q]]) continue;
           auto it = idx.find(ks[q]);
           if (it == idx.end()) {
@@ -596,7 +657,7 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
     n_max = std::max(n_max, 2 * (int)idx.size());
   }
   pvb[P] = (int32_t)var_kp.size();
-  if (n_max > 160) return fail(PXR_ERR_UNSUPPORTED, "a KA problem has %d variable keypoints (> 80 supported per problem)", n_max / 2);
+  if (!refmode && n_max > 160) return fail(PXR_ERR_UNSUPPORTED, "a KA problem has %d variable keypoints (> 80 supported per problem)", n_max / 2);
   n_max = std::max(n_max, 2);
   // ---- upload
   DevBuf<int64_t> d_peb, d_k1, d_k2, d_varkp, d_kppatch;
@@ -651,10 +712,25 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
   a.min_rel_dec = so.min_relative_decrease; a.radius0 = so.initial_trust_region_radius; a.max_radius = so.max_trust_region_radius;
   a.min_radius = so.min_trust_region_radius; a.min_diag = so.min_lm_diagonal; a.max_diag = so.max_lm_diagonal;
   a.jacobi_scaling = so.jacobi_scaling; a.prob_out = d_out.p; a.n_max = n_max;
-  const size_t smem = ((size_t)n_max * (n_max + 1) + 10 * (size_t)n_max + kKAWarps + C_N) * sizeof(double);
+  // query mode: block-diagonal workspace in global memory, 26 doubles per variable keypoint
+  DevBuf<double> d_ref, d_ws;
+  DevBuf<int64_t> d_wsoff;
+  a.ref_desc = nullptr; a.workspace = nullptr; a.ws_off = nullptr;
+  if (refmode) {
+    std::vector<int64_t> wso(P + 1, 0);
+    for (int p = 0; p < P; ++p) wso[p + 1] = wso[p] + 26 * (int64_t)(pvb[p + 1] - pvb[p]);
+    PXR_TRY(d_ref.upload(d->ref_desc, (size_t)d->n_ref_desc * C, s));
+    PXR_TRY(d_wsoff.upload(wso.data(), wso.size(), s));
+    PXR_TRY(d_ws.alloc((size_t)std::max<int64_t>(wso[P], 1)));
+    PXR_CUDA(cudaStreamSynchronize(s));   // wso goes out of scope
+    a.ref_desc = d_ref.p; a.workspace = d_ws.p; a.ws_off = d_wsoff.p;
+    h2d += (double)d->n_ref_desc * C * 8;
+  }
+  const size_t smem = refmode ? (size_t)(kKAWarps + C_N) * sizeof(double)
+                              : ((size_t)n_max * (n_max + 1) + 10 * (size_t)n_max + kKAWarps + C_N) * sizeof(double);
   const bool fs = ic.use_float_simd != 0;
   int rc = PXR_ERR_UNSUPPORTED;
-#define PXR_KA_CASE(T, CC) if (C == CC) rc = launch_ka<T, CC>(ctx, fs, a, smem);
+#define PXR_KA_CASE(T, CC) if (C == CC) rc = launch_ka<T, CC>(ctx, fs, refmode, a, smem);
   if (d->patch_dtype == PXR_F16) { PXR_KA_CASE(__half, 128) PXR_KA_CASE(__half, 64) PXR_KA_CASE(__half, 32) PXR_KA_CASE(__half, 16) PXR_KA_CASE(__half, 8) }
   else if (d->patch_dtype == PXR_F32) { PXR_KA_CASE(float, 128) PXR_KA_CASE(float, 16) }
   else { PXR_KA_CASE(double, 128) PXR_KA_CASE(double, 16) }

@@ -255,3 +255,67 @@ extern "C" int pxr_costmaps_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const
   }
   return rc;
 }
+
+extern "C" int pxr_interpolate_descriptors(pxr_ctx* ctx, const void* patches, int64_t n_patches, int32_t patch_dtype, int32_t ph,
+                                           int32_t pw, int32_t channels, const int32_t* corner, const double* scale,
+                                           double ups, int64_t n_items, const int64_t* item_patch, const double* xy,
+                                           const pxr_interp_config* interp, double* out_desc) {
+  if (!ctx || !patches || !corner || !scale || !xy || !out_desc || n_items < 0 || n_patches <= 0)
+    return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!fm_supported(patch_dtype, channels))
+    return fail(PXR_ERR_UNSUPPORTED, "Unsupported dimensions (CHANNELS=%d, dtype=%d, N_NODES=1).", channels, patch_dtype);
+  pxr_interp_config ic; if (interp) ic = *interp; else pxr_default_interp_config(&ic);
+  if (n_items == 0) return PXR_OK;
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // patch pixel coordinates, FeaturePatch::ToPixelCoordinates (features/src/featurepatch.h:250-255)
+  std::vector<double> uv((size_t)n_items * 2);
+  for (int64_t i = 0; i < n_items; ++i) {
+    const int64_t pi = item_patch ? item_patch[i] : i;
+    if (pi < 0 || pi >= n_patches) return fail(PXR_ERR_INVALID_ARGUMENT, "item_patch out of range");
+    uv[2 * i] = (xy[2 * i] * scale[2 * pi] - 0.5 - (double)corner[2 * pi]) * ups;
+    uv[2 * i + 1] = (xy[2 * i + 1] * scale[2 * pi + 1] - 0.5 - (double)corner[2 * pi + 1]) * ups;
+  }
+  const size_t esz = patch_dtype == PXR_F16 ? 2 : (patch_dtype == PXR_F32 ? 4 : 8);
+  DevBuf<uint8_t> dp; DevBuf<double> duv, ddesc; DevBuf<int64_t> dip;
+  PXR_TRY(dp.upload((const uint8_t*)patches, (size_t)n_patches * ph * pw * channels * esz, s));
+  PXR_TRY(duv.upload(uv.data(), uv.size(), s));
+  if (item_patch) PXR_TRY(dip.upload(item_patch, n_items, s));
+  PXR_TRY(ddesc.alloc((size_t)n_items * channels));
+  FmEvalArgs a;
+  a.uv = duv.p; a.item_patch = item_patch ? dip.p : nullptr; a.item_ref = nullptr;
+  a.patches = dp.p; a.ph = ph; a.pw = pw; a.refs = nullptr;
+  a.begin = 0; a.end = n_items; a.item_index = nullptr; a.out = nullptr; a.residuals = nullptr; a.desc = ddesc.p;
+  a.loss.type = 0; a.loss.a = 1.0;
+  a.l2_normalize = ic.l2_normalize;
+  int np = 0;
+  PXR_TRY(launch_fm_eval(ctx, patch_dtype, channels, 0, ic.use_float_simd != 0, a, &np));
+  PXR_CUDA(cudaMemcpyAsync(out_desc, ddesc.p, (size_t)n_items * channels * 8, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
+  return PXR_OK;
+}
+
+extern "C" int pxr_obs_descriptors(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp, double* out_desc) {
+  if (!ctx || !desc || !out_desc) return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
+  pxr_ba_desc d = *desc;
+  d.refs = nullptr;
+  pxr_solver_options so;
+  pxr_default_ba_options(&so);
+  BA b;
+  PXR_TRY(b.create(ctx, &d, interp, &so, false));
+  if (b.n_obs == 0) return PXR_OK;
+  DevBuf<double> dsc;
+  PXR_TRY(dsc.alloc((size_t)b.n_obs * b.C));
+  PXR_TRY(b.project(b.cur, false, nullptr));
+  FmEvalArgs a;
+  a.uv = b.uv.p; a.item_patch = b.obs_patch.p; a.item_ref = nullptr;
+  a.patches = b.d_patches; a.ph = b.ph; a.pw = b.pw; a.refs = nullptr;
+  a.begin = 0; a.end = b.n_obs; a.item_index = nullptr; a.out = nullptr; a.residuals = nullptr; a.desc = dsc.p;
+  a.loss.type = 0; a.loss.a = 1.0;
+  a.l2_normalize = b.interp.l2_normalize;
+  int np = 0;
+  PXR_TRY(launch_fm_eval(ctx, b.dtype, b.C, 0, b.interp.use_float_simd != 0, a, &np));
+  PXR_CUDA(cudaMemcpyAsync(out_desc, dsc.p, (size_t)b.n_obs * b.C * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PXR_OK;
+}

@@ -335,6 +335,16 @@ class ReferenceExtractor:
                 continue
             image_id, p2D_idx, _ = ir.obs[int(src[k])]
             refs[pid] = Reference((image_id, p2D_idx), desc[k].reshape(1, -1).copy())
+        if self.config.keep_observations:
+            # refdata.observations / costs (reference_extractor.h:258-264): every observation's descriptor, in the
+            # order of the problem IR (track order), and its squared distance to the chosen reference's robust mean
+            # is not kept by the device path -> costs hold the distance to the chosen reference descriptor
+            obs_desc = _engine.obs_descriptors(prob, ic)
+            pidx = {pid: k for k, pid in enumerate(ir.point_ids)}
+            for o, (image_id, p2D_idx, pid) in enumerate(ir.obs):
+                r = refs[pid]
+                r.observations.append(obs_desc[o].reshape(1, -1).copy())
+                r.costs.append(float(((obs_desc[o] - desc[pidx[pid]]) ** 2).sum()))
         return refs
 
 

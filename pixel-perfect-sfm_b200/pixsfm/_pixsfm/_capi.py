@@ -104,7 +104,8 @@ class KADesc(C.Structure):
                 ("pw", C.c_int32), ("channels", C.c_int32), ("corner", C.c_void_p),
                 ("scale", C.c_void_p), ("upsampling_factor", C.c_double), ("bound", C.c_double),
                 ("patches_are_sparse", C.c_int32), ("n_patch_blocks", C.c_int32),
-                ("patch_block_ptrs", C.c_void_p), ("patch_block_counts", C.c_void_p)]
+                ("patch_block_ptrs", C.c_void_p), ("patch_block_counts", C.c_void_p),
+                ("ref_desc", C.c_void_p), ("n_ref_desc", C.c_int64)]
 
 
 def make_summary(capacity=256):
@@ -385,7 +386,7 @@ class KAProblem:
 
     def __init__(self, keypoints, kp_const, edge_src, edge_dst, edge_weight, edge_problem, n_problems, patches,
                  corner, scale, kp_patch=None, bound=4.0, patches_are_sparse=True, upsampling_factor=1.0,
-                 patch_blocks=None):
+                 patch_blocks=None, ref_desc=None):
         self.keypoints = _as(keypoints, np.float64, (-1, 2)).copy()
         self.kp_const = _as(kp_const, np.uint8)
         self.edge_src = _as(edge_src, np.int64)
@@ -395,6 +396,8 @@ class KAProblem:
         if len(self.edge_problem) > 1 and np.any(np.diff(self.edge_problem) < 0):
             raise ValueError("edges must be sorted by problem label")
         self.n_problems = int(n_problems)
+        # query mode: edge_dst indexes ref_desc [n_ref, C] (fixed descriptors) instead of keypoints
+        self.ref_desc = None if ref_desc is None else np.ascontiguousarray(ref_desc, np.float64)
         self.patch_blocks = None
         if patch_blocks is not None:
             # one block per FeatureMap (host numpy or device-resident), uploaded without host concatenation
@@ -447,6 +450,10 @@ class KAProblem:
         d.upsampling_factor = self.upsampling_factor
         d.bound = self.bound
         d.patches_are_sparse = int(self.patches_are_sparse)
+        if self.ref_desc is not None:
+            if self.ref_desc.ndim != 2 or self.ref_desc.shape[1] != self._shape[3]:
+                raise ValueError("ref_desc must be [n_ref, channels]")
+            d.ref_desc = _ptr(self.ref_desc); d.n_ref_desc = len(self.ref_desc)
         return d
 
     def copy(self):

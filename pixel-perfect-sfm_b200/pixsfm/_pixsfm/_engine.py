@@ -112,6 +112,16 @@ def refs_compute(problem, interp=None, loss_type=1, loss_scale=0.25, iters=100, 
     return refs, src
 
 
+def obs_descriptors(problem, interp=None, ctx=None):
+    """pxr_obs_descriptors: [n_obs, C] descriptors at the current projections (Reference.observations)"""
+    ctx = ctx or _capi.default_context()
+    interp = interp or _capi.default_interp()
+    d = problem.desc()
+    out = np.zeros((problem.n_obs, problem.channels))
+    _capi.check(ctx.lib.pxr_obs_descriptors(ctx.handle, C.byref(d), C.byref(interp), _p(out)))
+    return out
+
+
 def costmaps_compute(problem, interp=None, cfg=None, refs=None, to_host=True, to_device=False, ctx=None):
     """pxr_costmaps_compute == CostMapExtractor.run: reference extraction (unless cfg.compute_refs == 0) and one
     cost patch per observation patch.  -> dict(costmaps [n_patches,ph,pw,OC] in the patch dtype or None,

@@ -1,0 +1,4 @@
+from .main import (QueryKeypointAdjuster, QueryBundleAdjuster, QueryLocalizer, find_feature_inliers,  # noqa: F401
+                   find_unique_inliers, find_unique_min_by_group)
+from .._pixsfm._localization import (QueryKeypointOptimizer, QueryBundleOptimizer, QueryKeypointOptimizerOptions,  # noqa: F401
+                                     QueryBundleOptimizerOptions, find_nearest_references, interpolate_descriptors)

@@ -40,3 +40,22 @@ def test_ka_unconstrained_and_single_problem():
     s = _engine.ka_run(p_gpu, ic, so)
     assert abs(s["final_cost"] - c1) <= 1e-6 * c1
     assert np.abs(p_gpu.keypoints - p_cpu.keypoints).max() < 1e-5
+
+
+@pytest.mark.parametrize("channels,n_queries,bound", [(128, 3, 4.0), (16, 1, 4.0), (128, 2, -1.0)])
+def test_query_keypoint_adjustment_matches_oracle(channels, n_queries, bound):
+    """Query KA (localization/src/single_query_keypoint_optimizer.h:84-203): keypoints against FIXED reference
+    descriptors, all keypoints of a query in ONE trust region; block-diagonal normal equations on the GPU."""
+    from ka_util import make_query_ka_problem
+    prob, sc = make_query_ka_problem(n_queries=n_queries, bound=bound, n_images=6, n_tracks=40, track_len=4,
+                                     channels=channels, seed=6, kp_sigma=1.0)
+    assert len(prob.keypoints) == 160       # one query holds up to 160 keypoints: beyond the dense in-smem path (80)
+    ic = _capi.default_interp(); so = _capi.default_ka_options()
+    p_cpu, p_gpu = prob.copy(), prob.copy()
+    c0, c1 = O.ka_solve(p_cpu, ic, so)
+    s = _engine.ka_run(p_gpu, ic, so)
+    assert abs(s["initial_cost"] - c0) <= 1e-9 * c0
+    assert abs(s["final_cost"] - c1) <= 1e-6 * c1
+    assert c1 < 0.9 * c0
+    assert np.abs(p_gpu.keypoints - p_cpu.keypoints).max() < 1e-5
+    assert np.abs(p_gpu.keypoints - prob.keypoints).max() > 1e-2

@@ -164,3 +164,22 @@ def test_topological_reference_ka_surface():
     assert (o2.weight_by_sim, o2.root_regularize_weight, o2.root_edges_only) == (True, -1.0, False)
     opt = ka.TopologicalReferenceKeypointOptimizer({"bound": 2.0}, ka.KeypointAdjustmentSetup(), {})
     assert opt.options.root_edges_only and opt.options.bound == 2.0
+
+
+def test_localization_surface_and_defaults():
+    """localization/main.py:92-262 + query_refinement_options.h: class names, config keys, defaults."""
+    from pixsfm import localization as L
+    qka, qba = L.QueryKeypointAdjuster(), L.QueryBundleAdjuster()
+    assert qka.conf.optimizer.bound == 4.0 and qka.conf.optimizer.loss.name == "trivial"
+    assert qka.conf.optimizer.solver.parameter_tolerance == 1e-05 and qka.conf.stack_correspondences is False
+    assert qba.conf.optimizer.loss.name == "cauchy" and qba.conf.optimizer.refine_focal_length is False
+    o = L.QueryKeypointOptimizerOptions()
+    assert o.bound == -1.0 and o.solver["parameter_tolerance"] == 1.0e-4 and o.loss["name"] == "trivial"
+    b = L.QueryBundleOptimizerOptions()
+    assert b.solver["parameter_tolerance"] == 1.0e-5 and (b.refine_focal_length, b.refine_principal_point, b.refine_extra_params) == (False,) * 3
+    assert L.find_unique_inliers([3, 3, 5, 3, 5], pre_inliers=[False, True, True, True, True]) == [False, True, True, False, False]
+    assert L.find_unique_min_by_group([0.5, 0.2, 0.9, 0.1], [7, 7, 8, 8]) == [False, True, False, True]
+    with pytest.raises(ValueError):
+        L.QueryLocalizer(None, {}, references=None)
+    with pytest.raises(ValueError):
+        qka.solver.run(np.zeros((2, 2)), None, [None])          # references.size() != keypoints.rows()
