@@ -274,6 +274,50 @@ struct SchurPairs {
   int64_t n_chunks;
 };
 
+// Fast path of the pair kernels (dc <= 8): the 4 groups of 8 lanes of a warp each walk every 4th pair of the chunk;
+// lane (g, a) owns row a of the 8x8 block.  Two pairs per trip with their indices fetched one trip ahead, so the
+// dependent index -> row loads of consecutive pairs overlap (the kernel is bound by L2 gather latency, not math).
+__device__ __forceinline__ void schur_pairs_accumulate(const BADev& d, const SchurPairs& sp, const double* __restrict__ T,
+                                                       int64_t kb, int64_t ke, int g, int a, int dcx, int dcy, double acc[8]) {
+  const int dcm = d.dcmax;
+  double acc2[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) { acc[b] = 0.0; acc2[b] = 0.0; }
+  int64_t k = kb + g;
+  int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  if (k < ke) { x0 = sp.px[k]; y0 = sp.py[k]; }
+  if (k + 4 < ke) { x1 = sp.px[k + 4]; y1 = sp.py[k + 4]; }
+  while (k < ke) {
+    const int32_t cx0 = x0, cy0 = y0, cx1 = x1, cy1 = y1;
+    const bool two = k + 4 < ke;
+    const int64_t kn = k + 8;
+    if (kn < ke) { x0 = sp.px[kn]; y0 = sp.py[kn]; }
+    if (kn + 4 < ke) { x1 = sp.px[kn + 4]; y1 = sp.py[kn + 4]; }
+    if (a < dcx) {
+      const double* Tx0 = T + ((int64_t)cx0 * dcm + a) * 3;
+      const double* Wy0 = d.W + (int64_t)cy0 * dcm * 3;
+      const double* Tx1 = T + ((int64_t)cx1 * dcm + a) * 3;
+      const double* Wy1 = d.W + (int64_t)cy1 * dcm * 3;
+      const double t00 = Tx0[0], t01 = Tx0[1], t02 = Tx0[2];
+      double t10 = 0.0, t11 = 0.0, t12 = 0.0;
+      if (two) { t10 = Tx1[0]; t11 = Tx1[1]; t12 = Tx1[2]; }
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        if (b < dcy) {
+          acc[b] += t00 * Wy0[b * 3] + t01 * Wy0[b * 3 + 1] + t02 * Wy0[b * 3 + 2];
+          if (two) acc2[b] += t10 * Wy1[b * 3] + t11 * Wy1[b * 3 + 1] + t12 * Wy1[b * 3 + 2];
+        }
+    }
+    k = kn;
+  }
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    acc[b] += acc2[b];
+    acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 8);
+    acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
+  }
+}
+
 static __global__ void __launch_bounds__(256) ba_schur_pairs_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
                                                                     double* S) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -289,23 +333,7 @@ static __global__ void __launch_bounds__(256) ba_schur_pairs_kernel(BADev d, Sch
     // fast path: 4 groups of 8 lanes work on 4 entries at a time; lane (g, a) owns row a of the block
     const int g = lane >> 3, a = lane & 7;
     double acc[8];
-#pragma unroll
-    for (int b = 0; b < 8; ++b) acc[b] = 0.0;
-    for (int64_t k = kb + g; k < ke; k += 4) {
-      const double* Tx = T + ((int64_t)sp.px[k] * dcm + a) * 3;
-      const double* Wy = d.W + (int64_t)sp.py[k] * dcm * 3;
-      if (a < dcx) {
-        const double t0 = Tx[0], t1 = Tx[1], t2 = Tx[2];
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (b < dcy) acc[b] += t0 * Wy[b * 3] + t1 * Wy[b * 3 + 1] + t2 * Wy[b * 3 + 2];
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 8);
-      acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
-    }
+    schur_pairs_accumulate(d, sp, T, kb, ke, g, a, dcx, dcy, acc);
     if (g == 0 && a < dcx) {
       const int ca = d.Wcols[ox0 * dcm + a];
 #pragma unroll

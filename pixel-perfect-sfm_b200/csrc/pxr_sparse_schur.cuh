@@ -45,23 +45,7 @@ static __global__ void __launch_bounds__(256) sp_schur_pairs_kernel(BADev d, Sch
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
   const int g = lane >> 3, a = lane & 7;
   double acc[8];
-#pragma unroll
-  for (int b = 0; b < 8; ++b) acc[b] = 0.0;
-  for (int64_t k = kb + g; k < ke; k += 4) {
-    const double* Tx = T + ((int64_t)sp.px[k] * dcm + a) * 3;
-    const double* Wy = d.W + (int64_t)sp.py[k] * dcm * 3;
-    if (a < dcx) {
-      const double t0 = Tx[0], t1 = Tx[1], t2 = Tx[2];
-#pragma unroll
-      for (int b = 0; b < 8; ++b)
-        if (b < dcy) acc[b] += t0 * Wy[b * 3] + t1 * Wy[b * 3 + 1] + t2 * Wy[b * 3 + 2];
-    }
-  }
-#pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 8);
-    acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
-  }
+  schur_pairs_accumulate(d, sp, T, kb, ke, g, a, dcx, dcy, acc);
   if (g == 0 && a < dcx) {
     double* dst = Bk + ((int64_t)chunk_key[c] * 8 + a) * 8;
 #pragma unroll
