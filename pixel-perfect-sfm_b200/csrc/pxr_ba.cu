@@ -225,25 +225,34 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     // per-image column tables: an observation's camera columns are [pose columns | intrinsics columns] of its image
     int dc_needed = 0;
     h_img_cols.assign((size_t)n_images * 8, -1); h_img_pd.assign(n_images, 0);
+    std::vector<int8_t> h_src((size_t)n_images * 8, -1);     // entry of the Jacobian row [rot3 | t3 | X3 | cam K] per column
+    std::vector<int32_t> h_dc(n_images, 0);
     for (int i = 0; i < n_images; ++i) {
-      std::vector<int> cols;
+      std::vector<int> cols, src;
       if (h_pose_off[i] >= 0) {
-        for (int k = 0; k < 3; ++k) cols.push_back(h_pose_off[i] + k);
+        for (int k = 0; k < 3; ++k) { cols.push_back(h_pose_off[i] + k); src.push_back(k); }
         int la = 3;
-        for (int k = 0; k < 3; ++k) if (!(d->tvec_const_mask[i] & (1u << k))) cols.push_back(h_pose_off[i] + la++);
+        for (int k = 0; k < 3; ++k) if (!(d->tvec_const_mask[i] & (1u << k))) { cols.push_back(h_pose_off[i] + la++); src.push_back(3 + k); }
       }
       const int pd = (int)cols.size();
       const int cam_i = d->img_cam[i];
       if (h_intr_off[cam_i] >= 0) {
         const int kc = cam_num_params(d->cam_model[cam_i]);
         int la = 0;
-        for (int k = 0; k < kc; ++k) if (!(cmask[cam_i] & (1u << k))) cols.push_back(h_intr_off[cam_i] + la++);
+        for (int k = 0; k < kc; ++k) if (!(cmask[cam_i] & (1u << k))) { cols.push_back(h_intr_off[cam_i] + la++); src.push_back(9 + k); }
       }
       dc_needed = std::max(dc_needed, (int)cols.size());
       h_img_pd[i] = pd;
-      for (size_t k = 0; k < cols.size() && k < 8; ++k) h_img_cols[(size_t)i * 8 + k] = cols[k];
+      h_dc[i] = (int32_t)cols.size();
+      for (size_t k = 0; k < cols.size() && k < 8; ++k) { h_img_cols[(size_t)i * 8 + k] = cols[k]; h_src[(size_t)i * 8 + k] = (int8_t)src[k]; }
     }
     img_dc_max = dc_needed;
+    if (dc_needed <= 8) {
+      PXR_TRY(img_cols8.upload(h_img_cols.data(), h_img_cols.size(), s));
+      PXR_TRY(img_src8.upload(h_src.data(), h_src.size(), s));
+      PXR_TRY(img_dc8.upload(h_dc.data(), h_dc.size(), s));
+      PXR_CUDA(cudaStreamSynchronize(s));   // h_src / h_dc are locals
+    }
     h_img_cam.assign(d->img_cam, d->img_cam + n_images);
     // implicit block-sparse reduced system: on request, or when the dense one would not fit comfortably
     sparse_schur = for_solve && use_pcg && dc_needed <= 8 && n_obs > 0 &&
@@ -311,6 +320,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
 int BA::build_schur_pairs() {
   if (sp_built) return PXR_OK;
   PXR_TRY(Tbuf.alloc((size_t)n_obs * dcmax * 3));
+  PXR_TRY(Hinv.alloc((size_t)std::max<int64_t>(n_points, 1) * 6));
   const int64_t kChunk = 128;
   const int64_t ni = n_images;
   auto key_of = [&](int ia, int ib, bool self) -> int64_t {  // ia >= ib
@@ -452,6 +462,7 @@ BADev BA::dev() {
   d.obs_img = obs_img.p; d.obs_pt = obs_pt.p; d.img_cam = img_cam.p; d.cam_model = cam_model.p;
   d.cam_mask = cam_mask.p; d.tmask = tmask.p; d.pose_off = pose_off.p; d.intr_off = intr_off.p;
   d.point_off = point_off.p; d.pt_begin = pt_begin.p; d.obs_out = obs_out.p; d.juv = juv.p;
+  d.img_cols8 = img_cols8.p; d.img_src8 = img_src8.p; d.img_dc8 = img_dc8.p;
   d.Hcc = Hcc.p; d.gc = gc.p; d.Hpp = Hpp.p; d.gp = gp.p; d.W = W.p; d.Wcols = Wcols.p; d.Wdc = Wdc.p;
   d.loss.type = opt.loss_type; d.loss.a = opt.loss_scale;
   return d;
@@ -466,7 +477,10 @@ int BA::build() {
   const bool chunked = io_n_chunks > 0 && (sparse_schur || getenv("PXR_BUILD_ATOMIC") == nullptr);
   if (sparse_schur && !chunked && n_obs > 0) return fail(PXR_ERR_INTERNAL, "block-sparse path without per-image chunks");
   if (sparse_schur) PXR_TRY(ss_Himg.zero(ctx->stream));
-  if (n_obs > 0) PXR_LAUNCH(ctx, ba_build_kernel, (unsigned)cdiv(n_obs, 128), 128, 0, dev(), chunked ? 0 : 1);
+  if (n_obs > 0) {
+    if (img_src8.p) PXR_LAUNCH(ctx, ba_build_kernel<true>, (unsigned)cdiv(n_obs, 128), 128, 0, dev(), chunked ? 0 : 1);
+    else PXR_LAUNCH(ctx, ba_build_kernel<false>, (unsigned)cdiv(n_obs, 128), 128, 0, dev(), chunked ? 0 : 1);
+  }
   if (n_obs > 0 && chunked)
     PXR_LAUNCH(ctx, ba_build_cam_kernel, (unsigned)cdiv(io_n_chunks * 32, 256), 256, 0, dev(), io_obs.p, io_chunk_begin.p, io_n_chunks,
                sparse_schur ? ss_Himg.p : nullptr);
@@ -509,8 +523,9 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     if (nc > 0) PXR_LAUNCH(ctx, sp_init_rhs_kernel, (unsigned)cdiv(nc, 256), 256, 0, ctx->world > 1 ? gc_local.p : gc.p, rhs.p, nc);
     PXR_TRY(ss_Bk.zero(s));
     if (n_points > 0) {
-      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, D2.p, Tbuf.p, rhs.p, flags.p);
-      if (sp_n_chunks > 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, 256), 256, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, ss_Bk.p);
+      PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
+      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
+      if (sp_n_chunks > 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, ss_Bk.p, rhs.p);
     }
     if (ctx->world > 1 && nc > 0) PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
   } else {
@@ -519,8 +534,9 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p,
                          ctx->world > 1 ? gc_local.p : gc.p, D2.p, S.p, rhs.p, nc, (ctx->world <= 1 || ctx->rank == 0) ? 1 : 0);
   if (n_points > 0) {
-    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, D2.p, Tbuf.p, rhs.p, flags.p);
-    if (sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, 256), 256, 0, d, schur_pairs(), Tbuf.p, S.p);
+    PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
+    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
+    if (sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
   }
   // rhs rides along as row nc of S: the factorisation performs the forward substitution
   if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
@@ -539,7 +555,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     // The factorisation + back-substitution is a fixed sequence of ~3*nc/32 dependent launches: it is
     // captured once into a CUDA graph and replayed, which removes the per-launch gaps.
     if (!chol_graph_exec) {
-      chol_multikernel = getenv("PXR_CHOL_MULTIKERNEL") != nullptr;
+      chol_multikernel = chol_force_multikernel || getenv("PXR_CHOL_MULTIKERNEL") != nullptr;
       if (!chol_multikernel) {
         // every CTA of the persistent kernel must be resident at once: grid = occupancy x SMs
         int per_sm = 0, sms = 0, dev = 0;
@@ -601,16 +617,40 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   delete st; st = new StageScope(this, 7);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
   if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p);
-  if (n_obs > 0) PXR_LAUNCH(ctx, ba_model_cost_kernel, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
+  if (n_obs > 0) {
+    if (img_src8.p) PXR_LAUNCH(ctx, ba_model_cost_kernel<true>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
+    else PXR_LAUNCH(ctx, ba_model_cost_kernel<false>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
+  }
   PXR_CUDA(cudaGetLastError());
   delete st;
   double acc = 0, fld = 0;
+  if (chol_graph_exec && !chol_multikernel && !use_pcg && getenv("PXR_CHOL_TEST_ABORT")) {
+    // test hook: pretend the persistent kernel bailed out of a wait (abort word + failure flag)
+    const int one = 1;
+    PXR_CUDA(cudaMemcpyAsync(chol_sync.p + (pxr_chol::sync_ints((int)cdiv(nc, kNB)) - 1), &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    PXR_CUDA(cudaMemcpyAsync(flags.p + 1, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    PXR_CUDA(cudaStreamSynchronize(s));
+  }
   PXR_LAUNCH(ctx, flags_to_double_kernel, 1, 1, 0, flags.p, scalars.p + 5);
   PXR_TRY(allreduce_f64(ctx, scalars.p + 4, 2));   // model cost change + failure flag: every rank takes the same branch
   double two[2] = {0, 0};
   PXR_CUDA(cudaMemcpyAsync(two, scalars.p + 4, 16, cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaStreamSynchronize(s));
   acc = two[0]; fld = two[1];
+  if (fld != 0.0 && chol_graph_exec && !chol_multikernel && !use_pcg && ctx->world <= 1) {
+    // Did the persistent Cholesky bail out of a wait?  That only happens when its CTAs were not all resident at
+    // once (GPU shared with another client, MPS/MIG partition smaller than queried): switch, for the rest of this
+    // handle's life, to the launch-per-panel path, which needs no co-residency, and redo this step.
+    int aborted = 0;
+    const int nbt = (int)cdiv(nc, kNB);
+    PXR_CUDA(cudaMemcpyAsync(&aborted, chol_sync.p + (pxr_chol::sync_ints(nbt) - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    PXR_CUDA(cudaStreamSynchronize(s));
+    if (aborted) {
+      cudaGraphExecDestroy(chol_graph_exec); chol_graph_exec = nullptr;
+      chol_force_multikernel = true;
+      return compute_step(radius, valid, model_cost_change);
+    }
+  }
   const bool solved = fld == 0.0 && std::isfinite(acc);
   *model_cost_change = -acc;
   *valid = solved && (*model_cost_change > 0.0);
@@ -1172,8 +1212,9 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
     if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, b->Hcc.p, b->gc.p, b->D2.p, b->S.p, b->rhs.p, (int)nc, 1);
     PXR_CUDA(cudaMemsetAsync(b->flags.p, 0, 4 * sizeof(int), s));
     if (b->n_points > 0) {
-      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_obs * b->dcmax, 256), 256, 0, d, b->D2.p, b->Tbuf.p, b->rhs.p, b->flags.p);
-      if (b->sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(b->sp_n_chunks * 32, 256), 256, 0, d, b->schur_pairs(), b->Tbuf.p, b->S.p);
+      PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(b->n_points, 256), 256, 0, d, b->D2.p, b->Hinv.p, b->flags.p);
+      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_obs * b->dcmax, 256), 256, 0, d, b->Hinv.p, b->Tbuf.p);
+      if (b->sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(b->sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, b->schur_pairs(), b->Tbuf.p, b->S.p, b->rhs.p);
     }
     if (S) PXR_CUDA(cudaMemcpyAsync(S, b->S.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));
     if (rhs) PXR_CUDA(cudaMemcpyAsync(rhs, b->rhs.p, nc * 8, cudaMemcpyDeviceToHost, s));

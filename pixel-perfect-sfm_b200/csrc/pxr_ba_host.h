@@ -98,7 +98,8 @@ struct BA {
   int pcg_setup_blocks();
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
-  bool chol_multikernel = false; int chol_grid = 0;
+  bool chol_multikernel = false, chol_force_multikernel = false; int chol_grid = 0;
+  DevBuf<int32_t> img_cols8, img_dc8; DevBuf<int8_t> img_src8;   // per-image column tables (<= 8 columns per image)
   DevBuf<int32_t> io_obs;           // observations grouped by image, chunks of <= 128 (camera-block build)
   DevBuf<int64_t> io_chunk_begin; int64_t io_n_chunks = 0;
   DevBuf<long long> chol_trace;     // PXR_CHOL_TRACE=<file>: panel-CTA time stamps
@@ -108,7 +109,7 @@ struct BA {
   DevBuf<int32_t> sp_px, sp_py;
   DevBuf<int64_t> sp_chunk_begin;
   DevBuf<uint8_t> sp_chunk_self;
-  DevBuf<double> Tbuf;
+  DevBuf<double> Tbuf, Hinv;
   int64_t sp_n_chunks = 0;
   bool sp_built = false;
   std::vector<int32_t> h_obs_img;

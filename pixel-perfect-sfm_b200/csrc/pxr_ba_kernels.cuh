@@ -15,6 +15,9 @@ namespace pxr {
 constexpr int kMaxDc = 6 + kMaxK;
 
 struct BADev {
+  // per-image column tables (present when every image has <= 8 camera columns): local column of block row a, and
+  // which entry of the per-observation Jacobian row feeds it; lets the kernels keep cols/Ju/Jv in registers
+  const int32_t* img_cols8; const int8_t* img_src8; const int32_t* img_dc8;
   // sizes
   int n_cameras, n_images, K;  // K = max #intrinsics in the problem (juv columns)
   int64_t n_points, n_obs;
@@ -62,9 +65,25 @@ __device__ __forceinline__ int obs_local_columns(const BADev& d, int64_t o, cons
   return dc;
 }
 
+// register-only variant of obs_local_columns for images with <= 8 camera columns (static indexing throughout)
+__device__ __forceinline__ int obs_local_columns8(const BADev& d, int64_t o, const double* J, int Wd, int cols[8], double Ju[8], double Jv[8]) {
+  const int img = d.obs_img[o];
+  const int32_t* ic = d.img_cols8 + img * 8;
+  const int8_t* is = d.img_src8 + img * 8;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int sidx = is[a];
+    cols[a] = ic[a];
+    Ju[a] = sidx >= 0 ? J[sidx] : 0.0;
+    Jv[a] = sidx >= 0 ? J[Wd + sidx] : 0.0;
+  }
+  return d.img_dc8[img];
+}
+
 // K2: one thread per observation.  W_o = J_c^T A' J_p, camera blocks J_c^T A' J_c / J_c^T b' into
 // the dense Hcc (lower triangle) / gc and the point blocks Hpp / gp, all with fp64 atomics
 // (Hpp/gp/Hcc/gc are zeroed by the caller).
+template <bool FAST>
 static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d, int cam_blocks) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= d.n_obs) return;
@@ -77,9 +96,12 @@ static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d, int cam_b
   const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
   const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
   const double* J = d.juv + o * (int64_t)d.juv_stride;  // rows: J[0..Wd), J[Wd..2Wd)
-  int cols[kMaxDc];
-  double Ju[kMaxDc], Jv[kMaxDc];
-  const int dc = obs_local_columns(d, o, J, Wd, cols, Ju, Jv);
+  constexpr int NA = FAST ? 8 : kMaxDc;
+  int cols[NA];
+  double Ju[NA], Jv[NA];
+  int dc;
+  if constexpr (FAST) dc = obs_local_columns8(d, o, J, Wd, cols, Ju, Jv);
+  else dc = obs_local_columns(d, o, J, Wd, cols, Ju, Jv);
   d.Wdc[o] = dc;
   const double pu[3] = {J[6], J[7], J[8]}, pv[3] = {J[Wd + 6], J[Wd + 7], J[Wd + 8]};
   double apu[3], apv[3];
@@ -96,7 +118,9 @@ static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d, int cam_b
   }
   double* Wo = d.W + o * (int64_t)d.dcmax * 3;
   int32_t* Wc = d.Wcols + o * (int64_t)d.dcmax;
-  for (int a = 0; a < dc; ++a) {
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    if (a >= dc) break;
     Wc[a] = cols[a];
     if (pvar) {
       Wo[a * 3 + 0] = Ju[a] * apu[0] + Jv[a] * apv[0];
@@ -127,7 +151,7 @@ static __global__ void __launch_bounds__(256) ba_build_cam_kernel(BADev d, const
   double acc[48];
 #pragma unroll
   for (int k = 0; k < 48; ++k) acc[k] = 0.0;
-  int cols[kMaxDc];
+  int cols[8];
   int dc = 0;
   for (int64_t e = beg + lane; e < end; e += 32) {
     const int64_t o = io_obs[e];
@@ -137,8 +161,8 @@ static __global__ void __launch_bounds__(256) ba_build_cam_kernel(BADev d, const
     const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
     const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
     const double* J = d.juv + o * (int64_t)d.juv_stride;
-    double Ju[kMaxDc], Jv[kMaxDc];
-    dc = obs_local_columns(d, o, J, Wd, cols, Ju, Jv);
+    double Ju[8], Jv[8];
+    dc = obs_local_columns8(d, o, J, Wd, cols, Ju, Jv);
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       if (a < dc) {
@@ -245,26 +269,34 @@ __device__ __forceinline__ bool inv3_sym(const double* H, const double* D2, doub
 //      the same (image_i, image_j) pair address the same block of S; the pair list is sorted by that
 //      key once on the host (static sparsity), a warp accumulates the dc_i x dc_j block of a chunk in
 //      registers and touches S once per element.
-static __global__ void __launch_bounds__(256) ba_schur_prep_kernel(BADev d, const double* D2, double* T, double* rhs,
-                                                                   int* fail_flag) {
-  // one thread per (observation, local camera row)
+// K3a': (Hpp + D)^-1 once per point (6 unique entries), instead of once per (observation, row)
+static __global__ void __launch_bounds__(256) ba_point_inverse_kernel(BADev d, const double* D2, double* Hinv, int* fail_flag) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.n_points) return;
+  const int64_t po = d.point_off[p];
+  if (po < 0) return;
+  double inv[9];
+  if (!inv3_sym(d.Hpp + p * 9, D2 + po, inv)) { *fail_flag = 1; inv[0] = inv[1] = inv[2] = inv[4] = inv[5] = inv[8] = 0.0; }
+  double* h = Hinv + p * 6;
+  h[0] = inv[0]; h[1] = inv[1]; h[2] = inv[2]; h[3] = inv[4]; h[4] = inv[5]; h[5] = inv[8];
+}
+
+// K3a: T = W (Hpp + D)^-1, one thread per (observation, local camera row).  The right-hand side part
+// sum_obs T gp is accumulated by the pair kernel on its self pairs (per image chunk, 8 atomics per 128 observations).
+static __global__ void __launch_bounds__(256) ba_schur_prep_kernel(BADev d, const double* __restrict__ Hinv, double* T) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int dcm = d.dcmax;
   const int64_t o = idx / dcm;
   const int a = (int)(idx - o * dcm);
   if (o >= d.n_obs || a >= d.Wdc[o]) return;
   const int64_t p = d.obs_pt[o];
-  const int64_t po = d.point_off[p];
-  if (po < 0) return;
-  double inv[9];
-  if (!inv3_sym(d.Hpp + p * 9, D2 + po, inv)) { *fail_flag = 1; return; }
+  if (d.point_off[p] < 0) return;
+  const double* h = Hinv + p * 6;
   const double* w = d.W + (o * dcm + a) * 3;
-  const double t0 = w[0] * inv[0] + w[1] * inv[3] + w[2] * inv[6];
-  const double t1 = w[0] * inv[1] + w[1] * inv[4] + w[2] * inv[7];
-  const double t2 = w[0] * inv[2] + w[1] * inv[5] + w[2] * inv[8];
   double* tp = T + (o * dcm + a) * 3;
-  tp[0] = t0; tp[1] = t1; tp[2] = t2;
-  atomic_add_f64(&rhs[d.Wcols[o * dcm + a]], t0 * d.gp[p * 3] + t1 * d.gp[p * 3 + 1] + t2 * d.gp[p * 3 + 2]);
+  tp[0] = w[0] * h[0] + w[1] * h[1] + w[2] * h[2];
+  tp[1] = w[0] * h[1] + w[1] * h[3] + w[2] * h[4];
+  tp[2] = w[0] * h[2] + w[1] * h[4] + w[2] * h[5];
 }
 
 struct SchurPairs {
@@ -274,52 +306,70 @@ struct SchurPairs {
   int64_t n_chunks;
 };
 
-// Fast path of the pair kernels (dc <= 8): the 4 groups of 8 lanes of a warp each walk every 4th pair of the chunk;
-// lane (g, a) owns row a of the 8x8 block.  Two pairs per trip with their indices fetched one trip ahead, so the
-// dependent index -> row loads of consecutive pairs overlap (the kernel is bound by L2 gather latency, not math).
+// Fast path of the pair kernels (dc <= 8).  The kernel is bound by the latency of its gathers (index -> 192 B row of
+// T, 192 B row of W per pair; ncu: long_scoreboard, 13 % issue-active), so a warp stages SB = 16 pairs at a time in
+// shared memory with every lane's loads independent (one round trip for the 32 indices, one for 16 x 48 doubles),
+// then the 4 groups of 8 lanes compute from shared memory; lane (g, a) owns row a of the 8x8 block of its pairs.
+constexpr int kPairSB = 16;
+constexpr int kPairStride = 52;     // 24 T + 24 W + 3 gp (self chunks) + 1 pad
+constexpr int kPairThreads = 128;   // 4 warps x 16 pairs x 52 doubles = 26.6 KB of static shared memory
 __device__ __forceinline__ void schur_pairs_accumulate(const BADev& d, const SchurPairs& sp, const double* __restrict__ T,
-                                                       int64_t kb, int64_t ke, int g, int a, int dcx, int dcy, double acc[8]) {
+                                                       int64_t kb, int64_t ke, int lane, int dcx, int dcy, bool self,
+                                                       double* __restrict__ stage, double acc[8], double& racc) {
   const int dcm = d.dcmax;
-  double acc2[8];
+  const int g = lane >> 3, a = lane & 7;
 #pragma unroll
-  for (int b = 0; b < 8; ++b) { acc[b] = 0.0; acc2[b] = 0.0; }
-  int64_t k = kb + g;
-  int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-  if (k < ke) { x0 = sp.px[k]; y0 = sp.py[k]; }
-  if (k + 4 < ke) { x1 = sp.px[k + 4]; y1 = sp.py[k + 4]; }
-  while (k < ke) {
-    const int32_t cx0 = x0, cy0 = y0, cx1 = x1, cy1 = y1;
-    const bool two = k + 4 < ke;
-    const int64_t kn = k + 8;
-    if (kn < ke) { x0 = sp.px[kn]; y0 = sp.py[kn]; }
-    if (kn + 4 < ke) { x1 = sp.px[kn + 4]; y1 = sp.py[kn + 4]; }
-    if (a < dcx) {
-      const double* Tx0 = T + ((int64_t)cx0 * dcm + a) * 3;
-      const double* Wy0 = d.W + (int64_t)cy0 * dcm * 3;
-      const double* Tx1 = T + ((int64_t)cx1 * dcm + a) * 3;
-      const double* Wy1 = d.W + (int64_t)cy1 * dcm * 3;
-      const double t00 = Tx0[0], t01 = Tx0[1], t02 = Tx0[2];
-      double t10 = 0.0, t11 = 0.0, t12 = 0.0;
-      if (two) { t10 = Tx1[0]; t11 = Tx1[1]; t12 = Tx1[2]; }
+  for (int b = 0; b < 8; ++b) acc[b] = 0.0;
+  racc = 0.0;
+  for (int64_t k0 = kb; k0 < ke; k0 += kPairSB) {
+    const int np = (int)min((int64_t)kPairSB, ke - k0);
+    // lanes 0..15: x observation of pair `lane`; lanes 16..31: y observation of pair `lane - 16`
+    const int pl = lane & 15;
+    int32_t idx = 0;
+    if (pl < np) idx = lane < 16 ? sp.px[k0 + pl] : sp.py[k0 + pl];
+    __syncwarp();
 #pragma unroll
-      for (int b = 0; b < 8; ++b)
-        if (b < dcy) {
-          acc[b] += t00 * Wy0[b * 3] + t01 * Wy0[b * 3 + 1] + t02 * Wy0[b * 3 + 2];
-          if (two) acc2[b] += t10 * Wy1[b * 3] + t11 * Wy1[b * 3 + 1] + t12 * Wy1[b * 3 + 2];
-        }
+    for (int t = 0; t < (kPairSB * kPairStride) / 32; ++t) {
+      const int e = lane + 32 * t;                 // element e of the staging buffer
+      const int pr = e / kPairStride, wi = e - pr * kPairStride;
+      const int src_lane = (wi < 24 || wi >= 48) ? pr : 16 + pr;
+      const int32_t o = __shfl_sync(0xffffffffu, idx, src_lane);
+      double v = 0.0;
+      if (pr < np) {
+        if (wi < 24) v = T[(int64_t)o * dcm * 3 + wi];
+        else if (wi < 48) v = d.W[(int64_t)o * dcm * 3 + (wi - 24)];
+        else if (self && wi < 51) v = d.gp[d.obs_pt[o] * 3 + (wi - 48)];
+      }
+      stage[e] = v;
     }
-    k = kn;
+    __syncwarp();
+    if (a < dcx) {
+#pragma unroll
+      for (int q = 0; q < kPairSB / 4; ++q) {
+        const int pr = g + 4 * q;
+        if (pr < np) {
+          const double* Tx = stage + pr * kPairStride + a * 3;
+          const double* Wy = stage + pr * kPairStride + 24;
+          const double t0 = Tx[0], t1 = Tx[1], t2 = Tx[2];
+#pragma unroll
+          for (int b = 0; b < 8; ++b)
+            if (b < dcy) acc[b] += t0 * Wy[b * 3] + t1 * Wy[b * 3 + 1] + t2 * Wy[b * 3 + 2];
+          if (self) { const double* gpv = stage + pr * kPairStride + 48; racc += t0 * gpv[0] + t1 * gpv[1] + t2 * gpv[2]; }
+        }
+      }
+    }
   }
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
-    acc[b] += acc2[b];
     acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 8);
     acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
   }
+  racc += __shfl_xor_sync(0xffffffffu, racc, 8);
+  racc += __shfl_xor_sync(0xffffffffu, racc, 16);
 }
 
-static __global__ void __launch_bounds__(256) ba_schur_pairs_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
-                                                                    double* S) {
+static __global__ void __launch_bounds__(kPairThreads) ba_schur_pairs_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
+                                                                    double* S, double* rhs) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= sp.n_chunks) return;
@@ -332,8 +382,10 @@ static __global__ void __launch_bounds__(256) ba_schur_pairs_kernel(BADev d, Sch
   if (dcx <= 8 && dcy <= 8) {
     // fast path: 4 groups of 8 lanes work on 4 entries at a time; lane (g, a) owns row a of the block
     const int g = lane >> 3, a = lane & 7;
-    double acc[8];
-    schur_pairs_accumulate(d, sp, T, kb, ke, g, a, dcx, dcy, acc);
+    __shared__ double stage_all[kPairThreads / 32][kPairSB * kPairStride];
+    double acc[8], racc;
+    schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, stage_all[threadIdx.x >> 5], acc, racc);
+    if (self && g == 0 && a < dcx) atomic_add_f64(&rhs[d.Wcols[ox0 * dcm + a]], racc);
     if (g == 0 && a < dcx) {
       const int ca = d.Wcols[ox0 * dcm + a];
 #pragma unroll
@@ -348,6 +400,18 @@ static __global__ void __launch_bounds__(256) ba_schur_pairs_kernel(BADev d, Sch
       }
     }
     return;
+  }
+  if (self) {   // rhs += sum_obs T gp (generic path: lanes over rows)
+    for (int r = lane; r < dcx; r += 32) {
+      double rs = 0.0;
+      for (int64_t k = kb; k < ke; ++k) {
+        const int64_t o = sp.px[k];
+        const double* Tx = T + ((int64_t)o * dcm + r) * 3;
+        const double* gpv = d.gp + d.obs_pt[o] * 3;
+        rs += Tx[0] * gpv[0] + Tx[1] * gpv[1] + Tx[2] * gpv[2];
+      }
+      atomic_add_f64(&rhs[d.Wcols[ox0 * dcm + r]], rs);
+    }
   }
   const int nel = dcx * dcy;
   constexpr int kMaxT = (kMaxDc * kMaxDc + 31) / 32;
@@ -530,6 +594,7 @@ static __global__ void __launch_bounds__(256) ba_backsub_kernel(BADev d, const d
 
 // K5b: model cost change, the literal ceres formula  -(J d)^T (r + J d / 2)  per residual block in
 // the reduced 2-D space:  u = d(uv)/d(theta) * delta ;  acc += u^T b' + u^T A' u / 2   (one thread per obs)
+template <bool FAST>
 static __global__ void __launch_bounds__(256) ba_model_cost_kernel(BADev d, const double* delta, double* acc) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double part = 0.0;
@@ -539,11 +604,18 @@ static __global__ void __launch_bounds__(256) ba_model_cost_kernel(BADev d, cons
     double rho[3];
     loss_eval(d.loss, 1.0, oo[0], rho);
     const double* J = d.juv + o * (int64_t)d.juv_stride;
-    int cols[kMaxDc];
-    double Ju[kMaxDc], Jv[kMaxDc];
-    const int dc = obs_local_columns(d, o, J, Wd, cols, Ju, Jv);
+    constexpr int NA = FAST ? 8 : kMaxDc;
+    int cols[NA];
+    double Ju[NA], Jv[NA];
+    int dc;
+    if constexpr (FAST) dc = obs_local_columns8(d, o, J, Wd, cols, Ju, Jv);
+    else dc = obs_local_columns(d, o, J, Wd, cols, Ju, Jv);
     double uu = 0.0, uv = 0.0;
-    for (int a = 0; a < dc; ++a) { const double dl = delta[cols[a]]; uu += Ju[a] * dl; uv += Jv[a] * dl; }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      if (a >= dc) break;
+      const double dl = delta[cols[a]]; uu += Ju[a] * dl; uv += Jv[a] * dl;
+    }
     const int64_t po = d.point_off[d.obs_pt[o]];
     if (po >= 0) {
 #pragma unroll

@@ -33,8 +33,8 @@ struct SparseSchur {
 };
 
 // Schur pair chunks -> image-pair blocks (the fast path of ba_schur_pairs_kernel with a different sink)
-static __global__ void __launch_bounds__(256) sp_schur_pairs_kernel(BADev d, SchurPairs sp, const int32_t* __restrict__ chunk_key,
-                                                                    const double* __restrict__ T, double* __restrict__ Bk) {
+static __global__ void __launch_bounds__(kPairThreads) sp_schur_pairs_kernel(BADev d, SchurPairs sp, const int32_t* __restrict__ chunk_key,
+                                                                    const double* __restrict__ T, double* __restrict__ Bk, double* rhs) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= sp.n_chunks) return;
@@ -44,8 +44,11 @@ static __global__ void __launch_bounds__(256) sp_schur_pairs_kernel(BADev d, Sch
   const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
   const int g = lane >> 3, a = lane & 7;
-  double acc[8];
-  schur_pairs_accumulate(d, sp, T, kb, ke, g, a, dcx, dcy, acc);
+  __shared__ double stage_all[kPairThreads / 32][kPairSB * kPairStride];
+  double acc[8], racc;
+  const bool self = sp.chunk_self[c] != 0;
+  schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, stage_all[threadIdx.x >> 5], acc, racc);
+  if (self && g == 0 && a < dcx) atomic_add_f64(&rhs[d.Wcols[ox0 * d.dcmax + a]], racc);
   if (g == 0 && a < dcx) {
     double* dst = Bk + ((int64_t)chunk_key[c] * 8 + a) * 8;
 #pragma unroll
