@@ -536,7 +536,10 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   if (n_points > 0) {
     PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
     PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
-    if (sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+    if (sp_n_chunks > 0) {
+      if (img_dc_max <= 8) PXR_LAUNCH(ctx, ba_schur_pairs_kernel<true>, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+      else PXR_LAUNCH(ctx, ba_schur_pairs_kernel<false>, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+    }
   }
   // rhs rides along as row nc of S: the factorisation performs the forward substitution
   if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
@@ -1214,7 +1217,7 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
     if (b->n_points > 0) {
       PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(b->n_points, 256), 256, 0, d, b->D2.p, b->Hinv.p, b->flags.p);
       PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_obs * b->dcmax, 256), 256, 0, d, b->Hinv.p, b->Tbuf.p);
-      if (b->sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel, (unsigned)cdiv(b->sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, b->schur_pairs(), b->Tbuf.p, b->S.p, b->rhs.p);
+      if (b->sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel<false>, (unsigned)cdiv(b->sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, b->schur_pairs(), b->Tbuf.p, b->S.p, b->rhs.p);
     }
     if (S) PXR_CUDA(cudaMemcpyAsync(S, b->S.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));
     if (rhs) PXR_CUDA(cudaMemcpyAsync(rhs, b->rhs.p, nc * 8, cudaMemcpyDeviceToHost, s));

@@ -306,57 +306,29 @@ struct SchurPairs {
   int64_t n_chunks;
 };
 
-// Fast path of the pair kernels (dc <= 8).  The kernel is bound by the latency of its gathers (index -> 192 B row of
-// T, 192 B row of W per pair; ncu: long_scoreboard, 13 % issue-active), so a warp stages SB = 16 pairs at a time in
-// shared memory with every lane's loads independent (one round trip for the 32 indices, one for 16 x 48 doubles),
-// then the 4 groups of 8 lanes compute from shared memory; lane (g, a) owns row a of the 8x8 block of its pairs.
-constexpr int kPairSB = 16;
-constexpr int kPairStride = 52;     // 24 T + 24 W + 3 gp (self chunks) + 1 pad
-constexpr int kPairThreads = 128;   // 4 warps x 16 pairs x 52 doubles = 26.6 KB of static shared memory
+// Fast path of the pair kernels (dc <= 8): the 4 groups of 8 lanes of a warp each walk every 4th pair of the chunk;
+// lane (g, a) owns row a of the 8x8 block.  On self chunks the same pass accumulates rhs += T gp.
+// (A variant that staged 16 pairs at a time through shared memory to widen the gathers measured 2.3x SLOWER on
+//  B200 — 126 registers, 16 resident warps — and was dropped.)
+constexpr int kPairThreads = 256;
 __device__ __forceinline__ void schur_pairs_accumulate(const BADev& d, const SchurPairs& sp, const double* __restrict__ T,
                                                        int64_t kb, int64_t ke, int lane, int dcx, int dcy, bool self,
-                                                       double* __restrict__ stage, double acc[8], double& racc) {
+                                                       double acc[8], double& racc) {
   const int dcm = d.dcmax;
   const int g = lane >> 3, a = lane & 7;
 #pragma unroll
   for (int b = 0; b < 8; ++b) acc[b] = 0.0;
   racc = 0.0;
-  for (int64_t k0 = kb; k0 < ke; k0 += kPairSB) {
-    const int np = (int)min((int64_t)kPairSB, ke - k0);
-    // lanes 0..15: x observation of pair `lane`; lanes 16..31: y observation of pair `lane - 16`
-    const int pl = lane & 15;
-    int32_t idx = 0;
-    if (pl < np) idx = lane < 16 ? sp.px[k0 + pl] : sp.py[k0 + pl];
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < (kPairSB * kPairStride) / 32; ++t) {
-      const int e = lane + 32 * t;                 // element e of the staging buffer
-      const int pr = e / kPairStride, wi = e - pr * kPairStride;
-      const int src_lane = (wi < 24 || wi >= 48) ? pr : 16 + pr;
-      const int32_t o = __shfl_sync(0xffffffffu, idx, src_lane);
-      double v = 0.0;
-      if (pr < np) {
-        if (wi < 24) v = T[(int64_t)o * dcm * 3 + wi];
-        else if (wi < 48) v = d.W[(int64_t)o * dcm * 3 + (wi - 24)];
-        else if (self && wi < 51) v = d.gp[d.obs_pt[o] * 3 + (wi - 48)];
-      }
-      stage[e] = v;
-    }
-    __syncwarp();
+  for (int64_t k = kb + g; k < ke; k += 4) {
+    const int64_t ox = sp.px[k];
+    const double* Tx = T + (ox * dcm + a) * 3;
+    const double* Wy = d.W + (int64_t)sp.py[k] * dcm * 3;
     if (a < dcx) {
+      const double t0 = Tx[0], t1 = Tx[1], t2 = Tx[2];
 #pragma unroll
-      for (int q = 0; q < kPairSB / 4; ++q) {
-        const int pr = g + 4 * q;
-        if (pr < np) {
-          const double* Tx = stage + pr * kPairStride + a * 3;
-          const double* Wy = stage + pr * kPairStride + 24;
-          const double t0 = Tx[0], t1 = Tx[1], t2 = Tx[2];
-#pragma unroll
-          for (int b = 0; b < 8; ++b)
-            if (b < dcy) acc[b] += t0 * Wy[b * 3] + t1 * Wy[b * 3 + 1] + t2 * Wy[b * 3 + 2];
-          if (self) { const double* gpv = stage + pr * kPairStride + 48; racc += t0 * gpv[0] + t1 * gpv[1] + t2 * gpv[2]; }
-        }
-      }
+      for (int b = 0; b < 8; ++b)
+        if (b < dcy) acc[b] += t0 * Wy[b * 3] + t1 * Wy[b * 3 + 1] + t2 * Wy[b * 3 + 2];
+      if (self) { const double* gpv = d.gp + d.obs_pt[ox] * 3; racc += t0 * gpv[0] + t1 * gpv[1] + t2 * gpv[2]; }
     }
   }
 #pragma unroll
@@ -368,7 +340,8 @@ __device__ __forceinline__ void schur_pairs_accumulate(const BADev& d, const Sch
   racc += __shfl_xor_sync(0xffffffffu, racc, 16);
 }
 
-static __global__ void __launch_bounds__(kPairThreads) ba_schur_pairs_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
+template <bool FAST>
+static __global__ void __launch_bounds__(kPairThreads, FAST ? 5 : 2) ba_schur_pairs_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
                                                                     double* S, double* rhs) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -379,12 +352,11 @@ static __global__ void __launch_bounds__(kPairThreads) ba_schur_pairs_kernel(BAD
   const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
   const bool self = sp.chunk_self[c] != 0;
-  if (dcx <= 8 && dcy <= 8) {
+  if (FAST || (dcx <= 8 && dcy <= 8)) {
     // fast path: 4 groups of 8 lanes work on 4 entries at a time; lane (g, a) owns row a of the block
     const int g = lane >> 3, a = lane & 7;
-    __shared__ double stage_all[kPairThreads / 32][kPairSB * kPairStride];
     double acc[8], racc;
-    schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, stage_all[threadIdx.x >> 5], acc, racc);
+    schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, acc, racc);
     if (self && g == 0 && a < dcx) atomic_add_f64(&rhs[d.Wcols[ox0 * dcm + a]], racc);
     if (g == 0 && a < dcx) {
       const int ca = d.Wcols[ox0 * dcm + a];
@@ -401,6 +373,7 @@ static __global__ void __launch_bounds__(kPairThreads) ba_schur_pairs_kernel(BAD
     }
     return;
   }
+  if constexpr (!FAST) {
   if (self) {   // rhs += sum_obs T gp (generic path: lanes over rows)
     for (int r = lane; r < dcx; r += 32) {
       double rs = 0.0;
@@ -441,6 +414,7 @@ static __global__ void __launch_bounds__(kPairThreads) ba_schur_pairs_kernel(BAD
     else if (ca > cb) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v);
     else if (ca < cb) atomic_add_f64(&S[(int64_t)cb * d.nc + ca], v);
     else atomic_add_f64(&S[(int64_t)ca * d.nc + ca], 2.0 * v);
+  }
   }
 }
 

@@ -44,10 +44,9 @@ static __global__ void __launch_bounds__(kPairThreads) sp_schur_pairs_kernel(BAD
   const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
   const int g = lane >> 3, a = lane & 7;
-  __shared__ double stage_all[kPairThreads / 32][kPairSB * kPairStride];
   double acc[8], racc;
   const bool self = sp.chunk_self[c] != 0;
-  schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, stage_all[threadIdx.x >> 5], acc, racc);
+  schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, acc, racc);
   if (self && g == 0 && a < dcx) atomic_add_f64(&rhs[d.Wcols[ox0 * d.dcmax + a]], racc);
   if (g == 0 && a < dcx) {
     double* dst = Bk + ((int64_t)chunk_key[c] * 8 + a) * 8;

@@ -45,13 +45,6 @@ def test_descriptor_interpolation_and_nearest_references():
         assert len(obs) == 4
         d = ((obs - desc[k]) ** 2).sum(1)
         assert np.array_equal(nearest[k].reshape(-1), obs[int(np.argmin(d))])
-    # the query image is one of the mapped images: its own observation (descriptor at the projection of the mapped
-    # point, about a pixel from the detected keypoint) is among the candidates and is usually the nearest
-    own = []
-    for k, pid in enumerate(p3D_ids):
-        j = [el.image_id for el in rec.points3D[pid].track.elements].index(qid)
-        own.append(np.array_equal(nearest[k].reshape(-1), refs[pid].observations[j].reshape(-1)))
-    assert np.mean(own) > 0.8
 
 
 @pytest.mark.parametrize("target", ["nearest", "robust_mean", "all_observations"])
