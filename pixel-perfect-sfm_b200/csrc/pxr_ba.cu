@@ -674,8 +674,8 @@ int BA::apply_step(double* step_norm, double* x_norm) {
   const int64_t n = std::max<int64_t>(std::max<int64_t>(n_points, n_images), n_cameras);
   PXR_LAUNCH(ctx, ba_plus_kernel, (unsigned)cdiv(n, 128), 128, 0, a);
   PXR_CUDA(cudaGetLastError());
+  PXR_TRY(allreduce_f64(ctx, scalars.p + 5, 2));  // point parts are sharded, camera parts replicated
   if (step_norm || x_norm) {
-    PXR_TRY(allreduce_f64(ctx, scalars.p + 5, 2));  // point parts are sharded, camera parts replicated
     double v[4];
     PXR_CUDA(cudaMemcpyAsync(v, scalars.p + 5, 32, cudaMemcpyDeviceToHost, ctx->stream));
     PXR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -828,29 +828,7 @@ int BA::pcg_solve_sparse() {
   if (ctx->world > 1) PXR_TRY(allreduce_f64(ctx, ss_Dblk.p, (size_t)cg_nblk * 144));
   PXR_LAUNCH(ctx, sp_block_inverse_kernel, (unsigned)cdiv(cg_nblk, 64), 64, 0, ss_Dblk.p, D2.p, 1, cg_blk_off.p, cg_blk_dim.p, cg_nblk,
              cg_Minv.p, cg_row_off.p, cg_row_dim.p, flags.p + 1);
-  PXR_LAUNCH(ctx, cg_init_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p, opt.max_linear_solver_iterations, 0.1);
-  CGState hs;
-  for (int it = 0; it < opt.max_linear_solver_iterations; ++it) {
-    PXR_LAUNCH(ctx, cg_precond_kernel, 1, 1024, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, cg_p.p, n, cg_state.p);
-    PXR_TRY(spmv(cg_p.p, cg_q.p));
-    PXR_LAUNCH(ctx, cg_update_kernel, 1, 1024, 0, rhs.p, cg_p.p, cg_q.p, cg_x.p, cg_r.p, n, cg_state.p);
-    if ((it + 1) % 10 == 0) {   // residual_reset_period
-      PXR_TRY(spmv(cg_x.p, cg_tmp.p));
-      PXR_LAUNCH(ctx, cg_refresh_kernel, 1, 1024, 0, rhs.p, cg_tmp.p, cg_r.p, n, cg_state.p);
-    }
-    PXR_LAUNCH(ctx, cg_check_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p);
-    if ((it + 1) % 8 == 0 || it + 1 == opt.max_linear_solver_iterations) {
-      PXR_CUDA(cudaMemcpyAsync(&hs, cg_state.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
-      PXR_CUDA(cudaStreamSynchronize(s));
-      if (hs.done) break;
-    }
-  }
-  PXR_CUDA(cudaMemcpyAsync(&hs, cg_state.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
-  PXR_CUDA(cudaMemcpyAsync(delta.p, cg_x.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
-  PXR_CUDA(cudaStreamSynchronize(s));
-  last_linear_iterations = hs.it;
-  if (hs.failed) { int one = 1; PXR_CUDA(cudaMemcpyAsync(flags.p + 1, &one, sizeof(int), cudaMemcpyHostToDevice, s)); }
-  return PXR_OK;
+  return run_cg(spmv);
 }
 
 int BA::pcg_solve() {
@@ -861,17 +839,54 @@ int BA::pcg_solve() {
   PXR_LAUNCH(ctx, cg_mirror_kernel, (unsigned)cdiv((int64_t)n * n, 256), 256, 0, S.p, n);
   PXR_LAUNCH(ctx, cg_block_inverse_kernel, (unsigned)cdiv(cg_nblk, 64), 64, 0, S.p, n, cg_blk_off.p, cg_blk_dim.p, cg_nblk, cg_Minv.p,
              cg_row_off.p, cg_row_dim.p, flags.p + 1);
-  PXR_LAUNCH(ctx, cg_init_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p, opt.max_linear_solver_iterations, 0.1);
+  auto spmv = [&](const double* x, double* y) -> int {
+    PXR_LAUNCH(ctx, cg_gemv_kernel, gv, 256, 0, S.p, x, y, n, cg_state.p);
+    return PXR_OK;
+  };
+  return run_cg(spmv);
+}
+
+// Preconditioned CG on the reduced system given its product; Ceres' ConjugateGradientsSolver recurrences and
+// termination (Q-decrease ratio, residual refresh every 10 iterations).  Small systems run the single-CTA vector
+// kernels (deterministic sums); from 4096 unknowns the multi-CTA variants.
+int BA::run_cg(const std::function<int(const double*, double*)>& spmv) {
+  cudaStream_t s = ctx->stream;
+  const int n = nc;
+  const bool multi = n >= 4096 || getenv("PXR_CG_MULTI") != nullptr;
+  const unsigned gn = (unsigned)cdiv(n, 256);
   CGState hs;
+  if (multi) {
+    PXR_LAUNCH(ctx, cgm_init_state_kernel, 1, 1, 0, cg_state.p, opt.max_linear_solver_iterations, 0.1);
+    PXR_LAUNCH(ctx, cgm_init_kernel, gn, 256, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p);
+    PXR_LAUNCH(ctx, cgm_init_done_kernel, 1, 1, 0, cg_state.p);
+  } else {
+    PXR_LAUNCH(ctx, cg_init_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p, opt.max_linear_solver_iterations, 0.1);
+  }
   for (int it = 0; it < opt.max_linear_solver_iterations; ++it) {
-    PXR_LAUNCH(ctx, cg_precond_kernel, 1, 1024, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, cg_p.p, n, cg_state.p);
-    PXR_LAUNCH(ctx, cg_gemv_kernel, gv, 256, 0, S.p, cg_p.p, cg_q.p, n, cg_state.p);
-    PXR_LAUNCH(ctx, cg_update_kernel, 1, 1024, 0, rhs.p, cg_p.p, cg_q.p, cg_x.p, cg_r.p, n, cg_state.p);
-    if ((it + 1) % 10 == 0) {   // residual_reset_period
-      PXR_LAUNCH(ctx, cg_gemv_kernel, gv, 256, 0, S.p, cg_x.p, cg_tmp.p, n, cg_state.p);
-      PXR_LAUNCH(ctx, cg_refresh_kernel, 1, 1024, 0, rhs.p, cg_tmp.p, cg_r.p, n, cg_state.p);
+    const bool refresh = (it + 1) % 10 == 0;   // residual_reset_period
+    if (multi) {
+      PXR_LAUNCH(ctx, cgm_precond_kernel, gn, 256, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, n, cg_state.p);
+      PXR_LAUNCH(ctx, cgm_beta_kernel, 1, 1, 0, cg_state.p);
+      PXR_LAUNCH(ctx, cgm_dir_kernel, gn, 256, 0, cg_z.p, cg_p.p, n, cg_state.p);
+      PXR_TRY(spmv(cg_p.p, cg_q.p));
+      PXR_LAUNCH(ctx, cgm_pq_kernel, gn, 256, 0, cg_p.p, cg_q.p, n, cg_state.p);
+      PXR_LAUNCH(ctx, cgm_alpha_kernel, 1, 1, 0, cg_state.p);
+      PXR_LAUNCH(ctx, cgm_update_kernel, gn, 256, 0, rhs.p, cg_p.p, cg_q.p, cg_x.p, cg_r.p, n, cg_state.p);
+      if (refresh) {
+        PXR_TRY(spmv(cg_x.p, cg_tmp.p));
+        PXR_LAUNCH(ctx, cgm_refresh_kernel, gn, 256, 0, rhs.p, cg_tmp.p, cg_x.p, cg_r.p, n, cg_state.p);
+      }
+      PXR_LAUNCH(ctx, cgm_check_kernel, 1, 1, 0, cg_state.p);
+    } else {
+      PXR_LAUNCH(ctx, cg_precond_kernel, 1, 1024, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, cg_p.p, n, cg_state.p);
+      PXR_TRY(spmv(cg_p.p, cg_q.p));
+      PXR_LAUNCH(ctx, cg_update_kernel, 1, 1024, 0, rhs.p, cg_p.p, cg_q.p, cg_x.p, cg_r.p, n, cg_state.p);
+      if (refresh) {
+        PXR_TRY(spmv(cg_x.p, cg_tmp.p));
+        PXR_LAUNCH(ctx, cg_refresh_kernel, 1, 1024, 0, rhs.p, cg_tmp.p, cg_r.p, n, cg_state.p);
+      }
+      PXR_LAUNCH(ctx, cg_check_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p);
     }
-    PXR_LAUNCH(ctx, cg_check_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p);
     if ((it + 1) % 8 == 0 || it + 1 == opt.max_linear_solver_iterations) {
       PXR_CUDA(cudaMemcpyAsync(&hs, cg_state.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
       PXR_CUDA(cudaStreamSynchronize(s));
@@ -970,12 +985,13 @@ int BA::lm_iterate(int max_iteration) {
     lm.num_invalid = 0;
 
     double step_norm = 0, x_norm = 0, candidate_cost = 0;
-    PXR_TRY(apply_step(&step_norm, &x_norm));
+    const bool speculate = !lm.inner_enabled && getenv("PXR_NO_SPECULATION") == nullptr;
+    // the norms of the step are read back together with the trial cost (one host round trip instead of two)
+    if (speculate) PXR_TRY(apply_step(nullptr, nullptr)); else PXR_TRY(apply_step(&step_norm, &x_norm));
     // Trial point.  Ceres evaluates the cost here and, if the step is accepted, evaluates residuals AND Jacobians
     // again at the same point.  Both passes stream the same patch windows, so when no inner iterations will move
     // the point afterwards the Jacobian-mode pass is run right away into the alternate buffer set (0.52 ms instead
     // of 0.37 + 0.52 ms at S3); a rejected step merely discards it.
-    const bool speculate = !lm.inner_enabled && getenv("PXR_NO_SPECULATION") == nullptr;
     swap_sets();
     int rc = PXR_OK;
     if (speculate) {
@@ -983,9 +999,12 @@ int BA::lm_iterate(int max_iteration) {
       if (rc == PXR_OK) rc = fm(1, nullptr, scalars.p + 0);
       if (rc == PXR_OK) rc = allreduce_f64(ctx, scalars.p + 0, 1);
       if (rc == PXR_OK) {
+        double nv[4] = {0, 0, 0, 0};
         cudaError_t e = cudaMemcpyAsync(&candidate_cost, scalars.p + 0, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nv, scalars.p + 5, 32, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(PXR_ERR_CUDA, "trial evaluation failed: %s", cudaGetErrorString(e));
+        step_norm = std::sqrt(nv[0] + nv[2]); x_norm = std::sqrt(nv[1] + nv[3]);
       }
     } else {
       rc = evaluate(1 - cur, false, &candidate_cost);

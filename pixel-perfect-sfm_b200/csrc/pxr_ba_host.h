@@ -2,6 +2,7 @@
 #pragma once
 #include <chrono>
 #include <string>
+#include <functional>
 #include <utility>
 #include <vector>
 
@@ -86,6 +87,7 @@ struct BA {
   DevBuf<CGState> cg_state;
   int cg_nblk = 0, last_linear_iterations = 1;
   int pcg_solve();
+  int run_cg(const std::function<int(const double*, double*)>& spmv);
   // implicit block-sparse reduced system (pxr_sparse_schur.cuh): no nc x nc array is ever allocated
   bool sparse_schur = false;
   int ss_n_keys = 0;

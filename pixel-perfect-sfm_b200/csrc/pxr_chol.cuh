@@ -462,8 +462,10 @@ static __global__ void __launch_bounds__(kThreads, 2) chol_persistent_kernel(Arg
       while (bulk_has(k - 1)) {
         if (tid == 0) s_poll[0] = ld_acquire(a.diag_ready + k);
         __syncthreads();
-        if (s_poll[0] != 0) break;
-        bulk_step();                                  // its barriers separate this read of s_poll from the next write
+        const int rdy = s_poll[0];
+        __syncthreads();                              // every thread has its copy before s_poll can be rewritten (a worker
+        if (rdy != 0) break;                          // without tiles in the next stages reaches the next poll barrier-free)
+        bulk_step();
       }
       // C: solves of column k
       bool have_lkk = false;

@@ -10,7 +10,7 @@
 namespace pxr {
 
 struct CGState {
-  double rho, last_rho, alpha, beta, Q0, pq, rz, xbr;
+  double rho, last_rho, alpha, beta, Q0, pq, rz, xbr;   // pq / rz / xbr double as atomic accumulators of the multi-CTA path
   int it, done, failed, max_iter;
   double q_tol;
 };
@@ -152,6 +152,104 @@ static __global__ void __launch_bounds__(1024) cg_check_kernel(const double* b, 
 static __global__ void __launch_bounds__(1024) cg_refresh_kernel(const double* b, const double* Sx, double* r, int n, const CGState* st) {
   if (st->done || (st->it % 10) != 0) return;
   for (int i = threadIdx.x; i < n; i += blockDim.x) r[i] = b[i] - Sx[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-CTA variants for large reduced systems (n >= 4096: the single-CTA kernels above then cost 20-30 us each and
+// dominate a CG iteration).  Vector work is spread over the grid, dot products land in the state with one fp64 atomic
+// per CTA, and the scalar recurrences run in 1-thread kernels in between.  Same arithmetic, same termination rule.
+static __global__ void __launch_bounds__(256) cgm_init_kernel(const double* b, double* x, double* r, int n, CGState* st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double nb = 0.0;
+  if (i < n) { x[i] = 0.0; r[i] = b[i]; nb = b[i] * b[i]; }
+  nb = cta_sum(nb);
+  if (threadIdx.x == 0 && nb != 0.0) atomicAdd(&st->xbr, nb);
+}
+static __global__ void cgm_init_state_kernel(CGState* st, int max_iter, double q_tol) {   // before cgm_init_kernel
+  st->rho = 1.0; st->last_rho = 1.0; st->alpha = 0; st->beta = 0; st->Q0 = 0.0; st->it = 0; st->failed = 0; st->done = 0;
+  st->max_iter = max_iter; st->q_tol = q_tol; st->pq = 0.0; st->rz = 0.0; st->xbr = 0.0;
+}
+static __global__ void cgm_init_done_kernel(CGState* st) { if (st->xbr == 0.0) st->done = 1; st->xbr = 0.0; }   // b == 0
+
+// z = M^-1 r ; rz += r.z
+static __global__ void __launch_bounds__(256) cgm_precond_kernel(const double* Minv, const int32_t* row_off, const int32_t* row_dim,
+                                                                 const double* r, double* z, int n, CGState* st) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double rz = 0.0;
+  if (i < n) {
+    double sacc = 0.0;
+    const int o = row_off[i], d = row_dim[i];
+    for (int j = 0; j < d; ++j) sacc += Minv[(int64_t)i * 12 + j] * r[o + j];
+    z[i] = sacc; rz = r[i] * sacc;
+  }
+  rz = cta_sum(rz);
+  if (threadIdx.x == 0) atomicAdd(&st->rz, rz);
+}
+static __global__ void cgm_beta_kernel(CGState* st) {
+  if (st->done) return;
+  const double rz = st->rz;
+  st->rz = 0.0; st->pq = 0.0; st->xbr = 0.0;
+  st->it += 1;
+  st->last_rho = st->rho; st->rho = rz;
+  if (rz == 0.0 || !isfinite(rz)) { st->failed = 1; st->done = 1; return; }
+  double beta = 0.0;
+  if (st->it > 1) { beta = rz / st->last_rho; if (beta == 0.0 || !isfinite(beta)) { st->failed = 1; st->done = 1; } }
+  st->beta = beta;
+}
+// p = z (+ beta p)
+static __global__ void __launch_bounds__(256) cgm_dir_kernel(const double* z, double* p, int n, const CGState* st) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = st->it == 1 ? z[i] : z[i] + st->beta * p[i];
+}
+// pq += p.q
+static __global__ void __launch_bounds__(256) cgm_pq_kernel(const double* p, const double* q, int n, CGState* st) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = i < n ? p[i] * q[i] : 0.0;
+  v = cta_sum(v);
+  if (threadIdx.x == 0) atomicAdd(&st->pq, v);
+}
+static __global__ void cgm_alpha_kernel(CGState* st) {
+  if (st->done) return;
+  const double pq = st->pq;
+  if (pq <= 0.0 || !isfinite(pq)) { st->done = 1; st->alpha = 0.0; return; }   // not positive definite along p: keep x
+  const double alpha = st->rho / pq;
+  if (!isfinite(alpha)) { st->failed = 1; st->done = 1; st->alpha = 0.0; return; }
+  st->alpha = alpha;
+}
+// x += alpha p ; r -= alpha q (unless this is a refresh iteration) ; xbr += x.(b + r) when no refresh follows
+static __global__ void __launch_bounds__(256) cgm_update_kernel(const double* b, const double* p, const double* q, double* x, double* r,
+                                                                int n, CGState* st) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool refresh = (st->it % 10) == 0;
+  const double alpha = st->alpha;
+  double v = 0.0;
+  if (i < n) {
+    const double xi = x[i] + alpha * p[i];
+    x[i] = xi;
+    if (!refresh) { const double ri = r[i] - alpha * q[i]; r[i] = ri; v = xi * (b[i] + ri); }
+  }
+  if (!refresh) { v = cta_sum(v); if (threadIdx.x == 0) atomicAdd(&st->xbr, v); }
+}
+// refresh iterations: r = b - S x ; xbr += x.(b + r)
+static __global__ void __launch_bounds__(256) cgm_refresh_kernel(const double* b, const double* Sx, const double* x, double* r, int n, CGState* st) {
+  if (st->done || (st->it % 10) != 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < n) { const double ri = b[i] - Sx[i]; r[i] = ri; v = x[i] * (b[i] + ri); }
+  v = cta_sum(v);
+  if (threadIdx.x == 0) atomicAdd(&st->xbr, v);
+}
+static __global__ void cgm_check_kernel(CGState* st) {
+  if (st->done) return;
+  const double Q1 = -0.5 * st->xbr;
+  const double zeta = st->it * (Q1 - st->Q0) / Q1;
+  if (zeta < st->q_tol) st->done = 1;
+  st->Q0 = Q1;
+  if (st->it >= st->max_iter) st->done = 1;
 }
 
 }  // namespace pxr

@@ -220,3 +220,14 @@ def test_iterative_schur_block_sparse_matches_dense_and_oracle(variant, monkeypa
     assert abs(s_sparse["final_cost"] - s_ref["final_cost"]) <= 1e-5 * s_ref["final_cost"]
     _compare_solutions(p_sparse, p_dense, 1e-5)
     _compare_solutions(p_sparse, p_ref, 1e-4)
+    # the multi-CTA vector kernels (what runs from 4096 unknowns) give the same trajectory
+    monkeypatch.setenv("PXR_CG_MULTI", "1")
+    for sparse in (False, True):
+        if sparse:
+            monkeypatch.setenv("PXR_PCG_SPARSE", "1")
+        p_m = prob.copy()
+        s_m = _engine.ba_run(p_m, ic, so)
+        it_m = [i["linear_solver_iterations"] for i in s_m["iterations"][1:]]
+        assert len(it_m) == len(it_d) and max(abs(a - b) for a, b in zip(it_m, it_d)) <= 2, (it_m, it_d)
+        assert abs(s_m["final_cost"] - s_dense["final_cost"]) <= 1e-6 * s_dense["final_cost"]
+        _compare_solutions(p_m, p_dense, 1e-5)
