@@ -121,6 +121,10 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   if (ic) interp = *ic; else pxr_default_interp_config(&interp);
   if (so) opt = *so; else pxr_default_ba_options(&opt);
   if (interp.check_bounds) return fail(PXR_ERR_UNSUPPORTED, "check_bounds=true is not supported on this path");
+  env.pcg_sparse = getenv("PXR_PCG_SPARSE") != nullptr; env.build_atomic = getenv("PXR_BUILD_ATOMIC") != nullptr;
+  env.chol_multikernel = getenv("PXR_CHOL_MULTIKERNEL") != nullptr; env.chol_test_abort = getenv("PXR_CHOL_TEST_ABORT") != nullptr;
+  env.cg_multi = getenv("PXR_CG_MULTI") != nullptr; env.no_speculation = getenv("PXR_NO_SPECULATION") != nullptr;
+  if (const char* t = getenv("PXR_CHOL_TRACE")) env.chol_trace = t;
   PXR_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   n_cameras = d->n_cameras; n_images = d->n_images; n_points = d->n_points; n_obs = d->n_obs;
@@ -256,7 +260,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     h_img_cam.assign(d->img_cam, d->img_cam + n_images);
     // implicit block-sparse reduced system: on request, or when the dense one would not fit comfortably
     sparse_schur = for_solve && use_pcg && dc_needed <= 8 && n_obs > 0 &&
-                   (getenv("PXR_PCG_SPARSE") != nullptr || (int64_t)nc * nc * 8 > (int64_t)4e9);
+                   (env.pcg_sparse || (int64_t)nc * nc * 8 > (int64_t)4e9);
     if (!sparse_schur && (int64_t)nc * nc * 8 > (int64_t)40e9)
       return fail(PXR_ERR_UNSUPPORTED, "reduced camera system too large for the dense path (nc=%d) and the block-sparse path needs ITERATIVE_SCHUR with <= 8 camera columns per image", nc);
   }
@@ -474,7 +478,7 @@ int BA::build() {
   PXR_TRY(gc.zero(ctx->stream));
   PXR_TRY(Hpp.zero(ctx->stream));
   PXR_TRY(gp.zero(ctx->stream));
-  const bool chunked = io_n_chunks > 0 && (sparse_schur || getenv("PXR_BUILD_ATOMIC") == nullptr);
+  const bool chunked = io_n_chunks > 0 && (sparse_schur || !env.build_atomic);
   if (sparse_schur && !chunked && n_obs > 0) return fail(PXR_ERR_INTERNAL, "block-sparse path without per-image chunks");
   if (sparse_schur) PXR_TRY(ss_Himg.zero(ctx->stream));
   if (n_obs > 0) {
@@ -558,7 +562,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     // The factorisation + back-substitution is a fixed sequence of ~3*nc/32 dependent launches: it is
     // captured once into a CUDA graph and replayed, which removes the per-launch gaps.
     if (!chol_graph_exec) {
-      chol_multikernel = chol_force_multikernel || getenv("PXR_CHOL_MULTIKERNEL") != nullptr;
+      chol_multikernel = chol_force_multikernel || env.chol_multikernel;
       if (!chol_multikernel) {
         // every CTA of the persistent kernel must be resident at once: grid = occupancy x SMs
         int per_sm = 0, sms = 0, dev = 0;
@@ -570,7 +574,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
         const int64_t tiles = (int64_t)(nbt + 1) * nbt / 2 + nbt;
         chol_grid = (int)std::min<int64_t>((int64_t)per_sm * sms, std::max<int64_t>(2, tiles + 1));
         PXR_TRY(chol_sync.alloc(pxr_chol::sync_ints(nbt)));
-        if (getenv("PXR_CHOL_TRACE")) { PXR_TRY(chol_trace.alloc((size_t)(nbt + 2) * 8 + nbt)); PXR_TRY(chol_trace.zero(s)); }
+        if (!env.chol_trace.empty()) { PXR_TRY(chol_trace.alloc((size_t)(nbt + 2) * 8 + nbt)); PXR_TRY(chol_trace.zero(s)); }
       }
       cudaGraph_t graph = nullptr;
       PXR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -608,7 +612,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
       std::vector<long long> h(chol_trace.n);
       PXR_CUDA(cudaMemcpyAsync(h.data(), chol_trace.p, h.size() * 8, cudaMemcpyDeviceToHost, s));
       PXR_CUDA(cudaStreamSynchronize(s));
-      if (FILE* f = fopen(getenv("PXR_CHOL_TRACE"), "w")) {
+      if (FILE* f = fopen(env.chol_trace.c_str(), "w")) {
         const int nbt = (int)cdiv(nc, kNB);
         for (int k = 0; k < nbt; ++k) { for (int q = 0; q < 7; ++q) fprintf(f, "%lld ", h[(size_t)k * 8 + q] - h[0]); fprintf(f, "\n"); }
         fprintf(f, "backsolve_start %lld\n", h[(size_t)nbt * 8] - h[0]);
@@ -627,7 +631,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   PXR_CUDA(cudaGetLastError());
   delete st;
   double acc = 0, fld = 0;
-  if (chol_graph_exec && !chol_multikernel && !use_pcg && getenv("PXR_CHOL_TEST_ABORT")) {
+  if (chol_graph_exec && !chol_multikernel && !use_pcg && env.chol_test_abort) {
     // test hook: pretend the persistent kernel bailed out of a wait (abort word + failure flag)
     const int one = 1;
     PXR_CUDA(cudaMemcpyAsync(chol_sync.p + (pxr_chol::sync_ints((int)cdiv(nc, kNB)) - 1), &one, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -852,7 +856,7 @@ int BA::pcg_solve() {
 int BA::run_cg(const std::function<int(const double*, double*)>& spmv) {
   cudaStream_t s = ctx->stream;
   const int n = nc;
-  const bool multi = n >= 4096 || getenv("PXR_CG_MULTI") != nullptr;
+  const bool multi = n >= 4096 || env.cg_multi;
   const unsigned gn = (unsigned)cdiv(n, 256);
   CGState hs;
   if (multi) {
@@ -985,7 +989,7 @@ int BA::lm_iterate(int max_iteration) {
     lm.num_invalid = 0;
 
     double step_norm = 0, x_norm = 0, candidate_cost = 0;
-    const bool speculate = !lm.inner_enabled && getenv("PXR_NO_SPECULATION") == nullptr;
+    const bool speculate = !lm.inner_enabled && !env.no_speculation;
     // the norms of the step are read back together with the trial cost (one host round trip instead of two)
     if (speculate) PXR_TRY(apply_step(nullptr, nullptr)); else PXR_TRY(apply_step(&step_norm, &x_norm));
     // Trial point.  Ceres evaluates the cost here and, if the step is accepted, evaluates residuals AND Jacobians
