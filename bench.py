@@ -70,20 +70,57 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons under load (B200_PROFILING.md).  The timed region of the default run is
+    ~12 ms, shorter than nvidia-smi's start-up and sampling period, so the sampler is started BEFORE the warm-up (the
+    same kernels on the same data) and every line is time-stamped: the summary uses the samples between the start of
+    the warm-up and the end of the timed region (plus the first one after it) and says how many fell inside the
+    timed region itself."""
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.t_load0 = self.t0 = self.t1 = None
+
+    def _start_nvml(self):
+        """NVML polled every 2 ms from a thread: fine enough for a 12 ms timed region (nvidia-smi -lms is not)."""
+        import pynvml
+        pynvml.nvmlInit()
+        self.nvml = pynvml
+        self.nv_handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nv_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.nv_handle, pynvml.NVML_CLOCK_SM))
+        self.nv_stop = False
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+        def loop():
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.nv_stop:
+                try:
+                    mhz = float(pynvml.nvmlDeviceGetClockInfo(self.nv_handle, pynvml.NVML_CLOCK_SM))
+                    r = int(get_reasons(self.nv_handle))
+                    flags = ",".join("Active" if (r & b) else "Not Active" for b in bits.values())
+                    self.lines.append((time.time(), "%d, %f, %f, 0, 0, %s" % (self.index, mhz, self.nv_max, flags)))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+        self.t = threading.Thread(target=loop, daemon=True)
+        self.t.start()
+        self.proc = True
+        self.period_ms = 2
 
     def start(self):
+        self.period_ms = 20
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml = None
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -92,19 +129,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def wait_first_sample(self, timeout=3.0):
+        t_end = time.time() + timeout
+        while self.proc and not self.lines and time.time() < t_end:
+            time.sleep(0.01)
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        time.sleep(0.06)        # let one more sample land right after the timed region
+        if getattr(self, "nvml", None):
+            self.nv_stop = True
+            self.t.join(timeout=1)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, smax, reasons, inside = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lo = self.t_load0 if self.t_load0 is not None else 0.0
+        hi = (self.t1 if self.t1 is not None else time.time()) + 0.05
+        for ts, ln in self.lines:
+            if ts < lo or ts > hi:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -112,11 +163,15 @@ class ClockSampler:
                 sm.append(float(f[1])); smax.append(float(f[2]))
             except ValueError:
                 continue
+            if self.t0 is not None and self.t1 is not None and self.t0 <= ts <= self.t1 + 0.02:
+                inside += 1
             for name, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": inside,
+                "window": "start of warm-up .. end of timed region (+50 ms)", "period_ms": self.period_ms,
+                "source": "NVML" if getattr(self, "nvml", None) else "nvidia-smi"}
 
 
 def geometry(args, rank):
@@ -276,20 +331,24 @@ def main():
     so = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.warmup + args.steps,
                                   linear_solver=args.linear_solver)
     h = _engine.BAHandle(prob, ic, so, ctx=ctx)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first_sample()
     # ---- warm-up: W iterations of the trajectory (plus iteration zero)
+    sampler.t_load0 = time.time()
     h.iterate(max(args.warmup, 0))
     ctx.sync()
     if dist is not None:
         dist.barrier()
     h.kernel_timing(enable=1, read=False)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.kernel_launches()
     ctx.timer_start()
     t0 = time.time()
+    sampler.t0 = t0
     s = h.iterate(args.steps)
     ms = ctx.timer_stop()
     wall = time.time() - t0
+    sampler.t1 = time.time()
     launches = ctx.kernel_launches() - launches0
     clocks = sampler.stop()
     stage_names = ["K1 cost-only", "K1 residual/Jacobian", "K0 projection", "block build", "damping+Schur assembly",

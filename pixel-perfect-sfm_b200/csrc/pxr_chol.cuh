@@ -248,19 +248,23 @@ __device__ __forceinline__ void solve_rows(double (*t)[TB + 1], double (*l)[TB +
 __device__ __forceinline__ void diag_block_inverses(double (*l)[TB + 1], double (*dinv)[8][9], int tid) {
   if (tid < TB) {
     const int b = tid >> 3, c = tid & 7, o = b * 8;
-    double x[8];
+    double rinv[8], x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) rinv[r] = 1.0 / l[o + r][o + r];     // independent: off the substitution chain
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       double sacc = (r == c) ? 1.0 : 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if (k < r) sacc -= l[o + r][o + k] * x[k];
-      x[r] = (r < c) ? 0.0 : sacc / l[o + r][o + r];
+      x[r] = (r < c) ? 0.0 : sacc * rinv[r];
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) dinv[b][r][c] = x[r];
   }
 }
+// Thread (r, j) = tid/8, tid%8 only ever touches row r of `t`, and the 8 threads of a row sit in one warp: the stages
+// are separated by __syncwarp(), not CTA barriers (l and dinv are read-only here).
 __device__ __forceinline__ void solve_rows_blocked(double (*t)[TB + 1], double (*l)[TB + 1], double (*dinv)[8][9], int tid) {
   const int r = tid >> 3, j = tid & 7;              // 256 threads: row r, column j of the current block
 #pragma unroll
@@ -271,9 +275,9 @@ __device__ __forceinline__ void solve_rows_blocked(double (*t)[TB + 1], double (
     double xv = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) xv += rv[k] * dinv[b][j][k];      // (L_bb^-1)^T: entries k <= j
-    __syncthreads();
+    __syncwarp();
     t[r][b * 8 + j] = xv;
-    __syncthreads();
+    __syncwarp();
     if (b < 3) {
       double xr[8];
 #pragma unroll
@@ -285,7 +289,7 @@ __device__ __forceinline__ void solve_rows_blocked(double (*t)[TB + 1], double (
         for (int k = 0; k < 8; ++k) u += xr[k] * l[c * 8 + j][b * 8 + k];
         t[r][c * 8 + j] -= u;
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
 }
@@ -358,12 +362,11 @@ static __global__ void __launch_bounds__(kThreads, 2) chol_persistent_kernel(Arg
       }
       __syncthreads();
       PXR_CHOL_STAMP(2);                              // factor done AND both prefetches landed
+      diag_block_inverses(sbuf[ia], sdinv, tid);      // warp 0, while the other warps already store L_kk
       store_tile<kThreads>(sbuf[ia], A, g, k, k, tid, true);
       __syncthreads();                                // barrier + release store by one thread is cumulative
       if (tid == 0) st_release(a.diag_ready + k, 1);
       PXR_CHOL_STAMP(3);
-      diag_block_inverses(sbuf[ia], sdinv, tid);
-      __syncthreads();
       solve_rows_blocked(sbuf[ib], sbuf[ia], sdinv, tid);
       __syncthreads();
       PXR_CHOL_STAMP(4);
