@@ -495,10 +495,14 @@ int BA::build() {
   if (ctx->world > 1 && nc > 0) {
     // multi-GPU: Hcc stays a per-rank partial sum (it only ever enters the reduced system, which is all-reduced
     // anyway); globally needed are its diagonal (Jacobi scaling / LM damping) and the gradient
-    if (!gc_local.p) PXR_TRY(gc_local.alloc(nc));
+    if (!gc_local.p) { PXR_TRY(gc_local.alloc(nc)); PXR_TRY(ar_buf.alloc((size_t)2 * nc)); }
     PXR_CUDA(cudaMemcpyAsync(gc_local.p, gc.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    PXR_TRY(allreduce_f64(ctx, diag.p, nc));
-    PXR_TRY(allreduce_f64(ctx, gc.p, nc));
+    // one collective for [diag(Hcc) | gc]
+    PXR_CUDA(cudaMemcpyAsync(ar_buf.p, diag.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    PXR_CUDA(cudaMemcpyAsync(ar_buf.p + nc, gc.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    PXR_TRY(allreduce_f64(ctx, ar_buf.p, (size_t)2 * nc));
+    PXR_CUDA(cudaMemcpyAsync(diag.p, ar_buf.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    PXR_CUDA(cudaMemcpyAsync(gc.p, ar_buf.p + nc, (size_t)nc * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   PXR_CUDA(cudaGetLastError());
   return PXR_OK;

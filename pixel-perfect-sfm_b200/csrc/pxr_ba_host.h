@@ -76,6 +76,7 @@ struct BA {
   // clobbers what the next compute_step reads.
   DevBuf<double> uv_alt, obs_out_alt, juv_alt;
   void swap_sets() { std::swap(uv.p, uv_alt.p); std::swap(uv.n, uv_alt.n); std::swap(obs_out.p, obs_out_alt.p); std::swap(obs_out.n, obs_out_alt.n); std::swap(juv.p, juv_alt.p); std::swap(juv.n, juv_alt.n); }
+  DevBuf<double> ar_buf;             // staging for the fused [diag | gc] all-reduce
   DevBuf<double> gc_local;           // multi-GPU: this rank's partial gradient (gc holds the global one)
   DevBuf<double> uv, obs_out, juv, Hcc, gc, Hpp, gp, W, S, rhs, diag, jscale, D2, delta, partials, scalars;
   DevBuf<int> flags;

@@ -50,6 +50,9 @@ struct KAArgs {
   double* prob_out;                 // [P][6]
   // query mode (REF): every edge is (keypoint e_k1, fixed descriptor ref_desc[e_k2]); block-diagonal normal equations,
   // workspace in global memory so that a problem may hold any number of keypoints
+  // dense mode: the normal equations are block diagonal over the connected components of the problem's edge graph
+  // (tracks packed into one problem do not couple); per variable the scalar range [lo, hi) of its component
+  const int32_t* var_blk_lo; const int32_t* var_blk_hi;   // [n_var]
   const double* ref_desc;           // [n_ref][C]
   double* workspace; const int64_t* ws_off;   // per problem: 26 * nv doubles at workspace + ws_off[p]
   int n_max;                        // max 2*nv over problems (shared memory sizing)
@@ -228,49 +231,60 @@ __device__ double ka_evaluate(const KAArgs& a, const KAWork& w, int64_t eb, int6
   return total;
 }
 
-// Cholesky of the packed lower matrix in place; returns false if not positive definite.
-__device__ bool ka_cholesky(double* L, int n, double* ctrl_flag) {
+// Block-diagonal variants: one warp per connected component [r0, r1) of the packed lower matrix.  The components of a
+// packed KA problem are its tracks (a handful of keypoints each), so this replaces an O(n^3) factorisation of the whole
+// problem (n up to 160, ~150 us) by many tiny ones that run in parallel.
+__device__ bool ka_cholesky_blocks(double* L, int n, const int32_t* bhi, double* ctrl_flag) {
   if (threadIdx.x == 0) *ctrl_flag = 0.0;
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    if (threadIdx.x == 0) {
-      const double d = L[tri(j, j)];
-      if (!(d > 0.0) || !isfinite(d)) { *ctrl_flag = 1.0; L[tri(j, j)] = 1.0; } else L[tri(j, j)] = sqrt(d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r0 = 0; r0 < n;) {
+    const int r1 = bhi[r0 >> 1];
+    // every warp walks the same block list; the block starting at variable v belongs to warp v % kKAWarps
+    if (((r0 >> 1) % kKAWarps) == warp) {
+      for (int j = r0; j < r1; ++j) {
+        double d = L[tri(j, j)];
+        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *ctrl_flag = 1.0; d = 1.0; }
+        const double dj = sqrt(d);
+        __syncwarp();
+        if (lane == 0) L[tri(j, j)] = dj;
+        for (int i = j + 1 + lane; i < r1; i += 32) L[tri(i, j)] /= dj;
+        __syncwarp();
+        const int m = r1 - (j + 1);
+        for (int e = lane; e < m * m; e += 32) {
+          const int i = j + 1 + e / m, k = j + 1 + e % m;
+          if (k <= i) L[tri(i, k)] -= L[tri(i, j)] * L[tri(k, j)];
+        }
+        __syncwarp();
+      }
     }
-    __syncthreads();
-    const double dj = L[tri(j, j)];
-    for (int i = j + 1 + threadIdx.x; i < n; i += kKAThreads) L[tri(i, j)] /= dj;
-    __syncthreads();
-    // trailing update: rows i > j, cols j < k <= i
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = j + 1 + warp; i < n; i += kKAWarps) {
-      const double lij = L[tri(i, j)];
-      for (int k = j + 1 + lane; k <= i; k += 32) L[tri(i, k)] -= lij * L[tri(k, j)];
-    }
-    __syncthreads();
+    r0 = r1;
   }
+  __syncthreads();
   return *ctrl_flag == 0.0;
 }
-
-// solves L L^T y = b (b -> y), warp 0
-__device__ void ka_chol_solve(const double* L, int n, double* b) {
+__device__ void ka_chol_solve_blocks(const double* L, int n, const int32_t* bhi, double* b) {
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    for (int i = 0; i < n; ++i) {
-      double s = 0.0;
-      for (int k = lane; k < i; k += 32) s += L[tri(i, k)] * b[k];
-      s = warp_sum(s);
-      if (lane == 0) b[i] = (b[i] - s) / L[tri(i, i)];
-      __syncwarp();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r0 = 0; r0 < n;) {
+    const int r1 = bhi[r0 >> 1];
+    if (((r0 >> 1) % kKAWarps) == warp) {
+      for (int i = r0; i < r1; ++i) {
+        double sacc = 0.0;
+        for (int k = r0 + lane; k < i; k += 32) sacc += L[tri(i, k)] * b[k];
+        sacc = warp_sum(sacc);
+        if (lane == 0) b[i] = (b[i] - sacc) / L[tri(i, i)];
+        __syncwarp();
+      }
+      for (int i = r1 - 1; i >= r0; --i) {
+        double sacc = 0.0;
+        for (int k = i + 1 + lane; k < r1; k += 32) sacc += L[tri(k, i)] * b[k];
+        sacc = warp_sum(sacc);
+        if (lane == 0) b[i] = (b[i] - sacc) / L[tri(i, i)];
+        __syncwarp();
+      }
     }
-    for (int i = n - 1; i >= 0; --i) {
-      double s = 0.0;
-      for (int k = i + 1 + lane; k < n; k += 32) s += L[tri(k, i)] * b[k];
-      s = warp_sum(s);
-      if (lane == 0) b[i] = (b[i] - s) / L[tri(i, i)];
-      __syncwarp();
-    }
+    r0 = r1;
   }
   __syncthreads();
 }
@@ -453,18 +467,20 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
       mcc = -block_sum(part);
       valid = w.ctrl[C_FLAG] == 0.0 && isfinite(mcc) && mcc > 0.0;
     } else {
+    const int32_t* blo = a.var_blk_lo + vb;
+    const int32_t* bhi = a.var_blk_hi + vb;
     for (int i = tid; i < n * (n + 1) / 2; i += kKAThreads) w.L[i] = w.H[i];
     __syncthreads();
     for (int i = tid; i < n; i += kKAThreads) w.L[tri(i, i)] += w.D2[i];
     __syncthreads();
-    valid = ka_cholesky(w.L, n, &w.ctrl[C_FLAG]);
+    valid = ka_cholesky_blocks(w.L, n, bhi, &w.ctrl[C_FLAG]);
     if (valid) {
-      ka_chol_solve(w.L, n, w.delta);
-      // model cost change = -g.d - d^T H d / 2
+      ka_chol_solve_blocks(w.L, n, bhi, w.delta);
+      // model cost change = -g.d - d^T H d / 2 (H is block diagonal over the components)
       double part = 0.0;
       for (int i = tid; i < n; i += kKAThreads) {
         double hd = 0.0;
-        for (int j = 0; j < n; ++j) hd += (i >= j ? w.H[tri(i, j)] : w.H[tri(j, i)]) * w.delta[j];
+        for (int j = blo[i >> 1]; j < bhi[i >> 1]; ++j) hd += (i >= j ? w.H[tri(i, j)] : w.H[tri(j, i)]) * w.delta[j];
         part += w.g[i] * w.delta[i] + 0.5 * w.delta[i] * hd;
         if (!isfinite(w.delta[i])) part = nan("");
       }
@@ -625,9 +641,12 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
   const bool constrained = d->bound > 0.0 || d->patches_are_sparse;
   int n_max = 0;
   std::vector<int64_t> owner(d->n_keypoints, -1);
+  std::vector<int32_t> vblo, vbhi;      // per variable: scalar range of its connected component (dense mode)
   for (int p = 0; p < P; ++p) {
     std::unordered_map<int64_t, int> idx;
-    pvb[p] = (int32_t)var_kp.size();
+    const size_t v0 = var_kp.size();
+    pvb[p] = (int32_t)v0;
+    std::vector<double> lo_p, hi_p;
     for (int64_t e = peb[p]; e < peb[p + 1]; ++e) {
       const int64_t ks[2] = {d->edge_src[e], refmode ? -1 : d->edge_dst[e]};
       int v[2] = {-1, -1};
@@ -648,13 +667,41 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
               hix = std::min(k[0] + d->bound / sx, hix); hiy = std::min(k[1] + d->bound / sy, hiy);
               lox = std::max(k[0] - d->bound / sx, lox); loy = std::max(k[1] - d->bound / sy, loy);
             }
-            vlo.push_back(lox); vlo.push_back(loy); vhi.push_back(hix); vhi.push_back(hiy);
+            lo_p.push_back(lox); lo_p.push_back(loy); hi_p.push_back(hix); hi_p.push_back(hiy);
           } else v[q] = it->second;
         }
       }
       ev1[e] = v[0]; ev2[e] = v[1];
     }
-    n_max = std::max(n_max, 2 * (int)idx.size());
+    const int nvp = (int)idx.size();
+    // connected components of the variables (union-find over edges with two variable endpoints), then a stable
+    // reordering that makes every component contiguous: J^T J is block diagonal over them
+    std::vector<int> parent(nvp), order(nvp), newidx(nvp);
+    for (int i = 0; i < nvp; ++i) parent[i] = i;
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    if (!refmode)
+      for (int64_t e = peb[p]; e < peb[p + 1]; ++e)
+        if (ev1[e] >= 0 && ev2[e] >= 0) { const int ra = find(ev1[e]), rb = find(ev2[e]); if (ra != rb) parent[std::max(ra, rb)] = std::min(ra, rb); }
+    for (int i = 0; i < nvp; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return find(x) < find(y); });
+    for (int i = 0; i < nvp; ++i) newidx[order[i]] = i;
+    std::vector<int64_t> kp_p(var_kp.begin() + v0, var_kp.end());
+    for (int i = 0; i < nvp; ++i) {
+      var_kp[v0 + i] = kp_p[order[i]];
+      vlo.push_back(lo_p[2 * order[i]]); vlo.push_back(lo_p[2 * order[i] + 1]);
+      vhi.push_back(hi_p[2 * order[i]]); vhi.push_back(hi_p[2 * order[i] + 1]);
+    }
+    for (int64_t e = peb[p]; e < peb[p + 1]; ++e) {
+      if (ev1[e] >= 0) ev1[e] = newidx[ev1[e]];
+      if (ev2[e] >= 0) ev2[e] = newidx[ev2[e]];
+    }
+    for (int i = 0; i < nvp;) {
+      int jn = i + 1;
+      while (jn < nvp && find(order[jn]) == find(order[i])) ++jn;
+      for (int q = i; q < jn; ++q) { vblo.push_back(2 * i); vbhi.push_back(2 * jn); }
+      i = jn;
+    }
+    n_max = std::max(n_max, 2 * nvp);
   }
   pvb[P] = (int32_t)var_kp.size();
   if (!refmode && n_max > 160) return fail(PXR_ERR_UNSUPPORTED, "a KA problem has %d variable keypoints (> 80 supported per problem)", n_max / 2);
@@ -671,6 +718,8 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
   if (d->edge_weight) PXR_TRY(d_w.upload(d->edge_weight, d->n_edges, s));
   PXR_TRY(d_varkp.upload(var_kp.data(), var_kp.size(), s));
   PXR_TRY(d_lo.upload(vlo.data(), vlo.size(), s)); PXR_TRY(d_hi.upload(vhi.data(), vhi.size(), s));
+  DevBuf<int32_t> d_vblo, d_vbhi;
+  PXR_TRY(d_vblo.upload(vblo.data(), vblo.size(), s)); PXR_TRY(d_vbhi.upload(vbhi.data(), vbhi.size(), s));
   PXR_TRY(d_kp.upload(d->keypoints, (size_t)d->n_keypoints * 2, s));
   if (d->kp_patch) PXR_TRY(d_kppatch.upload(d->kp_patch, d->n_keypoints, s));
   const int64_t n_patches = d->kp_patch ? d->n_patches : std::max(d->n_patches, d->n_keypoints);
@@ -703,7 +752,7 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
   KAArgs a;
   a.n_problems = P; a.prob_edge_begin = d_peb.p; a.prob_var_begin = d_pvb.p;
   a.e_k1 = d_k1.p; a.e_k2 = d_k2.p; a.e_v1 = d_v1.p; a.e_v2 = d_v2.p; a.e_w = d->edge_weight ? d_w.p : nullptr;
-  a.var_kp = d_varkp.p; a.var_lower = d_lo.p; a.var_upper = d_hi.p;
+  a.var_kp = d_varkp.p; a.var_lower = d_lo.p; a.var_upper = d_hi.p; a.var_blk_lo = d_vblo.p; a.var_blk_hi = d_vbhi.p;
   a.keypoints = d_kp.p; a.kp_patch = d->kp_patch ? d_kppatch.p : nullptr;
   a.patches = dp; a.ph = d->ph; a.pw = d->pw; a.corner = d_corner.p; a.scale = d_scale.p; a.ups = d->upsampling_factor;
   a.loss.type = so.loss_type; a.loss.a = so.loss_scale; a.l2_normalize = ic.l2_normalize; a.constrained = constrained ? 1 : 0;
