@@ -779,12 +779,16 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
                               : ((size_t)n_max * (n_max + 1) + 10 * (size_t)n_max + kKAWarps + C_N) * sizeof(double);
   const bool fs = ic.use_float_simd != 0;
   int rc = PXR_ERR_UNSUPPORTED;
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+  cudaEventCreate(&tev0); cudaEventCreate(&tev1);
+  cudaEventRecord(tev0, s);
 #define PXR_KA_CASE(T, CC) if (C == CC) rc = launch_ka<T, CC>(ctx, fs, refmode, a, smem);
   if (d->patch_dtype == PXR_F16) { PXR_KA_CASE(__half, 128) PXR_KA_CASE(__half, 64) PXR_KA_CASE(__half, 32) PXR_KA_CASE(__half, 16) PXR_KA_CASE(__half, 8) }
   else if (d->patch_dtype == PXR_F32) { PXR_KA_CASE(float, 128) PXR_KA_CASE(float, 16) }
   else { PXR_KA_CASE(double, 128) PXR_KA_CASE(double, 16) }
 #undef PXR_KA_CASE
-  if (rc != PXR_OK) return rc;
+  cudaEventRecord(tev1, s);
+  if (rc != PXR_OK) { cudaEventDestroy(tev0); cudaEventDestroy(tev1); return rc; }
   std::vector<double> out((size_t)P * 6);
   PXR_CUDA(cudaMemcpyAsync(out.data(), d_out.p, out.size() * 8, cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaMemcpyAsync(d->keypoints, d_kp.p, (size_t)d->n_keypoints * 16, cudaMemcpyDeviceToHost, s));
@@ -799,7 +803,10 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
     summary->h2d_bytes = h2d; summary->d2h_bytes = d->n_keypoints * 16.0 + P * 48.0;
     summary->kernel_launches = ctx->launches - launches0;
     summary->solve_time_s = summary->total_time_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    std::snprintf(summary->message, sizeof(summary->message), "%d problems, max %d LM iterations", P, iters);
+    float kms = 0.f;
+    cudaEventElapsedTime(&kms, tev0, tev1);
+    std::snprintf(summary->message, sizeof(summary->message), "%d problems, max %d LM iterations, solve kernel %.3f ms", P, iters, kms);
   }
+  cudaEventDestroy(tev0); cudaEventDestroy(tev1);
   return PXR_OK;
 }
