@@ -103,6 +103,7 @@ int pxr_ctx_destroy(pxr_ctx* ctx) {
   if (!ctx) return PXR_OK;
   cudaSetDevice(ctx->device);
   if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+  pxr::stager_destroy(ctx);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return PXR_OK;

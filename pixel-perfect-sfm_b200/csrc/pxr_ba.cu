@@ -141,23 +141,16 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     for (int b = 0; b < d->n_patch_blocks; ++b) tot += d->patch_block_counts[b];
     if (tot < n_patches) return fail(PXR_ERR_INVALID_ARGUMENT, "patch blocks hold %lld patches, %lld needed", (long long)tot, (long long)n_patches);
     PXR_TRY(patches_owned.alloc((size_t)tot * ph * pw * C * esz));
-    size_t off = 0;
-    for (int b = 0; b < d->n_patch_blocks; ++b) {
-      const size_t bytes = (size_t)d->patch_block_counts[b] * ph * pw * C * esz;
-      // a block may live in host OR device memory (device-resident feature store): UVA resolves the direction
-      if (bytes) PXR_CUDA(cudaMemcpyAsync(patches_owned.p + off, d->patch_block_ptrs[b], bytes, cudaMemcpyDefault, s));
-      cudaPointerAttributes pa;
-      const bool on_dev = bytes && cudaPointerGetAttributes(&pa, d->patch_block_ptrs[b]) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
-      cudaGetLastError();   // unregistered host memory makes the query fail on old drivers: not an error here
-      if (!on_dev) h2d_patch += (double)bytes;
-      off += bytes;
-    }
+    // a block may live in host OR device memory (device-resident feature store): UVA resolves the direction
+    std::vector<size_t> seg_bytes((size_t)d->n_patch_blocks);
+    for (int b = 0; b < d->n_patch_blocks; ++b) seg_bytes[b] = (size_t)d->patch_block_counts[b] * ph * pw * C * esz;
+    PXR_TRY(upload_segments(ctx, patches_owned.p, d->patch_block_ptrs, seg_bytes.data(), d->n_patch_blocks, &h2d_patch));
     d_patches = patches_owned.p;
   } else if (d->patches_on_device) {
     d_patches = (const uint8_t*)d->patches;
   } else {
     PXR_TRY(patches_owned.alloc(pbytes));
-    PXR_CUDA(cudaMemcpyAsync(patches_owned.p, d->patches, pbytes, cudaMemcpyHostToDevice, s));
+    PXR_TRY(upload_bytes(ctx, patches_owned.p, d->patches, pbytes));
     h2d_patch = (double)pbytes;
     d_patches = patches_owned.p;
   }

@@ -10,6 +10,8 @@
 
 #include "../../include/pxr.h"
 
+namespace pxr { struct Stager; }
+
 struct pxr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -19,6 +21,7 @@ struct pxr_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  pxr::Stager* stager = nullptr;          // pinned ring of the pageable-memory upload pipeline (pxr_upload.cu)
 };
 
 namespace pxr {
@@ -73,6 +76,12 @@ struct DevBuf {
 };
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// large input upload on ctx->stream: any source (pinned, pageable, device); pageable sources are pipelined through a
+// pinned ring (pxr_upload.cu).  *h2d_bytes (optional) is incremented by the bytes that crossed PCIe.
+int upload_bytes(pxr_ctx* ctx, void* dst, const void* src, size_t bytes, double* h2d_bytes = nullptr);
+int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size_t* sizes, int n, double* h2d_bytes = nullptr);
+void stager_destroy(pxr_ctx* ctx);
 
 // allreduce (sum, fp64) on ctx->stream when a communicator is attached; no-op otherwise
 int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count, bool max_op = false);

@@ -735,19 +735,12 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
     if (tot < n_patches) return fail(PXR_ERR_INVALID_ARGUMENT, "patch blocks hold %lld patches, %lld needed", (long long)tot, (long long)n_patches);
     const size_t per = (size_t)d->ph * d->pw * C * esz;
     PXR_TRY(d_patches.alloc((size_t)tot * per));
-    size_t off = 0;
-    for (int b = 0; b < d->n_patch_blocks; ++b) {
-      const size_t bytes = (size_t)d->patch_block_counts[b] * per;
-      if (bytes) PXR_CUDA(cudaMemcpyAsync(d_patches.p + off, d->patch_block_ptrs[b], bytes, cudaMemcpyDefault, s));
-      cudaPointerAttributes pa;
-      const bool on_dev = bytes && cudaPointerGetAttributes(&pa, d->patch_block_ptrs[b]) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
-      cudaGetLastError();
-      if (!on_dev) h2d += (double)bytes;
-      off += bytes;
-    }
+    std::vector<size_t> seg_bytes((size_t)d->n_patch_blocks);
+    for (int b = 0; b < d->n_patch_blocks; ++b) seg_bytes[b] = (size_t)d->patch_block_counts[b] * per;
+    PXR_TRY(upload_segments(ctx, d_patches.p, d->patch_block_ptrs, seg_bytes.data(), d->n_patch_blocks, &h2d));
     dp = d_patches.p;
   } else if (d->patches_on_device) dp = (const uint8_t*)d->patches;
-  else { PXR_TRY(d_patches.alloc(pbytes)); PXR_CUDA(cudaMemcpyAsync(d_patches.p, d->patches, pbytes, cudaMemcpyHostToDevice, s)); dp = d_patches.p; h2d += pbytes; }
+  else { PXR_TRY(d_patches.alloc(pbytes)); PXR_TRY(upload_bytes(ctx, d_patches.p, d->patches, pbytes)); dp = d_patches.p; h2d += pbytes; }
   h2d += d->n_edges * 40.0 + d->n_keypoints * 24.0;
   KAArgs a;
   a.n_problems = P; a.prob_edge_begin = d_peb.p; a.prob_var_begin = d_pvb.p;

@@ -1,0 +1,159 @@
+// pxr_upload.cu — host -> device transfer of the feature patches, the only large input of the path.
+//
+// The reference keeps its feature maps in pageable host memory (numpy arrays behind FeatureMap / FeaturePatch,
+// features/src/featurepatch.h:35-70).  cudaMemcpy from pageable memory goes through the driver's single staging
+// buffer (~11 GB/s measured on the B200 box, profiles/README.md "Keypoint adjustment"); PCIe Gen5 x16 carries
+// ~50 GB/s from pinned memory.  upload_bytes() therefore
+//   * forwards pinned / registered / device / managed sources to ONE cudaMemcpyAsync on the context stream, and
+//   * pipelines large PAGEABLE sources itself: kThreads host threads each copy 4 MB chunks into their own pinned
+//     double buffer and issue the H2D copy on their own stream, so the host memcpy of one chunk overlaps the DMA of
+//     the others; the context stream then waits on every worker stream.
+// On return the source has been read completely (same contract as cudaMemcpyAsync from pageable memory).
+// Switches: PXR_STAGED_UPLOAD=0 disables the pipeline, PXR_STAGED_UPLOAD_MIN / PXR_STAGED_CHUNK (bytes) override the
+// 16 MB threshold and the 4 MB chunk (used by the tests to push small inputs through it).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "pxr_internal.h"
+
+namespace pxr {
+
+struct Stager {
+  static constexpr int kThreads = 6, kBufs = 2;
+  size_t chunk = 0;
+  uint8_t* pin[kThreads][kBufs] = {};
+  cudaStream_t st[kThreads] = {};
+  cudaEvent_t ev[kThreads][kBufs] = {};
+  cudaEvent_t start = nullptr;
+  ~Stager() {
+    for (int t = 0; t < kThreads; ++t) {
+      for (int b = 0; b < kBufs; ++b) {
+        if (ev[t][b]) cudaEventDestroy(ev[t][b]);
+        if (pin[t][b]) cudaFreeHost(pin[t][b]);
+      }
+      if (st[t]) cudaStreamDestroy(st[t]);
+    }
+    if (start) cudaEventDestroy(start);
+  }
+};
+
+static size_t env_bytes(const char* name, size_t dflt) {
+  const char* v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  const long long x = std::atoll(v);
+  return x > 0 ? (size_t)x : dflt;
+}
+
+static int stager_get(pxr_ctx* ctx, Stager** out) {
+  const size_t chunk = env_bytes("PXR_STAGED_CHUNK", (size_t)4 << 20);
+  if (ctx->stager && ctx->stager->chunk == chunk) { *out = ctx->stager; return PXR_OK; }
+  delete ctx->stager;
+  ctx->stager = nullptr;
+  Stager* s = new Stager();
+  s->chunk = chunk;
+  cudaError_t e = cudaEventCreateWithFlags(&s->start, cudaEventDisableTiming);
+  for (int t = 0; t < Stager::kThreads && e == cudaSuccess; ++t) {
+    e = cudaStreamCreateWithFlags(&s->st[t], cudaStreamNonBlocking);
+    for (int b = 0; b < Stager::kBufs && e == cudaSuccess; ++b) {
+      e = cudaHostAlloc((void**)&s->pin[t][b], chunk, cudaHostAllocDefault);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev[t][b], cudaEventDisableTiming);
+    }
+  }
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(PXR_ERR_CUDA, "staged upload: cannot create the pinned ring (%s)", cudaGetErrorString(e));
+  }
+  ctx->stager = s;
+  *out = s;
+  return PXR_OK;
+}
+
+void stager_destroy(pxr_ctx* ctx) {
+  delete ctx->stager;
+  ctx->stager = nullptr;
+}
+
+static cudaMemoryType source_type(const void* src) {
+  cudaPointerAttributes pa;
+  cudaMemoryType type = cudaMemoryTypeUnregistered;
+  if (cudaPointerGetAttributes(&pa, src) == cudaSuccess) type = pa.type;
+  cudaGetLastError();   // plain host memory makes the query fail on old drivers: not an error here
+  return type;
+}
+
+// dst <- srcs[0] | srcs[1] | ... (the per-image blocks of a feature set land in one slab).  h2d_bytes (optional) is
+// incremented by the bytes that crossed PCIe.
+int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size_t* sizes, int n, double* h2d_bytes) {
+  static const bool enabled = []() { const char* v = std::getenv("PXR_STAGED_UPLOAD"); return !(v && v[0] == '0'); }();
+  const size_t min_bytes = env_bytes("PXR_STAGED_UPLOAD_MIN", (size_t)16 << 20);
+  std::vector<size_t> begin((size_t)n + 1, 0);
+  bool all_pageable = true;
+  for (int i = 0; i < n; ++i) {
+    begin[i + 1] = begin[i] + sizes[i];
+    if (sizes[i] == 0) continue;
+    const cudaMemoryType type = source_type(srcs[i]);
+    if (type != cudaMemoryTypeUnregistered) all_pageable = false;
+    if (h2d_bytes && type != cudaMemoryTypeDevice) *h2d_bytes += (double)sizes[i];
+  }
+  const size_t bytes = begin[n];
+  if (bytes == 0) return PXR_OK;
+  if (!all_pageable || !enabled || bytes < min_bytes) {
+    for (int i = 0; i < n; ++i)
+      if (sizes[i]) PXR_CUDA(cudaMemcpyAsync((uint8_t*)dst + begin[i], srcs[i], sizes[i], cudaMemcpyDefault, ctx->stream));
+    return PXR_OK;
+  }
+  Stager* s = nullptr;
+  PXR_TRY(stager_get(ctx, &s));
+  const size_t chunk = s->chunk;
+  const size_t n_chunks = (bytes + chunk - 1) / chunk;
+  const int n_threads = (int)std::min<size_t>(Stager::kThreads, n_chunks);
+  // the destination may still be in use by earlier work on the context stream
+  PXR_CUDA(cudaEventRecord(s->start, ctx->stream));
+  cudaError_t errs[Stager::kThreads];
+  const int device = ctx->device;
+  auto work = [&](int t) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->st[t], s->start, 0);
+    size_t k = 0;
+    for (size_t c = t; c < n_chunks && e == cudaSuccess; c += n_threads, ++k) {
+      const int b = (int)(k % Stager::kBufs);
+      const size_t off = c * chunk, len = std::min(chunk, bytes - off);
+      e = cudaEventSynchronize(s->ev[t][b]);     // the previous DMA out of this buffer (this call or the last) is done
+      if (e != cudaSuccess) break;
+      // gather [off, off+len) of the concatenation: first segment with begin[i+1] > off
+      size_t i = (size_t)(std::upper_bound(begin.begin(), begin.end(), off) - begin.begin()) - 1;
+      for (size_t done = 0; done < len; ++i) {
+        const size_t so = off + done - begin[i], take = std::min(len - done, sizes[i] - so);
+        if (take) std::memcpy(s->pin[t][b] + done, (const uint8_t*)srcs[i] + so, take);
+        done += take;
+      }
+      e = cudaMemcpyAsync((uint8_t*)dst + off, s->pin[t][b], len, cudaMemcpyHostToDevice, s->st[t]);
+      if (e == cudaSuccess) e = cudaEventRecord(s->ev[t][b], s->st[t]);
+    }
+    errs[t] = e;
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < n_threads; ++t)
+    if (errs[t] != cudaSuccess) {
+      cudaDeviceSynchronize();
+      return fail(PXR_ERR_CUDA, "staged upload failed: %s", cudaGetErrorString(errs[t]));
+    }
+  // consumers run on the context stream: make it wait for the copies of every worker stream
+  for (int t = 0; t < n_threads; ++t) {
+    const size_t mine = (n_chunks - t + n_threads - 1) / n_threads;
+    const int last = (int)((mine - 1) % Stager::kBufs);
+    PXR_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[t][last], 0));   // worker streams are in order: the last event covers all
+  }
+  return PXR_OK;
+}
+
+int upload_bytes(pxr_ctx* ctx, void* dst, const void* src, size_t bytes, double* h2d_bytes) {
+  return upload_segments(ctx, dst, &src, &bytes, 1, h2d_bytes);
+}
+
+}  // namespace pxr
