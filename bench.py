@@ -423,7 +423,8 @@ def main():
             it2 = max(1, s2["num_iterations"] - 1)
             e2e = {"value": total_obs * it2 / dt, "unit": "observations/s",
                    "h2d_bytes_per_step": s2["h2d_bytes"] / it2, "d2h_bytes_per_step": s2["d2h_bytes"] / it2,
-                   "seconds": dt, "lm_iterations": it2, "pinned_host": bool(pinned),
+                   "seconds": dt, "library_seconds": s2["total_time_s"], "lm_loop_seconds": s2["solve_time_s"],
+                   "lm_iterations": it2, "pinned_host": bool(pinned),
                    "call": "pxr_ba_run (upload %.1f GB of patches + solve + read back)" % (pbytes / 1e9),
                    "final_cost": s2["final_cost"]}
             if pinned:
