@@ -39,6 +39,25 @@ def usable_cpus():
     return n
 
 
+def host_memory_available():
+    """bytes of host memory this job can still take: MemAvailable capped by the cgroup limit"""
+    avail = None
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim != "max":
+            left = int(lim) - int(open("/sys/fs/cgroup/memory.current").read())
+            avail = left if avail is None else min(avail, left)
+    except Exception:
+        pass
+    return avail
+
+
 # the CPU baseline uses OpenMP: no busy-waiting worker threads, bind nothing
 os.environ["NCCL_DEBUG"] = os.environ.get("PXR_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
@@ -394,9 +413,25 @@ def main():
 
     # ---- e2e: the public one-shot call on HOST buffers (upload + K iterations + read-back)
     e2e = None
-    if not args.no_e2e:
+    pbytes = n_obs * args.ps * args.ps * args.channels * 2
+    e2e_ok = not args.no_e2e
+    if e2e_ok:
+        # every rank of the node stages its own host copy of its shard: refuse (on ALL ranks, decided together and
+        # before anyone allocates) rather than drive the box out of memory
+        avail = host_memory_available()
+        fits = avail is None or avail >= 1.2 * world * pbytes
+        if dist is not None:
+            import torch
+            ft = torch.tensor([1 if fits else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(ft, op=dist.ReduceOp.MIN)
+            fits = bool(ft.item())
+        if not fits:
+            e2e_ok = False
+            e2e = {"value": None, "unit": "observations/s",
+                   "error": "e2e needs %d x %.1f GB of host memory for the patch slabs, %.1f GB available"
+                            % (world, pbytes / 1e9, (avail or 0) / 1e9)}
+    if e2e_ok:
         try:
-            pbytes = n_obs * args.ps * args.ps * args.channels * 2
             hp = C.c_void_p()
             pinned = ctx.lib.pxr_host_alloc_pinned(C.byref(hp), C.c_size_t(pbytes)) == 0
             if pinned:
