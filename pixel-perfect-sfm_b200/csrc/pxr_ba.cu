@@ -131,7 +131,11 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   C = d->channels; ph = d->ph; pw = d->pw; dtype = d->patch_dtype; ups = d->upsampling_factor;
   n_patches = d->obs_patch ? d->n_patches : std::max(d->n_patches, d->n_obs);
   has_refs = d->refs != nullptr;
-  // the big patch upload goes first: the host-side layout / co-visibility work below overlaps with the DMA
+  // the big patch upload goes first, on the context's side stream: the host-side layout / co-visibility work below
+  // (and the small synchronous uploads it makes on `s`) overlaps with the DMA; joined when create() returns
+  cudaStream_t us = nullptr;
+  PXR_TRY(upload_stream(ctx, &us));
+  struct JoinUpload { cudaStream_t us; ~JoinUpload() { cudaStreamSynchronize(us); } } join_upload{us};
   double h2d_patch = 0;
   const size_t esz = dtype == PXR_F16 ? 2 : (dtype == PXR_F32 ? 4 : 8);
   const size_t pbytes = (size_t)n_patches * ph * pw * C * esz;
@@ -144,13 +148,13 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     // a block may live in host OR device memory (device-resident feature store): UVA resolves the direction
     std::vector<size_t> seg_bytes((size_t)d->n_patch_blocks);
     for (int b = 0; b < d->n_patch_blocks; ++b) seg_bytes[b] = (size_t)d->patch_block_counts[b] * ph * pw * C * esz;
-    PXR_TRY(upload_segments(ctx, patches_owned.p, d->patch_block_ptrs, seg_bytes.data(), d->n_patch_blocks, &h2d_patch));
+    PXR_TRY(upload_segments(ctx, patches_owned.p, d->patch_block_ptrs, seg_bytes.data(), d->n_patch_blocks, &h2d_patch, us));
     d_patches = patches_owned.p;
   } else if (d->patches_on_device) {
     d_patches = (const uint8_t*)d->patches;
   } else {
     PXR_TRY(patches_owned.alloc(pbytes));
-    PXR_TRY(upload_bytes(ctx, patches_owned.p, d->patches, pbytes));
+    PXR_TRY(upload_bytes(ctx, patches_owned.p, d->patches, pbytes, nullptr, us));
     h2d_patch = (double)pbytes;
     d_patches = patches_owned.p;
   }

@@ -22,6 +22,7 @@ struct pxr_ctx {
   int rank = 0, world = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   pxr::Stager* stager = nullptr;          // pinned ring of the pageable-memory upload pipeline (pxr_upload.cu)
+  cudaStream_t upload_stream = nullptr;   // carries the patch slab so that host-side setup (and its small syncs) overlaps it
 };
 
 namespace pxr {
@@ -79,8 +80,12 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // large input upload on ctx->stream: any source (pinned, pageable, device); pageable sources are pipelined through a
 // pinned ring (pxr_upload.cu).  *h2d_bytes (optional) is incremented by the bytes that crossed PCIe.
-int upload_bytes(pxr_ctx* ctx, void* dst, const void* src, size_t bytes, double* h2d_bytes = nullptr);
-int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size_t* sizes, int n, double* h2d_bytes = nullptr);
+// `stream` (default: ctx->stream) is the stream the copies are ordered on.
+int upload_bytes(pxr_ctx* ctx, void* dst, const void* src, size_t bytes, double* h2d_bytes = nullptr, cudaStream_t stream = nullptr);
+int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size_t* sizes, int n, double* h2d_bytes = nullptr,
+                    cudaStream_t stream = nullptr);
+// the context's side stream for the patch slab (created on first use)
+int upload_stream(pxr_ctx* ctx, cudaStream_t* out);
 void stager_destroy(pxr_ctx* ctx);
 
 // allreduce (sum, fp64) on ctx->stream when a communicator is attached; no-op otherwise

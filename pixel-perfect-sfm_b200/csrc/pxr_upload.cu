@@ -73,6 +73,8 @@ static int stager_get(pxr_ctx* ctx, Stager** out) {
 void stager_destroy(pxr_ctx* ctx) {
   delete ctx->stager;
   ctx->stager = nullptr;
+  if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+  ctx->upload_stream = nullptr;
 }
 
 static cudaMemoryType source_type(const void* src) {
@@ -85,7 +87,9 @@ static cudaMemoryType source_type(const void* src) {
 
 // dst <- srcs[0] | srcs[1] | ... (the per-image blocks of a feature set land in one slab).  h2d_bytes (optional) is
 // incremented by the bytes that crossed PCIe.
-int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size_t* sizes, int n, double* h2d_bytes) {
+int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size_t* sizes, int n, double* h2d_bytes,
+                    cudaStream_t stream) {
+  if (!stream) stream = ctx->stream;
   static const bool enabled = []() { const char* v = std::getenv("PXR_STAGED_UPLOAD"); return !(v && v[0] == '0'); }();
   const size_t min_bytes = env_bytes("PXR_STAGED_UPLOAD_MIN", (size_t)16 << 20);
   std::vector<size_t> begin((size_t)n + 1, 0);
@@ -100,8 +104,12 @@ int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size
   const size_t bytes = begin[n];
   if (bytes == 0) return PXR_OK;
   if (!all_pageable || !enabled || bytes < min_bytes) {
+    // in pieces: small copies other streams make meanwhile (the problem tables) are not queued behind 32 GB
+    const size_t piece = (size_t)256 << 20;
     for (int i = 0; i < n; ++i)
-      if (sizes[i]) PXR_CUDA(cudaMemcpyAsync((uint8_t*)dst + begin[i], srcs[i], sizes[i], cudaMemcpyDefault, ctx->stream));
+      for (size_t o = 0; o < sizes[i]; o += piece)
+        PXR_CUDA(cudaMemcpyAsync((uint8_t*)dst + begin[i] + o, (const uint8_t*)srcs[i] + o, std::min(piece, sizes[i] - o),
+                                 cudaMemcpyDefault, stream));
     return PXR_OK;
   }
   Stager* s = nullptr;
@@ -109,8 +117,8 @@ int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size
   const size_t chunk = s->chunk;
   const size_t n_chunks = (bytes + chunk - 1) / chunk;
   const int n_threads = (int)std::min<size_t>(Stager::kThreads, n_chunks);
-  // the destination may still be in use by earlier work on the context stream
-  PXR_CUDA(cudaEventRecord(s->start, ctx->stream));
+  // the destination may still be in use by earlier work on the consumer stream
+  PXR_CUDA(cudaEventRecord(s->start, stream));
   cudaError_t errs[Stager::kThreads];
   const int device = ctx->device;
   auto work = [&](int t) {
@@ -143,17 +151,24 @@ int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size
       cudaDeviceSynchronize();
       return fail(PXR_ERR_CUDA, "staged upload failed: %s", cudaGetErrorString(errs[t]));
     }
-  // consumers run on the context stream: make it wait for the copies of every worker stream
+  // make the consumer stream wait for the copies of every worker stream
   for (int t = 0; t < n_threads; ++t) {
     const size_t mine = (n_chunks - t + n_threads - 1) / n_threads;
     const int last = (int)((mine - 1) % Stager::kBufs);
-    PXR_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[t][last], 0));   // worker streams are in order: the last event covers all
+    PXR_CUDA(cudaStreamWaitEvent(stream, s->ev[t][last], 0));   // worker streams are in order: the last event covers all
   }
   return PXR_OK;
 }
 
-int upload_bytes(pxr_ctx* ctx, void* dst, const void* src, size_t bytes, double* h2d_bytes) {
-  return upload_segments(ctx, dst, &src, &bytes, 1, h2d_bytes);
+int upload_bytes(pxr_ctx* ctx, void* dst, const void* src, size_t bytes, double* h2d_bytes, cudaStream_t stream) {
+  return upload_segments(ctx, dst, &src, &bytes, 1, h2d_bytes, stream);
+}
+
+int upload_stream(pxr_ctx* ctx, cudaStream_t* out) {
+  if (std::getenv("PXR_UPLOAD_SAME_STREAM")) { *out = ctx->stream; return PXR_OK; }   // A/B switch: no overlap with host setup
+  if (!ctx->upload_stream) PXR_CUDA(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+  *out = ctx->upload_stream;
+  return PXR_OK;
 }
 
 }  // namespace pxr
