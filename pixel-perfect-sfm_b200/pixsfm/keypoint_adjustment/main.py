@@ -111,3 +111,22 @@ class TopologicalReferenceKeypointAdjuster(KeypointAdjuster):
         else:
             solver.run(keypoints_dict, graph, track_labels, root_labels, feature_set)
         return {"summary": solver.summary()}
+
+
+def build_matching_graph(pairs, matches, scores=None):
+    """matches of a COLMAP database / hloc match file -> base.Graph (reference main.py:262-271)"""
+    logger.info("Building matching graph...")
+    graph = base.Graph()
+    scores = scores if scores is not None else [None] * len(matches)
+    for (name1, name2), m, s in zip(pairs, matches, scores):
+        graph.register_matches(name1, name2, m, s)
+    return graph
+
+
+def extract_patchdata_from_graph(graph):
+    """image name -> feature indices that take part in a match, i.e. the keypoints that need a patch
+    (reference main.py:274-279)"""
+    needed = {}
+    for node in graph.nodes:
+        needed.setdefault(graph.image_id_to_name[node.image_id], []).append(node.feature_idx)
+    return needed

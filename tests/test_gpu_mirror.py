@@ -187,3 +187,50 @@ def test_dense_feature_maps_match_oracle():
     assert abs(s.final_cost - s_o["final_cost"]) <= 1e-4 * s_o["final_cost"]
     with pytest.raises(ValueError):
         ba_pkg.BundleAdjuster.create({"strategy": "costmaps"}).refine_multilevel(copy.deepcopy(rec), fm)
+
+
+def test_keypoint_adjustment_from_a_colmap_database(tmp_path):
+    """refine_colmap.py:105-112 shape: keypoints + matches come out of a COLMAP database, the matching graph is built
+    from them, the keypoints are adjusted on the GPU and written back."""
+    from pixsfm.util import colmap as cio
+    from pixsfm.util.database import COLMAPDatabase
+    sc = synthetic.make_ka_scene(n_images=6, n_tracks=50, track_len=4, channels=128, seed=15, kp_sigma=1.0)
+    names = ["im%d.jpg" % i for i in range(6)]
+    path = tmp_path / "database.db"
+    db = COLMAPDatabase.connect(path)
+    db.create_tables()
+    cam = db.add_camera(2, 1000, 1000, [1200.0, 500.0, 500.0, 0.0])
+    ids = [db.add_image(n, cam) for n in names]
+    for i in range(6):
+        db.add_keypoints(ids[i], sc["keypoints"][sc["node_image"] == i])
+    by_pair = {}
+    for s, d in zip(sc["edge_src"], sc["edge_dst"]):
+        a, b = int(sc["node_image"][s]), int(sc["node_image"][d])
+        fa, fb = int(sc["node_feature"][s]), int(sc["node_feature"][d])
+        if a > b:
+            a, b, fa, fb = b, a, fb, fa
+        by_pair.setdefault((a, b), []).append((fa, fb))
+    for (a, b), m in by_pair.items():
+        db.add_matches(ids[a], ids[b], np.array(m, np.uint32))
+    db.commit(); db.close()
+
+    keypoints = cio.read_keypoints_from_db(path)
+    pairs, matches, scores = cio.read_matches_from_db(path)
+    assert scores is None and sum(len(m) for m in matches) == len(sc["edge_src"])
+    graph = ka_pkg.build_matching_graph(pairs, matches, scores)
+    needed = ka_pkg.extract_patchdata_from_graph(graph)
+    fm = features.FeatureManager([128], np.float16)
+    for i in range(6):
+        m = np.where(sc["node_image"] == i)[0]
+        assert set(needed[names[i]]) <= set(sc["node_feature"][m].tolist())
+        fm.fset(0).emplace(names[i], features.FeatureMap(np.ascontiguousarray(sc["patches"][m]), sc["node_feature"][m].tolist(),
+                                                          sc["corner"][m], {"scale": sc["scale"][m[0]], "is_sparse": True}))
+    before = {k: v.copy() for k, v in keypoints.items()}
+    out = ka_pkg.KeypointAdjuster.create({"max_kps_per_problem": 20}).refine_multilevel(keypoints, fm, graph)
+    s = out["summary"][0]
+    assert s.final_cost < 0.5 * s.initial_cost
+    assert all(np.abs(keypoints[k] - before[k]).max() > 1e-3 for k in keypoints)
+    cio.write_keypoints_to_db(path, keypoints)
+    back = cio.read_keypoints_from_db(path)
+    for k in keypoints:
+        assert np.array_equal(back[k], keypoints[k].astype(np.float32).astype(np.float64))
