@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <thread>
 
 #include "pxr_internal.h"
@@ -143,8 +144,14 @@ int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size
     errs[t] = e;
   };
   std::vector<std::thread> pool;
-  for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+  int started = 1;
+  try {
+    for (int t = 1; t < n_threads; ++t) { pool.emplace_back(work, t); ++started; }
+  } catch (const std::exception&) {
+    // no more threads to be had (container limits): the remaining shares run on this thread
+  }
   work(0);
+  for (int t = started; t < n_threads; ++t) work(t);
   for (auto& th : pool) th.join();
   for (int t = 0; t < n_threads; ++t)
     if (errs[t] != cudaSuccess) {
