@@ -394,6 +394,10 @@ int pxr_ka_problem_labels(int64_t n_nodes, const int64_t* track_labels, int32_t 
 /* Multi-GPU sharding plan: contiguous point ranges balanced by observation count. */
 int pxr_shard_points(int64_t n_points, int64_t n_obs, const int64_t* obs_pt, int world,
                      int64_t* point_begin_out /*[world+1]*/, int64_t* obs_begin_out /*[world+1]*/);
+/* KA: the packed problems are independent (ParallelOptimizer::RunParallel, base/src/parallel_optimizer.h:77-211,
+ * runs one task per label), so ranks take whole problems and need no collective.  `weight` = cost of a problem
+ * (patch bytes or edge count); heaviest-first onto the least loaded rank, deterministic. */
+int pxr_shard_ka_problems(int32_t n_problems, const int64_t* weight, int world, int32_t* rank_of_problem_out);
 
 #ifdef __cplusplus
 }

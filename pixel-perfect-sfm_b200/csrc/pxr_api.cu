@@ -325,4 +325,22 @@ int pxr_shard_points(int64_t n_points, int64_t n_obs, const int64_t* obs_pt, int
   return PXR_OK;
 }
 
+int pxr_shard_ka_problems(int32_t n_problems, const int64_t* weight, int world, int32_t* rank_of_problem) {
+  if (world < 1 || n_problems < 0 || (n_problems > 0 && (!weight || !rank_of_problem)))
+    return fail(PXR_ERR_INVALID_ARGUMENT, "bad shard arguments");
+  // longest-processing-time-first: heaviest problem to the least loaded rank; ties by lower index / lower rank,
+  // so every rank computes the same plan
+  std::vector<int32_t> order(n_problems);
+  for (int32_t i = 0; i < n_problems; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return weight[a] > weight[b]; });
+  std::vector<int64_t> load(world, 0);
+  for (int32_t i : order) {
+    int best = 0;
+    for (int r = 1; r < world; ++r) if (load[r] < load[best]) best = r;
+    rank_of_problem[i] = best;
+    load[best] += std::max<int64_t>(weight[i], 0);
+  }
+  return PXR_OK;
+}
+
 }  // extern "C"

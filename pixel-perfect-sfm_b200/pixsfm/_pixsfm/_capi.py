@@ -461,3 +461,48 @@ class KAProblem:
         o = _copy.copy(self)
         o.keypoints = self.keypoints.copy()
         return o
+
+    # ---- multi-GPU: whole problems per rank (SURVEY §8e "KA: no collective")
+    def problem_weights(self):
+        """patch bytes a problem pulls in = distinct keypoints of its edges x bytes of one patch"""
+        per_patch = int(np.prod(self._shape[1:])) * self._dtype.itemsize
+        w = np.zeros(self.n_problems, np.int64)
+        stride = len(self.keypoints) + 1
+        ends = (self.edge_src,) if self.ref_desc is not None else (self.edge_src, self.edge_dst)
+        key = np.unique(np.concatenate([self.edge_problem.astype(np.int64) * stride + e for e in ends]))
+        np.add.at(w, key // stride, 1)
+        return w * per_patch
+
+    def shard(self, rank_of_problem, rank):
+        """-> (KAProblem of the problems `rank` owns, global index of each of its keypoints).  Keypoints, patches and
+        metadata are compacted to what the shard touches; solve it like any problem and hand both to merge_shard."""
+        rank_of_problem = np.asarray(rank_of_problem)
+        if len(rank_of_problem) != self.n_problems:
+            raise ValueError("rank_of_problem must have one entry per problem")
+        mine = rank_of_problem[self.edge_problem] == rank
+        es, ed = self.edge_src[mine], self.edge_dst[mine]
+        used = np.unique(es if self.ref_desc is not None else np.concatenate([es, ed]))
+        local = np.full(len(self.keypoints), -1, np.int64); local[used] = np.arange(len(used))
+        plocal = np.cumsum(rank_of_problem == rank) - 1                      # relabel the owned problems 0..m-1
+        kp_patch = self.kp_patch[used] if self.kp_patch is not None and len(self.kp_patch) else used
+        if self.patch_blocks is not None:
+            starts = np.concatenate([[0], np.cumsum(self._block_counts)])
+            blk = np.searchsorted(starts, kp_patch, side="right") - 1
+            patches = np.empty((len(used),) + self._shape[1:], self._dtype)
+            for k, (b, g) in enumerate(zip(blk, kp_patch)):
+                patches[k] = np.asarray(self.patch_blocks[b][g - starts[b]])
+        else:
+            patches = np.ascontiguousarray(self.patches[kp_patch])
+        if len(used) == 0:
+            patches = np.zeros((0,) + self._shape[1:], self._dtype)
+        sub = KAProblem(keypoints=self.keypoints[used], kp_const=self.kp_const[used], edge_src=local[es],
+                        edge_dst=ed if self.ref_desc is not None else local[ed], edge_weight=None if self.edge_weight is None else self.edge_weight[mine],
+                        edge_problem=plocal[self.edge_problem[mine]], n_problems=int(np.sum(rank_of_problem == rank)),
+                        patches=patches, corner=self.corner[kp_patch], scale=self.scale[kp_patch], kp_patch=None,
+                        bound=self.bound, patches_are_sparse=self.patches_are_sparse,
+                        upsampling_factor=self.upsampling_factor, ref_desc=self.ref_desc)
+        return sub, used
+
+    def merge_shard(self, sub, kp_global):
+        """write a solved shard's keypoints back"""
+        self.keypoints[kp_global] = sub.keypoints

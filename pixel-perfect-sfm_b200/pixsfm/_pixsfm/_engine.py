@@ -199,3 +199,12 @@ def ka_problem_labels(track_labels, max_per_problem=50):
     out = np.zeros(len(tl), np.int32); nb = C.c_int32()
     _capi.check(lib.pxr_ka_problem_labels(C.c_int64(len(tl)), _p(tl), int(max_per_problem), _p(out), C.byref(nb)))
     return out, nb.value
+
+
+def ka_shard_plan(problem_weight, world):
+    """pxr_shard_ka_problems: rank of every packed KA problem (whole problems per rank, no collective needed)"""
+    lib = _capi.load_lib()
+    w = np.ascontiguousarray(problem_weight, np.int64)
+    out = np.zeros(len(w), np.int32)
+    _capi.check(lib.pxr_shard_ka_problems(C.c_int32(len(w)), _p(w), int(world), _p(out)))
+    return out

@@ -62,3 +62,55 @@ def test_sharded_normal_equations_sum_to_the_single_process_ones():
     assert all(ok for _, ok, _ in res), res
     counts = [n for _, _, n in sorted(res)]
     assert sum(counts) == 41 * 3 and abs(counts[0] - counts[1]) <= 6
+
+
+def test_ka_problems_shard_without_a_collective():
+    """KA shards by whole problems: the plan is a balanced partition, and solving the shards
+    independently (here with the oracle as the solver) reproduces the unsharded solve exactly."""
+    import oracle_lib as O
+    from pixsfm._pixsfm import _capi, _engine
+    from ka_util import make_ka_problem, make_query_ka_problem
+    prob, _, _ = make_ka_problem(n_images=6, n_tracks=60, track_len=4, channels=16, seed=2, max_per_problem=12)
+    ic = _capi.default_interp()
+    so = _capi.default_ka_options()
+    w = prob.problem_weights()
+    assert len(w) == prob.n_problems and w.min() > 0
+    per_patch = 16 * 16 * 16 * 2
+    kp0 = np.unique(np.concatenate([prob.edge_src[prob.edge_problem == 0], prob.edge_dst[prob.edge_problem == 0]]))
+    assert w[0] == len(kp0) * per_patch
+    full = prob.copy()
+    O.ka_solve(full, ic, so)
+    for world in (1, 2, 3):
+        plan = _engine.ka_shard_plan(w, world)
+        assert plan.min() >= 0 and plan.max() < world
+        loads = np.array([w[plan == r].sum() for r in range(world)])
+        assert loads.sum() == w.sum() and loads.max() - loads.min() <= w.max()       # LPT bound
+        assert np.array_equal(plan, _engine.ka_shard_plan(w, world))                 # deterministic
+        merged = prob.copy()
+        seen = np.zeros(len(prob.keypoints), int)
+        n_edges = 0
+        for r in range(world):
+            sub, kp_global = merged.shard(plan, r)
+            assert sub.n_problems == int(np.sum(plan == r))
+            assert np.array_equal(sub.patches, prob.patches[kp_global])
+            seen[kp_global] += 1
+            n_edges += len(sub.edge_src)
+            O.ka_solve(sub, ic, so)
+            merged.merge_shard(sub, kp_global)
+        assert n_edges == len(prob.edge_src) and seen.max() == 1     # problems share no keypoint
+        assert np.array_equal(merged.keypoints, full.keypoints)
+    # heaviest-first: a single dominating problem sits alone
+    plan = _engine.ka_shard_plan(np.array([1, 1, 10, 1, 1], np.int64), 2)
+    assert list(plan) == [1, 1, 0, 1, 1]
+    assert list(_engine.ka_shard_plan(np.zeros(0, np.int64), 4)) == []
+    # query mode shards the same way (edge_dst indexes the fixed descriptors, which every rank keeps)
+    q, _ = make_query_ka_problem(n_images=4, n_tracks=20, track_len=3, channels=16, seed=3)[:2]
+    qfull = q.copy()
+    O.ka_solve(qfull, ic, so)
+    qplan = _engine.ka_shard_plan(q.problem_weights(), 2)
+    qm = q.copy()
+    for r in range(2):
+        sub, kg = qm.shard(qplan, r)
+        O.ka_solve(sub, ic, so)
+        qm.merge_shard(sub, kg)
+    assert np.array_equal(qm.keypoints, qfull.keypoints)
