@@ -1,7 +1,8 @@
 """2+ GPU consistency check of the point-sharded BA (run under torchrun on a multi-GPU box):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 scripts/check_multi_gpu.py
 Every rank solves its shard of ONE seeded problem through pxr_ba_run with the NCCL communicator attached; rank 0
-compares the result with the single-process oracle solution of the whole problem (test infrastructure, like tests/)."""
+compares the result with the single-process oracle solution of the whole problem (test infrastructure, like tests/).
+The last check shards a keypoint adjustment by whole problems (pxr_shard_ka_problems) and compares the same way."""
 import ctypes as C
 import os
 import sys
@@ -67,6 +68,29 @@ def main():
             print("inner=%d solver=%d sparse=%d world=%d: ranks identical=%s  |dq|=%.2e |dt|=%.2e |dX|=%.2e  dcost=%.2e  iters %d/%d  -> %s"
                   % (inner, solver, sparse, world, same, dq, dt, dx, dc, s["num_iterations"], sr["num_iterations"], "OK" if ok else "MISMATCH"), flush=True)
             ok_all = ok_all and ok
+    # ---- keypoint adjustment: whole problems per rank, no collective on the data path; the gather below is only
+    # how this check brings the shards' results together
+    os.environ.pop("PXR_PCG_SPARSE", None)
+    from ka_util import make_ka_problem
+    kprob = make_ka_problem(n_images=6, n_tracks=80, track_len=4, channels=128, seed=5, max_per_problem=12)[0]
+    kso = _capi.default_ka_options()
+    plan = _engine.ka_shard_plan(kprob.problem_weights(), world)
+    sub, kp_global = kprob.shard(plan, rank)
+    _engine.ka_run(sub, ic, kso, ctx=ctx)
+    mine = torch.zeros(len(kprob.keypoints), 2, dtype=torch.float64, device="cuda")
+    mine[torch.from_numpy(kp_global).cuda()] = torch.from_numpy(sub.keypoints).cuda()
+    dist.all_reduce(mine)       # every keypoint belongs to exactly one shard, the others contribute zeros
+    if rank == 0:
+        kfull = kprob.copy()
+        O.ka_solve(kfull, ic, kso)
+        touched = np.zeros(len(kprob.keypoints), bool)
+        for r in range(world):
+            touched[kprob.shard(plan, r)[1]] = True
+        dk = np.abs(mine.cpu().numpy() - kfull.keypoints)[touched].max()
+        ok = dk < 1e-5
+        print("KA sharded over %d ranks (%d problems): |dkp| vs single-process oracle = %.2e -> %s"
+              % (world, kprob.n_problems, dk, "OK" if ok else "MISMATCH"), flush=True)
+        ok_all = ok_all and ok
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
