@@ -481,7 +481,12 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp16 taps, fp32 horizontal, fp64 vertical/solve)",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cb, "stage_ms": stage_ms,
-                "lm": {"successful_steps": int(sum(i["step_is_successful"] for i in its)), "steps": steps_done,
+                "lm": {"inner_iterations_in_timed_steps": "inner iterations" in stage_ms,
+                       "inner_iterations_note": "Ceres rule (inner_iteration_tolerance): the solver itself stops running inner "
+                                                "iterations once their relative decrease is below tolerance - on this trajectory "
+                                                "after LM iteration 2, i.e. during warm-up; e2e and the reference arm both solve "
+                                                "from iteration 0 and include them",
+                       "successful_steps": int(sum(i["step_is_successful"] for i in its)), "steps": steps_done,
                        "cost_first": its[0]["cost"] if its else None, "cost_last": its[-1]["cost"] if its else None,
                        "wall_ms_per_step": 1e3 * wall / max(1, steps_done)},
                 "setup_seconds": setup_s}

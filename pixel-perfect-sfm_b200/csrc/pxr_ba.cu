@@ -123,6 +123,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   if (interp.check_bounds) return fail(PXR_ERR_UNSUPPORTED, "check_bounds=true is not supported on this path");
   env.pcg_sparse = getenv("PXR_PCG_SPARSE") != nullptr; env.build_atomic = getenv("PXR_BUILD_ATOMIC") != nullptr;
   env.chol_multikernel = getenv("PXR_CHOL_MULTIKERNEL") != nullptr; env.chol_test_abort = getenv("PXR_CHOL_TEST_ABORT") != nullptr;
+  env.build_staged = getenv("PXR_BUILD_STAGED") != nullptr;
   env.cg_multi = getenv("PXR_CG_MULTI") != nullptr; env.no_speculation = getenv("PXR_NO_SPECULATION") != nullptr;
   if (const char* t = getenv("PXR_CHOL_TRACE")) env.chol_trace = t;
   PXR_CUDA(cudaSetDevice(ctx->device));
@@ -479,8 +480,12 @@ int BA::build() {
   if (sparse_schur && !chunked && n_obs > 0) return fail(PXR_ERR_INTERNAL, "block-sparse path without per-image chunks");
   if (sparse_schur) PXR_TRY(ss_Himg.zero(ctx->stream));
   if (n_obs > 0) {
-    if (img_src8.p) PXR_LAUNCH(ctx, ba_build_kernel<true>, (unsigned)cdiv(n_obs, 128), 128, 0, dev(), chunked ? 0 : 1);
-    else PXR_LAUNCH(ctx, ba_build_kernel<false>, (unsigned)cdiv(n_obs, 128), 128, 0, dev(), chunked ? 0 : 1);
+    const BADev dv = dev();
+    const size_t staged_smem = (size_t)128 * ((std::max(dv.juv_stride, dv.dcmax * 3) | 1) + 9) * sizeof(double);
+    if (img_src8.p && chunked && env.build_staged && staged_smem <= 48 * 1024)
+      PXR_LAUNCH(ctx, ba_build_staged_kernel, (unsigned)cdiv(n_obs, 128), 128, staged_smem, dv);
+    else if (img_src8.p) PXR_LAUNCH(ctx, ba_build_kernel<true>, (unsigned)cdiv(n_obs, 128), 128, 0, dv, chunked ? 0 : 1);
+    else PXR_LAUNCH(ctx, ba_build_kernel<false>, (unsigned)cdiv(n_obs, 128), 128, 0, dv, chunked ? 0 : 1);
   }
   if (n_obs > 0 && chunked)
     PXR_LAUNCH(ctx, ba_build_cam_kernel, (unsigned)cdiv(io_n_chunks * 32, 256), 256, 0, dev(), io_obs.p, io_chunk_begin.p, io_n_chunks,

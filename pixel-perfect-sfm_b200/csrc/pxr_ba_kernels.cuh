@@ -135,6 +135,120 @@ static __global__ void __launch_bounds__(128) ba_build_kernel(BADev d, int cam_b
   }
 }
 
+// K2s: ba_build_kernel<true> without the camera part, with the per-observation records moved through shared memory.
+// ncu on K2 (profiles/schur_build_r01_final.md): issue-active 4 %, stalls long_scoreboard + lg_throttle — every
+// thread walks its own 176 B `juv` record and 192 B `W` row (32 different lines per warp instruction) and ten
+// neighbouring threads hit the same Hpp/gp words with atomics.  Here a CTA of 128 observations
+//   * copies the `juv` / `obs_out` records of its observations with coalesced 8 B-per-lane loads into shared memory
+//     (rows padded to an odd number of doubles: conflict-free per-thread access),
+//   * reduces Hpp / gp over the observations of a point with a segmented warp scan (observations are sorted by
+//     point): one atomic per element per (point, warp) instead of one per observation,
+//   * stages the W rows in the same shared memory and writes them back coalesced (entries beyond an observation's
+//     column count, which nothing reads, are written as zeros).
+// Dynamic shared memory: 128 * (max(juv_stride, 3*dcmax) | 1  +  9) doubles.
+static __global__ void __launch_bounds__(128) ba_build_staged_kernel(BADev d) {
+  extern __shared__ double sm_build[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t o0 = (int64_t)blockIdx.x * 128;
+  const int n = (int)min((int64_t)128, d.n_obs - o0);
+  const int js = d.juv_stride, wrow = d.dcmax * 3;
+  const int SP = max(js, wrow) | 1;                  // padded row (doubles), shared by the J and the W staging
+  double* sJ = sm_build;                             // [128][SP]
+  double* sO = sm_build + (size_t)128 * SP;          // [128][9]
+  {
+    const double* src = d.juv + o0 * (int64_t)js;
+    int r = tid / js, c = tid - r * js;
+    const int dr = 128 / js, dcol = 128 - dr * js;
+    for (int i = tid; i < n * js; i += 128) {
+      sJ[r * SP + c] = __ldg(src + i);
+      r += dr; c += dcol;
+      if (c >= js) { c -= js; ++r; }
+    }
+    const double* so = d.obs_out + o0 * 8;
+    for (int i = tid; i < n * 8; i += 128) sO[(i >> 3) * 9 + (i & 7)] = __ldg(so + i);
+  }
+  __syncthreads();
+  const bool live = tid < n;
+  const int64_t o = o0 + tid;
+  const int64_t p = live ? d.obs_pt[o] : -1;
+  const bool pvar = live && d.point_off[p] >= 0;
+  const int Wd = 9 + d.K;
+  int cols[8];
+  double Ju[8], Jv[8];
+  int dc = 0;
+  double v[12];                                      // gp (3) | Hpp (9)
+#pragma unroll
+  for (int k = 0; k < 12; ++k) v[k] = 0.0;
+  double apu[3] = {0, 0, 0}, apv[3] = {0, 0, 0};
+  if (live) {
+    const double* oo = sO + tid * 9;
+    double rho[3];
+    loss_eval(d.loss, 1.0, oo[0], rho);
+    const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
+    const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
+    const double* J = sJ + tid * SP;
+    dc = obs_local_columns8(d, o, J, Wd, cols, Ju, Jv);
+    const double pu[3] = {J[6], J[7], J[8]}, pv[3] = {J[Wd + 6], J[Wd + 7], J[Wd + 8]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { apu[k] = auu * pu[k] + auv * pv[k]; apv[k] = auv * pu[k] + avv * pv[k]; }
+    if (pvar) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        v[a] = pu[a] * bu + pv[a] * bv;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) v[3 + a * 3 + b] = pu[a] * apu[b] + pv[a] * apv[b];
+      }
+    }
+    d.Wdc[o] = dc;
+    int32_t* Wc = d.Wcols + o * (int64_t)d.dcmax;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) if (a < dc) Wc[a] = cols[a];
+  }
+  // segmented inclusive scan over the lanes of one point (contiguous), then the last lane of a segment adds once
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int64_t pq = __shfl_up_sync(0xffffffffu, p, off);
+    const bool take = lane >= off && pq == p;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const double w = __shfl_up_sync(0xffffffffu, v[k], off);
+      if (take) v[k] += w;
+    }
+  }
+  const int64_t pnext = __shfl_down_sync(0xffffffffu, p, 1);
+  if (pvar && (lane == 31 || pnext != p)) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomic_add_f64(&d.gp[p * 3 + a], v[a]);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) atomic_add_f64(&d.Hpp[p * 9 + k], v[3 + k]);
+  }
+  __syncthreads();                                   // every thread has its J values in registers: reuse sJ for W
+  if (live) {
+    double* Ws = sJ + tid * SP;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      if (a * 3 + 2 < wrow) {
+        const bool on = pvar && a < dc;
+        Ws[a * 3 + 0] = on ? Ju[a] * apu[0] + Jv[a] * apv[0] : 0.0;
+        Ws[a * 3 + 1] = on ? Ju[a] * apu[1] + Jv[a] * apv[1] : 0.0;
+        Ws[a * 3 + 2] = on ? Ju[a] * apu[2] + Jv[a] * apv[2] : 0.0;
+      }
+    }
+    for (int k = 24; k < wrow; ++k) Ws[k] = 0.0;     // dcmax > 8 cannot reach this kernel with dc > 8; keep rows defined
+  }
+  __syncthreads();
+  {
+    double* dst = d.W + o0 * (int64_t)wrow;
+    int r = tid / wrow, c = tid - r * wrow;
+    const int dr = 128 / wrow, dcol = 128 - dr * wrow;
+    for (int i = tid; i < n * wrow; i += 128) {
+      dst[i] = sJ[r * SP + c];
+      r += dr; c += dcol;
+      if (c >= wrow) { c -= wrow; ++r; }
+    }
+  }
+}
+
 // K2c: camera blocks without per-observation atomics.  Observations are listed per image in chunks of
 // <= 128 (all observations of an image share their parameter columns); one warp per chunk accumulates
 // J_c^T A' J_c (lower triangle, 36 values for dc <= 8) and J_c^T b' (8) in registers, reduces them across
