@@ -123,7 +123,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   if (interp.check_bounds) return fail(PXR_ERR_UNSUPPORTED, "check_bounds=true is not supported on this path");
   env.pcg_sparse = getenv("PXR_PCG_SPARSE") != nullptr; env.build_atomic = getenv("PXR_BUILD_ATOMIC") != nullptr;
   env.chol_multikernel = getenv("PXR_CHOL_MULTIKERNEL") != nullptr; env.chol_test_abort = getenv("PXR_CHOL_TEST_ABORT") != nullptr;
-  env.build_staged = getenv("PXR_BUILD_STAGED") != nullptr;
+  env.build_staged = getenv("PXR_BUILD_UNSTAGED") == nullptr;
   env.cg_multi = getenv("PXR_CG_MULTI") != nullptr; env.no_speculation = getenv("PXR_NO_SPECULATION") != nullptr;
   if (const char* t = getenv("PXR_CHOL_TRACE")) env.chol_trace = t;
   PXR_CUDA(cudaSetDevice(ctx->device));
