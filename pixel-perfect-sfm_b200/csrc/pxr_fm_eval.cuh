@@ -35,11 +35,9 @@ struct ProjectArgs {
   int juv_k;     // K columns stored per row
 };
 
+// one observation: uv (and xy) to global memory, the 2 x (9 + K) record d(uv)/d(theta) to `out` (global or shared)
 template <bool JAC>
-__global__ void __launch_bounds__(128) ba_project_kernel(ProjectArgs a) {
-  const int64_t k = a.obs_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.obs_end) return;
-  const int64_t o = a.item_index ? a.item_index[k] : k;
+__device__ __forceinline__ void project_observation(const ProjectArgs& a, int64_t o, double* out) {
   const int img = a.obs_img[o];
   const int64_t pt = a.obs_pt[o];
   const int64_t pi = a.obs_patch ? a.obs_patch[o] : o;
@@ -59,8 +57,7 @@ __global__ void __launch_bounds__(128) ba_project_kernel(ProjectArgs a) {
   a.uv[2 * o] = (xy[0] * sx - 0.5 - cx) * a.ups;
   a.uv[2 * o + 1] = (xy[1] * sy - 0.5 - cy) * a.ups;
   if (a.xy) { a.xy[2 * o] = xy[0]; a.xy[2 * o + 1] = xy[1]; }
-  if (JAC && a.juv) {
-    double* out = a.juv + o * (int64_t)a.juv_stride;
+  if (JAC && out) {
     const int W = 9 + a.juv_k;
     const double s[2] = {sx * a.ups, sy * a.ups};
 #pragma unroll
@@ -71,6 +68,35 @@ __global__ void __launch_bounds__(128) ba_project_kernel(ProjectArgs a) {
       for (int k = 0; k < 3; ++k) out[r * W + 6 + k] = s[r] * Jpt[r][k];
       for (int k = 0; k < a.juv_k; ++k) out[r * W + 9 + k] = s[r] * Jk[r][k];
     }
+  }
+}
+
+template <bool JAC>
+__global__ void __launch_bounds__(128) ba_project_kernel(ProjectArgs a) {
+  const int64_t k = a.obs_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.obs_end) return;
+  const int64_t o = a.item_index ? a.item_index[k] : k;
+  project_observation<JAC>(a, o, (JAC && a.juv) ? a.juv + o * (int64_t)a.juv_stride : nullptr);
+}
+
+// Full-pass variant (no item list): the 128 records of a CTA are contiguous in `juv`, so they are assembled in shared
+// memory (rows padded to an odd number of doubles) and written out with coalesced stores instead of 22 strided
+// 8 B stores per thread.  Dynamic shared memory: 128 * (juv_stride | 1) doubles.
+static __global__ void __launch_bounds__(128) ba_project_staged_kernel(ProjectArgs a) {
+  extern __shared__ double sm_proj[];
+  const int tid = threadIdx.x;
+  const int64_t o0 = a.obs_begin + (int64_t)blockIdx.x * 128;
+  const int n = (int)min((int64_t)128, a.obs_end - o0);
+  const int js = a.juv_stride, SP = js | 1;
+  if (tid < n) project_observation<true>(a, o0 + tid, sm_proj + tid * SP);
+  __syncthreads();
+  double* dst = a.juv + o0 * (int64_t)js;
+  int r = tid / js, c = tid - r * js;
+  const int dr = 128 / js, dcol = 128 - dr * js;
+  for (int i = tid; i < n * js; i += 128) {
+    dst[i] = sm_proj[r * SP + c];
+    r += dr; c += dcol;
+    if (c >= js) { c -= js; ++r; }
   }
 }
 
