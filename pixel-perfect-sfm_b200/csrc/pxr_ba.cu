@@ -124,7 +124,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   env.pcg_sparse = getenv("PXR_PCG_SPARSE") != nullptr; env.build_atomic = getenv("PXR_BUILD_ATOMIC") != nullptr;
   env.chol_multikernel = getenv("PXR_CHOL_MULTIKERNEL") != nullptr; env.chol_test_abort = getenv("PXR_CHOL_TEST_ABORT") != nullptr;
   env.build_staged = getenv("PXR_BUILD_UNSTAGED") == nullptr;
-  env.project_staged = getenv("PXR_PROJECT_STAGED") != nullptr; env.model_cost_staged = getenv("PXR_MODEL_COST_STAGED") != nullptr;
+  env.project_staged = getenv("PXR_PROJECT_UNSTAGED") == nullptr;
   env.cg_multi = getenv("PXR_CG_MULTI") != nullptr; env.no_speculation = getenv("PXR_NO_SPECULATION") != nullptr;
   if (const char* t = getenv("PXR_CHOL_TRACE")) env.chol_trace = t;
   PXR_CUDA(cudaSetDevice(ctx->device));
@@ -635,10 +635,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
   if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p);
   if (n_obs > 0) {
-    const size_t mc_smem = (size_t)128 * ((juv_stride | 1) + 9) * sizeof(double);
-    if (img_src8.p && env.model_cost_staged && mc_smem <= 48 * 1024)
-      PXR_LAUNCH(ctx, ba_model_cost_staged_kernel, (unsigned)cdiv(n_obs, 128), 128, mc_smem, d, delta.p, scalars.p + 4);
-    else if (img_src8.p) PXR_LAUNCH(ctx, ba_model_cost_kernel<true>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
+    if (img_src8.p) PXR_LAUNCH(ctx, ba_model_cost_kernel<true>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
     else PXR_LAUNCH(ctx, ba_model_cost_kernel<false>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
   }
   PXR_CUDA(cudaGetLastError());

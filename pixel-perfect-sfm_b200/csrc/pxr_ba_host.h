@@ -92,7 +92,7 @@ struct BA {
   // implicit block-sparse reduced system (pxr_sparse_schur.cuh): no nc x nc array is ever allocated
   // debugging / A-B switches, read from the environment once in create()
   struct EnvFlags { bool pcg_sparse = false, build_atomic = false, chol_multikernel = false, chol_test_abort = false,
-                         cg_multi = false, no_speculation = false, build_staged = true, project_staged = false, model_cost_staged = false; std::string chol_trace; } env;
+                         cg_multi = false, no_speculation = false, build_staged = true, project_staged = true; std::string chol_trace; } env;
   bool sparse_schur = false;
   int ss_n_keys = 0;
   std::vector<int32_t> h_img_cols, h_img_pd, h_img_pose_blk, h_img_cam_blk, h_img_cam;
