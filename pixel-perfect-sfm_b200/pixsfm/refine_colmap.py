@@ -1,0 +1,126 @@
+"""pixsfm.refine_colmap — the `PixSfM` driver around the two adjusters (reference pixsfm/refine_colmap.py:23-145):
+COLMAP database -> keypoint adjustment -> database, COLMAP model -> bundle adjustment -> model.
+
+What differs from the reference, and why:
+  * dense feature extraction (the S2DNet CNN, `features/extractor.py`) is not part of this package: pass an `extractor`
+    object with the reference's interface (`extract.features_from_graph` / `features_from_reconstruction` are called
+    on it) or hand the adjusters a ready `feature_manager`.  Without either the call raises — nothing is faked.
+  * models are read and written by `util.colmap_model_io` (pycolmap is not installable offline); pycolmap
+    reconstructions passed in by the caller work as well (duck typing, `util/colmap_types.py`).
+  * configuration: dicts (or a YAML path) merged over the reference's defaults; `${..interpolation}` of the reference's
+    YAML files is resolved here by handing the top-level `interpolation` block to KA and BA unless they set their own.
+  * `triangulation` / `reconstruction` (refine_hloc.py) shell out to COLMAP through pycolmap/hloc and are not provided."""
+import shutil
+from copy import deepcopy
+from pathlib import Path
+
+from . import logger
+from .base import interpolation_default_conf
+from .bundle_adjustment import BundleAdjuster
+from .keypoint_adjustment import KeypointAdjuster, build_matching_graph
+from .util.colmap import read_keypoints_from_db, read_matches_from_db, write_keypoints_to_db
+from .util.colmap_types import Reconstruction
+from .util.conf import merge, to_conf
+
+
+def _load_conf(conf):
+    if conf is None:
+        return {}
+    if isinstance(conf, (str, Path)):
+        import yaml
+        with open(conf) as f:
+            conf = yaml.safe_load(f) or {}
+    if not isinstance(conf, dict):
+        raise TypeError("conf must be a dict or the path of a YAML file")
+    return conf
+
+
+def _strip_interpolations(node, interpolation):
+    """OmegaConf-style references to the shared interpolation block -> the block itself"""
+    if isinstance(node, dict):
+        return {k: (deepcopy(interpolation) if isinstance(v, str) and v.startswith("${") and v.endswith("interpolation}")
+                    else _strip_interpolations(v, interpolation)) for k, v in node.items()}
+    return node
+
+
+class PixSfM:
+    default_conf = {
+        "interpolation": interpolation_default_conf,
+        "KA": {**KeypointAdjuster.default_conf},
+        "BA": {**BundleAdjuster.default_conf},
+    }
+
+    def __init__(self, conf=None, extractor=None):
+        conf = _load_conf(conf)
+        top = conf
+        conf = dict(conf.get("mapping", conf))
+        if isinstance(conf.get("interpolation"), str):      # "${interpolation}": the file's top-level block
+            conf["interpolation"] = top.get("interpolation") if isinstance(top.get("interpolation"), dict) else None
+            if conf["interpolation"] is None:
+                del conf["interpolation"]
+        if "dense_features" not in conf and "dense_features" in top:
+            conf["dense_features"] = top["dense_features"]
+        unknown = set(conf) - {"interpolation", "KA", "BA", "dense_features"}
+        if unknown:
+            raise ValueError("unknown configuration keys: %s" % sorted(unknown))
+        interpolation = merge(self.default_conf["interpolation"], conf.get("interpolation")
+                              if isinstance(conf.get("interpolation"), dict) else None)
+        conf = _strip_interpolations(conf, interpolation)
+        self.conf = merge(self.default_conf, {k: v for k, v in conf.items() if k != "dense_features"})
+        self.conf["dense_features"] = to_conf(conf.get("dense_features", {}))
+        for part in ("KA", "BA"):       # "${..interpolation}": the shared block unless the adjuster has its own
+            if "interpolation" not in conf.get(part, {}):
+                self.conf[part]["interpolation"] = to_conf(deepcopy(interpolation))
+        self.extractor = extractor
+        self.keypoint_adjuster = KeypointAdjuster.create(self.conf.KA)
+        self.bundle_adjuster = BundleAdjuster.create(self.conf.BA)
+
+    # ---------------------------------------------------------------------------------------- features
+    def _features(self, how, *args, cache_path=None):
+        if self.extractor is None:
+            raise ValueError("no feature_manager given and no extractor configured: dense feature extraction (the CNN) "
+                             "is outside this package — pass feature_manager= or PixSfM(conf, extractor=...)")
+        return getattr(self.extractor, how)(*args, cache_path=cache_path)
+
+    # ---------------------------------------------------------------------------------------- KA
+    def run_ka(self, keypoints, image_dir, pairs, matches_scores, cache_path=None, feature_manager=None):
+        graph = build_matching_graph(pairs, *matches_scores)
+        if feature_manager is None:
+            feature_manager = self._features("features_from_graph", image_dir, graph, keypoints, cache_path=cache_path)
+        ka_data = self.keypoint_adjuster.refine_multilevel(keypoints, feature_manager, graph)
+        return keypoints, ka_data, feature_manager
+
+    def refine_keypoints_from_db(self, output_path, database_path, image_dir=None, cache_path=None, feature_manager=None):
+        output_path, database_path = Path(output_path), Path(database_path)
+        keypoints = read_keypoints_from_db(database_path)
+        pairs, matches, scores = read_matches_from_db(database_path)
+        keypoints, ka_data, feature_manager = self.run_ka(keypoints, image_dir, pairs, (matches, scores), cache_path,
+                                                          feature_manager)
+        if database_path != output_path:
+            shutil.copy(database_path, output_path)
+        write_keypoints_to_db(output_path, keypoints)
+        return keypoints, ka_data, feature_manager
+
+    # ---------------------------------------------------------------------------------------- BA
+    def run_ba(self, reconstruction, image_dir=None, cache_path=None, feature_manager=None):
+        if feature_manager is None:
+            feature_manager = self._features("features_from_reconstruction", reconstruction, image_dir, cache_path=cache_path)
+        ba_data = self.bundle_adjuster.refine_multilevel(reconstruction, feature_manager)
+        return reconstruction, ba_data, feature_manager
+
+    def refine_reconstruction(self, output_path, input_path, image_dir=None, cache_path=None, feature_manager=None):
+        reconstruction = Reconstruction.read(input_path)
+        logger.info("Loaded a model with %d images, %d points, %d observations.", len(reconstruction.images),
+                    len(reconstruction.points3D), reconstruction.num_observations())
+        reconstruction, ba_data, feature_manager = self.run_ba(reconstruction, image_dir, cache_path=cache_path,
+                                                               feature_manager=feature_manager)
+        Path(output_path).mkdir(exist_ok=True, parents=True)
+        reconstruction.write(str(output_path))
+        return reconstruction, ba_data, feature_manager
+
+    def triangulation(self, *args, **kwargs):
+        raise NotImplementedError("COLMAP triangulation runs through pycolmap/hloc (refine_hloc.py:117-131), which this "
+                                  "package does not wrap; refine keypoints with refine_keypoints_from_db, run COLMAP, "
+                                  "then refine_reconstruction")
+
+    reconstruction = triangulation

@@ -88,3 +88,17 @@ class Reconstruction:
 
     def num_observations(self):
         return sum(p.track.length() for p in self.points3D.values())
+
+    # pycolmap.Reconstruction(path) / .write(path) / .write_text(path) (refine_colmap.py:117-131)
+    @classmethod
+    def read(cls, path):
+        from .colmap_model_io import read_model
+        return read_model(path)
+
+    def write(self, path):
+        from .colmap_model_io import write_model
+        write_model(self, path, ".bin")
+
+    def write_text(self, path):
+        from .colmap_model_io import write_model
+        write_model(self, path, ".txt")

@@ -234,3 +234,44 @@ def test_keypoint_adjustment_from_a_colmap_database(tmp_path):
     back = cio.read_keypoints_from_db(path)
     for k in keypoints:
         assert np.array_equal(back[k], keypoints[k].astype(np.float32).astype(np.float64))
+    # the same through the PixSfM driver, into a second database (refine_colmap.py:99-115)
+    from pixsfm.refine_colmap import PixSfM
+    db = COLMAPDatabase.connect(path)
+    db.execute("DELETE FROM keypoints")
+    for i in range(6):
+        db.add_keypoints(ids[i], sc["keypoints"][sc["node_image"] == i])
+    db.commit(); db.close()
+    out_db = tmp_path / "refined.db"
+    kp2, ka_data, _ = PixSfM({"KA": {"max_kps_per_problem": 20}}).refine_keypoints_from_db(out_db, path, feature_manager=fm)
+    assert ka_data["summary"][0].final_cost < 0.5 * ka_data["summary"][0].initial_cost
+    refined = cio.read_keypoints_from_db(out_db)
+    untouched = cio.read_keypoints_from_db(path)
+    for k in kp2:
+        assert np.abs(kp2[k] - keypoints[k]).max() < 1e-9                   # same solve as the direct call above
+        assert np.array_equal(refined[k], kp2[k].astype(np.float32).astype(np.float64))
+        assert np.array_equal(untouched[k], before[k])                      # the input database is left alone
+    assert cio.read_matches_from_db(out_db)[0] == pairs
+
+
+def test_pixsfm_refines_a_colmap_model_directory(tmp_path):
+    """PixSfM.refine_reconstruction (refine_colmap.py:117-131): model files -> BA on the GPU -> model files, equal to
+    running the adjuster on the in-memory reconstruction."""
+    from pixsfm.refine_colmap import PixSfM
+    from pixsfm.util.colmap_types import Reconstruction
+    rec, fm, _, gt = make_reconstruction(n_cams=6, n_points=60, track_len=4, channels=128, seed=23)
+    rec.write(str(tmp_path / "in"))
+    conf = {"BA": {"optimizer": {"solver": {"max_num_iterations": 8}}}}
+    sfm = PixSfM(conf)
+    out_rec, ba_data, fm_out = sfm.refine_reconstruction(tmp_path / "out", tmp_path / "in", feature_manager=fm)
+    assert fm_out is fm and ba_data["summary"][0].final_cost < ba_data["summary"][0].initial_cost
+    direct = copy.deepcopy(rec)
+    ba_pkg.BundleAdjuster.create(conf["BA"]).refine_multilevel(direct, fm)
+    back = Reconstruction.read(tmp_path / "out")
+    for iid in rec.images:
+        assert np.array_equal(back.images[iid].qvec, out_rec.images[iid].qvec)          # what was written is what was solved
+        assert np.abs(back.images[iid].qvec - direct.images[iid].qvec).max() < 1e-9     # and equals the direct call
+        assert np.abs(back.images[iid].tvec - direct.images[iid].tvec).max() < 1e-9
+    for pid in rec.points3D:
+        assert np.abs(back.points3D[pid].xyz - direct.points3D[pid].xyz).max() < 1e-9
+    moved = max(np.abs(back.points3D[p].xyz - rec.points3D[p].xyz).max() for p in rec.points3D)
+    assert moved > 1e-6
