@@ -483,9 +483,11 @@ def main():
                 "roofline": roofline, "cpu_baseline": cb, "stage_ms": stage_ms,
                 "lm": {"inner_iterations_in_timed_steps": "inner iterations" in stage_ms,
                        "inner_iterations_note": "Ceres rule (inner_iteration_tolerance): the solver itself stops running inner "
-                                                "iterations once their relative decrease is below tolerance - on this trajectory "
-                                                "after LM iteration 2, i.e. during warm-up; e2e and the reference arm both solve "
-                                                "from iteration 0 and include them",
+                                                "iterations once their relative decrease is below tolerance (on the default "
+                                                "trajectory after LM iteration 2); %s. e2e and the reference arm both solve "
+                                                "from iteration 0 and include them"
+                                                % ("some of the timed steps still ran them" if "inner iterations" in stage_ms
+                                                   else "they ended during warm-up, none ran in the timed steps"),
                        "successful_steps": int(sum(i["step_is_successful"] for i in its)), "steps": steps_done,
                        "cost_first": its[0]["cost"] if its else None, "cost_last": its[-1]["cost"] if its else None,
                        "wall_ms_per_step": 1e3 * wall / max(1, steps_done)},
