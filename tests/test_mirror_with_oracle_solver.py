@@ -1,0 +1,140 @@
+"""The reference-facing Python layer end to end WITHOUT a device: the device entry points of `_engine` are replaced by
+the oracle (same problem IR in, same summary/arrays out), and the mirror-level GPU tests are run as they are.  What
+this covers is the host logic above the C-ABI — problem construction from reconstructions / graphs / databases /
+model files, option handling, write-back — which is the same code whichever side solves the IR.  (The product never
+does this; it is test plumbing, like everything that touches oracle/.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pixsfm._pixsfm import _capi, _engine
+
+
+def _ka_run(problem, interp=None, options=None, ctx=None):
+    interp = interp or _capi.default_interp()
+    options = options or _capi.default_ka_options()
+    d = problem.desc()
+    s = _capi.make_summary(0)
+    O.lib().orc_ka_solve(C.byref(d), C.byref(interp), C.byref(options), C.byref(s))
+    out = _capi.summary_to_dict(s)
+    out["num_residual_blocks"] = len(problem.edge_src)
+    out["num_residuals"] = len(problem.edge_src) * problem.channels
+    return out
+
+
+def _ba_run(problem, interp=None, options=None, ctx=None, capacity=512):
+    out = O.ba_solve(problem, interp or _capi.default_interp(), options or _capi.default_ba_options())
+    out.setdefault("num_residual_blocks", problem.n_obs)
+    return out
+
+
+def _refs_compute(problem, interp=None, loss_type=1, loss_scale=0.25, iters=100, ctx=None):
+    return O.refs_compute(problem, interp or _capi.default_interp(), loss_type, loss_scale, iters)
+
+
+def _costmaps_compute(problem, interp=None, cfg=None, refs=None, to_host=True, to_device=False, ctx=None):
+    interp = interp or _capi.default_interp()
+    cfg = cfg or _capi.default_costmap_config()
+    src = np.full(len(problem.xyz), -1, np.int64)
+    if cfg.compute_refs:
+        refs, src = O.refs_compute(problem, interp, cfg.ref_loss_type, cfg.ref_loss_scale, cfg.ref_iters)
+    p2 = problem.copy()
+    p2.refs = np.ascontiguousarray(refs if refs is not None else problem.refs, np.float64)
+    out = O.costmaps_compute(p2, cfg.loss_type, cfg.loss_scale, bool(cfg.as_gradientfield), bool(cfg.apply_sqrt))
+    return {"costmaps": out, "device_ptr": None, "refs": p2.refs, "src_obs": src, "summary": {}}
+
+
+def _obs_descriptors(problem, interp=None, ctx=None):
+    interp = interp or _capi.default_interp()
+    xy = O.ba_evaluate(problem.copy() if problem.refs is not None else _with_zero_refs(problem), interp,
+                       _capi.default_ba_options())["xy"]
+    out = np.zeros((problem.n_obs, problem.channels))
+    for o in range(problem.n_obs):
+        pi = int(problem.obs_patch[o]) if problem.obs_patch is not None and len(problem.obs_patch) else o
+        uv = (xy[o] * problem.scale[pi] - 0.5 - problem.corner[pi]) * problem.upsampling_factor
+        out[o] = O.pixel_interp(_patch_of(problem, pi), uv[1], uv[0], bool(interp.l2_normalize), bool(interp.use_float_simd))[0]
+    return out
+
+
+def _with_zero_refs(problem):
+    q = problem.copy()
+    q.refs = np.zeros((len(problem.xyz), problem.channels))
+    return q
+
+
+def _patch_of(problem, pi):
+    if problem.patch_blocks is not None:
+        starts = np.concatenate([[0], np.cumsum([b.shape[0] for b in problem.patch_blocks])])
+        b = int(np.searchsorted(starts, pi, side="right") - 1)
+        return np.asarray(problem.patch_blocks[b][pi - starts[b]])
+    return problem.patches[pi]
+
+
+def _interpolate_descriptors(fmap, patch_idxs, xys, interpolation_config=None):
+    from pixsfm._pixsfm import _localization as L
+    from pixsfm._pixsfm._base import InterpolationConfig
+    interp = interpolation_config if isinstance(interpolation_config, InterpolationConfig) else InterpolationConfig(interpolation_config or {})
+    patches = L._host_patches(fmap)
+    xys = np.asarray(xys, np.float64).reshape(-1, 2)
+    out = np.zeros((len(xys), fmap.channels))
+    for k, i in enumerate(patch_idxs):
+        li = fmap.local_index(i)
+        uv = xys[k] * np.asarray(fmap.scale, np.float64) - 0.5 - fmap.corners[li]
+        out[k] = O.pixel_interp(patches[li], uv[1], uv[0], bool(interp.l2_normalize), bool(interp.use_float_simd))[0]
+    return out
+
+
+@pytest.fixture
+def oracle_engine(monkeypatch):
+    from pixsfm._pixsfm import _localization as L
+    monkeypatch.setattr(_engine, "obs_descriptors", _obs_descriptors)
+    monkeypatch.setattr(L, "interpolate_descriptors", _interpolate_descriptors)
+    monkeypatch.setattr(_engine, "ka_run", _ka_run)
+    monkeypatch.setattr(_engine, "ba_run", _ba_run)
+    monkeypatch.setattr(_engine, "refs_compute", _refs_compute)
+    monkeypatch.setattr(_engine, "costmaps_compute", _costmaps_compute)
+
+
+def test_bundle_adjuster_multilevel(oracle_engine):
+    import test_gpu_mirror as T
+    T.test_bundle_adjuster_refine_multilevel_matches_oracle()
+
+
+def test_keypoint_adjusters(oracle_engine):
+    import test_gpu_mirror as T
+    T.test_keypoint_adjuster_refine_multilevel_moves_keypoints_towards_truth()
+    T.test_topological_reference_keypoint_adjuster_matches_flat_oracle()
+
+
+def test_dense_feature_maps(oracle_engine):
+    import test_gpu_mirror as T
+    T.test_dense_feature_maps_match_oracle()
+
+
+def test_colmap_database_and_model_directory_drivers(oracle_engine, tmp_path):
+    import test_gpu_mirror as T
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    T.test_keypoint_adjustment_from_a_colmap_database(tmp_path / "a")
+    T.test_pixsfm_refines_a_colmap_model_directory(tmp_path / "b")
+
+
+def test_costmap_bundle_adjuster(oracle_engine):
+    import test_gpu_costmaps as T
+    T.test_costmap_bundle_adjuster_strategy_end_to_end()
+
+
+@pytest.mark.parametrize("arg", [0, 1])
+def test_query_adjusters(oracle_engine, arg):
+    import test_gpu_localization as T
+    params = [m.args[1] for m in getattr(T.test_query_keypoint_adjuster_matches_oracle, "pytestmark", []) if m.name == "parametrize"]
+    T.test_query_keypoint_adjuster_matches_oracle(params[0][arg] if params else arg)
+    params = [m.args[1] for m in getattr(T.test_query_bundle_adjuster_matches_oracle, "pytestmark", []) if m.name == "parametrize"]
+    T.test_query_bundle_adjuster_matches_oracle(params[0][arg] if params else bool(arg))
+
+
+def test_localizer_pipeline(oracle_engine):
+    import test_gpu_localization as T
+    T.test_descriptor_interpolation_and_nearest_references()
+    T.test_query_localizer_runs_qka_pnp_qba()
