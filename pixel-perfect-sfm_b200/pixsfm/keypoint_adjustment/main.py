@@ -1,14 +1,13 @@
-"""pixsfm.keypoint_adjustment.main — same surface and defaults as the reference's
-pixsfm/keypoint_adjustment/main.py:13-203."""
-from copy import deepcopy
-
+"""pixsfm.keypoint_adjustment.main — the reference's KeypointAdjuster surface (pixsfm/keypoint_adjustment/main.py:13-279:
+`create`, `refine_multilevel`, `refine`, `find_problem_labels`, `build_matching_graph`, same option names and values)
+over the B200-backed optimizers."""
 import numpy as np
 
-from .. import base, logger
+from .. import base, defaults, logger
 from .._pixsfm import _engine
 from .._pixsfm import _keypoint_adjustment as ka
-from ..bundle_adjustment.main import to_optim_ctr
-from ..util.conf import merge, to_ctr
+from ..util.conf import to_ctr
+from ..util.refine import StrategyRefiner, optimizer_options
 
 
 def find_problem_labels(track_labels, max_per_problem, track_edge_counts=None):
@@ -23,103 +22,51 @@ def find_problem_labels(track_labels, max_per_problem, track_edge_counts=None):
     return [int(v) for v in labels], [int(b) for b in bins]
 
 
-class KeypointAdjuster:
-    default_conf = {
-        'strategy': 'featuremetric',
-        'apply': True,
-        'interpolation': base.interpolation_default_conf,
-        'level_indices': None,
-        'max_kps_per_problem': 50,
-        'optimizer': {
-            'loss': {'name': 'cauchy', 'params': [0.25]},
-            'solver': {**base.solver_default_conf, 'parameter_tolerance': 1.0e-5, 'num_threads': 1},
-            'print_summary': False,
-            'bound': 4.0,
-            'num_threads': -1
-        },
-        'split_in_subproblems': True
-    }
-    callbacks = []
-
-    @classmethod
-    def create(cls, conf):
-        strategy_to_solver = {"featuremetric": FeatureMetricKeypointAdjuster,
-                              "topological_reference": TopologicalReferenceKeypointAdjuster}
-        strategy = conf["strategy"] if "strategy" in conf else cls.default_conf["strategy"]
-        if strategy not in strategy_to_solver:
-            raise ValueError("strategy '%s' is not on the B200 path" % strategy)
-        return strategy_to_solver[strategy](conf)
+class KeypointAdjuster(StrategyRefiner):
+    default_conf = defaults.keypoint_adjustment()
+    optimizer_cls = None      # the `_keypoint_adjustment` optimizer a strategy drives
 
     def refine_multilevel(self, keypoints_dict, feature_manager, graph, track_labels=None, root_labels=None,
                           problem_setup=None):
+        """one adjustment per feature level; `keypoints_dict` is refined in place"""
         if track_labels is None:
             track_labels = base.compute_track_labels(graph)
         if root_labels is None:
-            score_labels = base.compute_score_labels(graph, track_labels)
-            root_labels = base.compute_root_labels(graph, track_labels, score_labels)
-        levels = self.conf.level_indices if self.conf.level_indices not in [None, "all"] else \
-            list(reversed(range(feature_manager.num_levels)))
-        outputs = {}
-        for level_index in levels:
-            out = self.refine(keypoints_dict, feature_manager.fset(level_index), graph, track_labels, root_labels,
-                              problem_setup=problem_setup)
-            for k, v in out.items():
-                outputs.setdefault(k, []).append(v)
-        return outputs
-
-
-class FeatureMetricKeypointAdjuster(KeypointAdjuster):
-    default_conf = deepcopy(KeypointAdjuster.default_conf)
-    default_conf["optimizer"] = {**default_conf["optimizer"], "root_regularize_weight": -1, "weight_by_sim": True,
-                                 "root_edges_only": False, "num_threads": -1}
-
-    def __init__(self, conf):
-        self.conf = merge(self.default_conf, conf)
+            root_labels = base.compute_root_labels(graph, track_labels, base.compute_score_labels(graph, track_labels))
+        return self.per_level(feature_manager, lambda fset: self.refine(keypoints_dict, fset, graph, track_labels,
+                                                                        root_labels, problem_setup=problem_setup))
 
     def refine(self, keypoints_dict, feature_set, graph, track_labels, root_labels, problem_setup=None):
-        if problem_setup is None:
+        if problem_setup is None:        # the root of every track stays where it was detected
             problem_setup = ka.KeypointAdjustmentSetup()
             problem_setup.set_masked_nodes_constant(graph, root_labels)
-        solver = ka.FeatureMetricKeypointOptimizer(to_optim_ctr(self.conf.optimizer, self.callbacks), problem_setup,
-                                                   to_ctr(self.conf.interpolation))
+        optimizer = self.optimizer_cls(optimizer_options(self.conf.optimizer, self.callbacks), problem_setup,
+                                       to_ctr(self.conf.interpolation))
+        run_args = (keypoints_dict, graph, track_labels, root_labels, feature_set)
         if self.conf.split_in_subproblems:
-            problem_labels, _ = find_problem_labels(track_labels, self.conf.max_kps_per_problem)
-            solver.run(problem_labels, keypoints_dict, graph, track_labels, root_labels, feature_set)
-        else:
-            solver.run(keypoints_dict, graph, track_labels, root_labels, feature_set)
-        return {"summary": solver.summary()}
+            run_args = (find_problem_labels(track_labels, self.conf.max_kps_per_problem)[0],) + run_args
+        optimizer.run(*run_args)
+        return {"summary": optimizer.summary()}
 
 
-class TopologicalReferenceKeypointAdjuster(KeypointAdjuster):
-    """Optimize all keypoints of a track towards the node with the highest aggregated matching score (reference
-    keypoint_adjustment/main.py:206-250): linear instead of quadratic in the track length."""
-    default_conf = deepcopy(KeypointAdjuster.default_conf)
-    default_conf["optimizer"] = {**default_conf["optimizer"], "num_threads": -1}
+class FeatureMetricKeypointAdjuster(KeypointAdjuster, strategy="featuremetric"):
+    """every matched pair of a track pulls on both of its keypoints (reference main.py:140-203)"""
+    default_conf = defaults.keypoint_adjustment(root_regularize_weight=-1, weight_by_sim=True, root_edges_only=False)
+    optimizer_cls = ka.FeatureMetricKeypointOptimizer
 
-    def __init__(self, conf):
-        self.conf = merge(self.default_conf, conf)
 
-    def refine(self, keypoints_dict, feature_set, graph, track_labels, root_labels, problem_setup=None):
-        if problem_setup is None:
-            problem_setup = ka.KeypointAdjustmentSetup()
-            problem_setup.set_masked_nodes_constant(graph, root_labels)
-        solver = ka.TopologicalReferenceKeypointOptimizer(to_optim_ctr(self.conf.optimizer, self.callbacks), problem_setup,
-                                                          to_ctr(self.conf.interpolation))
-        if self.conf.split_in_subproblems:
-            problem_labels, _ = find_problem_labels(track_labels, self.conf.max_kps_per_problem)
-            solver.run(problem_labels, keypoints_dict, graph, track_labels, root_labels, feature_set)
-        else:
-            solver.run(keypoints_dict, graph, track_labels, root_labels, feature_set)
-        return {"summary": solver.summary()}
+class TopologicalReferenceKeypointAdjuster(KeypointAdjuster, strategy="topological_reference"):
+    """every keypoint of a track is pulled towards the node with the highest aggregated matching score (reference
+    main.py:206-250): linear instead of quadratic in the track length"""
+    optimizer_cls = ka.TopologicalReferenceKeypointOptimizer
 
 
 def build_matching_graph(pairs, matches, scores=None):
     """matches of a COLMAP database / hloc match file -> base.Graph (reference main.py:262-271)"""
     logger.info("Building matching graph...")
     graph = base.Graph()
-    scores = scores if scores is not None else [None] * len(matches)
-    for (name1, name2), m, s in zip(pairs, matches, scores):
-        graph.register_matches(name1, name2, m, s)
+    for k, (name1, name2) in enumerate(pairs):
+        graph.register_matches(name1, name2, matches[k], None if scores is None else scores[k])
     return graph
 
 

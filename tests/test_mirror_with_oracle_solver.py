@@ -138,3 +138,40 @@ def test_localizer_pipeline(oracle_engine):
     import test_gpu_localization as T
     T.test_descriptor_interpolation_and_nearest_references()
     T.test_query_localizer_runs_qka_pnp_qba()
+
+
+def test_query_helpers_and_stacked_correspondences(oracle_engine):
+    """localization/main.py helpers: the feature-inlier test only judges single-descriptor references, and stacking
+    the correspondences of one keypoint solves it once against all of its targets."""
+    import test_gpu_localization as T
+    from pixsfm import localization as loc_pkg
+    from pixsfm._pixsfm import _localization as L
+    from pixsfm.localization import main as M
+    rec, fm, refs, qid, fmap, p2D_idxs, p3D_ids, kps = T._scene()
+    desc = L.interpolate_descriptors(fmap, p2D_idxs, kps, {})
+    near = [desc[k].copy() for k in range(len(kps))]
+    far = [-desc[k] for k in range(len(kps))]
+    mixed = [near[0], far[1], refs[p3D_ids[2]]] + near[3:]
+    got = M.find_feature_inliers(kps, fmap, mixed, {}, thresh=0.5, point2D_idxs=p2D_idxs)
+    assert got[0] is True and got[1] is False and got[2] is True and all(got[3:])       # a Reference object is not judged
+    assert M.find_feature_inliers(kps, fmap, far, {}, thresh=-1, point2D_idxs=p2D_idxs) == [True] * len(kps)
+    # stacked QKA: duplicate every correspondence (same keypoint, two targets) -> the duplicates move together and the
+    # result equals solving the distinct keypoints once against both targets
+    rng = np.random.default_rng(1)
+    start = kps + rng.normal(0, 0.7, kps.shape)
+    t1 = [np.asarray(refs[p].descriptor, np.float64).reshape(-1) for p in p3D_ids]
+    t2 = [np.asarray(refs[p].observations[0], np.float64).reshape(-1) for p in p3D_ids]
+    dup_kps = np.concatenate([start, start])
+    dup_idx = list(p2D_idxs) + list(p2D_idxs)
+    qka = loc_pkg.QueryKeypointAdjuster({"stack_correspondences": True})
+    qka.refine(dup_kps, fmap, t1 + t2, point2D_idxs=dup_idx)
+    n = len(kps)
+    assert np.array_equal(dup_kps[:n], dup_kps[n:]) and np.abs(dup_kps[:n] - start).max() > 1e-3
+    direct = start.copy()
+    L.QueryKeypointOptimizer(qka.solver.options, qka.solver.interp).run(direct, fmap, [[a, b] for a, b in zip(t1, t2)],
+                                                                        patch_idxs=list(p2D_idxs))
+    assert np.abs(direct - dup_kps[:n]).max() < 1e-9
+    with pytest.raises(ValueError, match="np.ndarray reference"):
+        qka.refine(dup_kps, fmap, [refs[p] for p in p3D_ids] * 2, point2D_idxs=dup_idx)
+    with pytest.raises(ValueError, match="point2D_idxs must not be None"):
+        qka.refine(dup_kps, fmap, t1 + t2)
