@@ -58,5 +58,31 @@ def build(verbose=False):
     return out
 
 
+def build_bindings(verbose=False):
+    """bindings/_pxr_pybind*.so: the pybind11 binding of the C-ABI (host C++, g++).  Needs libpxr.so to link against.
+    A machine without pybind11 / Python headers gets a warning, not a failed CUDA build."""
+    import sysconfig
+    src = os.path.join(HERE, "bindings", "pxr_pybind.cc")
+    try:
+        import pybind11
+    except ImportError:
+        sys.stderr.write("pybind11 not importable: bindings/_pxr_pybind is not built\n")
+        return None
+    out = os.path.join(HERE, "bindings", "_pxr_pybind" + sysconfig.get_config_var("EXT_SUFFIX"))
+    deps = [src, os.path.join(HERE, "..", "include", "pxr.h"), os.path.join(CSRC, "libpxr.so")]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + pybind11.get_include(),
+           "-I" + sysconfig.get_paths()["include"], src, "-o", out, "-L" + CSRC, "-lpxr", "-Wl,-rpath,$ORIGIN/../csrc"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write("bindings/_pxr_pybind did not build:\n" + r.stderr[-3000:])
+        return None
+    if verbose:
+        print("  %-16s compiled" % "pxr_pybind.cc")
+    return out
+
+
 if __name__ == "__main__":
     print(build(verbose=True))
+    print(build_bindings(verbose=True))
