@@ -1,0 +1,79 @@
+"""Parity at the SHAPES of BASELINE.json's configs[0] and configs[1] (the sacre_coeur cases; synthetic features, since
+the S2DNet weights are not available offline):
+  configs[0]  keypoint adjustment, 10 images / ~8 000 matched keypoints, 16-channel single-level features
+  configs[1]  featuremetric BA, 10 cameras / 1 856 points / 8 076 observations (ragged tracks), 128 channels -> the
+              DENSE_SCHUR regime of bundle_optimizer.h:184-185
+Both against the oracle solving the same IR.  (configs[2] is tests/test_gpu_full_size.py + bench.py, configs[3] the
+triangulation case of tests/test_gpu_edge_cases.py and the cost-map tests.)"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pixsfm._pixsfm import _capi, _engine
+from pixsfm.util import synthetic
+from ka_util import make_ka_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config0_shape_keypoint_adjustment_16_channels():
+    prob, _, lab = make_ka_problem(n_images=10, n_tracks=2000, track_len=4, channels=16, seed=40, kp_sigma=0.8,
+                                    bound=4.0, max_per_problem=50)
+    assert len(prob.keypoints) == 8000 and prob.n_problems >= 150
+    ic = _capi.default_interp(); so = _capi.default_ka_options()
+    p_cpu, p_gpu = prob.copy(), prob.copy()
+    c0, c1 = O.ka_solve(p_cpu, ic, so)
+    s = _engine.ka_run(p_gpu, ic, so)
+    assert abs(s["initial_cost"] - c0) <= 1e-9 * c0
+    assert abs(s["final_cost"] - c1) <= 1e-5 * c1 and c1 < 0.7 * c0
+    d = np.abs(p_gpu.keypoints - p_cpu.keypoints).max(axis=1)
+    assert np.quantile(d, 0.999) < 1e-5 and d.max() < 1e-3          # one packed problem = one trust region: allow a rare late step
+    roots = lab["roots"].astype(bool)
+    assert np.array_equal(p_gpu.keypoints[roots], prob.keypoints[roots])
+
+
+def _ragged(prob, n_keep, rng):
+    """drop observations at random (every point keeps at least two) until n_keep are left"""
+    n_pts = len(prob.xyz)
+    keep = np.ones(prob.n_obs, bool)
+    per_point = np.bincount(prob.obs_pt, minlength=n_pts)
+    for o in rng.permutation(prob.n_obs):
+        if keep.sum() == n_keep:
+            break
+        if per_point[prob.obs_pt[o]] > 2:
+            keep[o] = False
+            per_point[prob.obs_pt[o]] -= 1
+    idx = np.where(keep)[0]
+    return _capi.BAProblem(cam_model=prob.cam_model, cam_params=prob.cam_params, cam_const_mask=prob.cam_const_mask,
+                           qvec=prob.qvec, tvec=prob.tvec, img_cam=prob.img_cam, pose_const=prob.pose_const,
+                           tvec_const_mask=prob.tvec_const_mask, xyz=prob.xyz, point_const=prob.point_const,
+                           obs_img=prob.obs_img[idx], obs_pt=prob.obs_pt[idx], patches=np.ascontiguousarray(prob.patches[idx]),
+                           corner=prob.corner[idx], scale=prob.scale[idx])
+
+
+def test_config1_shape_bundle_adjustment_dense_schur():
+    full, gt = synthetic.make_ba_scene(n_cams=10, n_points=1856, track_len=5, channels=128, seed=41)
+    prob = _ragged(full, 8076, np.random.default_rng(41))
+    assert prob.n_obs == 8076 and len(prob.xyz) == 1856
+    lens = np.bincount(prob.obs_pt)
+    assert lens.min() >= 2 and lens.max() == 5 and len(set(lens)) > 2
+    ic = _capi.default_interp()
+    refs_gpu, src_gpu = _engine.refs_compute(prob, ic)
+    refs_cpu, src_cpu = O.refs_compute(prob, ic)
+    ties = lens == 2                                        # two observations are equally far from their mean
+    assert np.array_equal(src_gpu[~ties], src_cpu[~ties]) and np.abs(refs_gpu[~ties] - refs_cpu[~ties]).max() < 1e-12
+    prob.refs = refs_cpu
+    so = _capi.default_ba_options(max_num_iterations=12)    # defaults: Cauchy(0.25), inner iterations, solver by #images
+    p_cpu, p_gpu = prob.copy(), prob.copy()
+    s_cpu = O.ba_solve(p_cpu, ic, so)
+    s_gpu = _engine.ba_run(p_gpu, ic, so)
+    assert abs(s_gpu["initial_cost"] - s_cpu["initial_cost"]) <= 1e-10 * s_cpu["initial_cost"]
+    for ig, ir in list(zip(s_gpu["iterations"], s_cpu["iterations"]))[:4]:
+        assert ig["step_is_successful"] == ir["step_is_successful"]
+        assert abs(ig["cost"] - ir["cost"]) <= 1e-6 * abs(ir["cost"])
+    assert s_cpu["final_cost"] < s_cpu["initial_cost"]
+    assert abs(s_gpu["final_cost"] - s_cpu["final_cost"]) <= 1e-5 * s_cpu["final_cost"]
+    # the reference's own tolerance for comparing two BA results is 1e-4 (bundle_optimizer_test.cc:52)
+    assert np.abs(p_gpu.qvec - p_cpu.qvec).max() < 1e-4 and np.abs(p_gpu.tvec - p_cpu.tvec).max() < 1e-4
+    assert np.abs(p_gpu.xyz - p_cpu.xyz).max() < 1e-4
+    assert np.abs(p_gpu.cam_params[:, 0] / p_cpu.cam_params[:, 0] - 1).max() < 1e-4
