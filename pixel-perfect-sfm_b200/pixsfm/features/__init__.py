@@ -1,6 +1,7 @@
-"""pixsfm.features — the feature containers consumed by the hot path (reference pixsfm/features/bindings.cc:38-300).
-CNN feature extraction (features/extractor.py, models/) is unchanged reference territory and out of scope."""
+"""pixsfm.features — the feature containers consumed by the hot path (reference pixsfm/features/bindings.cc:38-300) and
+the step that fills them from dense feature maps (features/extractor.py); the CNN itself (models/) is not included."""
 from .._pixsfm._features import (FeaturePatch, FeatureMap, FeatureSet, FeatureView, FeatureManager,  # noqa: F401
                                  Reference, kDenseId)
+from .extractor import DenseFeatureExtractor, dense_to_fmap, patch_corners, cut_patches  # noqa: F401
 
 Map_IdReference = dict
