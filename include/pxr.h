@@ -219,6 +219,15 @@ int pxr_ctx_timer_start(pxr_ctx* ctx);
 int pxr_ctx_timer_stop(pxr_ctx* ctx, double* elapsed_ms);
 int64_t pxr_ctx_kernel_launches(pxr_ctx* ctx);
 
+/* Interruptibility.  The reference polls PyErr_CheckSignals from a ceres::IterationCallback and from its thread-pool
+ * wait loop (util/src/py_interrupt.h:29-38, base/src/callbacks.h:10-20, parallel_optimizer.h:186).  Here the host
+ * registers ONE process-wide callback; the LM drivers call it between iterations (at most every 20 ms) and stop with
+ * PXR_ERR_INTERRUPTED when it returns non-zero.  fn == NULL removes it.  pxr_poll_interrupt() calls it right away
+ * (no device needed) and returns its answer, 0 without a callback. */
+typedef int (*pxr_interrupt_fn)(void* user);
+int pxr_set_interrupt_callback(pxr_interrupt_fn fn, void* user);
+int pxr_poll_interrupt(void);
+
 /* ---- default option blocks --------------------------------------------- */
 void pxr_default_interp_config(pxr_interp_config* c);  /* base/main.py:1-7 */
 void pxr_default_ba_options(pxr_solver_options* o);    /* bundle_adjustment/main.py:30-62 */

@@ -3,6 +3,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <mutex>
 #include <cstring>
 #include <limits>
 #include <set>
@@ -72,7 +74,39 @@ int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count, bool max_op) {
 
 using namespace pxr;
 
+// ---- interrupt callback (process-wide; see include/pxr.h)
+static std::mutex g_interrupt_mutex;
+static pxr_interrupt_fn g_interrupt_fn = nullptr;
+static void* g_interrupt_user = nullptr;
+static std::chrono::steady_clock::time_point g_interrupt_last;
+
+static int call_interrupt_callback() {
+  pxr_interrupt_fn fn; void* user;
+  { std::lock_guard<std::mutex> lock(g_interrupt_mutex); fn = g_interrupt_fn; user = g_interrupt_user; }
+  return fn ? (fn(user) != 0) : 0;
+}
+
+namespace pxr {
+bool interrupt_pending() {
+  const auto now = std::chrono::steady_clock::now();
+  {
+    std::lock_guard<std::mutex> lock(g_interrupt_mutex);
+    if (!g_interrupt_fn || now - g_interrupt_last < std::chrono::milliseconds(20)) return false;
+    g_interrupt_last = now;
+  }
+  return call_interrupt_callback() != 0;
+}
+}  // namespace pxr
+
 extern "C" {
+
+int pxr_set_interrupt_callback(pxr_interrupt_fn fn, void* user) {
+  std::lock_guard<std::mutex> lock(g_interrupt_mutex);
+  g_interrupt_fn = fn; g_interrupt_user = user;
+  g_interrupt_last = std::chrono::steady_clock::time_point();
+  return PXR_OK;
+}
+int pxr_poll_interrupt(void) { return call_interrupt_callback(); }
 
 const char* pxr_last_error(void) { return g_error.c_str(); }
 int pxr_version(void) { return PXR_VERSION_MAJOR * 100 + PXR_VERSION_MINOR; }

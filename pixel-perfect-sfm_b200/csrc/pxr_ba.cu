@@ -973,6 +973,11 @@ int BA::lm_iterate(int max_iteration) {
   if (!lm.started) PXR_TRY(lm_begin());
   lm.it_start = clk::now();
   while (!lm.finished && lm_finalize(max_iteration)) {
+    if (interrupt_pending()) {     // Ctrl-C in the host (util/src/py_interrupt.h:29-38): stop between iterations
+      lm.finished = true; lm.term = 3;
+      lm.message = "interrupted by the host";
+      return fail(PXR_ERR_INTERRUPTED, "interrupted by the host after LM iteration %d", lm.it.iteration);
+    }
     lm.it_start = clk::now();
     pxr_iteration_summary& it = lm.it;
     const double prev_gmax = it.gradient_max_norm;

@@ -313,8 +313,25 @@ def load_lib():
     lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
     lib.pxr_last_error.restype = C.c_char_p
     lib.pxr_ctx_kernel_launches.restype = C.c_int64
+    lib.pxr_set_interrupt_callback(_SIGNAL_POLL, None)      # Ctrl-C stops a solve between LM iterations
     _LIB = lib
     return lib
+
+
+def _signals_pending(_user):
+    """the library's interrupt callback: has a Python signal handler (SIGINT -> KeyboardInterrupt) fired?  Same probe
+    as the reference's PyInterrupt (util/src/py_interrupt.h:29-38); ctypes re-acquires the GIL around this call."""
+    try:
+        return 1 if _check_signals() != 0 else 0
+    except KeyboardInterrupt:
+        return 1
+
+
+def _check_signals():
+    return C.pythonapi.PyErr_CheckSignals()
+
+
+_SIGNAL_POLL = C.CFUNCTYPE(C.c_int, C.c_void_p)(_signals_pending)      # kept alive for the life of the process
 
 
 def check(status):

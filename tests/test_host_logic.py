@@ -117,3 +117,46 @@ def test_default_option_blocks_match_reference_python_defaults():
     assert o.loss_type == 1 and o.loss_scale == 0.25 and o.max_num_iterations == 100 and o.use_inner_iterations == 1
     lib.pxr_default_ka_options(C.byref(o))
     assert o.parameter_tolerance == 1e-5 and o.use_inner_iterations == 0
+
+
+def test_interrupt_callback_and_sigint_polling(monkeypatch):
+    """pxr_set_interrupt_callback / pxr_poll_interrupt (host only): the mirror registers a callback that reports a
+    pending Ctrl-C the way the reference's PyInterrupt does; a solve that sees it stops with PXR_ERR_INTERRUPTED,
+    which the mirror raises as KeyboardInterrupt."""
+    import ctypes as C
+    import signal
+    import threading
+    from pixsfm._pixsfm import _capi
+    lib = _capi.load_lib()
+    if threading.current_thread() is not threading.main_thread():
+        pytest.skip("signal handlers run in the main thread only")
+    assert lib.pxr_poll_interrupt() == 0                      # nothing pending
+
+    def sigint_arrives_now():
+        # Ctrl-C while the library runs: the signal becomes deliverable inside the callback, Python's handler raises there
+        signal.pthread_sigmask(signal.SIG_UNBLOCK, {signal.SIGINT})
+        for _ in range(1000):
+            pass
+        return 0
+    signal.pthread_sigmask(signal.SIG_BLOCK, {signal.SIGINT})
+    try:
+        signal.pthread_kill(threading.main_thread().ident, signal.SIGINT)     # stays pending: this thread blocks it
+        monkeypatch.setattr(_capi, "_check_signals", sigint_arrives_now)
+        assert lib.pxr_poll_interrupt() == 1                  # reported to the library, not leaked as an exception here
+    finally:
+        signal.pthread_sigmask(signal.SIG_UNBLOCK, {signal.SIGINT})
+        monkeypatch.undo()
+    assert lib.pxr_poll_interrupt() == 0                      # consumed
+    monkeypatch.setattr(_capi, "_check_signals", lambda: -1)  # PyErr_CheckSignals reporting a raised handler
+    assert lib.pxr_poll_interrupt() == 1
+    monkeypatch.undo()
+    hits = []
+    cb = C.CFUNCTYPE(C.c_int, C.c_void_p)(lambda user: hits.append(user) or 1)
+    try:
+        assert lib.pxr_set_interrupt_callback(cb, C.c_void_p(7)) == 0
+        assert lib.pxr_poll_interrupt() == 1 and hits == [7]
+        assert lib.pxr_set_interrupt_callback(None, None) == 0 and lib.pxr_poll_interrupt() == 0
+    finally:
+        lib.pxr_set_interrupt_callback(_capi._SIGNAL_POLL, None)
+    with pytest.raises(KeyboardInterrupt):
+        _capi.check(_capi.PXR_ERR_INTERRUPTED)
