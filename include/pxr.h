@@ -221,7 +221,7 @@ int64_t pxr_ctx_kernel_launches(pxr_ctx* ctx);
 
 /* Interruptibility.  The reference polls PyErr_CheckSignals from a ceres::IterationCallback and from its thread-pool
  * wait loop (util/src/py_interrupt.h:29-38, base/src/callbacks.h:10-20, parallel_optimizer.h:186).  Here the host
- * registers ONE process-wide callback; the LM drivers call it between iterations (at most every 20 ms) and stop with
+ * registers ONE process-wide callback; the LM drivers call it between iterations (at most every 200 ms; the reference polls every 2 s) and stop with
  * PXR_ERR_INTERRUPTED when it returns non-zero.  fn == NULL removes it.  pxr_poll_interrupt() calls it right away
  * (no device needed) and returns its answer, 0 without a callback. */
 typedef int (*pxr_interrupt_fn)(void* user);

@@ -91,7 +91,7 @@ bool interrupt_pending() {
   const auto now = std::chrono::steady_clock::now();
   {
     std::lock_guard<std::mutex> lock(g_interrupt_mutex);
-    if (!g_interrupt_fn || now - g_interrupt_last < std::chrono::milliseconds(20)) return false;
+    if (!g_interrupt_fn || now - g_interrupt_last < std::chrono::milliseconds(200)) return false;
     g_interrupt_last = now;
   }
   return call_interrupt_callback() != 0;

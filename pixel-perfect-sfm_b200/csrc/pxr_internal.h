@@ -88,7 +88,7 @@ int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size
 int upload_stream(pxr_ctx* ctx, cudaStream_t* out);
 void stager_destroy(pxr_ctx* ctx);
 
-// true when the host's interrupt callback (pxr_set_interrupt_callback) asks to stop; rate-limited to one call per 20 ms
+// true when the host's interrupt callback (pxr_set_interrupt_callback) asks to stop; rate-limited to one call per 200 ms
 bool interrupt_pending();
 
 // allreduce (sum, fp64) on ctx->stream when a communicator is attached; no-op otherwise
