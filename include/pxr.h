@@ -251,6 +251,14 @@ int pxr_ba_destroy(pxr_ba* ba);
 int pxr_ba_run(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
                const pxr_solver_options* opt, pxr_summary* summary);
 
+/* Device memory pxr_ba_create / pxr_ba_run will take for this problem, in bytes (host computation, no device needed) —
+ * the counterpart of the RAM estimate the reference logs before it solves (bundle_optimizer.h:200-208,
+ * util/src/memory.h:45-69).  patch_bytes: the patch slab (0 when it is already resident); state_bytes: per-observation
+ * buffers, Schur pair lists and point blocks; reduced_bytes: the reduced camera system (dense, or its block-sparse form
+ * when the solver is ITERATIVE_SCHUR and dense would exceed 4 GB).  Any output may be NULL. */
+int pxr_ba_estimate_device_bytes(const pxr_ba_desc* desc, const pxr_solver_options* opt, double* patch_bytes,
+                                 double* state_bytes, double* reduced_bytes);
+
 /* Parity / introspection: evaluates every residual block at the current parameters.
  * Replaces calling FeatureReferenceCostFunctor::operator() per block
  * (residuals/src/feature_reference.h:98-137).  Any output may be NULL.

@@ -12,6 +12,7 @@
 #include <unordered_map>
 
 #include "pxr_internal.h"
+#include "pxr_device.cuh"
 
 namespace pxr {
 
@@ -356,6 +357,45 @@ int pxr_shard_points(int64_t n_points, int64_t n_obs, const int64_t* obs_pt, int
     point_begin[r] = p; obs_begin[r] = pt_begin[p];
   }
   point_begin[world] = n_points; obs_begin[world] = n_obs;
+  return PXR_OK;
+}
+
+int pxr_ba_estimate_device_bytes(const pxr_ba_desc* d, const pxr_solver_options* opt, double* patch_bytes,
+                                 double* state_bytes, double* reduced_bytes) {
+  if (!d) return fail(PXR_ERR_INVALID_ARGUMENT, "desc is NULL");
+  if (d->n_obs < 0 || d->n_points < 0 || d->n_images < 0 || d->n_cameras < 0 || (d->n_obs > 0 && !d->obs_pt))
+    return fail(PXR_ERR_INVALID_ARGUMENT, "bad problem sizes");
+  const double esz = d->patch_dtype == PXR_F16 ? 2 : (d->patch_dtype == PXR_F32 ? 4 : 8);
+  double n_patches = (double)(d->obs_patch ? d->n_patches : std::max(d->n_patches, d->n_obs));
+  if (d->n_patch_blocks > 0 && d->patch_block_counts) {
+    n_patches = 0;
+    for (int b = 0; b < d->n_patch_blocks; ++b) n_patches += (double)d->patch_block_counts[b];
+  }
+  const double slab = d->patches_on_device ? 0.0 : n_patches * d->ph * d->pw * d->channels * esz;
+  int K = 0;
+  for (int i = 0; i < d->n_cameras; ++i) K = std::max(K, d->cam_model ? cam_num_params(d->cam_model[i]) : 0);
+  const double dcmax = 6 + K, juv = 2 * (9 + K), n_obs = (double)d->n_obs, n_pts = (double)d->n_points;
+  // observation pairs (i >= j) of every point: the static structure of the Schur complement
+  double pairs = 0;
+  for (int64_t o = 0, run = 0; o < d->n_obs; ++o) {
+    run = (o > 0 && d->obs_pt[o] == d->obs_pt[o - 1]) ? run + 1 : 1;
+    pairs += (double)run;
+  }
+  const double per_obs = 2.0 * (2 + 8 + juv) * 8       // uv, obs_out, juv: the linearisation and the trial point
+                         + 2.0 * dcmax * 3 * 8          // W and T = W (Hpp + D)^-1
+                         + dcmax * 4 + 4                // column table
+                         + 4 + 8 + 8;                   // obs_img, obs_pt, obs_patch
+  const double state = n_obs * per_obs + pairs * 8 + n_pts * ((9 + 3 + 6) * 8 + 2 * 3 * 8 + 8 + 8 + 1)
+                       + n_patches * (8 + 16) + (d->refs ? n_pts * d->channels * 8 : 0.0);
+  // upper bound of the camera unknowns: 6 per image + K per camera (constant blocks only make it smaller)
+  const double nc = 6.0 * d->n_images + (double)K * d->n_cameras;
+  const int solver = opt ? opt->linear_solver : PXR_SOLVER_AUTO;
+  const bool iterative = solver == PXR_SOLVER_ITERATIVE_SCHUR || (solver == PXR_SOLVER_AUTO && d->n_images > 1000);
+  double reduced = 2.0 * nc * nc * 8;                  // Hcc and [S; rhs]
+  if (iterative && nc * nc * 8 > 4e9) reduced = ((double)d->n_images + pairs / 16.0) * 64 * 8;   // image blocks + co-visible pairs (estimate)
+  if (patch_bytes) *patch_bytes = slab;
+  if (state_bytes) *state_bytes = state;
+  if (reduced_bytes) *reduced_bytes = reduced;
   return PXR_OK;
 }
 

@@ -379,6 +379,9 @@ class FeatureReferenceBundleOptimizer:
         so = solver_options_from(self.options.loss, self.options.solver, _capi.default_ba_options(use_inner_iterations=0))
         ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
         callbacks = self.options.solver.get("callbacks") or []
+        need = _engine.ba_estimate_device_bytes(prob, so)     # the reference logs its RAM estimate here (bundle_optimizer.h:200-208)
+        logger.info("Estimated device memory: %.3f GB (patches %.3f, problem state %.3f, reduced system %.3f).",
+                    need["total"] / 1e9, need["patches"] / 1e9, need["state"] / 1e9, need["reduced_system"] / 1e9)
         s = _engine.ba_run(prob, ic, so)
         for cb in callbacks:   # ceres IterationCallback-like objects are invoked once per recorded iteration
             for it in s["iterations"]:

@@ -208,3 +208,15 @@ def ka_shard_plan(problem_weight, world):
     out = np.zeros(len(w), np.int32)
     _capi.check(lib.pxr_shard_ka_problems(C.c_int32(len(w)), _p(w), int(world), _p(out)))
     return out
+
+
+def ba_estimate_device_bytes(problem, options=None):
+    """pxr_ba_estimate_device_bytes: what the solve will take on the device (host computation) ->
+    dict(patches, state, reduced_system, total) in bytes"""
+    lib = _capi.load_lib()
+    d = problem.desc()
+    out = [C.c_double(), C.c_double(), C.c_double()]
+    _capi.check(lib.pxr_ba_estimate_device_bytes(C.byref(d), C.byref(options) if options is not None else None,
+                                                 C.byref(out[0]), C.byref(out[1]), C.byref(out[2])))
+    p, s, r = (o.value for o in out)
+    return {"patches": p, "state": s, "reduced_system": r, "total": p + s + r}

@@ -160,3 +160,40 @@ def test_interrupt_callback_and_sigint_polling(monkeypatch):
         lib.pxr_set_interrupt_callback(_capi._SIGNAL_POLL, None)
     with pytest.raises(KeyboardInterrupt):
         _capi.check(_capi.PXR_ERR_INTERRUPTED)
+
+
+def test_device_memory_estimate():
+    """pxr_ba_estimate_device_bytes: host-side count of what a BA solve takes on the device"""
+    from pixsfm._pixsfm import _capi, _engine
+    from pixsfm.util import synthetic
+    prob, _ = synthetic.make_ba_scene(n_cams=6, n_points=50, track_len=4, channels=16, seed=1)
+    prob.refs = np.zeros((50, 16))
+    e = _engine.ba_estimate_device_bytes(prob, _capi.default_ba_options())
+    n_obs, K = prob.n_obs, 4                                         # SIMPLE_RADIAL: 4 intrinsics
+    assert e["patches"] == n_obs * 16 * 16 * 16 * 2                  # the fp16 slab, exactly
+    pairs = 50 * (4 * 5 // 2)
+    per_obs = 2 * (2 + 8 + 2 * (9 + K)) * 8 + 2 * (6 + K) * 3 * 8 + (6 + K) * 4 + 4 + 20
+    state = n_obs * per_obs + pairs * 8 + 50 * ((9 + 3 + 6) * 8 + 48 + 17) + n_obs * 24 + 50 * 16 * 8
+    assert e["state"] == state
+    nc = 6 * 6 + K * len(prob.cam_model)
+    assert e["reduced_system"] == 2 * nc * nc * 8 and e["total"] == e["patches"] + e["state"] + e["reduced_system"]
+    # resident patches cost nothing more; BASELINE configs[2] sizes: the slab dominates (32.8 GB), the rest is < 1 GB
+    big = dict(n_obs=500000, n_pts=50000, L=10)
+    obs_pt = np.repeat(np.arange(big["n_pts"], dtype=np.int64), big["L"])
+    import ctypes as C
+    d = prob.desc()
+    d.n_obs, d.n_points, d.n_patches, d.n_images = big["n_obs"], big["n_pts"], big["n_obs"], 200
+    d.obs_pt = obs_pt.ctypes.data_as(C.c_void_p); d.channels = 128; d.obs_patch = None; d.refs = None
+    out = [C.c_double() for _ in range(3)]
+    lib = _capi.load_lib()
+    assert lib.pxr_ba_estimate_device_bytes(C.byref(d), None, *[C.byref(o) for o in out]) == 0
+    assert out[0].value == 500000 * 16 * 16 * 128 * 2 == 32768000000.0
+    assert 0.4e9 < out[1].value < 1.0e9
+    d.patches_on_device = 1
+    assert lib.pxr_ba_estimate_device_bytes(C.byref(d), None, C.byref(out[0]), None, None) == 0 and out[0].value == 0
+    # ITERATIVE_SCHUR at config-5 camera counts: block-sparse, far below the dense 2 x 12.8 GB
+    d.n_images = 5000
+    so = _capi.default_ba_options(linear_solver=3)
+    assert lib.pxr_ba_estimate_device_bytes(C.byref(d), C.byref(so), None, None, C.byref(out[2])) == 0
+    assert out[2].value < 1e9
+    assert lib.pxr_ba_estimate_device_bytes(None, None, None, None, None) != 0
