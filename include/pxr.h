@@ -111,7 +111,8 @@ typedef struct {
   double min_lm_diagonal;           /* 1e-6 */
   double max_lm_diagonal;           /* 1e32 */
   int32_t jacobi_scaling;           /* 1 */
-  int32_t deterministic;            /* 1: fixed-order reductions (slower), 0: fp64 atomics */
+  int32_t deterministic;            /* reserved (must be 0): the normal equations are accumulated with fp64 atomics,
+                                     * cost reductions are fixed-order; a fixed-order build is not implemented */
 } pxr_solver_options;
 
 /* One featuremetric BA problem (reference: what BundleOptimizer::SetUp turns a
