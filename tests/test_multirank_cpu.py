@@ -114,3 +114,47 @@ def test_ka_problems_shard_without_a_collective():
         O.ka_solve(sub, ic, so)
         qm.merge_shard(sub, kg)
     assert np.array_equal(qm.keypoints, qfull.keypoints)
+
+
+def _ka_worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "pixel-perfect-sfm_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import oracle_lib as O
+    from pixsfm._pixsfm import _capi, _engine
+    from ka_util import make_ka_problem
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    prob = make_ka_problem(n_images=5, n_tracks=40, track_len=4, channels=16, seed=6, max_per_problem=10)[0]
+    ic = _capi.default_interp(); so = _capi.default_ka_options()
+    plan = _engine.ka_shard_plan(prob.problem_weights(), world)      # every rank computes the same plan, no exchange
+    sub, kp_global = prob.shard(plan, rank)
+    O.ka_solve(sub, ic, so)                                          # the rank's own problems only
+    mine = torch.zeros(len(prob.keypoints), 2, dtype=torch.float64)
+    mine[torch.from_numpy(kp_global)] = torch.from_numpy(sub.keypoints)
+    owned = torch.zeros(len(prob.keypoints), dtype=torch.int32); owned[torch.from_numpy(kp_global)] = 1
+    dist.all_reduce(mine); dist.all_reduce(owned)                    # only to bring the results together for the check
+    full = prob.copy()
+    O.ka_solve(full, ic, so)
+    touched = owned.numpy() > 0
+    ok = bool(owned.max().item() == 1 and np.array_equal(mine.numpy()[touched], full.keypoints[touched])
+              and np.array_equal(prob.keypoints[~touched], full.keypoints[~touched]))
+    q.put((rank, ok, int(sub.n_problems)))
+    dist.destroy_process_group()
+
+
+def test_ka_shards_solve_independently_on_two_ranks():
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_ka_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    counts = [n for _, _, n in sorted(res)]
+    assert min(counts) >= 1 and abs(counts[0] - counts[1]) <= 2
