@@ -352,6 +352,19 @@ int pxr_interpolate_descriptors(pxr_ctx* ctx, const void* patches, int64_t n_pat
                                 double upsampling_factor, int64_t n_items, const int64_t* item_patch, const double* xy,
                                 const pxr_interp_config* interp, double* out_desc);
 
+/* ---- dense map -> patch slab -----------------------------------------------
+ * replaces the sparse branch of FeatureExtractor.tensor_to_fmap + extract_patches_numpy
+ * (features/extractor.py:176-201, features/extract_patches.py:36-44: the GPU -> CPU copy the authors flag as their
+ * bottleneck): L2-normalise every pixel's C-vector (fp32, x / max(||x||, 1e-12)), cast, and gather one ps x ps window
+ * per keypoint into the slab layout [n][ps][ps][C] the optimizers take.
+ *  dense     one image's map, [C][H][W] (channels_first = 1, the CNN's NCHW) or [H][W][C]; host or device memory
+ *  corners   host [n][2] (x0, y0), every window must lie inside the map (features/extractor.py:192-193 clamps them)
+ *  out_host  optional host copy; out_device optional: receives a device pointer (release with pxr_device_free) that
+ *            pxr_ba_create / pxr_ka_run accept as device patches or as a device patch block */
+int pxr_extract_patches(pxr_ctx* ctx, const void* dense, int32_t dense_on_device, int32_t in_dtype, int32_t channels,
+                        int32_t height, int32_t width, int32_t channels_first, const int32_t* corners, int64_t n_patches,
+                        int32_t patch_size, int32_t l2_normalize, int32_t out_dtype, void* out_host, void** out_device);
+
 /* ---- featuremetric KA ---------------------------------------------------
  * replaces _keypoint_adjustment.FeatureMetricKeypointOptimizer.run
  * (keypoint_adjustment/bindings.cc:17-34; featuremetric_keypoint_optimizer.h:50-202;

@@ -220,3 +220,53 @@ def ba_estimate_device_bytes(problem, options=None):
                                                  C.byref(out[0]), C.byref(out[1]), C.byref(out[2])))
     p, s, r = (o.value for o in out)
     return {"patches": p, "state": s, "reduced_system": r, "total": p + s + r}
+
+
+class DeviceSlab:
+    """A [N,H,W,C] array in device memory owned by libpxr (returned by pxr_extract_patches); exposes the CUDA array
+    interface, so FeatureMap / DevicePatches take it like a torch tensor.  Freed with the object."""
+
+    def __init__(self, ptr, shape, dtype, ctx):
+        self.ptr, self.shape, self.dtype, self._ctx = int(ptr), tuple(int(v) for v in shape), np.dtype(dtype), ctx
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False),
+                                         "version": 3, "strides": None}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._ctx.lib.pxr_device_free(self._ctx.handle, C.c_void_p(self.ptr))
+                self.ptr = 0
+        except Exception:      # interpreter shutdown
+            pass
+
+
+def extract_patches(dense, corners, patch_size, l2_normalize=True, out_dtype=np.float16, channels_first=True,
+                    to_host=False, ctx=None):
+    """pxr_extract_patches: windows of ONE dense map, gathered on the device.  `dense` is a host numpy array or anything
+    with __cuda_array_interface__ (a contiguous torch.cuda tensor), [C,H,W] (or [H,W,C] with channels_first=False).
+    -> DeviceSlab [n, ps, ps, C] (or a numpy array with to_host=True)"""
+    ctx = ctx or _capi.default_context()
+    cai = getattr(dense, "__cuda_array_interface__", None)
+    if cai is not None:
+        if cai.get("strides") is not None:
+            raise ValueError("the dense map must be contiguous")
+        shape, in_dtype, ptr, on_dev = tuple(cai["shape"]), np.dtype(cai["typestr"]), int(cai["data"][0]), 1
+    else:
+        dense = np.ascontiguousarray(dense)
+        shape, in_dtype, ptr, on_dev = dense.shape, dense.dtype, dense.ctypes.data, 0
+    if len(shape) == 4 and shape[0] == 1:
+        shape = shape[1:]
+    if len(shape) != 3 or in_dtype not in _capi.DTYPE_IDS or np.dtype(out_dtype) not in _capi.DTYPE_IDS:
+        raise ValueError("a dense map is a [C,H,W] / [H,W,C] float16/32/64 array")
+    ch, h, w = shape if channels_first else (shape[2], shape[0], shape[1])
+    corners = np.ascontiguousarray(corners, np.int32).reshape(-1, 2)
+    n = len(corners)
+    out = np.zeros((n, patch_size, patch_size, ch), out_dtype) if to_host else None
+    if n == 0:
+        return out if to_host else DeviceSlab(0, (0, patch_size, patch_size, ch), out_dtype, ctx)
+    dptr = C.c_void_p()
+    _capi.check(ctx.lib.pxr_extract_patches(ctx.handle, C.c_void_p(ptr), on_dev, _capi.DTYPE_IDS[in_dtype], int(ch), int(h),
+                                            int(w), int(bool(channels_first)), _p(corners), C.c_int64(n), int(patch_size),
+                                            int(bool(l2_normalize)), _capi.DTYPE_IDS[np.dtype(out_dtype)],
+                                            _p(out) if to_host else None, None if to_host else C.byref(dptr)))
+    return out if to_host else DeviceSlab(dptr.value, (n, patch_size, patch_size, ch), out_dtype, ctx)

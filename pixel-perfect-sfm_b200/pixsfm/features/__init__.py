@@ -2,6 +2,7 @@
 the step that fills them from dense feature maps (features/extractor.py); the CNN itself (models/) is not included."""
 from .._pixsfm._features import (FeaturePatch, FeatureMap, FeatureSet, FeatureView, FeatureManager,  # noqa: F401
                                  Reference, kDenseId)
-from .extractor import DenseFeatureExtractor, dense_to_fmap, patch_corners, cut_patches  # noqa: F401
+from .extractor import (DenseFeatureExtractor, dense_to_fmap, dense_to_fmap_on_device, patch_corners,  # noqa: F401
+                        cut_patches)
 
 Map_IdReference = dict

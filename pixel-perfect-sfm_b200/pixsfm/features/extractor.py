@@ -19,6 +19,11 @@ def _as_numpy(x):
     return np.asarray(x)
 
 
+def _map_shape(x):
+    cai = getattr(x, "__cuda_array_interface__", None)
+    return tuple(cai["shape"]) if cai is not None else np.shape(x)
+
+
 def patch_corners(keypoints, scale, patch_size, map_wh):
     """top-left map pixel of every keypoint's patch (extractor.py:192-193): truncation towards zero, then clamped so
     that the patch and one more pixel stay inside the map"""
@@ -31,6 +36,31 @@ def cut_patches(dense_hwc, corners, patch_size):
     rows = corners[:, 1, None] + np.arange(patch_size)[None, :]            # [N, ps]
     cols = corners[:, 0, None] + np.arange(patch_size)[None, :]
     return np.ascontiguousarray(dense_hwc[rows[:, :, None], cols[:, None, :]])
+
+
+def dense_to_fmap_on_device(featuremap, image_size, keypoints, keypoint_ids=None, patch_size=16, l2_normalize=True,
+                            dtype=np.float16, channels_first=True):
+    """the sparse branch of dense_to_fmap with the gather done by libpxr on the GPU: `featuremap` may be the CNN's output
+    still in device memory (anything with __cuda_array_interface__) or a host array; the patches stay on the device and
+    the optimizers take them from there (no GPU -> numpy -> GPU round trip)"""
+    from .._pixsfm import _engine
+    cai = getattr(featuremap, "__cuda_array_interface__", None)
+    shape = tuple(cai["shape"]) if cai is not None else np.shape(featuremap)
+    if len(shape) == 4 and shape[0] == 1:
+        shape = shape[1:]
+    if len(shape) != 3:
+        raise ValueError("a feature map is [C,H,W] (or [H,W,C] with channels_first=False)")
+    h, w = (shape[1], shape[2]) if channels_first else (shape[0], shape[1])
+    keypoints = np.asarray(keypoints, np.float64).reshape(-1, 2)
+    if keypoint_ids is None:
+        keypoint_ids = list(range(len(keypoints)))
+    elif len(keypoint_ids) != len(keypoints):
+        raise ValueError("Number of provided keypoint_ids and keypoints do not match.")
+    scale = np.array((w / image_size[0], h / image_size[1]))
+    corners = patch_corners(keypoints, scale, patch_size, (w, h))
+    source = featuremap if cai is not None else _as_numpy(featuremap)
+    slab = _engine.extract_patches(source, corners, patch_size, l2_normalize, dtype, channels_first)
+    return features.FeatureMap(slab, keypoint_ids, corners, {"scale": scale, "is_sparse": True, "patch_size": patch_size})
 
 
 def dense_to_fmap(featuremap, image_size, keypoints=None, keypoint_ids=None, patch_size=16, sparse=True,
@@ -67,7 +97,7 @@ def dense_to_fmap(featuremap, image_size, keypoints=None, keypoint_ids=None, pat
 class DenseFeatureExtractor:
     """model(image_name) -> list of [C,H,W] maps (one per level) ; image_size(image_name) -> (width, height).
     Produces the FeatureManager the adjusters take: one FeatureSet per level, one FeatureMap per image."""
-    default_conf = dict(patch_size=16, sparse=True, l2_normalize=True, dtype="half")
+    default_conf = dict(patch_size=16, sparse=True, l2_normalize=True, dtype="half", on_device=False)
 
     def __init__(self, model, image_size, conf=None):
         self.model, self.image_size = model, image_size
@@ -91,11 +121,15 @@ class DenseFeatureExtractor:
                     kps = kps[ids]
             maps = self.model(name)
             if manager is None:
-                manager = features.FeatureManager([_as_numpy(m).shape[-3] for m in maps], _DTYPES[self.conf["dtype"]])
+                manager = features.FeatureManager([_map_shape(m)[-3] for m in maps], _DTYPES[self.conf["dtype"]])
             for level, fmap in enumerate(maps):
-                manager.fset(level).emplace(name, dense_to_fmap(
-                    fmap, self.image_size(name), kps, ids, self.conf["patch_size"], self.conf["sparse"],
-                    self.conf["l2_normalize"], _DTYPES[self.conf["dtype"]]))
+                if self.conf["on_device"] and self.conf["sparse"] and kps is not None:
+                    made = dense_to_fmap_on_device(fmap, self.image_size(name), kps, ids, self.conf["patch_size"],
+                                                   self.conf["l2_normalize"], _DTYPES[self.conf["dtype"]])
+                else:
+                    made = dense_to_fmap(fmap, self.image_size(name), kps, ids, self.conf["patch_size"], self.conf["sparse"],
+                                         self.conf["l2_normalize"], _DTYPES[self.conf["dtype"]])
+                manager.fset(level).emplace(name, made)
         if manager is None:
             raise ValueError("no image to extract features for")
         return manager

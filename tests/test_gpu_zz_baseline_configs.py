@@ -77,3 +77,37 @@ def test_config1_shape_bundle_adjustment_dense_schur():
     assert np.abs(p_gpu.qvec - p_cpu.qvec).max() < 1e-4 and np.abs(p_gpu.tvec - p_cpu.tvec).max() < 1e-4
     assert np.abs(p_gpu.xyz - p_cpu.xyz).max() < 1e-4
     assert np.abs(p_gpu.cam_params[:, 0] / p_cpu.cam_params[:, 0] - 1).max() < 1e-4
+
+
+def test_device_patch_gather_matches_the_host_extraction():
+    """pxr_extract_patches (dense CNN map -> patch slab on the device) against the numpy step it replaces
+    (features/extractor.py: dense_to_fmap), host and device-resident inputs, both memory layouts."""
+    from pixsfm.features.extractor import cut_patches, dense_to_fmap, dense_to_fmap_on_device, patch_corners
+    rng = np.random.default_rng(7)
+    C, H, W, ps = 128, 96, 96, 16
+    chw = rng.normal(size=(C, H, W)).astype(np.float32)
+    kps = rng.uniform(-10, 400, (300, 2))
+    corners = patch_corners(kps, np.array([W / 384.0, H / 384.0]), ps, (W, H))
+    want = dense_to_fmap(chw, (384, 384), kps, patch_size=ps).patches              # fp16, L2-normalised
+    got = _engine.extract_patches(chw, corners, ps, l2_normalize=True, out_dtype=np.float16, to_host=True)
+    assert got.shape == want.shape == (300, ps, ps, C) and got.dtype == np.float16
+    diff = np.abs(got.astype(np.float32) - want.astype(np.float32))
+    assert diff.max() <= 2.0 ** -11 and np.mean(got == want) > 0.99              # <= 1 fp16 ulp at |v| < 1, almost all equal
+    # no normalisation, same dtype: a pure gather, bit for bit; [H,W,C] layout too
+    hwc = np.ascontiguousarray(np.moveaxis(chw, 0, -1))
+    exact = cut_patches(hwc, corners, ps)
+    assert np.array_equal(_engine.extract_patches(chw, corners, ps, False, np.float32, True, to_host=True), exact)
+    assert np.array_equal(_engine.extract_patches(hwc, corners, ps, False, np.float32, False, to_host=True), exact)
+    assert np.array_equal(_engine.extract_patches(hwc.astype(np.float64), corners, ps, False, np.float64, False, to_host=True), exact)
+    # device-resident input: the whole map as one 96 x 96 "patch" stays on the device and is gathered from there
+    whole = _engine.extract_patches(hwc, np.zeros((1, 2), np.int32), H, False, np.float32, False)
+    assert whole.shape == (1, H, W, C)
+    assert np.array_equal(_engine.extract_patches(whole, corners, ps, False, np.float32, False, to_host=True), exact)
+    with pytest.raises(ValueError):
+        _engine.extract_patches(chw, np.array([[W - ps + 1, 0]], np.int32), ps, to_host=True)      # leaves the map
+    assert _engine.extract_patches(chw, np.zeros((0, 2), np.int32), ps, to_host=True).shape == (0, ps, ps, C)
+    # FeatureMap built on the device: same metadata as the host one, patches device-resident
+    fm_dev = dense_to_fmap_on_device(chw, (384, 384), kps, list(range(1000, 1300)), patch_size=ps)
+    fm_host = dense_to_fmap(chw, (384, 384), kps, list(range(1000, 1300)), patch_size=ps)
+    assert fm_dev.is_sparse and fm_dev.point2D_ids == fm_host.point2D_ids and np.array_equal(fm_dev.corners, fm_host.corners)
+    assert np.array_equal(fm_dev.scale, fm_host.scale) and fm_dev.patches.shape == fm_host.patches.shape
