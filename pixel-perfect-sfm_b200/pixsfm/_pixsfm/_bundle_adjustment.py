@@ -353,45 +353,70 @@ class _Summary(dict):
 
 
 class FeatureReferenceBundleOptimizer:
-    """_bundle_adjustment.FeatureReferenceBundleOptimizer(options, setup, interpolation)
-    .run(reconstruction, feature_view, references) -> bool   (mutates `reconstruction` in place)"""
+    """_bundle_adjustment.FeatureReferenceBundleOptimizer(options, setup, interpolation): `run(reconstruction,
+    feature_view, references) -> bool` (mutates `reconstruction` in place) = `set_up(...)` + `solve_problem()`;
+    `summary()`, `problem`, `reset()` as bound in bundle_adjustment/bindings.cc:36-51 (bundle_optimizer.h:114-245).
+    `problem` is the flat problem IR handed to libpxr (the reference exposes its ceres::Problem there)."""
+    _channels = (8, 16, 32, 64, 128, 256)
+    _banner = "Start feature-reference bundle adjustment."
 
     def __init__(self, options, setup, interpolation_config):
         self.options = options if isinstance(options, BundleOptimizerOptions) else BundleOptimizerOptions(options)
         self.setup = setup
         self.interp = interpolation_config if isinstance(interpolation_config, InterpolationConfig) else InterpolationConfig(interpolation_config)
         self._summary, self._used = None, False
-        logger.info("Start feature-reference bundle adjustment.")
+        self._prob = self._ir = self._reconstruction = None
+        logger.info(self._banner)
 
-    def run(self, reconstruction, feature_view, references):
+    # ---- BundleOptimizer::SetUp (bundle_optimizer.h:139-165): residual blocks + parameterisation -> problem IR
+    def set_up(self, reconstruction, feature_view, references=None):
         if reconstruction is None:
             raise ValueError("reconstruction cannot be NULL.")
         if self._used:
             raise ValueError("Cannot use the same BundleOptimizer multiple times")
         self._used = True
         self.interp.validate_for_device()
-        n_nodes = len(self.interp.nodes)
-        if (feature_view.channels, n_nodes) not in {(c, 1) for c in (8, 16, 32, 64, 128, 256)}:
+        if len(self.interp.nodes) != 1 or feature_view.channels not in self._channels:
             raise ValueError("Unsupported dimensions (CHANNELS,N_NODES).")
-        prob, ir = build_problem(reconstruction, feature_view, self.setup, self.options, references)
+        self._prob, self._ir = build_problem(reconstruction, feature_view, self.setup, self.options, references)
+        self._reconstruction = reconstruction
+        return True
+
+    @property
+    def problem(self):
+        return self._prob
+
+    # ---- BundleOptimizer::SolveProblem (bundle_optimizer.h:172-245)
+    def solve_problem(self):
+        if self._prob is None:
+            raise ValueError("set_up() has to run before solve_problem()")
+        prob = self._prob
         if prob.n_obs == 0:
-            return False   # problem_->NumResiduals() == 0 (bundle_optimizer.h:175-177)
+            return False   # problem_->NumResiduals() == 0 (:175-177)
         so = solver_options_from(self.options.loss, self.options.solver, _capi.default_ba_options(use_inner_iterations=0))
         ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
-        callbacks = self.options.solver.get("callbacks") or []
-        need = _engine.ba_estimate_device_bytes(prob, so)     # the reference logs its RAM estimate here (bundle_optimizer.h:200-208)
+        need = _engine.ba_estimate_device_bytes(prob, so)     # the reference logs its RAM estimate here (:200-208)
         logger.info("Estimated device memory: %.3f GB (patches %.3f, problem state %.3f, reduced system %.3f).",
                     need["total"] / 1e9, need["patches"] / 1e9, need["state"] / 1e9, need["reduced_system"] / 1e9)
         s = _engine.ba_run(prob, ic, so)
-        for cb in callbacks:   # ceres IterationCallback-like objects are invoked once per recorded iteration
-            for it in s["iterations"]:
+        for cb in (self.options.solver.get("callbacks") or []):   # ceres IterationCallback-like objects, once per
+            for it in s["iterations"]:                            # recorded iteration
                 cb(it)
-        write_back(reconstruction, prob, ir)
+        write_back(self._reconstruction, prob, self._ir)
         self._summary = _Summary(s, num_residuals_reduced=s["num_residuals"], total_time_in_seconds=s["total_time_s"])
         nres = max(1, s["num_residuals"])
         logger.info("BA Time: %.4gs, cost change: %.6g --> %.6g", s["total_time_s"],
                     np.sqrt(s["initial_cost"] / nres), np.sqrt(s["final_cost"] / nres))
         return True
+
+    def run(self, reconstruction, feature_view, references=None):
+        self.set_up(reconstruction, feature_view, references)
+        return self.solve_problem()
+
+    def reset(self):
+        """BundleOptimizer::Reset: forget the problem, the optimizer can be set up again"""
+        self._prob = self._ir = self._reconstruction = self._summary = None
+        self._used = False
 
     def summary(self):
         return self._summary
@@ -459,25 +484,12 @@ class CostMapBundleOptimizer(FeatureReferenceBundleOptimizer):
     """_bundle_adjustment.CostMapBundleOptimizer(options, setup, interpolation).run(reconstruction, costmap_view)
     (bindings.cc:143-160; costmap_bundle_optimizer.h:60-132): the residual of an observation is the interpolated
     cost-map vector itself (no reference descriptor, no L2 normalisation)."""
+    _channels = (1, 3, 4)
+    _banner = "Start cost-map bundle adjustment."
+
+    def set_up(self, reconstruction, feature_view):   # noqa: D102
+        return super().set_up(reconstruction, feature_view, None)
 
     def run(self, reconstruction, feature_view):   # noqa: D102
-        if reconstruction is None:
-            raise ValueError("reconstruction cannot be NULL.")
-        if self._used:
-            raise ValueError("Cannot use the same BundleOptimizer multiple times")
-        self._used = True
-        self.interp.validate_for_device()
-        if len(self.interp.nodes) != 1 or feature_view.channels not in (1, 3, 4):
-            raise ValueError("Unsupported dimensions (CHANNELS,N_NODES).")
-        prob, ir = build_problem(reconstruction, feature_view, self.setup, self.options, None)
-        if prob.n_obs == 0:
-            return False
-        so = solver_options_from(self.options.loss, self.options.solver, _capi.default_ba_options(use_inner_iterations=0))
-        ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
-        s = _engine.ba_run(prob, ic, so)
-        for cb in (self.options.solver.get("callbacks") or []):
-            for it in s["iterations"]:
-                cb(it)
-        write_back(reconstruction, prob, ir)
-        self._summary = _Summary(s, num_residuals_reduced=s["num_residuals"], total_time_in_seconds=s["total_time_s"])
-        return True
+        self.set_up(reconstruction, feature_view)
+        return self.solve_problem()

@@ -175,3 +175,35 @@ def test_query_helpers_and_stacked_correspondences(oracle_engine):
         qka.refine(dup_kps, fmap, [refs[p] for p in p3D_ids] * 2, point2D_idxs=dup_idx)
     with pytest.raises(ValueError, match="point2D_idxs must not be None"):
         qka.refine(dup_kps, fmap, t1 + t2)
+
+
+def test_two_phase_bundle_optimizer_surface(oracle_engine):
+    """set_up / problem / solve_problem / reset, as bound by bundle_adjustment/bindings.cc:36-51"""
+    import copy
+    from pixsfm import bundle_adjustment as ba_pkg, features
+    from pixsfm._pixsfm import _bundle_adjustment as ba
+    from recon_util import make_reconstruction
+    rec, fm, _, _ = make_reconstruction(n_cams=5, n_points=40, track_len=3, channels=16, seed=31)
+    rec2 = copy.deepcopy(rec)
+    setup = ba_pkg.default_problem_setup(rec)
+    labels = ba_pkg.find_problem_labels(rec, 10)
+    refs = ba.ReferenceExtractor({}, {}).run(labels, rec, fm.fset(0))
+    fview = features.FeatureView(fm.fset(0), rec)
+    opt = ba.FeatureReferenceBundleOptimizer({"solver": {"max_num_iterations": 5}}, setup, {})
+    with pytest.raises(ValueError, match="set_up"):
+        opt.solve_problem()
+    assert opt.problem is None and opt.set_up(rec, fview, refs) is True
+    prob = opt.problem
+    assert prob.n_obs == rec.num_observations() and len(prob.xyz) == len(rec.points3D)
+    with pytest.raises(ValueError, match="multiple times"):
+        opt.set_up(rec, fview, refs)
+    before = {i: im.tvec.copy() for i, im in rec.images.items()}
+    assert opt.solve_problem() is True and opt.summary().final_cost < opt.summary().initial_cost
+    assert any(not np.array_equal(rec.images[i].tvec, before[i]) for i in before)          # written back
+    # one-shot run on the untouched copy gives the same result
+    one = ba.FeatureReferenceBundleOptimizer({"solver": {"max_num_iterations": 5}}, ba_pkg.default_problem_setup(rec2), {})
+    assert one.run(rec2, features.FeatureView(fm.fset(0), rec2), refs) is True
+    for i in rec.images:
+        assert np.abs(rec.images[i].tvec - rec2.images[i].tvec).max() < 1e-9      # (the oracle sums with OpenMP)
+    opt.reset()
+    assert opt.problem is None and opt.summary() is None and opt.set_up(rec, fview, refs) is True
