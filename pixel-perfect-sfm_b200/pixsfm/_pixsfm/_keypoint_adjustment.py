@@ -65,6 +65,18 @@ class FeatureMetricKeypointOptimizer:
             problem_labels, keypoints, graph, track_labels, root_labels, feature_set = args
         else:
             raise TypeError("run() takes 5 or 6 positional arguments")
+        return self._run(None, problem_labels, keypoints, graph, track_labels, root_labels, feature_set)
+
+    def run_subset(self, nodes_in_problem, keypoints, graph, track_labels, root_labels, feature_set):
+        """one problem over the intra-track edges that START at the given nodes (RunSubset,
+        featuremetric_keypoint_optimizer.h:118-137 — what the reference's thread pool calls per label); -> summary"""
+        subset = sorted({int(n) for n in nodes_in_problem})
+        if subset and (subset[0] < 0 or subset[-1] >= len(graph.nodes)):
+            raise ValueError("nodes_in_problem holds an index outside the graph")
+        self._run(subset, [0] * len(graph.nodes), keypoints, graph, track_labels, root_labels, feature_set)
+        return self._summary
+
+    def _run(self, subset, problem_labels, keypoints, graph, track_labels, root_labels, feature_set):
         n_nodes = len(graph.nodes)
         if not (len(track_labels) == len(root_labels) == len(problem_labels) == n_nodes):
             raise ValueError("label arrays must have one entry per graph node")
@@ -76,7 +88,7 @@ class FeatureMetricKeypointOptimizer:
         regularize = opt.root_regularize_weight > 0.0
         connected, track_root = [False] * n_nodes, {}
         edges = []
-        for node in graph.nodes:
+        for node in (graph.nodes if subset is None else [graph.nodes[n] for n in subset]):
             for m in node.out_matches:
                 if track_labels[node.node_idx] != track_labels[m.node_idx]:
                     continue

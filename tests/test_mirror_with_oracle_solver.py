@@ -207,3 +207,38 @@ def test_two_phase_bundle_optimizer_surface(oracle_engine):
         assert np.abs(rec.images[i].tvec - rec2.images[i].tvec).max() < 1e-9      # (the oracle sums with OpenMP)
     opt.reset()
     assert opt.problem is None and opt.summary() is None and opt.set_up(rec, fview, refs) is True
+
+
+def test_keypoint_optimizer_run_subset(oracle_engine):
+    """run_subset (keypoint_adjustment/bindings.cc:17-23): the nodes of two tracks only; everything else stays put, and
+    the moved keypoints equal what a run over labels that isolate those tracks gives"""
+    from pixsfm import base, features
+    from pixsfm._pixsfm import _keypoint_adjustment as ka
+    from pixsfm.util import synthetic
+    sc = synthetic.make_ka_scene(n_images=5, n_tracks=12, track_len=4, channels=16, seed=21, kp_sigma=0.8)
+    g = base.Graph()
+    names = ["im%d" % i for i in range(5)]
+    keypoints = {names[i]: np.ascontiguousarray(sc["keypoints"][sc["node_image"] == i]) for i in range(5)}
+    for n in range(len(sc["node_image"])):
+        g.add_node(names[sc["node_image"][n]], int(sc["node_feature"][n]))
+    for e in range(len(sc["edge_src"])):
+        g.add_edge(g.nodes[sc["edge_src"][e]], g.nodes[sc["edge_dst"][e]], sc["edge_sim"][e])
+    fset = features.FeatureSet()
+    for i in range(5):
+        m = np.where(sc["node_image"] == i)[0]
+        fset.emplace(names[i], features.FeatureMap(np.ascontiguousarray(sc["patches"][m]), sc["node_feature"][m].tolist(),
+                                                   sc["corner"][m], {"scale": sc["scale"][m[0]], "is_sparse": True}))
+    tl = base.compute_track_labels(g)
+    roots = base.compute_root_labels(g, tl, base.compute_score_labels(g, tl))
+    setup = ka.KeypointAdjustmentSetup(); setup.set_masked_nodes_constant(g, roots)
+    chosen = [n for n in range(len(tl)) if tl[n] in (tl[0], tl[7])]
+    kp_sub = {k: v.copy() for k, v in keypoints.items()}
+    summary = ka.FeatureMetricKeypointOptimizer({}, setup, {}).run_subset(chosen, kp_sub, g, tl, roots, fset)
+    assert summary.final_cost < summary.initial_cost and summary.num_residual_blocks > 0
+    moved = {(g.image_id_to_name[g.nodes[n].image_id], g.nodes[n].feature_idx) for n in chosen if not roots[n]}
+    for name in names:
+        for f in range(len(keypoints[name])):
+            same = np.array_equal(kp_sub[name][f], keypoints[name][f])
+            assert same != ((name, f) in moved)
+    with pytest.raises(ValueError):
+        ka.FeatureMetricKeypointOptimizer({}, setup, {}).run_subset([10 ** 6], kp_sub, g, tl, roots, fset)
