@@ -153,3 +153,15 @@ def count_track_edges(graph, track_labels):
             if track_labels[n.node_idx] == track_labels[m.node_idx]:
                 out[track_labels[n.node_idx]] += 1
     return out
+
+
+def count_edges_AB(graph, track_labels, is_root):
+    """per track: (edges that touch a root, edges between two non-roots) — graph.cc:258-281; the list has one entry per
+    NODE index, as the reference allocates it, and only the entries of track labels are filled"""
+    counts = [[0, 0] for _ in graph.nodes]
+    for node in graph.nodes:
+        for m in node.out_matches:
+            t = track_labels[node.node_idx]
+            if t == track_labels[m.node_idx]:
+                counts[t][0 if (is_root[node.node_idx] or is_root[m.node_idx]) else 1] += 1
+    return [tuple(c) for c in counts]

@@ -183,3 +183,16 @@ def test_localization_surface_and_defaults():
         L.QueryLocalizer(None, {}, references=None)
     with pytest.raises(ValueError):
         qka.solver.run(np.zeros((2, 2)), None, [None])          # references.size() != keypoints.rows()
+
+
+def test_count_edges_AB_and_track_edges():
+    from pixsfm import base
+    g = base.Graph()
+    for im, f in [("a", 0), ("b", 0), ("c", 0), ("a", 1), ("b", 1)]:
+        g.add_node(im, f)
+    for s, d in [(0, 1), (1, 2), (0, 2), (3, 4), (2, 3)]:
+        g.add_edge(g.nodes[s], g.nodes[d], 1.0)
+    labels, roots = [0, 0, 0, 1, 1], [True, False, False, False, True]
+    assert base.count_track_edges(g, labels) == [3, 1]
+    ab = base.count_edges_AB(g, labels, roots)
+    assert len(ab) == 5 and ab[0] == (2, 1) and ab[1] == (1, 0) and ab[2:] == [(0, 0)] * 3      # the 2-3 edge is inter-track
