@@ -270,3 +270,25 @@ def extract_patches(dense, corners, patch_size, l2_normalize=True, out_dtype=np.
                                             int(bool(l2_normalize)), _capi.DTYPE_IDS[np.dtype(out_dtype)],
                                             _p(out) if to_host else None, None if to_host else C.byref(dptr)))
     return out if to_host else DeviceSlab(dptr.value, (n, patch_size, patch_size, ch), out_dtype, ctx)
+
+
+def interpolate_patches(patches, corners, scales, item_patch, xys, interp=None, upsampling_factor=1.0, ctx=None):
+    """pxr_interpolate_descriptors: the (bicubic, optionally L2-normalised) descriptor of patch item_patch[i] of a host
+    [N,H,W,C] patch array at IMAGE coordinates xys[i] -> [n_items, C] float64"""
+    ctx = ctx or _capi.default_context()
+    interp = interp or _capi.default_interp()
+    patches = np.ascontiguousarray(patches)
+    if patches.ndim != 4 or patches.dtype not in _capi.DTYPE_IDS:
+        raise ValueError("patches must be a [N,H,W,C] float16/32/64 array")
+    corners = np.ascontiguousarray(corners, np.int32).reshape(-1, 2)
+    scales = np.ascontiguousarray(scales, np.float64).reshape(-1, 2)
+    item_patch = np.ascontiguousarray(item_patch, np.int64).reshape(-1)
+    xys = np.ascontiguousarray(xys, np.float64).reshape(-1, 2)
+    if len(corners) != len(patches) or len(scales) != len(patches) or len(item_patch) != len(xys):
+        raise ValueError("one corner and scale per patch, one patch index per query point")
+    out = np.zeros((len(xys), patches.shape[3]))
+    _capi.check(ctx.lib.pxr_interpolate_descriptors(
+        ctx.handle, _p(patches), C.c_int64(len(patches)), _capi.DTYPE_IDS[patches.dtype], int(patches.shape[1]),
+        int(patches.shape[2]), int(patches.shape[3]), _p(corners), _p(scales), C.c_double(upsampling_factor),
+        C.c_int64(len(xys)), _p(item_patch), _p(xys), C.byref(interp), _p(out)))
+    return out

@@ -232,3 +232,35 @@ class PatchSlab:
 
     def arrays(self):
         return self.blocks, np.concatenate(self.corners), np.concatenate(self.scales)
+
+
+class PatchInterpolator:
+    """_features.PatchInterpolator(interpolation_config) (features/bindings.cc:276-292; dynamic_patch_interpolator.h:
+    57-132, patch_interpolator.h:125-158): the descriptor of ONE FeaturePatch at a point, evaluated by libpxr.
+      interpolate(patch, xy)        xy in image coordinates            -> [1, C]
+      interpolate_nodes(patch, xy)  one row per interpolation node     -> [n_nodes, C]  (the device path has one node)
+      interpolate_local(patch, uv)  uv = (column, row) inside the patch -> [1, C]"""
+
+    def __init__(self, interpolation_config=None):
+        from ._base import InterpolationConfig
+        self.config = interpolation_config if isinstance(interpolation_config, InterpolationConfig) \
+            else InterpolationConfig(interpolation_config or {})
+
+    def _evaluate(self, patch, corner, scale, xy, upsampling_factor):
+        from . import _capi, _engine
+        self.config.validate_for_device()
+        data = np.ascontiguousarray(patch.data)
+        if data.ndim != 3:
+            raise ValueError("a FeaturePatch holds an [H,W,C] array")
+        ic = _capi.default_interp(self.config.l2_normalize, self.config.use_float_simd)
+        return _engine.interpolate_patches(data[None], [corner], [scale], [0], [xy], ic, upsampling_factor)
+
+    def interpolate(self, patch, xy):
+        return self._evaluate(patch, patch.corner, patch.scale, np.asarray(xy, np.float64), patch.upsampling_factor)
+
+    def interpolate_nodes(self, patch, xy):
+        return self.interpolate(patch, xy)        # nodes = [[0, 0]]: the single node sits at xy itself
+
+    def interpolate_local(self, patch, uv):
+        # local coordinates are what ToPixelCoordinates produces: xy = uv + 0.5 with corner 0, scale 1 maps back onto uv
+        return self._evaluate(patch, (0, 0), (1.0, 1.0), np.asarray(uv, np.float64) + 0.5, 1.0)

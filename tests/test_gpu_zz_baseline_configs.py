@@ -111,3 +111,21 @@ def test_device_patch_gather_matches_the_host_extraction():
     fm_host = dense_to_fmap(chw, (384, 384), kps, list(range(1000, 1300)), patch_size=ps)
     assert fm_dev.is_sparse and fm_dev.point2D_ids == fm_host.point2D_ids and np.array_equal(fm_dev.corners, fm_host.corners)
     assert np.array_equal(fm_dev.scale, fm_host.scale) and fm_dev.patches.shape == fm_host.patches.shape
+
+
+def test_patch_interpolator_on_the_device_matches_the_oracle():
+    """features.PatchInterpolator (features/bindings.cc:276-292) through pxr_interpolate_descriptors, fp16 / fp32 / fp64
+    patches, image and local coordinates"""
+    from pixsfm import features
+    rng = np.random.default_rng(12)
+    for dtype in (np.float16, np.float32, np.float64):
+        data = rng.normal(size=(16, 16, 128)).astype(dtype)
+        patch = features.FeaturePatch(data, (100, 40), (0.5, 0.25))
+        for l2 in (True, False):
+            pi = features.PatchInterpolator({"l2_normalize": l2})
+            for xy in ([213.3, 188.9], [205.0, 170.0], [228.7, 219.1]):
+                uv = patch.to_pixel_coordinates(np.array(xy))
+                want = O.pixel_interp(data, uv[1], uv[0], l2)[0]
+                assert np.abs(pi.interpolate(patch, xy)[0] - want).max() < 1e-12
+                assert np.abs(pi.interpolate_local(patch, uv)[0] - want).max() < 1e-11
+                assert pi.interpolate_nodes(patch, xy).shape == (1, 128)

@@ -242,3 +242,34 @@ def test_keypoint_optimizer_run_subset(oracle_engine):
             assert same != ((name, f) in moved)
     with pytest.raises(ValueError):
         ka.FeatureMetricKeypointOptimizer({}, setup, {}).run_subset([10 ** 6], kp_sub, g, tl, roots, fset)
+
+
+def _interpolate_patches(patches, corners, scales, item_patch, xys, interp=None, upsampling_factor=1.0, ctx=None):
+    interp = interp or _capi.default_interp()
+    out = np.zeros((len(xys), np.shape(patches)[3]))
+    for k, (pi, xy) in enumerate(zip(item_patch, xys)):
+        uv = (np.asarray(xy, np.float64) * np.asarray(scales[pi], np.float64) - 0.5 - np.asarray(corners[pi])) * upsampling_factor
+        out[k] = O.pixel_interp(np.asarray(patches)[pi], uv[1], uv[0], bool(interp.l2_normalize), bool(interp.use_float_simd))[0]
+    return out
+
+
+def test_patch_interpolator_surface(monkeypatch):
+    """features.PatchInterpolator: image vs local coordinates, nodes, config handling (oracle as the evaluator)"""
+    from pixsfm import features
+    monkeypatch.setattr(_engine, "interpolate_patches", _interpolate_patches)
+    rng = np.random.default_rng(4)
+    data = rng.normal(size=(16, 16, 8)).astype(np.float16)
+    patch = features.FeaturePatch(data, (100, 40), (0.5, 0.25))
+    pi = features.PatchInterpolator({"l2_normalize": True})
+    xy = np.array([213.3, 188.9])
+    uv = patch.to_pixel_coordinates(xy)
+    assert np.allclose(uv, [213.3 * 0.5 - 0.5 - 100, 188.9 * 0.25 - 0.5 - 40])
+    f = pi.interpolate(patch, xy)
+    assert f.shape == (1, 8) and abs(np.linalg.norm(f) - 1) < 1e-12
+    assert np.abs(f - O.pixel_interp(data, uv[1], uv[0])[0]).max() < 1e-15
+    assert np.array_equal(pi.interpolate_nodes(patch, xy), f)
+    assert np.abs(pi.interpolate_local(patch, uv) - f).max() < 1e-12
+    raw = features.PatchInterpolator({"l2_normalize": False}).interpolate_local(patch, [3.0, 5.0])
+    assert np.abs(raw[0] - data[5, 3].astype(np.float64)).max() < 1e-6         # at a pixel centre the spline interpolates
+    with pytest.raises(ValueError):
+        features.PatchInterpolator({"nodes": [[0, 0], [1, 0]]}).interpolate(patch, xy)
