@@ -10,6 +10,7 @@ What differs from the reference, and why:
   * configuration: dicts (or a YAML path) merged over the reference's defaults; `${..interpolation}` of the reference's
     YAML files is resolved here by handing the top-level `interpolation` block to KA and BA unless they set their own.
   * `triangulation` / `reconstruction` (refine_hloc.py) shell out to COLMAP through pycolmap/hloc and are not provided."""
+import re
 import shutil
 from copy import deepcopy
 from pathlib import Path
@@ -24,23 +25,37 @@ from .util.conf import merge, to_conf
 
 
 def _load_conf(conf):
+    """dict | preset name | YAML path -> dict"""
     if conf is None:
         return {}
     if isinstance(conf, (str, Path)):
-        import yaml
-        with open(conf) as f:
-            conf = yaml.safe_load(f) or {}
+        from .configs import parse_config_path
+        conf = parse_config_path(str(conf))
+        if isinstance(conf, Path):
+            import yaml
+            with open(conf) as f:
+                conf = yaml.safe_load(f) or {}
     if not isinstance(conf, dict):
-        raise TypeError("conf must be a dict or the path of a YAML file")
+        raise TypeError("conf must be a dict, the name of a preset or the path of a YAML file")
     return conf
 
 
-def _strip_interpolations(node, interpolation):
-    """OmegaConf-style references to the shared interpolation block -> the block itself"""
-    if isinstance(node, dict):
-        return {k: (deepcopy(interpolation) if isinstance(v, str) and v.startswith("${") and v.endswith("interpolation}")
-                    else _strip_interpolations(v, interpolation)) for k, v in node.items()}
-    return node
+_REFERENCE = re.compile(r"^\$\{\.*([A-Za-z_]\w*)\}$")
+
+
+def _resolve_references(node, top):
+    """OmegaConf-style "${..name}" / "${name}" strings -> a copy of the top-level block of that name (the only kind of
+    interpolation the reference's configuration files use); a reference to a block the file does not have is dropped"""
+    if not isinstance(node, dict):
+        return node
+    out = {}
+    for key, value in node.items():
+        m = _REFERENCE.match(value) if isinstance(value, str) else None
+        if m is None:
+            out[key] = _resolve_references(value, top)
+        elif isinstance(top.get(m.group(1)), dict):
+            out[key] = deepcopy(top[m.group(1)])
+    return out
 
 
 class PixSfM:
@@ -51,21 +66,16 @@ class PixSfM:
     }
 
     def __init__(self, conf=None, extractor=None):
-        conf = _load_conf(conf)
-        top = conf
-        conf = dict(conf.get("mapping", conf))
-        if isinstance(conf.get("interpolation"), str):      # "${interpolation}": the file's top-level block
-            conf["interpolation"] = top.get("interpolation") if isinstance(top.get("interpolation"), dict) else None
-            if conf["interpolation"] is None:
-                del conf["interpolation"]
-        if "dense_features" not in conf and "dense_features" in top:
-            conf["dense_features"] = top["dense_features"]
+        top = _load_conf(conf)
+        conf = dict(top.get("mapping", top))
+        for shared in ("interpolation", "dense_features"):       # blocks a file keeps at its top level
+            if shared not in conf and isinstance(top.get(shared), dict):
+                conf[shared] = top[shared]
+        conf = _resolve_references(conf, top)
         unknown = set(conf) - {"interpolation", "KA", "BA", "dense_features"}
         if unknown:
             raise ValueError("unknown configuration keys: %s" % sorted(unknown))
-        interpolation = merge(self.default_conf["interpolation"], conf.get("interpolation")
-                              if isinstance(conf.get("interpolation"), dict) else None)
-        conf = _strip_interpolations(conf, interpolation)
+        interpolation = merge(self.default_conf["interpolation"], conf.get("interpolation"))
         self.conf = merge(self.default_conf, {k: v for k, v in conf.items() if k != "dense_features"})
         self.conf["dense_features"] = to_conf(conf.get("dense_features", {}))
         for part in ("KA", "BA"):       # "${..interpolation}": the shared block unless the adjuster has its own

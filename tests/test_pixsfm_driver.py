@@ -89,3 +89,25 @@ def test_extractor_is_used_when_no_feature_manager_is_given():
     with pytest.raises(RuntimeError):
         s.run_ka({"a": np.zeros((2, 2)), "b": np.zeros((2, 2))}, "imgs", [("a", "b")], ([np.array([[0, 1]], np.uint32)], None))
     assert calls == [("rec", "imgs", "c.h5"), ("graph", 2, ["a", "b"])]
+
+
+def test_named_presets_and_reference_resolution(tmp_path):
+    from pixsfm.configs import default_configs, parse_config_path
+    assert {"default", "low_memory", "norefine"} <= set(default_configs) and parse_config_path(None) is None
+    with pytest.raises(FileNotFoundError, match="Not in the default configs"):
+        parse_config_path("no_such_preset")
+    low = PixSfM("low_memory")
+    assert type(low.keypoint_adjuster).__name__ == "TopologicalReferenceKeypointAdjuster"
+    assert type(low.bundle_adjuster).__name__ == "CostMapBundleAdjuster"
+    assert low.conf.KA.optimizer.bound == 2.0 and low.conf.KA.max_kps_per_problem == 1000
+    assert low.conf.BA.optimizer.refine_extrinsics is False and low.conf.BA.max_tracks_per_problem == 100
+    assert low.conf.dense_features.patch_size == 8 and low.conf.KA.optimizer.solver.max_num_iterations == 100
+    assert PixSfM("norefine").conf.KA.apply is False and PixSfM("default").conf.BA.strategy == "feature_reference"
+    # "${..name}" / "${name}" anywhere in the mapping block refer to the file's top-level blocks
+    f = tmp_path / "c.yaml"
+    f.write_text("dense_features: {patch_size: 10}\\ninterpolation: {l2_normalize: false, mode: BICUBIC, nodes: [[0.0, 0.0]], "
+                 "ncc_normalize: false}\\nmapping:\\n  dense_features: ${..dense_features}\\n  interpolation: ${interpolation}\\n"
+                 "  KA: {interpolation: \\"${..interpolation}\\"}\\n  BA: {interpolation: \\"${..missing_block}\\"}\\n")
+    s = PixSfM(str(f))
+    assert s.conf.dense_features.patch_size == 10
+    assert s.conf.KA.interpolation.l2_normalize is False and s.conf.BA.interpolation.l2_normalize is False
