@@ -105,9 +105,15 @@ def test_named_presets_and_reference_resolution(tmp_path):
     assert PixSfM("norefine").conf.KA.apply is False and PixSfM("default").conf.BA.strategy == "feature_reference"
     # "${..name}" / "${name}" anywhere in the mapping block refer to the file's top-level blocks
     f = tmp_path / "c.yaml"
-    f.write_text("dense_features: {patch_size: 10}\\ninterpolation: {l2_normalize: false, mode: BICUBIC, nodes: [[0.0, 0.0]], "
-                 "ncc_normalize: false}\\nmapping:\\n  dense_features: ${..dense_features}\\n  interpolation: ${interpolation}\\n"
-                 "  KA: {interpolation: \\"${..interpolation}\\"}\\n  BA: {interpolation: \\"${..missing_block}\\"}\\n")
+    f.write_text("""
+dense_features: {patch_size: 10}
+interpolation: {l2_normalize: false, mode: BICUBIC, nodes: [[0.0, 0.0]], ncc_normalize: false}
+mapping:
+  dense_features: ${..dense_features}
+  interpolation: ${interpolation}
+  KA: {interpolation: "${..interpolation}"}
+  BA: {interpolation: "${..missing_block}"}
+""")
     s = PixSfM(str(f))
     assert s.conf.dense_features.patch_size == 10
     assert s.conf.KA.interpolation.l2_normalize is False and s.conf.BA.interpolation.l2_normalize is False
