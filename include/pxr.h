@@ -111,8 +111,12 @@ typedef struct {
   double min_lm_diagonal;           /* 1e-6 */
   double max_lm_diagonal;           /* 1e32 */
   int32_t jacobi_scaling;           /* 1 */
-  int32_t deterministic;            /* reserved (must be 0): the normal equations are accumulated with fp64 atomics,
-                                     * cost reductions are fixed-order; a fixed-order build is not implemented */
+  int32_t deterministic;            /* 1: fixed-order (bit-reproducible) build of the normal equations: Hcc/gc/Hpp/gp/S are
+                                     * accumulated by segmented reductions in a static order instead of fp64 atomics
+                                     * (SURVEY §5); slower. 0: atomics (run-to-run differences ~1e-16 relative) */
+  int32_t use_nonmonotonic_steps;   /* ceres::Solver::Options::use_nonmonotonic_steps (the reference's configs/default.yaml
+                                     * sets it for KA, BA and QKA); 0 */
+  int32_t max_consecutive_nonmonotonic_steps; /* 5 */
 } pxr_solver_options;
 
 /* One featuremetric BA problem (reference: what BundleOptimizer::SetUp turns a

@@ -723,6 +723,8 @@ inline TROptions ToTROptions(const pxr_solver_options& o) {
   t.max_num_consecutive_invalid_steps = o.max_num_consecutive_invalid_steps;
   t.use_inner_iterations = o.use_inner_iterations != 0;
   t.inner_iteration_tolerance = o.inner_iteration_tolerance;
+  t.use_nonmonotonic_steps = o.use_nonmonotonic_steps != 0;
+  t.max_consecutive_nonmonotonic_steps = o.max_consecutive_nonmonotonic_steps;
   return t;
 }
 

@@ -32,7 +32,45 @@ struct TROptions {
   bool use_inner_iterations = false;
   double inner_iteration_tolerance = 1e-3;
   int max_num_line_search_step_size_iterations = 20;
+  bool use_nonmonotonic_steps = false;            // ceres::Solver::Options, default false; the reference's default.yaml sets true
+  int max_consecutive_nonmonotonic_steps = 5;
   bool verbose = false;
+};
+
+// ceres::internal::TrustRegionStepEvaluator (trust_region_step_evaluator.cc; Conn, Gould & Toint, algorithm 10.1.2).
+// max_consecutive_nonmonotonic_steps == 0 is the monotonic minimizer: the reference iterate is reset on every accepted step.
+struct StepEvaluator {
+  int max_nonmonotonic;
+  double minimum_cost, current_cost, reference_cost, candidate_cost;
+  double acc_reference_model_cost_change = 0.0, acc_candidate_model_cost_change = 0.0;
+  int num_consecutive_nonmonotonic_steps = 0;
+  StepEvaluator(double initial_cost, int max_nm)
+      : max_nonmonotonic(max_nm), minimum_cost(initial_cost), current_cost(initial_cost), reference_cost(initial_cost),
+        candidate_cost(initial_cost) {}
+  double StepQuality(double cost, double model_cost_change) const {
+    if (cost >= std::numeric_limits<double>::max()) return std::numeric_limits<double>::lowest();
+    const double relative_decrease = (current_cost - cost) / model_cost_change;
+    const double historical_relative_decrease = (reference_cost - cost) / (acc_reference_model_cost_change + model_cost_change);
+    return std::max(relative_decrease, historical_relative_decrease);
+  }
+  void StepAccepted(double cost, double model_cost_change) {
+    current_cost = cost;
+    acc_candidate_model_cost_change += model_cost_change;
+    acc_reference_model_cost_change += model_cost_change;
+    if (current_cost < minimum_cost) {
+      minimum_cost = current_cost;
+      num_consecutive_nonmonotonic_steps = 0;
+      candidate_cost = current_cost;
+      acc_candidate_model_cost_change = 0.0;
+    } else {
+      ++num_consecutive_nonmonotonic_steps;
+      if (current_cost > candidate_cost) { candidate_cost = current_cost; acc_candidate_model_cost_change = 0.0; }
+    }
+    if (num_consecutive_nonmonotonic_steps == max_nonmonotonic) {
+      reference_cost = candidate_cost;
+      acc_reference_model_cost_change = acc_candidate_model_cost_change;
+    }
+  }
 };
 
 struct TRIteration {
@@ -202,9 +240,7 @@ class TrustRegionMinimizer {
     sum->initial_cost = x_cost;
     double minimum_cost = x_cost;
     std::vector<double> best_x = x;
-    // step evaluator (monotonic)
-    double current_cost = x_cost;
-    bool last_successful = false;
+    StepEvaluator step_evaluator(x_cost, opt.use_nonmonotonic_steps ? opt.max_consecutive_nonmonotonic_steps : 0);
 
     auto finalize = [&]() -> bool {  // FinalizeIterationAndCheckIfMinimizerCanContinue
       if (it.step_is_successful) {
@@ -224,7 +260,6 @@ class TrustRegionMinimizer {
       if (radius < opt.min_trust_region_radius) { sum->termination_type = 0; sum->message = "Minimum trust region radius reached."; return false; }
       return true;
     };
-    (void)last_successful;
 
     while (finalize()) {
       const double previous_gradient_max_norm = it.gradient_max_norm;
@@ -304,7 +339,7 @@ class TrustRegionMinimizer {
         break;
       }
       // ---- IsStepSuccessful
-      it.relative_decrease = (current_cost - candidate_cost) / model_cost_change;
+      it.relative_decrease = step_evaluator.StepQuality(candidate_cost, model_cost_change);
       const bool ok = inner_were_useful || it.relative_decrease > opt.min_relative_decrease;
       if (ok) {
         // ---- HandleSuccessfulStep
@@ -319,7 +354,7 @@ class TrustRegionMinimizer {
         radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
         radius = std::min(opt.max_trust_region_radius, radius);
         decrease_factor = 2.0;
-        current_cost = candidate_cost;  // TrustRegionStepEvaluator::StepAccepted (monotonic)
+        step_evaluator.StepAccepted(candidate_cost, model_cost_change);
       } else {
         it.step_is_successful = false;
         it.cost = candidate_cost;

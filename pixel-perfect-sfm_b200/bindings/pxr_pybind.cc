@@ -119,11 +119,20 @@ void apply_options(pxr_solver_options& o, const py::dict& c) {
   getd("function_tolerance", o.function_tolerance); getd("gradient_tolerance", o.gradient_tolerance);
   getd("parameter_tolerance", o.parameter_tolerance); geti("use_inner_iterations", o.use_inner_iterations);
   getd("initial_trust_region_radius", o.initial_trust_region_radius);
+  getd("inner_iteration_tolerance", o.inner_iteration_tolerance); getd("max_trust_region_radius", o.max_trust_region_radius);
+  getd("min_trust_region_radius", o.min_trust_region_radius); getd("min_relative_decrease", o.min_relative_decrease);
+  getd("min_lm_diagonal", o.min_lm_diagonal); getd("max_lm_diagonal", o.max_lm_diagonal);
+  geti("jacobi_scaling", o.jacobi_scaling); geti("deterministic", o.deterministic);
+  geti("use_nonmonotonic_steps", o.use_nonmonotonic_steps);
+  geti("max_consecutive_nonmonotonic_steps", o.max_consecutive_nonmonotonic_steps);
   for (auto item : c) {
     const std::string k = py::str(item.first);
     static const char* known[] = {"loss_type", "loss_scale", "linear_solver", "max_num_iterations", "max_linear_solver_iterations",
                                   "max_num_consecutive_invalid_steps", "function_tolerance", "gradient_tolerance",
-                                  "parameter_tolerance", "use_inner_iterations", "initial_trust_region_radius"};
+                                  "parameter_tolerance", "use_inner_iterations", "initial_trust_region_radius",
+                                  "inner_iteration_tolerance", "max_trust_region_radius", "min_trust_region_radius",
+                                  "min_relative_decrease", "min_lm_diagonal", "max_lm_diagonal", "jacobi_scaling",
+                                  "deterministic", "use_nonmonotonic_steps", "max_consecutive_nonmonotonic_steps"};
     bool ok = false;
     for (const char* n : known) ok = ok || k == n;
     if (!ok) throw py::value_error("unknown solver option '" + k + "'");   // strict keys, like _pixsfm/src/helpers.h:149-232

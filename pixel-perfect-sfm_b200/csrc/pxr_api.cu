@@ -201,6 +201,7 @@ void pxr_default_ba_options(pxr_solver_options* o) {
   o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1; o->deterministic = 0;
+  o->use_nonmonotonic_steps = 0; o->max_consecutive_nonmonotonic_steps = 5;
 }
 void pxr_default_ka_options(pxr_solver_options* o) {
   pxr_default_ba_options(o);

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstring>
 #include <limits>
+#include <memory>
 
 #include "pxr_ba_host.h"
 
@@ -528,7 +529,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   cudaStream_t s = ctx->stream;
   PXR_TRY(build_schur_pairs());
   BADev d = dev();
-  StageScope* st = new StageScope(this, 4);
+  std::unique_ptr<StageScope> st(new StageScope(this, 4));   // RAII: an early error return still closes the stage
   if (nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, D2.p, nl, radius,
                          opt.min_lm_diagonal, opt.max_lm_diagonal);
   PXR_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), s));
@@ -562,7 +563,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     PXR_CUDA(cudaMemcpyAsync(rhs.p, S.p + (size_t)nc * nc, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));   // PCG / debug read rhs
   }
   }
-  delete st; st = new StageScope(this, 5);
+  st.reset(); st.reset(new StageScope(this, 5));
   last_linear_iterations = 1;
   if (nc > 0 && sparse_schur) {
     PXR_TRY(pcg_solve_sparse());
@@ -588,6 +589,8 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
       }
       cudaGraph_t graph = nullptr;
       PXR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      // an error between Begin and EndCapture must not leave the context's stream capturing
+      struct CaptureGuard { cudaStream_t s; bool armed = true; ~CaptureGuard() { if (armed) { cudaGraph_t g = nullptr; cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); } } } cap_guard{s};
       const int nb = (int)cdiv(nc, kNB);
       int64_t captured = 0;
       if (!chol_multikernel) {
@@ -611,6 +614,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
       }
       chol_backsolve_kernel<<<1, 1024, 0, s>>>(S.p, S.p + (size_t)nc * nc, delta.p, nc); ++captured;
       }
+      cap_guard.armed = false;
       PXR_CUDA(cudaStreamEndCapture(s, &graph));
       PXR_CUDA(cudaGraphInstantiate(&chol_graph_exec, graph, 0));
       cudaGraphDestroy(graph);
@@ -631,7 +635,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
       }
     }
   }
-  delete st; st = new StageScope(this, 7);
+  st.reset(); st.reset(new StageScope(this, 7));
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
   if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p);
   if (n_obs > 0) {
@@ -639,7 +643,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     else PXR_LAUNCH(ctx, ba_model_cost_kernel<false>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
   }
   PXR_CUDA(cudaGetLastError());
-  delete st;
+  st.reset();
   double acc = 0, fld = 0;
   if (chol_graph_exec && !chol_multikernel && !use_pcg && env.chol_test_abort) {
     // test hook: pretend the persistent kernel bailed out of a wait (abort word + failure flag)
@@ -942,7 +946,9 @@ int BA::lm_begin() {
   std::memset(&lm.it, 0, sizeof(lm.it));
   lm.it.cost = lm.x_cost;
   PXR_TRY(gradient_max_norm(&lm.it.gradient_max_norm));
-  lm.initial_cost = lm.minimum_cost = lm.current_cost = lm.x_cost;
+  lm.initial_cost = lm.minimum_cost = lm.x_cost;
+  lm.ev.init(lm.x_cost, opt.use_nonmonotonic_steps ? opt.max_consecutive_nonmonotonic_steps : 0);
+  lm.best_is_current = true;
   lm.started = true;
   lm.pending_finalize = true;
   lm.term = 1;
@@ -954,8 +960,12 @@ int BA::lm_begin() {
 bool BA::lm_finalize(int max_iteration) {
   pxr_iteration_summary& it = lm.it;
   if (lm.pending_finalize) {
-    if (it.step_is_successful) { ++lm.n_succ; if (lm.x_cost < lm.minimum_cost) lm.minimum_cost = lm.x_cost; }
-    else if (it.iteration > 0) ++lm.n_unsucc;
+    if (it.step_is_successful) {
+      // ceres copies x into the user's parameters only when it is the best iterate so far; with monotonic steps every
+      // accepted iterate is, with use_nonmonotonic_steps the best one is snapshotted on the device
+      ++lm.n_succ;
+      if (lm.x_cost < lm.minimum_cost) lm.minimum_cost = lm.x_cost;
+    } else if (it.iteration > 0) ++lm.n_unsucc;
     it.trust_region_radius = lm.radius;
     it.iteration_time_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - lm.it_start).count();
     lm.its.push_back(it);
@@ -1057,7 +1067,7 @@ int BA::lm_iterate(int max_iteration) {
     if (std::fabs(it.cost_change) <= opt.function_tolerance * lm.x_cost) {
       lm.term = 0; lm.message = "Function tolerance reached."; lm.finished = true; break;
     }
-    it.relative_decrease = (lm.current_cost - candidate_cost) / model_cost_change;
+    it.relative_decrease = lm.ev.quality(candidate_cost, model_cost_change);
     const bool ok = inner_useful || it.relative_decrease > opt.min_relative_decrease;
     if (ok) {
       cur = 1 - cur;
@@ -1074,7 +1084,14 @@ int BA::lm_iterate(int max_iteration) {
       lm.radius = lm.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
       lm.radius = std::min(opt.max_trust_region_radius, lm.radius);
       lm.decrease_factor = 2.0;
-      lm.current_cost = candidate_cost;
+      lm.ev.accepted(candidate_cost, model_cost_change);
+      if (opt.use_nonmonotonic_steps) {
+        // ceres copies x into the user's parameter blocks only when it is the best iterate so far
+        // (FinalizeIterationAndCheckIfMinimizerCanContinue); a non-monotonic acceptance moves away from it, so the
+        // iterate being left (still intact in the other parameter set) is snapshotted on the device
+        if (lm.x_cost < lm.minimum_cost) lm.best_is_current = true;
+        else if (lm.best_is_current) { PXR_TRY(save_best(1 - cur)); lm.best_is_current = false; }
+      }
     } else {
       it.step_is_successful = 0;
       it.cost = candidate_cost;
@@ -1111,12 +1128,29 @@ int BA::solve(pxr_summary* sum) {
   return PXR_OK;
 }
 
+int BA::save_best(int set) {
+  cudaStream_t s = ctx->stream;
+  if (!best_cam.p) {
+    PXR_TRY(best_cam.alloc((size_t)n_cameras * kMaxK)); PXR_TRY(best_q.alloc((size_t)n_images * 4));
+    PXR_TRY(best_t.alloc((size_t)n_images * 3)); PXR_TRY(best_X.alloc((size_t)n_points * 3));
+  }
+  PXR_CUDA(cudaMemcpyAsync(best_cam.p, cam[set].p, best_cam.n * 8, cudaMemcpyDeviceToDevice, s));
+  PXR_CUDA(cudaMemcpyAsync(best_q.p, q[set].p, best_q.n * 8, cudaMemcpyDeviceToDevice, s));
+  PXR_CUDA(cudaMemcpyAsync(best_t.p, t[set].p, best_t.n * 8, cudaMemcpyDeviceToDevice, s));
+  if (best_X.n) PXR_CUDA(cudaMemcpyAsync(best_X.p, X[set].p, best_X.n * 8, cudaMemcpyDeviceToDevice, s));
+  return PXR_OK;
+}
+
 int BA::read_params(double* cam_o, double* q_o, double* t_o, double* X_o) {
   cudaStream_t s = ctx->stream;
-  if (cam_o) PXR_CUDA(cudaMemcpyAsync(cam_o, cam[cur].p, (size_t)n_cameras * kMaxK * 8, cudaMemcpyDeviceToHost, s));
-  if (q_o) PXR_CUDA(cudaMemcpyAsync(q_o, q[cur].p, (size_t)n_images * 4 * 8, cudaMemcpyDeviceToHost, s));
-  if (t_o) PXR_CUDA(cudaMemcpyAsync(t_o, t[cur].p, (size_t)n_images * 3 * 8, cudaMemcpyDeviceToHost, s));
-  if (X_o) PXR_CUDA(cudaMemcpyAsync(X_o, X[cur].p, (size_t)n_points * 3 * 8, cudaMemcpyDeviceToHost, s));
+  // the lowest-cost iterate, as ceres leaves it in the user's parameter blocks
+  const bool best = lm.started && !lm.best_is_current && best_cam.p;
+  const double* pc = best ? best_cam.p : cam[cur].p; const double* pq = best ? best_q.p : q[cur].p;
+  const double* pt = best ? best_t.p : t[cur].p; const double* pX = best ? best_X.p : X[cur].p;
+  if (cam_o) PXR_CUDA(cudaMemcpyAsync(cam_o, pc, (size_t)n_cameras * kMaxK * 8, cudaMemcpyDeviceToHost, s));
+  if (q_o) PXR_CUDA(cudaMemcpyAsync(q_o, pq, (size_t)n_images * 4 * 8, cudaMemcpyDeviceToHost, s));
+  if (t_o) PXR_CUDA(cudaMemcpyAsync(t_o, pt, (size_t)n_images * 3 * 8, cudaMemcpyDeviceToHost, s));
+  if (X_o) PXR_CUDA(cudaMemcpyAsync(X_o, pX, (size_t)n_points * 3 * 8, cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaStreamSynchronize(s));
   return PXR_OK;
 }

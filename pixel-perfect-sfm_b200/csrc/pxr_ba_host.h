@@ -3,6 +3,8 @@
 #include <chrono>
 #include <string>
 #include <functional>
+#include <limits>
+#include <algorithm>
 #include <utility>
 #include <vector>
 
@@ -22,9 +24,30 @@ int fm_max_partials(pxr_ctx* ctx);
 int launch_fm_eval(pxr_ctx* ctx, int dtype, int C, int mode, bool float_simd, const FmEvalArgs& a, int* n_partials);
 int launch_inner(pxr_ctx* ctx, int dtype, int C, bool float_simd, const InnerArgs& a);
 
+// ceres::internal::TrustRegionStepEvaluator (Conn, Gould & Toint, algorithm 10.1.2); max_nonmonotonic == 0 is the
+// monotonic minimizer.  Same arithmetic as oracle/orc_trust_region.h::StepEvaluator.
+struct StepEvaluator {
+  int max_nonmonotonic = 0, num_consecutive_nonmonotonic_steps = 0;
+  double minimum_cost = 0, current_cost = 0, reference_cost = 0, candidate_cost = 0;
+  double acc_reference = 0, acc_candidate = 0;
+  void init(double c, int max_nm) { *this = StepEvaluator(); max_nonmonotonic = max_nm; minimum_cost = current_cost = reference_cost = candidate_cost = c; }
+  double quality(double cost, double mcc) const {
+    if (cost >= std::numeric_limits<double>::max()) return std::numeric_limits<double>::lowest();
+    return std::max((current_cost - cost) / mcc, (reference_cost - cost) / (acc_reference + mcc));
+  }
+  void accepted(double cost, double mcc) {
+    current_cost = cost; acc_candidate += mcc; acc_reference += mcc;
+    if (current_cost < minimum_cost) { minimum_cost = current_cost; num_consecutive_nonmonotonic_steps = 0; candidate_cost = current_cost; acc_candidate = 0; }
+    else { ++num_consecutive_nonmonotonic_steps; if (current_cost > candidate_cost) { candidate_cost = current_cost; acc_candidate = 0; } }
+    if (num_consecutive_nonmonotonic_steps == max_nonmonotonic) { reference_cost = candidate_cost; acc_reference = acc_candidate; }
+  }
+};
+
 struct LMState {
   bool started = false, finished = false, pending_finalize = false, inner_enabled = false;
-  double x_cost = 0, radius = 1e4, decrease_factor = 2.0, initial_cost = 0, minimum_cost = 0, current_cost = 0;
+  StepEvaluator ev;
+  bool best_is_current = true;     // non-monotonic steps: the lowest-cost iterate lives in BA::best_* when false
+  double x_cost = 0, radius = 1e4, decrease_factor = 2.0, initial_cost = 0, minimum_cost = 0;
   int num_invalid = 0, n_succ = 0, n_unsucc = 0, n_inner = 0, term = 1;
   pxr_iteration_summary it;
   std::vector<pxr_iteration_summary> its;
@@ -69,6 +92,8 @@ struct BA {
   const uint8_t* d_patches = nullptr;
   // device: parameters (two sets: current / candidate)
   DevBuf<double> cam[2], q[2], t[2], X[2];
+  DevBuf<double> best_cam, best_q, best_t, best_X;   // use_nonmonotonic_steps: snapshot of the lowest-cost iterate
+  int save_best(int set);
   int cur = 0;
   // device: per-observation and linearisation
   // uv/obs_out/juv hold the linearisation at the CURRENT point; every trial-point evaluation (cost-only,

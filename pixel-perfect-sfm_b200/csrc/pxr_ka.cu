@@ -46,6 +46,7 @@ struct KAArgs {
   int max_iter, max_invalid;
   double ftol, gtol, ptol, min_rel_dec, radius0, max_radius, min_radius, min_diag, max_diag;
   int jacobi_scaling;
+  int max_nonmonotonic;             // 0: monotonic steps; > 0: use_nonmonotonic_steps with this many consecutive ones
   // outputs per problem: initial cost, final cost, iterations, successful, unsuccessful, termination
   double* prob_out;                 // [P][6]
   // query mode (REF): every edge is (keypoint e_k1, fixed descriptor ref_desc[e_k2]); block-diagonal normal equations,
@@ -426,6 +427,11 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
   }
   __syncthreads();
   int iter = 0, invalid = 0, n_succ = 0, n_unsucc = 0, term = 1;
+  // ceres TrustRegionStepEvaluator (uniform over the CTA: every input is a block-wide reduction); max_nonmonotonic == 0
+  // reproduces the monotonic rule  rel = (current_cost - candidate_cost) / mcc  bit for bit
+  double ev_min = x_cost, ev_ref = x_cost, ev_cand = x_cost, ev_acc_ref = 0.0, ev_acc_cand = 0.0;
+  int ev_nonmono = 0;
+  double minimum_cost = x_cost;     // ceres keeps the lowest-cost iterate in the user's parameter blocks
   while (true) {
     // FinalizeIterationAndCheckIfMinimizerCanContinue
     if (w.ctrl[C_STOP] != 0.0) { term = 2; break; }
@@ -558,7 +564,9 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
     double sn = 0; { double v = 0; for (int i = tid; i < n; i += kKAThreads) { const double d = w.x[i] - w.cand[i]; v += d * d; } sn = sqrt(block_sum(v)); }
     if (sn <= a.ptol * (w.ctrl[C_XNORM] + a.ptol)) { term = 0; break; }            // parameter tolerance: step not applied
     if (fabs(x_cost - candidate_cost) <= a.ftol * x_cost) { term = 0; break; }     // function tolerance: step not applied
-    const double rel = (w.ctrl[C_CURCOST] - candidate_cost) / mcc;
+    double rel = (w.ctrl[C_CURCOST] - candidate_cost) / mcc;
+    if (candidate_cost >= 1.7976931348623157e308) rel = -1.7976931348623157e308;
+    else if (a.max_nonmonotonic > 0) rel = fmax(rel, (ev_ref - candidate_cost) / (ev_acc_ref + mcc));
     if (rel > a.min_rel_dec) {
       __syncthreads();
       for (int i = tid; i < n; i += kKAThreads) w.x[i] = w.cand[i];
@@ -572,6 +580,16 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
         w.ctrl[C_DECF] = 2.0; w.ctrl[C_CURCOST] = candidate_cost; w.ctrl[C_XCOST] = x_cost;
       }
       ++n_succ;
+      if (a.max_nonmonotonic > 0) {
+        ev_acc_cand += mcc; ev_acc_ref += mcc;
+        if (candidate_cost < ev_min) { ev_min = candidate_cost; ev_nonmono = 0; ev_cand = candidate_cost; ev_acc_cand = 0.0; }
+        else { ++ev_nonmono; if (candidate_cost > ev_cand) { ev_cand = candidate_cost; ev_acc_cand = 0.0; } }
+        if (ev_nonmono == a.max_nonmonotonic) { ev_ref = ev_cand; ev_acc_ref = ev_acc_cand; }
+        if (x_cost < minimum_cost) {    // new best iterate: it goes to the output right away
+          minimum_cost = x_cost;
+          for (int i = tid; i < n; i += kKAThreads) a.keypoints[2 * a.var_kp[vb + i / 2] + (i & 1)] = w.x[i];
+        }
+      }
     } else {
       __syncthreads();
       if (tid == 0) { w.ctrl[C_RADIUS] /= w.ctrl[C_DECF]; w.ctrl[C_DECF] *= 2.0; }
@@ -580,7 +598,9 @@ __global__ void __launch_bounds__(kKAThreads) ka_solve_kernel(KAArgs a) {
     __syncthreads();
   }
   __syncthreads();
-  for (int i = tid; i < n; i += kKAThreads) a.keypoints[2 * a.var_kp[vb + i / 2] + (i & 1)] = w.x[i];
+  if (a.max_nonmonotonic == 0) {   // monotonic: the last accepted iterate is the best one
+    for (int i = tid; i < n; i += kKAThreads) a.keypoints[2 * a.var_kp[vb + i / 2] + (i & 1)] = w.x[i];
+  } else x_cost = minimum_cost;
   if (tid == 0) { out[1] = x_cost; out[2] = iter; out[3] = n_succ; out[4] = n_unsucc; out[5] = term; }
 }
 
@@ -754,6 +774,7 @@ extern "C" int pxr_ka_run(pxr_ctx* ctx, const pxr_ka_desc* d, const pxr_interp_c
   a.min_rel_dec = so.min_relative_decrease; a.radius0 = so.initial_trust_region_radius; a.max_radius = so.max_trust_region_radius;
   a.min_radius = so.min_trust_region_radius; a.min_diag = so.min_lm_diagonal; a.max_diag = so.max_lm_diagonal;
   a.jacobi_scaling = so.jacobi_scaling; a.prob_out = d_out.p; a.n_max = n_max;
+  a.max_nonmonotonic = so.use_nonmonotonic_steps ? std::max(0, so.max_consecutive_nonmonotonic_steps) : 0;
   // query mode: block-diagonal workspace in global memory, 26 doubles per variable keypoint
   DevBuf<double> d_ref, d_ws;
   DevBuf<int64_t> d_wsoff;

@@ -106,8 +106,6 @@ def solver_options_from(loss, solver, base):
     for k, v in solver.items():
         if k not in _SOLVER_KEYS:
             raise ValueError("solver: unknown option '%s'" % k)
-        if k == "use_nonmonotonic_steps" and v:
-            raise ValueError("use_nonmonotonic_steps=True is not supported on the B200 path")
         if hasattr(o, k) and k != "callbacks":
             setattr(o, k, type(getattr(o, k))(v))
     return o

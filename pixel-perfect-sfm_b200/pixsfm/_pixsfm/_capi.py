@@ -48,7 +48,8 @@ class SolverOptions(C.Structure):
                 ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
                 ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int32),
-                ("deterministic", C.c_int32)]
+                ("deterministic", C.c_int32), ("use_nonmonotonic_steps", C.c_int32),
+                ("max_consecutive_nonmonotonic_steps", C.c_int32)]
 
 
 class CostmapConfig(C.Structure):
@@ -148,7 +149,8 @@ def default_ba_options(**kw):
                       use_inner_iterations=1, inner_iteration_tolerance=1e-3,
                       initial_trust_region_radius=1e4, max_trust_region_radius=1e16,
                       min_trust_region_radius=1e-32, min_relative_decrease=1e-3,
-                      min_lm_diagonal=1e-6, max_lm_diagonal=1e32, jacobi_scaling=1, deterministic=0)
+                      min_lm_diagonal=1e-6, max_lm_diagonal=1e32, jacobi_scaling=1, deterministic=0,
+                      use_nonmonotonic_steps=0, max_consecutive_nonmonotonic_steps=5)
     for k, v in kw.items():
         setattr(o, k, v)
     return o

@@ -57,8 +57,20 @@ def dense_to_fmap_on_device(featuremap, image_size, keypoints, keypoint_ids=None
     elif len(keypoint_ids) != len(keypoints):
         raise ValueError("Number of provided keypoint_ids and keypoints do not match.")
     scale = np.array((w / image_size[0], h / image_size[1]))
-    corners = patch_corners(keypoints, scale, patch_size, (w, h))
     source = featuremap if cai is not None else _as_numpy(featuremap)
+    if cai is None and source.ndim == 4:
+        source = source[0]
+    if h * w <= len(keypoints) * patch_size * patch_size:
+        # sparse does not pay off (reference tensor_to_fmap, features/extractor.py:182-187, same rule as dense_to_fmap):
+        # ONE dense patch, normalised / cast / transposed to HWC by the same gather kernel with a single h x w window.
+        # pxr_extract_patches takes square windows, so a non-square map goes through the host path.
+        if h != w:
+            return dense_to_fmap(_as_numpy(featuremap), image_size, keypoints, keypoint_ids, patch_size, True, l2_normalize,
+                                 dtype, channels_first)
+        slab = _engine.extract_patches(source, np.zeros((1, 2), np.int32), h, l2_normalize, dtype, channels_first)
+        return features.FeatureMap(slab, [features.kDenseId], np.zeros((1, 2), np.int32),
+                                   {"scale": scale, "is_sparse": False, "patch_size": patch_size})
+    corners = patch_corners(keypoints, scale, patch_size, (w, h))
     slab = _engine.extract_patches(source, corners, patch_size, l2_normalize, dtype, channels_first)
     return features.FeatureMap(slab, keypoint_ids, corners, {"scale": scale, "is_sparse": True, "patch_size": patch_size})
 

@@ -86,11 +86,17 @@ def test_device_patch_gather_matches_the_host_extraction():
     rng = np.random.default_rng(7)
     C, H, W, ps = 128, 96, 96, 16
     chw = rng.normal(size=(C, H, W)).astype(np.float32)
-    kps = rng.uniform(-10, 400, (300, 2))
+    # 30 patches of 16 x 16 px are smaller than the 96 x 96 map: the reference's "sparse pays off" rule keeps the sparse
+    # branch (features/extractor.py:182-187); out-of-image keypoints exercise the corner clamp (:192-193)
+    n_kp = 30
+    assert n_kp * ps * ps < H * W
+    kps = rng.uniform(-10, 400, (n_kp, 2))
     corners = patch_corners(kps, np.array([W / 384.0, H / 384.0]), ps, (W, H))
-    want = dense_to_fmap(chw, (384, 384), kps, patch_size=ps).patches              # fp16, L2-normalised
+    fm_want = dense_to_fmap(chw, (384, 384), kps, patch_size=ps)
+    assert fm_want.is_sparse
+    want = fm_want.patches                                                         # fp16, L2-normalised
     got = _engine.extract_patches(chw, corners, ps, l2_normalize=True, out_dtype=np.float16, to_host=True)
-    assert got.shape == want.shape == (300, ps, ps, C) and got.dtype == np.float16
+    assert got.shape == want.shape == (n_kp, ps, ps, C) and got.dtype == np.float16
     diff = np.abs(got.astype(np.float32) - want.astype(np.float32))
     assert diff.max() <= 2.0 ** -11 and np.mean(got == want) > 0.99              # <= 1 fp16 ulp at |v| < 1, almost all equal
     # no normalisation, same dtype: a pure gather, bit for bit; [H,W,C] layout too
@@ -107,10 +113,17 @@ def test_device_patch_gather_matches_the_host_extraction():
         _engine.extract_patches(chw, np.array([[W - ps + 1, 0]], np.int32), ps, to_host=True)      # leaves the map
     assert _engine.extract_patches(chw, np.zeros((0, 2), np.int32), ps, to_host=True).shape == (0, ps, ps, C)
     # FeatureMap built on the device: same metadata as the host one, patches device-resident
-    fm_dev = dense_to_fmap_on_device(chw, (384, 384), kps, list(range(1000, 1300)), patch_size=ps)
-    fm_host = dense_to_fmap(chw, (384, 384), kps, list(range(1000, 1300)), patch_size=ps)
-    assert fm_dev.is_sparse and fm_dev.point2D_ids == fm_host.point2D_ids and np.array_equal(fm_dev.corners, fm_host.corners)
+    ids = list(range(1000, 1000 + n_kp))
+    fm_dev = dense_to_fmap_on_device(chw, (384, 384), kps, ids, patch_size=ps)
+    fm_host = dense_to_fmap(chw, (384, 384), kps, ids, patch_size=ps)
+    assert fm_dev.is_sparse and fm_host.is_sparse
+    assert fm_dev.point2D_ids == fm_host.point2D_ids and np.array_equal(fm_dev.corners, fm_host.corners)
     assert np.array_equal(fm_dev.scale, fm_host.scale) and fm_dev.patches.shape == fm_host.patches.shape
+    # semi-dense keypoints: sparse does not pay off -> both paths keep ONE dense patch (kDenseId), as tensor_to_fmap does
+    many = rng.uniform(0, 384, (300, 2))
+    fd, fh = dense_to_fmap_on_device(chw, (384, 384), many, patch_size=ps), dense_to_fmap(chw, (384, 384), many, patch_size=ps)
+    assert not fd.is_sparse and not fh.is_sparse and fd.patches.shape == fh.patches.shape == (1, H, W, C)
+    assert fd.point2D_ids == fh.point2D_ids
 
 
 def test_patch_interpolator_on_the_device_matches_the_oracle():
