@@ -59,7 +59,7 @@ def host_memory_available():
 
 
 # the CPU baseline uses OpenMP: no busy-waiting worker threads, bind nothing
-os.environ.setdefault("NCCL_DEBUG", "WARN")   # the driver may ask for INFO (rank proof); stdout stays the one JSON line either way (NCCL logs to stderr... see below)
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # never override what the launcher asked for (NCCL_DEBUG=INFO is the driver's rank proof)
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
 
