@@ -219,6 +219,11 @@ int pxr_ctx_destroy(pxr_ctx* ctx);
 int pxr_nccl_unique_id(void* id128);
 int pxr_ctx_init_comm(pxr_ctx* ctx, int rank, int world, const void* id128);
 int pxr_ctx_sync(pxr_ctx* ctx);
+/* NCCL collectives issued through this context so far (bench.py divides by the LM iterations it timed: the contract is
+ * ONE all-reduce of the reduced camera blocks per LM iteration), and whether the per-iteration SCALAR exchange runs over
+ * peer memory (cudaIpc-mapped mailboxes over NVLink, 1) or had to fall back to NCCL (0). */
+int64_t pxr_ctx_nccl_collectives(pxr_ctx* ctx);
+int pxr_ctx_mailbox_ready(pxr_ctx* ctx);
 /* CUDA-event stopwatch on the library stream (bench.py times K LM iterations with it) */
 int pxr_ctx_timer_start(pxr_ctx* ctx);
 int pxr_ctx_timer_stop(pxr_ctx* ctx, double* elapsed_ms);

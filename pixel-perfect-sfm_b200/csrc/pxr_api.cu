@@ -42,6 +42,7 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   void* InitRank = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -56,6 +57,7 @@ static int load_nccl() {
   g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
   g_nccl.InitRank = dlsym(h, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.InitRank || !g_nccl.AllReduce)
@@ -68,6 +70,149 @@ int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count, bool max_op) {
   // ncclFloat64 = 8, ncclSum = 0, ncclMax = 2
   const int rc = g_nccl.AllReduce(dptr, dptr, count, 8, max_op ? 2 : 0, ctx->nccl_comm, ctx->stream);
   if (rc != 0) return fail(PXR_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  ctx->nccl_collectives++;
+  return PXR_OK;
+}
+
+int allreduce_f64_oop(pxr_ctx* ctx, const double* send, double* recv, size_t count) {
+  if (count == 0) return PXR_OK;
+  if (!ctx->nccl_comm || ctx->world <= 1) {
+    if (send != recv) PXR_CUDA(cudaMemcpyAsync(recv, send, count * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return PXR_OK;
+  }
+  const int rc = g_nccl.AllReduce(send, recv, count, 8, 0, ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return fail(PXR_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  ctx->nccl_collectives++;
+  return PXR_OK;
+}
+
+int allgather_bytes(pxr_ctx* ctx, const void* send_dev, void* recv_dev, size_t bytes) {
+  if (ctx->world <= 1 || !ctx->nccl_comm) {
+    if (bytes) PXR_CUDA(cudaMemcpyAsync(recv_dev, send_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return PXR_OK;
+  }
+  if (!g_nccl.AllGather) return fail(PXR_ERR_NCCL, "libnccl.so.2 lacks ncclAllGather");
+  if (bytes == 0) return PXR_OK;
+  const int rc = g_nccl.AllGather(send_dev, recv_dev, bytes, 0 /* ncclInt8 */, ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return fail(PXR_ERR_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  ctx->nccl_collectives++;
+  return PXR_OK;
+}
+
+// ---- peer mailboxes -------------------------------------------------------------------------------------------
+// One launch, one warp: lane q < world writes this rank's payload into rank q's mailbox row [parity][rank] (peer
+// memory over NVLink, or local memory for q == rank), fences, then publishes the epoch in q's sequence word with a
+// system-scope release.  Lane q then acquires "source q has delivered epoch e" from the local sequence words and lane 0
+// folds the `world` rows in rank order.  Two parities: a rank can only start epoch e+2 after every peer has SENT e+1,
+// i.e. after every peer finished READING e, so the row of parity (e & 1) is free again.
+struct MboxArgs {
+  double* peer[16]; unsigned long long* seq_peer[16];
+  const double* local; const unsigned long long* seq_local;
+  const double* payload; double* out;
+  int rank, world, n_sum, n_max;
+  unsigned long long epoch;
+  int* fail_flag;
+};
+static __global__ void __launch_bounds__(32) mailbox_exchange_kernel(MboxArgs a) {
+  const int q = threadIdx.x;
+  const int n = a.n_sum + a.n_max;
+  const int par = (int)(a.epoch & 1ull);
+  if (q < a.world) {
+    double* dst = a.peer[q] + ((size_t)par * a.world + a.rank) * kMboxSlots;
+    for (int i = 0; i < n; ++i) dst[i] = a.payload[i];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.seq_peer[q] + a.rank), "l"(a.epoch) : "memory");
+    // wait for source q
+    const unsigned long long* sq = a.seq_local + q;
+    long long start = 0; unsigned spins = 0; bool ok = true;
+    while (true) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(sq) : "memory");
+      if (v >= a.epoch) break;
+      if ((++spins & 255u) == 0) {
+        const long long now = clock64();
+        if (start == 0) start = now;
+        else if (now - start > 40000000000LL) { ok = false; break; }     // ~20 s: a peer died; fail instead of hanging
+      }
+    }
+    if (!ok) *a.fail_flag = 1;
+  }
+  __syncwarp();
+  if (q == 0) {
+    // lane 0 re-acquires every sequence word itself (they are all up): its reads below are ordered after the peers' writes
+    for (int r = 0; r < a.world; ++r) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.seq_local + r) : "memory");
+      (void)v;
+    }
+    const double* rows = a.local + (size_t)par * a.world * kMboxSlots;
+    for (int i = 0; i < n; ++i) {
+      double v = __ldcv(rows + i);
+      for (int r = 1; r < a.world; ++r) {
+        const double w = __ldcv(rows + (size_t)r * kMboxSlots + i);
+        v = i < a.n_sum ? v + w : fmax(v, w);
+      }
+      a.out[i] = v;
+    }
+  }
+}
+
+static int mailbox_setup(pxr_ctx* ctx) {
+  if (ctx->mbox_ready) return PXR_OK;
+  const int world = ctx->world;
+  if (world > 16) return fail(PXR_ERR_UNSUPPORTED, "peer mailboxes support up to 16 ranks per node");
+  const size_t nb = (size_t)2 * world * kMboxSlots * sizeof(double), ns = (size_t)world * sizeof(unsigned long long);
+  PXR_CUDA(cudaMalloc((void**)&ctx->mbox_local, nb));
+  PXR_CUDA(cudaMalloc((void**)&ctx->mbox_seq_local, ns));
+  PXR_CUDA(cudaMemset(ctx->mbox_local, 0, nb));
+  PXR_CUDA(cudaMemset(ctx->mbox_seq_local, 0, ns));
+  PXR_CUDA(cudaDeviceSynchronize());
+  for (int r = 0; r < 16; ++r) { ctx->mbox_peer[r] = nullptr; ctx->mbox_seq_peer[r] = nullptr; }
+  ctx->mbox_peer[ctx->rank] = ctx->mbox_local; ctx->mbox_seq_peer[ctx->rank] = ctx->mbox_seq_local;
+  if (world > 1) {
+    // exchange the IPC handles of the two buffers through NCCL itself (no extra host-side plumbing)
+    struct Handles { cudaIpcMemHandle_t box, seq; int device; int pad[3]; };
+    Handles mine;
+    std::memset(&mine, 0, sizeof(mine));
+    PXR_CUDA(cudaIpcGetMemHandle(&mine.box, ctx->mbox_local));
+    PXR_CUDA(cudaIpcGetMemHandle(&mine.seq, ctx->mbox_seq_local));
+    mine.device = ctx->device;
+    DevBuf<uint8_t> d_send, d_recv;
+    PXR_TRY(d_send.alloc(sizeof(Handles))); PXR_TRY(d_recv.alloc(sizeof(Handles) * world));
+    PXR_CUDA(cudaMemcpyAsync(d_send.p, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
+    PXR_TRY(allgather_bytes(ctx, d_send.p, d_recv.p, sizeof(Handles)));
+    std::vector<Handles> all(world);
+    PXR_CUDA(cudaMemcpyAsync(all.data(), d_recv.p, sizeof(Handles) * world, cudaMemcpyDeviceToHost, ctx->stream));
+    PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < world; ++r) {
+      if (r == ctx->rank) continue;
+      int can = 0;
+      PXR_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, all[r].device));
+      if (!can) return fail(PXR_ERR_UNSUPPORTED, "device %d cannot access device %d: peer mailboxes need P2P", ctx->device, all[r].device);
+      void* pb = nullptr; void* ps = nullptr;
+      PXR_CUDA(cudaIpcOpenMemHandle(&pb, all[r].box, cudaIpcMemLazyEnablePeerAccess));
+      PXR_CUDA(cudaIpcOpenMemHandle(&ps, all[r].seq, cudaIpcMemLazyEnablePeerAccess));
+      ctx->mbox_peer[r] = (double*)pb; ctx->mbox_seq_peer[r] = (unsigned long long*)ps;
+    }
+  }
+  ctx->mbox_ready = true;
+  return PXR_OK;
+}
+
+int mailbox_exchange(pxr_ctx* ctx, const double* payload, int n_sum, int n_max, double* out, int* fail_flag) {
+  const int n = n_sum + n_max;
+  if (n <= 0 || n > kMboxSlots) return fail(PXR_ERR_INTERNAL, "mailbox payload of %d slots", n);
+  if (ctx->world <= 1) {
+    if (out != payload) PXR_CUDA(cudaMemcpyAsync(out, payload, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return PXR_OK;
+  }
+  if (!ctx->mbox_ready) return fail(PXR_ERR_INTERNAL, "peer mailboxes are not set up");
+  MboxArgs a;
+  for (int r = 0; r < 16; ++r) { a.peer[r] = ctx->mbox_peer[r]; a.seq_peer[r] = ctx->mbox_seq_peer[r]; }
+  a.local = ctx->mbox_local; a.seq_local = ctx->mbox_seq_local; a.payload = payload; a.out = out;
+  a.rank = ctx->rank; a.world = ctx->world; a.n_sum = n_sum; a.n_max = n_max; a.epoch = ++ctx->mbox_epoch; a.fail_flag = fail_flag;
+  PXR_LAUNCH(ctx, mailbox_exchange_kernel, 1, 32, 0, a);
+  PXR_CUDA(cudaGetLastError());
   return PXR_OK;
 }
 
@@ -139,6 +284,10 @@ int pxr_ctx_destroy(pxr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
   pxr::stager_destroy(ctx);
+  for (int r = 0; r < 16; ++r)
+    if (r != ctx->rank) { if (ctx->mbox_peer[r]) cudaIpcCloseMemHandle(ctx->mbox_peer[r]); if (ctx->mbox_seq_peer[r]) cudaIpcCloseMemHandle(ctx->mbox_seq_peer[r]); }
+  if (ctx->mbox_local) cudaFree(ctx->mbox_local);
+  if (ctx->mbox_seq_local) cudaFree(ctx->mbox_seq_local);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return PXR_OK;
@@ -162,8 +311,18 @@ int pxr_ctx_init_comm(pxr_ctx* ctx, int rank, int world, const void* id128) {
   typedef int (*init_t)(void**, int, Uid128, int);
   const int rc = ((init_t)g_nccl.InitRank)(&ctx->nccl_comm, world, uid, rank);
   if (rc != 0) return fail(PXR_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  // peer mailboxes for the per-iteration scalar exchange (PXR_NO_MAILBOX=1: keep every exchange on NCCL)
+  if (!getenv("PXR_NO_MAILBOX")) {
+    const int mrc = mailbox_setup(ctx);
+    if (mrc != PXR_OK) {
+      // every rank of a node sees the same P2P topology, so all of them fall back together
+      ctx->mbox_ready = false;
+    }
+  }
   return PXR_OK;
 }
+int64_t pxr_ctx_nccl_collectives(pxr_ctx* ctx) { return ctx ? ctx->nccl_collectives : 0; }
+int pxr_ctx_mailbox_ready(pxr_ctx* ctx) { return ctx && ctx->mbox_ready ? 1 : 0; }
 
 int pxr_ctx_sync(pxr_ctx* ctx) {
   if (!ctx) return fail(PXR_ERR_INVALID_ARGUMENT, "ctx is NULL");

@@ -259,17 +259,23 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     }
     h_img_cam.assign(d->img_cam, d->img_cam + n_images);
     // implicit block-sparse reduced system: on request, or when the dense one would not fit comfortably
-    sparse_schur = for_solve && use_pcg && dc_needed <= 8 && n_obs > 0 &&
+    sparse_schur = for_solve && use_pcg && dc_needed <= 8 && (n_obs > 0 || ctx->world > 1) &&
                    (env.pcg_sparse || (int64_t)nc * nc * 8 > (int64_t)4e9);
+    // block mode: image-block assembly + ONE all-reduce per LM iteration (pxr_block.cuh).  Always on with several ranks
+    // (the image tables are replicated, so every rank takes the same decision); PXR_BLOCK_ASSEMBLY=1 runs the same code on
+    // one GPU (tests).  Images with more than 8 camera columns keep the dense multi-collective path.
+    block_mode = for_solve && dc_needed <= 8 && (ctx->world > 1 || getenv("PXR_BLOCK_ASSEMBLY") != nullptr);
+    if (ctx->world > 1 && sparse_schur && !block_mode) sparse_schur = false;
     if (!sparse_schur && (int64_t)nc * nc * 8 > (int64_t)40e9)
       return fail(PXR_ERR_UNSUPPORTED, "reduced camera system too large for the dense path (nc=%d) and the block-sparse path needs ITERATIVE_SCHUR with <= 8 camera columns per image", nc);
   }
-  if (!sparse_schur) PXR_TRY(Hcc.alloc((size_t)nc * nc));
+  if (!sparse_schur && !block_mode) PXR_TRY(Hcc.alloc((size_t)nc * nc));
   PXR_TRY(gc.alloc(nc));
   PXR_TRY(Hpp.alloc((size_t)n_points * 9)); PXR_TRY(gp.alloc((size_t)n_points * 3));
   h_obs_img.assign(d->obs_img, d->obs_img + n_obs);
   use_monolithic_inner = std::getenv("PXR_INNER_MONOLITHIC") != nullptr;
   if (for_solve) PXR_TRY(build_schur_pairs());
+  if (block_mode) PXR_TRY(block_setup());
   if (for_solve && n_obs > 0 && n_obs < ((int64_t)1 << 31)) {
     // per-image observation chunks for the camera-block build (ba_build_cam_kernel): images whose pose and
     // intrinsics are both constant contribute nothing and are left out; usable when every image has <= 8 columns
@@ -305,7 +311,7 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     }
   }
   PXR_TRY(W.alloc((size_t)n_obs * dcmax * 3)); PXR_TRY(Wcols.alloc((size_t)n_obs * dcmax)); PXR_TRY(Wdc.alloc(n_obs));
-  if (!sparse_schur) PXR_TRY(S.alloc((size_t)(nc + 1) * nc));
+  if (!sparse_schur) PXR_TRY(S.alloc((size_t)(nc + 1) * nc));   // block mode: filled from the global blocks (blk_gather_kernel)
   PXR_TRY(rhs.alloc(nc));
   PXR_TRY(diag.alloc(nl)); PXR_TRY(jscale.alloc(nl)); PXR_TRY(D2.alloc(nl)); PXR_TRY(delta.alloc(nl));
   PXR_TRY(partials.alloc(fm_max_partials(ctx)));
@@ -369,15 +375,21 @@ int BA::build_schur_pairs() {
       for (int64_t ib = 0; ib <= ia; ++ib)
         for (int self = 0; self < 2; ++self, ++k) {
           if (count[k + 1] == count[k]) continue;
-          if (sparse_schur) { ka.push_back((int32_t)ia); kbv.push_back((int32_t)ib); kself.push_back((uint8_t)self); }
+          if (sparse_schur || block_mode) { ka.push_back((int32_t)ia); kbv.push_back((int32_t)ib); kself.push_back((uint8_t)self); h_key_code_local.push_back(k); }
           for (int64_t s = count[k]; s < count[k + 1]; s += kChunk) {
             cb.push_back(s); cself.push_back((uint8_t)self);
-            if (sparse_schur) ckey.push_back((int32_t)ka.size() - 1);
+            if (sparse_schur || block_mode) ckey.push_back((int32_t)ka.size() - 1);
           }
         }
   }
   cb.push_back(total);
-  if (sparse_schur) {
+  if (block_mode) {
+    // the key list becomes the union over the ranks, the blocks live in the packed buffer (block_setup)
+    h_key_a = ka; h_key_b = kbv; h_key_self = kself;
+    PXR_TRY(ss_chunk_key.upload(ckey.data(), ckey.size(), ctx->stream));     // local ids for now; block_setup remaps them
+    PXR_CUDA(cudaStreamSynchronize(ctx->stream));
+    h_chunk_key_local = ckey;
+  } else if (sparse_schur) {
     ss_n_keys = (int)ka.size();
     PXR_TRY(ss_key_a.upload(ka.data(), ka.size(), ctx->stream)); PXR_TRY(ss_key_b.upload(kbv.data(), kbv.size(), ctx->stream));
     PXR_TRY(ss_key_self.upload(kself.data(), kself.size(), ctx->stream));
@@ -454,6 +466,7 @@ int BA::evaluate(int set, bool jac, double* cost_out) {
   PXR_TRY(project(set, jac, nullptr));
   PXR_TRY(fm(jac ? 1 : 0, nullptr, scalars.p + 0));
   if (jac) PXR_TRY(build());
+  if (block_mode) return global_cost_block(cost_out);
   PXR_TRY(allreduce_f64(ctx, scalars.p + 0, 1));
   double c = 0;
   PXR_CUDA(cudaMemcpyAsync(&c, scalars.p + 0, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -470,12 +483,13 @@ BADev BA::dev() {
   d.cam_mask = cam_mask.p; d.tmask = tmask.p; d.pose_off = pose_off.p; d.intr_off = intr_off.p;
   d.point_off = point_off.p; d.pt_begin = pt_begin.p; d.obs_out = obs_out.p; d.juv = juv.p;
   d.img_cols8 = img_cols8.p; d.img_src8 = img_src8.p; d.img_dc8 = img_dc8.p;
-  d.Hcc = Hcc.p; d.gc = gc.p; d.Hpp = Hpp.p; d.gp = gp.p; d.W = W.p; d.Wcols = Wcols.p; d.Wdc = Wdc.p;
+  d.Hcc = Hcc.p; d.gc = block_mode ? pack_local.p + pk_off_gc : gc.p; d.Hpp = Hpp.p;   // block mode: the partial gradient lives in the packed buffer d.gp = gp.p; d.W = W.p; d.Wcols = Wcols.p; d.Wdc = Wdc.p;
   d.loss.type = opt.loss_type; d.loss.a = opt.loss_scale;
   return d;
 }
 
 int BA::build() {
+  if (block_mode) return build_block();
   StageScope st(this, 3);
   if (!sparse_schur) PXR_TRY(Hcc.zero(ctx->stream));
   PXR_TRY(gc.zero(ctx->stream));
@@ -524,52 +538,9 @@ SparseSchur BA::sparse() {
   return q;
 }
 
-// One LM step attempt at the current linearisation: fills delta, returns validity and model cost change
-int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
+// Dense Cholesky of [S; rhs] + both substitutions (pxr_chol.cuh) -> delta[0..nc): captured once into a CUDA graph.
+int BA::chol_launch() {
   cudaStream_t s = ctx->stream;
-  PXR_TRY(build_schur_pairs());
-  BADev d = dev();
-  std::unique_ptr<StageScope> st(new StageScope(this, 4));   // RAII: an early error return still closes the stage
-  if (nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, D2.p, nl, radius,
-                         opt.min_lm_diagonal, opt.max_lm_diagonal);
-  PXR_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), s));
-  if (sparse_schur) {
-    // image-block form (pxr_sparse_schur.cuh): rhs = -gc + sum T gp, B_ab = sum T_x W_y^T; nothing of size nc^2
-    if (nc > 0) PXR_LAUNCH(ctx, sp_init_rhs_kernel, (unsigned)cdiv(nc, 256), 256, 0, ctx->world > 1 ? gc_local.p : gc.p, rhs.p, nc);
-    PXR_TRY(ss_Bk.zero(s));
-    if (n_points > 0) {
-      PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
-      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
-      if (sp_n_chunks > 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, ss_Bk.p, rhs.p);
-    }
-    if (ctx->world > 1 && nc > 0) PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
-  } else {
-  // multi-GPU: every rank starts from ITS partial Hcc / gc (rank 0 adds the damping), subtracts its points' Schur
-  // contributions, and ONE all-reduce of [S | rhs] (rhs is row nc of the same array) yields the reduced system
-  if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p,
-                         ctx->world > 1 ? gc_local.p : gc.p, D2.p, S.p, rhs.p, nc, (ctx->world <= 1 || ctx->rank == 0) ? 1 : 0);
-  if (n_points > 0) {
-    PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
-    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
-    if (sp_n_chunks > 0) {
-      if (img_dc_max <= 8) PXR_LAUNCH(ctx, ba_schur_pairs_kernel<true>, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
-      else PXR_LAUNCH(ctx, ba_schur_pairs_kernel<false>, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
-    }
-  }
-  // rhs rides along as row nc of S: the factorisation performs the forward substitution
-  if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
-  if (ctx->world > 1 && nc > 0) {
-    PXR_TRY(allreduce_f64(ctx, S.p, (size_t)(nc + 1) * nc));
-    PXR_CUDA(cudaMemcpyAsync(rhs.p, S.p + (size_t)nc * nc, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));   // PCG / debug read rhs
-  }
-  }
-  st.reset(); st.reset(new StageScope(this, 5));
-  last_linear_iterations = 1;
-  if (nc > 0 && sparse_schur) {
-    PXR_TRY(pcg_solve_sparse());
-  } else if (nc > 0 && use_pcg) {
-    PXR_TRY(pcg_solve());
-  } else if (nc > 0) {
     // The factorisation + back-substitution is a fixed sequence of ~3*nc/32 dependent launches: it is
     // captured once into a CUDA graph and replayed, which removes the per-launch gaps.
     if (!chol_graph_exec) {
@@ -634,6 +605,57 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
         fclose(f);
       }
     }
+    return PXR_OK;
+}
+
+// One LM step attempt at the current linearisation: fills delta, returns validity and model cost change
+int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
+  cudaStream_t s = ctx->stream;
+  PXR_TRY(build_schur_pairs());
+  if (block_mode) return compute_step_block_sync(radius, valid, model_cost_change);
+  BADev d = dev();
+  std::unique_ptr<StageScope> st(new StageScope(this, 4));   // RAII: an early error return still closes the stage
+  if (nl > 0) PXR_LAUNCH(ctx, ba_d2_kernel, (unsigned)cdiv(nl, 256), 256, 0, diag.p, jscale.p, D2.p, nl, radius,
+                         opt.min_lm_diagonal, opt.max_lm_diagonal);
+  PXR_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), s));
+  if (sparse_schur) {
+    // image-block form (pxr_sparse_schur.cuh): rhs = -gc + sum T gp, B_ab = sum T_x W_y^T; nothing of size nc^2
+    if (nc > 0) PXR_LAUNCH(ctx, sp_init_rhs_kernel, (unsigned)cdiv(nc, 256), 256, 0, ctx->world > 1 ? gc_local.p : gc.p, rhs.p, nc);
+    PXR_TRY(ss_Bk.zero(s));
+    if (n_points > 0) {
+      PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
+      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
+      if (sp_n_chunks > 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, ss_Bk.p, rhs.p);
+    }
+    if (ctx->world > 1 && nc > 0) PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
+  } else {
+  // multi-GPU: every rank starts from ITS partial Hcc / gc (rank 0 adds the damping), subtracts its points' Schur
+  // contributions, and ONE all-reduce of [S | rhs] (rhs is row nc of the same array) yields the reduced system
+  if (nc > 0) PXR_LAUNCH(ctx, ba_init_reduced_kernel, (unsigned)cdiv((int64_t)nc * nc, 256), 256, 0, Hcc.p,
+                         ctx->world > 1 ? gc_local.p : gc.p, D2.p, S.p, rhs.p, nc, (ctx->world <= 1 || ctx->rank == 0) ? 1 : 0);
+  if (n_points > 0) {
+    PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
+    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
+    if (sp_n_chunks > 0) {
+      if (img_dc_max <= 8) PXR_LAUNCH(ctx, ba_schur_pairs_kernel<true>, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+      else PXR_LAUNCH(ctx, ba_schur_pairs_kernel<false>, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+    }
+  }
+  // rhs rides along as row nc of S: the factorisation performs the forward substitution
+  if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
+  if (ctx->world > 1 && nc > 0) {
+    PXR_TRY(allreduce_f64(ctx, S.p, (size_t)(nc + 1) * nc));
+    PXR_CUDA(cudaMemcpyAsync(rhs.p, S.p + (size_t)nc * nc, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));   // PCG / debug read rhs
+  }
+  }
+  st.reset(); st.reset(new StageScope(this, 5));
+  last_linear_iterations = 1;
+  if (nc > 0 && sparse_schur) {
+    PXR_TRY(pcg_solve_sparse());
+  } else if (nc > 0 && use_pcg) {
+    PXR_TRY(pcg_solve());
+  } else if (nc > 0) {
+    PXR_TRY(chol_launch());
   }
   st.reset(); st.reset(new StageScope(this, 7));
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));  // acc[0..3]
@@ -692,7 +714,7 @@ int BA::apply_step(double* step_norm, double* x_norm) {
   const int64_t n = std::max<int64_t>(std::max<int64_t>(n_points, n_images), n_cameras);
   PXR_LAUNCH(ctx, ba_plus_kernel, (unsigned)cdiv(n, 128), 128, 0, a);
   PXR_CUDA(cudaGetLastError());
-  PXR_TRY(allreduce_f64(ctx, scalars.p + 5, 2));  // point parts are sharded, camera parts replicated
+  if (!block_mode) PXR_TRY(allreduce_f64(ctx, scalars.p + 5, 2));  // point parts are sharded, camera parts replicated (block mode: scalar exchange)
   if (step_norm || x_norm) {
     double v[4];
     PXR_CUDA(cudaMemcpyAsync(v, scalars.p + 5, 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -874,27 +896,28 @@ int BA::run_cg(const std::function<int(const double*, double*)>& spmv) {
   const unsigned gn = (unsigned)cdiv(n, 256);
   CGState hs;
   if (multi) {
+    if (cg_part.n < (size_t)3 * gn) PXR_TRY(cg_part.alloc((size_t)3 * gn));
     PXR_LAUNCH(ctx, cgm_init_state_kernel, 1, 1, 0, cg_state.p, opt.max_linear_solver_iterations, 0.1);
-    PXR_LAUNCH(ctx, cgm_init_kernel, gn, 256, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p);
-    PXR_LAUNCH(ctx, cgm_init_done_kernel, 1, 1, 0, cg_state.p);
+    PXR_LAUNCH(ctx, cgm_init_kernel, gn, 256, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p, cg_part.p);
+    PXR_LAUNCH(ctx, cgm_init_done_kernel, 1, 32, 0, cg_state.p, cg_part.p, (int)gn);
   } else {
     PXR_LAUNCH(ctx, cg_init_kernel, 1, 1024, 0, rhs.p, cg_x.p, cg_r.p, n, cg_state.p, opt.max_linear_solver_iterations, 0.1);
   }
   for (int it = 0; it < opt.max_linear_solver_iterations; ++it) {
     const bool refresh = (it + 1) % 10 == 0;   // residual_reset_period
     if (multi) {
-      PXR_LAUNCH(ctx, cgm_precond_kernel, gn, 256, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, n, cg_state.p);
-      PXR_LAUNCH(ctx, cgm_beta_kernel, 1, 1, 0, cg_state.p);
+      PXR_LAUNCH(ctx, cgm_precond_kernel, gn, 256, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, n, cg_state.p, cg_part.p);
+      PXR_LAUNCH(ctx, cgm_beta_kernel, 1, 32, 0, cg_state.p, cg_part.p, (int)gn);
       PXR_LAUNCH(ctx, cgm_dir_kernel, gn, 256, 0, cg_z.p, cg_p.p, n, cg_state.p);
       PXR_TRY(spmv(cg_p.p, cg_q.p));
-      PXR_LAUNCH(ctx, cgm_pq_kernel, gn, 256, 0, cg_p.p, cg_q.p, n, cg_state.p);
-      PXR_LAUNCH(ctx, cgm_alpha_kernel, 1, 1, 0, cg_state.p);
-      PXR_LAUNCH(ctx, cgm_update_kernel, gn, 256, 0, rhs.p, cg_p.p, cg_q.p, cg_x.p, cg_r.p, n, cg_state.p);
+      PXR_LAUNCH(ctx, cgm_pq_kernel, gn, 256, 0, cg_p.p, cg_q.p, n, cg_state.p, cg_part.p);
+      PXR_LAUNCH(ctx, cgm_alpha_kernel, 1, 32, 0, cg_state.p, cg_part.p, (int)gn);
+      PXR_LAUNCH(ctx, cgm_update_kernel, gn, 256, 0, rhs.p, cg_p.p, cg_q.p, cg_x.p, cg_r.p, n, cg_state.p, cg_part.p);
       if (refresh) {
         PXR_TRY(spmv(cg_x.p, cg_tmp.p));
-        PXR_LAUNCH(ctx, cgm_refresh_kernel, gn, 256, 0, rhs.p, cg_tmp.p, cg_x.p, cg_r.p, n, cg_state.p);
+        PXR_LAUNCH(ctx, cgm_refresh_kernel, gn, 256, 0, rhs.p, cg_tmp.p, cg_x.p, cg_r.p, n, cg_state.p, cg_part.p);
       }
-      PXR_LAUNCH(ctx, cgm_check_kernel, 1, 1, 0, cg_state.p);
+      PXR_LAUNCH(ctx, cgm_check_kernel, 1, 32, 0, cg_state.p, cg_part.p, (int)gn);
     } else {
       PXR_LAUNCH(ctx, cg_precond_kernel, 1, 1024, 0, cg_Minv.p, cg_row_off.p, cg_row_dim.p, cg_r.p, cg_z.p, cg_p.p, n, cg_state.p);
       PXR_TRY(spmv(cg_p.p, cg_q.p));
@@ -935,6 +958,7 @@ int BA::gradient_max_norm(double* out) {
 // lives in the BA object so that a solve can be continued (pxr_ba_iterate) — bench.py times K
 // consecutive iterations of one trajectory after W warm-up iterations.
 int BA::lm_begin() {
+  if (block_mode) return lm_begin_block();
   PXR_CUDA(cudaSetDevice(ctx->device));
   lm = LMState();
   lm.radius = opt.initial_trust_region_radius;
@@ -979,6 +1003,7 @@ bool BA::lm_finalize(int max_iteration) {
 
 // Runs LM iterations until iteration index `max_iteration` (absolute) or termination.
 int BA::lm_iterate(int max_iteration) {
+  if (block_mode) return lm_iterate_block(max_iteration);
   using clk = std::chrono::steady_clock;
   if (!lm.started) PXR_TRY(lm_begin());
   lm.it_start = clk::now();
@@ -1124,6 +1149,7 @@ int BA::solve(pxr_summary* sum) {
   const int64_t l0 = ctx->launches;
   PXR_TRY(lm_begin());
   PXR_TRY(lm_iterate(opt.max_num_iterations));
+  if (block_mode) PXR_TRY(finish_gmax_block());
   fill_summary(sum, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), ctx->launches - l0);
   return PXR_OK;
 }
@@ -1267,14 +1293,17 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
   pxr_ctx* ctx = b->ctx;
   cudaStream_t s = ctx->stream;
   PXR_CUDA(cudaSetDevice(ctx->device));
-  if (b->sparse_schur && (Hcc || S)) return fail(PXR_ERR_UNSUPPORTED, "the block-sparse path has no dense Hcc / S to return");
+  if ((b->sparse_schur || b->block_mode) && (Hcc || S)) return fail(PXR_ERR_UNSUPPORTED, "the block-sparse path has no dense Hcc / S to return");
   double c = 0;
   PXR_TRY(b->evaluate(b->cur, true, &c));
   if (cost) *cost = c;
-  if (b->nl > 0) PXR_LAUNCH(ctx, ba_scale_kernel, (unsigned)cdiv(b->nl, 256), 256, 0, b->diag.p, b->jscale.p, b->nl, b->opt.jacobi_scaling);
+  if (b->block_mode) {   // point columns now, camera columns after the all-reduce inside compute_step
+    if (b->nl - b->nc > 0) PXR_LAUNCH(ctx, ba_scale_kernel, (unsigned)cdiv(b->nl - b->nc, 256), 256, 0, b->diag.p + b->nc, b->jscale.p + b->nc, b->nl - b->nc, b->opt.jacobi_scaling);
+    b->jscale_c_pending = true;
+  } else if (b->nl > 0) PXR_LAUNCH(ctx, ba_scale_kernel, (unsigned)cdiv(b->nl, 256), 256, 0, b->diag.p, b->jscale.p, b->nl, b->opt.jacobi_scaling);
   const size_t nc = b->nc;
   if (Hcc) PXR_CUDA(cudaMemcpyAsync(Hcc, b->Hcc.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));
-  if (gc) PXR_CUDA(cudaMemcpyAsync(gc, b->gc.p, nc * 8, cudaMemcpyDeviceToHost, s));
+  if (gc) PXR_CUDA(cudaMemcpyAsync(gc, b->block_mode ? b->pack_local.p + b->pk_off_gc : b->gc.p, nc * 8, cudaMemcpyDeviceToHost, s));   // block mode: this rank's partial
   if (Hpp) PXR_CUDA(cudaMemcpyAsync(Hpp, b->Hpp.p, (size_t)b->n_points * 72, cudaMemcpyDeviceToHost, s));
   if (gp) PXR_CUDA(cudaMemcpyAsync(gp, b->gp.p, (size_t)b->n_points * 24, cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaStreamSynchronize(s));

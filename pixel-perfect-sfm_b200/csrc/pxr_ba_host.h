@@ -16,6 +16,7 @@
 #include "pxr_internal.h"
 #include "pxr_pcg.cuh"
 #include "pxr_sparse_schur.cuh"
+#include "pxr_block.cuh"
 
 namespace pxr {
 
@@ -46,6 +47,7 @@ struct StepEvaluator {
 struct LMState {
   bool started = false, finished = false, pending_finalize = false, inner_enabled = false;
   StepEvaluator ev;
+  bool gmax_pending = false;       // block mode, several ranks: max |g| of the current point arrives with the next all-reduce
   bool best_is_current = true;     // non-monotonic steps: the lowest-cost iterate lives in BA::best_* when false
   double x_cost = 0, radius = 1e4, decrease_factor = 2.0, initial_cost = 0, minimum_cost = 0;
   int num_invalid = 0, n_succ = 0, n_unsucc = 0, n_inner = 0, term = 1;
@@ -108,7 +110,7 @@ struct BA {
   DevBuf<double> rdiag;
   // ITERATIVE_SCHUR (PCG) workspace
   bool use_pcg = false;
-  DevBuf<double> cg_Minv, cg_z, cg_p, cg_q, cg_r, cg_x, cg_tmp;
+  DevBuf<double> cg_Minv, cg_z, cg_p, cg_q, cg_r, cg_x, cg_tmp, cg_part;   // cg_part: per-CTA dot-product partials (fixed-order sums)
   DevBuf<int32_t> cg_blk_off, cg_blk_dim, cg_row_off, cg_row_dim;
   DevBuf<CGState> cg_state;
   int cg_nblk = 0, last_linear_iterations = 1;
@@ -126,6 +128,33 @@ struct BA {
   DevBuf<double> ss_Himg, ss_Bk, ss_Dblk;
   SparseSchur sparse();
   int pcg_solve_sparse();
+  // ---- block mode (pxr_block.cuh, pxr_ba_block.cu): image-block assembly into ONE packed buffer, ONE all-reduce per
+  // LM iteration, everything after it deterministic; scalar decisions travel through the peer mailboxes
+  bool block_mode = false;
+  DevBuf<double> pack_local, pack_global;          // world == 1: pack_global stays empty and aliases pack_local
+  size_t pk_off_B = 0, pk_off_rhs = 0, pk_off_gc = 0, pk_off_slots = 0, pk_n = 0;
+  double* pk(bool global) { return (global && pack_global.p) ? pack_global.p : pack_local.p; }
+  SparseSchur sparse_blk(bool global);
+  std::vector<int32_t> h_key_a, h_key_b; std::vector<uint8_t> h_key_self;     // global key list (host copy)
+  DevBuf<int64_t> gmS_dest, gmS_ptr, dg_ptr, gmD_dest, gmD_ptr, br_chunk_begin, br_cols_ptr;
+  DevBuf<int32_t> gmS_src, dg_src, gmD_src, br_chunk_img, br_ent_key, br_cols_src;
+  DevBuf<uint8_t> br_chunk_first;
+  DevBuf<double> br_ypart, mb_in, mb_out;
+  int64_t gmS_rows = 0, gmD_rows = 0, br_n_chunks = 0;
+  bool jscale_c_pending = false;
+  bool blk_lag_gmax = false;                       // world > 1: max |g| of the current point is known after the next all-reduce
+  int block_setup();                               // global keys, gather maps, block rows
+  int build_block();
+  int compute_step_block(double radius);
+  int compute_step_block_sync(double radius, bool* valid, double* model_cost_change);   // + exchange + read-back (debug entry points)
+  int global_cost_block(double* cost_out);         // scalars[0] summed over the ranks
+  int pcg_solve_block();
+  int lm_begin_block();
+  int lm_iterate_block(int max_iteration);
+  int finish_gmax_block();
+  int exchange_scalars(int n_sum);                 // mb_in -> mb_out (peer mailboxes, or NCCL when they are unavailable)
+  std::vector<int32_t> h_chunk_key_local;
+  std::vector<int64_t> h_key_code_local;           // local key codes in build order (set by build_schur_pairs)
   int pcg_setup_blocks();
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
@@ -154,6 +183,7 @@ struct BA {
   int build();
   int evaluate(int set, bool jac, double* cost_out);
   int compute_step(double radius, bool* valid, double* model_cost_change);
+  int chol_launch();
   int apply_step(double* step_norm, double* x_norm);
   int gradient_max_norm(double* out);
   int inner_iterations(int set);

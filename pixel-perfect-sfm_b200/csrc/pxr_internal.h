@@ -21,6 +21,15 @@ struct pxr_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // peer mailboxes (pxr_api.cu: mailbox_*): small scalar exchanges between the ranks of one node go through peer memory
+  // over NVLink (cudaIpc-mapped buffers), not through NCCL, so an LM iteration issues exactly ONE NCCL collective
+  double* mbox_local = nullptr;            // [2 parities][world][kMboxSlots] payloads written BY the peers
+  unsigned long long* mbox_seq_local = nullptr;   // [world] sequence number of the last exchange each peer has delivered
+  double* mbox_peer[16] = {};              // peer r's mbox_local as mapped into this process (own entry = mbox_local)
+  unsigned long long* mbox_seq_peer[16] = {};
+  unsigned long long mbox_epoch = 0;       // exchanges issued so far (same on every rank)
+  bool mbox_ready = false;
+  int64_t nccl_collectives = 0;            // NCCL calls issued through this context (bench.py reports them per LM iteration)
   pxr::Stager* stager = nullptr;          // pinned ring of the pageable-memory upload pipeline (pxr_upload.cu)
   cudaStream_t upload_stream = nullptr;   // carries the patch slab so that host-side setup (and its small syncs) overlaps it
 };
@@ -93,5 +102,15 @@ bool interrupt_pending();
 
 // allreduce (sum, fp64) on ctx->stream when a communicator is attached; no-op otherwise
 int allreduce_f64(pxr_ctx* ctx, double* dptr, size_t count, bool max_op = false);
+// out-of-place sum (send untouched: a rejected LM step re-reduces the same local blocks with new damping)
+int allreduce_f64_oop(pxr_ctx* ctx, const double* send, double* recv, size_t count);
+// every rank contributes `bytes` bytes (device memory); recv holds world * bytes, rank-major.  Setup-time use only.
+int allgather_bytes(pxr_ctx* ctx, const void* send_dev, void* recv_dev, size_t bytes);
+// Scalar exchange over peer memory: out[i] = sum over ranks (fixed rank order: bitwise identical everywhere) of
+// payload[i] for i < n_sum, and max over ranks for n_sum <= i < n_sum + n_max.  payload/out are device pointers,
+// n_sum + n_max <= kMboxSlots.  world == 1: a device copy.  Stream-ordered on ctx->stream; *fail_flag (device int)
+// is raised if a peer does not show up within the spin budget (no hang).
+constexpr int kMboxSlots = 16;
+int mailbox_exchange(pxr_ctx* ctx, const double* payload, int n_sum, int n_max, double* out, int* fail_flag);
 
 }  // namespace pxr

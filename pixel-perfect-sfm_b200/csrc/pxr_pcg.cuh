@@ -156,24 +156,34 @@ static __global__ void __launch_bounds__(1024) cg_refresh_kernel(const double* b
 
 // ---------------------------------------------------------------------------------------------------------------
 // Multi-CTA variants for large reduced systems (n >= 4096: the single-CTA kernels above then cost 20-30 us each and
-// dominate a CG iteration).  Vector work is spread over the grid, dot products land in the state with one fp64 atomic
-// per CTA, and the scalar recurrences run in 1-thread kernels in between.  Same arithmetic, same termination rule.
-static __global__ void __launch_bounds__(256) cgm_init_kernel(const double* b, double* x, double* r, int n, CGState* st) {
+// dominate a CG iteration).  Vector work is spread over the grid; every dot product is a two-stage FIXED-ORDER
+// reduction (one partial per CTA, summed by one warp of the scalar kernel that needs it), so the solve is a
+// deterministic function of (S, b): ranks that run it redundantly on the same all-reduced system stay bit-identical.
+// Same arithmetic and termination rule as the single-CTA kernels.  `part` holds 3 * gridDim.x doubles (rz | pq | xbr).
+__device__ __forceinline__ double det_sum_warp(const double* part, int n) {   // one full warp, fixed order
+  double v = 0.0;
+  for (int i = threadIdx.x & 31; i < n; i += 32) v += part[i];
+  return warp_sum(v);
+}
+static __global__ void __launch_bounds__(256) cgm_init_kernel(const double* b, double* x, double* r, int n, CGState* st, double* part) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double nb = 0.0;
   if (i < n) { x[i] = 0.0; r[i] = b[i]; nb = b[i] * b[i]; }
   nb = cta_sum(nb);
-  if (threadIdx.x == 0 && nb != 0.0) atomicAdd(&st->xbr, nb);
+  if (threadIdx.x == 0) part[2 * gridDim.x + blockIdx.x] = nb;
 }
 static __global__ void cgm_init_state_kernel(CGState* st, int max_iter, double q_tol) {   // before cgm_init_kernel
   st->rho = 1.0; st->last_rho = 1.0; st->alpha = 0; st->beta = 0; st->Q0 = 0.0; st->it = 0; st->failed = 0; st->done = 0;
   st->max_iter = max_iter; st->q_tol = q_tol; st->pq = 0.0; st->rz = 0.0; st->xbr = 0.0;
 }
-static __global__ void cgm_init_done_kernel(CGState* st) { if (st->xbr == 0.0) st->done = 1; st->xbr = 0.0; }   // b == 0
+static __global__ void __launch_bounds__(32) cgm_init_done_kernel(CGState* st, const double* part, int g) {   // b == 0
+  const double nb = det_sum_warp(part + 2 * g, g);
+  if (threadIdx.x == 0 && nb == 0.0) st->done = 1;
+}
 
-// z = M^-1 r ; rz += r.z
+// z = M^-1 r ; rz partial
 static __global__ void __launch_bounds__(256) cgm_precond_kernel(const double* Minv, const int32_t* row_off, const int32_t* row_dim,
-                                                                 const double* r, double* z, int n, CGState* st) {
+                                                                 const double* r, double* z, int n, CGState* st, double* part) {
   if (st->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double rz = 0.0;
@@ -184,12 +194,12 @@ static __global__ void __launch_bounds__(256) cgm_precond_kernel(const double* M
     z[i] = sacc; rz = r[i] * sacc;
   }
   rz = cta_sum(rz);
-  if (threadIdx.x == 0) atomicAdd(&st->rz, rz);
+  if (threadIdx.x == 0) part[blockIdx.x] = rz;
 }
-static __global__ void cgm_beta_kernel(CGState* st) {
+static __global__ void __launch_bounds__(32) cgm_beta_kernel(CGState* st, const double* part, int g) {
   if (st->done) return;
-  const double rz = st->rz;
-  st->rz = 0.0; st->pq = 0.0; st->xbr = 0.0;
+  const double rz = det_sum_warp(part, g);
+  if (threadIdx.x != 0) return;
   st->it += 1;
   st->last_rho = st->rho; st->rho = rz;
   if (rz == 0.0 || !isfinite(rz)) { st->failed = 1; st->done = 1; return; }
@@ -203,25 +213,26 @@ static __global__ void __launch_bounds__(256) cgm_dir_kernel(const double* z, do
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = st->it == 1 ? z[i] : z[i] + st->beta * p[i];
 }
-// pq += p.q
-static __global__ void __launch_bounds__(256) cgm_pq_kernel(const double* p, const double* q, int n, CGState* st) {
+// pq partial
+static __global__ void __launch_bounds__(256) cgm_pq_kernel(const double* p, const double* q, int n, CGState* st, double* part) {
   if (st->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v = i < n ? p[i] * q[i] : 0.0;
   v = cta_sum(v);
-  if (threadIdx.x == 0) atomicAdd(&st->pq, v);
+  if (threadIdx.x == 0) part[gridDim.x + blockIdx.x] = v;
 }
-static __global__ void cgm_alpha_kernel(CGState* st) {
+static __global__ void __launch_bounds__(32) cgm_alpha_kernel(CGState* st, const double* part, int g) {
   if (st->done) return;
-  const double pq = st->pq;
+  const double pq = det_sum_warp(part + g, g);
+  if (threadIdx.x != 0) return;
   if (pq <= 0.0 || !isfinite(pq)) { st->done = 1; st->alpha = 0.0; return; }   // not positive definite along p: keep x
   const double alpha = st->rho / pq;
   if (!isfinite(alpha)) { st->failed = 1; st->done = 1; st->alpha = 0.0; return; }
   st->alpha = alpha;
 }
-// x += alpha p ; r -= alpha q (unless this is a refresh iteration) ; xbr += x.(b + r) when no refresh follows
+// x += alpha p ; r -= alpha q (unless this is a refresh iteration) ; xbr partial = x.(b + r) when no refresh follows
 static __global__ void __launch_bounds__(256) cgm_update_kernel(const double* b, const double* p, const double* q, double* x, double* r,
-                                                                int n, CGState* st) {
+                                                                int n, CGState* st, double* part) {
   if (st->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool refresh = (st->it % 10) == 0;
@@ -232,20 +243,23 @@ static __global__ void __launch_bounds__(256) cgm_update_kernel(const double* b,
     x[i] = xi;
     if (!refresh) { const double ri = r[i] - alpha * q[i]; r[i] = ri; v = xi * (b[i] + ri); }
   }
-  if (!refresh) { v = cta_sum(v); if (threadIdx.x == 0) atomicAdd(&st->xbr, v); }
+  if (!refresh) { v = cta_sum(v); if (threadIdx.x == 0) part[2 * gridDim.x + blockIdx.x] = v; }
 }
-// refresh iterations: r = b - S x ; xbr += x.(b + r)
-static __global__ void __launch_bounds__(256) cgm_refresh_kernel(const double* b, const double* Sx, const double* x, double* r, int n, CGState* st) {
+// refresh iterations: r = b - S x ; xbr partial
+static __global__ void __launch_bounds__(256) cgm_refresh_kernel(const double* b, const double* Sx, const double* x, double* r, int n, CGState* st,
+                                                                 double* part) {
   if (st->done || (st->it % 10) != 0) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0.0;
   if (i < n) { const double ri = b[i] - Sx[i]; r[i] = ri; v = x[i] * (b[i] + ri); }
   v = cta_sum(v);
-  if (threadIdx.x == 0) atomicAdd(&st->xbr, v);
+  if (threadIdx.x == 0) part[2 * gridDim.x + blockIdx.x] = v;
 }
-static __global__ void cgm_check_kernel(CGState* st) {
+static __global__ void __launch_bounds__(32) cgm_check_kernel(CGState* st, const double* part, int g) {
   if (st->done) return;
-  const double Q1 = -0.5 * st->xbr;
+  const double xbr = det_sum_warp(part + 2 * g, g);
+  if (threadIdx.x != 0) return;
+  const double Q1 = -0.5 * xbr;
   const double zeta = st->it * (Q1 - st->Q0) / Q1;
   if (zeta < st->q_tol) st->done = 1;
   st->Q0 = Q1;

@@ -315,6 +315,7 @@ def load_lib():
     lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
     lib.pxr_last_error.restype = C.c_char_p
     lib.pxr_ctx_kernel_launches.restype = C.c_int64
+    lib.pxr_ctx_nccl_collectives.restype = C.c_int64
     lib.pxr_set_interrupt_callback(_SIGNAL_POLL, None)      # Ctrl-C stops a solve between LM iterations
     _LIB = lib
     return lib
@@ -366,6 +367,14 @@ class Context:
 
     def kernel_launches(self):
         return int(self.lib.pxr_ctx_kernel_launches(self.handle))
+
+    def nccl_collectives(self):
+        """NCCL calls issued through this context so far (the contract: ONE all-reduce per LM iteration)"""
+        return int(self.lib.pxr_ctx_nccl_collectives(self.handle))
+
+    def mailbox_ready(self):
+        """True when the per-iteration scalar exchange runs over peer memory (NVLink mailboxes), not NCCL"""
+        return bool(self.lib.pxr_ctx_mailbox_ready(self.handle))
 
     def timer_start(self):
         check(self.lib.pxr_ctx_timer_start(self.handle))

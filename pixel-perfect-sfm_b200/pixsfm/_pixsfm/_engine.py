@@ -47,14 +47,16 @@ class BAHandle:
             out["residuals"] = res
         return out
 
-    def debug_linearize(self, nc, nl, radius=1e4):
+    def debug_linearize(self, nc, nl, radius=1e4, dense=True):
+        """dense=False leaves Hcc / S out (the block-sparse and block-mode paths never form them)"""
         npts = len(self.problem.xyz)
-        out = dict(Hcc=np.zeros((nc, nc)), gc=np.zeros(nc), Hpp=np.zeros((npts, 3, 3)), gp=np.zeros((npts, 3)),
-                   S=np.zeros((nc, nc)), rhs=np.zeros(nc), delta=np.zeros(nl))
+        out = dict(gc=np.zeros(nc), Hpp=np.zeros((npts, 3, 3)), gp=np.zeros((npts, 3)), rhs=np.zeros(nc), delta=np.zeros(nl))
+        if dense:
+            out.update(Hcc=np.zeros((nc, nc)), S=np.zeros((nc, nc)))
         cost = C.c_double(); mcc = C.c_double()
-        _capi.check(self.lib.pxr_ba_debug_linearize(self.handle, C.c_double(radius), C.byref(cost), _p(out["Hcc"]),
-                                                    _p(out["gc"]), _p(out["Hpp"]), _p(out["gp"]), _p(out["S"]),
-                                                    _p(out["rhs"]), _p(out["delta"]), C.byref(mcc)))
+        _capi.check(self.lib.pxr_ba_debug_linearize(self.handle, C.c_double(radius), C.byref(cost), _p(out.get("Hcc")),
+                                                    _p(out["gc"]), _p(out["Hpp"]), _p(out["gp"]), _p(out.get("S")),
+                                                    _p(out["rhs"]) if dense else None, _p(out["delta"]), C.byref(mcc)))
         out["cost"] = cost.value; out["model_cost_change"] = mcc.value
         return out
 
