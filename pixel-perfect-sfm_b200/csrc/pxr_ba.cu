@@ -483,7 +483,8 @@ BADev BA::dev() {
   d.cam_mask = cam_mask.p; d.tmask = tmask.p; d.pose_off = pose_off.p; d.intr_off = intr_off.p;
   d.point_off = point_off.p; d.pt_begin = pt_begin.p; d.obs_out = obs_out.p; d.juv = juv.p;
   d.img_cols8 = img_cols8.p; d.img_src8 = img_src8.p; d.img_dc8 = img_dc8.p;
-  d.Hcc = Hcc.p; d.gc = block_mode ? pack_local.p + pk_off_gc : gc.p; d.Hpp = Hpp.p;   // block mode: the partial gradient lives in the packed buffer d.gp = gp.p; d.W = W.p; d.Wcols = Wcols.p; d.Wdc = Wdc.p;
+  d.Hcc = Hcc.p; d.Hpp = Hpp.p; d.gp = gp.p; d.W = W.p; d.Wcols = Wcols.p; d.Wdc = Wdc.p;
+  d.gc = block_mode ? pack_local.p + pk_off_gc : gc.p;   // block mode: the partial gradient lives in the packed buffer
   d.loss.type = opt.loss_type; d.loss.a = opt.loss_scale;
   return d;
 }
