@@ -945,8 +945,9 @@ int BA::run_cg(const std::function<int(const double*, double*)>& spmv) {
 
 int BA::gradient_max_norm(double* out) {
   PXR_CUDA(cudaMemsetAsync(scalars.p + 10, 0, 8, ctx->stream));
-  const int64_t n = std::max<int64_t>(nc, n_points);
-  if (n > 0) PXR_LAUNCH(ctx, ba_gradmax_kernel, (unsigned)cdiv(n, 256), 256, 0, dev(), scalars.p + 10);
+  const int64_t n = std::max<int64_t>(std::max<int64_t>(n_images, n_cameras), n_points);
+  const BADev d = dev();
+  if (n > 0) PXR_LAUNCH(ctx, ba_gradmax_kernel, (unsigned)cdiv(n, 256), 256, 0, d, d.gc, q[cur].p, 1, scalars.p + 10);
   PXR_TRY(allreduce_f64(ctx, scalars.p + 10, 1, true));
   PXR_CUDA(cudaMemcpyAsync(out, scalars.p + 10, 8, cudaMemcpyDeviceToHost, ctx->stream));
   PXR_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -354,9 +354,14 @@ int BA::compute_step_block(double radius) {
     st.reset(new StageScope(this, 4));
     const double* G = pk(true);
     PXR_CUDA(cudaMemsetAsync(scalars.p + 10, 0, 8, s));
+    PXR_CUDA(cudaMemsetAsync(scalars.p + 14, 0, 8, s));
     GatherMap dg{nullptr, dg_ptr.p, dg_src.p, nc};
     PXR_LAUNCH(ctx, blk_post_kernel, (unsigned)cdiv(nc, 256), 256, 0, dg, G, G + pk_off_gc, G + pk_off_rhs, diag.p, jscale.p,
-               jscale_c_pending ? 1 : 0, opt.jacobi_scaling, D2.p, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, rhs.p, nc, scalars.p + 10);
+               jscale_c_pending ? 1 : 0, opt.jacobi_scaling, D2.p, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, rhs.p, nc, scalars.p + 14);
+    {   // camera part of ceres' gradient_max_norm from the GLOBAL gradient (quaternion blocks through the manifold)
+      const int64_t n = std::max<int64_t>(n_images, n_cameras);
+      PXR_LAUNCH(ctx, ba_gradmax_kernel, (unsigned)cdiv(n, 256), 256, 0, d, G + pk_off_gc, q[cur].p, 0, scalars.p + 10);
+    }
     jscale_c_pending = false;
     last_linear_iterations = 1;
     if (sparse_schur) {
@@ -475,7 +480,8 @@ int BA::finish_gmax_block() {
   PXR_CUDA(cudaMemsetAsync(scalars.p + 10, 0, 8, s));
   if (nc > 0) {
     PXR_TRY(allreduce_f64_oop(ctx, pack_local.p + pk_off_gc, pk(true) + pk_off_gc, (size_t)nc));
-    PXR_LAUNCH(ctx, blk_absmax_kernel, (unsigned)cdiv(nc, 256), 256, 0, pk(true) + pk_off_gc, nc, scalars.p + 10);
+    const int64_t n = std::max<int64_t>(n_images, n_cameras);
+    PXR_LAUNCH(ctx, ba_gradmax_kernel, (unsigned)cdiv(n, 256), 256, 0, dev(), pk(true) + pk_off_gc, q[cur].p, 0, scalars.p + 10);
   }
   PXR_CUDA(cudaMemsetAsync(flags.p + 3, 0, sizeof(int), s));
   PXR_LAUNCH(ctx, blk_pack_scalars_kernel, 1, 1, 0, scalars.p, flags.p, mb_in.p, 3, ctx->rank == 0 ? 1 : 0, 0);

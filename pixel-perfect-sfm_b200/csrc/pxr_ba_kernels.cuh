@@ -803,12 +803,35 @@ static __global__ void __launch_bounds__(1024) reduce_partials_kernel(const doub
   }
 }
 
-// max |g| over the local gradient (cameras from gc, points from gp)
-static __global__ void __launch_bounds__(256) ba_gradmax_kernel(BADev d, double* out /* as ordered-uint max */) {
+// ceres' gradient_max_norm = || x - Plus(x, -g) ||_inf (trust_region_minimizer.cc: ComputeGradientNorms): for
+// Euclidean blocks (translations, intrinsics, points) that is max |g_i|, for the quaternion block the gradient step goes
+// through the manifold.  One thread per image / camera / point; `gc` is passed explicitly (block mode: the all-reduced
+// copy), with_points = 0 leaves the point part to the caller (block mode: per-rank maximum exchanged separately).
+static __global__ void __launch_bounds__(256) ba_gradmax_kernel(BADev d, const double* __restrict__ gc, const double* __restrict__ q,
+                                                                int with_points, double* out /* as ordered-uint max */) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double m = 0.0;
-  if (i < d.nc) m = fabs(d.gc[i]);
-  if (i < d.n_points && d.point_off[i] >= 0)
+  if (i < d.n_images) {
+    const int po = d.pose_off[i];
+    if (po >= 0) {
+      const double ng[3] = {-gc[po], -gc[po + 1], -gc[po + 2]};
+      double qn[4];
+      quaternion_plus(q + 4 * i, ng, qn);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m = fmax(m, fabs(q[4 * i + k] - qn[k]));
+      const int nt = 3 - __popc(d.tmask[i] & 7u);
+      for (int k = 0; k < nt; ++k) m = fmax(m, fabs(gc[po + 3 + k]));
+    }
+  }
+  if (i < d.n_cameras) {
+    const int io = d.intr_off[i];
+    if (io >= 0) {
+      const int Kc = cam_num_params(d.cam_model[i]);
+      const int nk = Kc - __popc(d.cam_mask[i] & ((1u << Kc) - 1u));
+      for (int k = 0; k < nk; ++k) m = fmax(m, fabs(gc[io + k]));
+    }
+  }
+  if (with_points && i < d.n_points && d.point_off[i] >= 0)
     m = fmax(m, fmax(fabs(d.gp[i * 3]), fmax(fabs(d.gp[i * 3 + 1]), fabs(d.gp[i * 3 + 2]))));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
