@@ -10,7 +10,14 @@ Cauchy(0.25), reference default options (inner iterations on).  north_star quote
 this config; configs[1] (8k observations, 33 MB of taps) fits in L2 and cannot exercise the HBM
 roofline.  A "step" is ONE Levenberg-Marquardt iteration of one continuing trajectory.
 With N>1 every rank holds its own 50k points / 500k observations over the SAME 200 cameras (weak
-scaling); the reduced camera system is all-reduced with NCCL every LM iteration.
+scaling; `--scaling strong` splits the 50k points instead); ONE NCCL all-reduce of the packed
+reduced-camera blocks per LM iteration, the accept/reject scalars travel through peer mailboxes.
+`--workload configs4` is BASELINE.json configs[4]: 5 000 cameras, 250 000 points / 2.5 M observations
+PER GPU (8 GPUs = the 2 M points / 20 M observations of the config), 8x8 patches, local co-visibility.
+
+Timing: W warm-up LM iterations, then the trajectory is RESET (pxr_ba_reset) and K iterations are
+timed from iteration zero — the same iterations the CPU arm times (inner iterations included while
+ceres' rule keeps them on).  `steady_state` repeats the measurement on the K iterations after that.
 """
 import argparse
 import ctypes as C
@@ -63,7 +70,6 @@ os.environ.setdefault("NCCL_DEBUG", "WARN")   # never override what the launcher
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
 
-ALGO_BYTES_PER_OBS = 4736  # 16 taps x 128 ch x 2 B + fp32-equivalent ref 512 B + 128 B metadata
 
 
 def parse():
@@ -85,7 +91,20 @@ def parse():
                     help="0: every point is seen by `track` cameras drawn uniformly (BASELINE configs[2]); W>0: drawn from a "
                          "window of W consecutive cameras (local co-visibility, what large scenes look like: configs[4])")
     ap.add_argument("--linear-solver", type=int, default=0, help="pxr_linear_solver (0 AUTO as bundle_optimizer.h:181-191)")
-    return ap.parse_args()
+    ap.add_argument("--workload", default="configs2", choices=["configs2", "configs4"],
+                    help="configs2: BASELINE configs[2] (default, the metric's config); configs4: BASELINE configs[4] shape")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --points per GPU; strong: --points in total, split over the GPUs")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0: all usable)")
+    args = ap.parse_args()
+    if args.workload == "configs4":
+        # 5k cams / 2M pts / 20M obs over 8 GPUs = 250k pts / 2.5M obs per GPU; 8x8 patches (41 GB per GPU instead of 164 GB)
+        d = ap.parse_args([])
+        if args.cams == d.cams: args.cams = 5000
+        if args.points == d.points: args.points = 250000
+        if args.ps == d.ps: args.ps = 8
+        if args.covis_window == d.covis_window: args.covis_window = 64
+    return args
 
 
 class ClockSampler:
@@ -198,7 +217,7 @@ def geometry(args, rank):
     from pixsfm.util import synthetic
     geo_c = synthetic.make_geometry(args.cams, 1, 1, seed=args.seed)  # cameras only
     rng = np.random.default_rng(args.seed * 1000 + 17 + rank)
-    n_pts, L = args.points, min(args.track, args.cams)
+    n_pts, L = getattr(args, "points_per_rank", args.points), min(args.track, args.cams)
     xyz = rng.uniform(-1, 1, (n_pts, 3))
     # every point is seen by L distinct cameras
     if args.covis_window > 0:
@@ -264,46 +283,134 @@ def make_problem(args, g, patches, on_device, sel=None):
                            scale=g["scale"][:n_obs], **kw)
 
 
-def cpu_arm(args, g, d_patches, refs, ctx, steps, label):
-    """Times the CPU restatement of the reference path (oracle/) on a bounded sample of the workload."""
+def oracle_fast():
+    """oracle/liboracle_fast.so (the -O3 / AVX2 build of the same sources; parity tests use the strict build)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    from pixsfm._pixsfm import _capi, _engine
+    path = os.path.join(ROOT, "oracle", "liboracle_fast.so")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+    lib = C.CDLL(path)
+    lib.orc_ka_problem_labels.restype = C.c_int
+    O._lib = lib               # oracle_lib's wrappers (ba_solve, refs_compute) now call this build
+    return O, lib, os.path.basename(path)
+
+
+def cpu_arm(args, g, steps, warmup, label, max_points=None):
+    """Times the CPU restatement of the reference path (oracle/, test infrastructure) on the host cores.  Nothing of
+    libpxr.so is used: patches come from the oracle's own generator (same hash / field model as the device one),
+    reference descriptors from the oracle's ReferenceExtractor.  The whole workload is solved when the host has the
+    memory for its patch slab (configs[2]: 32.8 GB), else (or when max_points bounds the leg) its first points."""
+    from pixsfm._pixsfm import _capi
+    O, lib, libname = oracle_fast()
+    nthreads = args.cpu_threads or usable_cpus()
+    lib.orc_set_num_threads(nthreads)
+    cores = lib.orc_num_threads()
     L = min(args.track, args.cams)
-    n_pts = min(args.cpu_sample_points, len(g["xyz"]))
+    n_pts_all = len(g["xyz"])
+    bytes_per_obs = args.ps * args.ps * args.channels * 2
+    avail = host_memory_available()
+    n_pts = n_pts_all
+    if avail is not None:
+        n_pts = min(n_pts, int(0.7 * avail / (bytes_per_obs * L)))
+    if max_points is not None:
+        n_pts = min(n_pts, max_points)
+    n_pts = max(1, n_pts)
     n_obs = n_pts * L
-    pbytes = n_obs * args.ps * args.ps * args.channels * 2
+    t_setup = time.time()
     host = np.empty((n_obs, args.ps, args.ps, args.channels), np.float16)
-    _engine.memcpy_d2h(host, d_patches, pbytes, ctx)
+    uv0 = np.ascontiguousarray(g["uv0"][:n_obs]); fid = np.ascontiguousarray(g["obs_pt"][:n_obs])
+    rc = lib.orc_synth_patches(host.ctypes.data_as(C.c_void_p), C.c_int64(n_obs), int(args.ps), int(args.channels),
+                               uv0.ctypes.data_as(C.c_void_p), fid.ctypes.data_as(C.c_void_p),
+                               C.c_uint64(args.seed * 7919), C.c_double(0.01))
+    if rc != 0:
+        raise RuntimeError("orc_synth_patches failed (%d)" % rc)
     prob = make_problem(args, g, host, False, sel=(n_pts, n_obs))
-    prob.refs = np.ascontiguousarray(refs[:n_pts])
     ic = _capi.default_interp()
-    so = _capi.default_ba_options(use_inner_iterations=0 if args.no_inner else 1, max_num_iterations=steps,
-                                  linear_solver=args.linear_solver)
-    O.lib().orc_set_num_threads(usable_cpus())
-    cores = O.lib().orc_num_threads()
+    prob.refs, _ = O.refs_compute(prob, ic)
+    setup_s = time.time() - t_setup
+    opts = dict(use_inner_iterations=0 if args.no_inner else 1, linear_solver=args.linear_solver)
+    # which inner kernel: the restatement as the compiler vectorises it, or the reference's own AVX2 header
+    # (oracle/_ref/libpxref.so, bit-identical results) — one LM iteration each, the faster one runs the timed solve
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libpxref.so")
+    kernels = {}
+    for name, enable in (("restated (auto-vectorised)", 0), ("reference AVX2 header", 1)):
+        if enable and (not os.path.exists(ref_so) or lib.orc_use_reference_spline(ref_so.encode(), 1) != 0):
+            continue
+        if not enable:
+            lib.orc_use_reference_spline(b"", 0)
+        t0 = time.time()
+        O.ba_solve(prob.copy(), ic, _capi.default_ba_options(max_num_iterations=1, **opts))
+        kernels[name] = time.time() - t0
+    best = min(kernels, key=kernels.get)
+    lib.orc_use_reference_spline(ref_so.encode() if best.startswith("reference") else b"", 1 if best.startswith("reference") else 0)
+    if warmup > 0:
+        O.ba_solve(prob.copy(), ic, _capi.default_ba_options(max_num_iterations=warmup, **opts))
+    lib.orc_stage_seconds(None, 1)
+    p2 = prob.copy()
     t0 = time.time()
-    s = O.ba_solve(prob, ic, so)
+    s = O.ba_solve(p2, ic, _capi.default_ba_options(max_num_iterations=steps, **opts))
     dt = time.time() - t0
+    st = (C.c_double * 6)()
+    lib.orc_stage_seconds(st, 0)
     iters = max(1, s["num_iterations"] - 1)
-    # subtract nothing: the iteration-zero evaluation is part of a Ceres solve as well
+    whole = n_pts == n_pts_all
     return {"value": n_obs * iters / dt, "unit": "observations/s", "cores": int(cores), "kind": "port",
-            "sample": "%s: first %d points / %d observations of the workload, %d LM iterations, all host threads "
-                      "(CPU restatement of the reference Ceres/AVX2 path; Ceres itself is not installable offline)"
-                      % (label, n_pts, n_obs, iters),
-            "ms_per_lm_iteration_sample": 1e3 * dt / iters, "seconds": dt}
+            "sample": "%s: %s (%d points / %d observations), %d LM iterations from iteration zero after %d warm-up iterations, "
+                      "%d host threads, %s, inner kernel: %s (CPU restatement of the reference Ceres/AVX2 path; Ceres itself is "
+                      "not installable offline)"
+                      % (label, "the whole workload" if whole else "first points of the workload", n_pts, n_obs, iters, warmup,
+                         cores, libname, best),
+            "ms_per_lm_iteration": 1e3 * dt / iters, "seconds": dt, "lm_iterations": iters, "observations": n_obs,
+            "whole_workload": whole, "setup_seconds": setup_s, "final_cost": s["final_cost"],
+            "one_iteration_seconds_by_inner_kernel": kernels,
+            "stage_seconds": dict(zip(["residual+Jacobian evaluation", "cost-only evaluation", "Schur elimination", "reduced solve",
+                                       "back-substitution+model cost", "inner iterations"], [float(v) for v in st]))}
+
+
+def workload_config(args, world, n_obs_rank, inner):
+    L = min(args.track, args.cams)
+    workload = ("synthetic %d cams / %d pts / %d obs per GPU, %d-ch fp16 %dx%d patches, bicubic+L2, Cauchy(0.25)%s"
+                % (args.cams, n_obs_rank // L, n_obs_rank, args.channels, args.ps, args.ps,
+                   ", local co-visibility (window of %d cameras)" % args.covis_window if args.covis_window else ""))
+    return {"workload": workload, "baseline_config": "configs[4]" if args.workload == "configs4" else "configs[2]",
+            "use_inner_iterations": bool(inner), "scaling_mode": args.scaling,
+            "parallelism": "point-sharded x%d, cameras replicated; ONE NCCL all-reduce of the packed reduced-camera blocks per LM "
+                           "iteration, accept/reject scalars over peer mailboxes (NVLink)" % world,
+            "l2_flush": "inputs (%.1f GB of taps per pass) larger than L2" % (n_obs_rank * 16 * args.channels * 2 / 1e9),
+            "timed_iterations": "LM iterations 1..K of a trajectory started at iteration zero (after W warm-up iterations and a reset); "
+                                "both arms time the same iterations",
+            "step": "one LM iteration (step solve + trial-point evaluation%s; the trial evaluation runs in Jacobian mode and is reused "
+                    "as the next linearisation on acceptance)" % (" + inner iterations while ceres' rule keeps them on" if inner else "")}
 
 
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return 0
-    from pixsfm._pixsfm import _capi, _engine
+    inner = 0 if args.no_inner else 1
+    L = min(args.track, args.cams)
+    args.points_per_rank = max(1, args.points // world) if (args.scaling == "strong" and args.impl != "reference") else args.points
 
+    # ------------------------------------------------------------------ reference arm: CPU only, libpxr.so never loaded
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        g = geometry(args, 0)
+        n_obs = len(g["obs_pt"])
+        cb = cpu_arm(args, g, max(1, args.steps), max(0, args.warmup), "reference arm")
+        line = {"impl": "reference", "metric": "featuremetric BA observations/sec", "value": cb["value"],
+                "unit": "observations/s", "n_gpus": args.gpus, "steps": cb["lm_iterations"], "warmup": args.warmup,
+                "ms_per_step": cb["ms_per_lm_iteration"],
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, 1, n_obs, inner), "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    from pixsfm._pixsfm import _capi, _engine
     dist = None
-    if world > 1 and args.impl != "reference":
+    if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -327,68 +434,65 @@ def main():
     refs, _ = _engine.refs_compute(prob, ic, ctx=ctx)
     prob.refs = refs
     setup_s = time.time() - t_setup
+    config = workload_config(args, world, n_obs, inner)
+    x0 = [np.array(a, np.float64, copy=True) for a in (prob.cam_params, prob.qvec, prob.tvec, prob.xyz)]
 
-    inner = 0 if args.no_inner else 1
-    workload = ("synthetic %d cams / %d pts / %d obs per GPU, %d-ch fp16 %dx%d patches, bicubic+L2, Cauchy(0.25)"
-                % (args.cams, args.points, n_obs, args.channels, args.ps, args.ps))
-    config = {"workload": workload, "baseline_config": "configs[2]", "use_inner_iterations": bool(inner),
-              "parallelism": "point-sharded x%d, cameras replicated, NCCL allreduce of the reduced camera system" % world,
-              "l2_flush": "inputs (%.1f GB of taps per pass) larger than L2" % (n_obs * 4096 / 1e9),
-              "step": "one LM iteration (step solve + trial-point evaluation%s; the trial evaluation runs in Jacobian mode and is reused as the next linearisation on acceptance)" % (" + inner iterations while active" if inner else "")}
-
-    if args.impl == "reference":
-        cb = cpu_arm(args, g, d_patches, refs, ctx, max(1, args.steps), "reference arm")
-        line = {"impl": "reference", "metric": "featuremetric BA observations/sec", "value": cb["value"],
-                "unit": "observations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * n_obs / cb["value"],  # full-workload LM iteration extrapolated from the sample rate
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config, "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
-
-    so = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.warmup + args.steps,
-                                  linear_solver=args.linear_solver)
+    so = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=10 ** 6, linear_solver=args.linear_solver)
     h = _engine.BAHandle(prob, ic, so, ctx=ctx)
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.wait_first_sample()
-    # ---- warm-up: W iterations of the trajectory (plus iteration zero)
+    # ---- warm-up: W iterations of the trajectory (plus iteration zero), then back to the start
     sampler.t_load0 = time.time()
     h.iterate(max(args.warmup, 0))
     ctx.sync()
-    if dist is not None:
-        dist.barrier()
+    h.reset(*x0)
+
+    def timed(n):
+        """n LM iterations continuing the handle's trajectory: device time (max over ranks), summary, launches, NCCL calls"""
+        if dist is not None:
+            dist.barrier()
+        c0, l0 = ctx.nccl_collectives(), ctx.kernel_launches()
+        ctx.timer_start()
+        t0 = time.time()
+        summ = h.iterate(n)
+        ms_dev = ctx.timer_stop()
+        wall = time.time() - t0
+        if dist is not None:
+            import torch
+            tt = torch.tensor([ms_dev], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_dev = float(tt.item())
+            dist.barrier()
+        return ms_dev, wall, summ, ctx.kernel_launches() - l0, ctx.nccl_collectives() - c0
+
     h.kernel_timing(enable=1, read=False)
-    launches0 = ctx.kernel_launches()
-    ctx.timer_start()
-    t0 = time.time()
-    sampler.t0 = t0
-    s = h.iterate(args.steps)
-    ms = ctx.timer_stop()
-    wall = time.time() - t0
+    sampler.t0 = time.time()
+    ms, wall, s, launches, ncoll = timed(args.steps)      # includes iteration zero's evaluation, like a ceres solve
     sampler.t1 = time.time()
-    launches = ctx.kernel_launches() - launches0
     clocks = sampler.stop()
     stage_names = ["K1 cost-only", "K1 residual/Jacobian", "K0 projection", "block build", "damping+Schur assembly",
-                   "Cholesky factor", "Cholesky solve", "back-substitution+model cost", "manifold plus",
-                   "inner iterations", "cost reduction", "misc"]
+                   "reduced solve", "Cholesky solve", "back-substitution+model cost", "manifold plus",
+                   "inner iterations", "cost reduction", "NCCL all-reduce of the packed blocks"]
     stage_ms = {}
     for sid, nm in enumerate(stage_names):
         tms, tn = h.kernel_timing(enable=-1, which=sid)
         if tn:
             stage_ms[nm] = {"ms_per_step": tms / max(1, args.steps), "launch_groups": tn}
     k1_ms, k1_n = h.kernel_timing(enable=0, which=1)
-    if dist is not None:
-        import torch
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-        dist.barrier()
-    its = s["iterations"][-args.steps:] if args.steps > 0 else []
+    its = s["iterations"][1:] if args.steps > 0 else []
     steps_done = len(its)
     total_obs = n_obs * world
     value = total_obs * steps_done / (ms / 1e3) if ms > 0 else 0.0
+    # ---- the K iterations after those (inner iterations long switched off): what round 1 reported as the headline
+    h.kernel_timing(enable=1, read=False)
+    ms2, _, s2, _, ncoll2 = timed(args.steps)
+    k1b_ms, k1b_n = h.kernel_timing(enable=0, which=1)
+    steps2 = max(0, len(s2["iterations"]) - len(s["iterations"]))
+    steady = {"ms_per_step": ms2 / max(1, steps2), "value": total_obs * steps2 / (ms2 / 1e3) if ms2 > 0 and steps2 else None,
+              "steps": steps2, "iterations": "LM iterations %d..%d of the same trajectory" % (steps_done + 1, steps_done + steps2),
+              "K1_avg_launch_ms": k1b_ms / k1b_n if k1b_n else None,
+              "nccl_collectives_per_lm_iteration": ncoll2 / max(1, steps2) if world > 1 else 0}
 
     # ---- roofline of the dominant kernel (K1, Jacobian mode), CUDA events inside the timed region
     peaks = {}
@@ -397,18 +501,20 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo_bytes = 16 * args.channels * 2 + args.channels * 4 + 128        # taps + fp32-equivalent reference + metadata
     k1_avg_ms = k1_ms / k1_n if k1_n else float("nan")
-    achieved = ALGO_BYTES_PER_OBS * n_obs / (k1_avg_ms * 1e-3) / 1e9 if k1_n else None
+    achieved = algo_bytes * n_obs / (k1_avg_ms * 1e-3) / 1e9 if k1_n else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+        if args.workload == "configs2" and args.scaling == "weak":
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"kernel": "fm_eval_kernel<half,128,JAC> (K1 residual/Jacobian)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "avg_launch_ms": k1_avg_ms, "launches_timed": k1_n,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_OBS * n_obs,
+                "algorithmic_bytes_per_launch": algo_bytes * n_obs,
                 "share_of_step": (k1_ms / ms) if ms else None}
 
     # ---- e2e: the public one-shot call on HOST buffers (upload + K iterations + read-back)
@@ -448,20 +554,20 @@ def main():
             if dist is not None:
                 dist.barrier()
             t0 = time.time()
-            s2 = _engine.ba_run(prob_h, ic, so2, ctx=ctx)
+            s3 = _engine.ba_run(prob_h, ic, so2, ctx=ctx)
             dt = time.time() - t0
             if dist is not None:
                 import torch
                 tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                 dt = float(tt.item())
-            it2 = max(1, s2["num_iterations"] - 1)
-            e2e = {"value": total_obs * it2 / dt, "unit": "observations/s",
-                   "h2d_bytes_per_step": s2["h2d_bytes"] / it2, "d2h_bytes_per_step": s2["d2h_bytes"] / it2,
-                   "seconds": dt, "library_seconds": s2["total_time_s"], "lm_loop_seconds": s2["solve_time_s"],
-                   "lm_iterations": it2, "pinned_host": bool(pinned),
+            it3 = max(1, s3["num_iterations"] - 1)
+            e2e = {"value": total_obs * it3 / dt, "unit": "observations/s",
+                   "h2d_bytes_per_step": s3["h2d_bytes"] / it3, "d2h_bytes_per_step": s3["d2h_bytes"] / it3,
+                   "seconds": dt, "library_seconds": s3["total_time_s"], "lm_loop_seconds": s3["solve_time_s"],
+                   "lm_iterations": it3, "pinned_host": bool(pinned),
                    "call": "pxr_ba_run (upload %.1f GB of patches + solve + read back)" % (pbytes / 1e9),
-                   "final_cost": s2["final_cost"]}
+                   "final_cost": s3["final_cost"]}
             if pinned:
                 del host
                 ctx.lib.pxr_host_free_pinned(hp)
@@ -471,28 +577,29 @@ def main():
     cb = None
     if rank == 0 and world == 1 and args.cpu_sample_points > 0:
         try:
-            cb = cpu_arm(args, g, d_patches, refs, ctx, 2, "cpu_baseline")
+            # bounded sample (the full-workload CPU solve is what `--impl reference` runs)
+            cb = cpu_arm(args, g, 2, 0, "cpu_baseline", max_points=args.cpu_sample_points)
         except Exception as ex:
             cb = {"value": None, "error": repr(ex)}
 
     if rank == 0:
         line = {"metric": "featuremetric BA observations/sec", "value": value, "unit": "observations/s",
                 "n_gpus": world, "steps": steps_done, "warmup": args.warmup, "ms_per_step": ms / max(1, steps_done),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp16 taps, fp32 horizontal, fp64 vertical/solve)",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f64 (fp16 taps, fp32 horizontal, fp64 vertical/solve)",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cb, "stage_ms": stage_ms,
-                "lm": {"inner_iterations_in_timed_steps": "inner iterations" in stage_ms,
-                       "inner_iterations_note": "Ceres rule (inner_iteration_tolerance): the solver itself stops running inner "
-                                                "iterations once their relative decrease is below tolerance (on the default "
-                                                "trajectory after LM iteration 2); %s. e2e and the reference arm both solve "
-                                                "from iteration 0 and include them"
-                                                % ("some of the timed steps still ran them" if "inner iterations" in stage_ms
-                                                   else "they ended during warm-up, none ran in the timed steps"),
+                "roofline": roofline, "cpu_baseline": cb, "stage_ms": stage_ms, "steady_state": steady,
+                "multi_gpu": {"nccl_collectives_in_timed_region": int(ncoll), "lm_iterations_in_timed_region": steps_done,
+                              "nccl_collectives_per_lm_iteration": (ncoll / max(1, steps_done)) if world > 1 else 0,
+                              "scalar_exchange": ("peer mailboxes over NVLink" if ctx.mailbox_ready() else "NCCL") if world > 1 else "none (1 GPU)"},
+                "lm": {"inner_iteration_rounds_in_timed_steps": int(s["num_inner_iteration_steps"]),
                        "successful_steps": int(sum(i["step_is_successful"] for i in its)), "steps": steps_done,
-                       "cost_first": its[0]["cost"] if its else None, "cost_last": its[-1]["cost"] if its else None,
+                       "cost_first": s["iterations"][0]["cost"] if s["iterations"] else None,
+                       "cost_last": its[-1]["cost"] if its else None,
                        "wall_ms_per_step": 1e3 * wall / max(1, steps_done)},
                 "setup_seconds": setup_s}
         print(json.dumps(line))
+    h.close()
     _engine.device_free(d_patches, ctx)
     if dist is not None:
         dist.destroy_process_group()

@@ -256,6 +256,11 @@ int pxr_ba_iterate(pxr_ba* ba, int n_iterations, pxr_summary* summary);
  * total_ms/count (optional) receive the summed device time and number of recorded launches. */
 int pxr_ba_kernel_timing(pxr_ba* ba, int enable, int which, double* total_ms, int* count);
 int pxr_ba_read_params(pxr_ba* ba, double* cam_params, double* qvec, double* tvec, double* xyz);
+/* Puts the resident problem back to the given parameters (same array shapes as in the desc) and forgets the LM
+ * trajectory; patches, topology, work space and captured graphs stay.  bench.py: W warm-up iterations, reset, then K
+ * timed iterations FROM ITERATION ZERO, like the CPU arm.  (The reference's optimizers are one-shot objects,
+ * bundle_optimizer.h:121-122; this is what constructing a second one on the same FeatureView amounts to.) */
+int pxr_ba_reset(pxr_ba* ba, const double* cam_params, const double* qvec, const double* tvec, const double* xyz);
 int pxr_ba_destroy(pxr_ba* ba);
 /* one-shot convenience = FeatureReferenceBundleOptimizer.run: upload, solve, write back into desc arrays */
 int pxr_ba_run(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,

@@ -1,6 +1,8 @@
 // oracle/orc_api.cc — TEST INFRASTRUCTURE ONLY: C entry points of the CPU oracle
 // (liboracle.so), loaded with ctypes by tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs.  Never linked into libpxr.so.
+#include <dlfcn.h>
+
 #include <chrono>
 #include <cstring>
 
@@ -21,6 +23,93 @@ static InterpConfig ToInterp(const pxr_interp_config* c) {
 extern "C" {
 
 int orc_num_threads() { return omp_get_max_threads(); }
+
+// The reference's own AVX2 spline as the inner kernel of every bicubic evaluation (see orc_core.h::RefSpline):
+// path = oracle/_ref/libpxref.so.  Returns 0 when all three entry points resolved; enable = 0 switches back.
+int orc_use_reference_spline(const char* path, int enable) {
+  RefSpline& R = GlobalRefSpline();
+  if (!enable) { R = RefSpline(); return 0; }
+  void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return 1;
+  RefSpline r;
+  r.f16 = (decltype(r.f16))dlsym(h, "ref_spline_f16");
+  r.f32 = (decltype(r.f32))dlsym(h, "ref_spline_f32");
+  r.f64 = (decltype(r.f64))dlsym(h, "ref_spline_f64");
+  if (!r.f16 || !r.f32 || !r.f64) return 2;
+  R = r;
+  return 0;
+}
+
+// wall-clock split of the solves since the last reset (orc_ba.h::StageClock): evaluation with Jacobians, cost-only
+// evaluation, Schur elimination, reduced solve, back-substitution + model cost, inner iterations
+void orc_stage_seconds(double* out6, int reset) {
+  StageClock& c = GlobalStageClock();
+  if (out6) for (int i = 0; i < 6; ++i) out6[i] = c.t[i];
+  if (reset) c = StageClock();
+}
+
+// CPU counterpart of pxr_synth_patches_device (pixel-perfect-sfm_b200/csrc/pxr_synth.cu): the same counter-based hash,
+// field model and noise, so that bench.py's reference arm can build its workload WITHOUT the CUDA library.  (libm's
+// logf / cosf / 1/sqrtf stand in for the device's fast-math intrinsics: same distribution, last bits differ.)
+static inline uint64_t Mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+static inline float NormalFrom(uint64_t key) {
+  const uint64_t h = Mix64(key);
+  const float u1 = ((uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);
+  const float u2 = (uint32_t)(h & 0xFFFFFF) * (1.0f / 16777216.0f);
+  return std::sqrt(-2.0f * std::log(u1)) * std::cos(6.2831853f * u2);
+}
+int orc_synth_patches(uint16_t* out, int64_t n_patches, int ps, int C, const double* uv0, const int64_t* field,
+                      uint64_t seed, double noise_sigma) {
+  if (!out || !uv0 || !field || n_patches < 1 || ps < 1 || C < 2 || (C & 1) || C > 1024) return 1;
+  const float noise = (float)noise_sigma;
+  const int npx = ps * ps;
+#pragma omp parallel
+  {
+    std::vector<float> coef((size_t)4 * C), vals(C), nz(C);
+    std::vector<uint64_t> keys(C);
+#pragma omp for schedule(static)
+    for (int64_t pi = 0; pi < n_patches; ++pi) {
+      const int64_t fid = field[pi];
+      for (int i = 0; i < 4 * C; ++i) {
+        const int k = i / C, c = i % C;
+        const float sd = k == 0 ? 1.0f : 0.15f;
+        coef[i] = sd * NormalFrom(seed ^ Mix64((uint64_t)fid * 4099ull + (uint64_t)k * 1000003ull + (uint64_t)c * 7919ull + 17ull));
+      }
+      for (int px = 0; px < npx; ++px) {
+        const int row = px / ps, col = px % ps;
+        const float du = (float)((double)col - uv0[2 * pi]);
+        const float dv = (float)((double)row - uv0[2 * pi + 1]);
+        const float dudv = du * dv;
+        float n2 = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const float f = coef[c] + coef[C + c] * du + coef[2 * C + c] * dv + coef[3 * C + c] * dudv;
+          vals[c] = f; n2 += f * f;
+        }
+        const float ninv = 1.0f / std::sqrt(n2);
+        if (noise > 0.f) {
+          const uint64_t key0 = seed * 0x100000001B3ull + ((uint64_t)pi * npx + px) * (uint64_t)C;
+          for (int c = 0; c < C; ++c) {           // hash, then Box-Muller: a plain loop the compiler can vectorise
+            const uint64_t h = Mix64(key0 + c);
+            const float u1 = ((uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);
+            const float u2 = (uint32_t)(h & 0xFFFFFF) * (1.0f / 16777216.0f);
+            nz[c] = std::sqrt(-2.0f * std::log(u1)) * std::cos(6.2831853f * u2);
+          }
+          for (int c = 0; c < C; ++c) vals[c] = vals[c] * ninv + noise * nz[c];
+        } else {
+          for (int c = 0; c < C; ++c) vals[c] *= ninv;
+        }
+        half_t* dst = reinterpret_cast<half_t*>(out) + ((size_t)pi * npx + px) * C;
+        for (int c = 0; c < C; ++c) dst[c] = (half_t)vals[c];
+      }
+    }
+  }
+  return 0;
+}
 void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 // a1 — single spline evaluations (pin against oracle/_ref)

@@ -318,6 +318,18 @@ inline bool SchurJacobiPCG(int n, const std::vector<double>& S, const std::vecto
   return true;
 }
 
+// wall-clock split of a solve (bench.py prints it next to the CPU number): 0 residual+Jacobian evaluation,
+// 1 cost-only evaluation, 2 Schur elimination, 3 reduced solve, 4 back-substitution, 5 inner iterations
+struct StageClock {
+  double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  struct Scope {
+    double* acc; double t0;
+    explicit Scope(double* a) : acc(a), t0(omp_get_wtime()) {}
+    ~Scope() { *acc += omp_get_wtime() - t0; }
+  };
+};
+inline StageClock& GlobalStageClock() { static StageClock c; return c; }
+
 class BAEvaluator : public TREvaluator {
  public:
   const pxr_ba_desc& d;
@@ -424,9 +436,14 @@ class BAEvaluator : public TREvaluator {
     return 0.5 * rho[0];
   }
 
+  // An observation's camera columns are the columns of its image (pose block, then the intrinsics block of the image's
+  // camera), so J_c^T J_c lands in ONE (dc x dc) block per image: every thread accumulates its own [n_images] blocks and
+  // the blocks are summed and scattered into Hcc once (what ceres' SchurEliminator does with per-thread buffers).
   bool Evaluate(const double* x, double* cost, bool with_jac) override {
+    StageClock::Scope clk(&GlobalStageClock().t[with_jac ? 0 : 1]);
     const int nc = L.n_cam_local;
     const int nthreads = omp_get_max_threads();
+    const int BD = kMaxDc;
     double total = 0;
     if (with_jac) {
       std::fill(Hcc.begin(), Hcc.end(), 0.0);
@@ -434,16 +451,21 @@ class BAEvaluator : public TREvaluator {
       std::fill(Hpp.begin(), Hpp.end(), 0.0);
       std::fill(gp.begin(), gp.end(), 0.0);
     }
-    // small systems: per-thread accumulators (deterministic given the schedule); large systems:
-    // atomic adds into the shared blocks (what ceres' SchurEliminator does with block locks)
-    const bool shared_acc = (size_t)nc * nc > (size_t)256 * 256;
     std::vector<std::vector<double>> tH(with_jac ? nthreads : 0), tg(with_jac ? nthreads : 0);
+    std::vector<int> img_dc(d.n_images, 0), img_cols((size_t)d.n_images * BD, -1);
+    for (int i = 0; i < d.n_images; ++i) {       // [pose block | intrinsics block], the order LinearizeBlock emits
+      int dc = 0;
+      for (int a = 0; a < L.pose_dim[i]; ++a) img_cols[(size_t)i * BD + dc++] = L.pose_off[i] + a;
+      const int cam = d.img_cam[i];
+      for (int a = 0; a < L.intr_dim[cam]; ++a) img_cols[(size_t)i * BD + dc++] = L.intr_off[cam] + a;
+      img_dc[i] = dc;
+    }
 #pragma omp parallel reduction(+ : total)
     {
       const int tid = omp_get_thread_num();
       std::vector<double> r, Jc, Jp, Jamb, scratch;
       int cols[kMaxDc];
-      if (with_jac && !shared_acc) { tH[tid].assign((size_t)nc * nc, 0.0); tg[tid].assign(nc, 0.0); }
+      if (with_jac) { tH[tid].assign((size_t)d.n_images * BD * BD, 0.0); tg[tid].assign((size_t)d.n_images * BD, 0.0); }
 #pragma omp for schedule(dynamic, 16)
       for (int64_t p = 0; p < d.n_points; ++p) {
         for (int64_t o = L.pt_begin[p]; o < L.pt_begin[p + 1]; ++o) {
@@ -454,52 +476,59 @@ class BAEvaluator : public TREvaluator {
           if (!with_jac) continue;
           const int C = d.channels;
           const bool pvar = L.point_off[p] >= 0;
-          double* Hc = shared_acc ? Hcc.data() : tH[tid].data();
-          double* g = shared_acc ? gc.data() : tg[tid].data();
-          for (int a = 0; a < dc; ++a) {
-            double ga = 0;
-            for (int i = 0; i < C; ++i) ga += Jc[(size_t)i * kMaxDc + a] * r[i];
-            if (shared_acc) {
-#pragma omp atomic
-              g[cols[a]] += ga;
-            } else g[cols[a]] += ga;
-            for (int b = 0; b < dc; ++b) {
-              double v = 0;
-              for (int i = 0; i < C; ++i) v += Jc[(size_t)i * kMaxDc + a] * Jc[(size_t)i * kMaxDc + b];
-              if (shared_acc) {
-#pragma omp atomic
-                Hc[(size_t)cols[a] * nc + cols[b]] += v;
-              } else Hc[(size_t)cols[a] * nc + cols[b]] += v;
+          const int img = d.obs_img[o];
+          double* Hb = &tH[tid][(size_t)img * BD * BD];
+          double* gb = &tg[tid][(size_t)img * BD];
+          // rank-1 accumulation per residual row: the inner loops run over contiguous columns (vectorisable)
+          for (int i = 0; i < C; ++i) {
+            const double* row = &Jc[(size_t)i * kMaxDc];
+            const double ri = r[i];
+            for (int a = 0; a < dc; ++a) {
+              const double ja = row[a];
+              gb[a] += ja * ri;
+              double* ha = Hb + a * BD;
+              for (int b = 0; b < dc; ++b) ha[b] += ja * row[b];
             }
           }
           Wdc[o] = dc;
           for (int a = 0; a < dc; ++a) Wcols[(size_t)o * kMaxDc + a] = cols[a];
           if (pvar) {
-            for (int a = 0; a < 3; ++a) {
-              double ga = 0;
-              for (int i = 0; i < C; ++i) ga += Jp[(size_t)i * 3 + a] * r[i];
-              gp[(size_t)p * 3 + a] += ga;
-              for (int b = 0; b < 3; ++b) {
-                double v = 0;
-                for (int i = 0; i < C; ++i) v += Jp[(size_t)i * 3 + a] * Jp[(size_t)i * 3 + b];
-                Hpp[(size_t)p * 9 + a * 3 + b] += v;
-              }
+            double hp[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gpa[3] = {0, 0, 0};
+            double* Wo = &W[(size_t)o * kMaxDc * 3];
+            for (int k = 0; k < dc * 3; ++k) Wo[k] = 0.0;
+            for (int i = 0; i < C; ++i) {
+              const double* jp = &Jp[(size_t)i * 3];
+              const double* row = &Jc[(size_t)i * kMaxDc];
+              const double ri = r[i];
+              for (int a = 0; a < 3; ++a) { gpa[a] += jp[a] * ri; for (int b = 0; b < 3; ++b) hp[a * 3 + b] += jp[a] * jp[b]; }
+              for (int a = 0; a < dc; ++a) { const double ja = row[a]; Wo[a * 3] += ja * jp[0]; Wo[a * 3 + 1] += ja * jp[1]; Wo[a * 3 + 2] += ja * jp[2]; }
             }
-            for (int a = 0; a < dc; ++a)
-              for (int b = 0; b < 3; ++b) {
-                double v = 0;
-                for (int i = 0; i < C; ++i) v += Jc[(size_t)i * kMaxDc + a] * Jp[(size_t)i * 3 + b];
-                W[((size_t)o * kMaxDc + a) * 3 + b] = v;
-              }
+            for (int a = 0; a < 3; ++a) gp[(size_t)p * 3 + a] += gpa[a];
+            for (int k = 0; k < 9; ++k) Hpp[(size_t)p * 9 + k] += hp[k];
           }
         }
       }
     }
     if (with_jac) {
-      for (int t = 0; t < nthreads; ++t) {
-        if (tH[t].empty()) continue;
-        for (size_t i = 0; i < Hcc.size(); ++i) Hcc[i] += tH[t][i];
-        for (int i = 0; i < nc; ++i) gc[i] += tg[t][i];
+      // sum the threads' image blocks (parallel over images), then scatter every image's block into Hcc / gc
+      std::vector<double>& H0 = tH[0];
+      std::vector<double>& g0 = tg[0];
+#pragma omp parallel for schedule(static)
+      for (int img = 0; img < d.n_images; ++img)
+        for (int t = 1; t < nthreads; ++t) {
+          if (tH[t].empty()) continue;
+          const double* hs = &tH[t][(size_t)img * BD * BD]; double* hd = &H0[(size_t)img * BD * BD];
+          for (int k = 0; k < BD * BD; ++k) hd[k] += hs[k];
+          const double* gs = &tg[t][(size_t)img * BD]; double* gd = &g0[(size_t)img * BD];
+          for (int k = 0; k < BD; ++k) gd[k] += gs[k];
+        }
+      for (int img = 0; img < d.n_images; ++img) {
+        const int dc = img_dc[img];
+        const int* cl = &img_cols[(size_t)img * BD];
+        for (int a = 0; a < dc; ++a) {
+          gc[cl[a]] += g0[(size_t)img * BD + a];
+          for (int b = 0; b < dc; ++b) Hcc[(size_t)cl[a] * nc + cl[b]] += H0[((size_t)img * BD + a) * BD + b];
+        }
       }
     }
     *cost = total;
@@ -526,37 +555,60 @@ class BAEvaluator : public TREvaluator {
     std::vector<double> S(Hcc), rhs(nc);
     for (int i = 0; i < nc; ++i) { S[(size_t)i * nc + i] += D2[i]; rhs[i] = -gc[i]; }
     std::vector<double> inv((size_t)d.n_points * 9, 0.0);
+    std::vector<double> T((size_t)d.n_obs * kMaxDc * 3, 0.0);
     bool ok = true;
-    for (int64_t p = 0; p < d.n_points; ++p) {
-      if (L.point_off[p] < 0) continue;
-      double H[9];
-      for (int k = 0; k < 9; ++k) H[k] = Hpp[(size_t)p * 9 + k];
-      for (int a = 0; a < 3; ++a) H[a * 4] += D2[L.point_off[p] + a];
-      double* iv = &inv[(size_t)p * 9];
-      if (!Invert3x3Sym(H, iv)) { ok = false; break; }
-      const double* g = &gp[(size_t)p * 3];
-      for (int64_t oi = L.pt_begin[p]; oi < L.pt_begin[p + 1]; ++oi) {
-        const int dci = Wdc[oi];
-        double T[kMaxDc * 3];
-        for (int a = 0; a < dci; ++a)
-          for (int b = 0; b < 3; ++b) {
-            double v = 0;
-            for (int k = 0; k < 3; ++k) v += W[((size_t)oi * kMaxDc + a) * 3 + k] * iv[k * 3 + b];
-            T[a * 3 + b] = v;
-          }
-        for (int a = 0; a < dci; ++a) {
-          const int ca = Wcols[(size_t)oi * kMaxDc + a];
-          rhs[ca] += T[a * 3 + 0] * g[0] + T[a * 3 + 1] * g[1] + T[a * 3 + 2] * g[2];
-        }
-        for (int64_t oj = L.pt_begin[p]; oj < L.pt_begin[p + 1]; ++oj) {
-          const int dcj = Wdc[oj];
-          for (int a = 0; a < dci; ++a) {
-            const int ca = Wcols[(size_t)oi * kMaxDc + a];
-            for (int b = 0; b < dcj; ++b) {
-              const int cb = Wcols[(size_t)oj * kMaxDc + b];
+    {
+      StageClock::Scope clk(&GlobalStageClock().t[2]);
+      // (H_pp + D)^-1 and T = W (H_pp + D)^-1 per observation: independent per point
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+      for (int64_t p = 0; p < d.n_points; ++p) {
+        if (L.point_off[p] < 0) continue;
+        double H[9];
+        for (int k = 0; k < 9; ++k) H[k] = Hpp[(size_t)p * 9 + k];
+        for (int a = 0; a < 3; ++a) H[a * 4] += D2[L.point_off[p] + a];
+        double* iv = &inv[(size_t)p * 9];
+        if (!Invert3x3Sym(H, iv)) { ok = false; continue; }
+        for (int64_t oi = L.pt_begin[p]; oi < L.pt_begin[p + 1]; ++oi)
+          for (int a = 0; a < Wdc[oi]; ++a)
+            for (int b = 0; b < 3; ++b) {
               double v = 0;
-              for (int k = 0; k < 3; ++k) v += T[a * 3 + k] * W[((size_t)oj * kMaxDc + b) * 3 + k];
-              S[(size_t)ca * nc + cb] -= v;
+              for (int k = 0; k < 3; ++k) v += W[((size_t)oi * kMaxDc + a) * 3 + k] * iv[k * 3 + b];
+              T[((size_t)oi * kMaxDc + a) * 3 + b] = v;
+            }
+      }
+      if (ok && nc > 0) {
+        // S -= sum_p sum_{i,j} T_i W_j^T, rhs += sum T_i g_p.  Every thread owns a contiguous range of ROWS of S and
+        // visits all observation pairs, keeping only the block rows whose column id falls in its range: no locks, no
+        // atomics, and a fixed summation order per entry (ceres' SchurEliminator is threaded over point chunks with
+        // per-block locks; the arithmetic per pair is the same).
+#pragma omp parallel
+        {
+          const int nt = omp_get_num_threads(), tid = omp_get_thread_num();
+          const int r0 = (int)((int64_t)nc * tid / nt), r1 = (int)((int64_t)nc * (tid + 1) / nt);
+          for (int64_t p = 0; p < d.n_points; ++p) {
+            if (L.point_off[p] < 0) continue;
+            const double* g = &gp[(size_t)p * 3];
+            for (int64_t oi = L.pt_begin[p]; oi < L.pt_begin[p + 1]; ++oi) {
+              const int dci = Wdc[oi];
+              const int* ci = &Wcols[(size_t)oi * kMaxDc];
+              // an observation's columns are ascending: [pose block | intrinsics block]; skip it when none is mine
+              bool mine = false;
+              for (int a = 0; a < dci; ++a) if (ci[a] >= r0 && ci[a] < r1) { mine = true; break; }
+              if (!mine) continue;
+              const double* Ti = &T[(size_t)oi * kMaxDc * 3];
+              for (int a = 0; a < dci; ++a) {
+                const int ca = ci[a];
+                if (ca < r0 || ca >= r1) continue;
+                rhs[ca] += Ti[a * 3 + 0] * g[0] + Ti[a * 3 + 1] * g[1] + Ti[a * 3 + 2] * g[2];
+                double* Srow = &S[(size_t)ca * nc];
+                for (int64_t oj = L.pt_begin[p]; oj < L.pt_begin[p + 1]; ++oj) {
+                  const int dcj = Wdc[oj];
+                  const int* cj = &Wcols[(size_t)oj * kMaxDc];
+                  const double* Wj = &W[(size_t)oj * kMaxDc * 3];
+                  for (int b = 0; b < dcj; ++b)
+                    Srow[cj[b]] -= Ti[a * 3] * Wj[b * 3] + Ti[a * 3 + 1] * Wj[b * 3 + 1] + Ti[a * 3 + 2] * Wj[b * 3 + 2];
+                }
+              }
             }
           }
         }
@@ -565,15 +617,20 @@ class BAEvaluator : public TREvaluator {
     if (!ok) return false;
     S_last = S; rhs_last = rhs;
     int lin_iters = 1;
-    if (eo.iterative_schur && nc > 0) {
-      std::vector<std::pair<int, int>> blocks;
-      for (int i = 0; i < d.n_images; ++i) if (L.pose_off[i] >= 0) blocks.push_back({L.pose_off[i], L.pose_dim[i]});
-      for (int c = 0; c < d.n_cameras; ++c) if (L.intr_off[c] >= 0) blocks.push_back({L.intr_off[c], L.intr_dim[c]});
-      std::vector<double> xs;
-      if (!SchurJacobiPCG(nc, S, rhs, blocks, eo.max_linear_solver_iterations, eo.eta, &xs, &lin_iters)) return false;
-      rhs = xs;
-    } else if (nc > 0 && !CholeskySolveInPlace(nc, S, rhs)) return false;
+    {
+      StageClock::Scope clk(&GlobalStageClock().t[3]);
+      if (eo.iterative_schur && nc > 0) {
+        std::vector<std::pair<int, int>> blocks;
+        for (int i = 0; i < d.n_images; ++i) if (L.pose_off[i] >= 0) blocks.push_back({L.pose_off[i], L.pose_dim[i]});
+        for (int c = 0; c < d.n_cameras; ++c) if (L.intr_off[c] >= 0) blocks.push_back({L.intr_off[c], L.intr_dim[c]});
+        std::vector<double> xs;
+        if (!SchurJacobiPCG(nc, S, rhs, blocks, eo.max_linear_solver_iterations, eo.eta, &xs, &lin_iters)) return false;
+        rhs = xs;
+      } else if (nc > 0 && !CholeskySolveInPlace(nc, S, rhs)) return false;
+    }
+    StageClock::Scope clk(&GlobalStageClock().t[4]);
     for (int i = 0; i < nc; ++i) delta[i] = rhs[i];
+#pragma omp parallel for schedule(static)
     for (int64_t p = 0; p < d.n_points; ++p) {
       if (L.point_off[p] < 0) continue;
       double v[3] = {-gp[(size_t)p * 3], -gp[(size_t)p * 3 + 1], -gp[(size_t)p * 3 + 2]};
@@ -592,14 +649,17 @@ class BAEvaluator : public TREvaluator {
 
   double ModelCostChange(const double* delta) const override {
     // -(J d)^T (r + J d / 2) = -g^T d - d^T H d / 2, H = J^T J (undamped)
+    StageClock::Scope clk(&GlobalStageClock().t[4]);
     const int nc = L.n_cam_local;
     double gd = 0, dHd = 0;
+#pragma omp parallel for schedule(static) reduction(+ : gd, dHd)
     for (int i = 0; i < nc; ++i) {
       gd += gc[i] * delta[i];
       double row = 0;
       for (int j = 0; j < nc; ++j) row += Hcc[(size_t)i * nc + j] * delta[j];
       dHd += delta[i] * row;
     }
+#pragma omp parallel for schedule(static) reduction(+ : gd, dHd)
     for (int64_t p = 0; p < d.n_points; ++p) {
       if (L.point_off[p] < 0) continue;
       const double* dp = delta + L.point_off[p];
@@ -694,6 +754,7 @@ class PointEvaluator : public TREvaluator {
 };
 
 inline void BAEvaluator::InnerIterations(double* x) {
+  StageClock::Scope clk(&GlobalStageClock().t[5]);
   std::vector<double> xin(x, x + L.n_ambient);
 #pragma omp parallel for schedule(dynamic, 8)
   for (int64_t p = 0; p < d.n_points; ++p) {

@@ -125,8 +125,45 @@ struct Patch {
 //            in `dtype` (double by default; float when use_float_simd, :619-623).
 //   C <  8 : ceres::CubicHermiteSpline in double (:230-262).
 // ---------------------------------------------------------------------------
+// Optional inner kernel: the reference's own AVX2 spline (pixsfm/base/src/cubic_hermite_spline_simd.h, compiled
+// verbatim into oracle/_ref/libpxref.so).  orc_use_reference_spline() resolves the three entry points with dlopen;
+// the restatement below stays the default and is pinned bit-exact against it (tests/test_oracle_golden.py), so
+// switching changes speed, not results.  Used by the timed CPU arm of bench.py.
+struct RefSpline {
+  int (*f16)(int, const uint16_t*, const uint16_t*, const uint16_t*, const uint16_t*, double, double*, double*) = nullptr;
+  int (*f32)(int, const float*, const float*, const float*, const float*, double, double*, double*) = nullptr;
+  int (*f64)(int, const double*, const double*, const double*, const double*, double, double*, double*) = nullptr;
+};
+inline RefSpline& GlobalRefSpline() { static RefSpline r; return r; }
+
+// BiCubicInterpolator::EvaluateSIMD (interpolation.h:177-218) through the verbatim header: four horizontal splines over
+// the C-contiguous taps of each window row, then the vertical pass in fp64 over the four rows of values / x-derivatives.
+inline bool BiCubicRef(const Patch& g, double r, double c, double* f, double* dfdr, double* dfdc) {
+  const RefSpline& R = GlobalRefSpline();
+  const int C = g.c;
+  if (C < 8 || C > 256 || !R.f64) return false;
+  if ((g.dtype == F16 && !R.f16) || (g.dtype == F32 && !R.f32)) return false;
+  const int row = (int)std::floor(r), col = (int)std::floor(c);
+  const double xc = c - col, xr = r - row;
+  double fi[4][256], di[4][256];
+  for (int i = 0; i < 4; ++i) {
+    size_t o[4];
+    for (int j = 0; j < 4; ++j) o[j] = g.Offset(row - 1 + i, col - 1 + j);
+    int rc;
+    if (g.dtype == F16) { const uint16_t* d = (const uint16_t*)g.data; rc = R.f16(C, d + o[0], d + o[1], d + o[2], d + o[3], xc, fi[i], di[i]); }
+    else if (g.dtype == F32) { const float* d = (const float*)g.data; rc = R.f32(C, d + o[0], d + o[1], d + o[2], d + o[3], xc, fi[i], di[i]); }
+    else { const double* d = (const double*)g.data; rc = R.f64(C, d + o[0], d + o[1], d + o[2], d + o[3], xc, fi[i], di[i]); }
+    if (rc != 0) return false;
+  }
+  double unused[256];
+  if (R.f64(C, fi[0], fi[1], fi[2], fi[3], xr, f, dfdr) != 0) return false;
+  if (dfdc && R.f64(C, di[0], di[1], di[2], di[3], xr, dfdc, unused) != 0) return false;
+  return true;
+}
+
 inline void BiCubic(const Patch& g, double r, double c, bool use_float_simd, double* f,
                     double* dfdr, double* dfdc) {
+  if (!use_float_simd && GlobalRefSpline().f64 && BiCubicRef(g, r, c, f, dfdr, dfdc)) return;
   const int row = (int)std::floor(r);
   const int col = (int)std::floor(c);
   const int C = g.c;

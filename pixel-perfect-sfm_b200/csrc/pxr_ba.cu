@@ -1241,6 +1241,23 @@ int pxr_ba_read_params(pxr_ba* ba, double* cam_params, double* qvec, double* tve
   if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
   return reinterpret_cast<BA*>(ba)->read_params(cam_params, qvec, tvec, xyz);
 }
+int pxr_ba_reset(pxr_ba* ba, const double* cam_params, const double* qvec, const double* tvec, const double* xyz) {
+  if (!ba || !cam_params || !qvec || !tvec) return fail(PXR_ERR_INVALID_ARGUMENT, "NULL argument");
+  BA* b = reinterpret_cast<BA*>(ba);
+  PXR_CUDA(cudaSetDevice(b->ctx->device));
+  cudaStream_t s = b->ctx->stream;
+  if (b->n_points > 0 && !xyz) return fail(PXR_ERR_INVALID_ARGUMENT, "xyz is NULL");
+  for (int k = 0; k < 2; ++k) {
+    PXR_CUDA(cudaMemcpyAsync(b->cam[k].p, cam_params, (size_t)b->n_cameras * kMaxK * 8, cudaMemcpyHostToDevice, s));
+    PXR_CUDA(cudaMemcpyAsync(b->q[k].p, qvec, (size_t)b->n_images * 4 * 8, cudaMemcpyHostToDevice, s));
+    PXR_CUDA(cudaMemcpyAsync(b->t[k].p, tvec, (size_t)b->n_images * 3 * 8, cudaMemcpyHostToDevice, s));
+    if (b->n_points > 0) PXR_CUDA(cudaMemcpyAsync(b->X[k].p, xyz, (size_t)b->n_points * 3 * 8, cudaMemcpyHostToDevice, s));
+  }
+  PXR_CUDA(cudaStreamSynchronize(s));
+  b->cur = 0;
+  b->lm = LMState();
+  return PXR_OK;
+}
 int pxr_ba_run(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp_config* interp,
                const pxr_solver_options* opt, pxr_summary* summary) {
   const auto t0 = std::chrono::steady_clock::now();

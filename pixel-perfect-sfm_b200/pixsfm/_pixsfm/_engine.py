@@ -84,6 +84,11 @@ class BAHandle:
         p = self.problem
         _capi.check(self.lib.pxr_ba_read_params(self.handle, _p(p.cam_params), _p(p.qvec), _p(p.tvec), _p(p.xyz)))
 
+    def reset(self, cam_params, qvec, tvec, xyz):
+        """pxr_ba_reset: back to the given parameters, LM trajectory forgotten (patches / work space stay resident)"""
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (cam_params, qvec, tvec, xyz)]
+        _capi.check(self.lib.pxr_ba_reset(self.handle, *[_p(a) for a in arrs]))
+
     def time_stage(self, stage, iters):
         ms = C.c_double()
         _capi.check(self.lib.pxr_ba_time_stage(self.handle, int(stage), int(iters), C.byref(ms)))
