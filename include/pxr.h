@@ -285,6 +285,16 @@ int pxr_ba_estimate_device_bytes(const pxr_ba_desc* desc, const pxr_solver_optio
  *  cost    scalar       sum 0.5*rho(||r||^2) */
 int pxr_ba_evaluate(pxr_ba* ba, double* sq_norm, double* gtr, double* gtg, double* xy,
                     double* residuals, double* cost);
+/* The cost-functor surface: what a ceres::CostFunction built by the reference's `_residuals` factories returns from
+ * Evaluate() (residuals/bindings.cc:14-30; CreateFeatureReferenceCostFunctor / ...ConstantPoseCostFunctor,
+ * residuals/src/feature_reference.h:256-321; parameter order of operator(), :98-137), for every residual block of the
+ * problem at once and in factored form: the Jacobian of block o is  J_o = G_o^T-less product  G_o (C x 2) * P_o (2 x p).
+ *  residuals [n_obs][C]       r (f - reference, or f when the problem has no references)
+ *  grad      [n_obs][2][C]    d r/d u, d r/d v in patch pixel units (after the L2-normalisation chain rule)
+ *  juv       [n_obs][2][W]    d(u,v)/d(3 rotation tangent (QuaternionManifold, left-multiplicative) | 3 t | 3 X | K
+ *                             camera parameters), W = 9 + K returned through juv_cols, K = largest kNumParams in use
+ *  xy        [n_obs][2]       projected image point.   Any output may be NULL. */
+int pxr_ba_evaluate_jacobians(pxr_ba* ba, double* residuals, double* grad, double* juv, int32_t* juv_cols, double* xy);
 /* Introspection for parity tests: linearise at the current parameters (camera blocks Hcc [nc*nc,
  * lower triangle], gc, point blocks Hpp [n_points*9], gp), assemble the damped Schur system S/rhs at
  * `radius` (Jacobi scaling taken from this linearisation, as in LM iteration 0), solve it and

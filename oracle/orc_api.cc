@@ -205,6 +205,40 @@ int orc_ba_evaluate(const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr
   return 0;
 }
 
+// The reference's cost functors as ceres would evaluate them (residuals/src/feature_reference.h:98-137 through
+// AutoDiffCostFunction): per block r [C] and the AMBIENT Jacobian, columns [q(4) t(3) X(3) cam(K of the block's model)],
+// row-major C x (10 + PXR_MAX_CAM_PARAMS) with the unused camera columns zero.  Checks pxr_ba_evaluate_jacobians
+// and the `_residuals` mirror.
+int orc_ba_block_jacobians(const pxr_ba_desc* d, const pxr_interp_config* ic, double* residuals, double* J) {
+  pxr_solver_options so; std::memset(&so, 0, sizeof(so));
+  BAEvalOptions eo = MakeEO(ic, &so);
+  const int C = d->channels;
+  const int W = 10 + PXR_MAX_CAM_PARAMS;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t o = 0; o < d->n_obs; ++o) {
+    const int img = d->obs_img[o];
+    const int64_t pt = d->obs_pt[o];
+    const int cam = d->img_cam[img];
+    const int model = d->cam_model[cam];
+    const int K = CameraNumParams(model);
+    EvalBlockFn fn = SelectEval<true>(model);
+    if (!fn) { bad = 1; continue; }
+    const Patch patch = MakePatch(*d, o);
+    std::vector<double> r(C), Jb((size_t)C * (10 + K)), scratch;
+    fn(model, d->cam_params + (size_t)cam * PXR_MAX_CAM_PARAMS, d->qvec + 4 * img, d->tvec + 3 * img, d->xyz + 3 * pt,
+       patch, eo.interp, d->refs ? d->refs + (size_t)pt * C : nullptr, r.data(), Jb.data(), nullptr, scratch);
+    for (int i = 0; i < C; ++i) {
+      if (residuals) residuals[(size_t)o * C + i] = r[i];
+      if (J) {
+        double* row = J + ((size_t)o * C + i) * W;
+        for (int n = 0; n < W; ++n) row[n] = n < 10 + K ? Jb[(size_t)i * (10 + K) + n] : 0.0;
+      }
+    }
+  }
+  return bad;
+}
+
 int orc_ba_layout(const pxr_ba_desc* d, int* n_cam_local, int* n_local, int* pose_off, int* intr_off,
                   int64_t* point_off) {
   BALayout L = MakeLayout(*d);

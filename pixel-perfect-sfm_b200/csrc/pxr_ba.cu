@@ -438,13 +438,13 @@ int BA::project(int set, bool jac, double* xy_out) {
   return PXR_OK;
 }
 
-int BA::fm(int mode, double* residuals_out, double* cost_dev /* device scalar */) {
+int BA::fm(int mode, double* residuals_out, double* cost_dev /* device scalar */, double* grad_out) {
   FmEvalArgs a;
   a.uv = uv.p; a.item_patch = obs_patch.p; a.item_ref = obs_pt.p;
   a.patches = d_patches; a.ph = ph; a.pw = pw;
   a.refs = has_refs ? refs.p : nullptr;
   a.begin = 0; a.end = n_obs; a.item_index = nullptr;
-  a.out = obs_out.p; a.residuals = residuals_out; a.desc = nullptr;
+  a.out = obs_out.p; a.residuals = residuals_out; a.desc = nullptr; a.grad = grad_out;
   a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
   a.l2_normalize = interp.l2_normalize;
   int np = 0;
@@ -1299,6 +1299,32 @@ int pxr_ba_evaluate(pxr_ba* ba, double* sq_norm, double* gtr, double* gtg, doubl
     if (gtg) { gtg[3 * o] = r[3]; gtg[3 * o + 1] = r[4]; gtg[3 * o + 2] = r[5]; }
   }
   if (cost) *cost = c;
+  return PXR_OK;
+}
+
+// The cost-functor surface (residuals/bindings.cc:14-30): residual vectors and the two factors of every block's
+// Jacobian, J = G * P.
+int pxr_ba_evaluate_jacobians(pxr_ba* ba, double* residuals, double* grad, double* juv, int32_t* juv_cols, double* xy) {
+  if (!ba) return fail(PXR_ERR_INVALID_ARGUMENT, "ba is NULL");
+  BA* b = reinterpret_cast<BA*>(ba);
+  pxr_ctx* ctx = b->ctx;
+  PXR_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)b->n_obs, C = (size_t)b->C;
+  const int W = 9 + b->K;
+  if (juv_cols) *juv_cols = W;
+  DevBuf<double> dxy, dres, dgrad;
+  if (xy) PXR_TRY(dxy.alloc(n * 2));
+  if (residuals) PXR_TRY(dres.alloc(n * C));
+  if (grad) PXR_TRY(dgrad.alloc(n * 2 * C));
+  PXR_TRY(b->project(b->cur, true, dxy.p));
+  PXR_TRY(b->fm(1, dres.p, b->scalars.p + 0, dgrad.p));
+  cudaStream_t s = ctx->stream;
+  if (xy) PXR_CUDA(cudaMemcpyAsync(xy, dxy.p, n * 16, cudaMemcpyDeviceToHost, s));
+  if (residuals) PXR_CUDA(cudaMemcpyAsync(residuals, dres.p, n * C * 8, cudaMemcpyDeviceToHost, s));
+  if (grad) PXR_CUDA(cudaMemcpyAsync(grad, dgrad.p, n * 2 * C * 8, cudaMemcpyDeviceToHost, s));
+  if (juv && n > 0)     // device rows are juv_stride doubles apart, 2 x W of them used
+    PXR_CUDA(cudaMemcpy2DAsync(juv, (size_t)2 * W * 8, b->juv.p, (size_t)b->juv_stride * 8, (size_t)2 * W * 8, n, cudaMemcpyDeviceToHost, s));
+  PXR_CUDA(cudaStreamSynchronize(s));
   return PXR_OK;
 }
 

@@ -179,7 +179,7 @@ struct BA {
   int create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so, bool for_solve);
   BADev dev();
   int project(int set, bool jac, double* xy_out);
-  int fm(int mode, double* residuals_out, double* cost_dev);
+  int fm(int mode, double* residuals_out, double* cost_dev, double* grad_out = nullptr);
   int build();
   int evaluate(int set, bool jac, double* cost_out);
   int compute_step(double radius, bool* valid, double* model_cost_change);

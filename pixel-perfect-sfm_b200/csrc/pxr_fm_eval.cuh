@@ -112,6 +112,7 @@ struct FmEvalArgs {
   double* out;                 // [n][8]: s, b_u, b_v, a_uu, a_uv, a_vv, 0, 0  (JAC) / only s (COST)
   double* residuals;           // optional [n][C]
   double* desc;                // optional [n][C]: interpolated (normalised) descriptor f (reference extraction)
+  double* grad = nullptr;      // optional [n][2][C]: d r/d u, d r/d v per channel (Jacobian mode; the cost-functor surface)
   LossParams loss;
   int l2_normalize;
 };
@@ -449,6 +450,13 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       if (a.desc && active) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) a.desc[oj * C + lane * CPL + k] = f[k];
+      }
+      if (DERIV && a.grad && active) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          a.grad[(oj * 2) * C + lane * CPL + k] = fc[k];
+          a.grad[(oj * 2 + 1) * C + lane * CPL + k] = fr[k];
+        }
       }
       if (a.out) {
         if (DERIV) {

@@ -80,6 +80,7 @@ static __global__ void __launch_bounds__(128) fm_eval_small_kernel(FmEvalArgs a)
     const double r = a.refs ? f[ch] - a.refs[ridx * C + ch] : f[ch];
     if (a.residuals) a.residuals[o * C + ch] = r;
     if (a.desc) a.desc[o * C + ch] = f[ch];
+    if (DERIV && a.grad) { a.grad[(o * 2) * C + ch] = fc[ch]; a.grad[(o * 2 + 1) * C + ch] = fr[ch]; }
     s += r * r;
     if (DERIV) { bu += fc[ch] * r; bv += fr[ch] * r; auu += fc[ch] * fc[ch]; auv += fc[ch] * fr[ch]; avv += fr[ch] * fr[ch]; }
   }

@@ -47,6 +47,17 @@ class BAHandle:
             out["residuals"] = res
         return out
 
+    def evaluate_jacobians(self):
+        """residuals [n,C], grad [n,2,C] (d r/d u, d r/d v), juv [n,2,9+K] (d(u,v)/d(rot3|t3|X3|cam K)), xy [n,2]:
+        pxr_ba_evaluate_jacobians, the factored form of every block's ceres-style Jacobian (J = grad^T-rows x juv)"""
+        n, Cc = self.problem.n_obs, self.problem.channels
+        kmax = int(np.asarray(self.problem.cam_params).shape[1])
+        res, grad, xy = np.zeros((n, Cc)), np.zeros((n, 2, Cc)), np.zeros((n, 2))
+        juv = np.zeros((n, 2, 9 + kmax)); w = C.c_int32()
+        _capi.check(self.lib.pxr_ba_evaluate_jacobians(self.handle, _p(res), _p(grad), _p(juv), C.byref(w), _p(xy)))
+        juv = juv.reshape(-1)[: n * 2 * w.value].reshape(n, 2, w.value)
+        return dict(residuals=res, grad=grad, juv=juv, xy=xy)
+
     def debug_linearize(self, nc, nl, radius=1e4, dense=True):
         """dense=False leaves Hcc / S out (the block-sparse and block-mode paths never form them)"""
         npts = len(self.problem.xyz)

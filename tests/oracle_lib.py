@@ -79,6 +79,17 @@ def ba_evaluate(prob, interp, opts, residuals=False):
     return out
 
 
+def ba_block_jacobians(prob, interp):
+    """per residual block: r [n,C] and the ambient ceres Jacobian [n,C,10+PXR_MAX_CAM_PARAMS] (q4|t3|X3|cam) by Jets"""
+    from pixsfm._pixsfm._capi import PXR_MAX_CAM_PARAMS
+    d = prob.desc()
+    n = prob.n_obs
+    res = np.zeros((n, prob.channels)); J = np.zeros((n, prob.channels, 10 + PXR_MAX_CAM_PARAMS))
+    rc = lib().orc_ba_block_jacobians(C.byref(d), C.byref(interp), p(res), p(J))
+    assert rc == 0
+    return res, J
+
+
 def ba_layout(prob):
     d = prob.desc()
     nc = C.c_int(); nl = C.c_int()
