@@ -365,6 +365,55 @@ int pxr_costmaps_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr_interp
                          const pxr_costmap_config* cfg, double* refs_io, int64_t* src_obs_out,
                          void* out_host, void** out_device, pxr_summary* summary);
 
+/* ---- problem construction -------------------------------------------------------
+ * replaces BundleOptimizer::SetUp / AddImageToProblem / AddPointToProblem / Parameterize{Points,Images,Cameras}
+ * (bundle_adjustment/src/bundle_optimizer.h:139-165,247-331,335-442) and ReferenceExtractor::GetVisibleObservations
+ * (bundle_adjustment/src/reference_extractor.h:171-205).  The reference walks a colmap::Reconstruction; the caller hands
+ * the same data as a structure-of-arrays view (host memory, caller-owned).  Host code only, no device needed. */
+typedef struct pxr_recon_view {
+  int64_t n_images;
+  const int64_t* image_id;          /* [n_images] */
+  const int64_t* image_camera_id;   /* [n_images] */
+  const int64_t* p2d_begin;         /* [n_images+1] offsets of the image's 2D points in p2d_point3D_id */
+  const int64_t* p2d_point3D_id;    /* [p2d_begin[n_images]] 3D point of every 2D point, -1 = none */
+  int64_t n_cameras;
+  const int64_t* camera_id;         /* [n_cameras] */
+  const int32_t* camera_model;      /* [n_cameras] COLMAP model id 0..6 */
+  int64_t n_points;
+  const int64_t* point3D_id;        /* [n_points] */
+  const int64_t* track_begin;       /* [n_points+1] */
+  const int64_t* track_image_id;    /* [track_begin[n_points]] */
+  const int64_t* track_point2D_idx; /* [track_begin[n_points]] */
+} pxr_recon_view;
+/* colmap::BundleAdjustmentConfig as pixsfm::BundleAdjustmentSetup exposes it (bundle_adjustment/bindings.cc:81-111) */
+typedef struct pxr_ba_setup_view {
+  int64_t n_images; const int64_t* image_ids;
+  int64_t n_const_poses; const int64_t* const_pose_ids;
+  int64_t n_const_tvecs; const int64_t* const_tvec_ids; const uint8_t* const_tvec_masks;   /* bit k: tvec[k] constant */
+  int64_t n_const_cameras; const int64_t* const_camera_ids;
+  int64_t n_var_points; const int64_t* var_point_ids;
+  int64_t n_const_points; const int64_t* const_point_ids;
+} pxr_ba_setup_view;
+typedef struct pxr_ba_build_options {
+  int32_t refine_focal_length, refine_principal_point, refine_extra_params, refine_extrinsics;   /* BundleOptimizerOptions */
+  int32_t min_track_length;          /* -1: off */
+  int32_t mode;                      /* 0: bundle adjustment (setup required), 1: reference extraction */
+  int64_t n_ref_points;              /* mode 1: the points to extract references for ...                        */
+  const int64_t* ref_point_ids;
+  const uint8_t* track_has_patch;    /* ... and, per track element, whether a feature patch exists (NULL: all do) */
+} pxr_ba_build_options;
+typedef struct pxr_problem_ir pxr_problem_ir;
+int pxr_problem_build(const pxr_recon_view* rec, const pxr_ba_setup_view* setup, const pxr_ba_build_options* opt,
+                      pxr_problem_ir** out);
+int pxr_problem_sizes(const pxr_problem_ir* ir, int64_t* n_obs, int64_t* n_images, int64_t* n_cameras, int64_t* n_points);
+/* observations sorted by point (stable), ids of the blocks in index order, index maps and constancy masks as
+ * pxr_ba_desc takes them; any output may be NULL */
+int pxr_problem_copy(const pxr_problem_ir* ir, int64_t* obs_point3D_id, int64_t* obs_image_id, int64_t* obs_point2D_idx,
+                     int32_t* obs_img, int64_t* obs_pt, int64_t* image_ids, int64_t* camera_ids, int64_t* point_ids,
+                     int32_t* img_cam, uint8_t* pose_const, uint8_t* tvec_const_mask, uint8_t* point_const,
+                     uint32_t* cam_const_mask);
+void pxr_problem_destroy(pxr_problem_ir* ir);
+
 /* ---- descriptor interpolation ------------------------------------------------
  * replaces _features.PatchInterpolator(cfg).interpolate / interpolate_nodes for one node
  * (features/bindings.cc, features/src/patch_interpolator.h:125-135, dynamic_patch_interpolator.h): the bicubic

@@ -375,6 +375,9 @@ int pxr_device_free(pxr_ctx* ctx, void* dptr) {
 }
 int pxr_host_alloc_pinned(void** out, size_t bytes) {
   if (!out) return fail(PXR_ERR_INVALID_ARGUMENT, "out is NULL");
+  int device = 0;
+  PXR_CUDA(cudaGetDevice(&device));
+  pxr::NumaLocalScope numa(device);      // pages on the NUMA node of the current device (see pxr_internal.h)
   PXR_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
   return PXR_OK;
 }

@@ -17,9 +17,64 @@
 #include <exception>
 #include <thread>
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "pxr_internal.h"
 
 namespace pxr {
+
+// ------------------------------------------------------------------------------------------------ NUMA placement
+static bool read_small_file(const char* path, char* buf, size_t cap) {
+  FILE* f = std::fopen(path, "r");
+  if (!f) return false;
+  const size_t n = std::fread(buf, 1, cap - 1, f);
+  std::fclose(f);
+  buf[n] = 0;
+  return n > 0;
+}
+
+NumaLocalScope::NumaLocalScope(int device) {
+  static const bool off = []() { const char* v = std::getenv("PXR_NUMA_LOCAL"); return v && v[0] == '0'; }();
+  if (off) return;
+  char bus[32] = {};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return; }
+  for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+  char path[160], buf[4096];
+  std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  if (!read_small_file(path, buf, sizeof(buf))) return;
+  cpu_set_t local; CPU_ZERO(&local);
+  for (const char* c = buf; *c && *c != '\n';) {        // "0-31,64-95"
+    char* e; long a = std::strtol(c, &e, 10); if (e == c) break;
+    long b = a; c = e;
+    if (*c == '-') { b = std::strtol(c + 1, &e, 10); c = e; }
+    for (long k = a; k <= b && k < CPU_SETSIZE; ++k) CPU_SET((int)k, &local);
+    if (*c == ',') ++c;
+  }
+  cpu_set_t old; CPU_ZERO(&old);
+  if (sched_getaffinity(0, sizeof(old), &old) != 0) return;
+  cpu_set_t both; CPU_AND(&both, &old, &local);
+  if (CPU_COUNT(&both) == 0) return;                     // the process may not run there (cpuset): leave it alone
+  static_assert(sizeof(cpu_set_t) <= sizeof(old_mask_), "cpu_set_t larger than expected");
+  std::memcpy(old_mask_, &old, sizeof(old));
+  if (sched_setaffinity(0, sizeof(both), &both) != 0) return;
+  have_old_ = true; bound = true;
+  // prefer the node for pages faulted / allocated by this thread (MPOL_PREFERRED = 1); raw syscall: no libnuma here
+  std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  if (read_small_file(path, buf, sizeof(buf))) {
+    const long node = std::strtol(buf, nullptr, 10);
+    if (node >= 0 && node < 64) {
+      unsigned long mask = 1ul << node;
+      if (syscall(SYS_set_mempolicy, 1 /*MPOL_PREFERRED*/, &mask, 65ul) == 0) policy_set_ = true;
+    }
+  }
+}
+
+NumaLocalScope::~NumaLocalScope() {
+  if (policy_set_) syscall(SYS_set_mempolicy, 0 /*MPOL_DEFAULT*/, nullptr, 0ul);
+  if (have_old_) { cpu_set_t old; std::memcpy(&old, old_mask_, sizeof(old)); sched_setaffinity(0, sizeof(old), &old); }
+}
 
 struct Stager {
   static constexpr int kThreads = 6, kBufs = 2;
@@ -54,6 +109,7 @@ static int stager_get(pxr_ctx* ctx, Stager** out) {
   ctx->stager = nullptr;
   Stager* s = new Stager();
   s->chunk = chunk;
+  NumaLocalScope numa(ctx->device);      // the ring the DMA engine reads from: on the GPU's node
   cudaError_t e = cudaEventCreateWithFlags(&s->start, cudaEventDisableTiming);
   for (int t = 0; t < Stager::kThreads && e == cudaSuccess; ++t) {
     e = cudaStreamCreateWithFlags(&s->st[t], cudaStreamNonBlocking);
@@ -123,6 +179,7 @@ int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size
   cudaError_t errs[Stager::kThreads];
   const int device = ctx->device;
   auto work = [&](int t) {
+    NumaLocalScope numa(device);         // the copy threads run next to the ring they fill
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(s->st[t], s->start, 0);
     size_t k = 0;

@@ -158,10 +158,192 @@ class ProblemIR:
         self.obs = []  # (image_id, point2D_idx, point3D_id)
 
 
+def _ids(values):
+    return np.ascontiguousarray(sorted(int(v) for v in values), np.int64)
+
+
+def _patch_plan(ir, feature_view):
+    """obs -> global patch index, blocks in first-use order (what PatchSlab builds one observation at a time),
+    vectorised per image"""
+    obs_image = np.fromiter((o[0] for o in ir.obs), np.int64, len(ir.obs)) if not hasattr(ir, "obs_image_id") else ir.obs_image_id
+    obs_p2d = np.fromiter((o[1] for o in ir.obs), np.int64, len(ir.obs)) if not hasattr(ir, "obs_point2D_idx") else ir.obs_point2D_idx
+    uniq, first = np.unique(obs_image, return_index=True)
+    order = uniq[np.argsort(first, kind="stable")]
+    blocks, corners, scales, offsets = [], [], [], {}
+    obs_patch = np.zeros(len(obs_image), np.int64)
+    n = 0
+    for image_id in order:
+        image_id = int(image_id)
+        name = feature_view.image_name(image_id)
+        fmap = feature_view.get_feature_map(image_id)
+        sel = np.flatnonzero(obs_image == image_id) if len(order) < 64 else None
+        if sel is None:
+            sel = ir._by_image[image_id]
+        if name not in offsets:
+            offsets[name] = n
+            blocks.append(fmap.patches); corners.append(fmap.corners); scales.append(np.tile(fmap.scale, (fmap.size(), 1)))
+            n += fmap.size()
+        if not fmap.is_sparse:
+            local = np.full(len(sel), fmap.local_index(0), np.int64)
+        else:
+            ids = np.asarray(fmap.point2D_ids, np.int64)
+            srt = np.argsort(ids, kind="stable")
+            pos = np.searchsorted(ids[srt], obs_p2d[sel])
+            pos = np.minimum(pos, len(ids) - 1)
+            if np.any(ids[srt][pos] != obs_p2d[sel]):
+                missing = obs_p2d[sel][ids[srt][pos] != obs_p2d[sel]][0]
+                raise KeyError(int(missing))
+            local = srt[pos]
+        obs_patch[sel] = offsets[name] + local
+    return blocks, np.concatenate(corners), np.concatenate(scales), obs_patch, offsets
+
+
 def build_problem(reconstruction, feature_view, setup, options, references=None, for_references=None):
-    """Restates BundleOptimizer::SetUp + Parameterize for the featuremetric optimizer and returns
-    (_capi.BAProblem, ProblemIR).  With `for_references` (a set of point3D ids) the observation list is the
-    one of ReferenceExtractor::GetVisibleObservations instead (reference_extractor.h:171-205)."""
+    """BundleOptimizer::SetUp + Parameterize (bundle_optimizer.h:139-165,247-442) through the C++ builder in libpxr
+    (pxr_problem_build, csrc/pxr_problem.cu) -> (_capi.BAProblem, ProblemIR).  With `for_references` (a set of
+    point3D ids) the observation list is ReferenceExtractor::GetVisibleObservations' (reference_extractor.h:171-205).
+    The reconstruction is handed over as arrays (`as_arrays()`); `build_problem_py` is the per-object restatement the
+    tests compare it with."""
+    import ctypes as C
+    rec = reconstruction
+    A = rec.as_arrays() if hasattr(rec, "as_arrays") else __import__("pixsfm.util.colmap_types", fromlist=["x"]).reconstruction_arrays(rec)
+    lib = _capi.load_lib()
+    p = _capi.ptr
+    view = _capi.ReconView(n_images=len(A["image_id"]), image_id=p(A["image_id"]), image_camera_id=p(A["image_camera_id"]),
+                           p2d_begin=p(A["p2d_begin"]), p2d_point3D_id=p(A["p2d_point3D_id"]),
+                           n_cameras=len(A["camera_id"]), camera_id=p(A["camera_id"]), camera_model=p(A["camera_model"]),
+                           n_points=len(A["point3D_id"]), point3D_id=p(A["point3D_id"]), track_begin=p(A["track_begin"]),
+                           track_image_id=p(A["track_image_id"]), track_point2D_idx=p(A["track_point2D_idx"]))
+    keep = [A]
+    if for_references is None:
+        img_ids = _ids(setup.image_ids)
+        if hasattr(rec, "qvec") and isinstance(getattr(rec, "qvec"), np.ndarray):      # image.NormalizeQvec() (:251)
+            rows = np.searchsorted(A["image_id"], img_ids)
+            rec.qvec[rows] /= np.linalg.norm(rec.qvec[rows], axis=1, keepdims=True)
+        else:
+            for image_id in img_ids:
+                image = rec.images[int(image_id)]
+                image.qvec /= np.linalg.norm(image.qvec)
+        cp, cam, vp, cpt = _ids(setup._const_poses), _ids(setup._const_cameras), _ids(setup._var_points), _ids(setup._const_points)
+        tv = _ids(setup._const_tvecs.keys())
+        tvm = np.array([sum(1 << int(k) for k in setup._const_tvecs[int(i)]) for i in tv], np.uint8)
+        sv = _capi.SetupView(n_images=len(img_ids), image_ids=p(img_ids), n_const_poses=len(cp), const_pose_ids=p(cp),
+                             n_const_tvecs=len(tv), const_tvec_ids=p(tv), const_tvec_masks=p(tvm),
+                             n_const_cameras=len(cam), const_camera_ids=p(cam), n_var_points=len(vp), var_point_ids=p(vp),
+                             n_const_points=len(cpt), const_point_ids=p(cpt))
+        bo = _capi.BuildOptions(refine_focal_length=int(bool(options.refine_focal_length)),
+                                refine_principal_point=int(bool(options.refine_principal_point)),
+                                refine_extra_params=int(bool(options.refine_extra_params)),
+                                refine_extrinsics=int(bool(options.refine_extrinsics)),
+                                min_track_length=int(options.min_track_length), mode=0)
+        keep += [img_ids, cp, cam, vp, cpt, tv, tvm]
+        sv_ref = C.byref(sv)
+    else:
+        ref_ids = _ids(for_references)
+        # which track elements have a feature patch: resolved per image
+        timg, tp2d = A["track_image_id"], A["track_point2D_idx"]
+        has = np.zeros(len(timg), np.uint8)
+        for image_id in np.unique(timg):
+            sel = np.flatnonzero(timg == image_id)
+            name = feature_view._id_to_name.get(int(image_id))
+            if name is None or not feature_view.fset.has_fmap(name):
+                continue
+            fmap = feature_view.fset.fmap(name)
+            if not fmap.is_sparse:
+                has[sel] = 1 if fmap.has_point2D(0) else 0
+            else:
+                has[sel] = np.isin(tp2d[sel], np.asarray(fmap.point2D_ids, np.int64))
+        bo = _capi.BuildOptions(mode=1, min_track_length=-1, n_ref_points=len(ref_ids), ref_point_ids=p(ref_ids), track_has_patch=p(has))
+        keep += [ref_ids, has]
+        sv_ref = None
+    handle = C.c_void_p()
+    _capi.check(lib.pxr_problem_build(C.byref(view), sv_ref, C.byref(bo), C.byref(handle)))
+    try:
+        n_obs, n_img, n_cam, n_pts = (C.c_int64() for _ in range(4))
+        _capi.check(lib.pxr_problem_sizes(handle, C.byref(n_obs), C.byref(n_img), C.byref(n_cam), C.byref(n_pts)))
+        n_obs, n_img, n_cam, n_pts = n_obs.value, n_img.value, n_cam.value, n_pts.value
+        o_pid, o_img, o_p2d = (np.zeros(n_obs, np.int64) for _ in range(3))
+        obs_img, obs_pt = np.zeros(n_obs, np.int32), np.zeros(n_obs, np.int64)
+        image_ids, camera_ids, point_ids = np.zeros(n_img, np.int64), np.zeros(n_cam, np.int64), np.zeros(n_pts, np.int64)
+        img_cam = np.zeros(n_img, np.int32)
+        pose_const, tmask, point_const = np.zeros(n_img, np.uint8), np.zeros(n_img, np.uint8), np.zeros(n_pts, np.uint8)
+        cam_mask = np.zeros(n_cam, np.uint32)
+        _capi.check(lib.pxr_problem_copy(handle, p(o_pid), p(o_img), p(o_p2d), p(obs_img), p(obs_pt), p(image_ids), p(camera_ids),
+                                         p(point_ids), p(img_cam), p(pose_const), p(tmask), p(point_const), p(cam_mask)))
+    finally:
+        lib.pxr_problem_destroy(handle)
+    del keep
+    if for_references is not None:
+        # the reference warns about every track element without a patch (reference_extractor.h:187-191)
+        missing = int((A["track_begin"][np.searchsorted(A["point3D_id"], ref_ids) + 1]
+                       - A["track_begin"][np.searchsorted(A["point3D_id"], ref_ids)]).sum()) - n_obs if len(ref_ids) else 0
+        if missing > 0:
+            logger.warning("Warning: %d track elements have no feature patch.", missing)
+    ir = ProblemIR()
+    ir.image_ids, ir.camera_ids, ir.point_ids = image_ids.tolist(), camera_ids.tolist(), point_ids.tolist()
+    ir.obs_image_id, ir.obs_point2D_idx, ir.obs_point3D_id = o_img, o_p2d, o_pid
+    ir.obs = _LazyObs(o_img, o_p2d, o_pid)
+    if n_obs == 0:
+        import types
+        return types.SimpleNamespace(n_obs=0), ir
+    if len(image_ids) >= 64:      # one pass instead of one mask per image
+        srt = np.argsort(o_img, kind="stable")
+        bounds = np.searchsorted(o_img[srt], image_ids)
+        bounds = np.append(bounds, len(srt))
+        ir._by_image = {int(i): srt[bounds[k]:bounds[k + 1]] for k, i in enumerate(image_ids)}
+    blocks, corners, scales, obs_patch, offsets = _patch_plan(ir, feature_view)
+    ir.slab_offsets = offsets
+    # parameters of the blocks, in index order
+    if isinstance(getattr(rec, "xyz", None), np.ndarray) and hasattr(rec, "point3D_id"):
+        rows_i = np.searchsorted(rec.image_id, image_ids); rows_p = np.searchsorted(rec.point3D_id, point_ids)
+        rows_c = np.searchsorted(rec.camera_id, camera_ids)
+        qvec, tvec, xyz = rec.qvec[rows_i], rec.tvec[rows_i], rec.xyz[rows_p]
+        cam_params = [rec.cam_params[r] for r in rows_c]
+        cam_model = rec.camera_model[rows_c]
+        ir._rows = (rows_i, rows_c, rows_p)
+    else:
+        qvec = np.array([rec.images[i].qvec for i in ir.image_ids], np.float64).reshape(-1, 4)
+        tvec = np.array([rec.images[i].tvec for i in ir.image_ids], np.float64).reshape(-1, 3)
+        xyz = np.array([rec.points3D[q].xyz for q in ir.point_ids], np.float64).reshape(-1, 3)
+        cam_params = [np.asarray(rec.cameras[c].params, np.float64) for c in ir.camera_ids]
+        cam_model = np.array([int(rec.cameras[c].model_id) for c in ir.camera_ids], np.int32)
+    refs = None
+    if references is not None:
+        C_ = feature_view.channels
+        refs = np.zeros((n_pts, C_))
+        for k, pid in enumerate(ir.point_ids):
+            refs[k] = np.asarray(references[pid].descriptor, np.float64).reshape(-1)[:C_]
+    prob = _capi.BAProblem(cam_model=cam_model, cam_params=cam_params, cam_const_mask=cam_mask, qvec=qvec, tvec=tvec,
+                           img_cam=img_cam, pose_const=pose_const, tvec_const_mask=tmask, xyz=xyz, point_const=point_const,
+                           obs_img=obs_img, obs_pt=obs_pt, patches=None, corner=corners, scale=scales, refs=refs,
+                           obs_patch=obs_patch, patch_blocks=blocks)
+    return prob, ir
+
+
+class _LazyObs:
+    """`ir.obs[k] -> (image_id, point2D_idx, point3D_id)` without materialising a list of tuples"""
+
+    def __init__(self, image_id, point2D_idx, point3D_id):
+        self._a = (image_id, point2D_idx, point3D_id)
+
+    def __len__(self):
+        return len(self._a[0])
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        return (int(self._a[0][k]), int(self._a[1][k]), int(self._a[2][k]))
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
+def build_problem_py(reconstruction, feature_view, setup, options, references=None, for_references=None):
+    """The per-object Python restatement of BundleOptimizer::SetUp + Parameterize (what build_problem was before the
+    C++ builder): kept as the independent statement the tests compare pxr_problem_build with."""
     rec = reconstruction
     ir = ProblemIR()
     obs = []                      # (point3D_id, image_id, point2D_idx)
@@ -296,6 +478,14 @@ def build_problem(reconstruction, feature_view, setup, options, references=None,
 
 def write_back(reconstruction, prob, ir):
     """the reference updates the Reconstruction in place through raw double* (feature_reference_bundle_optimizer.h:111-114)"""
+    rows = getattr(ir, "_rows", None)
+    if rows is not None:                      # array-backed reconstruction: three scatters
+        rows_i, rows_c, rows_p = rows
+        reconstruction.qvec[rows_i] = prob.qvec; reconstruction.tvec[rows_i] = prob.tvec; reconstruction.xyz[rows_p] = prob.xyz
+        for k, r in enumerate(rows_c):
+            n = len(reconstruction.cam_params[r])
+            reconstruction.cam_params[r][:] = prob.cam_params[k, :n]
+        return
     for k, i in enumerate(ir.image_ids):
         reconstruction.images[i].qvec[:] = prob.qvec[k]
         reconstruction.images[i].tvec[:] = prob.tvec[k]

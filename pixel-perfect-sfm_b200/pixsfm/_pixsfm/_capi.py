@@ -27,6 +27,31 @@ LOSS_IDS = {"trivial": 0, "cauchy": 1, "huber": 2, "soft_l1": 3, "softlone": 3, 
 DTYPE_IDS = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
 
 
+def ptr(a):
+    """ctypes pointer to a numpy array's data (None stays NULL)"""
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class ReconView(C.Structure):          # pxr_recon_view
+    _fields_ = [("n_images", C.c_int64), ("image_id", C.c_void_p), ("image_camera_id", C.c_void_p), ("p2d_begin", C.c_void_p),
+                ("p2d_point3D_id", C.c_void_p), ("n_cameras", C.c_int64), ("camera_id", C.c_void_p), ("camera_model", C.c_void_p),
+                ("n_points", C.c_int64), ("point3D_id", C.c_void_p), ("track_begin", C.c_void_p), ("track_image_id", C.c_void_p),
+                ("track_point2D_idx", C.c_void_p)]
+
+
+class SetupView(C.Structure):          # pxr_ba_setup_view
+    _fields_ = [("n_images", C.c_int64), ("image_ids", C.c_void_p), ("n_const_poses", C.c_int64), ("const_pose_ids", C.c_void_p),
+                ("n_const_tvecs", C.c_int64), ("const_tvec_ids", C.c_void_p), ("const_tvec_masks", C.c_void_p),
+                ("n_const_cameras", C.c_int64), ("const_camera_ids", C.c_void_p), ("n_var_points", C.c_int64),
+                ("var_point_ids", C.c_void_p), ("n_const_points", C.c_int64), ("const_point_ids", C.c_void_p)]
+
+
+class BuildOptions(C.Structure):       # pxr_ba_build_options
+    _fields_ = [("refine_focal_length", C.c_int32), ("refine_principal_point", C.c_int32), ("refine_extra_params", C.c_int32),
+                ("refine_extrinsics", C.c_int32), ("min_track_length", C.c_int32), ("mode", C.c_int32),
+                ("n_ref_points", C.c_int64), ("ref_point_ids", C.c_void_p), ("track_has_patch", C.c_void_p)]
+
+
 class PxrError(RuntimeError):
     pass
 

@@ -9,7 +9,7 @@ What differs from the reference, and why:
     reconstructions passed in by the caller work as well (duck typing, `util/colmap_types.py`).
   * configuration: dicts (or a YAML path) merged over the reference's defaults; `${..interpolation}` of the reference's
     YAML files is resolved here by handing the top-level `interpolation` block to KA and BA unless they set their own.
-  * `triangulation` / `reconstruction` (refine_hloc.py) shell out to COLMAP through pycolmap/hloc and are not provided."""
+  * `triangulation` / `reconstruction` live in `pixsfm.refine_hloc.PixSfM`, as in the reference."""
 import re
 import shutil
 from copy import deepcopy
@@ -128,9 +128,25 @@ class PixSfM:
         reconstruction.write(str(output_path))
         return reconstruction, ba_data, feature_manager
 
+    def resolve_cache_path(self, cache_path=None, output_dir=None):
+        """refine_colmap.py:131-145: where the dense-feature cache of this run lives (None without an extractor)"""
+        if self.extractor is None or getattr(self.extractor, "conf", None) is None:
+            return None if cache_path is None else Path(cache_path)
+        feature_conf = self.extractor.conf
+        if cache_path is None:
+            if output_dir is None:
+                return None
+            cache_path = output_dir
+        cache_path = Path(cache_path)
+        if cache_path.suffix != ".h5":
+            model = feature_conf["model"] if isinstance(feature_conf, dict) else feature_conf.model
+            name = model["name"] if isinstance(model, dict) else model.name
+            sparse = feature_conf["sparse"] if isinstance(feature_conf, dict) else feature_conf.sparse
+            cache_path = cache_path / "{}_featuremaps_{}.h5".format(name, "sparse" if sparse else "dense")
+        return cache_path
+
     def triangulation(self, *args, **kwargs):
-        raise NotImplementedError("COLMAP triangulation runs through pycolmap/hloc (refine_hloc.py:117-131), which this "
-                                  "package does not wrap; refine keypoints with refine_keypoints_from_db, run COLMAP, "
-                                  "then refine_reconstruction")
+        raise NotImplementedError("triangulation / reconstruction from hloc files are methods of pixsfm.refine_hloc.PixSfM "
+                                  "(refine_hloc.py:117-146)")
 
     reconstruction = triangulation

@@ -89,6 +89,11 @@ class Reconstruction:
     def num_observations(self):
         return sum(p.track.length() for p in self.points3D.values())
 
+    def as_arrays(self):
+        """structure-of-arrays view of the topology (what pxr_recon_view takes): one pass over the Python objects.
+        Works for pycolmap-like objects too (reconstruction_arrays)."""
+        return reconstruction_arrays(self)
+
     # pycolmap.Reconstruction(path) / .write(path) / .write_text(path) (refine_colmap.py:117-131)
     @classmethod
     def read(cls, path):
@@ -102,3 +107,75 @@ class Reconstruction:
     def write_text(self, path):
         from .colmap_model_io import write_model
         write_model(self, path, ".txt")
+
+
+def reconstruction_arrays(rec):
+    """topology of a (duck-typed) reconstruction as flat arrays: the host-side input of pxr_problem_build"""
+    image_ids = sorted(rec.images.keys())
+    images = [rec.images[i] for i in image_ids]
+    counts = np.fromiter((len(im.points2D) for im in images), np.int64, len(images))
+    p2d_begin = np.zeros(len(images) + 1, np.int64)
+    np.cumsum(counts, out=p2d_begin[1:])
+    p2d_pid = np.full(int(p2d_begin[-1]), -1, np.int64)
+    for k, im in enumerate(images):
+        if counts[k]:
+            # point3D_id is INVALID_POINT3D (2**64-1) where there is no 3D point: does not fit int64 -> -1
+            p2d_pid[p2d_begin[k]:p2d_begin[k + 1]] = [p.point3D_id if p.point3D_id != INVALID_POINT3D else -1 for p in im.points2D]
+    camera_ids = sorted(rec.cameras.keys())
+    point_ids = sorted(rec.points3D.keys())
+    tracks = [rec.points3D[p].track.elements for p in point_ids]
+    tcounts = np.fromiter((len(t) for t in tracks), np.int64, len(tracks))
+    track_begin = np.zeros(len(tracks) + 1, np.int64)
+    np.cumsum(tcounts, out=track_begin[1:])
+    n_el = int(track_begin[-1])
+    return dict(image_id=np.array(image_ids, np.int64), image_camera_id=np.array([im.camera_id for im in images], np.int64),
+                p2d_begin=p2d_begin, p2d_point3D_id=p2d_pid,
+                camera_id=np.array(camera_ids, np.int64),
+                camera_model=np.array([int(rec.cameras[c].model_id) for c in camera_ids], np.int32),
+                point3D_id=np.array(point_ids, np.int64), track_begin=track_begin,
+                track_image_id=np.fromiter((e.image_id for t in tracks for e in t), np.int64, n_el),
+                track_point2D_idx=np.fromiter((e.point2D_idx for t in tracks for e in t), np.int64, n_el))
+
+
+class ArrayReconstruction:
+    """A reconstruction that IS arrays (no per-point Python objects): what a large model looks like when it is read
+    straight into numpy, and what the bench's surface-level run uses.  Parameters live in `qvec [Ni,4]`, `tvec [Ni,3]`,
+    `xyz [Np,3]`, `cam_params` (list of arrays) and are refined in place; `as_arrays()` hands the topology to
+    pxr_problem_build without a pass over Python objects.  `images` / `cameras` / `points3D` give light read-only views
+    for code that wants names or a single entry."""
+
+    class _Image:
+        def __init__(self, image_id, name, camera_id):
+            self.image_id, self.name, self.camera_id = image_id, name, camera_id
+
+    def __init__(self, image_ids, image_names, image_camera_ids, qvec, tvec, p2d_begin, p2d_point3D_id,
+                 camera_ids, camera_models, cam_params, point3D_ids, xyz, track_begin, track_image_id, track_point2D_idx):
+        self.image_id = np.ascontiguousarray(image_ids, np.int64)
+        self.image_names = list(image_names)
+        self.image_camera_id = np.ascontiguousarray(image_camera_ids, np.int64)
+        self.qvec = np.ascontiguousarray(qvec, np.float64).reshape(-1, 4)
+        self.tvec = np.ascontiguousarray(tvec, np.float64).reshape(-1, 3)
+        self.p2d_begin = np.ascontiguousarray(p2d_begin, np.int64)
+        self.p2d_point3D_id = np.ascontiguousarray(p2d_point3D_id, np.int64)
+        self.camera_id = np.ascontiguousarray(camera_ids, np.int64)
+        self.camera_model = np.ascontiguousarray(camera_models, np.int32)
+        self.cam_params = [np.array(c, np.float64) for c in cam_params]
+        self.point3D_id = np.ascontiguousarray(point3D_ids, np.int64)
+        self.xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        self.track_begin = np.ascontiguousarray(track_begin, np.int64)
+        self.track_image_id = np.ascontiguousarray(track_image_id, np.int64)
+        self.track_point2D_idx = np.ascontiguousarray(track_point2D_idx, np.int64)
+        for name in ("image_id", "camera_id", "point3D_id"):
+            if np.any(np.diff(getattr(self, name)) <= 0):
+                raise ValueError("%s must be strictly ascending" % name)
+        self.images = {int(i): ArrayReconstruction._Image(int(i), n, int(c))
+                       for i, n, c in zip(self.image_id, self.image_names, self.image_camera_id)}
+
+    def as_arrays(self):
+        return dict(image_id=self.image_id, image_camera_id=self.image_camera_id, p2d_begin=self.p2d_begin,
+                    p2d_point3D_id=self.p2d_point3D_id, camera_id=self.camera_id, camera_model=self.camera_model,
+                    point3D_id=self.point3D_id, track_begin=self.track_begin, track_image_id=self.track_image_id,
+                    track_point2D_idx=self.track_point2D_idx)
+
+    def num_observations(self):
+        return int(self.track_begin[-1])
