@@ -85,6 +85,7 @@ def parse():
     ap.add_argument("--ps", type=int, default=16)
     ap.add_argument("--no-inner", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-surface", action="store_true", help="skip the run through the reference's Python surface")
     ap.add_argument("--cpu-sample-points", type=int, default=20000)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--covis-window", type=int, default=0,
@@ -368,6 +369,59 @@ def cpu_arm(args, g, steps, warmup, label, max_points=None):
                                        "back-substitution+model cost", "inner iterations"], [float(v) for v in st]))}
 
 
+def surface_e2e(args, g, d_patches, ctx, inner):
+    """End to end through the mirror of the reference's API, as a pixsfm user calls it: per-image FeatureMaps holding
+    pageable numpy patch arrays, a reconstruction, `ReferenceExtractor.run` (HOT LOOP A) then
+    `FeatureReferenceBundleOptimizer.run` (problem construction in libpxr's C++ builder, upload, LM, write-back)."""
+    from pixsfm._pixsfm import _bundle_adjustment as ba, _engine
+    from pixsfm._pixsfm._features import FeatureMap, FeatureSet, FeatureView
+    from pixsfm.util.colmap_types import ArrayReconstruction
+    n_obs = len(g["obs_pt"]); NC = args.cams; NP = len(g["xyz"]); L = min(args.track, args.cams)
+    pbytes = n_obs * args.ps * args.ps * args.channels * 2
+    avail = host_memory_available()
+    if avail is not None and avail < 2.3 * pbytes:
+        return {"value": None, "unit": "observations/s", "error": "needs 2 x %.1f GB of host memory to lay out the FeatureMaps" % (pbytes / 1e9)}
+    obs_img = g["obs_img"]; obs_pt = g["obs_pt"]
+    order = np.argsort(obs_img, kind="stable")                 # observations grouped by image, point order inside
+    counts = np.bincount(obs_img, minlength=NC)
+    begin = np.zeros(NC + 1, np.int64); np.cumsum(counts, out=begin[1:])
+    p2d_of_obs = np.empty(n_obs, np.int64); p2d_of_obs[order] = np.arange(n_obs) - begin[obs_img[order]]
+    # the patches of image i = the device slab's rows order[begin[i]:begin[i+1]]: one device gather + D2H per image
+    fset = FeatureSet(args.channels, np.dtype(np.float16))
+    host_all = np.empty((n_obs, args.ps, args.ps, args.channels), np.float16)     # pageable
+    _engine.memcpy_d2h(host_all, d_patches, pbytes, ctx)
+    names = ["image%04d.jpg" % i for i in range(NC)]
+    for i in range(NC):
+        sel = order[begin[i]:begin[i + 1]]
+        fset.emplace(names[i], FeatureMap(np.ascontiguousarray(host_all[sel]), list(range(len(sel))), g["corners"][sel],
+                                          {"scale": g["scale"][sel[0]] if len(sel) else (1.0, 1.0), "is_sparse": True}))
+    del host_all
+    rec = ArrayReconstruction(np.arange(1, NC + 1), names, g["img_cam"] + 1, g["qvec"].copy(), g["tvec"].copy(), begin,
+                              (obs_pt[order] + 1).astype(np.int64), np.arange(1, len(g["cam_params"]) + 1),
+                              np.full(len(g["cam_params"]), 2, np.int32), [c[:4].copy() for c in g["cam_params"]],
+                              np.arange(1, NP + 1), g["xyz"].copy(), np.arange(NP + 1, dtype=np.int64) * L,
+                              (obs_img + 1).astype(np.int64), p2d_of_obs)
+    setup = ba.BundleAdjustmentSetup(); setup.add_images(range(1, NC + 1)); setup.set_constant_pose(1); setup.set_constant_tvec(2, [0])
+    interp = {"l2_normalize": True}
+    options = {"loss": {"name": "cauchy", "params": [0.25]}, "print_summary": False,
+               "solver": {"max_num_iterations": args.steps, "use_inner_iterations": bool(inner)}}
+    labels = np.zeros(NP + 2, np.int64)
+    t0 = time.time()
+    refs = ba.ReferenceExtractor({"iters": 100, "loss": {"name": "cauchy", "params": [0.25]}}, interp).run(labels, rec, fset)
+    t1 = time.time()
+    opt = ba.FeatureReferenceBundleOptimizer(options, setup, interp)
+    ok = opt.run(rec, FeatureView(fset, rec), refs)
+    t2 = time.time()
+    s = opt.summary()
+    its = max(1, s["num_iterations"] - 1)
+    return {"value": n_obs * its / (t2 - t0), "unit": "observations/s", "seconds": t2 - t0,
+            "reference_extraction_seconds": t1 - t0, "bundle_adjustment_seconds": t2 - t1, "lm_iterations": its,
+            "library_seconds_ba": s["total_time_s"], "lm_loop_seconds": s["solve_time_s"], "h2d_bytes_ba": s["h2d_bytes"],
+            "resident_window_ba": s["resident_window"], "final_cost": s["final_cost"], "ok": bool(ok),
+            "call": "ReferenceExtractor.run + FeatureReferenceBundleOptimizer.run on %d per-image FeatureMaps (pageable numpy, %.1f GB), "
+                    "array-backed reconstruction; includes problem construction, both uploads, write-back" % (NC, pbytes / 1e9)}
+
+
 def workload_config(args, world, n_obs_rank, inner):
     L = min(args.track, args.cams)
     workload = ("synthetic %d cams / %d pts / %d obs per GPU, %d-ch fp16 %dx%d patches, bicubic+L2, Cauchy(0.25)%s"
@@ -546,33 +600,69 @@ def main():
             else:
                 host = np.empty((n_obs, args.ps, args.ps, args.channels), np.float16)
             _engine.memcpy_d2h(host, d_patches, pbytes, ctx)
-            g2 = geometry(args, rank)
-            prob_h = make_problem(args, g2, host, False)
-            prob_h.refs = refs
             so2 = _capi.default_ba_options(use_inner_iterations=inner, max_num_iterations=args.steps,
                                            linear_solver=args.linear_solver)
-            if dist is not None:
-                dist.barrier()
-            t0 = time.time()
-            s3 = _engine.ba_run(prob_h, ic, so2, ctx=ctx)
-            dt = time.time() - t0
-            if dist is not None:
-                import torch
-                tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                dt = float(tt.item())
-            it3 = max(1, s3["num_iterations"] - 1)
-            e2e = {"value": total_obs * it3 / dt, "unit": "observations/s",
-                   "h2d_bytes_per_step": s3["h2d_bytes"] / it3, "d2h_bytes_per_step": s3["d2h_bytes"] / it3,
-                   "seconds": dt, "library_seconds": s3["total_time_s"], "lm_loop_seconds": s3["solve_time_s"],
-                   "lm_iterations": it3, "pinned_host": bool(pinned),
-                   "call": "pxr_ba_run (upload %.1f GB of patches + solve + read back)" % (pbytes / 1e9),
-                   "final_cost": s3["final_cost"]}
+
+            def one_shot(window):
+                """pxr_ba_run on the host buffer from scratch; window: None = the library's default (window residency on a
+                pinned buffer), 0 = the whole slab crosses PCIe"""
+                prob_h = make_problem(args, geometry(args, rank), host, False)
+                prob_h.refs = refs
+                old = os.environ.get("PXR_RESIDENT_WINDOW")
+                if window is not None:
+                    os.environ["PXR_RESIDENT_WINDOW"] = str(window)
+                try:
+                    if dist is not None:
+                        dist.barrier()
+                    t0 = time.time()
+                    s3 = _engine.ba_run(prob_h, ic, so2, ctx=ctx)
+                    dt = time.time() - t0
+                finally:
+                    if window is not None:
+                        if old is None:
+                            os.environ.pop("PXR_RESIDENT_WINDOW", None)
+                        else:
+                            os.environ["PXR_RESIDENT_WINDOW"] = old
+                if dist is not None:
+                    import torch
+                    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    dt = float(tt.item())
+                it3 = max(1, s3["num_iterations"] - 1)
+                return {"value": total_obs * it3 / dt, "unit": "observations/s",
+                        "h2d_bytes_per_step": s3["h2d_bytes"] / it3, "d2h_bytes_per_step": s3["d2h_bytes"] / it3,
+                        "seconds": dt, "library_seconds": s3["total_time_s"], "lm_loop_seconds": s3["solve_time_s"],
+                        "lm_iterations": it3, "pinned_host": bool(pinned), "final_cost": s3["final_cost"],
+                        "resident_window": s3["resident_window"], "observations_refetched": s3["resident_refetched"],
+                        "evaluation_passes_repeated": s3["resident_passes_repeated"], "h2d_bytes_total": s3["h2d_bytes"]}
+
+            e2e = one_shot(None)
+            e2e["call"] = ("pxr_ba_run on a pinned host buffer of %.1f GB of patches: %s + solve + read back"
+                           % (pbytes / 1e9, ("only the %dx%d tap window of every observation crosses PCIe (packed by host threads, DMA, "
+                                             "scattered on the device; whole patches for observations that leave it)"
+                                             % (e2e["resident_window"], e2e["resident_window"])) if e2e["resident_window"]
+                              else "upload of the whole slab"))
+            if e2e["resident_window"]:
+                full = one_shot(0)
+                e2e["full_upload"] = {k: full[k] for k in ("value", "seconds", "library_seconds", "lm_loop_seconds", "h2d_bytes_total",
+                                                           "final_cost")}
+                # same taps, same arithmetic; what differs is the order of the fp64 atomics in the normal equations
+                e2e["full_upload"]["relative_cost_difference"] = abs(full["final_cost"] - e2e["final_cost"]) / abs(full["final_cost"])
+                e2e["full_upload"]["same_result"] = bool(e2e["full_upload"]["relative_cost_difference"] < 1e-9)
             if pinned:
                 del host
                 ctx.lib.pxr_host_free_pinned(hp)
         except Exception as ex:  # report, never fake
             e2e = {"value": None, "unit": "observations/s", "error": repr(ex)}
+
+    # ---- the same solve through the reference's own surface: ReferenceExtractor.run + FeatureReferenceBundleOptimizer.run on
+    # FeatureMaps that are ordinary (pageable) numpy arrays, problem construction included
+    surface = None
+    if rank == 0 and world == 1 and not args.no_e2e and not args.no_surface:
+        try:
+            surface = surface_e2e(args, g, d_patches, ctx, inner)
+        except Exception as ex:
+            surface = {"value": None, "unit": "observations/s", "error": repr(ex)}
 
     cb = None
     if rank == 0 and world == 1 and args.cpu_sample_points > 0:
@@ -588,7 +678,7 @@ def main():
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f64 (fp16 taps, fp32 horizontal, fp64 vertical/solve)",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cb, "stage_ms": stage_ms, "steady_state": steady,
+                "e2e_reference_surface": surface, "roofline": roofline, "cpu_baseline": cb, "stage_ms": stage_ms, "steady_state": steady,
                 "multi_gpu": {"nccl_collectives_in_timed_region": int(ncoll), "lm_iterations_in_timed_region": steps_done,
                               "nccl_collectives_per_lm_iteration": (ncoll / max(1, steps_done)) if world > 1 else 0,
                               "scalar_exchange": ("peer mailboxes over NVLink" if ctx.mailbox_ready() else "NCCL") if world > 1 else "none (1 GPU)"},

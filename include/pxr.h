@@ -201,6 +201,12 @@ typedef struct {
   pxr_iteration_summary* iterations; /* caller-allocated */
   int64_t kernel_launches;        /* CUDA kernels of this library launched by the call */
   char message[256];
+  /* window residency of the patch slab (pxr_ba_run on a pinned host buffer, csrc/pxr_resident.cuh): side of the window
+   * brought over per observation (0: the whole slab was uploaded), observations whose whole patch was fetched later
+   * because the point left its window, and evaluation passes repeated for that; h2d_bytes counts what really crossed */
+  int32_t resident_window;
+  int32_t resident_passes_repeated;
+  int64_t resident_refetched;
 } pxr_summary;
 
 typedef struct pxr_ctx pxr_ctx;

@@ -284,6 +284,7 @@ int pxr_ctx_destroy(pxr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
   pxr::stager_destroy(ctx);
+  if (ctx->slab_cache) cudaFree(ctx->slab_cache);
   for (int r = 0; r < 16; ++r)
     if (r != ctx->rank) { if (ctx->mbox_peer[r]) cudaIpcCloseMemHandle(ctx->mbox_peer[r]); if (ctx->mbox_seq_peer[r]) cudaIpcCloseMemHandle(ctx->mbox_seq_peer[r]); }
   if (ctx->mbox_local) cudaFree(ctx->mbox_local);

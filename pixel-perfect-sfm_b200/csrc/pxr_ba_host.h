@@ -3,6 +3,7 @@
 #include <chrono>
 #include <string>
 #include <functional>
+#include <thread>
 #include <limits>
 #include <algorithm>
 #include <utility>
@@ -89,7 +90,8 @@ struct BA {
   DevBuf<int32_t> obs_img, img_cam, cam_model, pose_off, intr_off, corner, Wcols, Wdc;
   DevBuf<int64_t> obs_pt, obs_patch, point_off, pt_begin;
   DevBuf<uint32_t> cam_mask;
-  DevBuf<uint8_t> tmask, patches_owned;
+  DevBuf<uint8_t> tmask;
+  PatchSlab patches_owned;
   DevBuf<double> scale, refs;
   const uint8_t* d_patches = nullptr;
   // device: parameters (two sets: current / candidate)
@@ -158,13 +160,13 @@ struct BA {
   int pcg_setup_blocks();
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
-  bool chol_multikernel = false, chol_force_multikernel = false; int chol_grid = 0;
+  bool chol_multikernel = false, chol_force_multikernel = false, chol_band = false; int chol_grid = 0;
   DevBuf<int32_t> img_cols8, img_dc8; DevBuf<int8_t> img_src8;   // per-image column tables (<= 8 columns per image)
   DevBuf<int32_t> io_obs;           // observations grouped by image, chunks of <= 128 (camera-block build)
   DevBuf<int64_t> io_chunk_begin; int64_t io_n_chunks = 0;
   DevBuf<long long> chol_trace;     // PXR_CHOL_TRACE=<file>: panel-CTA time stamps
   DevBuf<int> chol_sync;            // flags of the persistent tile-DAG Cholesky (pxr_chol.cuh)
-  ~BA() { if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
+  ~BA() { if (res_thread.joinable()) res_thread.join(); if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
   // static co-visibility structure for the Schur complement (see ba_schur_pairs_kernel)
   DevBuf<int32_t> sp_px, sp_py;
   DevBuf<int64_t> sp_chunk_begin;
@@ -177,9 +179,32 @@ struct BA {
   SchurPairs schur_pairs();
 
   int create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, const pxr_solver_options* so, bool for_solve);
+  // ---- window residency of the patch slab (pxr_resident.cuh): only in the one-shot pxr_ba_run (the host source must
+  // outlive the solve), mapped pinned host source, C >= 8.  A repeated pass is local to the rank, so it composes with the
+  // multi-GPU block mode (it only adds a host look at the violation counter after each evaluation).
+  bool allow_resident = false, resident = false;
+  int res_window = 8;
+  bool res_window_fixed = false;                   // the caller knows the exact window (reference extraction: the points do not move)
+  DevBuf<uint32_t> res_rect;
+  DevBuf<unsigned long long> res_viol_count;
+  DevBuf<int64_t> res_viol_list, res_fix_list;
+  DevBuf<uint8_t> res_shared;
+  std::vector<const void*> res_srcs;               // host blocks of whole patches (one entry for a contiguous source)
+  std::vector<int64_t> res_block_first;            // [n_blocks+1]
+  std::vector<int64_t> h_obs_patch;                // host copy (which patch an observation reads), empty = identity
+  int64_t res_refetched = 0, res_passes_repeated = 0;
+  size_t res_esz = 2;
+  std::thread res_thread;                          // packs and uploads the windows while create() goes on
+  int res_thread_rc = 0; std::string res_thread_err;
+  int resident_setup(const pxr_ba_desc* d, size_t esz);                    // decides and allocates
+  int resident_begin(cudaStream_t us, double* h2d_patch);                  // K0 + rectangles + the window upload (own thread)
+  int resident_fix(int64_t* n_fixed);               // after an evaluation: fetch the patches of reported observations
+  void resident_args(FmEvalArgs& a);                // hooks the guard into an evaluation launch
   BADev dev();
   int project(int set, bool jac, double* xy_out);
   int fm(int mode, double* residuals_out, double* cost_dev, double* grad_out = nullptr);
+  int fm_k1(int mode, double* residuals_out, double* grad_out, const int64_t* list, int64_t n);   // K1 over all observations or a list
+  int fm_cost(double* cost_dev);                                                                   // robustified cost from obs_out
   int build();
   int evaluate(int set, bool jac, double* cost_out);
   int compute_step(double radius, bool* valid, double* model_cost_change);

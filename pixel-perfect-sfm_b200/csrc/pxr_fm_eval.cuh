@@ -113,9 +113,24 @@ struct FmEvalArgs {
   double* residuals;           // optional [n][C]
   double* desc;                // optional [n][C]: interpolated (normalised) descriptor f (reference extraction)
   double* grad = nullptr;      // optional [n][2][C]: d r/d u, d r/d v per channel (Jacobian mode; the cost-functor surface)
+  // window residency (pxr_resident.cuh): when set, only the rectangle res_rect[patch] of every patch has been brought
+  // to the device; an item whose 4x4 tap window leaves it is appended to viol_list (its outputs are garbage and the
+  // host re-runs the pass after fetching the patch)
+  const uint32_t* res_rect = nullptr;        // [n_patches] r0 | c0 << 8 | rows << 16 | cols << 24
+  unsigned long long* viol_count = nullptr;  // [1]
+  int64_t* viol_list = nullptr;              // [capacity >= n items]
   LossParams loss;
   int l2_normalize;
 };
+
+// the taps an item reads are rows clamp(row-1 .. row+2) and columns clamp(col-1 .. col+2) (per-tap clamp, grid2d.h:29-35):
+// are they all inside the resident rectangle?
+__device__ __forceinline__ bool window_resident(uint32_t rect, int row, int col, int ph, int pw) {
+  const int r0 = (int)(rect & 255u), c0 = (int)((rect >> 8) & 255u), nr = (int)((rect >> 16) & 255u), ncol = (int)(rect >> 24);
+  const int rlo = min(max(row - 1, 0), ph - 1), rhi = min(max(row + 2, 0), ph - 1);
+  const int clo = min(max(col - 1, 0), pw - 1), chi = min(max(col + 2, 0), pw - 1);
+  return rlo >= r0 && rhi < r0 + nr && clo >= c0 && chi < c0 + ncol;
+}
 
 #ifndef PXR_FM_WARPS
 #define PXR_FM_WARPS 16
@@ -394,6 +409,8 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       x.src = a.patches + pidx * patch_bytes;
       aux[lane] = x;
       ref_idx = ridx;
+      if (a.res_rect && lane < nvalid && !window_resident(a.res_rect[pidx], x.row, x.col, a.ph, a.pw))
+        a.viol_list[atomicAdd(a.viol_count, 1ull)] = o;
     }
     __syncwarp();
 

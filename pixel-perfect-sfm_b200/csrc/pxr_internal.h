@@ -32,6 +32,10 @@ struct pxr_ctx {
   int64_t nccl_collectives = 0;            // NCCL calls issued through this context (bench.py reports them per LM iteration)
   pxr::Stager* stager = nullptr;          // pinned ring of the pageable-memory upload pipeline (pxr_upload.cu)
   cudaStream_t upload_stream = nullptr;   // carries the patch slab so that host-side setup (and its small syncs) overlaps it
+  // one cached patch slab: cudaMalloc / cudaFree of tens of GB cost 0.1-0.5 s each, a multi-level refinement (or a
+  // reference extraction followed by the adjustment) would pay them per call; released with the context
+  void* slab_cache = nullptr;
+  size_t slab_cache_bytes = 0;
 };
 
 namespace pxr {
@@ -87,12 +91,52 @@ struct DevBuf {
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// The patch slab of one optimizer: taken from / returned to the context's one-entry cache when it is large.
+struct PatchSlab {
+  pxr_ctx* ctx = nullptr;
+  uint8_t* p = nullptr;
+  size_t n = 0;
+  static constexpr size_t kCacheFrom = (size_t)256 << 20;
+  PatchSlab() {}
+  PatchSlab(const PatchSlab&) = delete;
+  PatchSlab& operator=(const PatchSlab&) = delete;
+  ~PatchSlab() { release(); }
+  int alloc(pxr_ctx* c, size_t bytes) {
+    release();
+    ctx = c; n = bytes;
+    if (bytes == 0) return PXR_OK;
+    if (c->slab_cache && c->slab_cache_bytes >= bytes) {
+      p = (uint8_t*)c->slab_cache; n = c->slab_cache_bytes; c->slab_cache = nullptr; c->slab_cache_bytes = 0;
+      return PXR_OK;
+    }
+    if (c->slab_cache && bytes >= kCacheFrom) { cudaFree(c->slab_cache); c->slab_cache = nullptr; c->slab_cache_bytes = 0; }
+    PXR_CUDA(cudaMalloc((void**)&p, bytes));
+    return PXR_OK;
+  }
+  void release() {
+    if (!p) return;
+    if (ctx && n >= kCacheFrom && n > ctx->slab_cache_bytes) {
+      if (ctx->slab_cache) cudaFree(ctx->slab_cache);
+      ctx->slab_cache = p; ctx->slab_cache_bytes = n;
+    } else {
+      cudaFree(p);
+    }
+    p = nullptr; n = 0;
+  }
+};
+
 // large input upload on ctx->stream: any source (pinned, pageable, device); pageable sources are pipelined through a
 // pinned ring (pxr_upload.cu).  *h2d_bytes (optional) is incremented by the bytes that crossed PCIe.
 // `stream` (default: ctx->stream) is the stream the copies are ordered on.
 int upload_bytes(pxr_ctx* ctx, void* dst, const void* src, size_t bytes, double* h2d_bytes = nullptr, cudaStream_t stream = nullptr);
 int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size_t* sizes, int n, double* h2d_bytes = nullptr,
                     cudaStream_t stream = nullptr);
+// window residency (pxr_resident.cuh): the rectangle h_rect[p] of every patch -> its place in the full-layout slab, packed
+// on the host, moved by DMA, scattered on the device; pinned or pageable sources given as blocks of whole patches
+int upload_windows(pxr_ctx* ctx, uint8_t* slab, const void* const* srcs, const int64_t* block_first, int n_blocks,
+                   const uint32_t* h_rect, const uint32_t* d_rect, int64_t n_patches, int ph, int pw, int tap_bytes,
+                   double* h2d_bytes, cudaStream_t stream = nullptr);
+size_t staged_chunk_bytes();     // bytes of one staging buffer (PXR_STAGED_CHUNK, default 4 MB): a window / patch must fit
 // the context's side stream for the patch slab (created on first use)
 int upload_stream(pxr_ctx* ctx, cudaStream_t* out);
 void stager_destroy(pxr_ctx* ctx);

@@ -125,7 +125,15 @@ static int refs_on_device(pxr_ctx* ctx, BA& b, int loss_type, double loss_scale,
   a.loss.type = loss_type; a.loss.a = loss_scale;
   a.l2_normalize = b.interp.l2_normalize;
   int np = 0;
+  b.resident_args(a);       // window residency: the 4x4 taps under the projections are all that was brought over
   if (b.n_obs > 0) PXR_TRY(launch_fm_eval(ctx, b.dtype, b.C, 0, b.interp.use_float_simd != 0, a, &np));
+  for (;;) {                // (cannot trigger with windows cut from these very projections; kept as the general contract)
+    int64_t n_fixed = 0;
+    PXR_TRY(b.resident_fix(&n_fixed));
+    if (n_fixed == 0) break;
+    a.item_index = b.res_fix_list.p; a.begin = 0; a.end = n_fixed;
+    PXR_TRY(launch_fm_eval(ctx, b.dtype, b.C, 0, b.interp.use_float_simd != 0, a, &np));
+  }
   LossParams lp; lp.type = loss_type; lp.a = loss_scale;
   if (b.n_points > 0) {
     switch (b.C) {
@@ -177,6 +185,9 @@ extern "C" int pxr_refs_compute(pxr_ctx* ctx, const pxr_ba_desc* desc, const pxr
   so.loss_type = loss_type; so.loss_scale = loss_scale;
   BA b;
   const int64_t launches0 = ctx->launches;
+  // the descriptors are interpolated at the projections of the CURRENT reconstruction and nothing moves: exactly the
+  // 4x4 tap window of every observation is needed (1/16 of a 16x16 patch)
+  b.allow_resident = true; b.res_window = 4; b.res_window_fixed = true;
   PXR_TRY(b.create(ctx, &d, interp, &so, false));
   DevBuf<double> refs;
   DevBuf<int64_t> src;

@@ -77,9 +77,11 @@ NumaLocalScope::~NumaLocalScope() {
 }
 
 struct Stager {
-  static constexpr int kThreads = 6, kBufs = 2;
+  static constexpr int kThreads = 16, kBufs = 2;     // 6 threads carry the plain slab upload, up to 16 the window packing
+  static constexpr int kPlainThreads = 6;
   size_t chunk = 0;
   uint8_t* pin[kThreads][kBufs] = {};
+  uint8_t* dev[kThreads][kBufs] = {};                // device side of the window upload (packed windows before the scatter)
   cudaStream_t st[kThreads] = {};
   cudaEvent_t ev[kThreads][kBufs] = {};
   cudaEvent_t start = nullptr;
@@ -88,6 +90,7 @@ struct Stager {
       for (int b = 0; b < kBufs; ++b) {
         if (ev[t][b]) cudaEventDestroy(ev[t][b]);
         if (pin[t][b]) cudaFreeHost(pin[t][b]);
+        if (dev[t][b]) cudaFree(dev[t][b]);
       }
       if (st[t]) cudaStreamDestroy(st[t]);
     }
@@ -101,6 +104,8 @@ static size_t env_bytes(const char* name, size_t dflt) {
   const long long x = std::atoll(v);
   return x > 0 ? (size_t)x : dflt;
 }
+
+size_t staged_chunk_bytes() { return env_bytes("PXR_STAGED_CHUNK", (size_t)4 << 20); }
 
 static int stager_get(pxr_ctx* ctx, Stager** out) {
   const size_t chunk = env_bytes("PXR_STAGED_CHUNK", (size_t)4 << 20);
@@ -173,7 +178,7 @@ int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size
   PXR_TRY(stager_get(ctx, &s));
   const size_t chunk = s->chunk;
   const size_t n_chunks = (bytes + chunk - 1) / chunk;
-  const int n_threads = (int)std::min<size_t>(Stager::kThreads, n_chunks);
+  const int n_threads = (int)std::min<size_t>(Stager::kPlainThreads, n_chunks);
   // the destination may still be in use by earlier work on the consumer stream
   PXR_CUDA(cudaEventRecord(s->start, stream));
   cudaError_t errs[Stager::kThreads];
@@ -221,6 +226,136 @@ int upload_segments(pxr_ctx* ctx, void* dst, const void* const* srcs, const size
     const int last = (int)((mine - 1) % Stager::kBufs);
     PXR_CUDA(cudaStreamWaitEvent(stream, s->ev[t][last], 0));   // worker streams are in order: the last event covers all
   }
+  return PXR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ window upload
+// Packed windows -> their places in the slab.  One CTA per patch of the chunk; the window of patch p sits at
+// packed + (p - first) * win_bytes, row-major rows x (cols * tap_bytes).
+static __global__ void __launch_bounds__(256) scatter_windows_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ slab,
+                                                                     const uint32_t* __restrict__ rect, const int64_t* __restrict__ chunk_off,
+                                                                     int64_t first, int count, int ph, int pw, int tap_bytes) {
+  const int64_t patch_bytes = (int64_t)ph * pw * tap_bytes;
+  for (int k = blockIdx.x; k < count; k += gridDim.x) {
+    const int64_t p = first + k;
+    const uint32_t rc = rect[p];
+    const int r0 = (int)(rc & 255u), c0 = (int)((rc >> 8) & 255u), rows = (int)((rc >> 16) & 255u), cols = (int)(rc >> 24);
+    const int row_words = cols * tap_bytes / 16;
+    const uint8_t* src = packed + (chunk_off[p] - chunk_off[first]);
+    uint8_t* dst = slab + p * patch_bytes;
+    for (int w = threadIdx.x; w < rows * row_words; w += blockDim.x) {
+      const int r = w / row_words, q = w - r * row_words;
+      *reinterpret_cast<uint4*>(dst + ((int64_t)(r0 + r) * pw + c0) * tap_bytes + (int64_t)q * 16) =
+          *reinterpret_cast<const uint4*>(src + (int64_t)w * 16);
+    }
+  }
+}
+
+// Brings the rectangle h_rect[p] (r0 | c0<<8 | rows<<16 | cols<<24) of every patch into the slab (full [n][ph][pw][tap]
+// layout in device memory): host threads pack the rectangles of a chunk of patches into a pinned buffer (the only
+// bytes of the source they touch), the DMA engine moves the packed chunk, a small kernel on the same stream scatters
+// it into place.  Works for pinned and pageable sources alike; `srcs` as in upload_segments (blocks of whole patches).
+int upload_windows(pxr_ctx* ctx, uint8_t* slab, const void* const* srcs, const int64_t* block_first, int n_blocks,
+                   const uint32_t* h_rect, const uint32_t* d_rect, int64_t n_patches, int ph, int pw, int tap_bytes,
+                   double* h2d_bytes, cudaStream_t stream) {
+  if (!stream) stream = ctx->stream;
+  if (n_patches <= 0) return PXR_OK;
+  Stager* s = nullptr;
+  PXR_TRY(stager_get(ctx, &s));
+  const size_t chunk = s->chunk;
+  // packed offsets of the patches and the chunk boundaries (chunks of whole patches, at most `chunk` bytes)
+  std::vector<int64_t> off((size_t)n_patches + 1, 0);
+  for (int64_t p = 0; p < n_patches; ++p) {
+    const uint32_t rc = h_rect[p];
+    off[p + 1] = off[p] + (int64_t)((rc >> 16) & 255u) * (int64_t)(rc >> 24) * tap_bytes;
+  }
+  std::vector<int64_t> cfirst;       // first patch of every chunk
+  for (int64_t p = 0; p < n_patches;) {
+    cfirst.push_back(p);
+    int64_t q = p;
+    while (q < n_patches && off[q + 1] - off[p] <= (int64_t)chunk) ++q;
+    if (q == p) return fail(PXR_ERR_INTERNAL, "window of patch %lld exceeds the staging chunk", (long long)p);
+    p = q;
+  }
+  cfirst.push_back(n_patches);
+  const size_t n_chunks = cfirst.size() - 1;
+  DevBuf<int64_t> d_off;
+  PXR_TRY(d_off.upload(off.data(), off.size(), stream));
+  PXR_CUDA(cudaEventRecord(s->start, stream));          // d_off (and the slab's earlier users) before the worker streams
+  int n_threads = (int)std::min<size_t>(Stager::kThreads, n_chunks);
+  {
+    cpu_set_t cs; CPU_ZERO(&cs);
+    if (sched_getaffinity(0, sizeof(cs), &cs) == 0) n_threads = std::max(1, std::min(n_threads, CPU_COUNT(&cs)));
+    long quota = 0, period = 0;
+    if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      char q[32] = {};
+      if (std::fscanf(f, "%31s %ld", q, &period) == 2 && q[0] != 'm' && period > 0) quota = std::atol(q);
+      std::fclose(f);
+    }
+    if (quota > 0) n_threads = std::max(1, std::min<int>(n_threads, (int)(quota / period)));
+  }
+  const size_t patch_bytes = (size_t)ph * pw * tap_bytes;
+  cudaError_t errs[Stager::kThreads];
+  const int device = ctx->device;
+  for (int t = 0; t < n_threads; ++t)
+    for (int b = 0; b < Stager::kBufs; ++b)
+      if (!s->dev[t][b]) PXR_CUDA(cudaMalloc((void**)&s->dev[t][b], chunk));
+  auto work = [&](int t) {
+    NumaLocalScope numa(device);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->st[t], s->start, 0);
+    size_t k = 0;
+    for (size_t c = t; c < n_chunks && e == cudaSuccess; c += n_threads, ++k) {
+      const int b = (int)(k % Stager::kBufs);
+      e = cudaEventSynchronize(s->ev[t][b]);     // the previous DMA out of this pinned buffer and the scatter out of its device twin
+      if (e != cudaSuccess) break;
+      const int64_t p0 = cfirst[c], p1 = cfirst[c + 1];
+      uint8_t* out = s->pin[t][b];
+      int blk = 0;
+      if (n_blocks > 1) blk = (int)(std::upper_bound(block_first, block_first + n_blocks + 1, p0) - block_first) - 1;
+      for (int64_t p = p0; p < p1; ++p) {
+        while (n_blocks > 1 && p >= block_first[blk + 1]) ++blk;
+        const uint8_t* src = (const uint8_t*)srcs[blk] + (size_t)(p - (n_blocks > 0 ? block_first[blk] : 0)) * patch_bytes;
+        const uint32_t rc = h_rect[p];
+        const int r0 = (int)(rc & 255u), c0 = (int)((rc >> 8) & 255u), rows = (int)((rc >> 16) & 255u), cols = (int)(rc >> 24);
+        const size_t row_bytes = (size_t)cols * tap_bytes;
+        if (cols == pw) { std::memcpy(out, src + (size_t)r0 * pw * tap_bytes, row_bytes * rows); out += row_bytes * rows; }
+        else for (int r = 0; r < rows; ++r) { std::memcpy(out, src + ((size_t)(r0 + r) * pw + c0) * tap_bytes, row_bytes); out += row_bytes; }
+      }
+      const size_t len = (size_t)(off[p1] - off[p0]);
+      e = cudaMemcpyAsync(s->dev[t][b], s->pin[t][b], len, cudaMemcpyHostToDevice, s->st[t]);
+      if (e == cudaSuccess) {
+        scatter_windows_kernel<<<(unsigned)std::min<int64_t>(p1 - p0, 1024), 256, 0, s->st[t]>>>(s->dev[t][b], slab, d_rect, d_off.p, p0,
+                                                                                            (int)(p1 - p0), ph, pw, tap_bytes);
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(s->ev[t][b], s->st[t]);
+    }
+    errs[t] = e;
+  };
+  std::vector<std::thread> pool;
+  int started = 1;
+  try {
+    for (int t = 1; t < n_threads; ++t) { pool.emplace_back(work, t); ++started; }
+  } catch (const std::exception&) {
+  }
+  work(0);
+  for (int t = started; t < n_threads; ++t) work(t);
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < n_threads; ++t)
+    if (errs[t] != cudaSuccess) {
+      cudaDeviceSynchronize();
+      return fail(PXR_ERR_CUDA, "window upload failed: %s", cudaGetErrorString(errs[t]));
+    }
+  for (int t = 0; t < n_threads; ++t) {
+    const size_t mine = (n_chunks - t + n_threads - 1) / n_threads;
+    const int last = (int)((mine - 1) % Stager::kBufs);
+    PXR_CUDA(cudaStreamWaitEvent(stream, s->ev[t][last], 0));
+  }
+  ctx->launches += (int64_t)n_chunks;
+  // d_off is read by the scatter kernels: keep it until they are done (the caller's stream now depends on all of them)
+  PXR_CUDA(cudaStreamSynchronize(stream));
+  if (h2d_bytes) *h2d_bytes += (double)off[n_patches];
   return PXR_OK;
 }
 

@@ -506,7 +506,13 @@ class ReferenceExtractor:
         self.interp.validate_for_device()
 
     def run(self, problem_labels, reconstruction, feature_set):
-        ids = {p for p in reconstruction.points3D.keys() if p < len(problem_labels) and problem_labels[p] >= 0}
+        if hasattr(reconstruction, "point3D_id") and not hasattr(reconstruction, "points3D"):     # array-backed
+            pids = np.asarray(reconstruction.point3D_id)
+            labels = np.asarray(problem_labels)
+            inside = pids < len(labels)
+            ids = set(pids[inside][labels[pids[inside]] >= 0].tolist())
+        else:
+            ids = {p for p in reconstruction.points3D.keys() if p < len(problem_labels) and problem_labels[p] >= 0}
         fview = FeatureView(feature_set, reconstruction)
         prob, ir = build_problem(reconstruction, fview, None, None, None, for_references=ids)
         refs = {p: Reference() for p in ids}   # InitReferences

@@ -118,7 +118,8 @@ class Summary(C.Structure):
                 ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("num_iterations", C.c_int32), ("iterations_capacity", C.c_int32),
                 ("iterations", C.POINTER(IterationSummary)), ("kernel_launches", C.c_int64),
-                ("message", C.c_char * 256)]
+                ("message", C.c_char * 256), ("resident_window", C.c_int32), ("resident_passes_repeated", C.c_int32),
+                ("resident_refetched", C.c_int64)]
 
 
 class KADesc(C.Structure):

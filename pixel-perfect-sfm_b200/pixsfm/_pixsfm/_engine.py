@@ -117,6 +117,34 @@ def ba_run(problem, interp=None, options=None, ctx=None, capacity=512):
     return _capi.summary_to_dict(s)
 
 
+class PinnedArray:
+    """A numpy array in pinned (page-locked, device-mapped) host memory from pxr_host_alloc_pinned: the patch source
+    pxr_ba_run reads tap windows from directly (window residency, csrc/pxr_resident.cuh) and full-rate DMA otherwise.
+    `array` is the numpy view; the memory is released by close() / when the object dies."""
+
+    def __init__(self, shape, dtype, ctx=None):
+        self.ctx = ctx or _capi.default_context()
+        self.array = None
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        self._ptr = C.c_void_p()
+        _capi.check(self.ctx.lib.pxr_host_alloc_pinned(C.byref(self._ptr), C.c_size_t(max(nbytes, 1))))
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            self.ctx.lib.pxr_host_free_pinned(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def refs_compute(problem, interp=None, loss_type=1, loss_scale=0.25, iters=100, ctx=None):
     """pxr_refs_compute == ReferenceExtractor.run: -> (refs [n_points,C] f64, src_obs [n_points])"""
     ctx = ctx or _capi.default_context()

@@ -142,3 +142,73 @@ def test_patch_interpolator_on_the_device_matches_the_oracle():
                 assert np.abs(pi.interpolate(patch, xy)[0] - want).max() < 1e-12
                 assert np.abs(pi.interpolate_local(patch, uv)[0] - want).max() < 1e-11
                 assert pi.interpolate_nodes(patch, xy).shape == (1, 128)
+
+
+def _multilevel_scene(n_cams, n_points, track_len, channels, level_scales, seed):
+    """configs[3]-shaped inputs: one reconstruction and a FeatureManager with one FeatureSet per level.  Level l holds, per
+    observation, a patch of the point's feature field rendered at resolution `level_scales[l]` of the image (S2DNet's
+    levels sit at 1, 1/4, 1/16 of the image, reference models/s2dnet.py:65,92-98), the way features_from_reconstruction
+    delivers them: corner and scale in that level's pixel grid (features/extractor.py:192-193)."""
+    from pixsfm import features
+    from recon_util import make_reconstruction
+    rec, fm0, prob, gt = make_reconstruction(n_cams=n_cams, n_points=n_points, track_len=track_len, channels=channels, seed=seed)
+    fm = features.FeatureManager([channels] * len(level_scales), prob.patches.dtype)
+    per_image = {i: [o for o in range(prob.n_obs) if int(prob.obs_img[o]) == i] for i in range(n_cams)}
+    for lvl, sc in enumerate(level_scales):
+        size = int(round(1000 * sc))
+        patches, corners, _ = synthetic.render_patches(gt["xy_true"] * sc, prob.obs_pt, n_points, channels, 16, seed + 17 * lvl,
+                                                       0.01, prob.patches.dtype, image_size=max(size, 40))
+        fset = features.FeatureSet(channels, prob.patches.dtype)
+        for i in range(n_cams):
+            obs = per_image[i]
+            fset.emplace("image%03d.jpg" % i, features.FeatureMap(np.ascontiguousarray(patches[obs]), list(range(len(obs))),
+                                                                  corners[obs], {"scale": (sc, sc), "is_sparse": True}))
+        fm.fsets[lvl] = fset
+    return rec, fm
+
+
+def test_config3_shape_multilevel_costmap_triangulation_ba():
+    """BASELINE configs[3]: ETH3D-courtyard-shaped triangulation refinement — 38 images (the courtyard scene's size; the
+    reference tree only names the scene, eval/eth3d/config.py:7-8), multi-level features processed coarse to fine,
+    strategy `costmaps`, poses and intrinsics fixed, 10 iterations per level (configs/pixsfm_eth3d.yaml:
+    refine_focal_length / refine_extra_params / refine_extrinsics: false; bundle_adjustment/main.py:218-286).
+    The mirror's three refinements against the oracle doing references -> cost maps -> cost-map BA level by level."""
+    import copy
+    from pixsfm import bundle_adjustment as ba_pkg, features
+    from pixsfm._pixsfm import _bundle_adjustment as ba
+    scales = (1.0, 0.25, 0.0625)
+    rec, fm = _multilevel_scene(n_cams=38, n_points=700, track_len=5, channels=128, level_scales=scales, seed=43)
+    rec_ref = copy.deepcopy(rec)
+    conf = {"strategy": "costmaps",
+            "optimizer": {"refine_focal_length": False, "refine_extra_params": False, "refine_extrinsics": False,
+                          "solver": {"max_num_iterations": 10}}}
+    adj = ba_pkg.BundleAdjuster.create(conf)
+    out = adj.refine_multilevel(rec, fm)
+    assert len(out["summary"]) == 3 and len(out["costmaps"]) == 3
+    # nothing but the points may move
+    for i in rec.images:
+        assert np.array_equal(rec.images[i].tvec, rec_ref.images[i].tvec)
+        assert np.abs(rec.images[i].qvec - rec_ref.images[i].qvec / np.linalg.norm(rec_ref.images[i].qvec)).max() < 1e-15
+    for c in rec.cameras:
+        assert np.array_equal(rec.cameras[c].params, rec_ref.cameras[c].params)
+    # the oracle, level by level in the adjuster's order (coarse to fine: reverse index order, util/misc.py:19-23)
+    setup = ba_pkg.default_problem_setup(rec_ref)
+    options = ba.BundleOptimizerOptions(refine_focal_length=False, refine_extra_params=False, refine_extrinsics=False)
+    ic = _capi.default_interp()
+    ic_cm = _capi.default_interp(); ic_cm.l2_normalize = 0
+    so = _capi.default_ba_options(max_num_iterations=10)     # the adjuster's defaults: inner iterations on, Cauchy(0.25)
+    for k, lvl in enumerate((2, 1, 0)):
+        fview = features.FeatureView(fm.fset(lvl), rec_ref)
+        prob_r, ir_r = ba.build_problem(rec_ref, fview, None, None, None, for_references=set(rec_ref.points3D.keys()))
+        prob_r.refs = O.refs_compute(prob_r, ic, iters=100)[0]
+        cm = O.costmaps_compute(prob_r)
+        prob, ir = ba.build_problem(rec_ref, fview, setup, options, None)
+        assert prob.n_obs == prob_r.n_obs and np.all(prob.pose_const == 1) and np.all(prob.cam_const_mask & 0xF == 0xF)
+        p = prob.with_patches(cm)
+        s = O.ba_solve(p, ic_cm, so)
+        summ = out["summary"][k]
+        assert abs(summ.initial_cost - s["initial_cost"]) <= 1e-5 * max(s["initial_cost"], 1e-12)
+        assert abs(summ.final_cost - s["final_cost"]) <= 1e-4 * max(s["final_cost"], 1e-12) + 1e-9
+        ba.write_back(rec_ref, p, ir)
+    moved = [np.abs(rec.points3D[q].xyz - rec_ref.points3D[q].xyz).max() for q in rec.points3D]
+    assert max(moved) < 1e-5
