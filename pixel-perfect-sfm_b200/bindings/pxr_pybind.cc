@@ -1,7 +1,7 @@
 // pxr_pybind.cc — the pybind11 form of the binding INTEGRATION.md describes: what a maintainer of the reference puts
 // in place of `pixsfm/_pixsfm/bindings.cc:34-63` to reach libpxr.so from C++.  It binds the C-ABI of include/pxr.h
-// one to one (flat numpy arrays in, numpy arrays / dicts out); the problem construction that the reference does in
-// BundleOptimizer::SetUp stays with the caller.  Error codes become the exception types the reference throws:
+// one to one (flat numpy arrays in, numpy arrays / dicts out), the problem construction of BundleOptimizer::SetUp /
+// Parameterize included (`build_problem` -> pxr_problem_build, csrc/pxr_problem.cu).  Error codes become the exception types the reference throws:
 // PXR_ERR_INVALID_ARGUMENT / PXR_ERR_UNSUPPORTED -> ValueError (THROW_CHECK*, util/src/log_exceptions.h:52-84),
 // everything else -> RuntimeError.  The module is thin by design: no algorithm lives here.
 #include <pybind11/numpy.h>
@@ -207,6 +207,56 @@ PYBIND11_MODULE(_pxr_pybind, m) {
     check(pxr_shard_ka_problems((int32_t)weight.size(), weight.data(), world, out.mutable_data()));
     return out;
   }, "weight"_a, "world"_a);
+
+  // ---- problem construction: BundleOptimizer::SetUp + Parameterize (bundle_optimizer.h:139-165,247-442) and
+  // ReferenceExtractor::GetVisibleObservations (reference_extractor.h:171-205) over a structure-of-arrays reconstruction.
+  // `recon`: image_id, image_camera_id, p2d_begin, p2d_point3D_id, camera_id, camera_model, point3D_id, track_begin,
+  // track_image_id, track_point2D_idx.  `setup` (BA mode): image_ids, const_pose_ids, const_tvec_ids, const_tvec_masks,
+  // const_camera_ids, var_point_ids, const_point_ids.  `options`: refine_* flags, min_track_length; or mode = 1 with
+  // ref_point_ids (+ track_has_patch).  Returns the arrays of pxr_problem_copy by name.
+  m.def("build_problem", [](py::dict recon, py::dict setup, py::dict options) {
+    Fields r{recon, {}}, su{setup, {}}, op{options, {}};
+    pxr_recon_view v; std::memset(&v, 0, sizeof(v));
+    v.n_images = r.len("image_id"); v.image_id = r.arr<int64_t>("image_id"); v.image_camera_id = r.arr<int64_t>("image_camera_id");
+    v.p2d_begin = r.arr<int64_t>("p2d_begin"); v.p2d_point3D_id = r.arr<int64_t>("p2d_point3D_id", false);
+    v.n_cameras = r.len("camera_id"); v.camera_id = r.arr<int64_t>("camera_id"); v.camera_model = r.arr<int32_t>("camera_model");
+    v.n_points = r.len("point3D_id"); v.point3D_id = r.arr<int64_t>("point3D_id", false); v.track_begin = r.arr<int64_t>("track_begin");
+    v.track_image_id = r.arr<int64_t>("track_image_id", false); v.track_point2D_idx = r.arr<int64_t>("track_point2D_idx", false);
+    pxr_ba_build_options bo; std::memset(&bo, 0, sizeof(bo));
+    bo.refine_focal_length = op.scalar<int>("refine_focal_length", 1); bo.refine_principal_point = op.scalar<int>("refine_principal_point", 0);
+    bo.refine_extra_params = op.scalar<int>("refine_extra_params", 1); bo.refine_extrinsics = op.scalar<int>("refine_extrinsics", 1);
+    bo.min_track_length = op.scalar<int>("min_track_length", -1); bo.mode = op.scalar<int>("mode", 0);
+    bo.n_ref_points = op.len("ref_point_ids"); bo.ref_point_ids = op.arr<int64_t>("ref_point_ids", false);
+    bo.track_has_patch = op.arr<uint8_t>("track_has_patch", false);
+    pxr_ba_setup_view sv; std::memset(&sv, 0, sizeof(sv));
+    if (bo.mode == 0) {
+      sv.n_images = su.len("image_ids"); sv.image_ids = su.arr<int64_t>("image_ids", false);
+      sv.n_const_poses = su.len("const_pose_ids"); sv.const_pose_ids = su.arr<int64_t>("const_pose_ids", false);
+      sv.n_const_tvecs = su.len("const_tvec_ids"); sv.const_tvec_ids = su.arr<int64_t>("const_tvec_ids", false);
+      sv.const_tvec_masks = su.arr<uint8_t>("const_tvec_masks", false);
+      sv.n_const_cameras = su.len("const_camera_ids"); sv.const_camera_ids = su.arr<int64_t>("const_camera_ids", false);
+      sv.n_var_points = su.len("var_point_ids"); sv.var_point_ids = su.arr<int64_t>("var_point_ids", false);
+      sv.n_const_points = su.len("const_point_ids"); sv.const_point_ids = su.arr<int64_t>("const_point_ids", false);
+    }
+    pxr_problem_ir* ir = nullptr;
+    check(pxr_problem_build(&v, bo.mode == 0 ? &sv : nullptr, &bo, &ir));
+    int64_t n_obs = 0, n_img = 0, n_cam = 0, n_pts = 0;
+    pxr_problem_sizes(ir, &n_obs, &n_img, &n_cam, &n_pts);
+    carray<int64_t> o_pid(n_obs), o_img(n_obs), o_p2d(n_obs), obs_pt(n_obs), image_ids(n_img), camera_ids(n_cam), point_ids(n_pts);
+    carray<int32_t> obs_img(n_obs), img_cam(n_img);
+    carray<uint8_t> pose_const(n_img), tmask(n_img), point_const(n_pts);
+    carray<uint32_t> cam_mask(n_cam);
+    const int rc = pxr_problem_copy(ir, o_pid.mutable_data(), o_img.mutable_data(), o_p2d.mutable_data(), obs_img.mutable_data(),
+                                    obs_pt.mutable_data(), image_ids.mutable_data(), camera_ids.mutable_data(), point_ids.mutable_data(),
+                                    img_cam.mutable_data(), pose_const.mutable_data(), tmask.mutable_data(), point_const.mutable_data(),
+                                    cam_mask.mutable_data());
+    pxr_problem_destroy(ir);
+    check(rc);
+    return py::dict("obs_point3D_id"_a = o_pid, "obs_image_id"_a = o_img, "obs_point2D_idx"_a = o_p2d, "obs_img"_a = obs_img,
+                    "obs_pt"_a = obs_pt, "image_ids"_a = image_ids, "camera_ids"_a = camera_ids, "point_ids"_a = point_ids,
+                    "img_cam"_a = img_cam, "pose_const"_a = pose_const, "tvec_const_mask"_a = tmask, "point_const"_a = point_const,
+                    "cam_const_mask"_a = cam_mask);
+  }, "recon"_a, "setup"_a = py::dict(), "options"_a = py::dict());
 
   // ---- defaults (base/main.py:1-22, bundle_adjustment/main.py:30-62, keypoint_adjustment/main.py:60-83)
   m.def("default_ba_options", []() {

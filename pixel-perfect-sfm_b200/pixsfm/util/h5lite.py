@@ -386,7 +386,8 @@ class Group:
         self._require_writable()
         parts = [p for p in path.split("/") if p]
         parent = self.create_group("/".join(parts[:-1])) if len(parts) > 1 else self
-        arr = np.ascontiguousarray(data)
+        arr = np.asarray(data)
+        arr = arr if arr.flags["C_CONTIGUOUS"] else arr.copy()
         if arr.dtype.kind == "U":
             arr = np.char.encode(arr, "utf-8")
         if arr.dtype.kind not in "iufS":

@@ -1,7 +1,5 @@
 """hloc-side inputs of the keypoint adjustment (reference pixsfm/util/hloc.py:11-70): the image-pair list (text) and
-the keypoint / match files hloc writes (HDF5).  The text part and the array conversion live here unconditionally; the
-HDF5 part needs `h5py`, which is imported on use (it is not installable in the offline build image, so those few lines
-are the only ones of this module the tests cannot reach)."""
+the keypoint / match files hloc writes (HDF5), through h5py when present and util/h5lite.py otherwise."""
 import numpy as np
 
 
@@ -30,12 +28,14 @@ def matches_from_hloc_arrays(matches0, scores0=None, reverse=False):
 
 
 def _h5py():
+    """h5py when it is installed, else the built-in reader/writer of the classic HDF5 layout (util/h5lite.py: what h5py
+    writes by default and hloc's files use)"""
     try:
         import h5py
-    except ImportError as e:
-        raise ImportError("hloc keypoint / match files are HDF5: install h5py to read them (COLMAP databases are "
-                          "read without it, util/colmap.py)") from e
-    return h5py
+        return h5py
+    except ImportError:
+        from . import h5lite
+        return h5lite
 
 
 def _pair_key(h5f, name1, name2):

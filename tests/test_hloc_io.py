@@ -35,13 +35,8 @@ def test_pair_lookup_like_hloc_find_pair():
         hloc._pair_key(store, "a.jpg", "zzz.jpg")
 
 
-def test_hdf5_functions_say_what_is_missing(tmp_path):
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        with pytest.raises(ImportError, match="install h5py"):
-            hloc.read_keypoints_hloc(tmp_path / "kp.h5")
-        return
+def test_hdf5_keypoints_round_trip_with_or_without_h5py(tmp_path):
+    """h5py when installed, util/h5lite.py otherwise (tests/test_h5lite.py covers that reader against real HDF5 files)"""
     kp = {"a.jpg": np.random.default_rng(0).uniform(0, 100, (5, 2))}
     hloc.write_keypoints_hloc(tmp_path / "kp.h5", kp)
     assert np.array_equal(hloc.read_keypoints_hloc(tmp_path / "kp.h5")["a.jpg"], kp["a.jpg"])

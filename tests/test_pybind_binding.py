@@ -91,3 +91,27 @@ def test_ba_run_through_the_pybind_binding_equals_the_ctypes_mirror():
     assert np.abs(b.xyz - a.xyz).max() < 1e-7 and np.abs(b.qvec - a.qvec).max() < 1e-7   # atomics' summation order differs
     with pytest.raises(ValueError, match="unknown solver option"):
         pb.ba_run(ctx, d, {}, {"max_iterations": 6})
+
+
+def test_problem_builder_through_pybind_equals_the_mirror():
+    """BundleOptimizer::SetUp + Parameterize reached from C++ (pxr_problem_build): same arrays as the ctypes mirror"""
+    import recon_util
+    from pixsfm._pixsfm import _bundle_adjustment as ba
+    from pixsfm._pixsfm._features import FeatureView
+    rec, fm, _, _ = recon_util.make_reconstruction(n_cams=6, n_points=40, track_len=4, channels=16, seed=4)
+    ids = sorted(rec.images)
+    setup = ba.BundleAdjustmentSetup(); setup.add_images(ids[:4]); setup.set_constant_pose(ids[0]); setup.set_constant_tvec(ids[1], [0])
+    for pid in sorted(rec.points3D)[:10]:
+        setup.add_variable_point(pid)
+    options = ba.BundleOptimizerOptions(refine_extra_params=False, min_track_length=2)
+    prob, ir = ba.build_problem(rec, FeatureView(fm.fset(0), rec), setup, options)
+    out = pb.build_problem(rec.as_arrays(),
+                           {"image_ids": ids[:4], "const_pose_ids": [ids[0]], "const_tvec_ids": [ids[1]], "const_tvec_masks": np.array([1], np.uint8),
+                            "var_point_ids": sorted(rec.points3D)[:10]},
+                           {"refine_extra_params": 0, "min_track_length": 2})
+    assert list(out["image_ids"]) == ir.image_ids and list(out["point_ids"]) == ir.point_ids and list(out["camera_ids"]) == ir.camera_ids
+    for name in ("obs_img", "obs_pt", "img_cam", "pose_const", "tvec_const_mask", "point_const", "cam_const_mask"):
+        assert np.array_equal(out[name], getattr(prob, name)), name
+    assert [tuple(t) for t in zip(out["obs_image_id"], out["obs_point2D_idx"], out["obs_point3D_id"])] == list(ir.obs)
+    with pytest.raises(ValueError, match="setup image"):
+        pb.build_problem(rec.as_arrays(), {"image_ids": [999]}, {})
