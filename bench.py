@@ -636,7 +636,11 @@ def main():
                         "resident_window": s3["resident_window"], "observations_refetched": s3["resident_refetched"],
                         "evaluation_passes_repeated": s3["resident_passes_repeated"], "h2d_bytes_total": s3["h2d_bytes"]}
 
+            # one untimed call first: it pays cudaMalloc of the 33 GB slab (0.4-1.0 s, the context keeps the slab for the next
+            # call) and the creation of the staging ring — the e2e counterpart of the W warm-up steps of the device-timed value
+            cold = one_shot(None)
             e2e = one_shot(None)
+            e2e["first_call_seconds"] = cold["seconds"]
             e2e["call"] = ("pxr_ba_run on a pinned host buffer of %.1f GB of patches: %s + solve + read back"
                            % (pbytes / 1e9, ("only the %dx%d tap window of every observation crosses PCIe (packed by host threads, DMA, "
                                              "scattered on the device; whole patches for observations that leave it)"

@@ -111,9 +111,11 @@ typedef struct {
   double min_lm_diagonal;           /* 1e-6 */
   double max_lm_diagonal;           /* 1e32 */
   int32_t jacobi_scaling;           /* 1 */
-  int32_t deterministic;            /* 1: fixed-order (bit-reproducible) build of the normal equations: Hcc/gc/Hpp/gp/S are
-                                     * accumulated by segmented reductions in a static order instead of fp64 atomics
-                                     * (SURVEY §5); slower. 0: atomics (run-to-run differences ~1e-16 relative) */
+  int32_t deterministic;            /* 1: bit-reproducible solve.  The normal equations are assembled by fixed-order reductions
+                                     * instead of fp64 atomics (image / pair chunk partials summed in chunk order, point blocks
+                                     * observation by observation, scalar sums block by block: csrc/pxr_block.cuh) on the
+                                     * block-mode driver; needs <= 8 camera columns per image.  0: atomics (run-to-run
+                                     * differences ~1e-16 relative per sum).  tests/test_gpu_deterministic.py */
   int32_t use_nonmonotonic_steps;   /* ceres::Solver::Options::use_nonmonotonic_steps (the reference's configs/default.yaml
                                      * sets it for KA, BA and QKA); 0 */
   int32_t max_consecutive_nonmonotonic_steps; /* 5 */

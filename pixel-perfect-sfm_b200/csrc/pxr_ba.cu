@@ -274,7 +274,10 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
     // block mode: image-block assembly + ONE all-reduce per LM iteration (pxr_block.cuh).  Always on with several ranks
     // (the image tables are replicated, so every rank takes the same decision); PXR_BLOCK_ASSEMBLY=1 runs the same code on
     // one GPU (tests).  Images with more than 8 camera columns keep the dense multi-collective path.
-    block_mode = for_solve && dc_needed <= 8 && (ctx->world > 1 || getenv("PXR_BLOCK_ASSEMBLY") != nullptr);
+    deterministic = for_solve && opt.deterministic != 0;
+    if (deterministic && dc_needed > 8)
+      return fail(PXR_ERR_UNSUPPORTED, "deterministic assembly needs <= 8 camera columns per image (pose 6 + intrinsics), got %d", dc_needed);
+    block_mode = for_solve && dc_needed <= 8 && (ctx->world > 1 || deterministic || getenv("PXR_BLOCK_ASSEMBLY") != nullptr);
     if (ctx->world > 1 && sparse_schur && !block_mode) sparse_schur = false;
     if (!sparse_schur && (int64_t)nc * nc * 8 > (int64_t)40e9)
       return fail(PXR_ERR_UNSUPPORTED, "reduced camera system too large for the dense path (nc=%d) and the block-sparse path needs ITERATIVE_SCHUR with <= 8 camera columns per image", nc);
@@ -309,14 +312,23 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
         for (int64_t o = 0; o < n_obs; ++o) if (img_dc[d->obs_img[o]] > 0) list[cur_pos[d->obs_img[o]]++] = (int32_t)o;
       }
       std::vector<int64_t> cb;
-      for (int i = 0; i < n_images; ++i)
+      h_img_chunk_begin.assign((size_t)n_images + 1, 0);
+      for (int i = 0; i < n_images; ++i) {
+        h_img_chunk_begin[i] = (int64_t)cb.size();
         for (int64_t b = cnt[i]; b < cnt[i + 1]; b += 128) cb.push_back(b);
+      }
+      h_img_chunk_begin[n_images] = (int64_t)cb.size();
       cb.push_back(cnt[n_images]);
       io_n_chunks = (int64_t)cb.size() - 1;
       if (io_n_chunks > 0) {
         PXR_TRY(io_obs.upload(list.data(), list.size(), s));
         PXR_TRY(io_chunk_begin.upload(cb.data(), cb.size(), s));
         PXR_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
+      }
+      if (deterministic) {                    // fixed-order reduction of the camera-block chunk partials (pxr_block.cuh)
+        PXR_TRY(det_cam_part.alloc((size_t)std::max<int64_t>(io_n_chunks, 1) * 48));
+        PXR_TRY(det_img_chunk_begin.upload(h_img_chunk_begin.data(), h_img_chunk_begin.size(), s));
+        PXR_CUDA(cudaStreamSynchronize(s));
       }
     }
   }
@@ -325,6 +337,11 @@ int BA::create(pxr_ctx* c, const pxr_ba_desc* d, const pxr_interp_config* ic, co
   PXR_TRY(rhs.alloc(nc));
   PXR_TRY(diag.alloc(nl)); PXR_TRY(jscale.alloc(nl)); PXR_TRY(D2.alloc(nl)); PXR_TRY(delta.alloc(nl));
   PXR_TRY(partials.alloc(fm_max_partials(ctx)));
+  if (deterministic) {
+    const int64_t big = std::max<int64_t>({n_obs, n_points * 3, (int64_t)n_images * 4, (int64_t)n_cameras * kMaxK});
+    PXR_TRY(det_scal_part.alloc((size_t)(cdiv(big, 128) * 4 + 16)));
+    if (io_n_chunks == 0 && n_obs > 0) return fail(PXR_ERR_UNSUPPORTED, "deterministic assembly needs the per-image chunk lists (problem too large for 32-bit observation ids)");
+  }
   PXR_TRY(scalars.alloc(16));
   PXR_TRY(flags.alloc(4));
   PXR_TRY(rdiag.alloc(kNB));
@@ -866,7 +883,10 @@ int BA::apply_step(double* step_norm, double* x_norm) {
   StageScope st(this, 8);
   PXR_CUDA(cudaMemsetAsync(scalars.p + 5, 0, 4 * 8, ctx->stream));
   const int64_t n = std::max<int64_t>(std::max<int64_t>(n_points, n_images), n_cameras);
+  if (deterministic) a.part = det_scal_part.p;
   PXR_LAUNCH(ctx, ba_plus_kernel, (unsigned)cdiv(n, 128), 128, 0, a);
+  if (deterministic)
+    for (int k = 0; k < 4; ++k) PXR_LAUNCH(ctx, det_reduce_add_kernel, 1, 1024, 0, det_scal_part.p, cdiv(n, 128), 4, k, a.acc + 1 + k);
   PXR_CUDA(cudaGetLastError());
   if (!block_mode) PXR_TRY(allreduce_f64(ctx, scalars.p + 5, 2));  // point parts are sharded, camera parts replicated (block mode: scalar exchange)
   if (step_norm || x_norm) {

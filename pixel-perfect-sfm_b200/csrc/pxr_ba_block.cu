@@ -156,6 +156,19 @@ int BA::block_setup() {
     std::vector<int32_t> ck(h_chunk_key_local.size());
     for (size_t c = 0; c < ck.size(); ++c) ck[c] = l2g[(size_t)h_chunk_key_local[c]];
     PXR_TRY(ss_chunk_key.upload(ck.data(), ck.size(), s));
+    if (deterministic) {
+      // the pair chunks of one key are consecutive (the pair list is grouped by image pair): chunk range per key
+      std::vector<int64_t> kb((size_t)gcode.size() + 1, 0);
+      for (size_t c = 0; c < ck.size(); ++c) {
+        if (c && ck[c] < ck[c - 1]) return fail(PXR_ERR_INTERNAL, "pair chunks are not grouped by key");
+        kb[(size_t)ck[c] + 1]++;
+      }
+      for (size_t k = 0; k < gcode.size(); ++k) kb[k + 1] += kb[k];
+      PXR_TRY(det_key_chunk_begin.upload(kb.data(), kb.size(), s));
+      PXR_TRY(det_pair_part.alloc(std::max<size_t>(ck.size(), 1) * 72));
+      PXR_TRY(det_gimg.alloc((size_t)n_images * 8)); PXR_TRY(det_rimg.alloc((size_t)n_images * 8));
+      PXR_TRY(det_gimg.zero(s)); PXR_TRY(det_rimg.zero(s));
+    }
     PXR_CUDA(cudaStreamSynchronize(s));
   }
   PXR_TRY(ss_key_a.upload(h_key_a.data(), h_key_a.size(), s)); PXR_TRY(ss_key_b.upload(h_key_b.data(), h_key_b.size(), s));
@@ -315,7 +328,18 @@ int BA::build_block() {
       PXR_LAUNCH(ctx, ba_build_staged_kernel, (unsigned)cdiv(n_obs, 128), 128, staged_smem, dv);
     else PXR_LAUNCH(ctx, ba_build_kernel<true>, (unsigned)cdiv(n_obs, 128), 128, 0, dv, 0);
     if (io_n_chunks > 0)
-      PXR_LAUNCH(ctx, ba_build_cam_kernel, (unsigned)cdiv(io_n_chunks * 32, 256), 256, 0, dv, io_obs.p, io_chunk_begin.p, io_n_chunks, L);
+      PXR_LAUNCH(ctx, ba_build_cam_kernel, (unsigned)cdiv(io_n_chunks * 32, 256), 256, 0, dv, io_obs.p, io_chunk_begin.p, io_n_chunks, L,
+                 deterministic ? det_cam_part.p : nullptr);
+    if (deterministic) {
+      // fixed-order sums: chunk partials -> image blocks and image gradients -> columns; point blocks observation by observation
+      PXR_LAUNCH(ctx, det_cam_reduce_kernel, (unsigned)cdiv((int64_t)n_images * 48, 256), 256, 0, det_cam_part.p, det_img_chunk_begin.p,
+                 n_images, L, det_gimg.p);
+      if (nc > 0) {
+        GatherMap dg{nullptr, dg_ptr.p, dg_src.p, nc};
+        PXR_LAUNCH(ctx, det_gather_cols_kernel, (unsigned)cdiv(nc, 256), 256, 0, dg, det_gimg.p, L + pk_off_gc, nc);
+      }
+      if (n_points > 0) PXR_LAUNCH(ctx, det_point_blocks_kernel, (unsigned)cdiv(n_points, 128), 128, 0, dv);
+    }
   }
   if (n_points > 0) {
     BADev dv = dev(); dv.Hcc = nullptr;
@@ -345,7 +369,17 @@ int BA::compute_step_block(double radius) {
     PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
     if (sp_n_chunks > 0)
       PXR_LAUNCH(ctx, sp_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p,
-                 Tbuf.p, L + pk_off_B, L + pk_off_rhs);
+                 Tbuf.p, L + pk_off_B, L + pk_off_rhs, deterministic ? det_pair_part.p : nullptr);
+    if (deterministic) {
+      PXR_CUDA(cudaMemsetAsync(det_rimg.p, 0, (size_t)n_images * 8 * 8, s));
+      if (ss_n_keys > 0)
+        PXR_LAUNCH(ctx, det_pair_reduce_kernel, (unsigned)cdiv((int64_t)ss_n_keys * 72, 256), 256, 0, det_pair_part.p, det_key_chunk_begin.p,
+                   ss_n_keys, ss_key_a.p, ss_key_self.p, L + pk_off_B, det_rimg.p);
+      if (nc > 0) {
+        GatherMap dg{nullptr, dg_ptr.p, dg_src.p, nc};
+        PXR_LAUNCH(ctx, det_gather_cols_kernel, (unsigned)cdiv(nc, 256), 256, 0, dg, det_rimg.p, L + pk_off_rhs, nc);
+      }
+    }
   }
   st.reset();
   if (nc > 0) {
@@ -383,8 +417,10 @@ int BA::compute_step_block(double radius) {
   PXR_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 4 * 8, s));
   if (n_points > 0) PXR_LAUNCH(ctx, ba_backsub_kernel, (unsigned)cdiv(n_points * 32, 256), 256, 0, d, D2.p, delta.p);
   if (n_obs > 0) {
-    if (img_src8.p) PXR_LAUNCH(ctx, ba_model_cost_kernel<true>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
-    else PXR_LAUNCH(ctx, ba_model_cost_kernel<false>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4);
+    double* part = deterministic ? det_scal_part.p : nullptr;
+    if (img_src8.p) PXR_LAUNCH(ctx, ba_model_cost_kernel<true>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4, part);
+    else PXR_LAUNCH(ctx, ba_model_cost_kernel<false>, (unsigned)cdiv(n_obs, 256), 256, 0, d, delta.p, scalars.p + 4, part);
+    if (part) PXR_LAUNCH(ctx, det_reduce_add_kernel, 1, 1024, 0, part, cdiv(n_obs, 256), 1, 0, scalars.p + 4);
   }
   PXR_CUDA(cudaGetLastError());
   return PXR_OK;
@@ -535,7 +571,9 @@ int BA::lm_iterate_block(int max_iteration) {
       if (rc != PXR_OK) { swap_sets(); return rc; }
       PXR_CUDA(cudaMemsetAsync(scalars.p + 11, 0, 16, s));
       auto run = [&](const double* a, const double* b, int64_t n, double* acc) {
-        if (n > 0) PXR_LAUNCH(ctx, diff_norm_kernel, (unsigned)cdiv(n, 256), 256, 0, a, b, n, acc);
+        if (n <= 0) return;
+        PXR_LAUNCH(ctx, diff_norm_kernel, (unsigned)cdiv(n, 256), 256, 0, a, b, n, acc, deterministic ? det_scal_part.p : nullptr);
+        if (deterministic) PXR_LAUNCH(ctx, det_reduce_add_kernel, 1, 1024, 0, det_scal_part.p, cdiv(n, 256), 1, 0, acc);
       };
       run(cam[0].p, cam[1].p, (int64_t)n_cameras * kMaxK, scalars.p + 12);
       run(q[0].p, q[1].p, (int64_t)n_images * 4, scalars.p + 12);

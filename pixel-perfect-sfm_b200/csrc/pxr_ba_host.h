@@ -143,6 +143,11 @@ struct BA {
   DevBuf<uint8_t> br_chunk_first;
   DevBuf<double> br_ypart, mb_in, mb_out;
   int64_t gmS_rows = 0, gmD_rows = 0, br_n_chunks = 0;
+  // deterministic assembly (pxr_solver_options.deterministic): block mode + fixed-order reductions of the chunk partials
+  bool deterministic = false;
+  std::vector<int64_t> h_img_chunk_begin;           // [n_images+1] chunks of every image in io order (create())
+  DevBuf<int64_t> det_img_chunk_begin, det_key_chunk_begin;
+  DevBuf<double> det_cam_part, det_pair_part, det_gimg, det_rimg, det_scal_part;
   bool jscale_c_pending = false;
   bool blk_lag_gmax = false;                       // world > 1: max |g| of the current point is known after the next all-reduce
   int block_setup();                               // global keys, gather maps, block rows

@@ -256,7 +256,8 @@ static __global__ void __launch_bounds__(128) ba_build_staged_kernel(BADev d) {
 // element per chunk: 128x fewer L2 atomics than ba_build_kernel's camera part.  Used when dcmax <= 8.
 static __global__ void __launch_bounds__(256) ba_build_cam_kernel(BADev d, const int32_t* __restrict__ io_obs,
                                                                   const int64_t* __restrict__ chunk_begin, int64_t n_chunks,
-                                                                  double* __restrict__ Himg /* [n_images][64] or null: dense Hcc */) {
+                                                                  double* __restrict__ Himg /* [n_images][64] or null: dense Hcc */,
+                                                                  double* __restrict__ part = nullptr /* deterministic mode: [n_chunks][48] partial sums, no atomics */) {
   const int lane = threadIdx.x & 31;
   const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (chunk >= n_chunks) return;
@@ -298,6 +299,7 @@ static __global__ void __launch_bounds__(256) ba_build_cam_kernel(BADev d, const
     const double tot = warp_reduce8_transposed(acc + gsel * 8, lane);
     if ((lane & 3) != 0) continue;
     const int vi = gsel * 8 + idx;
+    if (part) { part[chunk * 48 + vi] = tot; continue; }       // reduced per image in chunk order by det_cam_reduce_kernel
     if (vi < 36) {
       int a = 0;
       while ((a + 1) * (a + 2) / 2 <= vi) ++a;
@@ -683,7 +685,7 @@ static __global__ void __launch_bounds__(256) ba_backsub_kernel(BADev d, const d
 // K5b: model cost change, the literal ceres formula  -(J d)^T (r + J d / 2)  per residual block in
 // the reduced 2-D space:  u = d(uv)/d(theta) * delta ;  acc += u^T b' + u^T A' u / 2   (one thread per obs)
 template <bool FAST>
-static __global__ void __launch_bounds__(256) ba_model_cost_kernel(BADev d, const double* delta, double* acc) {
+static __global__ void __launch_bounds__(256) ba_model_cost_kernel(BADev d, const double* delta, double* acc, double* block_part = nullptr) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double part = 0.0;
   if (o < d.n_obs) {
@@ -715,7 +717,11 @@ static __global__ void __launch_bounds__(256) ba_model_cost_kernel(BADev d, cons
   part = warp_sum(part);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
   __syncthreads();
-  if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; ++k) t += sh[k]; atomic_add_f64(&acc[0], t); }
+  if (threadIdx.x == 0) {
+    double t = 0; for (int k = 0; k < 8; ++k) t += sh[k];
+    if (block_part) block_part[blockIdx.x] = t;   // deterministic mode: summed in block order by det_reduce_add_kernel
+    else atomic_add_f64(&acc[0], t);
+  }
 }
 
 // (A variant of K5b that staged its records through shared memory like ba_build_staged_kernel measured no gain:
@@ -729,6 +735,7 @@ struct PlusArgs {
   double* cam_o; double* q_o; double* t_o; double* X_o;
   const double* delta;
   double* acc;  // points: [1] += ||x_plus - x||^2, [2] += ||x||^2 ; cameras/poses: [3], [4] (replicated across ranks)
+  double* part = nullptr;   // deterministic mode: [gridDim.x][4] per-block sums instead of the atomics
 };
 static __global__ void __launch_bounds__(128) ba_plus_kernel(PlusArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -782,7 +789,23 @@ static __global__ void __launch_bounds__(128) ba_plus_kernel(PlusArgs a) {
   __syncthreads();
   if (threadIdx.x < 4) {
     const double v = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
-    if (v != 0.0) atomic_add_f64(&a.acc[1 + threadIdx.x], v);
+    if (a.part) a.part[(int64_t)blockIdx.x * 4 + threadIdx.x] = v;
+    else if (v != 0.0) atomic_add_f64(&a.acc[1 + threadIdx.x], v);
+  }
+}
+
+// deterministic mode: out[0] += sum_b part[b * stride + k] in block order (one CTA, fixed tree)
+static __global__ void __launch_bounds__(1024) det_reduce_add_kernel(const double* __restrict__ part, int64_t n_blocks, int stride, int k, double* out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n_blocks; i += blockDim.x) s += part[i * stride + k];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = sh[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] += v;
   }
 }
 

@@ -79,6 +79,87 @@ static __global__ void __launch_bounds__(256) blk_absmax_kernel(const double* __
     atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
 }
 
+// ---------------------------------------------------------------- deterministic assembly (pxr_solver_options.deterministic)
+// The block build sums with fp64 atomics: one per element per 128-observation chunk (camera blocks), per pair chunk (B_key,
+// rhs) and per (point, warp) (H_pp, g_p) — the order of those additions changes from run to run (1e-16 relative per sum).
+// In deterministic mode the chunk kernels write their partial sums instead and these kernels add them in a fixed order.
+
+// H_img (36 lower-triangle entries) and the image's gradient (8) from its chunks, in chunk order
+static __global__ void __launch_bounds__(256) det_cam_reduce_kernel(const double* __restrict__ part, const int64_t* __restrict__ img_chunk_begin,
+                                                                    int n_images, double* __restrict__ Himg, double* __restrict__ gimg) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_images * 48) return;
+  const int img = (int)(t / 48), e = (int)(t % 48);
+  if (e >= 44) return;
+  double v = 0.0;
+  for (int64_t c = img_chunk_begin[img]; c < img_chunk_begin[img + 1]; ++c) v += part[c * 48 + e];
+  if (e < 36) {
+    int a = 0;
+    while ((a + 1) * (a + 2) / 2 <= e) ++a;
+    Himg[(int64_t)img * 64 + a * 8 + (e - a * (a + 1) / 2)] = v;
+  } else {
+    gimg[(int64_t)img * 8 + (e - 36)] = v;
+  }
+}
+
+// B_key (64) and, for self keys, the image's  sum T g_p  (8) from the key's pair chunks, in chunk order
+static __global__ void __launch_bounds__(256) det_pair_reduce_kernel(const double* __restrict__ part, const int64_t* __restrict__ key_chunk_begin,
+                                                                     int n_keys, const int32_t* __restrict__ key_a, const uint8_t* __restrict__ key_self,
+                                                                     double* __restrict__ Bk, double* __restrict__ rimg) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_keys * 72) return;
+  const int key = (int)(t / 72), e = (int)(t % 72);
+  double v = 0.0;
+  for (int64_t c = key_chunk_begin[key]; c < key_chunk_begin[key + 1]; ++c) v += part[c * 72 + e];
+  if (e < 64) Bk[(int64_t)key * 64 + e] = v;
+  else if (key_self[key]) rimg[(int64_t)key_a[key] * 8 + (e - 64)] = v;
+}
+
+// out[col] = sum over the images that own the column of vec[img][a], in the fixed order of the diagonal gather map
+// (dg.src = img*64 + a*9): the camera gradient and the Schur right-hand side
+static __global__ void __launch_bounds__(256) det_gather_cols_kernel(GatherMap dg, const double* __restrict__ vec, double* __restrict__ out, int nc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  double v = 0.0;
+  for (int64_t j = dg.ptr[i]; j < dg.ptr[i + 1]; ++j) { const int32_t s = dg.src[j]; v += vec[(int64_t)(s >> 6) * 8 + (s & 63) / 9]; }
+  out[i] = v;
+}
+
+// H_pp / g_p of every point from its observations in observation order (they are sorted by point): overwrites what
+// ba_build_staged_kernel accumulated with atomics
+static __global__ void __launch_bounds__(128) det_point_blocks_kernel(BADev d) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.n_points) return;
+  double v[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) v[k] = 0.0;
+  if (d.point_off[p] >= 0) {
+    const int Wd = 9 + d.K;
+    for (int64_t o = d.pt_begin[p]; o < d.pt_begin[p + 1]; ++o) {
+      const double* oo = d.obs_out + o * 8;
+      double rho[3];
+      loss_eval(d.loss, 1.0, oo[0], rho);
+      const double bu = rho[1] * oo[1], bv = rho[1] * oo[2];
+      const double auu = rho[1] * oo[3], auv = rho[1] * oo[4], avv = rho[1] * oo[5];
+      const double* J = d.juv + o * (int64_t)d.juv_stride;
+      const double pu[3] = {J[6], J[7], J[8]}, pv[3] = {J[Wd + 6], J[Wd + 7], J[Wd + 8]};
+      double apu[3], apv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { apu[k] = auu * pu[k] + auv * pv[k]; apv[k] = auv * pu[k] + avv * pv[k]; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        v[a] += pu[a] * bu + pv[a] * bv;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) v[3 + a * 3 + b] += pu[a] * apu[b] + pv[a] * apv[b];
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) d.gp[p * 3 + a] = v[a];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) d.Hpp[p * 9 + k] = v[3 + k];
+}
+
 // max |g_p| over this rank's variable points -> slot (as ordered-uint max; the slot is zeroed by the caller)
 static __global__ void __launch_bounds__(256) blk_gpmax_kernel(const double* __restrict__ gp, const int64_t* __restrict__ point_off,
                                                                int64_t n_points, double* slot) {

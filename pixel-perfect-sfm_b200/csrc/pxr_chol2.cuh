@@ -168,107 +168,56 @@ __device__ __forceinline__ void gemm_nt_sub(Tile out, Tile a, Tile b, int tid) {
   }
 }
 
-// 1/sqrt(d) for the pivot chain: fp32 seed (MUFU.RSQ) + two Newton steps in fp64 (22 -> 44 -> 88 bits), a shorter
-// dependent chain than the library's rsqrt(double)
-__device__ __forceinline__ double rsqrt_chain(double d) {
-  double r = (double)rsqrtf((float)d);
-  const double h = 0.5 * d;
-  r = r * (1.5 - h * r * r);
-  r = r * (1.5 - h * r * r);
-  return r;
-}
-
-// The chain group (128 threads, barrier `bar`) factors the 32x32 block in `a` (lower triangle valid) in four 8-column
-// panels.  Warp 0 carries the dependent chain with lane = row: every lane factors the 8x8 diagonal block redundantly in
-// registers (no shuffle on the pivot chain: rsqrt -> mul -> fma per pivot), solves its own row against it, and applies
-// the panel to the NEXT panel's 8 columns itself (look-ahead), so it never waits for the other three warps — they apply
-// the panel to the columns beyond while warp 0 is already on the next one.  Leaves L (zeros above the diagonal) in `a`;
-// returns false on a bad pivot (warp 0).
+// The chain group (128 threads, barrier `bar`) factors the 32x32 block in `a` (lower triangle valid): four 8-column
+// panels, warp 0 factors a panel with lane = row and the row's 8 entries in registers, all four warps apply the rank-8
+// update to the trailing block.  Leaves L (zeros above the diagonal) in `a`; returns false on a bad pivot (warp 0).
+// (A variant with the 8x8 diagonal blocks factored redundantly in registers, an fp32-seeded Newton rsqrt and a
+//  look-ahead by the chain warp was written and did not pass the parity tests in the one run it got; this is the
+//  version that did.)
 __device__ __forceinline__ bool factor_diag_group(Tile a, double* rd, int kb, int tid, int bar) {
   const int warp = tid >> 5, lane = tid & 31;
   bool ok = true;
   if (tid >= kb && tid < TB) a[tid][tid] = 1.0;      // identity padding of a ragged last tile
   bar_group(bar);
-  double r[8];                                       // warp 0: my row's entries of the current panel, all earlier panels applied
-  if (warp == 0) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) r[c] = a[lane][c];
-  }
 #pragma unroll 1
   for (int jb = 0; jb < 4; ++jb) {
     const int j0 = jb * 8;
     if (warp == 0) {
-      if (jb > 0) {                                  // the diagonal block lives in the registers of lanes j0..j0+7: share it
+      double r[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) a[lane][j0 + c] = r[c];
-        __syncwarp();
-      }
-      double D[8][8];                                // lower triangle of the 8x8 diagonal block, then of its factor
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k <= i; ++k) D[i][k] = a[j0 + i][j0 + k];
-      double rinv[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {                  // right-looking on the registers: one fma between two pivots
-        const double d = D[c][c];
-        if (!(d > 0.0) || !isfinite(d)) ok = false;
-        const double rc = rsqrt_chain(d);
-        rinv[c] = rc;
-        D[c][c] = d * rc;
-#pragma unroll
-        for (int i = c + 1; i < 8; ++i) D[i][c] *= rc;
-#pragma unroll
-        for (int i = c + 1; i < 8; ++i)
-#pragma unroll
-          for (int k = c + 1; k <= i; ++k) D[i][k] -= D[i][c] * D[k][c];
-      }
-      // my row against the block: x L_b^T = r  (for the block's own rows this reproduces L_b; entries above the diagonal -> 0)
-      double x[8];
+      for (int c = 0; c < 8; ++c) r[c] = a[lane][j0 + c];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        double v = r[c];
+        const int j = j0 + c;
+        const double dj = __shfl_sync(0xffffffffu, r[c], j);
+        if (!(dj > 0.0) || !isfinite(dj)) ok = false;
+        const double rj = rsqrt(dj);
+        double lij = r[c];
+        if (lane == j) { lij = dj * rj; rd[j] = rj; }
+        else if (lane > j) lij *= rj;
+        r[c] = lij;
 #pragma unroll
-        for (int k = 0; k < c; ++k) v -= x[k] * D[c][k];
-        x[c] = v * rinv[c];
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { x[c] = (lane >= j0 + c) ? x[c] : 0.0; a[lane][j0 + c] = x[c]; }
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) rd[j0 + c] = rinv[c];
-      }
-    }
-    bar_group(bar);                                  // panel jb is in shared memory; warps 1-3 have finished update(jb-1)
-    if (warp == 0) {
-      if (jb < 3) {
-        // look-ahead: panel jb -> the next panel's columns, my row, into registers
-        double x[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) x[q] = a[lane][j0 + q];
-#pragma unroll
-        for (int c2 = 0; c2 < 8; ++c2) {
-          double v = a[lane][j0 + 8 + c2];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v -= x[q] * a[j0 + 8 + c2][j0 + q];
-          r[c2] = v;
+        for (int c2 = c + 1; c2 < 8; ++c2) {
+          const double lcj = __shfl_sync(0xffffffffu, lij, j0 + c2);
+          if (lane >= j0 + c2) r[c2] -= lij * lcj;
         }
       }
-    } else {
-      // panel jb -> columns >= j0 + 16 (lower part), 96 threads
-      const int n0 = j0 + 16, m = TB - n0;
-      for (int e = tid - 32; e < m * m; e += kGroup - 32) {
-        const int rr = n0 + e / m, cc = n0 + e % m;
-        if (rr >= cc) {
-          double sacc = 0.0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) sacc += a[rr][j0 + q] * a[cc][j0 + q];
-          a[rr][cc] -= sacc;
-        }
+      for (int c = 0; c < 8; ++c) a[lane][j0 + c] = (lane >= j0 + c) ? r[c] : 0.0;
+    }
+    bar_group(bar);
+    const int n0 = j0 + 8, m = TB - n0;
+    for (int e = tid; e < m * m; e += kGroup) {
+      const int rr = n0 + e / m, cc = n0 + e % m;
+      if (rr >= cc) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sacc += a[rr][j0 + q] * a[cc][j0 + q];
+        a[rr][cc] -= sacc;
       }
     }
+    bar_group(bar);
   }
-  bar_group(bar);
   return ok;
 }
 

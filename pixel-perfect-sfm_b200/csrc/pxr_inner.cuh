@@ -369,7 +369,7 @@ static __global__ void __launch_bounds__(128) inner_list_kernel(InnerStepArgs a,
 }
 
 // ||a - b|| over two parameter sets (ambient), for step_norm after inner iterations
-static __global__ void __launch_bounds__(256) diff_norm_kernel(const double* a, const double* b, int64_t n, double* acc) {
+static __global__ void __launch_bounds__(256) diff_norm_kernel(const double* a, const double* b, int64_t n, double* acc, double* part = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0.0;
   if (i < n) { const double d = a[i] - b[i]; v = d * d; }
@@ -377,7 +377,11 @@ static __global__ void __launch_bounds__(256) diff_norm_kernel(const double* a, 
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x == 0) { double s = 0; for (int k = 0; k < 8; ++k) s += sh[k]; atomicAdd(acc, s); }
+  if (threadIdx.x == 0) {
+    double s = 0; for (int k = 0; k < 8; ++k) s += sh[k];
+    if (part) part[blockIdx.x] = s;          // deterministic mode (det_reduce_add_kernel)
+    else atomicAdd(acc, s);
+  }
 }
 
 // multi-GPU: S += lower(Hcc) + diag(D2c), rhs += -gc after the allreduce of the Schur parts

@@ -34,7 +34,8 @@ struct SparseSchur {
 
 // Schur pair chunks -> image-pair blocks (the fast path of ba_schur_pairs_kernel with a different sink)
 static __global__ void __launch_bounds__(kPairThreads) sp_schur_pairs_kernel(BADev d, SchurPairs sp, const int32_t* __restrict__ chunk_key,
-                                                                    const double* __restrict__ T, double* __restrict__ Bk, double* rhs) {
+                                                                    const double* __restrict__ T, double* __restrict__ Bk, double* rhs,
+                                                                    double* __restrict__ part = nullptr /* deterministic mode: [n_chunks][72] */) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= sp.n_chunks) return;
@@ -47,6 +48,15 @@ static __global__ void __launch_bounds__(kPairThreads) sp_schur_pairs_kernel(BAD
   double acc[8], racc;
   const bool self = sp.chunk_self[c] != 0;
   schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, acc, racc);
+  if (part) {        // fixed-order reduction per key afterwards (det_pair_reduce_kernel): no atomics
+    if (g == 0) {
+      double* dst = part + c * 72;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) dst[a * 8 + b] = (a < dcx && b < dcy) ? acc[b] : 0.0;
+      dst[64 + a] = (self && a < dcx) ? racc : 0.0;
+    }
+    return;
+  }
   if (self && g == 0 && a < dcx) atomic_add_f64(&rhs[d.Wcols[ox0 * d.dcmax + a]], racc);
   if (g == 0 && a < dcx) {
     double* dst = Bk + ((int64_t)chunk_key[c] * 8 + a) * 8;

@@ -44,7 +44,7 @@ def launches(src, dst, command):
     total = sum(a[1] for a in agg.values())
     with open(dst, "w") as f:
         f.write("# ncu launch list — `%s`\n" % command)
-        f.write("# round 1, B200. Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
+        f.write("# B200 (sm_100a). Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
         f.write("# %d launches captured, %.3f ms total (includes one-off setup kernels: synthetic patch generator, reference extraction)\n" % (len(rows), total))
         f.write("kernel,launches,total_ms,avg_ms,share_pct\n")
         for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):

@@ -1,7 +1,7 @@
 """Window residency of the patch slab (csrc/pxr_resident.cuh): pxr_ba_run brings over a W x W tap window per observation
 (packed on the host, pinned or pageable source), fetches whole patches for observations that leave it, and must give
-the results of the same solve on fully uploaded patches: the same taps go through the same arithmetic, what is left is
-the run-to-run noise of the fp64 atomics in the normal equations (1e-16 relative per sum)."""
+the results of the same solve on fully uploaded patches: the same taps go through the same arithmetic.  In deterministic
+mode (fixed-order sums) that means bit for bit; with the default atomics what is left is their run-to-run noise."""
 import os
 
 import numpy as np
@@ -48,30 +48,34 @@ def _run(prob, ic, so, window):
     return out
 
 
-def _identical(a, b, tol=1e-11):
+def _identical(a, b, exact):
+    """exact: the solves ran in deterministic mode (fixed-order sums) -> every bit must agree; otherwise the fp64 atomics
+    of the assembly leave run-to-run noise that the LM iterations amplify (a few 1e-11 on the final cost at most)"""
     sa, sb = a[0], b[0]
     assert len(sa["iterations"]) == len(sb["iterations"])
     assert sa["iterations"][0]["cost"] == sb["iterations"][0]["cost"]          # the first evaluation has no atomics in it: bit-equal
+    tol = 0.0 if exact else 1e-9
     for x, y in zip(sa["iterations"], sb["iterations"]):
         assert x["step_is_successful"] == y["step_is_successful"] and x["step_is_valid"] == y["step_is_valid"]
         for key in ("cost", "cost_change", "step_norm", "relative_decrease", "trust_region_radius"):
-            assert abs(x[key] - y[key]) <= tol * max(abs(y[key]), 1e-300) + 1e-14, key
+            assert abs(x[key] - y[key]) <= tol * abs(y[key]) + (0.0 if exact else 1e-13), key
     assert abs(sa["final_cost"] - sb["final_cost"]) <= tol * sb["final_cost"]
     assert sa["num_inner_iteration_steps"] == sb["num_inner_iteration_steps"]
     for u, v in zip(a[1:], b[1:]):
-        assert np.abs(u - v).max() <= 1e-10
+        assert np.array_equal(u, v) if exact else np.abs(u - v).max() <= 1e-8
 
 
+@pytest.mark.parametrize("deterministic", [1, 0])
 @pytest.mark.parametrize("inner", [0, 1])
 @pytest.mark.parametrize("window", [8, 4])
-def test_windowed_solve_is_bit_identical_to_the_fully_resident_one(inner, window):
+def test_windowed_solve_is_bit_identical_to_the_fully_resident_one(inner, window, deterministic):
     # a rough start (5x the usual perturbation) so that points do leave small windows
     prob, ic = _scene(rot_sigma_deg=0.06, pt_sigma=0.012)
-    so = _capi.default_ba_options(max_num_iterations=12, use_inner_iterations=inner)
+    so = _capi.default_ba_options(max_num_iterations=12, use_inner_iterations=inner, deterministic=deterministic)
     full = _run(prob, ic, so, 0)
     win = _run(prob, ic, so, window)
     assert full[0]["resident_window"] == 0 and win[0]["resident_window"] == window
-    _identical(win, full)
+    _identical(win, full, exact=bool(deterministic))
     pbytes = prob.patches.nbytes
     assert full[0]["h2d_bytes"] >= pbytes
     # every observation got its window, violators their whole patch: far fewer bytes than the slab unless W = 4 met a
@@ -106,8 +110,8 @@ def test_shared_patches_and_pageable_sources_fall_back_to_what_is_safe():
         s0 = _engine.ba_run(p0, ic, so)
     finally:
         os.environ.pop("PXR_RESIDENT_WINDOW", None)
-    assert s0["resident_window"] == 0 and abs(s1["final_cost"] - s0["final_cost"]) <= 1e-11 * s0["final_cost"]
-    assert np.abs(p1.xyz - p0.xyz).max() < 1e-10
+    assert s0["resident_window"] == 0 and abs(s1["final_cost"] - s0["final_cost"]) <= 1e-9 * s0["final_cost"]
+    assert np.abs(p1.xyz - p0.xyz).max() < 1e-8
     # two observations reading ONE patch (a dense map does that): such patches come over whole, the rest as windows
     q, pin = _pinned_copy(prob)
     n = q.n_obs
@@ -123,5 +127,5 @@ def test_shared_patches_and_pageable_sources_fall_back_to_what_is_safe():
         os.environ.pop("PXR_RESIDENT_WINDOW", None)
     s_win = _engine.ba_run(q2, ic, so)
     assert s_win["resident_window"] == 8 and s_full["resident_window"] == 0
-    assert abs(s_win["final_cost"] - s_full["final_cost"]) <= 1e-11 * s_full["final_cost"] and np.abs(q.xyz - q2.xyz).max() < 1e-10
+    assert abs(s_win["final_cost"] - s_full["final_cost"]) <= 1e-9 * s_full["final_cost"] and np.abs(q.xyz - q2.xyz).max() < 1e-8
     pin.close()
