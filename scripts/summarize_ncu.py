@@ -22,7 +22,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def short(name):
     name = re.sub(r"\(.*\)$", "", name)
-    name = name.replace("pxr::", "").replace("pxr_chol::", "")
+    name = name.replace("pxr::", "").replace("pxr_chol2::", "").replace("pxr_chol::", "")
     return name.strip()
 
 
@@ -53,7 +53,11 @@ def launches(src, dst, command):
 
 
 def report(src, dst, title):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    # src: a .ncu-rep, or the raw-page CSV made from one on the GPU box (`ncu -i x.ncu-rep --page raw --csv`)
+    if src.endswith(".csv"):
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rd = list(csv.reader(io.StringIO(out)))
     header, units = rd[0], rd[1]
     with open(dst, "w") as f:
