@@ -548,7 +548,7 @@ int BA::resident_begin(cudaStream_t us, double* h2d_patch) {
 
 void BA::resident_args(FmEvalArgs& a) {
   if (!resident) return;
-  a.res_rect = res_rect.p; a.viol_count = res_viol_count.p; a.viol_list = res_viol_list.p;
+  a.res_rect = res_rect.p; a.viol_count = res_viol_count.p; a.viol_list = res_viol_list.p; a.viol_capacity = (long long)n_obs;
 }
 
 // Called after an evaluation pass: did any observation read outside its resident rectangle?  Then fetch those
@@ -561,6 +561,7 @@ int BA::resident_fix(int64_t* n_fixed) {
   PXR_CUDA(cudaMemcpyAsync(&n, res_viol_count.p, sizeof(n), cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaStreamSynchronize(s));
   if (n == 0) return PXR_OK;
+  n = std::min<unsigned long long>(n, (unsigned long long)n_obs);      // entries beyond the capacity were dropped (reported again later)
   std::vector<int64_t> list((size_t)n);
   PXR_CUDA(cudaMemcpyAsync(list.data(), res_viol_list.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
   PXR_CUDA(cudaMemcpyAsync(res_fix_list.p, res_viol_list.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
@@ -899,39 +900,76 @@ int BA::apply_step(double* step_norm, double* x_norm) {
   return PXR_OK;
 }
 
-// K0 (with Jacobians) + K1 (Jacobian mode) over an explicit list of observations
-int BA::eval_list(int set, const int64_t* list, int64_t n) {
+// K0 (with Jacobians) + K1 (Jacobian mode) over an explicit list of observations.  With n_dev the number of entries is
+// read on the device (n is then the upper bound the grids are sized for); settle = false leaves the window-residency
+// check to the caller (inner_rounds checks once per batch of rounds).
+int BA::eval_list(int set, const int64_t* list, int64_t n, const unsigned long long* n_dev, bool settle) {
   if (n <= 0) return PXR_OK;
   ProjectArgs pa;
   pa.obs_img = obs_img.p; pa.obs_pt = obs_pt.p; pa.obs_patch = obs_patch.p;
   pa.img_cam = img_cam.p; pa.cam_model = cam_model.p;
   pa.cam_params = cam[set].p; pa.qvec = q[set].p; pa.tvec = t[set].p; pa.xyz = X[set].p;
   pa.corner = corner.p; pa.scale = scale.p; pa.ups = ups;
-  pa.obs_begin = 0; pa.obs_end = n; pa.item_index = list;
+  pa.obs_begin = 0; pa.obs_end = n; pa.item_index = list; pa.n_dev = n_dev;
   pa.uv = uv.p; pa.xy = nullptr; pa.juv = juv.p; pa.juv_stride = juv_stride; pa.juv_k = K;
   PXR_LAUNCH(ctx, ba_project_kernel<true>, (unsigned)cdiv(n, 128), 128, 0, pa);
   FmEvalArgs a;
   a.uv = uv.p; a.item_patch = obs_patch.p; a.item_ref = obs_pt.p;
   a.patches = d_patches; a.ph = ph; a.pw = pw;
   a.refs = has_refs ? refs.p : nullptr;
-  a.begin = 0; a.end = n; a.item_index = list;
+  a.begin = 0; a.end = n; a.item_index = list; a.end_dev = n_dev;
   a.out = obs_out.p; a.residuals = nullptr; a.desc = nullptr;
   a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
   a.l2_normalize = interp.l2_normalize;
   resident_args(a);
   int np = 0;
   PXR_TRY(launch_fm_eval(ctx, dtype, C, 1, interp.use_float_simd != 0, a, &np));
-  for (;;) {     // window residency: the inner-iteration step consumes these results right away, so settle them first
+  if (!settle) return PXR_OK;
+  for (;;) {     // window residency: whoever consumes these results right away needs them settled first
     int64_t n_fixed = 0;
     PXR_TRY(resident_fix(&n_fixed));
     if (n_fixed == 0) break;
-    a.item_index = res_fix_list.p; a.begin = 0; a.end = n_fixed;
+    a.item_index = res_fix_list.p; a.begin = 0; a.end = n_fixed; a.end_dev = nullptr;
     PXR_TRY(launch_fm_eval(ctx, dtype, C, 1, interp.use_float_simd != 0, a, &np));
   }
   return PXR_OK;
 }
 
 // Inner iterations, batched: see pxr_inner.cuh.  Same state machine as ba_inner_kernel.
+// The rounds are enqueued WITHOUT waiting for the host: the list length of a round stays on the device (K0 / K1 read it
+// there, their grids are sized for all observations), its copy travels to a pinned slot behind an event, and the host
+// stops enqueuing once a round two behind has reported an empty list (the two extra rounds find nothing to do).
+constexpr int kInnerRounds = 53;
+int BA::inner_rounds(int set) {
+  cudaStream_t s = ctx->stream;
+  InnerStepArgs a;
+  a.n_points = n_points; a.point_off = point_off.p; a.pt_begin = pt_begin.p;
+  a.obs_out = obs_out.p; a.juv = juv.p; a.juv_stride = juv_stride; a.juv_w = 9 + K;
+  a.xyz = X[set].p; a.st = inner_state.p;
+  a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
+  a.list = inner_list.p; a.counters = inner_counters.p;
+  const unsigned pgrid = (unsigned)cdiv(n_points, 128);
+  for (int round = 0; round < kInnerRounds; ++round) {
+    if (round >= 2) {
+      const cudaError_t q = cudaEventQuery(inner_events[round - 2]);
+      if (q == cudaSuccess) { if (inner_cnt_host[2 * (round - 2)] == 0) break; }
+      else if (q != cudaErrorNotReady) PXR_CUDA(q);
+      else if ((void)cudaGetLastError(), round >= 8 && (round & 3) == 0) {        // far ahead of the device: let it catch up rather than pile up empty rounds
+        PXR_CUDA(cudaEventSynchronize(inner_events[round - 2]));
+        if (inner_cnt_host[2 * (round - 2)] == 0) break;
+      }
+    }
+    PXR_CUDA(cudaMemsetAsync(inner_counters.p, 0, 2 * sizeof(unsigned long long), s));
+    PXR_LAUNCH(ctx, inner_list_kernel, pgrid, 128, 0, a, round == 0 ? 1 : 0);
+    PXR_CUDA(cudaMemcpyAsync(inner_cnt_host + 2 * round, inner_counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    PXR_CUDA(cudaEventRecord(inner_events[round], s));
+    PXR_TRY(eval_list(set, inner_list.p, n_obs, inner_counters.p, false));
+    PXR_LAUNCH(ctx, inner_step_kernel, pgrid, 128, 0, a, round == 0 ? 0 : 1);
+  }
+  PXR_CUDA(cudaGetLastError());
+  return PXR_OK;
+}
+
 int BA::inner_iterations_batched(int set) {
   if (n_points == 0 || n_obs == 0) return PXR_OK;
   StageScope stg(this, 9);
@@ -940,25 +978,22 @@ int BA::inner_iterations_batched(int set) {
     PXR_TRY(inner_state.alloc(n_points));
     PXR_TRY(inner_list.alloc(n_obs));
     PXR_TRY(inner_counters.alloc(2));
+    PXR_CUDA(cudaHostAlloc((void**)&inner_cnt_host, (size_t)kInnerRounds * 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    inner_events.resize(kInnerRounds, nullptr);
+    for (auto& e : inner_events) PXR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  InnerStepArgs a;
-  a.n_points = n_points; a.point_off = point_off.p; a.pt_begin = pt_begin.p;
-  a.obs_out = obs_out.p; a.juv = juv.p; a.juv_stride = juv_stride; a.juv_w = 9 + K;
-  a.xyz = X[set].p; a.st = inner_state.p;
-  a.loss.type = opt.loss_type; a.loss.a = opt.loss_scale;
-  a.list = inner_list.p; a.counters = inner_counters.p;
-  const unsigned pgrid = (unsigned)cdiv(n_points, 128);
-  unsigned long long cnt[2] = {0, 0};
-  for (int round = 0; round <= 52; ++round) {
-    PXR_CUDA(cudaMemsetAsync(inner_counters.p, 0, 2 * sizeof(unsigned long long), s));
-    PXR_LAUNCH(ctx, inner_list_kernel, pgrid, 128, 0, a, round == 0 ? 1 : 0);
-    PXR_CUDA(cudaMemcpyAsync(cnt, inner_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
-    PXR_CUDA(cudaStreamSynchronize(s));
-    if (cnt[0] == 0) break;
-    PXR_TRY(eval_list(set, inner_list.p, (int64_t)cnt[0]));
-    PXR_LAUNCH(ctx, inner_step_kernel, pgrid, 128, 0, a, round == 0 ? 0 : 1);
+  if (!resident) return inner_rounds(set);
+  // window residency: an observation may leave its window in any round and nobody looks before the rounds are over — keep
+  // the starting points, and if something was reported fetch those patches and run the rounds again from the start
+  if (!inner_snapshot.p) PXR_TRY(inner_snapshot.alloc((size_t)n_points * 3));
+  PXR_CUDA(cudaMemcpyAsync(inner_snapshot.p, X[set].p, (size_t)n_points * 24, cudaMemcpyDeviceToDevice, s));
+  for (;;) {
+    PXR_TRY(inner_rounds(set));
+    int64_t n_fixed = 0;
+    PXR_TRY(resident_fix(&n_fixed));
+    if (n_fixed == 0) break;
+    PXR_CUDA(cudaMemcpyAsync(X[set].p, inner_snapshot.p, (size_t)n_points * 24, cudaMemcpyDeviceToDevice, s));
   }
-  PXR_CUDA(cudaGetLastError());
   return PXR_OK;
 }
 

@@ -171,7 +171,7 @@ struct BA {
   DevBuf<int64_t> io_chunk_begin; int64_t io_n_chunks = 0;
   DevBuf<long long> chol_trace;     // PXR_CHOL_TRACE=<file>: panel-CTA time stamps
   DevBuf<int> chol_sync;            // flags of the persistent tile-DAG Cholesky (pxr_chol.cuh)
-  ~BA() { if (res_thread.joinable()) res_thread.join(); if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
+  ~BA() { if (inner_cnt_host) cudaFreeHost(inner_cnt_host); for (auto e : inner_events) cudaEventDestroy(e); if (res_thread.joinable()) res_thread.join(); if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
   // static co-visibility structure for the Schur complement (see ba_schur_pairs_kernel)
   DevBuf<int32_t> sp_px, sp_py;
   DevBuf<int64_t> sp_chunk_begin;
@@ -218,7 +218,11 @@ struct BA {
   int gradient_max_norm(double* out);
   int inner_iterations(int set);
   int inner_iterations_batched(int set);
-  int eval_list(int set, const int64_t* list, int64_t n);
+  int eval_list(int set, const int64_t* list, int64_t n, const unsigned long long* n_dev = nullptr, bool settle = true);
+  int inner_rounds(int set);                       // the <= 52 rounds of inner_iterations_batched, without a host wait per round
+  unsigned long long* inner_cnt_host = nullptr;    // pinned [kInnerRounds][2]: the rounds' list counts, read back asynchronously
+  std::vector<cudaEvent_t> inner_events;
+  DevBuf<double> inner_snapshot;                   // window residency: the points before a batch of rounds (redo after a refetch)
   DevBuf<InnerState> inner_state;
   DevBuf<int64_t> inner_list;
   DevBuf<unsigned long long> inner_counters;

@@ -28,6 +28,8 @@ struct ProjectArgs {
   const int32_t* corner; const double* scale; double ups;
   int64_t obs_begin, obs_end;
   const int64_t* item_index;  // optional: process observations item_index[obs_begin..obs_end) (inner iterations)
+  const unsigned long long* n_dev = nullptr;   // optional: the item count lives on the device (obs_end = obs_begin + *n_dev; the
+                                               // grid is sized for an upper bound) — no host round trip between list and launch
   double* uv;    // [n_obs][2] (u = col, v = row), patch pixel units
   double* xy;    // optional [n_obs][2]
   double* juv;   // optional [n_obs][juv_stride]: 2 x (6 pose | 3 point | K intr), row-major
@@ -74,7 +76,8 @@ __device__ __forceinline__ void project_observation(const ProjectArgs& a, int64_
 template <bool JAC>
 __global__ void __launch_bounds__(128) ba_project_kernel(ProjectArgs a) {
   const int64_t k = a.obs_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.obs_end) return;
+  const int64_t end = a.n_dev ? a.obs_begin + (int64_t)*a.n_dev : a.obs_end;
+  if (k >= end) return;
   const int64_t o = a.item_index ? a.item_index[k] : k;
   project_observation<JAC>(a, o, (JAC && a.juv) ? a.juv + o * (int64_t)a.juv_stride : nullptr);
 }
@@ -118,7 +121,10 @@ struct FmEvalArgs {
   // host re-runs the pass after fetching the patch)
   const uint32_t* res_rect = nullptr;        // [n_patches] r0 | c0 << 8 | rows << 16 | cols << 24
   unsigned long long* viol_count = nullptr;  // [1]
-  int64_t* viol_list = nullptr;              // [capacity >= n items]
+  int64_t* viol_list = nullptr;              // [viol_capacity]
+  long long viol_capacity = 0;               // entries beyond it are dropped (they are reported again by the repeated pass)
+  const unsigned long long* end_dev = nullptr;   // optional: item count on the device (end = begin + *end_dev; `end` is then the
+                                                 // upper bound the grid was sized for)
   LossParams loss;
   int l2_normalize;
 };
@@ -376,7 +382,8 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
   }
   __syncwarp();
   const bool active = lane < ACTIVE;
-  const int64_t n_items = a.end - a.begin;
+  const int64_t item_end = a.end_dev ? a.begin + (int64_t)*a.end_dev : a.end;
+  const int64_t n_items = item_end - a.begin;
   const int64_t n_batches = (n_items + 31) / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * kFmWarps + warp;
   const int64_t warps_total = (int64_t)gridDim.x * kFmWarps;
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
   const bool has_ref = a.refs != nullptr;
 
   for (int64_t batch = warp_global; batch < n_batches; batch += warps_total) {
-    const int nvalid = (int)min((int64_t)32, a.end - (a.begin + batch * 32));
+    const int nvalid = (int)min((int64_t)32, item_end - (a.begin + batch * 32));
     int64_t o = a.begin + batch * 32 + lane;
     if (a.item_index && lane < nvalid) o = a.item_index[o];
     // ---- phase 1: per-lane window geometry, published to the warp through shared memory
@@ -409,8 +416,10 @@ __global__ void __launch_bounds__(FmCfg<T, C>::kWarps * 32, 1) fm_eval_kernel(Fm
       x.src = a.patches + pidx * patch_bytes;
       aux[lane] = x;
       ref_idx = ridx;
-      if (a.res_rect && lane < nvalid && !window_resident(a.res_rect[pidx], x.row, x.col, a.ph, a.pw))
-        a.viol_list[atomicAdd(a.viol_count, 1ull)] = o;
+      if (a.res_rect && lane < nvalid && !window_resident(a.res_rect[pidx], x.row, x.col, a.ph, a.pw)) {
+        const unsigned long long slot = atomicAdd(a.viol_count, 1ull);
+        if ((long long)slot < a.viol_capacity) a.viol_list[slot] = o;
+      }
     }
     __syncwarp();
 

@@ -24,7 +24,7 @@ template <typename T, int C, int MODE>
 static __global__ void __launch_bounds__(128) fm_eval_small_kernel(FmEvalArgs a) {
   constexpr bool DERIV = MODE == 1;
   const int64_t k = a.begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.end) return;
+  if (k >= (a.end_dev ? a.begin + (int64_t)*a.end_dev : a.end)) return;
   const int64_t o = a.item_index ? a.item_index[k] : k;
   const double u = a.uv[2 * o], v = a.uv[2 * o + 1];
   const int64_t pidx = a.item_patch ? a.item_patch[o] : o;
