@@ -568,16 +568,22 @@ int BA::resident_fix(int64_t* n_fixed) {
   PXR_CUDA(cudaMemsetAsync(res_viol_count.p, 0, sizeof(unsigned long long), s));
   PXR_CUDA(cudaStreamSynchronize(s));
   const size_t patch_bytes = (size_t)ph * pw * C * res_esz;
+  // an observation is reported by every pass that evaluates it before its patch is whole (several inner-iteration rounds
+  // run between two looks at the list): fetch each patch once
+  if (res_whole.size() != (size_t)n_patches) res_whole.assign((size_t)n_patches, 0);
+  int64_t fetched = 0;
   for (int64_t o : list) {
     const int64_t p = h_obs_patch.empty() ? o : h_obs_patch[(size_t)o];
+    if (res_whole[(size_t)p]) continue;
+    res_whole[(size_t)p] = 1; ++fetched;
     const size_t blk = (size_t)(std::upper_bound(res_block_first.begin(), res_block_first.end(), p) - res_block_first.begin()) - 1;
     const uint8_t* src = (const uint8_t*)res_srcs[blk] + (size_t)(p - res_block_first[blk]) * patch_bytes;
     PXR_CUDA(cudaMemcpyAsync(patches_owned.p + (size_t)p * patch_bytes, src, patch_bytes, cudaMemcpyHostToDevice, s));
   }
   PXR_LAUNCH(ctx, resident_mark_full_kernel, (unsigned)cdiv((int64_t)n, 256), 256, 0, res_fix_list.p, (int64_t)n, obs_patch.p, ph, pw, res_rect.p);
   PXR_CUDA(cudaGetLastError());
-  res_refetched += (int64_t)n; res_passes_repeated++;
-  h2d_bytes += (double)n * (double)patch_bytes;
+  res_refetched += fetched; res_passes_repeated++;
+  h2d_bytes += (double)fetched * (double)patch_bytes;
   *n_fixed = (int64_t)n;
   return PXR_OK;
 }

@@ -197,6 +197,7 @@ struct BA {
   std::vector<const void*> res_srcs;               // host blocks of whole patches (one entry for a contiguous source)
   std::vector<int64_t> res_block_first;            // [n_blocks+1]
   std::vector<int64_t> h_obs_patch;                // host copy (which patch an observation reads), empty = identity
+  std::vector<uint8_t> res_whole;                  // patches already fetched whole
   int64_t res_refetched = 0, res_passes_repeated = 0;
   size_t res_esz = 2;
   std::thread res_thread;                          // packs and uploads the windows while create() goes on

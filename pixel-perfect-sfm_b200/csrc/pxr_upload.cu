@@ -319,6 +319,17 @@ int upload_windows(pxr_ctx* ctx, uint8_t* slab, const void* const* srcs, const i
         const uint32_t rc = h_rect[p];
         const int r0 = (int)(rc & 255u), c0 = (int)((rc >> 8) & 255u), rows = (int)((rc >> 16) & 255u), cols = (int)(rc >> 24);
         const size_t row_bytes = (size_t)cols * tap_bytes;
+        if (p + 1 < p1 && (n_blocks <= 1 || p + 1 < block_first[blk + 1])) {
+          // the next patch's rows: 2 KiB pieces 4 KiB apart defeat the hardware prefetcher, ask for them a patch ahead
+          const uint32_t rn = h_rect[p + 1];
+          const int nr0 = (int)(rn & 255u), nc0 = (int)((rn >> 8) & 255u), nrows = (int)((rn >> 16) & 255u), ncols = (int)(rn >> 24);
+          const uint8_t* nsrc = src + patch_bytes;
+          const size_t nrb = (size_t)ncols * tap_bytes;
+          for (int r = 0; r < nrows; ++r) {
+            const uint8_t* q = nsrc + ((size_t)(nr0 + r) * pw + nc0) * tap_bytes;
+            for (size_t b = 0; b < nrb; b += 64) __builtin_prefetch(q + b, 0, 0);
+          }
+        }
         if (cols == pw) { std::memcpy(out, src + (size_t)r0 * pw * tap_bytes, row_bytes * rows); out += row_bytes * rows; }
         else for (int r = 0; r < rows; ++r) { std::memcpy(out, src + ((size_t)(r0 + r) * pw + c0) * tap_bytes, row_bytes); out += row_bytes; }
       }

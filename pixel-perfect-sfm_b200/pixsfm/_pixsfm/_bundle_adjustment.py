@@ -243,8 +243,11 @@ def build_problem(reconstruction, feature_view, setup, options, references=None,
         # which track elements have a feature patch: resolved per image
         timg, tp2d = A["track_image_id"], A["track_point2D_idx"]
         has = np.zeros(len(timg), np.uint8)
-        for image_id in np.unique(timg):
-            sel = np.flatnonzero(timg == image_id)
+        order_t = np.argsort(timg, kind="stable")              # track elements grouped by image: one sort instead of a scan per image
+        uniq_t, first_t = np.unique(timg[order_t], return_index=True)
+        bounds_t = np.append(first_t, len(order_t))
+        for k_img, image_id in enumerate(uniq_t):
+            sel = order_t[bounds_t[k_img]:bounds_t[k_img + 1]]
             name = feature_view._id_to_name.get(int(image_id))
             if name is None or not feature_view.fset.has_fmap(name):
                 continue
@@ -310,9 +313,15 @@ def build_problem(reconstruction, feature_view, setup, options, references=None,
     refs = None
     if references is not None:
         C_ = feature_view.channels
-        refs = np.zeros((n_pts, C_))
-        for k, pid in enumerate(ir.point_ids):
-            refs[k] = np.asarray(references[pid].descriptor, np.float64).reshape(-1)[:C_]
+        dense = getattr(references, "dense", None)
+        if dense is not None and dense[1].shape[1] == C_ and bool(dense[2].all()) and np.array_equal(dense[0], point_ids):
+            refs = np.ascontiguousarray(dense[1], np.float64)
+        elif dense is not None and dense[1].shape[1] == C_ and bool(dense[2].all()) and np.all(np.isin(point_ids, dense[0])):
+            refs = np.ascontiguousarray(dense[1][np.searchsorted(dense[0], point_ids)], np.float64)
+        else:
+            refs = np.zeros((n_pts, C_))
+            for k, pid in enumerate(ir.point_ids):
+                refs[k] = np.asarray(references[pid].descriptor, np.float64).reshape(-1)[:C_]
     prob = _capi.BAProblem(cam_model=cam_model, cam_params=cam_params, cam_const_mask=cam_mask, qvec=qvec, tvec=tvec,
                            img_cam=img_cam, pose_const=pose_const, tvec_const_mask=tmask, xyz=xyz, point_const=point_const,
                            obs_img=obs_img, obs_pt=obs_pt, patches=None, corner=corners, scale=scales, refs=refs,
@@ -496,6 +505,18 @@ def write_back(reconstruction, prob, ir):
         reconstruction.points3D[p].xyz[:] = prob.xyz[k]
 
 
+class ReferenceMap(dict):
+    """Map_IdReference (features/bindings.cc): point3D id -> Reference.  `dense` remembers that the descriptors are rows of one
+    [n_points, C] array (as the extractor produces them), so an optimizer that is handed the unmodified map copies one block
+    instead of walking 50 000 Python objects."""
+    dense = None
+
+    def __setitem__(self, key, value):
+        if self.dense is not None and key in self and value is not self[key]:
+            self.dense = None              # edited by the caller: fall back to the per-entry walk
+        super().__setitem__(key, value)
+
+
 class ReferenceExtractor:
     """_bundle_adjustment.ReferenceExtractor(ReferenceConfig|dict, InterpolationConfig|dict).run(problem_labels,
     reconstruction, feature_set) -> {point3D_id: Reference}"""
@@ -515,7 +536,7 @@ class ReferenceExtractor:
             ids = {p for p in reconstruction.points3D.keys() if p < len(problem_labels) and problem_labels[p] >= 0}
         fview = FeatureView(feature_set, reconstruction)
         prob, ir = build_problem(reconstruction, fview, None, None, None, for_references=ids)
-        refs = {p: Reference() for p in ids}   # InitReferences
+        refs = ReferenceMap((p, Reference()) for p in ids)   # InitReferences
         if prob.n_obs == 0:
             return refs
         loss = self.config.loss
@@ -524,11 +545,12 @@ class ReferenceExtractor:
         ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
         desc, src = _engine.refs_compute(prob, ic, _capi.LOSS_IDS[str(loss.get("name", "cauchy")).lower()],
                                          float(loss.get("params", [1.0])[0]), int(self.config.iters))
+        src_img = ir.obs_image_id[np.maximum(src, 0)].tolist(); src_p2d = ir.obs_point2D_idx[np.maximum(src, 0)].tolist()
+        valid = (src >= 0).tolist()
         for k, pid in enumerate(ir.point_ids):
-            if src[k] < 0:
-                continue
-            image_id, p2D_idx, _ = ir.obs[int(src[k])]
-            refs[pid] = Reference((image_id, p2D_idx), desc[k].reshape(1, -1).copy())
+            if valid[k]:
+                refs[pid] = Reference((src_img[k], src_p2d[k]), desc[k:k + 1])      # [1, C] view of the extractor's output
+        refs.dense = (np.asarray(ir.point_ids, np.int64), desc, np.asarray(valid))  # the optimizer takes the block as a whole
         if self.config.keep_observations:
             # refdata.observations / costs (reference_extractor.h:258-264): every observation's descriptor, in the
             # order of the problem IR (track order), and its squared distance to the chosen reference's robust mean
