@@ -91,7 +91,8 @@ _SOLVER_KEYS = {"function_tolerance", "gradient_tolerance", "parameter_tolerance
                 "max_consecutive_nonmonotonic_steps", "use_inner_iterations", "use_nonmonotonic_steps",
                 "update_state_every_iteration", "num_threads", "callbacks", "inner_iteration_tolerance",
                 "initial_trust_region_radius", "max_trust_region_radius", "min_trust_region_radius",
-                "min_relative_decrease", "min_lm_diagonal", "max_lm_diagonal", "jacobi_scaling", "logging_type"}
+                "min_relative_decrease", "min_lm_diagonal", "max_lm_diagonal", "jacobi_scaling", "logging_type",
+                "deterministic"}       # the last one is this library's own: fixed-order (bit-reproducible) assembly
 
 
 def solver_options_from(loss, solver, base):
