@@ -615,16 +615,51 @@ class FeatureReferenceBundleOptimizer:
         need = _engine.ba_estimate_device_bytes(prob, so)     # the reference logs its RAM estimate here (:200-208)
         logger.info("Estimated device memory: %.3f GB (patches %.3f, problem state %.3f, reduced system %.3f).",
                     need["total"] / 1e9, need["patches"] / 1e9, need["state"] / 1e9, need["reduced_system"] / 1e9)
-        s = _engine.ba_run(prob, ic, so)
-        for cb in (self.options.solver.get("callbacks") or []):   # ceres IterationCallback-like objects, once per
-            for it in s["iterations"]:                            # recorded iteration
-                cb(it)
+        callbacks = list(self.options.solver.get("callbacks") or [])
+        if not callbacks:
+            s = _engine.ba_run(prob, ic, so)
+        else:
+            s = self._solve_with_callbacks(prob, ic, so, callbacks)
         write_back(self._reconstruction, prob, self._ir)
         self._summary = _Summary(s, num_residuals_reduced=s["num_residuals"], total_time_in_seconds=s["total_time_s"])
         nres = max(1, s["num_residuals"])
         logger.info("BA Time: %.4gs, cost change: %.6g --> %.6g", s["total_time_s"],
                     np.sqrt(s["initial_cost"] / nres), np.sqrt(s["final_cost"] / nres))
         return True
+
+    @staticmethod
+    def _solve_with_callbacks(prob, ic, so, callbacks):
+        """ceres::IterationCallback semantics (the reference injects its callbacks through `solver.callbacks`,
+        util/misc.py:30-36): every callback sees each iteration record right after the iteration, starting with
+        iteration 0, and may stop the solve by returning 1 / "SOLVER_ABORT" (-> USER_FAILURE) or 2 /
+        "SOLVER_TERMINATE_SUCCESSFULLY" (-> USER_SUCCESS); None / 0 / "SOLVER_CONTINUE" go on.  The problem stays
+        resident on the device between the iterations (pxr_ba_create + pxr_ba_iterate, one LM iteration per call)."""
+        import time
+        t0 = time.time()
+        limit = int(so.max_num_iterations)
+        h = _engine.BAHandle(prob, ic, so)
+        try:
+            seen, verdict = 0, 0
+            s = h.iterate(0)                              # iteration 0: the evaluation at the start point
+            while True:
+                for it in s["iterations"][seen:]:
+                    for cb in callbacks:
+                        r = cb(it)
+                        r = {"SOLVER_CONTINUE": 0, "SOLVER_ABORT": 1, "SOLVER_TERMINATE_SUCCESSFULLY": 2}.get(getattr(r, "name", r), r)
+                        verdict = max(verdict, int(r or 0))
+                grew = len(s["iterations"]) > seen
+                seen = len(s["iterations"])
+                if verdict or not grew or seen - 1 >= limit or s["termination_type"] != 1:
+                    break
+                s = h.iterate(1)
+            h.read_params()
+        finally:
+            h.close()
+        if verdict:
+            s["termination_type"] = 3
+            s["message"] = "User callback returned %s." % ("SOLVER_ABORT" if verdict == 1 else "SOLVER_TERMINATE_SUCCESSFULLY")
+        s["total_time_s"] = time.time() - t0
+        return s
 
     def run(self, reconstruction, feature_view, references=None):
         self.set_up(reconstruction, feature_view, references)

@@ -63,6 +63,18 @@ def main():
     ic_cm = _capi.default_interp(); ic_cm.l2_normalize = 0
     so = _capi.default_ba_options(max_num_iterations=10)
     cfg = _capi.default_costmap_config()
+    # warm-up outside the timed region: module load, pinned staging buffers, the first launches of every kernel
+    n_w = min(n_points, 500) * track
+    d_w = _engine.synth_patches_device(n_w, ps, C_, xy[:n_w] - 0.5 - np.clip((xy[:n_w] - ps / 2.0).astype(np.int32), 0, 1000 - ps - 1),
+                                       geo["obs_pt"][:n_w], seed=7, noise=0.01, ctx=ctx)
+    pw, _ = level_problem(geo, xy, X0, 1.0, d_w, True, ps, C_, sel=(n_w // track, n_w))
+    ow = _engine.costmaps_compute(pw, ic, cfg, to_host=False, to_device=True, ctx=ctx)
+    cw = _capi.BAProblem(cam_model=pw.cam_model, cam_params=pw.cam_params, cam_const_mask=pw.cam_const_mask, qvec=pw.qvec, tvec=pw.tvec,
+                         img_cam=pw.img_cam, pose_const=pw.pose_const, tvec_const_mask=pw.tvec_const_mask, xyz=pw.xyz.copy(),
+                         point_const=pw.point_const, obs_img=pw.obs_img, obs_pt=pw.obs_pt, patches=ow["device_ptr"], corner=pw.corner,
+                         scale=pw.scale, patches_on_device=True, patch_shape=(n_w, ps, ps, 3), patch_dtype=0)
+    _engine.ba_run(cw, ic_cm, so, ctx=ctx)
+    _engine.device_free(ow["device_ptr"], ctx); _engine.device_free(d_w, ctx)
     levels = []
     X = X0.copy()
     total_obs_iters = 0

@@ -277,3 +277,33 @@ def test_pixsfm_refines_a_colmap_model_directory(tmp_path):
         assert np.abs(back.points3D[pid].xyz - direct.points3D[pid].xyz).max() < 1e-9
     moved = max(np.abs(back.points3D[p].xyz - rec.points3D[p].xyz).max() for p in rec.points3D)
     assert moved > 1e-6
+
+
+def test_solver_callbacks_see_every_iteration_and_can_stop_the_solve():
+    """ceres::IterationCallback through `solver.callbacks` (reference util/misc.py:30-36): one call per iteration record,
+    starting with iteration 0; the trajectory equals the one-shot solve's; a callback can terminate the solve."""
+    rec, fm, _, _ = make_reconstruction(n_cams=6, n_points=60, track_len=4, channels=128, seed=23)
+    rec_a, rec_b, rec_c = copy.deepcopy(rec), copy.deepcopy(rec), copy.deepcopy(rec)
+    conf = {"optimizer": {"solver": {"max_num_iterations": 8}}}
+    plain = ba_pkg.BundleAdjuster.create(conf).refine_multilevel(rec_a, fm)["summary"][0]
+
+    seen = []
+    adj = ba_pkg.BundleAdjuster.create(conf)
+    adj.callbacks = [lambda it: seen.append((it["iteration"], it["cost"]))]
+    stepped = adj.refine_multilevel(rec_b, fm)["summary"][0]
+    assert [i for i, _ in seen] == list(range(len(seen))) and len(seen) == len(stepped.iterations)
+    assert len(seen) == len(plain.iterations)
+    assert abs(stepped.final_cost - plain.final_cost) <= 1e-8 * plain.final_cost
+    for p in rec_a.points3D:
+        assert np.abs(rec_a.points3D[p].xyz - rec_b.points3D[p].xyz).max() < 1e-7
+
+    calls = []
+    def stop_after_two(it):
+        calls.append(it["iteration"])
+        return 2 if it["iteration"] >= 2 else 0
+    adj = ba_pkg.BundleAdjuster.create(conf)
+    adj.callbacks = [stop_after_two]
+    stopped = adj.refine_multilevel(rec_c, fm)["summary"][0]
+    assert calls == [0, 1, 2]
+    assert "SOLVER_TERMINATE_SUCCESSFULLY" in stopped.message
+    assert stopped.final_cost < stopped.initial_cost and stopped.final_cost >= plain.final_cost
