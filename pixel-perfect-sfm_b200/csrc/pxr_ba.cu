@@ -786,6 +786,25 @@ int BA::chol_launch() {
     return PXR_OK;
 }
 
+// S -= sum over observation pairs T_x W_y^T, rhs += sum T gp: the staged pair kernel when every image has at most 8
+// columns (the usual case: pose + up to two intrinsics, or pose only), the direct kernels otherwise
+int BA::launch_schur_pairs(const BADev& d) {
+  if (sp_n_chunks <= 0) return PXR_OK;
+  const unsigned pair_grid = (unsigned)cdiv(sp_n_chunks * 32, kPairThreads);
+  if (img_dc_max <= 8 && dcmax >= 9 && !schur_direct) {
+    const bool vec = dcmax % 2 == 0;               // 16-byte gathers need 16-byte records
+    if (schur_ctas == 3) {
+      if (vec) PXR_LAUNCH(ctx, (ba_schur_pairs_staged_kernel<true, 3>), pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+      else PXR_LAUNCH(ctx, (ba_schur_pairs_staged_kernel<false, 3>), pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+    } else {
+      if (vec) PXR_LAUNCH(ctx, (ba_schur_pairs_staged_kernel<true, 4>), pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+      else PXR_LAUNCH(ctx, (ba_schur_pairs_staged_kernel<false, 4>), pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+    }
+  } else if (img_dc_max <= 8) PXR_LAUNCH(ctx, ba_schur_pairs_kernel<true>, pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+  else PXR_LAUNCH(ctx, ba_schur_pairs_kernel<false>, pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+  return PXR_OK;
+}
+
 // One LM step attempt at the current linearisation: fills delta, returns validity and model cost change
 int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   cudaStream_t s = ctx->stream;
@@ -814,10 +833,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   if (n_points > 0) {
     PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
     PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
-    if (sp_n_chunks > 0) {
-      if (img_dc_max <= 8) PXR_LAUNCH(ctx, ba_schur_pairs_kernel<true>, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
-      else PXR_LAUNCH(ctx, ba_schur_pairs_kernel<false>, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
-    }
+    PXR_TRY(launch_schur_pairs(d));
   }
   // rhs rides along as row nc of S: the factorisation performs the forward substitution
   if (nc > 0) PXR_CUDA(cudaMemcpyAsync(S.p + (size_t)nc * nc, rhs.p, (size_t)nc * 8, cudaMemcpyDeviceToDevice, s));
@@ -1594,7 +1610,7 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
     if (b->n_points > 0) {
       PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(b->n_points, 256), 256, 0, d, b->D2.p, b->Hinv.p, b->flags.p);
       PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_obs * b->dcmax, 256), 256, 0, d, b->Hinv.p, b->Tbuf.p);
-      if (b->sp_n_chunks > 0) PXR_LAUNCH(ctx, ba_schur_pairs_kernel<false>, (unsigned)cdiv(b->sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, b->schur_pairs(), b->Tbuf.p, b->S.p, b->rhs.p);
+      PXR_TRY(b->launch_schur_pairs(d));
     }
     if (S) PXR_CUDA(cudaMemcpyAsync(S, b->S.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));
     if (rhs) PXR_CUDA(cudaMemcpyAsync(rhs, b->rhs.p, nc * 8, cudaMemcpyDeviceToHost, s));

@@ -1,5 +1,6 @@
 // pxr_ba_host.h — host-side state of one featuremetric BA problem resident on the device.
 #pragma once
+#include <cstdlib>
 #include <chrono>
 #include <string>
 #include <functional>
@@ -163,9 +164,12 @@ struct BA {
   std::vector<int32_t> h_chunk_key_local;
   std::vector<int64_t> h_key_code_local;           // local key codes in build order (set by build_schur_pairs)
   int pcg_setup_blocks();
+  int launch_schur_pairs(const BADev& d);
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
   bool chol_multikernel = false, chol_force_multikernel = false, chol_band = false; int chol_grid = 0;
+  bool schur_direct = getenv("PXR_SCHUR_DIRECT") != nullptr;   // the direct pair kernel instead of the staged one (A/B switch)
+  int schur_ctas = getenv("PXR_SCHUR_CTAS") ? atoi(getenv("PXR_SCHUR_CTAS")) : 4;   // register budget of the staged kernel: 4 (64 regs) or 3 (80)
   DevBuf<int32_t> img_cols8, img_dc8; DevBuf<int8_t> img_src8;   // per-image column tables (<= 8 columns per image)
   DevBuf<int32_t> io_obs;           // observations grouped by image, chunks of <= 128 (camera-block build)
   DevBuf<int64_t> io_chunk_begin; int64_t io_n_chunks = 0;

@@ -404,9 +404,15 @@ static __global__ void __launch_bounds__(256) ba_schur_prep_kernel(BADev d, cons
   const int dcm = d.dcmax;
   const int64_t o = idx / dcm;
   const int a = (int)(idx - o * dcm);
-  if (o >= d.n_obs || a >= d.Wdc[o]) return;
+  if (o >= d.n_obs) return;
   const int64_t p = d.obs_pt[o];
   if (d.point_off[p] < 0) return;
+  if (a >= d.Wdc[o]) {
+    // record row 8 is free when the image has at most 8 columns: it carries the point's gradient, so that the staged
+    // pair kernel finds everything a self pair needs in ONE record (dcm = 6 + K >= 9 for every camera model)
+    if (a == 8) { double* tp = T + (o * dcm + 8) * 3; const double* g = d.gp + p * 3; tp[0] = g[0]; tp[1] = g[1]; tp[2] = g[2]; }
+    return;
+  }
   const double* h = Hinv + p * 6;
   const double* w = d.W + (o * dcm + a) * 3;
   double* tp = T + (o * dcm + a) * 3;
@@ -531,6 +537,111 @@ static __global__ void __launch_bounds__(kPairThreads, FAST ? 5 : 2) ba_schur_pa
     else if (ca < cb) atomic_add_f64(&S[(int64_t)cb * d.nc + ca], v);
     else atomic_add_f64(&S[(int64_t)ca * d.nc + ca], 2.0 * v);
   }
+  }
+}
+
+// Staged pair kernel (dc <= 8, the default): the same chunk-per-warp walk as above, 4 pairs per round, but the two
+// 192 B records of a pair (T of x, W of y) are fetched ONCE per round by the 8 lanes of the pair's group — 48 contiguous
+// bytes per lane — one round AHEAD of their use, staged through a per-warp double buffer in shared memory and read back
+// as a row (T, 3 x LDS.64) and a broadcast block (W, 12 x LDS.128).  Against the direct kernel: 4 instead of 27 global
+// load instructions per lane and round, every gather a full 32 B sector run, the gather latency of round r+1 hidden
+// behind the FMAs of round r, and the pair indices prefetched two rounds ahead.  On self chunks lane 0 of a group also
+// brings row 8 of the T record (the point's gradient, written by ba_schur_prep_kernel) for rhs += T gp.
+constexpr int kStageStride = 56;                      // doubles per staged pair: T rows at 0..23, gp at 24..26, W at 28..51;
+                                                      // 448 B = 16 banks mod 32, so two groups' row reads never collide
+template <bool VEC, int CTAS>
+static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_staged_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
+                                                                                                      double* S, double* rhs) {
+  __shared__ __align__(16) double stage_all[(kPairThreads / 32) * 2 * 4 * kStageStride];
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= sp.n_chunks) return;
+  const int64_t kb = sp.chunk_begin[c], ke = sp.chunk_begin[c + 1];
+  if (ke <= kb) return;
+  const int dcm = d.dcmax;
+  const bool self = sp.chunk_self[c] != 0;
+  const int g = lane >> 3, a = lane & 7;
+  // this lane's share of a pair's fetch: lanes 0..3 of a group the T record of x, lanes 4..7 the W record of y
+  const int32_t* __restrict__ my_idx = (a < 4 ? sp.px : sp.py) + kb;
+  const double* __restrict__ my_src = (a < 4 ? T : d.W) + (a & 3) * 6;
+  const bool take_gp = self && a == 0;
+  const int n = (int)(ke - kb), last = n - 1;
+  const int rounds = (n + 3) >> 2;
+  double* const st0 = stage_all + (threadIdx.x >> 5) * (2 * 4 * kStageStride) + g * kStageStride;   // this group's pair, buffer 0
+  double* const st1 = st0 + 4 * kStageStride;
+  const int my_slot = (a < 4 ? 0 : 28) + (a & 3) * 6; // where this lane's 6 doubles go inside the staged pair
+
+  double2 r0, r1, r2;                                 // the 48 bytes in flight
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0;                // row 8 (self chunks, lane 0 of the group)
+  const uint32_t rec = (uint32_t)dcm * 3u;
+  auto fetch = [&](int32_t o) {
+    const double* src = my_src + (uint64_t)(uint32_t)o * rec;
+    if (VEC) {
+      const double2* s2 = reinterpret_cast<const double2*>(src);
+      r0 = __ldg(s2); r1 = __ldg(s2 + 1); r2 = __ldg(s2 + 2);
+    } else {
+      r0 = make_double2(__ldg(src), __ldg(src + 1)); r1 = make_double2(__ldg(src + 2), __ldg(src + 3)); r2 = make_double2(__ldg(src + 4), __ldg(src + 5));
+    }
+    if (take_gp) { g0 = __ldg(src + 24); g1 = __ldg(src + 25); g2 = __ldg(src + 26); }   // a == 0: src is the T record's start
+  };
+  double acc[8], racc = 0.0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) acc[b] = 0.0;
+  // Rows of T beyond the image's column count and columns beyond dcy hold whatever the buffers hold: they are multiplied
+  // along (no predicates in the loop) and never written out.  Entries past the chunk's end re-read its last pair and
+  // are skipped by the `live` test.
+  int32_t o_next;
+  auto round = [&](double* st, int r) {
+    double2* dst = reinterpret_cast<double2*>(st + my_slot);
+    dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    if (take_gp) { st[24] = g0; st[25] = g1; st[26] = g2; }
+    __syncwarp();
+    if (r + 1 < rounds) {                             // next round's gathers leave before this round's arithmetic
+      fetch(o_next);
+      o_next = __ldg(my_idx + min(4 * (r + 2) + g, last));
+    }
+    if (4 * r + g <= last) {
+      const double t0 = st[a * 3], t1 = st[a * 3 + 1], t2 = st[a * 3 + 2];
+      const double2* w2 = reinterpret_cast<const double2*>(st + 28);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                   // rows 2q, 2q+1 of W: 6 doubles = 3 double2
+        const double2 u0 = w2[q * 3], u1 = w2[q * 3 + 1], u2 = w2[q * 3 + 2];
+        acc[2 * q] = fma(t0, u0.x, fma(t1, u0.y, fma(t2, u1.x, acc[2 * q])));
+        acc[2 * q + 1] = fma(t0, u1.y, fma(t1, u2.x, fma(t2, u2.y, acc[2 * q + 1])));
+      }
+      if (self) racc = fma(t0, st[24], fma(t1, st[25], fma(t2, st[26], racc)));
+    }
+  };
+  // pipeline prologue: data of round 0, index of round 1
+  fetch(__ldg(my_idx + min(g, last)));
+  o_next = __ldg(my_idx + min(4 + g, last));
+  // two buffers, one barrier per round: round r+1 stages into the other buffer, and every lane has left round r-1's
+  // reads of it before it passed round r's __syncwarp
+  for (int r = 0; r < rounds; r += 2) {
+    round(st0, r);
+    if (r + 1 < rounds) round(st1, r + 1);
+  }
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 8);
+    acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
+  }
+  racc += __shfl_xor_sync(0xffffffffu, racc, 8);
+  racc += __shfl_xor_sync(0xffffffffu, racc, 16);
+  const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
+  const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
+  if (g != 0 || a >= dcx) return;
+  const int ca = d.Wcols[ox0 * dcm + a];
+  if (self) atomic_add_f64(&rhs[ca], racc);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    if (b >= dcy) continue;
+    const int cb = d.Wcols[oy0 * dcm + b];
+    const double v = -acc[b];
+    if (self) { if (a >= b) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v); }
+    else if (ca > cb) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v);
+    else if (ca < cb) atomic_add_f64(&S[(int64_t)cb * d.nc + ca], v);
+    else atomic_add_f64(&S[(int64_t)ca * d.nc + ca], 2.0 * v);
   }
 }
 
