@@ -805,6 +805,18 @@ int BA::launch_schur_pairs(const BADev& d) {
   return PXR_OK;
 }
 
+// the same walk with the image-pair blocks as the sink (block-sparse ITERATIVE_SCHUR, block mode); these paths only
+// exist for images of at most 8 columns
+int BA::launch_sp_schur_pairs(const BADev& d, double* Bk, double* rhs_out, double* part) {
+  if (sp_n_chunks <= 0) return PXR_OK;
+  const unsigned pair_grid = (unsigned)cdiv(sp_n_chunks * 32, kPairThreads);
+  if (dcmax >= 9 && !schur_direct) {
+    if (dcmax % 2 == 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel<1>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
+    else PXR_LAUNCH(ctx, sp_schur_pairs_kernel<2>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
+  } else PXR_LAUNCH(ctx, sp_schur_pairs_kernel<0>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
+  return PXR_OK;
+}
+
 // One LM step attempt at the current linearisation: fills delta, returns validity and model cost change
 int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
   cudaStream_t s = ctx->stream;
@@ -822,7 +834,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     if (n_points > 0) {
       PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
       PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
-      if (sp_n_chunks > 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel, (unsigned)cdiv(sp_n_chunks * 32, kPairThreads), kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, ss_Bk.p, rhs.p);
+      PXR_TRY(launch_sp_schur_pairs(d, ss_Bk.p, rhs.p, nullptr));
     }
     if (ctx->world > 1 && nc > 0) PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
   } else {

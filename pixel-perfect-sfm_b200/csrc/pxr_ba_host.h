@@ -165,6 +165,7 @@ struct BA {
   std::vector<int64_t> h_key_code_local;           // local key codes in build order (set by build_schur_pairs)
   int pcg_setup_blocks();
   int launch_schur_pairs(const BADev& d);
+  int launch_sp_schur_pairs(const BADev& d, double* Bk, double* rhs_out, double* part);
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
   bool chol_multikernel = false, chol_force_multikernel = false, chol_band = false; int chol_grid = 0;

@@ -549,17 +549,14 @@ static __global__ void __launch_bounds__(kPairThreads, FAST ? 5 : 2) ba_schur_pa
 // brings row 8 of the T record (the point's gradient, written by ba_schur_prep_kernel) for rhs += T gp.
 constexpr int kStageStride = 56;                      // doubles per staged pair: T rows at 0..23, gp at 24..26, W at 28..51;
                                                       // 448 B = 16 banks mod 32, so two groups' row reads never collide
-template <bool VEC, int CTAS>
-static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_staged_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
-                                                                                                      double* S, double* rhs) {
-  __shared__ __align__(16) double stage_all[(kPairThreads / 32) * 2 * 4 * kStageStride];
-  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= sp.n_chunks) return;
-  const int64_t kb = sp.chunk_begin[c], ke = sp.chunk_begin[c + 1];
-  if (ke <= kb) return;
+constexpr int kStageDoubles = (kPairThreads / 32) * 2 * 4 * kStageStride;   // per CTA: 8 warps x 2 buffers x 4 pairs
+// The walk over one chunk; `stage_all` is the CTA's staging area (kStageDoubles, 16-byte aligned).  Leaves the chunk's
+// 8x8 block in acc (row a on the lanes of EVERY group after the final butterfly) and the rhs row in racc.
+template <bool VEC>
+__device__ __forceinline__ void schur_pairs_accumulate_staged(const BADev& d, const SchurPairs& sp, const double* __restrict__ T,
+                                                              int64_t kb, int64_t ke, int lane, bool self, double* stage_all,
+                                                              double acc[8], double& racc) {
   const int dcm = d.dcmax;
-  const bool self = sp.chunk_self[c] != 0;
   const int g = lane >> 3, a = lane & 7;
   // this lane's share of a pair's fetch: lanes 0..3 of a group the T record of x, lanes 4..7 the W record of y
   const int32_t* __restrict__ my_idx = (a < 4 ? sp.px : sp.py) + kb;
@@ -584,7 +581,7 @@ static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_stag
     }
     if (take_gp) { g0 = __ldg(src + 24); g1 = __ldg(src + 25); g2 = __ldg(src + 26); }   // a == 0: src is the T record's start
   };
-  double acc[8], racc = 0.0;
+  racc = 0.0;
 #pragma unroll
   for (int b = 0; b < 8; ++b) acc[b] = 0.0;
   // Rows of T beyond the image's column count and columns beyond dcy hold whatever the buffers hold: they are multiplied
@@ -600,7 +597,7 @@ static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_stag
       fetch(o_next);
       o_next = __ldg(my_idx + min(4 * (r + 2) + g, last));
     }
-    if (4 * r + g <= last) {
+    if (4 * r + g <= last) {                          // live: this group's pair of the round exists
       const double t0 = st[a * 3], t1 = st[a * 3 + 1], t2 = st[a * 3 + 2];
       const double2* w2 = reinterpret_cast<const double2*>(st + 28);
 #pragma unroll
@@ -628,6 +625,22 @@ static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_stag
   }
   racc += __shfl_xor_sync(0xffffffffu, racc, 8);
   racc += __shfl_xor_sync(0xffffffffu, racc, 16);
+}
+
+template <bool VEC, int CTAS>
+static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_staged_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
+                                                                                          double* S, double* rhs) {
+  __shared__ __align__(16) double stage_all[kStageDoubles];
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= sp.n_chunks) return;
+  const int64_t kb = sp.chunk_begin[c], ke = sp.chunk_begin[c + 1];
+  if (ke <= kb) return;
+  const int dcm = d.dcmax;
+  const bool self = sp.chunk_self[c] != 0;
+  const int g = lane >> 3, a = lane & 7;
+  double acc[8], racc;
+  schur_pairs_accumulate_staged<VEC>(d, sp, T, kb, ke, lane, self, stage_all, acc, racc);
   const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
   if (g != 0 || a >= dcx) return;

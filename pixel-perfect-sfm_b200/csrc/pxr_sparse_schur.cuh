@@ -33,9 +33,12 @@ struct SparseSchur {
 };
 
 // Schur pair chunks -> image-pair blocks (the fast path of ba_schur_pairs_kernel with a different sink)
-static __global__ void __launch_bounds__(kPairThreads) sp_schur_pairs_kernel(BADev d, SchurPairs sp, const int32_t* __restrict__ chunk_key,
+// STAGED: 0 the direct walk, 1 the staged one with 16-byte gathers, 2 with 8-byte gathers (odd record length)
+template <int STAGED>
+static __global__ void __launch_bounds__(kPairThreads, STAGED ? 4 : 1) sp_schur_pairs_kernel(BADev d, SchurPairs sp, const int32_t* __restrict__ chunk_key,
                                                                     const double* __restrict__ T, double* __restrict__ Bk, double* rhs,
                                                                     double* __restrict__ part = nullptr /* deterministic mode: [n_chunks][72] */) {
+  __shared__ __align__(16) double stage_all[STAGED ? kStageDoubles : 2];
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= sp.n_chunks) return;
@@ -47,7 +50,9 @@ static __global__ void __launch_bounds__(kPairThreads) sp_schur_pairs_kernel(BAD
   const int g = lane >> 3, a = lane & 7;
   double acc[8], racc;
   const bool self = sp.chunk_self[c] != 0;
-  schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, acc, racc);
+  if constexpr (STAGED == 1) schur_pairs_accumulate_staged<true>(d, sp, T, kb, ke, lane, self, stage_all, acc, racc);
+  else if constexpr (STAGED == 2) schur_pairs_accumulate_staged<false>(d, sp, T, kb, ke, lane, self, stage_all, acc, racc);
+  else schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, acc, racc);
   if (part) {        // fixed-order reduction per key afterwards (det_pair_reduce_kernel): no atomics
     if (g == 0) {
       double* dst = part + c * 72;

@@ -14,6 +14,16 @@ print('$name', 'ms %.3f steady %.3f'%(d['ms_per_step'],d['steady_state']['ms_per
 PY
 }
 echo "== A/B"; ab staged4 PXR_X=1; ab staged3 PXR_SCHUR_CTAS=3; ab direct PXR_SCHUR_DIRECT=1; ab staged4b PXR_X=1
+ab4() {  # configs[4] shard on one GPU: block-sparse path (sp_schur_pairs_kernel)
+  name=$1; shift
+  env "$@" timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --workload configs4 --no-e2e --no-surface --cpu-sample-points 0 > $out/bench_${tag}_c4_$name.json 2> $out/bench_${tag}_c4_$name.err
+  python - <<PY
+import json
+d=json.load(open('$out/bench_${tag}_c4_$name.json'))
+print('configs4 shard $name', 'ms %.3f steady %.3f'%(d['ms_per_step'],d['steady_state']['ms_per_step']), {k:round(v['ms_per_step'],4) for k,v in d['stage_ms'].items()})
+PY
+}
+echo "== A/B configs4 shard"; ab4 staged PXR_X=1; ab4 direct PXR_SCHUR_DIRECT=1
 echo "== parity subset with the 3-CTA build"; PXR_SCHUR_CTAS=3 timeout 600 python -m pytest tests/test_gpu_ba_parity.py tests/test_gpu_resident.py tests/test_gpu_mirror.py -x -q 2>&1 | tail -3
 echo "== ncu of the pair kernels"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ba_schur_pairs -c 2 -f -o $out/schur_pairs_$tag python bench.py --steps 2 --warmup 1 --no-e2e --no-surface --cpu-sample-points 0 > $out/ncu_$tag.log 2>&1
