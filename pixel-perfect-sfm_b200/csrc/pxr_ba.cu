@@ -791,7 +791,11 @@ int BA::chol_launch() {
 int BA::launch_schur_pairs(const BADev& d) {
   if (sp_n_chunks <= 0) return PXR_OK;
   const unsigned pair_grid = (unsigned)cdiv(sp_n_chunks * 32, kPairThreads);
-  if (img_dc_max <= 8 && dcmax >= 9 && !schur_direct) {
+  const bool small = img_dc_max <= 8 && dcmax >= 9;   // dcmax = 6 + K >= 9 for every camera model: row 8 of a record exists
+  if (small && schur_kernel == 0) {
+    if (schur_ctas == 4) PXR_LAUNCH(ctx, ba_schur_pairs_mma_kernel<4>, pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+    else PXR_LAUNCH(ctx, ba_schur_pairs_mma_kernel<3>, pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+  } else if (small && schur_kernel == 1) {
     const bool vec = dcmax % 2 == 0;               // 16-byte gathers need 16-byte records
     if (schur_ctas == 3) {
       if (vec) PXR_LAUNCH(ctx, (ba_schur_pairs_staged_kernel<true, 3>), pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
@@ -810,7 +814,8 @@ int BA::launch_schur_pairs(const BADev& d) {
 int BA::launch_sp_schur_pairs(const BADev& d, double* Bk, double* rhs_out, double* part) {
   if (sp_n_chunks <= 0) return PXR_OK;
   const unsigned pair_grid = (unsigned)cdiv(sp_n_chunks * 32, kPairThreads);
-  if (dcmax >= 9 && !schur_direct) {
+  if (dcmax >= 9 && schur_kernel == 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel<3>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
+  else if (dcmax >= 9 && schur_kernel == 1) {
     if (dcmax % 2 == 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel<1>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
     else PXR_LAUNCH(ctx, sp_schur_pairs_kernel<2>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
   } else PXR_LAUNCH(ctx, sp_schur_pairs_kernel<0>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);

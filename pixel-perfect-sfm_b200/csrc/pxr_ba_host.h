@@ -169,8 +169,10 @@ struct BA {
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
   bool chol_multikernel = false, chol_force_multikernel = false, chol_band = false; int chol_grid = 0;
-  bool schur_direct = getenv("PXR_SCHUR_DIRECT") != nullptr;   // the direct pair kernel instead of the staged one (A/B switch)
-  int schur_ctas = getenv("PXR_SCHUR_CTAS") ? atoi(getenv("PXR_SCHUR_CTAS")) : 4;   // register budget of the staged kernel: 4 (64 regs) or 3 (80)
+  // pair-walk kernel of the Schur assembly (images of <= 8 columns): 0 tensor-core (default), 1 staged, 2 direct.
+  // PXR_SCHUR_KERNEL=mma|staged|direct and PXR_SCHUR_CTAS=3|4 (register budget) are A/B switches for measurements.
+  int schur_kernel = [] { const char* e = getenv("PXR_SCHUR_KERNEL"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'd' ? 2 : 0)); }();
+  int schur_ctas = getenv("PXR_SCHUR_CTAS") ? atoi(getenv("PXR_SCHUR_CTAS")) : 0;   // 0: the kernel's default (mma 3, staged 4)
   DevBuf<int32_t> img_cols8, img_dc8; DevBuf<int8_t> img_src8;   // per-image column tables (<= 8 columns per image)
   DevBuf<int32_t> io_obs;           // observations grouped by image, chunks of <= 128 (camera-block build)
   DevBuf<int64_t> io_chunk_begin; int64_t io_n_chunks = 0;

@@ -658,6 +658,106 @@ static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_stag
   }
 }
 
+// Tensor-core pair walk (the default when every image has at most 8 columns).  One observation pair contributes the
+// 8x8 block T_x W_y^T = (8x3)(3x8): exactly ONE fp64 tensor-core instruction, mma.sync m8n8k4 with k padded from 3 to 4.
+// Its fragment layout wants from lane L = 4*gid + tig the elements A[gid][tig] = T_x[gid][tig] and
+// B[tig][gid] = W_y[gid][tig] — the SAME offset 3*gid + tig into both records, and over the 24 lanes with tig < 3 those
+// offsets are the 24 consecutive doubles of the record: one fully coalesced 192-byte gather per record, no staging, no
+// shuffles, no per-lane copies of W.  A warp walks its chunk 8 pairs at a time (16 gathers in flight, then 8 MMAs into
+// 4 rotating accumulators); the block ends up distributed as D[gid][2*tig + i].  On self chunks a second MMA against
+// B2[k][0] = gp[k] (row 8 of the T record, see ba_schur_prep_kernel) yields rhs += T gp in the lanes with tig == 0.
+// Rows / columns beyond an image's column count multiply whatever the buffers hold into rows / columns of D that are
+// never written out (an MMA never mixes rows of A or columns of B).
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double ldg_f64_at(const char* base, uint32_t index, uint32_t stride_bytes) {
+  return __ldg(reinterpret_cast<const double*>(base + (uint64_t)index * stride_bytes));   // one IMAD.WIDE.U32
+}
+template <bool SELF, int U>
+__device__ __forceinline__ void schur_pairs_walk_mma(const int32_t* __restrict__ px, const int32_t* __restrict__ py, int n, int lane,
+                                                     const char* Tl, const char* Wl, const char* Gl, uint32_t rec_bytes,
+                                                     bool ld, bool ldg, double c[4][2], double r[2]) {
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    // the next 32 pair indices, one per lane (coalesced); broadcast by shuffle as the walk reaches them
+    const int kk = min(k0 + lane, n - 1);              // past the end: the last pair again, its MMA is skipped
+    const int32_t oxl = __ldg(px + kk);
+    const int32_t oyl = SELF ? oxl : __ldg(py + kk);
+    const int m = min(32, n - k0);
+    for (int u0 = 0; u0 < m; u0 += U) {
+      double a[U], b[U], g[SELF ? U : 1];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t ox = (uint32_t)__shfl_sync(0xffffffffu, oxl, u0 + u);
+        const uint32_t oy = SELF ? ox : (uint32_t)__shfl_sync(0xffffffffu, oyl, u0 + u);
+        a[u] = ld ? ldg_f64_at(Tl, ox, rec_bytes) : 0.0;
+        b[u] = ld ? ldg_f64_at(Wl, oy, rec_bytes) : 0.0;
+        if (SELF) g[u] = ldg ? ldg_f64_at(Gl, ox, rec_bytes) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u0 + u < m) {                              // warp-uniform
+          dmma_884(c[u & 3][0], c[u & 3][1], a[u], b[u]);
+          if (SELF) dmma_884(r[0], r[1], a[u], g[u]);
+        }
+      }
+    }
+  }
+}
+
+// leaves D[gid][2*tig], D[gid][2*tig + 1] in c0, c1 and (self chunks, lanes with tig == 0) the rhs entry of row gid in racc;
+// U = pairs in flight per warp (8 wants the 80-register build: 3 CTAs of 256 threads per SM)
+template <int U>
+__device__ __forceinline__ void schur_pairs_accumulate_mma(const BADev& d, const SchurPairs& sp, const double* __restrict__ T,
+                                                           int64_t kb, int64_t ke, int lane, bool self,
+                                                           double& c0, double& c1, double& racc) {
+  const int gid = lane >> 2, tig = lane & 3;
+  const bool ld = tig < 3;
+  const uint32_t rec_bytes = (uint32_t)d.dcmax * 24u;
+  const int e = ld ? gid * 3 + tig : 0;                // lanes with tig == 3 carry the zero padding of k
+  const char* Tl = reinterpret_cast<const char*>(T + e);
+  const char* Wl = reinterpret_cast<const char*>(d.W + e);
+  const char* Gl = reinterpret_cast<const char*>(T + 24 + (ld ? tig : 0));   // row 8 of the T record: the point's gradient
+  double c[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}, r[2] = {0.0, 0.0};
+  if (self) schur_pairs_walk_mma<true, 4>(sp.px + kb, sp.py + kb, (int)(ke - kb), lane, Tl, Wl, Gl, rec_bytes, ld, ld && gid == 0, c, r);
+  else schur_pairs_walk_mma<false, U>(sp.px + kb, sp.py + kb, (int)(ke - kb), lane, Tl, Wl, Gl, rec_bytes, ld, false, c, r);
+  c0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+  c1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+  racc = r[0];
+}
+
+template <int CTAS>
+static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_mma_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
+                                                                                       double* S, double* rhs) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= sp.n_chunks) return;
+  const int64_t kb = sp.chunk_begin[c], ke = sp.chunk_begin[c + 1];
+  if (ke <= kb) return;
+  const int dcm = d.dcmax;
+  const bool self = sp.chunk_self[c] != 0;
+  double acc[2], racc;
+  schur_pairs_accumulate_mma<(CTAS <= 3 ? 8 : 4)>(d, sp, T, kb, ke, lane, self, acc[0], acc[1], racc);
+  const int a = lane >> 2, tig = lane & 3;
+  const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
+  const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
+  if (a >= dcx) return;
+  const int ca = d.Wcols[ox0 * dcm + a];
+  if (self && tig == 0) atomic_add_f64(&rhs[ca], racc);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int b = 2 * tig + i;
+    if (b >= dcy) continue;
+    const int cb = d.Wcols[oy0 * dcm + b];
+    const double v = -acc[i];
+    if (self) { if (a >= b) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v); }
+    else if (ca > cb) atomic_add_f64(&S[(int64_t)ca * d.nc + cb], v);
+    else if (ca < cb) atomic_add_f64(&S[(int64_t)cb * d.nc + ca], v);
+    else atomic_add_f64(&S[(int64_t)ca * d.nc + ca], 2.0 * v);
+  }
+}
+
 // ---------------------------------------------------------------- dense Cholesky (lower, in place)
 // The reduced system is stored as an (n+1) x n row-major array: rows 0..n-1 hold the lower
 // triangle of S, row n holds the right-hand side.  Factorising with the extra row performs the

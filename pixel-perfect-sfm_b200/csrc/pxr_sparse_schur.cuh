@@ -33,12 +33,13 @@ struct SparseSchur {
 };
 
 // Schur pair chunks -> image-pair blocks (the fast path of ba_schur_pairs_kernel with a different sink)
-// STAGED: 0 the direct walk, 1 the staged one with 16-byte gathers, 2 with 8-byte gathers (odd record length)
+// STAGED: 0 the direct walk, 1 the staged one with 16-byte gathers, 2 with 8-byte gathers (odd record length),
+//         3 the tensor-core walk (the default)
 template <int STAGED>
-static __global__ void __launch_bounds__(kPairThreads, STAGED ? 4 : 1) sp_schur_pairs_kernel(BADev d, SchurPairs sp, const int32_t* __restrict__ chunk_key,
+static __global__ void __launch_bounds__(kPairThreads, STAGED == 3 ? 3 : (STAGED ? 4 : 1)) sp_schur_pairs_kernel(BADev d, SchurPairs sp, const int32_t* __restrict__ chunk_key,
                                                                     const double* __restrict__ T, double* __restrict__ Bk, double* rhs,
                                                                     double* __restrict__ part = nullptr /* deterministic mode: [n_chunks][72] */) {
-  __shared__ __align__(16) double stage_all[STAGED ? kStageDoubles : 2];
+  __shared__ __align__(16) double stage_all[(STAGED == 1 || STAGED == 2) ? kStageDoubles : 2];
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= sp.n_chunks) return;
@@ -47,9 +48,29 @@ static __global__ void __launch_bounds__(kPairThreads, STAGED ? 4 : 1) sp_schur_
   const int dcm = d.dcmax;
   const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
+  const bool self = sp.chunk_self[c] != 0;
+  if constexpr (STAGED == 3) {
+    // block distributed as D[row][2*tig + i] over the warp (schur_pairs_accumulate_mma)
+    double cc[2], rr;
+    schur_pairs_accumulate_mma<8>(d, sp, T, kb, ke, lane, self, cc[0], cc[1], rr);
+    const int row = lane >> 2, tig = lane & 3;
+    if (part) {
+      double* dst = part + c * 72;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) dst[row * 8 + 2 * tig + i] = (row < dcx && 2 * tig + i < dcy) ? cc[i] : 0.0;
+      if (tig == 0) dst[64 + row] = (self && row < dcx) ? rr : 0.0;
+      return;
+    }
+    if (row >= dcx) return;
+    if (self && tig == 0) atomic_add_f64(&rhs[d.Wcols[ox0 * d.dcmax + row]], rr);
+    double* dst = Bk + ((int64_t)chunk_key[c] * 8 + row) * 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (2 * tig + i < dcy) atomic_add_f64(dst + 2 * tig + i, cc[i]);
+    return;
+  }
   const int g = lane >> 3, a = lane & 7;
   double acc[8], racc;
-  const bool self = sp.chunk_self[c] != 0;
   if constexpr (STAGED == 1) schur_pairs_accumulate_staged<true>(d, sp, T, kb, ke, lane, self, stage_all, acc, racc);
   else if constexpr (STAGED == 2) schur_pairs_accumulate_staged<false>(d, sp, T, kb, ke, lane, self, stage_all, acc, racc);
   else schur_pairs_accumulate(d, sp, T, kb, ke, lane, dcx, dcy, self, acc, racc);
