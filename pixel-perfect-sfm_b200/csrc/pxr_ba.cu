@@ -379,10 +379,10 @@ int BA::build_schur_pairs() {
         ++total;
       }
   }
-  if (total >= ((int64_t)1 << 31) || n_obs >= ((int64_t)1 << 31))
+  if (total >= ((int64_t)1 << 31) || n_obs >= ((int64_t)1 << 31) || n_points >= ((int64_t)1 << 31))
     return fail(PXR_ERR_UNSUPPORTED, "too many observation pairs for 32-bit pair indices");
   for (int64_t k = 0; k < n_keys; ++k) count[k + 1] += count[k];
-  std::vector<int32_t> px(total), py(total);
+  std::vector<int32_t> px(total), py(total), pp(total);
   {
     std::vector<int64_t> cursor(count.begin(), count.end() - 1);
     for (int64_t p = 0; p < n_points; ++p) {
@@ -393,6 +393,7 @@ int BA::build_schur_pairs() {
           const int64_t k = cursor[key_of(std::max(a, b), std::min(a, b), i == j)]++;
           // x = the observation in the image with the larger index
           if (a >= b) { px[k] = (int32_t)i; py[k] = (int32_t)j; } else { px[k] = (int32_t)j; py[k] = (int32_t)i; }
+          pp[k] = (int32_t)p;
         }
     }
   }
@@ -435,6 +436,7 @@ int BA::build_schur_pairs() {
   cudaStream_t s = ctx->stream;
   PXR_TRY(sp_px.upload(px.data(), px.size(), s));
   PXR_TRY(sp_py.upload(py.data(), py.size(), s));
+  PXR_TRY(sp_pp.upload(pp.data(), pp.size(), s));
   PXR_TRY(sp_chunk_begin.upload(cb.data(), cb.size(), s));
   PXR_TRY(sp_chunk_self.upload(cself.data(), cself.size(), s));
   PXR_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
@@ -444,7 +446,7 @@ int BA::build_schur_pairs() {
 
 SchurPairs BA::schur_pairs() {
   SchurPairs sp;
-  sp.px = sp_px.p; sp.py = sp_py.p; sp.chunk_begin = sp_chunk_begin.p; sp.chunk_self = sp_chunk_self.p;
+  sp.px = sp_px.p; sp.py = sp_py.p; sp.pp = sp_pp.p; sp.chunk_begin = sp_chunk_begin.p; sp.chunk_self = sp_chunk_self.p;
   sp.n_chunks = sp_n_chunks;
   return sp;
 }
@@ -792,9 +794,15 @@ int BA::launch_schur_pairs(const BADev& d) {
   if (sp_n_chunks <= 0) return PXR_OK;
   const unsigned pair_grid = (unsigned)cdiv(sp_n_chunks * 32, kPairThreads);
   const bool small = img_dc_max <= 8 && dcmax >= 9;   // dcmax = 6 + K >= 9 for every camera model: row 8 of a record exists
-  if (small && schur_kernel == 0) {
-    if (schur_ctas == 4) PXR_LAUNCH(ctx, ba_schur_pairs_mma_kernel<4>, pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
-    else PXR_LAUNCH(ctx, ba_schur_pairs_mma_kernel<3>, pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+  if (small && schur_kernel == 0) {                   // fused tensor-core walk: no T buffer
+    if (schur_ctas == 3) PXR_LAUNCH(ctx, (ba_schur_pairs_mma_kernel<3, true>), pair_grid, kPairThreads, 0, d, schur_pairs(), Hinv.p, S.p, rhs.p);
+    else PXR_LAUNCH(ctx, (ba_schur_pairs_mma_kernel<4, true>), pair_grid, kPairThreads, 0, d, schur_pairs(), Hinv.p, S.p, rhs.p);
+    return PXR_OK;
+  }
+  PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
+  if (small && schur_kernel == 3) {
+    if (schur_ctas == 4) PXR_LAUNCH(ctx, (ba_schur_pairs_mma_kernel<4, false>), pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
+    else PXR_LAUNCH(ctx, (ba_schur_pairs_mma_kernel<3, false>), pair_grid, kPairThreads, 0, d, schur_pairs(), Tbuf.p, S.p, rhs.p);
   } else if (small && schur_kernel == 1) {
     const bool vec = dcmax % 2 == 0;               // 16-byte gathers need 16-byte records
     if (schur_ctas == 3) {
@@ -814,7 +822,12 @@ int BA::launch_schur_pairs(const BADev& d) {
 int BA::launch_sp_schur_pairs(const BADev& d, double* Bk, double* rhs_out, double* part) {
   if (sp_n_chunks <= 0) return PXR_OK;
   const unsigned pair_grid = (unsigned)cdiv(sp_n_chunks * 32, kPairThreads);
-  if (dcmax >= 9 && schur_kernel == 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel<3>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
+  if (dcmax >= 9 && schur_kernel == 0) {
+    PXR_LAUNCH(ctx, sp_schur_pairs_kernel<4>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Hinv.p, Bk, rhs_out, part);
+    return PXR_OK;
+  }
+  PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
+  if (dcmax >= 9 && schur_kernel == 3) PXR_LAUNCH(ctx, sp_schur_pairs_kernel<3>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
   else if (dcmax >= 9 && schur_kernel == 1) {
     if (dcmax % 2 == 0) PXR_LAUNCH(ctx, sp_schur_pairs_kernel<1>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
     else PXR_LAUNCH(ctx, sp_schur_pairs_kernel<2>, pair_grid, kPairThreads, 0, d, schur_pairs(), ss_chunk_key.p, Tbuf.p, Bk, rhs_out, part);
@@ -838,8 +851,7 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
     PXR_TRY(ss_Bk.zero(s));
     if (n_points > 0) {
       PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
-      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
-      PXR_TRY(launch_sp_schur_pairs(d, ss_Bk.p, rhs.p, nullptr));
+      PXR_TRY(launch_sp_schur_pairs(d, ss_Bk.p, rhs.p, nullptr));   // T = W Hinv first, unless the walk forms it itself
     }
     if (ctx->world > 1 && nc > 0) PXR_TRY(allreduce_f64(ctx, rhs.p, nc));
   } else {
@@ -849,7 +861,6 @@ int BA::compute_step(double radius, bool* valid, double* model_cost_change) {
                          ctx->world > 1 ? gc_local.p : gc.p, D2.p, S.p, rhs.p, nc, (ctx->world <= 1 || ctx->rank == 0) ? 1 : 0);
   if (n_points > 0) {
     PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
-    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
     PXR_TRY(launch_schur_pairs(d));
   }
   // rhs rides along as row nc of S: the factorisation performs the forward substitution
@@ -1626,7 +1637,6 @@ int pxr_ba_debug_linearize(pxr_ba* ba, double radius, double* cost, double* Hcc,
     PXR_CUDA(cudaMemsetAsync(b->flags.p, 0, 4 * sizeof(int), s));
     if (b->n_points > 0) {
       PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(b->n_points, 256), 256, 0, d, b->D2.p, b->Hinv.p, b->flags.p);
-      PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(b->n_obs * b->dcmax, 256), 256, 0, d, b->Hinv.p, b->Tbuf.p);
       PXR_TRY(b->launch_schur_pairs(d));
     }
     if (S) PXR_CUDA(cudaMemcpyAsync(S, b->S.p, nc * nc * 8, cudaMemcpyDeviceToHost, s));

@@ -366,7 +366,6 @@ int BA::compute_step_block(double radius) {
   PXR_CUDA(cudaMemsetAsync(L + pk_off_B, 0, ((size_t)ss_n_keys * 64 + nc) * 8, s));               // B_key, rhsS
   if (n_points > 0 && n_obs > 0) {
     PXR_LAUNCH(ctx, ba_point_inverse_kernel, (unsigned)cdiv(n_points, 256), 256, 0, d, D2.p, Hinv.p, flags.p);
-    PXR_LAUNCH(ctx, ba_schur_prep_kernel, (unsigned)cdiv(n_obs * dcmax, 256), 256, 0, d, Hinv.p, Tbuf.p);
     PXR_TRY(launch_sp_schur_pairs(d, L + pk_off_B, L + pk_off_rhs, deterministic ? det_pair_part.p : nullptr));
     if (deterministic) {
       PXR_CUDA(cudaMemsetAsync(det_rimg.p, 0, (size_t)n_images * 8 * 8, s));

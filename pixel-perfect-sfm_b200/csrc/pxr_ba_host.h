@@ -169,10 +169,11 @@ struct BA {
   cudaGraphExec_t chol_graph_exec = nullptr;
   int64_t chol_graph_kernels = 0;
   bool chol_multikernel = false, chol_force_multikernel = false, chol_band = false; int chol_grid = 0;
-  // pair-walk kernel of the Schur assembly (images of <= 8 columns): 0 tensor-core (default), 1 staged, 2 direct.
-  // PXR_SCHUR_KERNEL=mma|staged|direct and PXR_SCHUR_CTAS=3|4 (register budget) are A/B switches for measurements.
-  int schur_kernel = [] { const char* e = getenv("PXR_SCHUR_KERNEL"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'd' ? 2 : 0)); }();
-  int schur_ctas = getenv("PXR_SCHUR_CTAS") ? atoi(getenv("PXR_SCHUR_CTAS")) : 0;   // 0: the kernel's default (mma 3, staged 4)
+  // pair-walk kernel of the Schur assembly (images of <= 8 columns): 0 fused tensor-core walk (default), 3 tensor-core walk
+  // on a precomputed T, 1 staged, 2 direct.  PXR_SCHUR_KERNEL=fused|mma|staged|direct and PXR_SCHUR_CTAS=3|4 (register
+  // budget) are A/B switches for measurements.
+  int schur_kernel = [] { const char* e = getenv("PXR_SCHUR_KERNEL"); return !e ? 0 : (e[0] == 'm' ? 3 : (e[0] == 's' ? 1 : (e[0] == 'd' ? 2 : 0))); }();
+  int schur_ctas = getenv("PXR_SCHUR_CTAS") ? atoi(getenv("PXR_SCHUR_CTAS")) : 0;   // 0: the kernel's default (fused 4, mma 3, staged 4)
   DevBuf<int32_t> img_cols8, img_dc8; DevBuf<int8_t> img_src8;   // per-image column tables (<= 8 columns per image)
   DevBuf<int32_t> io_obs;           // observations grouped by image, chunks of <= 128 (camera-block build)
   DevBuf<int64_t> io_chunk_begin; int64_t io_n_chunks = 0;
@@ -180,7 +181,7 @@ struct BA {
   DevBuf<int> chol_sync;            // flags of the persistent tile-DAG Cholesky (pxr_chol.cuh)
   ~BA() { if (inner_cnt_host) cudaFreeHost(inner_cnt_host); for (auto e : inner_events) cudaEventDestroy(e); if (res_thread.joinable()) res_thread.join(); if (chol_graph_exec) cudaGraphExecDestroy(chol_graph_exec); for (int k = 0; k < kNumStages; ++k) for (auto& pr : timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
   // static co-visibility structure for the Schur complement (see ba_schur_pairs_kernel)
-  DevBuf<int32_t> sp_px, sp_py;
+  DevBuf<int32_t> sp_px, sp_py, sp_pp;
   DevBuf<int64_t> sp_chunk_begin;
   DevBuf<uint8_t> sp_chunk_self;
   DevBuf<double> Tbuf, Hinv;

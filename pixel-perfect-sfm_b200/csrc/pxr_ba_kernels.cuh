@@ -423,6 +423,7 @@ static __global__ void __launch_bounds__(256) ba_schur_prep_kernel(BADev d, cons
 
 struct SchurPairs {
   const int32_t* px; const int32_t* py;   // observation pair entries, sorted by chunk
+  const int32_t* pp;                      // the pairs' 3D point (fused tensor-core walk: H_pp^-1 and g_p without a detour over obs_pt)
   const int64_t* chunk_begin;             // [n_chunks + 1]
   const uint8_t* chunk_self;              // [n_chunks] 1: entries are (o,o) self pairs
   int64_t n_chunks;
@@ -727,8 +728,77 @@ __device__ __forceinline__ void schur_pairs_accumulate_mma(const BADev& d, const
   racc = r[0];
 }
 
-template <int CTAS>
-static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_mma_kernel(BADev d, SchurPairs sp, const double* __restrict__ T,
+// Fused variant (the default): T_x = W_x (H_pp + D)^-1 is not read from a precomputed buffer but formed per pair by one
+// more MMA — A = the W_x fragment, B[k][2j] = Hinv[k][j] (the point's symmetric 3x3 inverse in the EVEN columns, 9 lanes
+// load it) — whose accumulator D[gid][2*tig] = T[gid][tig] already is the A fragment of the product with W_y.
+// Both record gathers now hit the SAME array (W; 120 MB at configs[2] instead of 240 MB for W and T), which is what
+// the kernel is bound by (random 192-byte gathers against an L2 that cannot hold both arrays), ba_schur_prep_kernel
+// and its 0.2 GB of traffic disappear, and g_p comes from its own array by the pair's point index.
+template <bool SELF, int U>
+__device__ __forceinline__ void schur_pairs_walk_fused(const int32_t* __restrict__ px, const int32_t* __restrict__ py,
+                                                       const int32_t* __restrict__ pp, int n, int lane,
+                                                       const char* Wl, const char* Hl, const char* Gl, uint32_t rec_bytes,
+                                                       bool ld, bool ldh, bool ldg, double c[2][2], double r[2]) {
+  // the next 32 pair indices, one per lane, fetched one block ahead (past the end: the last pair again, its MMAs are skipped)
+  int kk = min(lane, n - 1);
+  int32_t oxn = __ldg(px + kk), oyn = SELF ? 0 : __ldg(py + kk), ppn = __ldg(pp + kk);
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int32_t oxl = oxn, oyl = oyn, ppl = ppn;
+    kk = min(k0 + 32 + lane, n - 1);
+    oxn = __ldg(px + kk); if (!SELF) oyn = __ldg(py + kk); ppn = __ldg(pp + kk);
+    const int m = min(32, n - k0);
+    for (int u0 = 0; u0 < m; u0 += U) {
+      double a[U], b[U], h[U], g[SELF ? U : 1];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t ox = (uint32_t)__shfl_sync(0xffffffffu, oxl, u0 + u);
+        const uint32_t oy = SELF ? ox : (uint32_t)__shfl_sync(0xffffffffu, oyl, u0 + u);
+        const uint32_t pt = (uint32_t)__shfl_sync(0xffffffffu, ppl, u0 + u);
+        a[u] = ld ? ldg_f64_at(Wl, ox, rec_bytes) : 0.0;
+        b[u] = SELF ? a[u] : (ld ? ldg_f64_at(Wl, oy, rec_bytes) : 0.0);
+        h[u] = ldh ? ldg_f64_at(Hl, pt, 48u) : 0.0;
+        if (SELF) g[u] = ldg ? ldg_f64_at(Gl, pt, 24u) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u0 + u < m) {                              // warp-uniform
+          double t = 0.0, unused = 0.0;
+          dmma_884(t, unused, a[u], h[u]);             // T = W_x Hinv with Hinv's column j placed in column 2j of B:
+                                                       // D[gid][2*tig] = T[gid][tig] IS the A fragment of the next MMA
+          dmma_884(c[u & 1][0], c[u & 1][1], t, b[u]);
+          if (SELF) dmma_884(r[0], r[1], t, g[u]);
+        }
+      }
+    }
+  }
+}
+
+template <int U>
+__device__ __forceinline__ void schur_pairs_accumulate_fused(const BADev& d, const SchurPairs& sp, const double* __restrict__ Hinv,
+                                                             int64_t kb, int64_t ke, int lane, bool self,
+                                                             double& c0, double& c1, double& racc) {
+  const int gid = lane >> 2, tig = lane & 3;
+  // B of the first MMA: B[k][2j] = Hinv[k][j], j < 3 (odd columns and columns 6, 7 zero): lane (gid = 2j, tig = k) loads it
+  const bool ld = tig < 3, ldh = ld && gid < 6 && (gid & 1) == 0;
+  const uint32_t rec_bytes = (uint32_t)d.dcmax * 24u;
+  const int e = ld ? gid * 3 + tig : 0;                // lanes with tig == 3 carry the zero padding of k
+  // symmetric storage of the inverse: (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+  const int lo = min(gid >> 1, tig), hi = max(gid >> 1, tig);
+  const int hidx = ldh ? (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5)) : 0;
+  const char* Wl = reinterpret_cast<const char*>(d.W + e);
+  const char* Hl = reinterpret_cast<const char*>(Hinv + hidx);
+  const char* Gl = reinterpret_cast<const char*>(d.gp + (ld ? tig : 0));
+  double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, r[2] = {0.0, 0.0};
+  const int n = (int)(ke - kb);
+  if (self) schur_pairs_walk_fused<true, 4>(sp.px + kb, sp.py + kb, sp.pp + kb, n, lane, Wl, Hl, Gl, rec_bytes, ld, ldh, ld && gid == 0, c, r);
+  else schur_pairs_walk_fused<false, U>(sp.px + kb, sp.py + kb, sp.pp + kb, n, lane, Wl, Hl, Gl, rec_bytes, ld, ldh, false, c, r);
+  c0 = c[0][0] + c[1][0];
+  c1 = c[0][1] + c[1][1];
+  racc = r[0];
+}
+
+template <int CTAS, bool FUSED>
+static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_mma_kernel(BADev d, SchurPairs sp, const double* __restrict__ T /* FUSED: Hinv */,
                                                                                        double* S, double* rhs) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -738,7 +808,8 @@ static __global__ void __launch_bounds__(kPairThreads, CTAS) ba_schur_pairs_mma_
   const int dcm = d.dcmax;
   const bool self = sp.chunk_self[c] != 0;
   double acc[2], racc;
-  schur_pairs_accumulate_mma<(CTAS <= 3 ? 8 : 4)>(d, sp, T, kb, ke, lane, self, acc[0], acc[1], racc);
+  if constexpr (FUSED) schur_pairs_accumulate_fused<(CTAS <= 3 ? 8 : 4)>(d, sp, T, kb, ke, lane, self, acc[0], acc[1], racc);
+  else schur_pairs_accumulate_mma<(CTAS <= 3 ? 8 : 4)>(d, sp, T, kb, ke, lane, self, acc[0], acc[1], racc);
   const int a = lane >> 2, tig = lane & 3;
   const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];

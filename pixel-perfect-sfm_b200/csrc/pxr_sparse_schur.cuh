@@ -34,7 +34,7 @@ struct SparseSchur {
 
 // Schur pair chunks -> image-pair blocks (the fast path of ba_schur_pairs_kernel with a different sink)
 // STAGED: 0 the direct walk, 1 the staged one with 16-byte gathers, 2 with 8-byte gathers (odd record length),
-//         3 the tensor-core walk (the default)
+//         3 the tensor-core walk on the precomputed T, 4 the fused tensor-core walk (the default; `T` is Hinv then)
 template <int STAGED>
 static __global__ void __launch_bounds__(kPairThreads, STAGED == 3 ? 3 : (STAGED ? 4 : 1)) sp_schur_pairs_kernel(BADev d, SchurPairs sp, const int32_t* __restrict__ chunk_key,
                                                                     const double* __restrict__ T, double* __restrict__ Bk, double* rhs,
@@ -49,10 +49,11 @@ static __global__ void __launch_bounds__(kPairThreads, STAGED == 3 ? 3 : (STAGED
   const int64_t ox0 = sp.px[kb], oy0 = sp.py[kb];
   const int dcx = d.Wdc[ox0], dcy = d.Wdc[oy0];
   const bool self = sp.chunk_self[c] != 0;
-  if constexpr (STAGED == 3) {
-    // block distributed as D[row][2*tig + i] over the warp (schur_pairs_accumulate_mma)
+  if constexpr (STAGED >= 3) {
+    // block distributed as D[row][2*tig + i] over the warp (schur_pairs_accumulate_mma / _fused)
     double cc[2], rr;
-    schur_pairs_accumulate_mma<8>(d, sp, T, kb, ke, lane, self, cc[0], cc[1], rr);
+    if constexpr (STAGED == 4) schur_pairs_accumulate_fused<4>(d, sp, T, kb, ke, lane, self, cc[0], cc[1], rr);
+    else schur_pairs_accumulate_mma<8>(d, sp, T, kb, ke, lane, self, cc[0], cc[1], rr);
     const int row = lane >> 2, tig = lane & 3;
     if (part) {
       double* dst = part + c * 72;
