@@ -1,7 +1,7 @@
 """Mirror of `pixsfm._pixsfm._features` (pixsfm/features/bindings.cc:38-300): FeaturePatch / FeatureMap /
 FeatureSet / FeatureView / FeatureManager and Reference.  Patches stay numpy references (no copy), as
-featuremap.cc:9-45 does; the device upload happens when an optimizer runs.  HDF5 loading
-(featuremap.cc:138-267) is out of scope this round (no HDF5 offline)."""
+featuremap.cc:9-45 does; the device upload happens when an optimizer runs.  HDF5 loading (featuremap.cc:138-267)
+lives in features/store_features.py; `LazyFeatureMap` is what it returns for `fill=False`."""
 import numpy as np
 
 kDenseId = 1000000  # util/src/types.h:33
@@ -117,6 +117,81 @@ class FeatureMap:
         return FeaturePatch(self.patches[k], self.corners[k], self.scale)
 
 
+class LazyFeatureMap(FeatureMap):
+    """A FeatureMap whose metadata is resident and whose patches come from the cache file on demand — the reference's
+    `FeatureMap(h5_group, fill=false)` with `Load()` / `Unload()` / `Lock()` (featuremap.h:43-71, featuremap.cc:60-136).
+    Granularity is the whole map (one image): `load()` reads all its patches through `reader()` and counts a user,
+    `unload()` drops them when the last user is gone and the map is not locked.  Reading `patches` without a `load()`
+    loads implicitly (and leaves the data in place until an `unload()`)."""
+
+    def __init__(self, reader, n_patches, patch_shape, dtype, point2D_ids, corners, metadata):
+        self._reader, self._data, self._users, self._locked = reader, None, 0, False
+        self._shape4 = (int(n_patches),) + tuple(int(v) for v in patch_shape)
+        self._dtype = np.dtype(dtype)
+        if len(self._shape4) != 4:
+            raise ValueError("patches must be [N,H,W,C]")
+        if self._dtype not in (np.float16, np.float32, np.float64):
+            raise ValueError("patches must be float16/float32/float64")
+        self.point2D_ids = [int(i) for i in point2D_ids]
+        if len(self.point2D_ids) != self._shape4[0]:
+            raise ValueError("number of point2D_ids and patches differ")
+        self.corners = np.ascontiguousarray(corners, np.int32).reshape(-1, 2)
+        self.scale = np.asarray(metadata["scale"], np.float64).reshape(2)
+        self.is_sparse = bool(metadata.get("is_sparse", True))
+        self._index = {pid: k for k, pid in enumerate(self.point2D_ids)}
+
+    # -- the reference's Load / Unload / Lock
+    @property
+    def is_loaded(self):
+        return self._data is not None
+
+    def load(self):
+        if self._data is None:
+            data = np.ascontiguousarray(self._reader())
+            if data.shape != self._shape4 or data.dtype != self._dtype:
+                raise ValueError("cache holds %s %s, metadata says %s %s" % (data.shape, data.dtype, self._shape4, self._dtype))
+            self._data = data
+        self._users += 1
+        return self
+
+    def unload(self):
+        self._users = max(0, self._users - 1)
+        if self._users == 0 and not self._locked:
+            self._data = None
+
+    def lock(self):
+        """features stay resident from now on (FeatureMap::Lock)"""
+        if self._data is None:
+            self.load(); self._users -= 1
+        self._locked = True
+
+    @property
+    def patches(self):
+        if self._data is None:
+            self.load(); self._users -= 1
+        return self._data
+
+    # -- what the base class derives from the array
+    @property
+    def shape(self):
+        return self._shape4[1:]
+
+    @property
+    def channels(self):
+        return self._shape4[3]
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    def size(self):
+        return self._shape4[0]
+
+    def fpatch(self, point2D_idx):
+        k = self.local_index(point2D_idx)
+        return FeaturePatch(self.patches[k], self.corners[k], self.scale)
+
+
 class FeatureSet:
     def __init__(self, channels=None, dtype=None):
         self._channels, self._dtype, self._maps = channels, dtype, {}
@@ -173,6 +248,32 @@ class FeatureView:
             self._id_to_name = dict(source.image_id_to_name)
         else:
             self._id_to_name = {iid: im.name for iid, im in source.images.items()}
+        # a view over a lazily filled set brings in the maps of ITS images and releases them when it goes away
+        # (featureview.cc:70-126 loads the required patches in the constructor, the destructor unloads them)
+        self._loaded = []
+        for name in (dict.fromkeys(self._id_to_name.values()) if hasattr(feature_set, "has_fmap") else ()):
+            if feature_set.has_fmap(name):
+                fmap = feature_set.fmap(name)
+                if isinstance(fmap, LazyFeatureMap):
+                    fmap.load()
+                    self._loaded.append(fmap)
+
+    def close(self):
+        for fmap in self._loaded:
+            fmap.unload()
+        self._loaded = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @property
     def channels(self):

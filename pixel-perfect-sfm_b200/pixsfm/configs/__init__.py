@@ -20,7 +20,8 @@ def _low_memory():
               references=dict(keep_observations=False), costmaps=dict(num_threads=-1),
               optimizer=dict(loss=dict(name="cauchy", params=[0.25]), print_summary=False, refine_focal_length=False,
                              refine_principal_point=False, refine_extra_params=False, refine_extrinsics=False))
-    return {"dense_features": dict(sparse=True, dtype="half", patch_size=8),
+    return {"dense_features": dict(sparse=True, dtype="half", use_cache=True, overwrite_cache=True, load_cache_on_init=False,
+                                   patch_size=8, cache_format="chunked"),
             "interpolation": dict(nodes=[[0.0, 0.0]], mode="BICUBIC"),
             "mapping": {"KA": ka, "BA": ba}}
 

@@ -5,6 +5,8 @@ The reference's FeatureExtractor (pixsfm/features/extractor.py) owns the CNN (S2
 `patch_size` x `patch_size` patch per keypoint with `corner = clip(int(kp * scale - ps / 2), 0, [w, h] - ps - 1)`.  The CNN
 is not part of this package; the step after it is, so that any model — a callable image name -> list of [C,H,W] maps,
 finest level first — plugs into `PixSfM(conf, extractor=DenseFeatureExtractor(model, ...))`."""
+import os
+
 import numpy as np
 
 from .. import logger
@@ -109,7 +111,9 @@ def dense_to_fmap(featuremap, image_size, keypoints=None, keypoint_ids=None, pat
 class DenseFeatureExtractor:
     """model(image_name) -> list of [C,H,W] maps (one per level) ; image_size(image_name) -> (width, height).
     Produces the FeatureManager the adjusters take: one FeatureSet per level, one FeatureMap per image."""
-    default_conf = dict(patch_size=16, sparse=True, l2_normalize=True, dtype="half", on_device=False)
+    default_conf = dict(patch_size=16, sparse=True, l2_normalize=True, dtype="half", on_device=False,
+                        # the dense-feature cache (reference features/extractor.py:46-49, extract.py:72-147)
+                        use_cache=False, overwrite_cache=False, load_cache_on_init=False, cache_format="chunked")
 
     def __init__(self, model, image_size, conf=None):
         self.model, self.image_size = model, image_size
@@ -120,9 +124,23 @@ class DenseFeatureExtractor:
         if self.conf["dtype"] not in _DTYPES:
             raise ValueError("dtype must be one of %s" % sorted(_DTYPES))
 
-    def features_from_image_list(self, image_dir, image_names, keypoints=None, req_keypoint_ids=None, cache_path=None):
-        if cache_path is not None:
-            logger.warning("HDF5 feature caches are not supported by this package: cache_path is ignored")
+    def features_from_image_list(self, image_dir, image_names, keypoints=None, req_keypoint_ids=None, cache_path=None,
+                                 level_prefix=""):
+        """extract.py:57-150.  With `use_cache` an existing cache file is taken as it is (unless `overwrite_cache`), and a
+        fresh extraction is written to `cache_path` and handed back THROUGH the file — filled, or with `load_cache_on_init`
+        off as metadata whose patches a FeatureView brings in per image (store_features.load_features_from_cache).  The
+        file is written once all images are done (h5lite writes at close), not image by image as the reference does."""
+        from . import store_features
+        use_cache = bool(self.conf["use_cache"])
+        if use_cache and cache_path is None:
+            raise RuntimeError("Trying to write features to H5 but no path given.")
+        if use_cache and self.conf["on_device"]:
+            raise ValueError("use_cache stores host arrays: it cannot be combined with on_device")
+        if use_cache and os.path.exists(str(cache_path)):
+            if self.conf["overwrite_cache"]:
+                os.unlink(str(cache_path))
+            else:
+                return store_features.load_features_from_cache(cache_path, bool(self.conf["load_cache_on_init"]), level_prefix)
         manager = None
         for name in image_names:
             kps, ids = None, None
@@ -144,6 +162,10 @@ class DenseFeatureExtractor:
                 manager.fset(level).emplace(name, made)
         if manager is None:
             raise ValueError("no image to extract features for")
+        if use_cache:
+            os.makedirs(os.path.dirname(os.path.abspath(str(cache_path))), exist_ok=True)
+            store_features.write_feature_manager_cache(cache_path, manager, self.conf["cache_format"], level_prefix)
+            return store_features.load_features_from_cache(cache_path, bool(self.conf["load_cache_on_init"]), level_prefix)
         return manager
 
     def features_from_graph(self, image_dir, graph, keypoints, cache_path=None):

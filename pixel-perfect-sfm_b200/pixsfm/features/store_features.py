@@ -10,7 +10,7 @@
 Goes through h5py when it is installed and util/h5lite.py otherwise (classic HDF5 layout, see that module)."""
 import numpy as np
 
-from .._pixsfm._features import FeatureManager, FeatureMap, kDenseId
+from .._pixsfm._features import FeatureManager, FeatureMap, LazyFeatureMap, kDenseId
 from ..util.hloc import _h5py
 
 _DTYPES = {"half": np.float16, "float": np.float32, "double": np.float64}
@@ -108,9 +108,40 @@ def _load_featuremap(group, point2D_ids=None):
     return FeatureMap(np.ascontiguousarray(patches), ids, corners, {"scale": scale, "is_sparse": sparse})
 
 
+def _lazy_featuremap(cache_path, group):
+    """FeatureMap::InitFromH5Group with fill = false: metadata now, patches when a FeatureView needs the image.  Returns
+    None for layouts whose metadata cannot be had without the data (they are read eagerly instead)."""
+    fmt = int(group.attrs["format"])
+    sparse = bool(int(group.attrs["is_sparse"]))
+    if fmt != 2:
+        return None                                   # "grouped": one dataset per keypoint, corner / scale on each
+    ds = group["patches"]
+    ids = [int(v) for v in np.asarray(group["keypoint_ids"]).reshape(-1)]
+    if not sparse and len(ids) > 1:
+        return None                                   # dense stored, sparse read: the windows are cut at load time
+    corners = np.asarray(group["corners"]).reshape(-1, 2).astype(np.int32)
+    scales = np.asarray(group["scales"]).reshape(-1, 2).astype(np.float64)
+    scale = scales[0] if len(scales) else np.asarray(group.attrs["scale"], np.float64).reshape(2)
+    if not sparse:
+        ids = [kDenseId]
+    name = group.name
+
+    def reader():
+        f = _h5py().File(str(cache_path), "r")
+        try:
+            return np.asarray(f[name]["patches"])
+        finally:
+            if hasattr(f, "close"):
+                f.close()
+
+    shape, dtype = tuple(ds.shape), np.dtype(ds.dtype)
+    return LazyFeatureMap(reader, shape[0], shape[1:], dtype, ids, corners, {"scale": scale, "is_sparse": sparse})
+
+
 def load_features_from_cache(cache_path, fill=True, level_prefix=""):
     """extract.py:218-222 / FeatureManager(path, fill, level_prefix): the cache file -> FeatureManager (numpy patches).
-    `fill=False` (load lazily) is what the reference uses to bound RAM; here patches are read at once."""
+    `fill=False` (what the reference's low-memory configuration uses, extractor.py:49 `load_cache_on_init`) reads the
+    metadata only: every map is a LazyFeatureMap that a FeatureView loads for the images it covers and drops again."""
     h5 = _h5py()
     f = h5.File(str(cache_path), "r")
     try:
@@ -124,7 +155,8 @@ def load_features_from_cache(cache_path, fill=True, level_prefix=""):
                 node = group[key]
                 name = prefix + key
                 if hasattr(node, "keys") and "format" in node.attrs:
-                    fset.emplace(name, _load_featuremap(node))
+                    fmap = None if fill else _lazy_featuremap(cache_path, node)
+                    fset.emplace(name, fmap if fmap is not None else _load_featuremap(node))
                 elif hasattr(node, "keys"):
                     collect(node, name + "/", fset)          # an image name with a directory part
 

@@ -82,6 +82,11 @@ class PixSfM:
             if "interpolation" not in conf.get(part, {}):
                 self.conf[part]["interpolation"] = to_conf(deepcopy(interpolation))
         self.extractor = extractor
+        # the reference builds its extractor FROM conf.dense_features (refine_colmap.py:52-56); here the extractor comes in
+        # from outside (the CNN is not part of this package), so the block is applied to it where it knows the option
+        known = getattr(extractor, "default_conf", None)
+        if isinstance(known, dict) and isinstance(getattr(extractor, "conf", None), dict):
+            extractor.conf.update({k: v for k, v in dict(self.conf["dense_features"]).items() if k in known})
         self.keypoint_adjuster = KeypointAdjuster.create(self.conf.KA)
         self.bundle_adjuster = BundleAdjuster.create(self.conf.BA)
 
@@ -94,6 +99,7 @@ class PixSfM:
 
     # ---------------------------------------------------------------------------------------- KA
     def run_ka(self, keypoints, image_dir, pairs, matches_scores, cache_path=None, feature_manager=None):
+        cache_path = self.resolve_cache_path(cache_path)
         graph = build_matching_graph(pairs, *matches_scores)
         if feature_manager is None:
             feature_manager = self._features("features_from_graph", image_dir, graph, keypoints, cache_path=cache_path)
@@ -102,6 +108,7 @@ class PixSfM:
 
     def refine_keypoints_from_db(self, output_path, database_path, image_dir=None, cache_path=None, feature_manager=None):
         output_path, database_path = Path(output_path), Path(database_path)
+        cache_path = self.resolve_cache_path(cache_path, output_path.parent)
         keypoints = read_keypoints_from_db(database_path)
         pairs, matches, scores = read_matches_from_db(database_path)
         keypoints, ka_data, feature_manager = self.run_ka(keypoints, image_dir, pairs, (matches, scores), cache_path,
@@ -113,6 +120,7 @@ class PixSfM:
 
     # ---------------------------------------------------------------------------------------- BA
     def run_ba(self, reconstruction, image_dir=None, cache_path=None, feature_manager=None):
+        cache_path = self.resolve_cache_path(cache_path)
         if feature_manager is None:
             feature_manager = self._features("features_from_reconstruction", reconstruction, image_dir, cache_path=cache_path)
         ba_data = self.bundle_adjuster.refine_multilevel(reconstruction, feature_manager)
@@ -122,6 +130,7 @@ class PixSfM:
         reconstruction = Reconstruction.read(input_path)
         logger.info("Loaded a model with %d images, %d points, %d observations.", len(reconstruction.images),
                     len(reconstruction.points3D), reconstruction.num_observations())
+        cache_path = self.resolve_cache_path(cache_path, Path(output_path))
         reconstruction, ba_data, feature_manager = self.run_ba(reconstruction, image_dir, cache_path=cache_path,
                                                                feature_manager=feature_manager)
         Path(output_path).mkdir(exist_ok=True, parents=True)
@@ -139,8 +148,9 @@ class PixSfM:
             cache_path = output_dir
         cache_path = Path(cache_path)
         if cache_path.suffix != ".h5":
-            model = feature_conf["model"] if isinstance(feature_conf, dict) else feature_conf.model
-            name = model["name"] if isinstance(model, dict) else model.name
+            model = feature_conf.get("model") if isinstance(feature_conf, dict) else getattr(feature_conf, "model", None)
+            name = (model["name"] if isinstance(model, dict) else getattr(model, "name", None)) if model is not None else None
+            name = name or getattr(self.extractor, "name", None) or "features"     # DenseFeatureExtractor wraps a callable
             sparse = feature_conf["sparse"] if isinstance(feature_conf, dict) else feature_conf.sparse
             cache_path = cache_path / "{}_featuremaps_{}.h5".format(name, "sparse" if sparse else "dense")
         return cache_path

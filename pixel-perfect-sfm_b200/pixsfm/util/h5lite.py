@@ -14,6 +14,7 @@ API (the slice of h5py the callers need):
     f = File(path, "r" | "w");  g = f["a/b"];  name in g;  g.keys();  g.create_group(name);  g.attrs[name]
     d = g.create_dataset(name, data=array, chunks=None | tuple);  d[...] / d[i] / np.asarray(d);  d.shape, d.dtype, d.attrs
     f.visititems(fn);  f.close() (writing happens at close)."""
+import mmap
 import struct
 import zlib
 
@@ -82,8 +83,12 @@ def _pad8(b):
 # ------------------------------------------------------------------------------------------------------------ reading
 class _Reader:
     def __init__(self, path):
+        # mapped, not read: a feature cache is tens of GB and a lazily filled FeatureManager touches a few patches of it
         with open(path, "rb") as fh:
-            self.buf = fh.read()
+            try:
+                self.buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            except (ValueError, OSError):              # empty file / a file system without mmap
+                self.buf = fh.read()
         b = self.buf
         base = b.find(_SIG)
         if base != 0:

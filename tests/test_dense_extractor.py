@@ -118,3 +118,66 @@ def test_extractor_places_patches_at_projections_and_feeds_the_driver(monkeypatc
     assert all(s.final_cost <= s.initial_cost for s in ba_data["summary"])
     with pytest.raises(ValueError, match="unknown extractor options"):
         DenseFeatureExtractor(None, None, {"patchsize": 8})
+
+
+def test_extractor_feature_cache(tmp_path):
+    """use_cache / overwrite_cache / load_cache_on_init as in the reference (features/extractor.py:46-49, extract.py:72-147):
+    a fresh extraction goes to the cache file and comes back through it; an existing file is taken as it is."""
+    from pixsfm._pixsfm._features import LazyFeatureMap
+    from recon_util import make_reconstruction
+    rec = make_reconstruction(n_cams=3, n_points=20, track_len=3, channels=8, seed=11)[0]
+    rng = np.random.default_rng(4)
+    maps = {im.name: [rng.normal(size=(8, 250, 250)).astype(np.float32)] for im in rec.images.values()}
+    calls = []
+
+    def model(name):
+        calls.append(name)
+        return maps[name]
+
+    plain = DenseFeatureExtractor(model, lambda name: (1000, 1000), {"patch_size": 8}).features_from_reconstruction(rec, "unused")
+    n_plain = len(calls)
+    ex = DenseFeatureExtractor(model, lambda name: (1000, 1000), {"patch_size": 8, "use_cache": True})
+    with pytest.raises(RuntimeError, match="no path given"):
+        ex.features_from_reconstruction(rec, "unused")
+    cache = tmp_path / "features.h5"
+    fm = ex.features_from_reconstruction(rec, "unused", cache_path=cache)
+    assert cache.exists() and len(calls) == 2 * n_plain
+    for name in plain.fset(0).keys():
+        a, b = plain.fset(0).fmap(name), fm.fset(0).fmap(name)
+        assert isinstance(b, LazyFeatureMap) and not b.is_loaded          # load_cache_on_init off: metadata only
+        assert a.point2D_ids == b.point2D_ids and np.array_equal(a.corners, b.corners) and np.array_equal(a.patches, b.patches)
+    again = ex.features_from_reconstruction(rec, "unused", cache_path=cache)
+    assert len(calls) == 2 * n_plain and sorted(again.fset(0).keys()) == sorted(plain.fset(0).keys())      # read, not extracted
+    filled = DenseFeatureExtractor(model, lambda name: (1000, 1000), {"patch_size": 8, "use_cache": True, "load_cache_on_init": True,
+                                                                     "overwrite_cache": True})
+    fm3 = filled.features_from_reconstruction(rec, "unused", cache_path=cache)
+    assert len(calls) == 3 * n_plain and not isinstance(next(iter(fm3.fset(0)._maps.values())), LazyFeatureMap)
+
+
+def test_low_memory_preset_configures_the_extractor_cache(tmp_path, monkeypatch):
+    """configs/low_memory.yaml: dense_features.use_cache / overwrite_cache / load_cache_on_init=false, patch_size 8 — the block
+    reaches the extractor, `refine_reconstruction` puts the cache next to its output (refine_colmap.py:120-145) and the
+    adjustment runs on the lazily filled manager."""
+    import test_mirror_with_oracle_solver as H
+    from pixsfm._pixsfm import _engine
+    from pixsfm._pixsfm._features import LazyFeatureMap
+    from pixsfm.refine_colmap import PixSfM
+    from recon_util import make_reconstruction
+    monkeypatch.setattr(_engine, "ba_run", H._ba_run)
+    monkeypatch.setattr(_engine, "refs_compute", H._refs_compute)
+    rec = make_reconstruction(n_cams=4, n_points=30, track_len=3, channels=16, seed=12)[0]
+    rng = np.random.default_rng(6)
+    maps = {im.name: [rng.normal(size=(16, 250, 250)).astype(np.float32)] for im in rec.images.values()}
+    ex = DenseFeatureExtractor(lambda name: maps[name], lambda name: (1000, 1000))
+    conf = {"dense_features": dict(sparse=True, dtype="half", use_cache=True, overwrite_cache=True, load_cache_on_init=False, patch_size=8),
+            "BA": {"optimizer": {"solver": {"max_num_iterations": 2}}}}
+    sfm = PixSfM(conf, extractor=ex)
+    assert ex.conf["patch_size"] == 8 and ex.conf["use_cache"] and not ex.conf["load_cache_on_init"]
+    (tmp_path / "in").mkdir()
+    rec.write(str(tmp_path / "in"))
+    out_rec, ba_data, fm = sfm.refine_reconstruction(tmp_path / "out", tmp_path / "in", "unused")
+    assert (tmp_path / "out" / "features_featuremaps_sparse.h5").exists()
+    maps0 = list(fm.fset(0)._maps.values())
+    assert all(isinstance(m, LazyFeatureMap) for m in maps0) and maps0[0].shape == (8, 8, 16)
+    assert not any(m.is_loaded for m in maps0)                   # the views of the adjustment have let go of the patches
+    assert ba_data["summary"][0].final_cost <= ba_data["summary"][0].initial_cost

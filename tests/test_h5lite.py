@@ -123,3 +123,61 @@ def test_dense_map_stored_once_is_read_back_as_patches(tmp_path):
     m = fm.fset(0).fmap("img.jpg")
     assert m.is_sparse and m.point2D_ids == [7, 8, 9] and m.patches.shape == (3, 16, 16, 8)
     assert np.array_equal(m.patches[1], dense[0, 10:26, 20:36])
+
+
+def test_lazy_cache_loads_per_feature_view_and_unloads(tmp_path):
+    """FeatureManager(path, fill=False) (extract.py:218-222, featuremap.h:43-71): metadata is resident, the patches of an
+    image arrive when a FeatureView covers it and leave with the view; the problem built from a lazily filled set is the
+    one built from the in-memory set."""
+    from pixsfm import features
+    from pixsfm._pixsfm import _bundle_adjustment as ba
+    from pixsfm._pixsfm._features import LazyFeatureMap
+    from pixsfm.features import store_features
+    from recon_util import make_reconstruction
+    rec, fm, _, _ = make_reconstruction(n_cams=5, n_points=30, track_len=3, channels=16, seed=4)
+    store_features.write_feature_manager_cache(tmp_path / "cache.h5", fm)
+    lazy = store_features.load_features_from_cache(tmp_path / "cache.h5", fill=False)
+    fset = lazy.fset(0)
+    maps = [fset.fmap(n) for n in fset.keys()]
+    assert len(maps) == 5 and all(isinstance(m, LazyFeatureMap) and not m.is_loaded for m in maps)
+    ref = fm.fset(0)
+    for name in ref.keys():                                   # metadata without a single patch read
+        a, b = ref.fmap(name), fset.fmap(name)
+        assert a.point2D_ids == b.point2D_ids and np.array_equal(a.corners, b.corners) and np.array_equal(a.scale, b.scale)
+        assert b.shape == a.shape and b.channels == 16 and b.dtype == a.dtype and b.size() == a.size() and b.has_point2D(0)
+    assert not any(m.is_loaded for m in maps)
+
+    class Two:                                                # a view over two of the five images
+        images = {i: rec.images[i] for i in (1, 2)}
+    with features.FeatureView(fset, Two) as view:
+        assert sorted(n for n in fset.keys() if fset.fmap(n).is_loaded) == ["image000.jpg", "image001.jpg"]
+        inner = features.FeatureView(fset, Two)               # a second user keeps the data when the first leaves
+        assert np.array_equal(view.get_feature_patch(1, 0).data, ref.fmap("image000.jpg").patches[0])
+    assert fset.fmap("image000.jpg").is_loaded
+    inner.close()
+    assert not any(m.is_loaded for m in maps)
+
+    full = features.FeatureView(fset, rec)
+    prob_lazy, _ = ba.build_problem(rec, full, None, None, None, for_references=set(rec.points3D.keys()))
+    prob_ref, _ = ba.build_problem(rec, features.FeatureView(ref, rec), None, None, None, for_references=set(rec.points3D.keys()))
+    assert np.array_equal(np.asarray(prob_lazy.patches), np.asarray(prob_ref.patches))
+    assert np.array_equal(prob_lazy.corner, prob_ref.corner) and np.array_equal(prob_lazy.obs_pt, prob_ref.obs_pt)
+    del prob_lazy
+    full.close()
+    assert not any(m.is_loaded for m in maps)
+    maps[0].lock()                                            # Lock(): resident for good
+    features.FeatureView(fset, rec).close()
+    assert maps[0].is_loaded and not any(m.is_loaded for m in maps[1:])
+
+
+def test_lazy_cache_falls_back_to_eager_maps_where_metadata_needs_the_data(tmp_path):
+    from pixsfm import features
+    from pixsfm._pixsfm._features import LazyFeatureMap
+    from pixsfm.features import store_features
+    rng = np.random.default_rng(5)
+    fm = features.FeatureManager([8], np.float16)
+    fm.fset(0).emplace("a.jpg", features.FeatureMap(rng.normal(size=(3, 4, 4, 8)).astype(np.float16), [1, 2, 5], np.zeros((3, 2), np.int32),
+                                                    {"scale": (1.0, 1.0), "is_sparse": True}))
+    store_features.write_feature_manager_cache(tmp_path / "g.h5", fm, "grouped")
+    got = store_features.load_features_from_cache(tmp_path / "g.h5", fill=False).fset(0).fmap("a.jpg")
+    assert not isinstance(got, LazyFeatureMap) and np.array_equal(got.patches, fm.fset(0).fmap("a.jpg").patches)
