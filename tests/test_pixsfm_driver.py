@@ -1,4 +1,6 @@
 """PixSfM (pixsfm/refine_colmap.py): configuration handling and the parts of the driver that need no device."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -88,7 +90,7 @@ def test_extractor_is_used_when_no_feature_manager_is_given():
         s.run_ba(object(), "imgs", cache_path="c.h5")
     with pytest.raises(RuntimeError):
         s.run_ka({"a": np.zeros((2, 2)), "b": np.zeros((2, 2))}, "imgs", [("a", "b")], ([np.array([[0, 1]], np.uint32)], None))
-    assert calls == [("rec", "imgs", "c.h5"), ("graph", 2, ["a", "b"])]
+    assert calls == [("rec", "imgs", Path("c.h5")), ("graph", 2, ["a", "b"])]     # resolve_cache_path hands on a Path
 
 
 def test_named_presets_and_reference_resolution(tmp_path):
