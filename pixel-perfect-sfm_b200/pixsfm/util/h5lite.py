@@ -15,6 +15,7 @@ API (the slice of h5py the callers need):
     d = g.create_dataset(name, data=array, chunks=None | tuple);  d[...] / d[i] / np.asarray(d);  d.shape, d.dtype, d.attrs
     f.visititems(fn);  f.close() (writing happens at close)."""
 import mmap
+import os
 import struct
 import zlib
 
@@ -484,8 +485,11 @@ class _Writer:
         sb += struct.pack("<QQQQ", 0, UNDEF, len(self.buf), UNDEF)
         sb += struct.pack("<QQII", 0, root_addr, 1, 0) + struct.pack("<QQ", btree, heap)
         self.buf[:len(sb)] = sb
-        with open(path, "wb") as fh:
+        # a new inode, moved into place: a reader that still has the old file mapped keeps seeing the old bytes
+        tmp = "%s.tmp%d" % (path, os.getpid())
+        with open(tmp, "wb") as fh:
             fh.write(bytes(self.buf))
+        os.replace(tmp, path)
 
     # -- messages / headers
     @staticmethod
