@@ -682,6 +682,47 @@ def _loss_id_scale(loss):
     return _capi.LOSS_IDS[name], float(params[0]) if params else 1.0
 
 
+def slice_dense_maps(feature_set, reconstruction, point3D_ids, cut_size):
+    """Dense feature maps -> one `cut_size` x `cut_size` window per observation of `point3D_ids`, cut around the CURRENT
+    reprojection: what the reference's cost-map extractor does with dense maps (costmap_extractor.h:207-222 `Slice(xy,
+    dense_cut_size)`, :398-428; the corner rule is FeaturePatch::ToCorner, featurepatch.cc:324-336: truncate
+    `uv - cut/2` towards zero, clamp to [0, size - cut]).  Sparse maps pass through.  The windows hold the same taps as the
+    map they are cut from around the projection, edge clamping included, so references extracted from them equal the ones
+    extracted from the dense map."""
+    from ._features import DevicePatches, FeatureMap, FeatureSet
+    from ..util.cameras import world_to_image
+    cut = int(cut_size)
+    out = FeatureSet(feature_set.channels, feature_set.dtype)
+    ids = set(point3D_ids)
+    for image in reconstruction.images.values():
+        if not feature_set.has_fmap(image.name):
+            continue
+        fmap = feature_set.fmap(image.name)
+        if fmap.is_sparse:
+            out.emplace(image.name, fmap)
+            continue
+        sel = [k for k, p in enumerate(image.points2D) if p.has_point3D() and p.point3D_id in ids]
+        if not sel:
+            continue
+        if isinstance(fmap.patches, DevicePatches):
+            raise ValueError("cost maps from device-resident dense maps are not built (the windows are cut on the host)")
+        k0 = fmap.local_index(0)
+        dense = fmap.patches[k0]                                   # [H, W, C]
+        height, width = dense.shape[:2]
+        if height < cut or width < cut:
+            raise ValueError("dense_cut_size %d exceeds the %dx%d feature map of %s" % (cut, width, height, image.name))
+        cam = reconstruction.cameras[image.camera_id]
+        xyz = np.array([reconstruction.points3D[image.points2D[k].point3D_id].xyz for k in sel])
+        xy = world_to_image(cam.model_id, cam.params, image.qvec, image.tvec, xyz)
+        uv = xy * fmap.scale - 0.5 - fmap.corners[k0]
+        corners = np.trunc(uv - cut / 2.0).astype(np.int64)
+        corners = np.minimum(np.maximum(corners, 0), np.array([width - cut, height - cut]))
+        windows = np.stack([dense[c[1]:c[1] + cut, c[0]:c[0] + cut] for c in corners])
+        out.emplace(image.name, FeatureMap(np.ascontiguousarray(windows), sel, (corners + fmap.corners[k0]).astype(np.int32),
+                                           {"scale": fmap.scale, "is_sparse": True}))
+    return out
+
+
 class CostMapExtractor:
     """_bundle_adjustment.CostMapExtractor(CostMapConfig|dict, InterpolationConfig|dict)
     .run(problem_labels, reconstruction, feature_set, ref_extractor) -> (costmap FeatureSet, {point3D_id: Reference})
@@ -700,6 +741,9 @@ class CostMapExtractor:
             raise ValueError("a ReferenceExtractor is required (the references are computed in the same pass)")
         from ._features import FeatureMap, FeatureSet
         ids = {p for p in reconstruction.points3D.keys() if p < len(problem_labels) and problem_labels[p] >= 0}
+        if hasattr(feature_set, "fmap") and any(not feature_set.fmap(name).is_sparse for name in feature_set.keys()):
+            # dense maps: a dense_cut_size window per observation around its reprojection (costmap_extractor.h:186-224)
+            feature_set = slice_dense_maps(feature_set, reconstruction, ids, self.config.dense_cut_size)
         fview = FeatureView(feature_set, reconstruction)
         prob, ir = build_problem(reconstruction, fview, None, None, None, for_references=ids)
         refs = {p: Reference() for p in ids}
@@ -717,7 +761,7 @@ class CostMapExtractor:
         ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
         if any(not (feature_set.fmap(name) if hasattr(feature_set, "fmap") else feature_set[name]).is_sparse
                for name in ir.slab_offsets):
-            raise ValueError("cost maps from dense feature maps (dense_cut_size slicing, costmap_extractor.h:186-200) are not built")
+            raise ValueError("cost maps need sparse feature maps or a FeatureSet of dense ones (dense_cut_size slicing)")
         out = _engine.costmaps_compute(prob, ic, cfg)
         for k, pid in enumerate(ir.point_ids):
             if out["src_obs"][k] < 0:

@@ -187,8 +187,6 @@ def test_dense_feature_maps_match_oracle():
     assert abs(s.initial_cost - s_o["initial_cost"]) <= 1e-10 * s_o["initial_cost"]
     # random (unmatched) feature fields make a badly conditioned problem: rounding differences grow along the LM path
     assert abs(s.final_cost - s_o["final_cost"]) <= 1e-4 * s_o["final_cost"]
-    with pytest.raises(ValueError):
-        ba_pkg.BundleAdjuster.create({"strategy": "costmaps"}).refine_multilevel(copy.deepcopy(rec), fm)
 
 
 def test_keypoint_adjustment_from_a_colmap_database(tmp_path):

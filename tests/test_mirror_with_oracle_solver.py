@@ -273,3 +273,53 @@ def test_patch_interpolator_surface(monkeypatch):
     assert np.abs(raw[0] - data[5, 3].astype(np.float64)).max() < 1e-6         # at a pixel centre the spline interpolates
     with pytest.raises(ValueError):
         features.PatchInterpolator({"nodes": [[0, 0], [1, 0]]}).interpolate(patch, xy)
+
+
+def test_costmaps_from_dense_feature_maps(oracle_engine):
+    """The cost-map strategy on DENSE feature maps (costmap_extractor.h:186-224, 398-428): a dense_cut_size window per
+    observation around its reprojection (corner rule: FeaturePatch::ToCorner), references as from the dense map itself."""
+    import copy
+    from pixsfm import bundle_adjustment as ba_pkg, features
+    from pixsfm._pixsfm import _bundle_adjustment as ba
+    from pixsfm.util import cameras
+    from recon_util import make_reconstruction
+    rec, fm_sparse, _, _ = make_reconstruction(n_cams=5, n_points=40, track_len=3, channels=16, seed=41)
+    rng = np.random.default_rng(7)
+    H = W = 72
+    fm = features.FeatureManager([16], np.float16)
+    for name in fm_sparse.fset(0).keys():
+        base_f = rng.normal(size=(H // 8 + 2, W // 8 + 2, 16))          # a smooth random field
+        yy, xx = np.meshgrid(np.linspace(1, H // 8, H), np.linspace(1, W // 8, W), indexing="ij")
+        y0, x0 = yy.astype(int), xx.astype(int)
+        fy, fx = (yy - y0)[..., None], (xx - x0)[..., None]
+        dense = ((1 - fy) * (1 - fx) * base_f[y0, x0] + (1 - fy) * fx * base_f[y0, x0 + 1]
+                 + fy * (1 - fx) * base_f[y0 + 1, x0] + fy * fx * base_f[y0 + 1, x0 + 1]).astype(np.float16)
+        fm.fset(0).emplace(name, features.FeatureMap(np.ascontiguousarray(dense[None]), [features.kDenseId], np.zeros((1, 2), np.int32),
+                                                     {"scale": (W / 1000.0, H / 1000.0), "is_sparse": False}))
+    rec0 = copy.deepcopy(rec)
+    cut = 12
+    conf = {"strategy": "costmaps", "costmaps": {"dense_cut_size": cut}, "optimizer": {"solver": {"max_num_iterations": 6}}}
+    out = ba_pkg.BundleAdjuster.create(conf).refine_multilevel(rec, fm)
+    s, cmaps, refs = out["summary"][0], out["costmaps"][0], out["references"][0]
+    assert s.final_cost < s.initial_cost and cmaps.channels == 3
+    for image in rec0.images.values():
+        cm = cmaps.fmap(image.name)
+        seen = [k for k, p in enumerate(image.points2D) if p.has_point3D()]
+        assert cm.is_sparse and cm.point2D_ids == seen and cm.shape == (cut, cut, 3)
+        cam = rec0.cameras[image.camera_id]
+        xy = cameras.world_to_image(cam.model_id, cam.params, image.qvec, image.tvec,
+                                    np.array([rec0.points3D[image.points2D[k].point3D_id].xyz for k in seen]))
+        uv = xy * np.array([W / 1000.0, H / 1000.0]) - 0.5
+        want = np.clip(np.trunc(uv - cut / 2.0), 0, [W - cut, H - cut]).astype(np.int32)       # ToCorner, featurepatch.cc:324-336
+        assert np.array_equal(cm.corners, want)
+        assert ((uv - want >= 1.0) | (want == 0)).all() and ((uv - want <= cut - 2.0) | (want == W - cut)).all()
+    # the references are those of the dense maps themselves
+    dense_refs = ba.ReferenceExtractor({"iters": 100, "keep_observations": False}, {}).run(
+        [0] * (max(rec0.points3D.keys()) + 1), rec0, fm.fset(0))
+    for pid, r in dense_refs.items():
+        assert refs[pid].source == r.source and np.abs(refs[pid].descriptor - r.descriptor).max() < 1e-12
+    # and the windows hold the map's own values
+    sliced = ba.slice_dense_maps(fm.fset(0), rec0, set(rec0.points3D.keys()), cut)
+    name = next(iter(fm.fset(0).keys()))
+    win, c = sliced.fmap(name).patches[3], sliced.fmap(name).corners[3]
+    assert np.array_equal(win, fm.fset(0).fmap(name).patches[0][c[1]:c[1] + cut, c[0]:c[0] + cut])
