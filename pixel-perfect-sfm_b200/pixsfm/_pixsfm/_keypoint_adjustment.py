@@ -122,11 +122,15 @@ class FeatureMetricKeypointOptimizer:
         kidx = {n: k for k, n in enumerate(used)}
         kps = np.zeros((len(used), 2)); kconst = np.zeros(len(used), np.uint8); kpatch = np.zeros(len(used), np.int64)
         sparse = True
+        held = {}    # lazily filled maps (fill=False caches): resident from here to the end of the solve, like the
+                     # FeatureView every problem of the reference's RunParallel builds and drops (featureview.cc:70-126)
         for n in used:
             name, fidx = kp_of(n)
             if not feature_set.has_fmap(name) or not feature_set.fmap(name).has_point2D(fidx):
                 raise ValueError("no feature patch for keypoint (%s, %d)" % (name, fidx))
             fmap = feature_set.fmap(name)
+            if name not in held and hasattr(fmap, "unload"):
+                held[name] = fmap.load()
             sparse = sparse and fmap.is_sparse
             kps[kidx[n]] = keypoints[name][fidx]
             kconst[kidx[n]] = 1 if self.setup.is_node_constant(graph.nodes[n]) else 0
@@ -143,7 +147,11 @@ class FeatureMetricKeypointOptimizer:
             raise ValueError("Unsupported dimensions (CHANNELS,N_NODES).")
         so = solver_options_from(opt.loss, opt.solver, _capi.default_ka_options(parameter_tolerance=1e-4))
         ic = _capi.default_interp(self.interp.l2_normalize, self.interp.use_float_simd)
-        s = _engine.ka_run(prob, ic, so)
+        try:
+            s = _engine.ka_run(prob, ic, so)
+        finally:
+            for fmap in held.values():
+                fmap.unload()
         for n in used:   # keypoints are refined in place
             name, fidx = kp_of(n)
             keypoints[name][fidx] = prob.keypoints[kidx[n]]

@@ -323,3 +323,35 @@ def test_costmaps_from_dense_feature_maps(oracle_engine):
     name = next(iter(fm.fset(0).keys()))
     win, c = sliced.fmap(name).patches[3], sliced.fmap(name).corners[3]
     assert np.array_equal(win, fm.fset(0).fmap(name).patches[0][c[1]:c[1] + cut, c[0]:c[0] + cut])
+
+
+def test_keypoint_adjustment_on_a_lazily_filled_cache(oracle_engine, tmp_path):
+    """KA on FeatureManager(path, fill=False): the maps a solve touches are resident for its duration only, and the refined
+    keypoints are the ones the in-memory manager gives."""
+    import copy
+    from pixsfm import base, features, keypoint_adjustment as ka_pkg
+    from pixsfm.features import store_features
+    from pixsfm.util import synthetic
+    sc = synthetic.make_ka_scene(n_images=5, n_tracks=30, track_len=3, channels=16, seed=5, kp_sigma=1.0)
+    g = base.Graph()
+    names = ["im%d" % i for i in range(5)]
+    keypoints = {names[i]: np.ascontiguousarray(sc["keypoints"][sc["node_image"] == i]) for i in range(5)}
+    for n in range(len(sc["node_image"])):
+        g.add_node(names[sc["node_image"][n]], int(sc["node_feature"][n]))
+    for e in range(len(sc["edge_src"])):
+        g.add_edge(g.nodes[sc["edge_src"][e]], g.nodes[sc["edge_dst"][e]], sc["edge_sim"][e])
+    fm = features.FeatureManager([16], np.float16)
+    for i in range(5):
+        m = np.where(sc["node_image"] == i)[0]
+        fm.fset(0).emplace(names[i], features.FeatureMap(np.ascontiguousarray(sc["patches"][m]), sc["node_feature"][m].tolist(),
+                                                          sc["corner"][m], {"scale": sc["scale"][m[0]], "is_sparse": True}))
+    store_features.write_feature_manager_cache(tmp_path / "ka.h5", fm)
+    lazy = store_features.load_features_from_cache(tmp_path / "ka.h5", fill=False)
+    kp_a, kp_b = copy.deepcopy(keypoints), copy.deepcopy(keypoints)
+    conf = {"max_kps_per_problem": 20}
+    ka_pkg.KeypointAdjuster.create(conf).refine_multilevel(kp_a, fm, g)
+    ka_pkg.KeypointAdjuster.create(conf).refine_multilevel(kp_b, lazy, g)
+    assert any(np.abs(kp_a[n] - keypoints[n]).max() > 1e-3 for n in names)
+    for name in names:
+        assert np.array_equal(kp_a[name], kp_b[name])
+    assert not any(m.is_loaded for m in lazy.fset(0)._maps.values())
