@@ -199,6 +199,40 @@ def test_world_to_pixel_known_values():
         assert np.allclose(xy, [cp[0] * (u + u * rad) + cp[1], cp[0] * (v + v * rad) + cp[2]], atol=1e-9)
 
 
+# --- (vi-b) the camera models on the parameter vectors and the [-0.5, 0.5]^2 grid of the reference's undistortion_test.cc:
+# 67-101 (SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL; WorldToImage then back to the normalised point to 1e-6, :15-27).
+# The inverse is a Newton iteration written here; the oracle and the Python restatement must both be the forward map.
+@pytest.mark.parametrize("model,params", [
+    (0, [655.123, 386.123, 511.123]), (1, [651.123, 655.123, 386.123, 511.123]),
+    (2, [651.123, 386.123, 511.123, 0.0]), (2, [651.123, 386.123, 511.123, 0.1]),
+    (3, [651.123, 386.123, 511.123, 0.0, 0.0]), (3, [651.123, 386.123, 511.123, 0.1, 0.0]),
+    (3, [651.123, 386.123, 511.123, 0.05, 0.0]), (3, [651.123, 386.123, 511.123, 0.05, 0.03])])
+def test_world_to_image_round_trip_on_the_reference_grid(model, params):
+    from pixsfm.util import cameras
+    cp = np.zeros(12); cp[:len(params)] = params
+    q = np.array([1.0, 0, 0, 0]); t = np.zeros(3); xy = np.zeros(2)
+    fx = params[0]; fy = params[1] if model == 1 else params[0]
+    cx, cy = (params[2], params[3]) if model == 1 else (params[1], params[2])
+    k1 = params[3] if model in (2, 3) else 0.0
+    k2 = params[4] if model == 3 else 0.0
+    for u0 in np.arange(-0.5, 0.5001, 0.1):
+        for v0 in np.arange(-0.5, 0.5001, 0.1):
+            O.lib().orc_world_to_pixel(model, p(cp), p(q), p(t), p(np.array([u0, v0, 1.0])), p(xy))
+            py = cameras.world_to_image(model, np.asarray(params), q, t, np.array([[u0, v0, 1.0]]))[0]
+            assert np.abs(py - xy).max() < 1e-10
+            # back: undo the affine part, then solve d(u, v) = (u, v)(1 + k1 r^2 + k2 r^4) for (u, v)
+            xd, yd = (xy[0] - cx) / fx, (xy[1] - cy) / fy
+            u, v = xd, yd
+            for _ in range(50):
+                r2 = u * u + v * v
+                s = 1 + k1 * r2 + k2 * r2 * r2
+                ds = 2 * k1 + 4 * k2 * r2
+                J = np.array([[s + u * u * ds, u * v * ds], [u * v * ds, s + v * v * ds]])
+                step = np.linalg.solve(J, np.array([u * s - xd, v * s - yd]))
+                u, v = u - step[0], v - step[1]
+            assert abs(u - u0) < 1e-6 and abs(v - v0) < 1e-6
+
+
 def test_loss_functions_derivatives():
     rho = np.zeros(3); rp = np.zeros(3); rm = np.zeros(3)
     for t in range(5):
