@@ -181,3 +181,30 @@ def test_lazy_cache_falls_back_to_eager_maps_where_metadata_needs_the_data(tmp_p
     store_features.write_feature_manager_cache(tmp_path / "g.h5", fm, "grouped")
     got = store_features.load_features_from_cache(tmp_path / "g.h5", fill=False).fset(0).fmap("a.jpg")
     assert not isinstance(got, LazyFeatureMap) and np.array_equal(got.patches, fm.fset(0).fmap("a.jpg").patches)
+
+
+def test_references_cache_round_trip(tmp_path):
+    """features/store_references.py:14-58: one {point3D_id: Reference} map per level, observations and empty tracks included"""
+    from pixsfm import features
+    from pixsfm.features import store_references
+    rng = np.random.default_rng(8)
+    levels = []
+    for lvl, ch in enumerate((16, 8)):
+        refs = {}
+        for pid in (3, 11, 400):
+            r = features.Reference((pid % 7 + 1, pid % 5), rng.normal(size=(1, ch)))
+            if pid != 11:
+                r.observations = [rng.normal(size=(1, ch)) for _ in range(3)]
+                r.costs = [0.1 * k for k in range(3)]
+                r.track = [(1, 4), (2, 0), (5, 9)]
+            refs[pid] = r
+        levels.append(refs)
+    store_references.write_references_cache(tmp_path / "refs.h5", levels)
+    got = store_references.load_references_from_cache(tmp_path / "refs.h5")
+    assert len(got) == 2 and all(sorted(g) == [3, 11, 400] for g in got)
+    for a_map, b_map in zip(levels, got):
+        for pid, a in a_map.items():
+            b = b_map[pid]
+            assert b.source == a.source and np.array_equal(a.descriptor, b.descriptor) and b.descriptor.dtype == np.float64
+            assert len(b.observations) == len(a.observations) and all(np.array_equal(x, y) for x, y in zip(a.observations, b.observations))
+            assert b.costs == [float(c) for c in a.costs] and b.track == (a.track or [])
