@@ -55,5 +55,9 @@ def query_bundle_adjustment():
 
 
 def query_localizer():
-    return dict(interpolation=interpolation(), target_reference="nearest", unique_inliers="min_error",
-                QKA=query_keypoint_adjustment(), QBA=query_bundle_adjustment())
+    # localization/main.py:262-299 (dense_features: the options of the extractor handed in, see features/extractor.py)
+    return dict(dense_features={}, overwrite_features_sparse=None, interpolation=interpolation(), target_reference="nearest",
+                unique_inliers="min_error",
+                references=dict(loss=dict(name="cauchy", params=[0.25]), iters=100, keep_observations=True, num_threads=-1),
+                max_tracks_per_problem=50, QKA=query_keypoint_adjustment(),
+                PnP=dict(estimation=dict(ransac=dict(max_error=12)), refinement={}), QBA=query_bundle_adjustment())

@@ -118,54 +118,172 @@ class QueryBundleAdjuster:
                         point2D_idxs=point2D_idxs)
 
 
+def compute_reprojection_errors(pnp_points2D, pnp_points3D, qvec, tvec, camera):
+    """pixel distance between every 2D point and the projection of its 3D point (reference main.py:96-102)"""
+    from ..util.cameras import world_to_image
+    xyz = np.array([np.asarray(getattr(p, "xyz", p), np.float64) for p in pnp_points3D]).reshape(-1, 3)
+    proj = world_to_image(camera.model_id, np.asarray(camera.params, np.float64), np.asarray(qvec, np.float64),
+                          np.asarray(tvec, np.float64), xyz)
+    return [float(np.linalg.norm(proj[i] - np.asarray(p2D, np.float64))) for i, p2D in enumerate(pnp_points2D)]
+
+
+def find_unique_min_reproj_inliers(pnp_points3D_id, qvec, tvec, camera, pnp_points2D, rec, pre_inliers=None, point2D_idxs=None):
+    """of the correspondences that share a 3D point, then of those that share a keypoint, keep the one with the smallest
+    reprojection error under the PnP pose (reference main.py:81-93)"""
+    p3Ds = [rec.points3D[p3D_id] for p3D_id in pnp_points3D_id]
+    errors = compute_reprojection_errors(pnp_points2D, p3Ds, qvec, tvec, camera)
+    inliers = pre_inliers
+    for idxs in (pnp_points3D_id, point2D_idxs):
+        if idxs is None:
+            continue
+        inliers = find_unique_min_by_group(errors, idxs, pre_inliers=inliers)
+    return inliers
+
+
 class QueryLocalizer:
-    """QKA -> PnP -> QBA for one query image (reference localization/main.py:262-537).  Holds the reconstruction and
-    one {point3D_id: Reference} map per feature level.  The absolute-pose estimator is a callable
-    `pose_estimator(points2D [N,2], points3D [N,3], camera) -> dict(success, qvec, tvec, inliers)` — the reference uses
-    pycolmap.absolute_pose_estimation, which is outside this package."""
+    """QKA -> PnP -> QBA for one query image (reference localization/main.py:262-537), with the reference's constructor
+    and `localize` signatures.  Holds the reconstruction and one {point3D_id: Reference} map per feature level: given
+    (`references=`), or extracted at construction from `dense_features` (a FeatureManager, or the path of a feature cache)
+    or from features the `extractor` computes for `image_dir`.  The absolute-pose step is pycolmap.absolute_pose_estimation
+    when pycolmap imports; `pose_estimator(points2D [N,2], points3D [N,3], camera) -> dict(success, qvec, tvec, inliers)`
+    replaces it (pycolmap is outside this package)."""
     default_conf = defaults.query_localizer()
 
-    def __init__(self, reconstruction, conf=None, references=None, pose_estimator=None):
+    def __init__(self, reconstruction, conf=None, dense_features=None, image_dir=None, references=None, extractor=None,
+                 pose_estimator=None):
+        from pathlib import Path
+        from .. import bundle_adjustment as ba_pkg
+        from .._pixsfm import _bundle_adjustment as ba
+        if isinstance(conf, (str, Path)):
+            from ..refine_colmap import _load_conf
+            conf = _load_conf(conf)
+        if isinstance(conf, dict) and isinstance(conf.get("localization"), dict):
+            conf = conf["localization"]
         self.conf = merge(self.default_conf, conf or {})
-        self.reconstruction = reconstruction
-        if references is None:
-            raise ValueError("references (one {point3D_id: Reference} map per level) are required")
-        self.references = references
+        if self.conf.QKA.stack_correspondences and self.conf.target_reference not in ("nearest", "robust_mean"):
+            raise ValueError("Stacked QKA requires a np.ndarray reference for each 2D-3D correspondence. Consider setting "
+                             "target_references to 'nearest' or 'robust_mean'.")
+        self.query_keypoint_adjuster = QueryKeypointAdjuster(to_ctr(self.conf.QKA))
+        self.query_bundle_adjuster = QueryBundleAdjuster(to_ctr(self.conf.QBA))
+        self.extractor = extractor
         self.pose_estimator = pose_estimator
+        self.reference_extractor = ba.ReferenceExtractor(to_ctr(self.conf.references), to_ctr(self.conf.interpolation))
+        self.target_reference_funcs = {"nearest": self.get_nearest_references, "robust_mean": self.get_robust_mean_references,
+                                       "all_observations": self.get_all_references, "full": self.get_full_references}
+        if self.conf.target_reference not in self.target_reference_funcs:
+            raise ValueError("unknown target_reference %r" % (self.conf.target_reference,))
+        self.get_query_references = self.target_reference_funcs[self.conf.target_reference]
+        self.references = references
+        if self.references is None and (self.conf.QKA.apply or self.conf.QBA.apply):
+            cache_path = None
+            if isinstance(dense_features, (str, Path)):
+                cache_path = Path(dense_features)
+                if cache_path.exists():
+                    from ..features.store_features import load_features_from_cache
+                    dense_features = load_features_from_cache(cache_path)
+                else:
+                    dense_features = None
+            if dense_features is None:
+                if image_dir is None or self.extractor is None:
+                    raise ValueError("references (one {point3D_id: Reference} map per level), dense_features, or an extractor "
+                                     "together with image_dir are required")
+                dense_features = self.extractor.features_from_reconstruction(reconstruction, image_dir, cache_path=cache_path)
+            labels = ba_pkg.find_problem_labels(reconstruction, self.conf.max_tracks_per_problem)
+            self.references = [self.reference_extractor.run(labels, reconstruction, dense_features.fset(i))
+                               for i in range(dense_features.num_levels)]
+        self.reconstruction = reconstruction
 
-    def _target_references(self, level, fmap, keypoints, point3D_ids, point2D_idxs):
-        refs = self.references[level]
-        if self.conf.target_reference == "nearest":
-            return loc.find_nearest_references(fmap, refs, keypoints, point3D_ids, to_ctr(self.conf.interpolation), point2D_idxs)
-        if self.conf.target_reference == "robust_mean":
-            return [refs[p] for p in point3D_ids]
-        if self.conf.target_reference == "all_observations":
-            return [[np.asarray(o) for o in refs[p].observations] for p in point3D_ids]
-        raise ValueError("unknown target_reference %r" % (self.conf.target_reference,))
+    # ---- the reference descriptors a query's correspondences are compared with, one list per level (main.py:499-537)
+    def get_nearest_references(self, pnp_points3D_id, query_fmaps, pnp_points2D, patch_idxs):
+        return [loc.find_nearest_references(query_fmaps[level], refs, pnp_points2D, pnp_points3D_id,
+                                            to_ctr(self.conf.interpolation), patch_idxs)
+                for level, refs in enumerate(self.references)]
 
-    def localize(self, pnp_points2D, pnp_point3D_ids, query_camera, query_fmaps, pnp_point2D_idxs=None, pose_estimator=None):
-        keypoints = np.ascontiguousarray(pnp_points2D, np.float64).copy()
-        levels = resolve_level_indices(self.conf.QKA.level_indices, len(query_fmaps))
-        if self.conf.QKA.apply:
-            qka = QueryKeypointAdjuster(to_ctr(self.conf.QKA))
-            for level in levels:
-                refs = self._target_references(level, query_fmaps[level], keypoints, pnp_point3D_ids, pnp_point2D_idxs)
-                qka.refine(keypoints, query_fmaps[level], refs, point2D_idxs=pnp_point2D_idxs)
+    def get_robust_mean_references(self, pnp_points3D_id, *args):
+        return [[np.asarray(refs[p3D_id].descriptor, np.float64) for p3D_id in pnp_points3D_id] for refs in self.references]
+
+    def get_all_references(self, pnp_points3D_id, *args):
+        out = []
+        for refs in self.references:
+            level = []
+            for p3D_id in pnp_points3D_id:
+                if not len(refs[p3D_id].observations):
+                    raise RuntimeError("Missing descriptors for observations.\nAssure that references.keep_observations==True.")
+                level.append([np.asarray(o) for o in refs[p3D_id].observations])
+            out.append(level)
+        return out
+
+    def get_full_references(self, pnp_points3D_id, *args):
+        return [[refs[p3D_id] for p3D_id in pnp_points3D_id] for refs in self.references]
+
+    def _query_features(self, image_path, keypoints, required_kp_ids):
+        """the patches of the query image around the keypoints that take part in a correspondence (main.py:432-439)"""
+        if self.extractor is None:
+            raise ValueError("query_fmaps or an extractor (with image_path) are required")
+        name = str(image_path)
+        manager = self.extractor.features_from_image_list(None, [name], {name: keypoints}, {name: required_kp_ids})
+        return [manager.fset(level).fmap(name) for level in range(manager.num_levels)]
+
+    def _absolute_pose(self, pnp_points2D, pnp_points3D, query_camera, pose_estimator):
         estimator = pose_estimator or self.pose_estimator
-        if estimator is None:
-            raise ValueError("a pose_estimator callable is required (pycolmap.absolute_pose_estimation is not bundled)")
-        points3D = [np.asarray(self.reconstruction.points3D[p].xyz, np.float64) for p in pnp_point3D_ids]
-        pose = estimator(keypoints, np.array(points3D), query_camera)
-        if not pose.get("success", False):
-            return pose
+        if estimator is not None:
+            return estimator(pnp_points2D, np.array(pnp_points3D), query_camera)
+        try:
+            import pycolmap
+        except ImportError:
+            raise ValueError("a pose_estimator callable is required (pycolmap.absolute_pose_estimation is not importable)")
+        return pycolmap.absolute_pose_estimation(pnp_points2D, pnp_points3D, query_camera,
+                                                 estimation_options=to_ctr(self.conf.PnP.estimation),
+                                                 refinement_options=to_ctr(self.conf.PnP.refinement))
+
+    def localize(self, keypoints, pnp_point2D_idxs, pnp_points3D_id, query_camera, image_path=None, query_fmaps=None,
+                 pose_estimator=None):
+        """reference main.py:414-497.  `keypoints` [K,2] are the query image's keypoints, correspondence k pairs keypoint
+        `pnp_point2D_idxs[k]` with 3D point `pnp_points3D_id[k]`.  Returns the pose dict of the PnP step with the refined
+        pose, `inliers` / `num_inliers` recomputed from it, and (an addition) `keypoints`: the refined 2D points of the
+        correspondences."""
+        if len(pnp_point2D_idxs) != len(pnp_points3D_id):
+            raise ValueError("one 3D point id per 2D index is required")
+        if image_path is None and query_fmaps is None:
+            raise ValueError("image_path or query_fmaps are required")
+        if len(pnp_point2D_idxs) == 0:
+            return {"success": False}
+        pnp_point2D_idxs = [int(i) for i in pnp_point2D_idxs]
+        pnp_points3D = [np.asarray(self.reconstruction.points3D[p3D_id].xyz, np.float64) for p3D_id in pnp_points3D_id]
+        keypoints = np.array(keypoints, dtype=np.float64)
+        require_feats = bool(self.conf.QKA.apply or self.conf.QBA.apply)
+        if query_fmaps is None and require_feats:
+            query_fmaps = self._query_features(image_path, keypoints, sorted(set(pnp_point2D_idxs)))
+        pnp_points2D = keypoints[pnp_point2D_idxs]           # a copy: QKA refines the correspondences' points
+        query_references = None
+        if require_feats:
+            query_references = self.get_query_references(pnp_points3D_id, query_fmaps, pnp_points2D, pnp_point2D_idxs)
+            if len(query_fmaps) != len(query_references):
+                raise ValueError("one reference map per feature level is required")
+        if self.conf.QKA.apply:
+            self.query_keypoint_adjuster.refine_multilevel(pnp_points2D, query_fmaps, query_references,
+                                                           point2D_idxs=pnp_point2D_idxs)
+        pose_dict = self._absolute_pose(pnp_points2D, pnp_points3D, query_camera, pose_estimator)
+        if not pose_dict.get("success", False):
+            return pose_dict
+        inliers = pose_dict.get("inliers", [True] * len(pnp_points3D))
+        if self.conf.unique_inliers:                          # None / False: keep what PnP says
+            if self.conf.unique_inliers == "random":
+                inliers = find_unique_inliers(pnp_points3D_id, pre_inliers=inliers)
+            elif self.conf.unique_inliers == "min_error":
+                inliers = find_unique_min_reproj_inliers(pnp_points3D_id, pose_dict["qvec"], pose_dict["tvec"], query_camera,
+                                                         pnp_points2D, self.reconstruction, pre_inliers=inliers,
+                                                         point2D_idxs=pnp_point2D_idxs)
+            else:
+                from .. import logger
+                logger.warning("Unknown unique_inlier method %s.", self.conf.unique_inliers)
         if self.conf.QBA.apply:
-            inliers = list(pose.get("inliers", [True] * len(points3D)))
-            if self.conf.unique_inliers == "min_error" and pnp_point2D_idxs is not None:
-                inliers = find_unique_inliers(pnp_point2D_idxs, pre_inliers=inliers)
-            qba = QueryBundleAdjuster(to_ctr(self.conf.QBA))
-            for level in resolve_level_indices(self.conf.QBA.level_indices, len(query_fmaps)):
-                refs = self._target_references(level, query_fmaps[level], keypoints, pnp_point3D_ids, pnp_point2D_idxs)
-                qba.refine(pose["qvec"], pose["tvec"], query_camera, points3D, query_fmaps[level], refs, inliers=inliers,
-                           point2D_idxs=pnp_point2D_idxs)
-        pose["keypoints"] = keypoints
-        return pose
+            self.query_bundle_adjuster.refine_multilevel(pose_dict["qvec"], pose_dict["tvec"], query_camera, pnp_points3D,
+                                                         query_fmaps, query_references, inliers=list(inliers),
+                                                         point2D_idxs=pnp_point2D_idxs)
+        errors = compute_reprojection_errors(pnp_points2D, pnp_points3D, pose_dict["qvec"], pose_dict["tvec"], query_camera)
+        max_error = self.conf.PnP.estimation.ransac.max_error
+        pose_dict["inliers"] = [err < max_error for err in errors]
+        pose_dict["num_inliers"] = sum(pose_dict["inliers"])
+        pose_dict["keypoints"] = pnp_points2D
+        return pose_dict

@@ -123,7 +123,9 @@ def test_query_localizer_runs_qka_pnp_qba():
 
     ql = loc_pkg.QueryLocalizer(rec, {"target_reference": "robust_mean"}, references=[refs], pose_estimator=pnp)
     noisy = kps + rng.normal(0, 0.7, kps.shape)
-    out = ql.localize(noisy, p3D_ids, cam, [fmap], pnp_point2D_idxs=p2D_idxs)
+    all_kps = np.zeros((max(p2D_idxs) + 1, 2)); all_kps[list(p2D_idxs)] = noisy     # the query image's keypoint array
+    out = ql.localize(all_kps, p2D_idxs, p3D_ids, cam, query_fmaps=[fmap])
+    assert len(out["inliers"]) == len(kps) and out["num_inliers"] == sum(out["inliers"])
     assert out["success"] and np.abs(seen["kps"] - noisy).max() > 1e-2      # QKA moved the keypoints before PnP
     assert np.abs(out["tvec"] - start["tvec"]).max() > 1e-6                  # QBA refined the PnP pose
     # reprojection of the mapped points with the refined pose stays within a pixel of the refined keypoints

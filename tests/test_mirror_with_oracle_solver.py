@@ -355,3 +355,47 @@ def test_keypoint_adjustment_on_a_lazily_filled_cache(oracle_engine, tmp_path):
     for name in names:
         assert np.array_equal(kp_a[name], kp_b[name])
     assert not any(m.is_loaded for m in lazy.fset(0)._maps.values())
+
+
+def test_query_localizer_reference_surface(oracle_engine):
+    """QueryLocalizer with the reference's constructor options and `localize` signature (localization/main.py:301-497):
+    references extracted at construction from a FeatureManager, the four target_reference kinds, unique inliers by minimal
+    reprojection error, inliers recomputed from the final pose."""
+    import copy
+    import test_gpu_localization as T
+    from pixsfm import localization as loc_pkg
+    from pixsfm.localization import main as M
+    from pixsfm.util import cameras
+    rec, fm, refs, qid, fmap, p2D_idxs, p3D_ids, kps = T._scene()
+    img = rec.images[qid]
+    cam = copy.deepcopy(rec.cameras[img.camera_id])
+    pose = {"success": True, "qvec": img.qvec.copy(), "tvec": img.tvec.copy(), "inliers": [True] * (len(kps) + 2)}
+    pnp = lambda p2, p3, c: dict(pose, qvec=pose["qvec"].copy(), tvec=pose["tvec"].copy())        # noqa: E731
+    ql = loc_pkg.QueryLocalizer(rec, {"max_tracks_per_problem": 10}, dense_features=fm, pose_estimator=pnp)
+    assert len(ql.references) == 1 and sorted(ql.references[0]) == sorted(refs)
+    for pid in list(refs)[:5]:                                  # the same references as extracted by hand
+        assert ql.references[0][pid].source == refs[pid].source
+        assert np.abs(ql.references[0][pid].descriptor - refs[pid].descriptor).max() < 1e-12
+    for kind, check in (("nearest", lambda r: isinstance(r, np.ndarray)), ("robust_mean", lambda r: isinstance(r, np.ndarray)),
+                        ("all_observations", lambda r: isinstance(r, list) and len(r) == 4),
+                        ("full", lambda r: hasattr(r, "descriptor"))):
+        q = loc_pkg.QueryLocalizer(rec, {"target_reference": kind}, references=[refs], pose_estimator=pnp)
+        got = q.get_query_references(p3D_ids, [fmap], kps, p2D_idxs)
+        assert len(got) == 1 and len(got[0]) == len(kps) and all(check(r) for r in got[0])
+    # two correspondences of ONE keypoint (and two of one 3D point): the one with the smaller reprojection error survives
+    all_kps = np.zeros((max(p2D_idxs) + 1, 2)); all_kps[list(p2D_idxs)] = kps
+    idxs = list(p2D_idxs) + [p2D_idxs[0], p2D_idxs[1]]
+    pids = list(p3D_ids) + [p3D_ids[5], p3D_ids[1]]
+    errors = M.compute_reprojection_errors(all_kps[idxs], [rec.points3D[p] for p in pids], img.qvec, img.tvec, cam)
+    proj = cameras.world_to_image(cam.model_id, cam.params, img.qvec, img.tvec, np.array([rec.points3D[p].xyz for p in pids]))
+    assert np.allclose(errors, np.linalg.norm(proj - all_kps[idxs], axis=1), atol=1e-12)
+    keep = M.find_unique_min_reproj_inliers(pids, img.qvec, img.tvec, cam, all_kps[idxs], rec, pre_inliers=[True] * len(idxs),
+                                            point2D_idxs=idxs)
+    assert keep[0] and not keep[-2]                              # keypoint p2D_idxs[0]: its true point beats point p3D_ids[5]
+    assert sum(keep[k] for k in (1, len(idxs) - 1)) == 1         # the duplicate of correspondence 1: exactly one is kept
+    out = ql.localize(all_kps, idxs, pids, cam, query_fmaps=[fmap])
+    assert out["success"] and len(out["inliers"]) == len(idxs) and out["num_inliers"] == sum(out["inliers"])
+    assert not out["inliers"][-2]                                # 12 px threshold on the final pose: the wrong pairing is out
+    assert loc_pkg.QueryLocalizer(rec, {}, references=[refs], pose_estimator=pnp).localize(all_kps, [], [], cam, query_fmaps=[fmap]) == {"success": False}
+    with pytest.raises(ValueError, match="image_path or query_fmaps"):
+        ql.localize(all_kps, idxs, pids, cam)
