@@ -181,3 +181,23 @@ def test_low_memory_preset_configures_the_extractor_cache(tmp_path, monkeypatch)
     assert all(isinstance(m, LazyFeatureMap) for m in maps0) and maps0[0].shape == (8, 8, 16)
     assert not any(m.is_loaded for m in maps0)                   # the views of the adjustment have let go of the patches
     assert ba_data["summary"][0].final_cost <= ba_data["summary"][0].initial_cost
+
+
+def test_extract_module_functions():
+    """pixsfm.extract: the reference's free functions (extract.py:22-222) over the extractor object"""
+    from pixsfm import extract
+    from recon_util import make_reconstruction
+    rec = make_reconstruction(n_cams=3, n_points=20, track_len=3, channels=8, seed=13)[0]
+    rng = np.random.default_rng(5)
+    maps = {im.name: [rng.normal(size=(8, 250, 250)).astype(np.float32)] for im in rec.images.values()}
+    ex = DenseFeatureExtractor(lambda name: maps[name], lambda name: (1000, 1000), {"patch_size": 8})
+    a = extract.features_from_reconstruction(ex, rec, "unused")
+    b = ex.features_from_reconstruction(rec, "unused")
+    for name in b.fset(0).keys():
+        assert a.fset(0).fmap(name).point2D_ids == b.fset(0).fmap(name).point2D_ids
+        assert np.array_equal(a.fset(0).fmap(name).patches, b.fset(0).fmap(name).patches)
+    kps = {"x": np.arange(12.0).reshape(6, 2)}
+    k, ids, n = extract.get_keypoints_and_ids("x", kps, {"x": [4, 1]})
+    assert n == 2 and ids == [4, 1] and np.array_equal(k, kps["x"][[4, 1]])
+    assert extract.get_keypoints_and_ids("x", None, None) == (None, None, 0)
+    assert extract.estimate_required_memory(ex, None, ["x"], kps, {"x": [4, 1]}, use_cache=True) == 0
