@@ -5,6 +5,6 @@ from .._pixsfm._features import (FeaturePatch, FeatureMap, FeatureSet, FeatureVi
 from .extractor import (DenseFeatureExtractor, dense_to_fmap, dense_to_fmap_on_device, patch_corners,  # noqa: F401
                         cut_patches)
 
-from . import store_features, store_references  # noqa: F401,E402  (features/__init__.py:2 of the reference)
+from . import extract_patches, store_features, store_references  # noqa: F401,E402  (features/__init__.py:2 of the reference)
 
 Map_IdReference = dict
