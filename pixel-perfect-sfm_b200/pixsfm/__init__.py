@@ -20,3 +20,23 @@ def _make_logger(name="pixsfm", level=_logging.INFO):
 
 
 logger = _make_logger()
+
+_SUBMODULES = ("base", "features", "bundle_adjustment", "keypoint_adjustment", "extract", "localization", "util", "residuals",
+               "configs", "refine_colmap", "refine_hloc")
+
+
+def __getattr__(name):
+    """`import pixsfm; pixsfm.features...` as with the reference, whose __init__ imports its subpackages (:19-22); here they
+    load on first use"""
+    if name in _SUBMODULES:
+        import importlib
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))
+
+
+def set_debug():
+    """reference __init__.py:28-30: DEBUG records from the "pixsfm" logger (the C++ side reports through status codes and
+    pxr_last_error, it has no log level)"""
+    logger.setLevel(_logging.DEBUG)
+    for handler in logger.handlers:
+        handler.setLevel(_logging.DEBUG)
